@@ -1,0 +1,191 @@
+"""Pins the CPU oracle (oracle/zkb_oracle.c + oracle/pyref.py) before anything trusts it.
+
+The reference holds no golden vectors for the MSM/NTT path: these are first-principles
+known-answer values plus cross-checks between two independent restatements (C limbs vs Python big-ints).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyref as R
+from util import FQ_LIMBS, int_to_limbs, ints_to_limbs, limbs_to_int, limbs_to_ints, random_field
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hotpath_kats.json")))
+
+
+def fr_mont(xs):
+    return ints_to_limbs([R.to_mont(x, R.FR) for x in xs])
+
+
+def fr_unmont(a):
+    return [R.from_mont(x, R.FR) for x in limbs_to_ints(a)]
+
+
+def aff_mont(P):
+    return np.array(R.g1_affine_encode(P), dtype=np.uint64)
+
+
+def test_constants_match_survey():
+    # SURVEY.md §8 [COMPUTED] constants
+    assert R.FR_ROOT_OF_UNITY == 0x03DDB9F5166D18B798865EA93DD31F743215CF6DD39329C8D34F1ED960C37C9C
+    assert R.FR_ROOT_OF_UNITY_INV == 0x048127174DAABC261BBE587180F34361B22625F59115ABA70ED3E50A414E6DBA
+    assert R.FR_ZETA == 0x30644E72E131A029048B6E193FD84104CC37A73FEC2BC5E9B8CA0B2D36636F23
+    assert R.FR_R == 0x0E0A77C19A07DF2F666EA36F7879462E36FC76959F60CD29AC96341C4FFFFFFB
+    assert R.FR_R2 == 0x0216D0B17F4E44A58C49833D53BB808553FE3AB1E35C59E31BB8E645AE216DA7
+    assert R.FQ_R == 0x0E0A77C19A07DF2F666EA36F7879462C0A78EB28F5C70B3DD35D438DC58F0D9D
+    assert R.FQ_R2 == 0x06D89F71CAB8351F47AB1EFF0A417FF6B5E71911D44501FBF32CFC5B538AFA89
+    assert R.FR_INV64 == 0xC2E1F593EFFFFFFF and R.FQ_INV64 == 0x87D20782E4866389
+    assert R.omega_for(13) == 0x10E3D295C1599FF535A1BB49F23D81AA03BD0ED25881F9ED12B179AF67F67AE1
+    assert R.omega_for(22) == 0x18C95F1AE6514E11A1B30FD7923947C5FFCEC5347F16E91B4DD654168326BEDE
+    assert R.omega_for(24) == 0x1951441010B2B95A6E47A6075066A50A036F5BA978C050F2821DF86636C0FACB
+    assert pow(R.FR_ZETA, 3, R.FR) == 1 and R.FR_ZETA != 1
+    assert pow(R.FR_ROOT_OF_UNITY, 1 << 28, R.FR) == 1 and pow(R.FR_ROOT_OF_UNITY, 1 << 27, R.FR) != 1
+
+
+def test_c_field_ops_match_bigint(oracle):
+    for field, m in (("fr", R.FR), ("fq", R.FQ)):
+        mod = FQ_LIMBS if field == "fq" else None
+        a = random_field(500, 1, *([mod] if mod is not None else []))
+        b = random_field(500, 2, *([mod] if mod is not None else []))
+        # edge rows
+        a[0] = 0; b[0] = 0
+        a[1] = int_to_limbs(m - 1); b[1] = int_to_limbs(m - 1)
+        a[2] = int_to_limbs(1); b[2] = int_to_limbs(m - 1)
+        ai, bi = limbs_to_ints(a), limbs_to_ints(b)
+        rinv = pow(R.R256, -1, m)
+        assert limbs_to_ints(oracle.vec_op(field, "mul", a, b)) == [x * y * rinv % m for x, y in zip(ai, bi)]
+        assert limbs_to_ints(oracle.vec_op(field, "add", a, b)) == [(x + y) % m for x, y in zip(ai, bi)]
+        assert limbs_to_ints(oracle.vec_op(field, "sub", a, b)) == [(x - y) % m for x, y in zip(ai, bi)]
+
+
+def test_c_omega_and_montgomery_layout(oracle):
+    # in-memory Montgomery limbs of the SURVEY KAT out[1]
+    for k in (3, 13, 22, 24):
+        assert limbs_to_int(oracle.fr_omega(k)) == R.to_mont(R.omega_for(k), R.FR)
+    g = oracle.g1_generator()
+    assert limbs_to_int(g[:4]) == R.FQ_R and limbs_to_int(g[4:]) == 2 * R.FQ_R % R.FQ
+
+
+@pytest.mark.parametrize("case", GOLD["best_fft"], ids=lambda c: f"k{c['k']}")
+def test_best_fft_golden(oracle, case):
+    a = [int(x, 16) for x in case["in"]]
+    want = [int(x, 16) for x in case["out"]]
+    w = int(case["omega"], 16)
+    # python twin
+    b = list(a)
+    R.best_fft(b, w, case["k"])
+    assert b == want
+    # C oracle
+    got = oracle.best_fft(fr_mont(a), fr_mont([w])[0], case["k"])
+    assert fr_unmont(got) == want
+
+
+def test_best_fft_survey_kat_memory_limbs(oracle):
+    a = fr_mont(range(1, 9))
+    out = oracle.best_fft(a, oracle.fr_omega(3), 3)
+    assert [int(x) for x in out[1]] == [0x1069F4287460CB5F, 0xEA22DD8C9B017FC5, 0xC9CDFB2B2395711E, 0x2758DB28A5C09FDD]
+    assert fr_unmont(out)[0] == 0x24 and fr_unmont(out)[4] == R.FR - 4
+    assert fr_unmont(out)[7] == 0x303D4CCDE3F282EB3E1FA8DA0EB98F60726A9D586FEE27AA5ECD945D75D0E863
+
+
+@pytest.mark.parametrize("case", GOLD["lagrange_to_coeff"], ids=lambda c: f"k{c['k']}")
+def test_lagrange_to_coeff_golden(oracle, case):
+    a = [int(x, 16) for x in case["in"]]
+    want = [int(x, 16) for x in case["out"]]
+    assert R.EvaluationDomain(4, case["k"]).lagrange_to_coeff(a) == want
+    assert fr_unmont(oracle.lagrange_to_coeff(fr_mont(a), case["k"])) == want
+    assert fr_unmont(oracle.coeff_to_lagrange(fr_mont(want), case["k"])) == a
+
+
+@pytest.mark.parametrize("case", GOLD["coeff_to_extended"], ids=lambda c: f"j{c['j']}k{c['k']}")
+def test_coeff_to_extended_golden(oracle, case):
+    a = [int(x, 16) for x in case["in"]]
+    want = [int(x, 16) for x in case["out"]]
+    d = R.EvaluationDomain(case["j"], case["k"])
+    assert d.extended_k == case["extended_k"]
+    assert d.coeff_to_extended(a) == want
+    got = oracle.coeff_to_extended(fr_mont(a), case["k"], d.extended_k)
+    assert fr_unmont(got) == want
+    back = fr_unmont(oracle.extended_to_coeff(got, case["k"], d.extended_k))
+    assert back[: len(a)] == a and all(x == 0 for x in back[len(a):])
+    assert d.extended_to_coeff(want) == (a + [0] * len(want))[: d.n * d.quotient_poly_degree]
+
+
+def test_coeff_to_extended_survey_kat():
+    e = R.EvaluationDomain(4, 2).coeff_to_extended([1, 2, 3, 4])
+    assert e[0] == 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90E0
+    assert e[1] == 0x02784A0A8A0E97B1E4BDF0FF35FF9CC7E84CE82C0568A0F5022C8379EABAD181
+    assert e[2] == 0x0F474B2DC63AC314F5DDFFAA966E250CBC434908CCF08F98880600F34B714E16
+
+
+def test_fft_c_vs_python_random_and_threads(oracle):
+    for k in (0, 1, 7, 10):
+        a = random_field(1 << k, 100 + k)
+        w = oracle.fr_omega(k)
+        ai = fr_unmont(a)
+        R.best_fft(ai, R.omega_for(k), k)
+        for threads in (1, 3):
+            assert fr_unmont(oracle.best_fft(a, w, k, threads)) == ai
+
+
+@pytest.mark.parametrize("case", GOLD["g1_mul"], ids=lambda c: c["s"][:12])
+def test_g1_mul_golden(oracle, case):
+    s = int(case["s"], 16)
+    want = tuple(int(x, 16) for x in case["out"]) if case["out"] else None
+    assert R.g1_mul(R.G1_GENERATOR, s) == want
+    got = oracle.g1_mul(oracle.g1_generator(), fr_mont([s])[0])
+    assert R.g1_affine_decode([int(x) for x in got]) == want
+    assert oracle.g1_is_on_curve(got)
+
+
+@pytest.mark.parametrize("case", GOLD["msm"], ids=lambda c: c["name"])
+def test_msm_golden(oracle, case):
+    scal = [int(x, 16) for x in case["scalars"]]
+    bases = [tuple(int(c, 16) for c in b) if b else None for b in case["bases"]]
+    want = tuple(int(x, 16) for x in case["out"])
+    assert R.best_multiexp(scal, bases, 3) == want
+    s = fr_mont(scal)
+    b = np.stack([aff_mont(P) for P in bases])
+    for threads in (1, 2, 8):
+        got = oracle.best_multiexp(s, b, threads)
+        assert R.g1_jacobian_decode([int(x) for x in got]) == want
+        assert limbs_to_int(got[8:12]) == R.FQ_R  # z normalised to Montgomery one
+    assert R.g1_jacobian_decode([int(x) for x in oracle.msm_naive(s, b)]) == want
+
+
+def test_msm_known_dlog_property(oracle):
+    """bases b_i*G  =>  MSM == (sum s_i b_i) * G  (the check used at full size on the GPU)."""
+    n = 300
+    s = random_field(n, 7)
+    b = random_field(n, 8)
+    bases = oracle.g1_fixed_base_mul(b)
+    assert all(oracle.g1_is_on_curve(p) for p in bases[:10])
+    got = oracle.g1_to_affine(oracle.best_multiexp(s, bases))
+    ip = oracle.fr_inner_product(s, b)  # Montgomery(sum s_i*b_i / R) -> need true product: use to_mont of one side
+    # inner product of Montgomery forms: mont_mul(sR, bR) = s*b*R  => sum is Montgomery form of sum s_i b_i
+    want = oracle.g1_mul(oracle.g1_generator(), ip)
+    assert (got == want).all()
+    # and against python
+    si, bi = fr_unmont(s), fr_unmont(b)
+    tot = sum(x * y for x, y in zip(si, bi)) % R.FR
+    assert R.g1_affine_decode([int(x) for x in got]) == R.g1_mul(R.G1_GENERATOR, tot)
+
+
+def test_msm_edge_cases(oracle):
+    g = oracle.g1_generator()
+    # empty
+    out = oracle.best_multiexp(np.zeros((0, 4), np.uint64), np.zeros((0, 8), np.uint64))
+    assert limbs_to_int(out[8:12]) == 0
+    # all zero scalars
+    out = oracle.best_multiexp(np.zeros((5, 4), np.uint64), np.tile(g, (5, 1)))
+    assert limbs_to_int(out[8:12]) == 0
+    # [r-1]G + [1]G = identity
+    s = fr_mont([R.FR - 1, 1])
+    out = oracle.best_multiexp(s, np.tile(g, (2, 1)))
+    assert limbs_to_int(out[8:12]) == 0
+    # all-equal scalars and bases
+    s = fr_mont([12345] * 64)
+    out = oracle.best_multiexp(s, np.tile(g, (64, 1)))
+    assert R.g1_jacobian_decode([int(x) for x in out]) == R.g1_mul(R.G1_GENERATOR, 12345 * 64)
