@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the zkb200 hot path (see DESIGN.md "Measurement").
+
+Step   : one 2^24-point BN254 G1 MSM (ParamsKZG::commit shape: uniform Fr scalars against an SRS resident in
+         HBM) per GPU.  At N GPUs the MSM is sharded by SRS point range, one 2^24-point shard per rank (weak
+         scaling; at N=4 this is the 2^26-point MSM of BASELINE.json's sweep), the 96-byte partial results are
+         folded on the host.
+value  : points/s, whole job, scalars already in HBM, timed with CUDA events on the launch stream.
+e2e    : the same through the host-buffer C ABI call (zkb_msm_g1_srs): pinned host scalars -> H2D -> kernels ->
+         window sums D2H -> host fold, wall clock (the host fold is part of the call).
+ntt    : secondary object: batched 2^22 Fr NTT (16 columns) elements/s and its HBM roofline.
+`--impl reference` times the CPU restatement of halo2's best_multiexp (oracle/, all host threads) on a bounded
+sample of the same workload; the reference itself is Rust with un-vendored dependencies and cannot be built
+in this image (DESIGN.md "Oracle").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LOG_N_MSM = int(os.environ.get("ZKB_BENCH_LOG_N", "24"))
+NTT_LOG_N = int(os.environ.get("ZKB_BENCH_NTT_LOG_N", "22"))
+NTT_COLS = int(os.environ.get("ZKB_BENCH_NTT_COLS", "16"))
+CPU_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_CPU_LOG_N", "20"))
+METRIC = "BN254 G1 MSM throughput (2^%d points per GPU, SRS resident)" % LOG_N_MSM
+
+
+def random_field(n, seed):
+    from util import random_field as rf
+
+    return rf(n, seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_msm(log_n: int, repeats: int = 1):
+    """Oracle restatement of best_multiexp on all host threads; returns (pts/s, cores, seconds)."""
+    from oracle import coracle
+
+    coracle.build()
+    n = 1 << log_n
+    s = random_field(n, 0x5EED0000 + log_n)
+    # bases: cheap synthetic curve points for the CPU arm — multiples of G by small random scalars (CPU fixed-base)
+    b = coracle.g1_fixed_base_mul(random_field(min(n, 4096), 7))
+    bases = np.ascontiguousarray(np.tile(b, (n // b.shape[0] + 1, 1))[:n])
+    cores = coracle.num_threads()
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        coracle.best_multiexp(s, bases, 0)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return n / best, cores, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ts = []
+    cores = 0
+    for i in range(args.warmup + args.steps):
+        v, cores, dt = cpu_baseline_msm(CPU_SAMPLE_LOG_N)
+        if i >= args.warmup:
+            ts.append(dt)
+    n = 1 << CPU_SAMPLE_LOG_N
+    value = n * len(ts) / sum(ts)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (254-bit Montgomery)",
+        "data": "synthetic",
+        "config": {"workload": "msm_g1_2^%d_uniform" % LOG_N_MSM, "sample": "2^%d points per step" % CPU_SAMPLE_LOG_N},
+        "cpu_baseline": {"value": value, "unit": "pts/s", "cores": cores, "kind": "port",
+                         "sample": "best_multiexp restatement (C, pthreads; not rayon) on 2^%d uniform points per step"
+                                   % CPU_SAMPLE_LOG_N},
+        "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zkb200")
+    ap.add_argument("--skip-ntt", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    zkb = importlib.import_module("zksnap-circuits-halo2_b200")
+    zkb.init(local_rank)
+    lib = zkb.lib()
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic inputs: this rank's point-range shard -------------------------------------------------------------
+    n = 1 << LOG_N_MSM
+    seed = 0x5EED0000 + LOG_N_MSM + 1000 * rank
+    scal_np = random_field(n, seed)
+    h_scal = torch.from_numpy(scal_np.view(np.int64)).pin_memory()
+    d_scal = h_scal.to(dev, non_blocking=False)
+    dlog = random_field(n, seed + 7)
+    bases = zkb.g1_fixed_base_mul(dlog)           # [b_i]G on the GPU, known discrete logs
+    params = zkb.ParamsKZG(LOG_N_MSM, bases)
+    del bases
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+    c_bits, n_win, chunk = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    lib.zkb_msm_get_params(n, ctypes.byref(c_bits), ctypes.byref(n_win), ctypes.byref(chunk))
+
+    def step_dev():
+        rc = lib.zkb_msm_g1_srs_dev(params.handle_g, 0, ctypes.c_void_p(d_scal.data_ptr()), n, outp, sptr)
+        if rc != 0:
+            raise RuntimeError(lib.zkb_last_error().decode())
+
+    def step_e2e():
+        rc = lib.zkb_msm_g1_srs(params.handle_g, ctypes.cast(h_scal.data_ptr(), ctypes.POINTER(ctypes.c_uint64)), n, outp)
+        if rc != 0:
+            raise RuntimeError(lib.zkb_last_error().decode())
+
+    def fold(result):
+        if world == 1:
+            return result
+        t = torch.from_numpy(result.view(np.int64).copy()).to(dev)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return zkb.g1_sum(np.stack([p.cpu().numpy().view(np.uint64) for p in parts]))
+
+    # ---- warm-up + correctness of the measured configuration (rank-local known-dlog check on the first step) ------------
+    for _ in range(args.warmup):
+        step_dev()
+    from oracle import coracle  # checker only, outside the timed region
+
+    ip = coracle.fr_inner_product(scal_np, dlog)
+    want = coracle.g1_mul(coracle.g1_generator(), ip)
+    parity = bool((out[:8] == want).all())
+
+    # ---- timed: device-resident ------------------------------------------------------------------------------------------
+    zkb.prof.enable(True)
+    zkb.prof.reset()
+    launches0 = zkb.launch_count()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+        total = fold(out)
+    e1.record(stream)
+    barrier()
+    clock_info = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = zkb.launch_count() - launches0
+    acc_ms, acc_calls = zkb.prof.get("msm_accumulate")
+    sort_ms, _ = zkb.prof.get("msm_sort")
+    dig_ms, _ = zkb.prof.get("msm_digits")
+    red_ms, _ = zkb.prof.get("msm_reduce")
+    zkb.prof.enable(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- timed: end to end through the host-buffer ABI ---------------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+        total = fold(out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n * args.steps / e2e_s
+
+    # ---- integer-pipe peak (measured here) and the roofline of the dominant kernel -----------------------------------------
+    peak = ctypes.c_double(0)
+    lib.zkb_measure_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    lib.zkb_measure_imad_peak(ctypes.byref(peak))
+    alg_mac = n * n_win.value * 10 * 128          # n*W mixed adds x 10 Fq mul x 128 32-bit MACs
+    acc_launch_ms = acc_ms / max(acc_calls, 1)
+    achieved = alg_mac / (acc_launch_ms * 1e-3) / 1e9 if acc_launch_ms else 0.0
+    roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel<level0> (+partial levels, bucket memset)",
+                "achieved": achieved, "peak": peak.value / 1e9, "unit": "GMAC/s (32x32+64 wide MACs)",
+                "frac": achieved / (peak.value / 1e9) if peak.value else None, "traffic": None,
+                "peak_source": "measured in this run: unrolled independent mad.wide.u32 chains (zkb_measure_imad_peak)",
+                "ms_per_launch": acc_launch_ms, "window_bits": c_bits.value, "windows": n_win.value,
+                "share_of_step": acc_launch_ms / ms_per_step if ms_per_step else None,
+                "other_ms": {"digits": dig_ms / max(acc_calls, 1), "sort": sort_ms / max(acc_calls, 1), "reduce": red_ms / max(acc_calls, 1)}}
+
+    # ---- secondary: batched NTT ----------------------------------------------------------------------------------------------
+    ntt_obj = None
+    if not args.skip_ntt:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, src = 6650.0, "fallback"
+        if os.path.exists(peaks_path):
+            hbm_peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+        N = 1 << NTT_LOG_N
+        cols = NTT_COLS
+        a_np = random_field(N * cols, 0xF0F0 + NTT_LOG_N + rank)
+        h_a = torch.from_numpy(a_np.view(np.int64)).pin_memory()
+        d_a = h_a.to(dev)
+        d_s = torch.empty_like(d_a)
+        w = zkb.omega(NTT_LOG_N)
+        wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+        def ntt_step():
+            rc = lib.zkb_ntt_fr_dev(ctypes.c_void_p(d_a.data_ptr()), ctypes.c_void_p(d_s.data_ptr()), cols, wp, NTT_LOG_N, sptr)
+            if rc != 0:
+                raise RuntimeError(lib.zkb_last_error().decode())
+
+        for _ in range(args.warmup):
+            ntt_step()
+        barrier()
+        launches1 = zkb.launch_count()
+        e0.record(stream)
+        for _ in range(args.steps):
+            ntt_step()
+        e1.record(stream)
+        barrier()
+        nms = e0.elapsed_time(e1) / args.steps
+        launches += zkb.launch_count() - launches1
+        alg_bytes = 64.0 * N * cols
+        gbs = alg_bytes / (nms * 1e-3) / 1e9
+        # e2e: host columns through zkb_ntt_fr_batch (H2D + kernels + D2H)
+        cols_np = [a_np[i * N:(i + 1) * N] for i in range(cols)]
+        ptrs = (ctypes.POINTER(ctypes.c_uint64) * cols)(*[ctypes.cast(h_a.data_ptr() + i * N * 32, ctypes.POINTER(ctypes.c_uint64)) for i in range(cols)])
+        lib.zkb_ntt_fr_batch(ptrs, cols, wp, NTT_LOG_N)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            lib.zkb_ntt_fr_batch(ptrs, cols, wp, NTT_LOG_N)
+        barrier()
+        ntt_e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
+        ntt_obj = {"workload": "best_fft 2^%d x %d columns (batched, in HBM)" % (NTT_LOG_N, cols),
+                   "value": world * N * cols / (nms * 1e-3), "unit": "elems/s", "ms_per_step": nms,
+                   "e2e": {"value": world * N * cols / ntt_e2e_s, "unit": "elems/s", "h2d_bytes_per_step": N * cols * 32,
+                           "d2h_bytes_per_step": N * cols * 32},
+                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                "traffic": None, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
+                                "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound, see DESIGN.md"}}
+        del cols_np
+
+    # ---- CPU baseline on this box (rank 0, N=1 only) ---------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        v, cores, dt = cpu_baseline_msm(CPU_SAMPLE_LOG_N)
+        cpu = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port",
+               "sample": "best_multiexp restatement (C, pthreads; not rayon) on 2^%d uniform points, %.1f s" % (CPU_SAMPLE_LOG_N, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
+            "config": {"workload": "msm_g1_2^%d_uniform_per_gpu" % LOG_N_MSM, "sharding": "srs_point_range_per_rank, host fold",
+                       "l2": "inputs_exceed_l2 (512 MiB scalars + 1 GiB bases per step)", "window_bits": c_bits.value,
+                       "chunk": chunk.value},
+            "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": n * 32 * world,
+                    "d2h_bytes_per_step": n_win.value * 128 * world, "timer": "wall clock around the C-ABI call (includes host fold)"},
+            "gpu_launches": int(launches), "parity_checked": parity, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clock_info, "ntt": ntt_obj,
+        }
+        print(json.dumps(line))
+    params.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if parity else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

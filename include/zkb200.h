@@ -1,0 +1,144 @@
+/*
+ * zkb200.h — C ABI of libzkb200.so: B200-native BN254 G1 MSM and Fr NTT behind halo2's call signatures.
+ *
+ * This is the drop-in boundary for the zksnap provers.  The reference
+ * (aerius-labs/zksnap-circuits-halo2) has no FFI layer of its own; it reaches the hot path only through
+ * halo2-axiom's keygen_vk / keygen_pk / create_proof
+ *   /root/reference/aggregator/src/wrapper.rs:106-109   (gen_pk -> keygen_vk, keygen_pk)
+ *   /root/reference/aggregator/src/wrapper.rs:129-137   (create_proof::<_, ProverGWC<_>, ...>)
+ *   /root/reference/voter/benches/voter_circuit.rs:60-62,80
+ *   /root/reference/aggregator/benches/state_transition_circuit.rs:64-66,84
+ *   /root/reference/aggregator/benches/wrapper_circuit.rs:107,140
+ * so each entry point below names the halo2-axiom / halo2curves function whose body it replaces (sources
+ * are un-vendored third-party crates; see INTEGRATION.md for the Rust shim that binds these symbols).
+ *
+ * Encoding (exactly what the Rust side holds in memory):
+ *   Fr / Fq     4 little-endian u64 limbs, Montgomery form (a * 2^256 mod m), canonical (< m)
+ *   G1Affine    8 u64: x, y; the identity is (0, 0)
+ *   G1          12 u64: x, y, z Jacobian (affine = (x/z^2, y/z^3)); identity has z = 0 and is returned as
+ *               (0, R, 0); every other result is returned normalised to z = R (Montgomery one), so the bytes
+ *               are deterministic and equal to `to_affine()` of the CPU result.
+ * Pointers need only 8-byte alignment.  The caller owns every buffer; the library keeps no reference past
+ * return except the device copy of SRS bases registered with zkb_srs_register.
+ *
+ * All functions return 0 on success or a negative ZKB_ERR_* code; zkb_last_error() gives the thread-local
+ * message.  There is no CPU fallback: without a usable CUDA device every compute call fails with
+ * ZKB_ERR_NO_DEVICE.  Entry points are thread-safe (serialised per process) and synchronous: host buffers are
+ * valid when the call returns.  The *_dev variants take device pointers and a CUDA stream and are
+ * asynchronous with respect to the host unless stated otherwise.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define ZKB_OK 0
+#define ZKB_ERR_ARG (-1)        /* bad argument (NULL, size mismatch, log_n out of range) */
+#define ZKB_ERR_CUDA (-2)       /* CUDA runtime error */
+#define ZKB_ERR_OOM (-3)        /* device or pinned-host allocation failed */
+#define ZKB_ERR_NO_DEVICE (-4)  /* no CUDA device / library not initialised */
+#define ZKB_ERR_HANDLE (-5)     /* unknown SRS handle */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+
+/* Bind this process to one GPU (one process per GPU; ndev must be 0 or 1).  devices == NULL or ndev == 0
+ * selects the current CUDA device.  Idempotent. */
+int zkb_init(const int* devices, int ndev);
+void zkb_shutdown(void);
+const char* zkb_last_error(void);
+/* Number of visible CUDA devices (0 if none) — never fails. */
+int zkb_device_count(void);
+const char* zkb_version(void);
+
+/* ---- MSM: halo2_proofs::arithmetic::best_multiexp / ParamsKZG::{commit, commit_lagrange} ------------------ */
+
+/* best_multiexp(coeffs, bases) -> G1.  scalars: n x 4, bases: n x 8, out: 12. */
+int zkb_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]);
+
+/* Keep an SRS (ParamsKZG.g or ParamsKZG.g_lagrange) resident in HBM; returns an opaque handle. */
+int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle);
+int zkb_srs_release(uint64_t handle);
+/* ParamsKZG::commit / commit_lagrange: best_multiexp(scalars, srs[..n]).  n <= registered length. */
+int zkb_msm_g1_srs(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_jac[12]);
+/* Same over the sub-range srs[offset .. offset+n) — the point-range shard of a multi-GPU MSM. */
+int zkb_msm_g1_srs_range(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]);
+/* ncols commitments against the same SRS (the prover's per-column commit loop).  out: ncols x 12. */
+int zkb_msm_g1_srs_batch(uint64_t handle, const uint64_t* const* scalars, size_t ncols, size_t n, uint64_t* out_jac);
+
+/* Host-side combination of partial results (multi-GPU point-range shards): out = sum of `count` Jacobian points. */
+int zkb_g1_sum(const uint64_t* points_jac, size_t count, uint64_t out_jac[12]);
+
+/* out[i] = [s_i] G as G1Affine (n x 8) — the fixed-base multiples ParamsKZG::setup computes for g[i] = [tau^i]G;
+ * also used to synthesise bases with known discrete logs. */
+int zkb_g1_fixed_base_mul(const uint64_t* scalars, size_t n, uint64_t* out_affine);
+
+/* ---- NTT: halo2_proofs::arithmetic::best_fft and EvaluationDomain::{lagrange_to_coeff, coeff_to_extended,
+ *      extended_to_coeff} ----------------------------------------------------------------------------------- */
+
+/* best_fft(a, omega, log_n): in place, natural order in and out, a has 2^log_n elements (1 <= log_n <= 28). */
+int zkb_ntt_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
+int zkb_ntt_fr_batch(uint64_t* const* cols, size_t ncols, const uint64_t omega[4], uint32_t log_n);
+
+/* EvaluationDomain::lagrange_to_coeff: best_fft(a, omega_inv(k), k) then * 2^-k.  In place, 2^k elements. */
+int zkb_lagrange_to_coeff(uint64_t* a, uint32_t k);
+int zkb_lagrange_to_coeff_batch(uint64_t* const* cols, size_t ncols, uint32_t k);
+/* EvaluationDomain::coeff_to_lagrange: best_fft(a, omega(k), k). */
+int zkb_coeff_to_lagrange(uint64_t* a, uint32_t k);
+
+/* EvaluationDomain::coeff_to_extended: in = 2^k coefficients, out = 2^extended_k evaluations on the coset
+ * zeta * <extended_omega>  (a_i *= zeta^(i mod 3), zero-extend, best_fft(extended_omega)). */
+int zkb_coeff_to_extended(const uint64_t* in, uint64_t* out, uint32_t k, uint32_t extended_k);
+int zkb_coeff_to_extended_batch(const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k,
+                                uint32_t extended_k);
+/* EvaluationDomain::extended_to_coeff: in place over 2^extended_k elements (inverse FFT, * 2^-extended_k,
+ * inverse coset shift).  The caller truncates to n * quotient_poly_degree like the Rust original. */
+int zkb_extended_to_coeff(uint64_t* a, uint32_t k, uint32_t extended_k);
+
+/* omega(k) = Fr::ROOT_OF_UNITY^(2^(28-k)) in Montgomery limbs (EvaluationDomain::new) */
+int zkb_fr_omega(uint32_t k, uint64_t out[4]);
+
+/* ---- device-resident variants (data already in HBM; `stream` is a cudaStream_t, NULL = default stream) ----- */
+
+/* d_scalars: n x 32 B on the device; result written to host out_jac (synchronises `stream`). */
+int zkb_msm_g1_srs_dev(uint64_t handle, size_t offset, const void* d_scalars, size_t n, uint64_t out_jac[12], void* stream);
+/* ncols NTTs of 2^log_n elements, column c at d_data + c * 2^log_n * 32; result overwrites d_data
+ * (d_scratch must hold the same number of bytes).  Asynchronous on `stream`. */
+int zkb_ntt_fr_dev(void* d_data, void* d_scratch, size_t ncols, const uint64_t omega[4], uint32_t log_n, void* stream);
+/* d_in: ncols x 2^k, d_out: ncols x 2^extended_k, d_scratch: as d_out.  Asynchronous on `stream`. */
+int zkb_coeff_to_extended_dev(const void* d_in, void* d_out, void* d_scratch, size_t ncols, uint32_t k,
+                              uint32_t extended_k, void* stream);
+int zkb_extended_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, uint32_t extended_k, void* stream);
+int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, void* stream);
+
+/* ---- tuning and measurement -------------------------------------------------------------------------------- */
+
+/* MSM window bits / level-0 chunk length override (0 = automatic). */
+int zkb_msm_set_params(uint32_t window_bits, uint32_t chunk);
+int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, uint32_t* chunk);
+
+/* Per-kernel CUDA-event timers.  Names: "msm_digits", "msm_sort", "msm_accumulate", "msm_reduce",
+ * "ntt_pass".  zkb_prof_get returns the summed milliseconds and launch count since the last reset. */
+int zkb_prof_enable(int on);
+int zkb_prof_reset(void);
+int zkb_prof_get(const char* name, double* total_ms, uint64_t* launches);
+/* Measured integer-pipe peak of this GPU: independent unrolled mad.wide.u32 (32x32+64) chains, MACs per second —
+ * the denominator of the MSM roofline. */
+int zkb_measure_imad_peak(double* wide_macs_per_s);
+/* Kernels launched by this library since load (the bench's gpu_launches claim). */
+uint64_t zkb_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

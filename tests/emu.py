@@ -1,0 +1,70 @@
+"""ctypes binding of the CPU emulator of the device code (test infrastructure, see csrc/hostemu.cu)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "zksnap-circuits-halo2_b200")
+LIB = os.path.join(PKG, "libzkb200_hostemu.so")
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC",
+                               "-shared", "-o", LIB, os.path.join(PKG, "csrc", "hostemu.cu")])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_u64p) if a is not None else None
+
+
+def vec_op(field, op, a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    o = np.zeros_like(a)
+    lib().zkb_emu_vec_op(ctypes.c_int(0 if field == "fr" else 1), ctypes.c_int({"mul": 0, "add": 1, "sub": 2}[op]),
+                         _p(a), _p(b), _p(o), ctypes.c_size_t(a.shape[0]))
+    return o
+
+
+def ntt(a, log_n, omega, in_scale3=None, out_scale3=None, cols=1):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(cols, -1, 4)
+    in_len = a.shape[1]
+    out = np.zeros((cols, 1 << log_n, 4), dtype=np.uint64)
+    ins = np.ascontiguousarray(in_scale3, dtype=np.uint64) if in_scale3 is not None else None
+    outs = np.ascontiguousarray(out_scale3, dtype=np.uint64) if out_scale3 is not None else None
+    rc = lib().zkb_emu_ntt(_p(a), ctypes.c_uint64(in_len), _p(out), ctypes.c_uint32(log_n),
+                           _p(np.ascontiguousarray(omega, dtype=np.uint64)), _p(ins), _p(outs), ctypes.c_uint32(cols))
+    assert rc == 0
+    return out if cols > 1 else out[0]
+
+
+def msm(scalars, bases, c=0, chunk=0):
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(12, dtype=np.uint64)
+    rc = lib().zkb_emu_msm(_p(s), _p(b), ctypes.c_uint64(s.shape[0]), ctypes.c_uint32(c), ctypes.c_uint32(chunk), _p(out))
+    assert rc == 0
+    return out
+
+
+def fixed_base_mul(scalars):
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((s.shape[0], 8), dtype=np.uint64)
+    lib().zkb_emu_fixed_base_mul(_p(s), ctypes.c_uint64(s.shape[0]), _p(out))
+    return out

@@ -1,0 +1,147 @@
+"""CPU emulation of the device code (csrc/hostemu.cu runs the kernels' per-thread functions) vs the oracle.
+
+This is how limb arithmetic, NTT index maths and MSM chunk/partial logic are checked where no GPU exists; the
+`-m gpu` tests repeat the comparisons on the real kernels through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import emu
+from oracle import pyref as R
+from util import FQ_LIMBS, FR_LIMBS, int_to_limbs, ints_to_limbs, limbs_to_int, random_field
+
+
+def mont(xs):
+    return ints_to_limbs([R.to_mont(x, R.FR) for x in xs])
+
+
+@pytest.mark.parametrize("field,mod", [("fr", FR_LIMBS), ("fq", FQ_LIMBS)])
+def test_field_ops(oracle, field, mod):
+    a = random_field(5000, 1, mod)
+    b = random_field(5000, 2, mod)
+    m = limbs_to_int(mod)
+    a[0] = 0; b[1] = 0
+    a[2] = int_to_limbs(m - 1); b[2] = a[2]
+    a[3] = int_to_limbs(1); b[3] = int_to_limbs(m - 1)
+    a[4] = int_to_limbs(m - 1); b[4] = int_to_limbs(1)
+    for op in ("mul", "add", "sub"):
+        assert (emu.vec_op(field, op, a, b) == oracle.vec_op(field, op, a, b)).all(), (field, op)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15])
+def test_ntt_matches_best_fft(oracle, k):
+    a = random_field(1 << k, 10 + k)
+    w = oracle.fr_omega(k)
+    assert (emu.ntt(a, k, w) == oracle.best_fft(a, w, k)).all()
+
+
+def test_ntt_three_passes(oracle):
+    k = 19
+    a = random_field(1 << k, 19)
+    w = oracle.fr_omega(k)
+    assert (emu.ntt(a, k, w) == oracle.best_fft(a, w, k)).all()
+
+
+def test_ntt_inverse_omega_and_delta(oracle):
+    k = 11
+    w = oracle.fr_omega(k)
+    wi = oracle.fr_inv(w)
+    a = random_field(1 << k, 3)
+    assert (emu.ntt(a, k, wi) == oracle.best_fft(a, wi, k)).all()
+    delta = np.zeros((1 << k, 4), dtype=np.uint64)
+    delta[0] = mont([1])[0]
+    assert (emu.ntt(delta, k, w) == np.tile(mont([1])[0], (1 << k, 1))).all()
+
+
+@pytest.mark.parametrize("k,ek", [(3, 5), (5, 7), (9, 11), (10, 12), (12, 13), (12, 12)])
+def test_coset_fusions(oracle, k, ek):
+    z = R.FR_ZETA
+    zeta3 = mont([1, z, z * z % R.FR])
+    a = random_field(1 << k, 50 + k)
+    ext = emu.ntt(a, ek, oracle.fr_omega(ek), in_scale3=zeta3)
+    assert (ext == oracle.coeff_to_extended(a, k, ek)).all()
+    ninv = pow(1 << ek, -1, R.FR)
+    wi = mont([pow(R.omega_for(ek), -1, R.FR)])[0]
+    outs = mont([ninv, ninv * z * z % R.FR, ninv * z % R.FR])
+    back = emu.ntt(ext, ek, wi, out_scale3=outs)
+    assert (back == oracle.extended_to_coeff(ext, k, ek)).all()
+    assert (back[: 1 << k] == a).all() and not back[1 << k:].any()
+
+
+def test_ntt_batched_columns(oracle):
+    k, cols = 12, 3
+    a = random_field(cols << k, 77).reshape(cols, -1, 4)
+    w = oracle.fr_omega(k)
+    got = emu.ntt(a, k, w, cols=cols)
+    for i in range(cols):
+        assert (got[i] == oracle.best_fft(a[i], w, k)).all()
+
+
+def _bases(oracle, n, seed):
+    return oracle.g1_fixed_base_mul(random_field(n, seed))
+
+
+def test_fixed_base_mul(oracle):
+    s = random_field(6, 3)
+    s[0] = 0
+    s[1] = mont([1])[0]
+    s[2] = mont([R.FR - 1])[0]
+    assert (emu.fixed_base_mul(s) == oracle.g1_fixed_base_mul(s)).all()
+
+
+@pytest.mark.parametrize("n,c,chunk", [(1, 0, 0), (2, 0, 0), (3, 0, 0), (17, 0, 0), (64, 0, 0), (300, 0, 0),
+                                       (1000, 4, 8), (1000, 7, 3), (1000, 13, 128), (2000, 0, 0)])
+def test_msm_matches_best_multiexp(oracle, n, c, chunk):
+    s = random_field(n, n + c)
+    b = _bases(oracle, n, 1000 + n)
+    assert (emu.msm(s, b, c, chunk) == oracle.best_multiexp(s, b)).all()
+
+
+def test_msm_edge_cases(oracle):
+    n = 300
+    b = _bases(oracle, n, 5)
+    # all-equal scalars: every level-0 chunk is a single run of one bucket per window
+    s = random_field(n, 6)
+    s[:] = s[0]
+    assert (emu.msm(s, b, 5, 4) == oracle.best_multiexp(s, b)).all()
+    # all-equal scalars and bases: exercises the doubling branch of the mixed add
+    b2 = np.tile(b[0], (n, 1))
+    assert (emu.msm(s, b2, 6, 5) == oracle.best_multiexp(s, b2)).all()
+    # zeros, identity base, r-1
+    s = random_field(n, 7)
+    s[::2] = 0
+    s[7] = mont([R.FR - 1])[0]
+    b3 = b.copy()
+    b3[5] = 0
+    assert (emu.msm(s, b3, 8, 16) == oracle.best_multiexp(s, b3)).all()
+    # cancelling pair -> identity partial sums
+    s = random_field(64, 8)
+    b4 = b[:64].copy()
+    y = limbs_to_int(b4[0][4:])
+    b4[1][:4] = b4[0][:4]
+    b4[1][4:] = int_to_limbs(R.FQ - y)
+    s[1] = s[0]
+    assert (emu.msm(s, b4, 4, 2) == oracle.best_multiexp(s, b4)).all()
+    # everything cancels: result is the identity, returned as (0, R, 0)
+    s2 = np.stack([s[0], s[0]])
+    out = emu.msm(s2, b4[:2], 4, 2)
+    assert not out[:4].any() and not out[8:].any() and limbs_to_int(out[4:8]) == R.FQ_R
+    # all-zero scalars
+    out = emu.msm(np.zeros((10, 4), np.uint64), b[:10])
+    assert not out[8:].any()
+
+
+def test_msm_witness_like_distribution(oracle):
+    """50% zero, 25% < 2^16, 20% < 2^88, 5% uniform (SURVEY.md §8d distribution W)."""
+    n = 1500
+    rng = np.random.default_rng(9)
+    vals = []
+    for i in range(n):
+        u = rng.random()
+        if u < 0.5: vals.append(0)
+        elif u < 0.75: vals.append(int(rng.integers(0, 1 << 16)))
+        elif u < 0.95: vals.append(int.from_bytes(rng.bytes(11), "little"))
+        else: vals.append(int.from_bytes(rng.bytes(31), "little") % R.FR)
+    s = mont(vals)
+    b = _bases(oracle, n, 11)
+    assert (emu.msm(s, b) == oracle.best_multiexp(s, b)).all()

@@ -1,0 +1,87 @@
+"""ctypes loader of libzkb200.so — binds exactly the symbols declared in include/zkb200.h.
+
+There is no fallback: if the shared library is missing or no CUDA device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "zkb200.h")
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u64pp = ctypes.POINTER(u64p)
+
+_lib = None
+
+
+class ZkbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libzkb200 error {code}: {msg}")
+        self.code = code
+
+
+def header_symbols() -> list[str]:
+    """Every function name declared in include/zkb200.h."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkb_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZkbError(-4, f"{LIB_PATH} not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(libzkb200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.zkb_last_error.restype = ctypes.c_char_p
+    lib.zkb_version.restype = ctypes.c_char_p
+    lib.zkb_launch_count.restype = ctypes.c_uint64
+    sz, u32, u64, vp, ci = ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int
+    sigs = {
+        "zkb_init": [ctypes.POINTER(ci), ci],
+        "zkb_msm_g1": [u64p, u64p, sz, u64p],
+        "zkb_srs_register": [u64p, sz, u64p],
+        "zkb_srs_release": [u64],
+        "zkb_msm_g1_srs": [u64, u64p, sz, u64p],
+        "zkb_msm_g1_srs_range": [u64, sz, u64p, sz, u64p],
+        "zkb_msm_g1_srs_batch": [u64, u64pp, sz, sz, u64p],
+        "zkb_g1_sum": [u64p, sz, u64p],
+        "zkb_g1_fixed_base_mul": [u64p, sz, u64p],
+        "zkb_ntt_fr": [u64p, u64p, u32],
+        "zkb_ntt_fr_batch": [u64pp, sz, u64p, u32],
+        "zkb_lagrange_to_coeff": [u64p, u32],
+        "zkb_lagrange_to_coeff_batch": [u64pp, sz, u32],
+        "zkb_coeff_to_lagrange": [u64p, u32],
+        "zkb_coeff_to_extended": [u64p, u64p, u32, u32],
+        "zkb_coeff_to_extended_batch": [u64pp, u64pp, sz, u32, u32],
+        "zkb_extended_to_coeff": [u64p, u32, u32],
+        "zkb_fr_omega": [u32, u64p],
+        "zkb_msm_g1_srs_dev": [u64, sz, vp, sz, u64p, vp],
+        "zkb_ntt_fr_dev": [vp, vp, sz, u64p, u32, vp],
+        "zkb_coeff_to_extended_dev": [vp, vp, vp, sz, u32, u32, vp],
+        "zkb_extended_to_coeff_dev": [vp, vp, sz, u32, u32, vp],
+        "zkb_lagrange_to_coeff_dev": [vp, vp, sz, u32, vp],
+        "zkb_msm_set_params": [u32, u32],
+        "zkb_msm_get_params": [sz, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)],
+        "zkb_prof_enable": [ci],
+        "zkb_prof_reset": [],
+        "zkb_measure_imad_peak": [ctypes.POINTER(ctypes.c_double)],
+        "zkb_prof_get": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ci
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise ZkbError(rc, load().zkb_last_error().decode(errors="replace"))

@@ -1,0 +1,547 @@
+// api.cu — the C ABI of libzkb200.so (include/zkb200.h): context, SRS registry, host-buffer and device-buffer
+// entry points.  No CPU fallback lives here: every compute call requires an initialised CUDA device.
+#include <cstring>
+
+#include "msm_host.hpp"
+#include "ntt_host.hpp"
+
+namespace zkb {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+Ctx& ctx() {
+    static Ctx c;
+    return c;
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return ZKB_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + (bytes >> 3);  // slack so slowly growing sizes do not reallocate every call
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return ZKB_ERR_OOM;
+    }
+    cap = want;
+    return ZKB_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+int require_init() {
+    Ctx& c = ctx();
+    if (c.inited) {
+        cudaSetDevice(c.device);
+        return ZKB_OK;
+    }
+    return zkb_init(nullptr, 0);
+}
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : c(ctx()), s(stream) {
+    if (!c.prof_on) return;
+    t = &c.timers[name];
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!c.event_pool.empty()) { e = c.event_pool.back(); c.event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    start = get();
+    stop = get();
+    cudaEventRecord(start, s);
+}
+ProfScope::~ProfScope() {
+    if (!t) return;
+    cudaEventRecord(stop, s);
+    t->pending.emplace_back(start, stop);
+    t->launches++;
+}
+
+// ---- host-side field constants (EvaluationDomain::new) ---------------------------------------------------------------
+static Fr fr_from_limbs64(const uint64_t* p) {
+    Fr r;
+    for (int i = 0; i < 4; ++i) { r.l[2 * i] = (uint32_t)p[i]; r.l[2 * i + 1] = (uint32_t)(p[i] >> 32); }
+    return r;
+}
+static void fr_to_limbs64(const Fr& v, uint64_t* p) {
+    for (int i = 0; i < 4; ++i) p[i] = (uint64_t)v.l[2 * i] | ((uint64_t)v.l[2 * i + 1] << 32);
+}
+static Fr fr_root_of_unity() {  // Fr::ROOT_OF_UNITY = 7^((r-1)/2^28), Montgomery form
+    const uint32_t w[8] = {0xb639feb8u, 0x9632c7c5u, 0x0d0ff299u, 0x985ce340u, 0x01b0ecd8u, 0xb2dd8800u, 0x6d98ce29u, 0x1d69070du};
+    return fr_from_words(w);
+}
+static Fr fr_zeta() {  // Fr::ZETA, Montgomery form
+    const uint32_t w[8] = {0x55fcd653u, 0x0363f299u, 0x5fc1e200u, 0x73e7950bu, 0x576d9d24u, 0xc5fce83eu, 0xa1c3a4d4u, 0x059c805du};
+    return fr_from_words(w);
+}
+static Fr fr_inv_host(const Fr& a) {  // a^(r-2)
+    Fr acc = Fr::one();
+    for (int i = 255; i >= 0; --i) {
+        acc = fp_sqr(acc);
+        uint32_t limb = FrParams::M(i >> 5);
+        if (i < 32) limb -= 2;  // r - 2: low limb 0xf0000001 - 2 borrows nothing
+        if ((limb >> (i & 31)) & 1) acc = fp_mul(acc, a);
+    }
+    return acc;
+}
+static Fr fr_omega_host(uint32_t k) {
+    Fr w = fr_root_of_unity();
+    for (uint32_t i = k; i < 28; ++i) w = fp_sqr(w);
+    return w;
+}
+static Fr fr_pow2_inv_host(uint32_t k) {  // (2^k)^-1
+    Fr two = fp_dbl(Fr::one()), v = Fr::one();
+    for (uint32_t i = 0; i < k; ++i) v = fp_mul(v, two);
+    return fr_inv_host(v);
+}
+
+// ---- SRS registry ---------------------------------------------------------------------------------------------------------
+struct Srs {
+    DevBuf bases;
+    size_t n = 0;
+};
+static std::map<uint64_t, Srs*>& srs_map() {
+    static std::map<uint64_t, Srs*> m;
+    return m;
+}
+static uint64_t g_next_handle = 1;
+
+struct HostIo {  // device staging for the host-buffer entry points
+    DevBuf scalars, bases, x, y, in;
+};
+static HostIo& hostio() {
+    static HostIo h;
+    return h;
+}
+
+static int check_ptr(const void* p, const char* what) {
+    if (!p) { set_error("%s is NULL", what); return ZKB_ERR_ARG; }
+    return ZKB_OK;
+}
+
+enum DomainOp { OP_FFT, OP_L2C, OP_C2L, OP_C2E, OP_E2C };
+
+// One NTT-family operation over `ncols` columns resident on the device.
+//   d_in: columns of in_len elements; result (N elements per column) ends in d_a; d_b is scratch of the same size.
+//   For OP_C2E d_in is separate from d_a; otherwise d_in == d_a.
+static int domain_op_dev(DomainOp op, const uint4* d_in, uint4* d_a, uint4* d_b, size_t ncols, uint32_t k, uint32_t ek,
+                         const uint64_t* omega_user, cudaStream_t s) {
+    uint32_t log_n = (op == OP_C2E || op == OP_E2C) ? ek : k;
+    if (log_n < 1 || log_n > 28 || k > log_n) { set_error("bad domain sizes k=%u extended_k=%u", k, ek); return ZKB_ERR_ARG; }
+    uint64_t om[4];
+    Fr scale[3];
+    const Fr* in_scale = nullptr;
+    const Fr* out_scale = nullptr;
+    switch (op) {
+        case OP_FFT: memcpy(om, omega_user, 32); break;
+        case OP_C2L: fr_to_limbs64(fr_omega_host(k), om); break;
+        case OP_L2C: {
+            fr_to_limbs64(fr_inv_host(fr_omega_host(k)), om);
+            scale[0] = scale[1] = scale[2] = fr_pow2_inv_host(k);
+            out_scale = scale;
+            break;
+        }
+        case OP_C2E: {
+            fr_to_limbs64(fr_omega_host(ek), om);
+            scale[0] = Fr::one(); scale[1] = fr_zeta(); scale[2] = fp_sqr(scale[1]);
+            in_scale = scale;
+            break;
+        }
+        case OP_E2C: {
+            fr_to_limbs64(fr_inv_host(fr_omega_host(ek)), om);
+            Fr ninv = fr_pow2_inv_host(ek), z = fr_zeta(), z2 = fp_sqr(z);
+            scale[0] = ninv; scale[1] = fp_mul(ninv, z2); scale[2] = fp_mul(ninv, z);
+            out_scale = scale;
+            break;
+        }
+    }
+    NttPlan* plan = nullptr;
+    ZKB_TRY(ntt_get_plan(log_n, om, s, &plan));
+    const uint64_t N = 1ull << log_n;
+    NttIo io;
+    io.in = d_in;
+    io.in_len = op == OP_C2E ? (1ull << k) : N;
+    io.in_col_stride = io.in_len;
+    io.cols = ncols;
+    io.in_scale = in_scale;
+    io.out_scale = out_scale;
+    if (plan->geom.npass == 1) {
+        if (op == OP_C2E) { io.work = d_b; io.out = d_a; return ntt_run(*plan, io, s); }
+        io.work = d_a; io.out = d_b;
+        ZKB_TRY(ntt_run(*plan, io, s));
+        ZKB_CUDA_TRY(cudaMemcpyAsync(d_a, d_b, ncols * N * 32, cudaMemcpyDeviceToDevice, s));
+        return ZKB_OK;
+    }
+    io.work = d_b;  // first pass d_in -> d_b, inner passes in place in d_b, last pass d_b -> d_a
+    io.out = d_a;
+    return ntt_run(*plan, io, s);
+}
+
+// host-buffer flavour: columns are separate host arrays
+static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k, uint32_t ek,
+                          const uint64_t* omega_user) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(in, "input column array"));
+    ZKB_TRY(check_ptr(out, "output column array"));
+    uint32_t log_n = (op == OP_C2E || op == OP_E2C) ? ek : k;
+    if (log_n < 1 || log_n > 28 || k > log_n) { set_error("bad domain sizes k=%u extended_k=%u", k, ek); return ZKB_ERR_ARG; }
+    for (size_t cidx = 0; cidx < ncols; ++cidx) {
+        ZKB_TRY(check_ptr(in[cidx], "input column"));
+        ZKB_TRY(check_ptr(out[cidx], "output column"));
+    }
+    Ctx& c = ctx();
+    HostIo& h = hostio();
+    const uint64_t N = 1ull << log_n, in_len = op == OP_C2E ? (1ull << k) : N;
+    // bound staging to ~2 GiB per buffer
+    size_t per = (size_t)((2ull << 30) / (N * 32));
+    if (per < 1) per = 1;
+    if (per > 4096) per = 4096;
+    for (size_t c0 = 0; c0 < ncols; c0 += per) {
+        size_t nc = ncols - c0 < per ? ncols - c0 : per;
+        ZKB_TRY(h.x.reserve(nc * N * 32));
+        ZKB_TRY(h.y.reserve(nc * N * 32));
+        uint4* d_in = h.x.as<uint4>();
+        if (op == OP_C2E) {
+            ZKB_TRY(h.in.reserve(nc * in_len * 32));
+            d_in = h.in.as<uint4>();
+        }
+        for (size_t i = 0; i < nc; ++i)
+            ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(d_in) + i * in_len * 32, in[c0 + i], in_len * 32,
+                                         cudaMemcpyHostToDevice, c.stream));
+        ZKB_TRY(domain_op_dev(op, d_in, h.x.as<uint4>(), h.y.as<uint4>(), nc, k, ek, omega_user, c.stream));
+        for (size_t i = 0; i < nc; ++i)
+            ZKB_CUDA_TRY(cudaMemcpyAsync(out[c0 + i], reinterpret_cast<char*>(h.x.p) + i * N * 32, N * 32,
+                                         cudaMemcpyDeviceToHost, c.stream));
+        ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    }
+    return ZKB_OK;
+}
+
+static int msm_with_bases(const uint4* d_bases, const uint64_t* scalars, size_t n, uint64_t out[12]) {
+    Ctx& c = ctx();
+    HostIo& h = hostio();
+    if (n == 0) { msm_identity_out(out); return ZKB_OK; }
+    ZKB_TRY(check_ptr(scalars, "scalars"));
+    ZKB_TRY(h.scalars.reserve(n * 32));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    return msm_run(h.scalars.as<uint4>(), d_bases, n, c.stream, out);
+}
+
+static int find_srs(uint64_t handle, Srs** out) {
+    auto it = srs_map().find(handle);
+    if (it == srs_map().end()) { set_error("unknown SRS handle %llu", (unsigned long long)handle); return ZKB_ERR_HANDLE; }
+    *out = it->second;
+    return ZKB_OK;
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+int zkb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* zkb_version(void) { return "zkb200 0.1 (sm_100a)"; }
+const char* zkb_last_error(void) { return g_error.c_str(); }
+
+int zkb_init(const int* devices, int ndev) {
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> lock(c.mu);
+    if (ndev < 0 || ndev > 1) { set_error("one process per GPU: ndev must be 0 or 1 (got %d)", ndev); return ZKB_ERR_ARG; }
+    int count = zkb_device_count();
+    if (count == 0) { set_error("no CUDA device visible; libzkb200 has no CPU fallback"); return ZKB_ERR_NO_DEVICE; }
+    int dev = 0;
+    if (devices && ndev == 1) dev = devices[0];
+    else if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    if (dev < 0 || dev >= count) { set_error("device %d out of range (count %d)", dev, count); return ZKB_ERR_ARG; }
+    if (c.inited) {
+        if (dev != c.device && devices) { set_error("already bound to device %d", c.device); return ZKB_ERR_ARG; }
+        return ZKB_OK;
+    }
+    ZKB_CUDA_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    ZKB_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor); return ZKB_ERR_NO_DEVICE; }
+    ZKB_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.device = dev;
+    c.sm_count = prop.multiProcessorCount;
+    c.inited = true;
+    return ZKB_OK;
+}
+
+void zkb_shutdown(void) {
+    Ctx& c = ctx();
+    std::lock_guard<std::recursive_mutex> lock(c.mu);
+    if (!c.inited) return;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : srs_map()) { kv.second->bases.release(); delete kv.second; }
+    srs_map().clear();
+    ntt_clear_plans();
+    msm_release_workspace();
+    HostIo& h = hostio();
+    h.scalars.release(); h.bases.release(); h.x.release(); h.y.release(); h.in.release();
+    for (auto& kv : c.timers)
+        for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    c.timers.clear();
+    for (auto e : c.event_pool) cudaEventDestroy(e);
+    c.event_pool.clear();
+    cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+    c.inited = false;
+}
+
+// ---- MSM ---------------------------------------------------------------------------------------------------------------------
+int zkb_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(out_jac, "out_jac"));
+    if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
+    ZKB_TRY(check_ptr(bases, "bases"));
+    HostIo& h = hostio();
+    ZKB_TRY(h.bases.reserve(n * 64));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, bases, n * 64, cudaMemcpyHostToDevice, ctx().stream));
+    return msm_with_bases(h.bases.as<uint4>(), scalars, n, out_jac);
+}
+
+int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(handle, "handle"));
+    if (n) ZKB_TRY(check_ptr(bases, "bases"));
+    Srs* s = new Srs();
+    s->n = n;
+    int rc = s->bases.reserve(n ? n * 64 : 64);
+    if (rc != ZKB_OK) { delete s; return rc; }
+    if (n) {
+        cudaError_t e = cudaMemcpy(s->bases.p, bases, n * 64, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("SRS upload failed: %s", cudaGetErrorString(e)); s->bases.release(); delete s; return ZKB_ERR_CUDA; }
+    }
+    *handle = g_next_handle++;
+    srs_map()[*handle] = s;
+    return ZKB_OK;
+}
+
+int zkb_srs_release(uint64_t handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    cudaSetDevice(ctx().device);
+    cudaDeviceSynchronize();
+    s->bases.release();
+    delete s;
+    srs_map().erase(handle);
+    return ZKB_OK;
+}
+
+int zkb_msm_g1_srs_range(uint64_t handle, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(out_jac, "out_jac"));
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    if (offset > s->n || n > s->n - offset) {
+        set_error("MSM range [%zu, %zu) exceeds the registered SRS length %zu", offset, offset + n, s->n);
+        return ZKB_ERR_ARG;
+    }
+    return msm_with_bases(s->bases.as<uint4>() + 4 * offset, scalars, n, out_jac);
+}
+
+int zkb_msm_g1_srs(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
+    return zkb_msm_g1_srs_range(handle, 0, scalars, n, out_jac);
+}
+
+int zkb_msm_g1_srs_batch(uint64_t handle, const uint64_t* const* scalars, size_t ncols, size_t n, uint64_t* out_jac) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (ncols) { ZKB_TRY(check_ptr(scalars, "scalars")); ZKB_TRY(check_ptr(out_jac, "out_jac")); }
+    for (size_t i = 0; i < ncols; ++i) ZKB_TRY(zkb_msm_g1_srs_range(handle, 0, scalars[i], n, out_jac + 12 * i));
+    return ZKB_OK;
+}
+
+int zkb_msm_g1_srs_dev(uint64_t handle, size_t offset, const void* d_scalars, size_t n, uint64_t out_jac[12], void* stream) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(out_jac, "out_jac"));
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    if (offset > s->n || n > s->n - offset) { set_error("MSM range exceeds the registered SRS length %zu", s->n); return ZKB_ERR_ARG; }
+    if (n) ZKB_TRY(check_ptr(d_scalars, "d_scalars"));
+    return msm_run(reinterpret_cast<const uint4*>(d_scalars), s->bases.as<uint4>() + 4 * offset, n, (cudaStream_t)stream, out_jac);
+}
+
+int zkb_g1_sum(const uint64_t* points_jac, size_t count, uint64_t out_jac[12]) {
+    if (count) ZKB_TRY(check_ptr(points_jac, "points_jac"));
+    ZKB_TRY(check_ptr(out_jac, "out_jac"));
+    return g1_sum_host(points_jac, count, out_jac);
+}
+
+int zkb_g1_fixed_base_mul(const uint64_t* scalars, size_t n, uint64_t* out_affine) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (n == 0) return ZKB_OK;
+    ZKB_TRY(check_ptr(scalars, "scalars"));
+    ZKB_TRY(check_ptr(out_affine, "out_affine"));
+    HostIo& h = hostio();
+    Ctx& c = ctx();
+    ZKB_TRY(h.scalars.reserve(n * 32));
+    ZKB_TRY(h.bases.reserve(n * 64));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    ZKB_TRY(g1_fixed_base_mul_dev(h.scalars.as<uint4>(), n, h.bases.as<uint4>(), c.stream));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
+    ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return ZKB_OK;
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------------------------------------
+int zkb_ntt_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
+    ZKB_TRY(check_ptr(omega, "omega"));
+    const uint64_t* in[1] = {a};
+    uint64_t* out[1] = {a};
+    return domain_op_host(OP_FFT, in, out, 1, log_n, log_n, omega);
+}
+int zkb_ntt_fr_batch(uint64_t* const* cols, size_t ncols, const uint64_t omega[4], uint32_t log_n) {
+    ZKB_TRY(check_ptr(omega, "omega"));
+    return domain_op_host(OP_FFT, const_cast<const uint64_t* const*>(cols), cols, ncols, log_n, log_n, omega);
+}
+int zkb_lagrange_to_coeff(uint64_t* a, uint32_t k) {
+    const uint64_t* in[1] = {a};
+    uint64_t* out[1] = {a};
+    return domain_op_host(OP_L2C, in, out, 1, k, k, nullptr);
+}
+int zkb_lagrange_to_coeff_batch(uint64_t* const* cols, size_t ncols, uint32_t k) {
+    return domain_op_host(OP_L2C, const_cast<const uint64_t* const*>(cols), cols, ncols, k, k, nullptr);
+}
+int zkb_coeff_to_lagrange(uint64_t* a, uint32_t k) {
+    const uint64_t* in[1] = {a};
+    uint64_t* out[1] = {a};
+    return domain_op_host(OP_C2L, in, out, 1, k, k, nullptr);
+}
+int zkb_coeff_to_extended(const uint64_t* in, uint64_t* out, uint32_t k, uint32_t extended_k) {
+    const uint64_t* i1[1] = {in};
+    uint64_t* o1[1] = {out};
+    return domain_op_host(OP_C2E, i1, o1, 1, k, extended_k, nullptr);
+}
+int zkb_coeff_to_extended_batch(const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k, uint32_t extended_k) {
+    return domain_op_host(OP_C2E, in, out, ncols, k, extended_k, nullptr);
+}
+int zkb_extended_to_coeff(uint64_t* a, uint32_t k, uint32_t extended_k) {
+    const uint64_t* in[1] = {a};
+    uint64_t* out[1] = {a};
+    return domain_op_host(OP_E2C, in, out, 1, k, extended_k, nullptr);
+}
+int zkb_fr_omega(uint32_t k, uint64_t out[4]) {
+    ZKB_TRY(check_ptr(out, "out"));
+    if (k > 28) { set_error("k %u exceeds the two-adicity 28", k); return ZKB_ERR_ARG; }
+    fr_to_limbs64(fr_omega_host(k), out);
+    return ZKB_OK;
+}
+
+static int dev_common(DomainOp op, const void* d_in, void* d_a, void* d_b, size_t ncols, uint32_t k, uint32_t ek,
+                      const uint64_t* omega, void* stream) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(d_in, "device input"));
+    ZKB_TRY(check_ptr(d_a, "device data"));
+    ZKB_TRY(check_ptr(d_b, "device scratch"));
+    return domain_op_dev(op, reinterpret_cast<const uint4*>(d_in), reinterpret_cast<uint4*>(d_a), reinterpret_cast<uint4*>(d_b),
+                         ncols, k, ek, omega, (cudaStream_t)stream);
+}
+int zkb_ntt_fr_dev(void* d_data, void* d_scratch, size_t ncols, const uint64_t omega[4], uint32_t log_n, void* stream) {
+    ZKB_TRY(check_ptr(omega, "omega"));
+    return dev_common(OP_FFT, d_data, d_data, d_scratch, ncols, log_n, log_n, omega, stream);
+}
+int zkb_coeff_to_extended_dev(const void* d_in, void* d_out, void* d_scratch, size_t ncols, uint32_t k, uint32_t extended_k, void* stream) {
+    return dev_common(OP_C2E, d_in, d_out, d_scratch, ncols, k, extended_k, nullptr, stream);
+}
+int zkb_extended_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, uint32_t extended_k, void* stream) {
+    return dev_common(OP_E2C, d_data, d_data, d_scratch, ncols, k, extended_k, nullptr, stream);
+}
+int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, void* stream) {
+    return dev_common(OP_L2C, d_data, d_data, d_scratch, ncols, k, k, nullptr, stream);
+}
+
+// ---- tuning / measurement ----------------------------------------------------------------------------------------------------
+int zkb_msm_set_params(uint32_t window_bits, uint32_t chunk) {
+    if (window_bits && (window_bits < 2 || window_bits > 22)) { set_error("window_bits must be 0 or in [2, 22]"); return ZKB_ERR_ARG; }
+    ctx().msm_c_override = window_bits;
+    ctx().msm_chunk_override = chunk;
+    return ZKB_OK;
+}
+int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, uint32_t* chunk) {
+    MsmGeometry g = msm_geometry(n, ctx().msm_c_override, ctx().msm_chunk_override);
+    if (window_bits) *window_bits = g.c;
+    if (num_windows) *num_windows = g.nwin;
+    if (chunk) *chunk = g.chunk0;
+    return ZKB_OK;
+}
+int zkb_prof_enable(int on) {
+    ctx().prof_on = on != 0;
+    return ZKB_OK;
+}
+static void prof_drain(ProfTimer& t) {
+    Ctx& c = ctx();
+    for (auto& pr : t.pending) {
+        float ms = 0;
+        cudaEventSynchronize(pr.second);
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) t.total_ms += ms;
+        else cudaGetLastError();
+        c.event_pool.push_back(pr.first);
+        c.event_pool.push_back(pr.second);
+    }
+    t.pending.clear();
+}
+int zkb_prof_reset(void) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    for (auto& kv : ctx().timers) { prof_drain(kv.second); kv.second.total_ms = 0; kv.second.launches = 0; }
+    return ZKB_OK;
+}
+int zkb_prof_get(const char* name, double* total_ms, uint64_t* launches) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(check_ptr(name, "name"));
+    auto it = ctx().timers.find(name);
+    if (it == ctx().timers.end()) {
+        if (total_ms) *total_ms = 0;
+        if (launches) *launches = 0;
+        return ZKB_OK;
+    }
+    prof_drain(it->second);
+    if (total_ms) *total_ms = it->second.total_ms;
+    if (launches) *launches = it->second.launches;
+    return ZKB_OK;
+}
+uint64_t zkb_launch_count(void) { return ctx().launches.load(); }
+int zkb_measure_imad_peak(double* wide_macs_per_s) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(wide_macs_per_s, "wide_macs_per_s"));
+    return measure_imad_peak(wide_macs_per_s);
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// hostemu.cu — CPU emulator of the device code (TEST INFRASTRUCTURE; built as libzkb200_hostemu.so).
+//
+// The kernels in this package are written as __host__ __device__ per-thread phase functions.  This file runs
+// exactly those functions on the CPU, thread by thread and CTA by CTA (the PTX carry chains are replaced by
+// their portable twins in field.cuh), so limb arithmetic, index maths, digit reversal, chunk-boundary logic
+// etc. are validated against the oracle in the `-m "not gpu"` tests of this repo, where no GPU exists.
+// It is NOT a CPU fallback: libzkb200.so never links it and the product fails loudly without a CUDA device.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "curve.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "ntt_plan.hpp"
+
+using namespace zkb;
+
+#define EMU_EXPORT extern "C" __attribute__((visibility("default")))
+
+static Fr fr_from_u64(const uint64_t* p) {
+    Fr r;
+    for (int i = 0; i < 4; ++i) { r.l[2 * i] = (uint32_t)p[i]; r.l[2 * i + 1] = (uint32_t)(p[i] >> 32); }
+    return r;
+}
+template <class F>
+static void f_to_u64(const F& v, uint64_t* p) {
+    for (int i = 0; i < 4; ++i) p[i] = (uint64_t)v.l[2 * i] | ((uint64_t)v.l[2 * i + 1] << 32);
+}
+static Fq fq_from_u64(const uint64_t* p) {
+    Fq r;
+    for (int i = 0; i < 4; ++i) { r.l[2 * i] = (uint32_t)p[i]; r.l[2 * i + 1] = (uint32_t)(p[i] >> 32); }
+    return r;
+}
+
+// field: 0 Fr, 1 Fq; op: 0 mul, 1 add, 2 sub
+EMU_EXPORT void zkb_emu_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (field == 0) {
+            Fr x = fr_from_u64(a + 4 * i), y = fr_from_u64(b + 4 * i);
+            Fr r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+            f_to_u64(r, o + 4 * i);
+        } else {
+            Fq x = fq_from_u64(a + 4 * i), y = fq_from_u64(b + 4 * i);
+            Fq r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
+            f_to_u64(r, o + 4 * i);
+        }
+    }
+}
+
+// ---- NTT -----------------------------------------------------------------------------------------------------
+template <int LOGR>
+static void emu_run_pass(const NttPassArgs& a, uint32_t nthreads, uint64_t nctas, uint32_t cols, size_t smem_bytes) {
+    std::vector<uint4> sm(smem_bytes / 16);
+    for (uint32_t col = 0; col < cols; ++col)
+        for (uint64_t cta = 0; cta < nctas; ++cta) {
+            for (uint32_t t = 0; t < nthreads; ++t) ntt_phase_load<LOGR>(a, sm.data(), t, nthreads, cta, col);
+            int left = LOGR;
+            while (left > 0) {
+                int r = left >= 3 ? 3 : left;
+                for (uint32_t t = 0; t < nthreads; ++t)
+                    ntt_phase_round<LOGR>(a, sm.data(), t, nthreads, (uint32_t)left, (uint32_t)r);
+                left -= r;
+            }
+            for (uint32_t t = 0; t < nthreads; ++t) ntt_phase_store<LOGR>(a, sm.data(), t, nthreads, cta, col);
+        }
+}
+
+static void emu_dispatch_pass(const NttPassArgs& a, uint32_t logr, uint32_t nthreads, uint64_t nctas, uint32_t cols,
+                              size_t smem) {
+    switch (logr) {
+#define C(L) case L: emu_run_pass<L>(a, nthreads, nctas, cols, smem); break;
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10)
+#undef C
+        default: break;
+    }
+}
+
+static void pow_table(std::vector<uint4>& out, const Fr& omega, uint64_t count, uint32_t shift) {
+    out.resize(2 * count);
+    for (uint64_t t = 0; t < count; ++t) fr_store2(out.data(), t, fp_pow_u64(omega, t << shift));
+}
+
+// in: cols x in_len elements (column stride in_len); out: cols x 2^log_n.  *_scale3: 3x4 u64 Montgomery or NULL.
+EMU_EXPORT int zkb_emu_ntt(const uint64_t* in, uint64_t in_len, uint64_t* out, uint32_t log_n, const uint64_t* omega,
+                           const uint64_t* in_scale3, const uint64_t* out_scale3, uint32_t cols) {
+    if (log_n < 1 || log_n > 28) return -1;
+    const uint64_t N = 1ull << log_n;
+    NttGeometry g = ntt_geometry(log_n);
+    Fr w = fr_from_u64(omega);
+    std::vector<uint4> tw_lo, tw_hi, tw_r[NTT_MAX_PASSES];
+    pow_table(tw_lo, w, 1ull << g.tw_h, 0);
+    pow_table(tw_hi, w, N >> g.tw_h ? N >> g.tw_h : 1, g.tw_h);
+    for (uint32_t p = 0; p < g.npass; ++p) pow_table(tw_r[p], w, 1ull << g.lr[p], log_n - g.lr[p]);
+    std::vector<uint4> work(2 * N * cols);
+    for (uint32_t p = 0; p < g.npass; ++p) {
+        NttPassArgs a{};
+        bool fin = p + 1 == g.npass;
+        a.src = p == 0 ? reinterpret_cast<const uint4*>(in) : work.data();
+        a.src_col_stride = p == 0 ? in_len : N;
+        a.dst = fin ? reinterpret_cast<uint4*>(out) : work.data();
+        a.dst_col_stride = N;
+        a.log_n = log_n; a.npass = g.npass; a.pass = p;
+        for (uint32_t q = 0; q < g.npass; ++q) a.lr[q] = g.lr[q];
+        a.log_t = g.log_t[p];
+        a.is_final = fin;
+        a.tw_r = tw_r[p].data(); a.tw_hi = tw_hi.data(); a.tw_lo = tw_lo.data(); a.tw_h = g.tw_h;
+        a.in_len = p == 0 ? in_len : N;
+        a.in_scale_on = (p == 0 && in_scale3) ? 1 : 0;
+        a.out_scale_on = (fin && out_scale3) ? 1 : 0;
+        for (int m = 0; m < 3; ++m)
+            for (int i = 0; i < 4; ++i) {
+                if (in_scale3) { a.in_scale[m][2 * i] = (uint32_t)in_scale3[4 * m + i]; a.in_scale[m][2 * i + 1] = (uint32_t)(in_scale3[4 * m + i] >> 32); }
+                if (out_scale3) { a.out_scale[m][2 * i] = (uint32_t)out_scale3[4 * m + i]; a.out_scale[m][2 * i + 1] = (uint32_t)(out_scale3[4 * m + i] >> 32); }
+            }
+        emu_dispatch_pass(a, g.lr[p], ntt_cta_threads(g, p), ntt_cta_count(g, p), cols, ntt_cta_smem_bytes(g, p));
+    }
+    return 0;
+}
+
+// ---- MSM -----------------------------------------------------------------------------------------------------
+#include "hostemu_msm.inc"

@@ -1,0 +1,242 @@
+// msm.cuh — BN254 G1 multi-scalar multiplication, device code as per-thread functions.
+//
+// Replaces halo2_proofs::arithmetic::best_multiexp.  The result is a group element, so
+// it does not depend on the algorithm; this one is a sort-based Pippenger:
+//
+//   1. digits   : scalar -> canonical integer (one Montgomery mul by 1, == Fr::to_repr) -> W signed c-bit digits
+//                 d_w in [-2^(c-1)+1, 2^(c-1)];  emits key = w*2^(c-1) + |d_w|-1, value = point index | sign<<31
+//                 (zero digits get key = INVALID and sort to the end).
+//   2. sort     : radix sort of (key, value) pairs — all points of one bucket become one contiguous run.
+//   3. accumulate: the sorted array is cut into fixed chunks of S entries, one thread per chunk, so the load is
+//                 balanced for ANY digit distribution (witness-like columns put most points in a few buckets).
+//                 A thread sums each run of equal keys with mixed additions (XYZZ accumulator).  Runs strictly
+//                 inside a chunk are complete buckets and are written to the bucket array; the first and last
+//                 run of a chunk may continue in the neighbours and go to a (key, partial) list, which is
+//                 reduced by the same routine one level up (full XYZZ adds) until one thread remains.
+//   4. reduce   : per window sum_b (b+1)*B[b] by segments: running sums inside a segment of m buckets, plus
+//                 (segment offset)*(segment sum) by a short double-and-add; segment results are tree-summed.
+//   5. the W window sums (128 B each) go to the host, which does the c-bit Horner combination and the final
+//                 normalisation (north_star: "tiny bucket sums combined on the host").
+#pragma once
+#include "curve.cuh"
+
+namespace zkb {
+
+constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
+
+struct MsmDigitArgs {
+    const uint4* scalars;  // n Montgomery Fr
+    uint64_t n;
+    uint32_t c;            // window bits
+    uint32_t nwin;         // W, W*c >= 255
+    uint32_t* keys;        // [W*n], window-major
+    uint32_t* vals;
+    uint32_t invalid_key;  // W << (c-1)
+    uint32_t index_base;   // added to the point index (for range-sharded bases)
+};
+
+ZKB_HD uint32_t msm_extract_bits(const Fr& s, uint32_t bit, uint32_t c) {  // c <= 24
+    if (bit >= 256) return 0;
+    uint32_t w = bit >> 5, sh = bit & 31;
+    uint64_t v = s.l[w];
+    if (w + 1 < 8) v |= (uint64_t)s.l[w + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1);
+}
+
+ZKB_HD void msm_digits_thread(const MsmDigitArgs& a, uint64_t i) {
+    if (i >= a.n) return;
+    Fr s = fp_from_mont(fr_load2(a.scalars, i));
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (a.c - 1);
+    for (uint32_t w = 0; w < a.nwin; ++w) {
+        uint32_t v = msm_extract_bits(s, w * a.c, a.c) + carry;
+        uint32_t neg = v > half;
+        uint32_t mag = neg ? (1u << a.c) - v : v;
+        carry = neg;
+        uint32_t key = mag ? (w << (a.c - 1)) + (mag - 1) : a.invalid_key;
+        a.keys[(uint64_t)w * a.n + i] = key;
+        a.vals[(uint64_t)w * a.n + i] = (uint32_t)(i + a.index_base) | (neg << 31);
+    }
+}
+
+// ---- accumulate ----------------------------------------------------------------------------------------------------
+struct MsmAccArgs {
+    const uint32_t* keys;   // level 0: sorted keys; level >= 1: partial keys (INVALID entries are skipped)
+    const uint32_t* vals;   // level 0: point index | sign<<31
+    const uint4* bases;     // level 0: affine points (64 B each)
+    const uint4* pin;       // level >= 1: partial XYZZ values (128 B each)
+    uint64_t count;         // entries at this level
+    uint32_t chunk;         // S
+    uint32_t invalid_key;
+    uint32_t last_level;    // single thread: head/tail are complete and go to the bucket array
+    uint4* buckets;         // XYZZ [nbuckets], zero-initialised
+    uint32_t* pkeys_out;    // [2 * nthreads]
+    uint4* pvals_out;       // XYZZ [2 * nthreads]
+};
+
+ZKB_HD void msm_store_xyzz(uint4* base, uint64_t idx, const XYZZ& p) { p.store(base + 8 * idx); }
+ZKB_HD XYZZ msm_load_xyzz(const uint4* base, uint64_t idx) { return XYZZ::load(base + 8 * idx); }
+
+template <bool LEVEL0>
+ZKB_HD void msm_accumulate_thread(const MsmAccArgs& a, uint64_t t) {
+    const uint64_t lo = t * a.chunk;
+    if (lo >= a.count) return;
+    const uint64_t hi = lo + a.chunk < a.count ? lo + a.chunk : a.count;
+    XYZZ acc = XYZZ::identity();
+    uint32_t cur = MSM_INVALID_KEY;
+    uint32_t runs_done = 0;       // completed runs before the current one
+    uint32_t head_key = MSM_INVALID_KEY, tail_key = MSM_INVALID_KEY;
+    XYZZ tail = XYZZ::identity();
+
+    for (uint64_t i = lo; i < hi; ++i) {
+        uint32_t k = a.keys[i];
+        if (k >= a.invalid_key) {
+            if (LEVEL0) break;   // sorted: only invalid entries follow
+            continue;            // partial lists carry holes
+        }
+        if (k != cur) {
+            if (cur != MSM_INVALID_KEY) {
+                if (runs_done == 0) {                      // first run of the chunk: may continue to the left
+                    if (a.last_level) msm_store_xyzz(a.buckets, cur, acc);
+                    else { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, acc); }
+                } else {
+                    msm_store_xyzz(a.buckets, cur, acc);   // strictly interior run == complete bucket
+                }
+                ++runs_done;
+            }
+            acc = XYZZ::identity();
+            cur = k;
+        }
+        if (LEVEL0) {
+            uint32_t v = a.vals[i];
+            Affine p = affine_load(a.bases + 4 * (uint64_t)(v & 0x7fffffffu));
+            if (!p.is_identity()) {
+                if (v >> 31) p.y = fp_neg(p.y);
+                xyzz_add_mixed(acc, p.x, p.y);
+            }
+        } else {
+            xyzz_add(acc, msm_load_xyzz(a.pin, i));
+        }
+    }
+    if (cur != MSM_INVALID_KEY) {
+        if (a.last_level) msm_store_xyzz(a.buckets, cur, acc);
+        else if (runs_done == 0) { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, acc); }
+        else { tail_key = cur; tail = acc; }
+    }
+    if (!a.last_level) {
+        a.pkeys_out[2 * t] = head_key;
+        a.pkeys_out[2 * t + 1] = tail_key;
+        if (tail_key != MSM_INVALID_KEY) msm_store_xyzz(a.pvals_out, 2 * t + 1, tail);
+    }
+}
+
+// ---- bucket reduction ------------------------------------------------------------------------------------------------
+struct MsmReduceArgs {
+    const uint4* buckets;   // XYZZ [nwin << (c-1)]
+    uint32_t c;
+    uint32_t nwin;
+    uint32_t log_m;         // segment length m = 2^log_m buckets
+    uint4* seg_out;         // XYZZ [nwin * J], J = 2^(c-1-log_m)
+};
+
+// k*P for a small public k (double-and-add from the top bit)
+ZKB_HD XYZZ xyzz_mul_small(const XYZZ& p, uint32_t k) {
+    XYZZ r = XYZZ::identity();
+    if (k == 0 || p.is_identity()) return r;
+    int top = 31;
+    while (!((k >> top) & 1)) --top;
+    for (int i = top; i >= 0; --i) {
+        r = xyzz_double(r);
+        if ((k >> i) & 1) xyzz_add(r, p);
+    }
+    return r;
+}
+
+// thread t = w*J + j : sum_{i<m} (j*m + i + 1) * B[w][j*m + i]
+ZKB_HD void msm_reduce_segment_thread(const MsmReduceArgs& a, uint64_t t) {
+    const uint32_t log_j = a.c - 1 - a.log_m;
+    const uint64_t total = (uint64_t)a.nwin << log_j;
+    if (t >= total) return;
+    const uint32_t w = (uint32_t)(t >> log_j), j = (uint32_t)(t & ((1u << log_j) - 1));
+    const uint32_t m = 1u << a.log_m;
+    const uint64_t first = ((uint64_t)w << (a.c - 1)) + ((uint64_t)j << a.log_m);
+    XYZZ run = XYZZ::identity(), acc = XYZZ::identity();
+    for (uint32_t i = m; i-- > 0;) {
+        xyzz_add(run, msm_load_xyzz(a.buckets, first + i));
+        xyzz_add(acc, run);
+    }
+    XYZZ off = xyzz_mul_small(run, j << a.log_m);
+    xyzz_add(acc, off);
+    msm_store_xyzz(a.seg_out, t, acc);
+}
+
+// out[t] = sum_{i<g} in[t*g + i]   (tree level of the segment sum)
+struct MsmSumArgs {
+    const uint4* in;
+    uint4* out;
+    uint64_t out_count;
+    uint32_t group;
+};
+ZKB_HD void msm_sum_groups_thread(const MsmSumArgs& a, uint64_t t) {
+    if (t >= a.out_count) return;
+    XYZZ acc = msm_load_xyzz(a.in, t * a.group);
+    for (uint32_t i = 1; i < a.group; ++i) xyzz_add(acc, msm_load_xyzz(a.in, t * a.group + i));
+    msm_store_xyzz(a.out, t, acc);
+}
+
+// ---- window combination + normalisation (host side of step 5; also usable on the device) ----------------------------
+// a^(p-2)
+ZKB_HD_NOINLINE Fq fq_inv(const Fq& a) {
+    Fq acc = Fq::one();
+    for (int i = 255; i >= 0; --i) {
+        acc = fp_sqr(acc);
+        uint32_t limb = FqParams::M(i >> 5);
+        if (i < 32) limb -= 2;  // p - 2 : low limb 0xd87cfd47 - 2, no borrow
+        if ((limb >> (i & 31)) & 1) acc = fp_mul(acc, a);
+    }
+    return acc;
+}
+
+// XYZZ -> affine (identity -> (0,0))
+ZKB_HD_NOINLINE Affine xyzz_to_affine(const XYZZ& p) {
+    Affine r;
+    if (p.is_identity()) { r.x = Fq::zero(); r.y = Fq::zero(); return r; }
+    Fq inv = fq_inv(fp_mul(p.zz, p.zzz));
+    r.x = fp_mul(p.x, fp_mul(inv, p.zzz));
+    r.y = fp_mul(p.y, fp_mul(inv, p.zz));
+    return r;
+}
+
+// sum_w 2^(c*w) * S_w by Horner from the top window
+ZKB_HD_NOINLINE XYZZ msm_combine_windows(const XYZZ* sums, uint32_t nwin, uint32_t c) {
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t w = nwin; w-- > 0;) {
+        for (uint32_t i = 0; i < c; ++i) acc = xyzz_double(acc);
+        xyzz_add(acc, sums[w]);
+    }
+    return acc;
+}
+
+// ---- fixed-base multiples of the generator: out[i] = [s_i] G (affine) — ParamsKZG::setup building block, and the
+// generator of synthetic bases with known discrete logs for full-size parity checks --------------------------------------
+struct FixedBaseArgs {
+    const uint4* scalars;  // n Montgomery Fr
+    uint64_t n;
+    uint4* out;            // n affine points
+};
+ZKB_HD void g1_fixed_base_mul_thread(const FixedBaseArgs& a, uint64_t i) {
+    if (i >= a.n) return;
+    Fr s = fp_from_mont(fr_load2(a.scalars, i));
+    Fq gx = Fq::one();
+    Fq gy = fp_dbl(gx);  // G = (1, 2)
+    XYZZ acc = XYZZ::identity();
+    for (int b = 253; b >= 0; --b) {
+        acc = xyzz_double(acc);
+        if ((s.l[b >> 5] >> (b & 31)) & 1) xyzz_add_mixed(acc, gx, gy);
+    }
+    Affine r = xyzz_to_affine(acc);
+    r.x.store(a.out + 4 * i);
+    r.y.store(a.out + 4 * i + 2);
+}
+
+}  // namespace zkb

@@ -1,0 +1,52 @@
+// msm_plan.hpp — host-side geometry of the Pippenger pipeline (shared by the CUDA driver and the CPU emulator).
+#pragma once
+#include <cstdint>
+
+namespace zkb {
+
+struct MsmGeometry {
+    uint32_t c;            // window bits
+    uint32_t nwin;         // W = ceil(255 / c)
+    uint32_t nbuckets;     // W << (c-1)
+    uint32_t invalid_key;  // == nbuckets
+    uint32_t key_bits;     // radix-sort bits covering [0, invalid_key]
+    uint32_t chunk0;       // entries per thread, level 0
+    uint32_t chunk_up;     // entries per thread, levels >= 1
+    uint32_t last_max;     // a level with <= last_max entries is finished by one thread
+    uint32_t log_m;        // bucket-reduction segment length 2^log_m
+    uint32_t sum_group;    // tree fan-in of the segment sum
+};
+
+// cost model: W * (n mixed adds + ~2.8 * 2^(c-1) full-add equivalents for the reduction)
+inline uint32_t msm_pick_window(uint64_t n) {
+    double best = 1e300;
+    uint32_t best_c = 8;
+    for (uint32_t c = 4; c <= 22; ++c) {
+        uint32_t w = (255 + c - 1) / c;
+        double cost = (double)w * ((double)n + 2.8 * (double)(1ull << (c - 1)));
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0) {
+    MsmGeometry g{};
+    g.c = c_override ? c_override : msm_pick_window(n ? n : 1);
+    if (g.c < 2) g.c = 2;
+    if (g.c > 22) g.c = 22;
+    g.nwin = (255 + g.c - 1) / g.c;
+    g.nbuckets = g.nwin << (g.c - 1);
+    g.invalid_key = g.nbuckets;
+    g.key_bits = 1;
+    while ((1ull << g.key_bits) <= g.invalid_key) ++g.key_bits;
+    g.chunk0 = chunk_override ? chunk_override : 128;
+    g.chunk_up = 32;
+    g.last_max = 64;
+    // segments: keep >= ~32 segments per window when the window has that many buckets, m <= 128
+    uint32_t lb = g.c - 1;
+    g.log_m = lb > 12 ? 7 : (lb > 5 ? lb - 5 : 0);
+    g.sum_group = 32;
+    return g;
+}
+
+}  // namespace zkb

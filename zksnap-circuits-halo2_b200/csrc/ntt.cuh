@@ -1,0 +1,305 @@
+// ntt.cuh — Fr NTT passes (device code written as per-thread phase functions).
+//
+// Replaces halo2_proofs::arithmetic::best_fft: natural order in, natural order out,
+// out[i] = sum_j a[j] * omega^(i*j).  The field is exact, so any correct factorisation gives bit-identical
+// output; this one is a mixed-radix Cooley-Tukey ("four-step" generalised to P passes):
+//
+//   N = R_1 * R_2 * ... * R_P          (R_p = 2^lr[p], <= 1024)
+//   n = sum_p n_p * S_p ,  S_p = prod_{q>p} R_q      (n_1 most significant input digit)
+//   k = sum_p k_p * Q_p ,  Q_p = prod_{q<p} R_q      (k_1 least significant output digit)
+//
+// Pass p transforms digit n_p -> k_p (an R_p-point NTT per (hi, lo) pair) in place: k_p is stored where n_p
+// was (stride S_p).  Before the transform each element is multiplied by the inter-pass twiddle
+//   omega_N ^ ( n_p * K_{p-1} * N / Q_{p+1} ),    K_{p-1} = sum_{q<p} k_q * Q_q ,
+// read from a two-level table (hi/lo split of the exponent).  The last pass writes out of place to the
+// digit-reversed address k = K_{P-1} + Q_P * k_P, so the result lands in natural order with no separate
+// transpose pass.  One CTA stages R*T elements (T adjacent columns of the strided dimension, so every global
+// row it touches is T*32 contiguous bytes) in shared memory, runs radix-8 DIF rounds with 8 elements per thread
+// in registers, and reads the digit-reversed shared-memory position on the way out.
+//
+// Fusions: first pass can zero-extend (in_len < N) and scale by c[i mod 3] (coset shift of
+// coeff_to_extended); last pass can scale by c[i mod 3] (1/N and the inverse coset shift of extended_to_coeff,
+// or the plain 1/N of lagrange_to_coeff).
+//
+// Every phase is a __host__ __device__ function of (cta, tid): the kernels in ntt.cu call them with
+// __syncthreads() in between, and the CPU emulator (hostemu.cu, test infrastructure) runs the very same code
+// thread by thread so index logic is checked without a GPU.
+#pragma once
+#include "field.cuh"
+
+namespace zkb {
+
+constexpr int NTT_MAX_PASSES = 4;
+
+struct NttPassArgs {
+    const uint4* src;     // column 0 of the input  (element = 2 x uint4)
+    uint4* dst;           // column 0 of the output
+    uint64_t src_col_stride;  // elements between columns in src
+    uint64_t dst_col_stride;
+    uint32_t log_n;
+    uint32_t npass;           // P
+    uint32_t pass;            // p (0-based)
+    uint32_t lr[NTT_MAX_PASSES];  // log2 R_q
+    uint32_t log_t;           // log2 T (tile width)
+    uint32_t is_final;        // last pass: transposed (digit-reversed) store
+    // twiddles (device pointers)
+    const uint4* tw_r;        // omega_R^t, t < R for this pass' R
+    const uint4* tw_hi;       // omega_N^(t << tw_h)
+    const uint4* tw_lo;       // omega_N^t, t < 2^tw_h
+    uint32_t tw_h;
+    // fusions
+    uint64_t in_len;          // first pass: elements >= in_len read as zero (in_len == N otherwise)
+    uint32_t in_scale_on;     // first pass: multiply by in_scale[i % 3]
+    uint32_t out_scale_on;    // last pass: multiply by out_scale[i % 3]
+    uint32_t in_scale[3][8];
+    uint32_t out_scale[3][8];
+};
+
+// shared memory is split in two planes (low / high 16 bytes) so a warp's 128-bit accesses are conflict-free
+ZKB_HD Fr sm_load(const uint4* lo, const uint4* hi, uint32_t i) { return fr_from_u4(lo[i], hi[i]); }
+ZKB_HD void sm_store(uint4* lo, uint4* hi, uint32_t i, const Fr& v) {
+    lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+ZKB_HD Fr fr_from_words(const uint32_t (&w)[8]) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = w[i];
+    return r;
+}
+
+// ---- geometry helpers ---------------------------------------------------------------------------------
+// stored hi index (k_1 most significant, radices R_1..R_{p-1}) -> K = sum k_q Q_q (k_1 least significant)
+ZKB_HD uint64_t ntt_hi_to_K(const NttPassArgs& a, uint64_t hi) {
+    uint64_t K = 0;
+    uint32_t shift = 0;
+    for (uint32_t q = 0; q < a.pass; ++q) shift += a.lr[q];
+    for (int q = (int)a.pass - 1; q >= 0; --q) {
+        shift -= a.lr[q];
+        uint64_t d = hi & ((1ull << a.lr[q]) - 1);
+        hi >>= a.lr[q];
+        K |= d << shift;
+    }
+    return K;
+}
+ZKB_HD uint64_t ntt_K_to_hi(const NttPassArgs& a, uint64_t K) {
+    uint64_t hi = 0;
+    for (uint32_t q = 0; q < a.pass; ++q) {
+        uint64_t d = K & ((1ull << a.lr[q]) - 1);
+        K >>= a.lr[q];
+        hi = (hi << a.lr[q]) | d;
+    }
+    return hi;
+}
+
+// position of output k inside the R-point block after DIF rounds of radix 8,8,..,rem
+template <int LOGR>
+ZKB_HD uint32_t ntt_dif_pos(uint32_t k) {
+    uint32_t pos = 0;
+    int left = LOGR;
+    while (left > 0) {
+        int t = left >= 3 ? 3 : left;
+        uint32_t d = k & ((1u << t) - 1);
+        k >>= t;
+        left -= t;
+        pos |= d << left;
+    }
+    return pos;
+}
+
+// shared-memory index of (row r, column c)
+template <int LOGR>
+ZKB_HD uint32_t ntt_sm_index(const NttPassArgs& a, uint32_t r, uint32_t c) {
+    constexpr uint32_t R = 1u << LOGR;
+    return a.is_final ? c * (R + 1) + r : (r << a.log_t) + c;
+}
+template <int LOGR>
+ZKB_HD uint32_t ntt_sm_plane(const NttPassArgs& a) {  // uint4 elements per plane
+    constexpr uint32_t R = 1u << LOGR;
+    return a.is_final ? ((R + 1) << a.log_t) : (R << a.log_t);
+}
+
+// ---- phase 1: global -> shared, with zero-extension, coset scale and inter-pass twiddle ------------------
+template <int LOGR>
+ZKB_HD void ntt_phase_load(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32_t nthreads, uint64_t cta,
+                           uint32_t col) {
+    constexpr uint32_t R = 1u << LOGR;
+    const uint32_t T = 1u << a.log_t;
+    const uint32_t E = R << a.log_t;
+    uint4* lo = sm;
+    uint4* hi = sm + ntt_sm_plane<LOGR>(a);
+    const uint4* src = a.src + 2 * a.src_col_stride * col;
+
+    uint32_t log_stride = 0;  // log2 S_p
+    for (uint32_t q = a.pass + 1; q < a.npass; ++q) log_stride += a.lr[q];
+    uint32_t log_q_next = 0;  // log2 Q_{p+1}
+    for (uint32_t q = 0; q <= a.pass; ++q) log_q_next += a.lr[q];
+    const uint32_t tw_shift = a.log_n - log_q_next;
+
+    uint64_t base, K0;
+    if (!a.is_final) {
+        uint64_t tiles_per_hi = (1ull << log_stride) >> a.log_t;
+        uint64_t hidx = cta / tiles_per_hi;
+        uint64_t lo0 = (cta % tiles_per_hi) << a.log_t;
+        base = ((hidx << LOGR) << log_stride) + lo0;
+        K0 = ntt_hi_to_K(a, hidx);
+    } else {
+        K0 = cta << a.log_t;
+        base = 0;
+    }
+
+    for (uint32_t q = tid; q < E; q += nthreads) {
+        uint32_t r, c;
+        uint64_t gi, K;
+        if (!a.is_final) {
+            r = q >> a.log_t; c = q & (T - 1);
+            gi = base + ((uint64_t)r << log_stride) + c;
+            K = K0;
+        } else {
+            c = q >> LOGR; r = q & (R - 1);
+            K = K0 + c;
+            gi = (ntt_K_to_hi(a, K) << LOGR) + r;
+        }
+        Fr v;
+        if (gi < a.in_len) {
+            v = fr_load2(src, gi);
+            if (a.in_scale_on) {
+                uint32_t m = (uint32_t)(gi % 3);
+                if (m) v = fp_mul(v, fr_from_words(a.in_scale[m]));
+            }
+        } else {
+            v = Fr::zero();
+        }
+        if (a.pass > 0) {
+            uint64_t e = ((uint64_t)r * K) << tw_shift;  // < N
+            uint64_t eh = e >> a.tw_h, el = e & ((1ull << a.tw_h) - 1);
+            if (eh) v = fp_mul(v, fr_load2(a.tw_hi, eh));
+            if (el) v = fp_mul(v, fr_load2(a.tw_lo, el));
+        }
+        sm_store(lo, hi, ntt_sm_index<LOGR>(a, r, c), v);
+    }
+}
+
+// ---- phase 2: one DIF round of radix 2^t on blocks of size L = 2^log_l -------------------------------------
+// group g handles inputs pos_j = b*L + i + j*(L/rho); output p goes to b*L + p*(L/rho) + i times omega_L^(i*p)
+template <int LOGR>
+ZKB_HD void ntt_phase_round(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32_t nthreads, uint32_t log_l,
+                            uint32_t t) {
+    constexpr uint32_t R = 1u << LOGR;
+    const uint32_t T = 1u << a.log_t;
+    uint4* lo = sm;
+    uint4* hi = sm + ntt_sm_plane<LOGR>(a);
+    const uint32_t log_sub = log_l - t;             // log2 (L / rho)
+    const uint32_t groups = (R >> t) << a.log_t;    // (R/rho) * T
+    const uint32_t tw_step = LOGR - log_l;          // omega_L = omega_R^(R/L)
+
+    for (uint32_t g = tid; g < groups; g += nthreads) {
+        uint32_t u, c;
+        if (!a.is_final) { u = g >> a.log_t; c = g & (T - 1); }
+        else { c = g / (R >> t); u = g % (R >> t); }
+        uint32_t b = u >> log_sub, i = u & ((1u << log_sub) - 1);
+        uint32_t p0 = (b << log_l) + i;
+        if (t == 3) {
+            Fr x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)j << log_sub), c));
+            const Fr w1 = fr_load2(a.tw_r, R / 8), w2 = fr_load2(a.tw_r, R / 4), w3 = fr_load2(a.tw_r, 3 * (R / 8));
+            Fr a0 = fp_add(x[0], x[4]), a1 = fp_add(x[1], x[5]), a2 = fp_add(x[2], x[6]), a3 = fp_add(x[3], x[7]);
+            Fr b0 = fp_sub(x[0], x[4]);
+            Fr b1 = fp_mul(fp_sub(x[1], x[5]), w1);
+            Fr b2 = fp_mul(fp_sub(x[2], x[6]), w2);
+            Fr b3 = fp_mul(fp_sub(x[3], x[7]), w3);
+            Fr c0 = fp_add(a0, a2), c1 = fp_add(a1, a3), d0 = fp_sub(a0, a2), d1 = fp_mul(fp_sub(a1, a3), w2);
+            Fr e0 = fp_add(b0, b2), e1 = fp_add(b1, b3), f0 = fp_sub(b0, b2), f1 = fp_mul(fp_sub(b1, b3), w2);
+            x[0] = fp_add(c0, c1); x[4] = fp_sub(c0, c1);
+            x[2] = fp_add(d0, d1); x[6] = fp_sub(d0, d1);
+            x[1] = fp_add(e0, e1); x[5] = fp_sub(e0, e1);
+            x[3] = fp_add(f0, f1); x[7] = fp_sub(f0, f1);
+            if (log_sub > 0 && i > 0) {
+#pragma unroll
+                for (int p = 1; p < 8; ++p) x[p] = fp_mul(x[p], fr_load2(a.tw_r, (uint64_t)(i * p) << tw_step));
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)p << log_sub), c), x[p]);
+        } else if (t == 2) {
+            Fr x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)j << log_sub), c));
+            const Fr w4 = fr_load2(a.tw_r, R / 4);
+            Fr a0 = fp_add(x[0], x[2]), a1 = fp_add(x[1], x[3]), d0 = fp_sub(x[0], x[2]);
+            Fr d1 = fp_mul(fp_sub(x[1], x[3]), w4);
+            x[0] = fp_add(a0, a1); x[2] = fp_sub(a0, a1);
+            x[1] = fp_add(d0, d1); x[3] = fp_sub(d0, d1);
+            if (log_sub > 0 && i > 0) {
+#pragma unroll
+                for (int p = 1; p < 4; ++p) x[p] = fp_mul(x[p], fr_load2(a.tw_r, (uint64_t)(i * p) << tw_step));
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)p << log_sub), c), x[p]);
+        } else {
+            Fr x0 = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0, c));
+            Fr x1 = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0 + (1u << log_sub), c));
+            Fr y0 = fp_add(x0, x1), y1 = fp_sub(x0, x1);
+            if (log_sub > 0 && i > 0) y1 = fp_mul(y1, fr_load2(a.tw_r, (uint64_t)i << tw_step));
+            sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0, c), y0);
+            sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0 + (1u << log_sub), c), y1);
+        }
+    }
+}
+
+// ---- phase 3: shared -> global (in place for inner passes, digit-reversed address for the last) ------------
+template <int LOGR>
+ZKB_HD void ntt_phase_store(const NttPassArgs& a, const uint4* sm, uint32_t tid, uint32_t nthreads, uint64_t cta,
+                            uint32_t col) {
+    constexpr uint32_t R = 1u << LOGR;
+    const uint32_t T = 1u << a.log_t;
+    const uint32_t E = R << a.log_t;
+    const uint4* lo = sm;
+    const uint4* hi = sm + ntt_sm_plane<LOGR>(a);
+    uint4* dst = a.dst + 2 * a.dst_col_stride * col;
+
+    uint32_t log_stride = 0;
+    for (uint32_t q = a.pass + 1; q < a.npass; ++q) log_stride += a.lr[q];
+    uint32_t log_q = 0;  // log2 Q_p
+    for (uint32_t q = 0; q < a.pass; ++q) log_q += a.lr[q];
+
+    uint64_t base = 0, K0 = 0;
+    if (!a.is_final) {
+        uint64_t tiles_per_hi = (1ull << log_stride) >> a.log_t;
+        uint64_t hidx = cta / tiles_per_hi;
+        uint64_t lo0 = (cta % tiles_per_hi) << a.log_t;
+        base = ((hidx << LOGR) << log_stride) + lo0;
+    } else {
+        K0 = cta << a.log_t;
+    }
+    for (uint32_t q = tid; q < E; q += nthreads) {
+        uint32_t k = q >> a.log_t, c = q & (T - 1);
+        Fr v = sm_load(lo, hi, ntt_sm_index<LOGR>(a, ntt_dif_pos<LOGR>(k), c));
+        uint64_t go;
+        if (!a.is_final) go = base + ((uint64_t)k << log_stride) + c;
+        else go = K0 + c + ((uint64_t)k << log_q);
+        if (a.is_final && a.out_scale_on) v = fp_mul(v, fr_from_words(a.out_scale[go % 3]));
+        fr_store2(dst, go, v);
+    }
+}
+
+// number of DIF rounds and their radices for an R = 2^LOGR block: 3,3,...,rem
+ZKB_HD int ntt_num_rounds(int logr) { return (logr + 2) / 3; }
+
+// the whole CTA program (used by the kernel with a real barrier, by the emulator with a thread loop)
+template <int LOGR, class Barrier>
+ZKB_HD void ntt_cta_program(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32_t nthreads, uint64_t cta,
+                            uint32_t col, Barrier& bar) {
+    ntt_phase_load<LOGR>(a, sm, tid, nthreads, cta, col);
+    bar.sync();
+    int left = LOGR;
+    while (left > 0) {
+        int t = left >= 3 ? 3 : left;
+        ntt_phase_round<LOGR>(a, sm, tid, nthreads, (uint32_t)left, (uint32_t)t);
+        bar.sync();
+        left -= t;
+    }
+    ntt_phase_store<LOGR>(a, sm, tid, nthreads, cta, col);
+}
+
+}  // namespace zkb

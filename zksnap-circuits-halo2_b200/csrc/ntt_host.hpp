@@ -1,0 +1,33 @@
+// ntt_host.hpp — host-side types of the NTT driver.
+#pragma once
+#include <array>
+
+#include "common.hpp"
+#include "ntt.cuh"
+#include "ntt_plan.hpp"
+
+namespace zkb {
+
+struct NttPlan {
+    NttGeometry geom;
+    Fr omega;
+    DevBuf tw_lo, tw_hi;
+    DevBuf tw_r[NTT_MAX_PASSES];
+};
+
+struct NttIo {
+    const uint4* in = nullptr;   // cols x in_len elements, column stride in_col_stride
+    uint64_t in_len = 0;
+    uint64_t in_col_stride = 0;
+    uint4* work = nullptr;       // cols x N (inner passes run in place here; may alias `in` when in_len == N)
+    uint4* out = nullptr;        // cols x N, must differ from `work`
+    size_t cols = 1;
+    const Fr* in_scale = nullptr;   // 3 constants or NULL
+    const Fr* out_scale = nullptr;  // 3 constants or NULL
+};
+
+int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPlan** out);
+int ntt_run(const NttPlan& plan, const NttIo& io, cudaStream_t s);
+void ntt_clear_plans();
+
+}  // namespace zkb

@@ -1,0 +1,59 @@
+// ntt_plan.hpp — host-side geometry of the multi-pass NTT (shared by the CUDA driver and the CPU emulator).
+#pragma once
+#include <cstdint>
+
+#include "ntt.cuh"
+
+namespace zkb {
+
+struct NttGeometry {
+    uint32_t log_n;
+    uint32_t npass;
+    uint32_t lr[NTT_MAX_PASSES];
+    uint32_t log_t[NTT_MAX_PASSES];
+    uint32_t tw_h;
+};
+
+// R <= 2^10 in a single pass, otherwise ceil(log_n / 9) passes with radices as equal as possible
+inline NttGeometry ntt_geometry(uint32_t log_n) {
+    NttGeometry g{};
+    g.log_n = log_n;
+    if (log_n <= 10) {
+        g.npass = 1;
+        g.lr[0] = log_n;
+    } else {
+        g.npass = (log_n + 8) / 9;
+        uint32_t base = log_n / g.npass, rem = log_n % g.npass;
+        for (uint32_t p = 0; p < g.npass; ++p) g.lr[p] = base + (p < rem ? 1 : 0);
+    }
+    g.tw_h = (log_n + 1) / 2;
+    for (uint32_t p = 0; p < g.npass; ++p) {
+        uint32_t want = g.lr[p] >= 11 ? 0 : 11 - g.lr[p];  // R*T = 2048 elements per CTA
+        uint32_t cap;
+        if (p + 1 < g.npass) {  // strided pass: T <= S_p
+            cap = 0;
+            for (uint32_t q = p + 1; q < g.npass; ++q) cap += g.lr[q];
+        } else {  // final pass: T <= Q_P
+            cap = log_n - g.lr[p];
+        }
+        g.log_t[p] = want < cap ? want : cap;
+    }
+    return g;
+}
+
+inline uint32_t ntt_cta_threads(const NttGeometry& g, uint32_t p) {
+    uint32_t e = 1u << (g.lr[p] + g.log_t[p]);
+    uint32_t t = e / 8;
+    return t < 32 ? 32 : (t > 256 ? 256 : t);
+}
+inline uint64_t ntt_cta_count(const NttGeometry& g, uint32_t p) {
+    return (1ull << g.log_n) >> (g.lr[p] + g.log_t[p]);
+}
+inline size_t ntt_cta_smem_bytes(const NttGeometry& g, uint32_t p) {
+    uint32_t R = 1u << g.lr[p];
+    bool fin = (p + 1 == g.npass);
+    size_t plane = fin ? ((size_t)(R + 1) << g.log_t[p]) : ((size_t)R << g.log_t[p]);
+    return plane * 2 * 16;
+}
+
+}  // namespace zkb

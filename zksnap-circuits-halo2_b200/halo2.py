@@ -1,0 +1,250 @@
+"""halo2-shaped host API over libzkb200's C ABI (see package docstring)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, u64p, u64pp
+
+
+def lib():
+    return _ffi.load()
+
+
+def device_count() -> int:
+    return lib().zkb_device_count()
+
+
+def init(device: int | None = None) -> None:
+    """Bind this process to one GPU (one process per GPU).  Raises ZkbError if no CUDA device is usable."""
+    if device is None:
+        check(lib().zkb_init(None, 0))
+    else:
+        arr = (ctypes.c_int * 1)(device)
+        check(lib().zkb_init(arr, 1))
+
+
+def shutdown() -> None:
+    lib().zkb_shutdown()
+
+
+def launch_count() -> int:
+    return int(lib().zkb_launch_count())
+
+
+def _fr(a, name="array") -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 4)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError(f"{name}: expected (n, 4) uint64 Montgomery limbs, got {a.shape}")
+    return a
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(u64p)
+
+
+def omega(k: int) -> np.ndarray:
+    """EvaluationDomain::get_omega for n = 2^k: Fr::ROOT_OF_UNITY^(2^(28-k))."""
+    out = np.zeros(4, dtype=np.uint64)
+    check(lib().zkb_fr_omega(k, _p(out)))
+    return out
+
+
+# ---- halo2_proofs::arithmetic ------------------------------------------------------------------------------------
+def best_fft(a: np.ndarray, omega_: np.ndarray, log_n: int) -> None:
+    """best_fft(a: &mut [Fr], omega, log_n): in place; asserts a.len() == 1 << log_n like the Rust original."""
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]):
+        raise ValueError("best_fft operates in place on a contiguous writable uint64 array")
+    v = a.reshape(-1, 4)
+    assert v.shape[0] == 1 << log_n, "assertion failed: a.len() == 1 << log_n"
+    w = np.ascontiguousarray(omega_, dtype=np.uint64).reshape(4)
+    check(lib().zkb_ntt_fr(_p(v), _p(w), log_n))
+
+
+def best_multiexp(coeffs: np.ndarray, bases: np.ndarray) -> np.ndarray:
+    """best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 (12 limbs, z normalised)."""
+    s = _fr(coeffs, "coeffs")
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    assert s.shape[0] == b.shape[0], "assertion failed: coeffs.len() == bases.len()"
+    out = np.zeros(12, dtype=np.uint64)
+    check(lib().zkb_msm_g1(_p(s), _p(b), s.shape[0], _p(out)))
+    return out
+
+
+def g1_sum(points_jac: np.ndarray) -> np.ndarray:
+    """Host-side fold of partial MSM results (the `results.iter().fold(identity, |a, b| a + b)` of best_multiexp,
+    applied to per-GPU shards)."""
+    p = np.ascontiguousarray(points_jac, dtype=np.uint64).reshape(-1, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    check(lib().zkb_g1_sum(_p(p), p.shape[0], _p(out)))
+    return out
+
+
+def g1_fixed_base_mul(scalars: np.ndarray) -> np.ndarray:
+    s = _fr(scalars, "scalars")
+    out = np.zeros((s.shape[0], 8), dtype=np.uint64)
+    check(lib().zkb_g1_fixed_base_mul(_p(s), s.shape[0], _p(out)))
+    return out
+
+
+# ---- halo2_proofs::poly::EvaluationDomain ------------------------------------------------------------------------------
+class EvaluationDomain:
+    """EvaluationDomain::<Fr>::new(j, k): j = cs.degree(), n = 2^k."""
+
+    def __init__(self, j: int, k: int):
+        self.k = k
+        self.n = 1 << k
+        self.quotient_poly_degree = j - 1
+        ek = k
+        while (1 << ek) < self.n * self.quotient_poly_degree:
+            ek += 1
+        self.extended_k = ek
+
+    def extended_len(self) -> int:
+        return 1 << self.extended_k
+
+    def get_omega(self) -> np.ndarray:
+        return omega(self.k)
+
+    def get_extended_omega(self) -> np.ndarray:
+        return omega(self.extended_k)
+
+    def lagrange_to_coeff(self, a: np.ndarray) -> np.ndarray:
+        v = np.array(_fr(a), copy=True)
+        assert v.shape[0] == self.n, "assertion failed: a.values.len() == 1 << self.k"
+        check(lib().zkb_lagrange_to_coeff(_p(v), self.k))
+        return v
+
+    def lagrange_to_coeff_batch(self, cols: list[np.ndarray]) -> list[np.ndarray]:
+        vs = [np.array(_fr(a), copy=True) for a in cols]
+        for v in vs:
+            assert v.shape[0] == self.n
+        ptrs = (u64p * len(vs))(*[_p(v) for v in vs])
+        check(lib().zkb_lagrange_to_coeff_batch(ptrs, len(vs), self.k))
+        return vs
+
+    def coeff_to_lagrange(self, a: np.ndarray) -> np.ndarray:
+        v = np.array(_fr(a), copy=True)
+        assert v.shape[0] == self.n
+        check(lib().zkb_coeff_to_lagrange(_p(v), self.k))
+        return v
+
+    def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
+        v = _fr(a)
+        assert v.shape[0] == self.n, "assertion failed: a.values.len() == 1 << self.k"
+        out = np.zeros((self.extended_len(), 4), dtype=np.uint64)
+        check(lib().zkb_coeff_to_extended(_p(v), _p(out), self.k, self.extended_k))
+        return out
+
+    def coeff_to_extended_batch(self, cols: list[np.ndarray]) -> list[np.ndarray]:
+        vs = [_fr(a) for a in cols]
+        for v in vs:
+            assert v.shape[0] == self.n
+        outs = [np.zeros((self.extended_len(), 4), dtype=np.uint64) for _ in vs]
+        pi = (u64p * len(vs))(*[_p(v) for v in vs])
+        po = (u64p * len(vs))(*[_p(o) for o in outs])
+        check(lib().zkb_coeff_to_extended_batch(pi, po, len(vs), self.k, self.extended_k))
+        return outs
+
+    def extended_to_coeff(self, a: np.ndarray) -> np.ndarray:
+        v = np.array(_fr(a), copy=True)
+        assert v.shape[0] == self.extended_len(), "assertion failed: a.values.len() == self.extended_len()"
+        check(lib().zkb_extended_to_coeff(_p(v), self.k, self.extended_k))
+        return v[: self.n * self.quotient_poly_degree]
+
+
+# ---- halo2_proofs::poly::kzg::commitment::ParamsKZG --------------------------------------------------------------------
+class ParamsKZG:
+    """The MSM-facing part of ParamsKZG: `g` (monomial SRS) and `g_lagrange`, kept resident in HBM."""
+
+    def __init__(self, k: int, g: np.ndarray, g_lagrange: np.ndarray | None = None):
+        self.k = k
+        self.n = 1 << k
+        g = np.ascontiguousarray(g, dtype=np.uint64).reshape(-1, 8)
+        assert g.shape[0] == self.n, "g must hold 2^k points"
+        self._h_g = ctypes.c_uint64(0)
+        check(lib().zkb_srs_register(_p(g), g.shape[0], ctypes.byref(self._h_g)))
+        self._h_gl = None
+        if g_lagrange is not None:
+            gl = np.ascontiguousarray(g_lagrange, dtype=np.uint64).reshape(-1, 8)
+            assert gl.shape[0] == self.n
+            self._h_gl = ctypes.c_uint64(0)
+            check(lib().zkb_srs_register(_p(gl), gl.shape[0], ctypes.byref(self._h_gl)))
+
+    def _commit(self, h, poly: np.ndarray) -> np.ndarray:
+        s = _fr(poly, "poly")
+        assert s.shape[0] <= self.n, "assertion failed: bases.len() >= scalars.len()"
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib().zkb_msm_g1_srs(h, _p(s), s.shape[0], _p(out)))
+        return out
+
+    def commit(self, poly: np.ndarray) -> np.ndarray:
+        """commit(&Polynomial<Fr, Coeff>, Blind) -> G1   (the blind is unused under KZG)"""
+        return self._commit(self._h_g, poly)
+
+    def commit_lagrange(self, poly: np.ndarray) -> np.ndarray:
+        """commit_lagrange(&Polynomial<Fr, LagrangeCoeff>, Blind) -> G1"""
+        if self._h_gl is None:
+            raise ValueError("g_lagrange was not supplied")
+        return self._commit(self._h_gl, poly)
+
+    def commit_batch(self, polys: list[np.ndarray], lagrange: bool = False) -> np.ndarray:
+        h = self._h_gl if lagrange else self._h_g
+        vs = [_fr(p) for p in polys]
+        n = vs[0].shape[0]
+        for v in vs:
+            assert v.shape[0] == n
+        ptrs = (u64p * len(vs))(*[_p(v) for v in vs])
+        out = np.zeros((len(vs), 12), dtype=np.uint64)
+        check(lib().zkb_msm_g1_srs_batch(h, ptrs, len(vs), n, _p(out)))
+        return out
+
+    def commit_range(self, offset: int, scalars: np.ndarray, lagrange: bool = False) -> np.ndarray:
+        """Partial commitment over srs[offset .. offset+len) — one GPU's shard of a point-range-sharded MSM."""
+        h = self._h_gl if lagrange else self._h_g
+        s = _fr(scalars)
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib().zkb_msm_g1_srs_range(h, offset, _p(s), s.shape[0], _p(out)))
+        return out
+
+    @property
+    def handle_g(self) -> int:
+        return self._h_g.value
+
+    @property
+    def handle_g_lagrange(self) -> int:
+        return self._h_gl.value if self._h_gl is not None else 0
+
+    def close(self) -> None:
+        for h in (self._h_g, self._h_gl):
+            if h is not None and h.value:
+                lib().zkb_srs_release(h)
+                h.value = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- measurement helpers ---------------------------------------------------------------------------------------------------
+class prof:
+    @staticmethod
+    def enable(on: bool = True) -> None:
+        check(lib().zkb_prof_enable(1 if on else 0))
+
+    @staticmethod
+    def reset() -> None:
+        check(lib().zkb_prof_reset())
+
+    @staticmethod
+    def get(name: str) -> tuple[float, int]:
+        ms = ctypes.c_double(0)
+        n = ctypes.c_uint64(0)
+        check(lib().zkb_prof_get(name.encode(), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
