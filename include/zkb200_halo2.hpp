@@ -1,0 +1,111 @@
+// zkb200_halo2.hpp — C++ host-side mirror of the halo2-axiom interface on the zksnap hot path, over the C ABI in
+// zkb200.h.  The reference's host language is Rust (absent from the build image), so this header is the compiled
+// host layer that mirrors the same names, argument meaning and error behaviour (a failed call throws, where the
+// Rust callers `.unwrap()` / `.expect()` — /root/reference/aggregator/src/wrapper.rs:107-108,137):
+//
+//   halo2_proofs::arithmetic::best_multiexp / best_fft
+//   halo2_proofs::poly::EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff}
+//   halo2_proofs::poly::kzg::commitment::ParamsKZG::{commit, commit_lagrange}
+//
+// Types are the in-memory layouts of halo2curves::bn256 (Montgomery limbs).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "zkb200.h"
+
+namespace halo2 {
+
+using Fr = std::array<uint64_t, 4>;        // bn256::Fr
+using G1Affine = std::array<uint64_t, 8>;  // bn256::G1Affine (x, y); identity (0, 0)
+using G1 = std::array<uint64_t, 12>;       // bn256::G1 (x, y, z) Jacobian
+
+inline void check(int rc, const char* what) {
+    if (rc != ZKB_OK) throw std::runtime_error(std::string(what) + ": " + zkb_last_error());
+}
+
+// arithmetic::best_multiexp(coeffs, bases) -> G1
+inline G1 best_multiexp(const std::vector<Fr>& coeffs, const std::vector<G1Affine>& bases) {
+    if (coeffs.size() != bases.size()) throw std::invalid_argument("assertion failed: coeffs.len() == bases.len()");
+    G1 out{};
+    check(zkb_msm_g1(coeffs.empty() ? nullptr : coeffs[0].data(), bases.empty() ? nullptr : bases[0].data(), coeffs.size(), out.data()),
+          "best_multiexp");
+    return out;
+}
+
+// arithmetic::best_fft(a, omega, log_n)
+inline void best_fft(std::vector<Fr>& a, const Fr& omega, uint32_t log_n) {
+    if (a.size() != (size_t(1) << log_n)) throw std::invalid_argument("assertion failed: a.len() == 1 << log_n");
+    check(zkb_ntt_fr(a[0].data(), omega.data(), log_n), "best_fft");
+}
+
+// poly::EvaluationDomain<Fr>
+class EvaluationDomain {
+   public:
+    EvaluationDomain(uint32_t j, uint32_t k) : k_(k), quotient_poly_degree_(j - 1) {
+        extended_k_ = k;
+        while ((uint64_t(1) << extended_k_) < (uint64_t(1) << k) * quotient_poly_degree_) ++extended_k_;
+    }
+    uint32_t k() const { return k_; }
+    uint32_t extended_k() const { return extended_k_; }
+    size_t extended_len() const { return size_t(1) << extended_k_; }
+    uint64_t get_quotient_poly_degree() const { return quotient_poly_degree_; }
+    Fr get_omega() const { Fr w; check(zkb_fr_omega(k_, w.data()), "get_omega"); return w; }
+    Fr get_extended_omega() const { Fr w; check(zkb_fr_omega(extended_k_, w.data()), "get_extended_omega"); return w; }
+
+    std::vector<Fr> lagrange_to_coeff(std::vector<Fr> a) const {
+        if (a.size() != (size_t(1) << k_)) throw std::invalid_argument("assertion failed: a.values.len() == 1 << self.k");
+        check(zkb_lagrange_to_coeff(a[0].data(), k_), "lagrange_to_coeff");
+        return a;
+    }
+    std::vector<Fr> coeff_to_extended(const std::vector<Fr>& a) const {
+        if (a.size() != (size_t(1) << k_)) throw std::invalid_argument("assertion failed: a.values.len() == 1 << self.k");
+        std::vector<Fr> out(extended_len());
+        check(zkb_coeff_to_extended(a[0].data(), out[0].data(), k_, extended_k_), "coeff_to_extended");
+        return out;
+    }
+    std::vector<Fr> extended_to_coeff(std::vector<Fr> a) const {
+        if (a.size() != extended_len()) throw std::invalid_argument("assertion failed: a.values.len() == self.extended_len()");
+        check(zkb_extended_to_coeff(a[0].data(), k_, extended_k_), "extended_to_coeff");
+        a.resize((size_t(1) << k_) * quotient_poly_degree_);
+        return a;
+    }
+
+   private:
+    uint32_t k_, extended_k_;
+    uint64_t quotient_poly_degree_;
+};
+
+// poly::kzg::commitment::ParamsKZG — the MSM-facing part: g and g_lagrange resident in HBM
+class ParamsKZG {
+   public:
+    ParamsKZG(uint32_t k, const std::vector<G1Affine>& g, const std::vector<G1Affine>& g_lagrange) : k_(k) {
+        if (g.size() != (size_t(1) << k) || g_lagrange.size() != g.size()) throw std::invalid_argument("SRS must hold 2^k points");
+        check(zkb_srs_register(g[0].data(), g.size(), &h_g_), "ParamsKZG (g)");
+        check(zkb_srs_register(g_lagrange[0].data(), g_lagrange.size(), &h_gl_), "ParamsKZG (g_lagrange)");
+    }
+    ParamsKZG(const ParamsKZG&) = delete;
+    ParamsKZG& operator=(const ParamsKZG&) = delete;
+    ~ParamsKZG() {
+        if (h_g_) zkb_srs_release(h_g_);
+        if (h_gl_) zkb_srs_release(h_gl_);
+    }
+    uint32_t k() const { return k_; }
+    // commit(&Polynomial<Fr, Coeff>, Blind) — the blind is unused under KZG
+    G1 commit(const std::vector<Fr>& poly) const { return msm(h_g_, poly); }
+    G1 commit_lagrange(const std::vector<Fr>& poly) const { return msm(h_gl_, poly); }
+
+   private:
+    G1 msm(uint64_t h, const std::vector<Fr>& poly) const {
+        G1 out{};
+        check(zkb_msm_g1_srs(h, poly.empty() ? nullptr : poly[0].data(), poly.size(), out.data()), "commit");
+        return out;
+    }
+    uint32_t k_;
+    uint64_t h_g_ = 0, h_gl_ = 0;
+};
+
+}  // namespace halo2

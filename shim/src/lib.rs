@@ -1,0 +1,125 @@
+//! zkb200-sys: the Rust side of the drop-in boundary (include/zkb200.h).
+//!
+//! `halo2curves::bn256::{Fr, Fq}` are `#[repr(transparent)]`-like wrappers over `[u64; 4]` holding Montgomery
+//! limbs, `G1Affine { x, y }` is 64 bytes and `G1 { x, y, z }` 96 bytes, so slices of them are passed to C as plain
+//! `*const u64` without any conversion.  Every wrapper keeps the exact signature of the halo2-axiom function it
+//! replaces and panics on a non-zero status, matching the `.unwrap()` / `.expect()` convention of the callers
+//! (/root/reference/aggregator/src/wrapper.rs:107-108,137).  There is no CPU fallback behind these calls.
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S BUILD IMAGE (no cargo/rustc).  INTEGRATION.md shows the `[patch]` of
+//! halo2-axiom that routes `best_multiexp` / `best_fft` / `EvaluationDomain` here.
+
+use halo2curves::bn256::{Fr, G1Affine, G1};
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[allow(non_camel_case_types)]
+type size_t = usize;
+
+extern "C" {
+    pub fn zkb_init(devices: *const c_int, ndev: c_int) -> c_int;
+    pub fn zkb_shutdown();
+    pub fn zkb_last_error() -> *const c_char;
+    pub fn zkb_msm_g1(scalars: *const u64, bases: *const u64, n: size_t, out_jac: *mut u64) -> c_int;
+    pub fn zkb_srs_register(bases: *const u64, n: size_t, handle: *mut u64) -> c_int;
+    pub fn zkb_srs_release(handle: u64) -> c_int;
+    pub fn zkb_msm_g1_srs(handle: u64, scalars: *const u64, n: size_t, out_jac: *mut u64) -> c_int;
+    pub fn zkb_msm_g1_srs_batch(handle: u64, scalars: *const *const u64, ncols: size_t, n: size_t, out_jac: *mut u64) -> c_int;
+    pub fn zkb_ntt_fr(a: *mut u64, omega: *const u64, log_n: u32) -> c_int;
+    pub fn zkb_ntt_fr_batch(cols: *const *mut u64, ncols: size_t, omega: *const u64, log_n: u32) -> c_int;
+    pub fn zkb_lagrange_to_coeff(a: *mut u64, k: u32) -> c_int;
+    pub fn zkb_coeff_to_extended(input: *const u64, out: *mut u64, k: u32, extended_k: u32) -> c_int;
+    pub fn zkb_extended_to_coeff(a: *mut u64, k: u32, extended_k: u32) -> c_int;
+    pub fn zkb_msm_g1_srs_dev(handle: u64, offset: size_t, d_scalars: *const c_void, n: size_t, out_jac: *mut u64, stream: *mut c_void) -> c_int;
+}
+
+#[inline]
+fn check(rc: c_int, what: &str) {
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(zkb_last_error()) }.to_string_lossy().into_owned();
+        panic!("zkb200 {what} failed ({rc}): {msg}");
+    }
+}
+
+const _: () = assert!(std::mem::size_of::<Fr>() == 32);
+const _: () = assert!(std::mem::size_of::<G1Affine>() == 64);
+const _: () = assert!(std::mem::size_of::<G1>() == 96);
+
+/// Drop-in body for `halo2_proofs::arithmetic::best_multiexp::<G1Affine>`.
+pub fn best_multiexp(coeffs: &[Fr], bases: &[G1Affine]) -> G1 {
+    assert_eq!(coeffs.len(), bases.len());
+    let mut out = std::mem::MaybeUninit::<G1>::uninit();
+    let rc = unsafe { zkb_msm_g1(coeffs.as_ptr() as *const u64, bases.as_ptr() as *const u64, coeffs.len(), out.as_mut_ptr() as *mut u64) };
+    check(rc, "best_multiexp");
+    unsafe { out.assume_init() }
+}
+
+/// Drop-in body for `halo2_proofs::arithmetic::best_fft::<Fr, Fr>`.
+pub fn best_fft(a: &mut [Fr], omega: Fr, log_n: u32) {
+    assert_eq!(a.len(), 1 << log_n);
+    let rc = unsafe { zkb_ntt_fr(a.as_mut_ptr() as *mut u64, &omega as *const Fr as *const u64, log_n) };
+    check(rc, "best_fft");
+}
+
+/// An SRS (`ParamsKZG.g` or `ParamsKZG.g_lagrange`) resident in HBM for the life of the params.
+pub struct ResidentSrs {
+    handle: u64,
+    len: usize,
+}
+
+impl ResidentSrs {
+    pub fn new(bases: &[G1Affine]) -> Self {
+        let mut handle = 0u64;
+        check(unsafe { zkb_srs_register(bases.as_ptr() as *const u64, bases.len(), &mut handle) }, "srs_register");
+        Self { handle, len: bases.len() }
+    }
+    /// `ParamsKZG::commit` / `commit_lagrange`: `best_multiexp(&poly, &bases[..poly.len()])`.
+    pub fn commit(&self, poly: &[Fr]) -> G1 {
+        assert!(poly.len() <= self.len);
+        let mut out = std::mem::MaybeUninit::<G1>::uninit();
+        check(unsafe { zkb_msm_g1_srs(self.handle, poly.as_ptr() as *const u64, poly.len(), out.as_mut_ptr() as *mut u64) }, "commit");
+        unsafe { out.assume_init() }
+    }
+    /// The prover's per-column commit loop in one call.
+    pub fn commit_batch(&self, polys: &[&[Fr]]) -> Vec<G1> {
+        if polys.is_empty() {
+            return vec![];
+        }
+        let n = polys[0].len();
+        assert!(polys.iter().all(|p| p.len() == n) && n <= self.len);
+        let ptrs: Vec<*const u64> = polys.iter().map(|p| p.as_ptr() as *const u64).collect();
+        let mut out = Vec::<G1>::with_capacity(polys.len());
+        check(unsafe { zkb_msm_g1_srs_batch(self.handle, ptrs.as_ptr(), polys.len(), n, out.as_mut_ptr() as *mut u64) }, "commit_batch");
+        unsafe { out.set_len(polys.len()) };
+        out
+    }
+}
+
+impl Drop for ResidentSrs {
+    fn drop(&mut self) {
+        unsafe { zkb_srs_release(self.handle) };
+    }
+}
+
+/// `EvaluationDomain::lagrange_to_coeff` body (in place on the polynomial's values).
+pub fn lagrange_to_coeff(values: &mut [Fr], k: u32) {
+    assert_eq!(values.len(), 1 << k);
+    check(unsafe { zkb_lagrange_to_coeff(values.as_mut_ptr() as *mut u64, k) }, "lagrange_to_coeff");
+}
+
+/// `EvaluationDomain::coeff_to_extended` body: returns the 2^extended_k coset evaluations.
+pub fn coeff_to_extended(values: &[Fr], k: u32, extended_k: u32) -> Vec<Fr> {
+    assert_eq!(values.len(), 1 << k);
+    let mut out = Vec::<Fr>::with_capacity(1 << extended_k);
+    check(unsafe { zkb_coeff_to_extended(values.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64, k, extended_k) }, "coeff_to_extended");
+    unsafe { out.set_len(1 << extended_k) };
+    out
+}
+
+/// `EvaluationDomain::extended_to_coeff` body: in place, then truncated to n * quotient_poly_degree.
+pub fn extended_to_coeff(mut values: Vec<Fr>, k: u32, extended_k: u32, quotient_poly_degree: u64) -> Vec<Fr> {
+    assert_eq!(values.len(), 1 << extended_k);
+    check(unsafe { zkb_extended_to_coeff(values.as_mut_ptr() as *mut u64, k, extended_k) }, "extended_to_coeff");
+    values.truncate(((1u64 << k) * quotient_poly_degree) as usize);
+    values
+}
