@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "curve.cuh"
+#include "field29.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "ntt_plan.hpp"
@@ -45,6 +46,30 @@ EMU_EXPORT void zkb_emu_vec_op(int field, int op, const uint64_t* a, const uint6
             Fq r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
             f_to_u64(r, o + 4 * i);
         }
+    }
+}
+
+// 29-bit-limb arithmetic: op 0: from29(mul29(to29 a, to29 b)); 1: lazy add; 2: sub29<K=34> + carry; 3: chain
+// ((a*b) - a + b) * (a - b) exercising lazy inputs to mul29.  field: 0 Fr, 1 Fq
+template <class P29, class F>
+static F emu29_one(int op, const F& x, const F& y) {
+    F29<P29> a = to29<P29>(x), b = to29<P29>(y);
+    F29<P29> r;
+    if (op == 0) r = mul29<P29>(a, b);
+    else if (op == 1) r = add29<P29>(a, b);
+    else if (op == 2) r = carry29<P29>(sub29<P29, 34>(a, b));
+    else {
+        F29<P29> ab = mul29<P29>(a, b);                          // < 7.1 p
+        F29<P29> t = add29<P29>(carry29<P29>(sub29<P29, 34>(ab, a)), b);   // < 7.1p + 34p + 32p, lazy limbs
+        F29<P29> u = carry29<P29>(sub29<P29, 34>(a, b));         // < 66 p
+        r = mul29<P29>(carry29<P29>(t), u);                      // product < 74*66 p^2 = 4884 p^2 > 169 p^2 * 28: result < 30 p
+    }
+    return from29<P29>(r);
+}
+EMU_EXPORT void zkb_emu_vec_op29(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        if (field == 0) f_to_u64(emu29_one<Fr29Params>(op, fr_from_u64(a + 4 * i), fr_from_u64(b + 4 * i)), o + 4 * i);
+        else f_to_u64(emu29_one<Fq29Params>(op, fq_from_u64(a + 4 * i), fq_from_u64(b + 4 * i)), o + 4 * i);
     }
 }
 

@@ -26,23 +26,25 @@ __global__ void __launch_bounds__(128) g1_fixed_base_mul_kernel(const FixedBaseA
     g1_fixed_base_mul_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-// Integer-pipe peak probe: 8 independent 32x32+64 multiply-add chains per thread (IMAD.WIDE.U32), no memory traffic.
+// Integer-pipe peak probe: 8 independent chains per thread of a_j = a_j * y + x (IMAD, multiplicand is the running
+// value so ptxas cannot hoist the product).  A plain IMAD.WIDE.U32 issues at the same 2 cycles per warp instruction
+// (tools/ubench.cu, profiles/r1_ubench.txt); the carry-chained IMAD.WIDE.U32.X costs 4.
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint64_t* out, uint32_t x, uint32_t y, int iters) {
-    uint64_t acc[8];
+    uint32_t a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = threadIdx.x + j;
-    x += threadIdx.x;
+    for (int j = 0; j < 8; ++j) a[j] = threadIdx.x + j;
+    y |= 1;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x), "r"(y));
+            for (int j = 0; j < 8; ++j) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(y), "r"(x));
         }
     }
-    uint64_t r = 0;
+    uint32_t r = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r ^= acc[j];
-    if (r == 0x123456789abcdefull) out[0] = r;  // keeps the chains alive
+    for (int j = 0; j < 8; ++j) r ^= a[j];
+    if (r == 0x12345678u) out[0] = r;  // keeps the chains alive
 }
 
 int measure_imad_peak(double* macs_per_s) {

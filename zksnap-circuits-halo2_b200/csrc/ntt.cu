@@ -8,7 +8,7 @@ struct CtaBarrier {
 };
 
 template <int LOGR>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(const NttPassArgs a) {
+__global__ void __launch_bounds__(128, 4) ntt_pass_kernel(const NttPassArgs a) {
     extern __shared__ uint4 ntt_smem[];
     CtaBarrier bar;
     ntt_cta_program<LOGR>(a, ntt_smem, threadIdx.x, blockDim.x, (uint64_t)blockIdx.x, blockIdx.y, bar);

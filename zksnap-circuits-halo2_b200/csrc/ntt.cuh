@@ -194,9 +194,9 @@ ZKB_HD void ntt_phase_round(const NttPassArgs& a, uint4* sm, uint32_t tid, uint3
     const uint32_t tw_step = LOGR - log_l;          // omega_L = omega_R^(R/L)
 
     for (uint32_t g = tid; g < groups; g += nthreads) {
-        uint32_t u, c;
-        if (!a.is_final) { u = g >> a.log_t; c = g & (T - 1); }
-        else { c = g / (R >> t); u = g % (R >> t); }
+        // column fastest in both layouts: 8 adjacent threads touch 8 adjacent columns, i.e. adjacent uint4 slots
+        // (strided layout) or slots R+1 apart (final layout, R+1 = 1 mod 8): conflict-free in every round
+        const uint32_t u = g >> a.log_t, c = g & (T - 1);
         uint32_t b = u >> log_sub, i = u & ((1u << log_sub) - 1);
         uint32_t p0 = (b << log_l) + i;
         if (t == 3) {

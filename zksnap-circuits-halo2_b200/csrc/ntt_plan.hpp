@@ -28,7 +28,7 @@ inline NttGeometry ntt_geometry(uint32_t log_n) {
     }
     g.tw_h = (log_n + 1) / 2;
     for (uint32_t p = 0; p < g.npass; ++p) {
-        uint32_t want = g.lr[p] >= 11 ? 0 : 11 - g.lr[p];  // R*T = 2048 elements per CTA
+        uint32_t want = g.lr[p] >= 10 ? 0 : 10 - g.lr[p];  // R*T = 1024 elements (32 KiB) per CTA, 4 CTAs per SM
         uint32_t cap;
         if (p + 1 < g.npass) {  // strided pass: T <= S_p
             cap = 0;
@@ -44,7 +44,7 @@ inline NttGeometry ntt_geometry(uint32_t log_n) {
 inline uint32_t ntt_cta_threads(const NttGeometry& g, uint32_t p) {
     uint32_t e = 1u << (g.lr[p] + g.log_t[p]);
     uint32_t t = e / 8;
-    return t < 32 ? 32 : (t > 256 ? 256 : t);
+    return t < 32 ? 32 : (t > 128 ? 128 : t);
 }
 inline uint64_t ntt_cta_count(const NttGeometry& g, uint32_t p) {
     return (1ull << g.log_n) >> (g.lr[p] + g.log_t[p]);
