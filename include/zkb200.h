@@ -73,6 +73,14 @@ int zkb_msm_g1_srs_range(uint64_t handle, size_t offset, const uint64_t* scalars
 /* ncols commitments against the same SRS (the prover's per-column commit loop).  out: ncols x 12. */
 int zkb_msm_g1_srs_batch(uint64_t handle, const uint64_t* const* scalars, size_t ncols, size_t n, uint64_t* out_jac);
 
+/* SRS window table: T[w][i] = 2^(c*w) * P_i for every digit window w, kept in HBM next to the bases (W x the SRS size,
+ * e.g. 12 x 256 MiB at k = 22).  With it all windows of all scalars share one bucket set, so a commit needs one
+ * bucket reduction and no Horner fold.  Built lazily on the first commit against the handle (default on; switch with
+ * zkb_srs_set_precompute or ZKB_SRS_PRECOMPUTE=0); zkb_srs_precompute forces the build now and reports the window
+ * bits / bytes used (0 / 0 when disabled or when the table would not fit).  Results are identical either way. */
+int zkb_srs_set_precompute(int on);
+int zkb_srs_precompute(uint64_t handle, uint32_t* window_bits, uint64_t* table_bytes);
+
 /* Host-side combination of partial results (multi-GPU point-range shards): out = sum of `count` Jacobian points. */
 int zkb_g1_sum(const uint64_t* points_jac, size_t count, uint64_t out_jac[12]);
 

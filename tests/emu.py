@@ -54,11 +54,12 @@ def ntt(a, log_n, omega, in_scale3=None, out_scale3=None, cols=1):
     return out if cols > 1 else out[0]
 
 
-def msm(scalars, bases, c=0, chunk=0):
+def msm(scalars, bases, c=0, chunk=0, table=False):
     s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
     b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
     out = np.zeros(12, dtype=np.uint64)
-    rc = lib().zkb_emu_msm(_p(s), _p(b), ctypes.c_uint64(s.shape[0]), ctypes.c_uint32(c), ctypes.c_uint32(chunk), _p(out))
+    fn = lib().zkb_emu_msm_table if table else lib().zkb_emu_msm
+    rc = fn(_p(s), _p(b), ctypes.c_uint64(s.shape[0]), ctypes.c_uint32(c), ctypes.c_uint32(chunk), _p(out))
     assert rc == 0
     return out
 

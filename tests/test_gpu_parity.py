@@ -197,7 +197,9 @@ def test_msm_witness_like_distribution(oracle):
     assert (zkb.best_multiexp(s, b) == oracle.best_multiexp(s, b)).all()
 
 
-def test_params_kzg_commit_and_range_split(oracle):
+@pytest.mark.parametrize("precompute", [1, 0])
+def test_params_kzg_commit_and_range_split(oracle, precompute):
+    zkb.lib().zkb_srs_set_precompute(precompute)
     k = 12
     n = 1 << k
     _, g = _bases_known_dlog(n, 21)
@@ -217,6 +219,34 @@ def test_params_kzg_commit_and_range_split(oracle):
     # point-range shards folded on the host == single MSM (multi-GPU invariance)
     parts = [params.commit_range(o, poly[o:o + n // 4]) for o in range(0, n, n // 4)]
     assert (zkb.g1_sum(np.stack(parts)) == c1).all()
+    import ctypes
+    cb, tb = ctypes.c_uint32(), ctypes.c_uint64()
+    zkb.lib().zkb_srs_precompute(params.handle_g, ctypes.byref(cb), ctypes.byref(tb))
+    assert (cb.value > 0) == bool(precompute)
+    params.close()
+    zkb.lib().zkb_srs_set_precompute(1)
+
+
+@pytest.mark.parametrize("n", [64, 100, 1 << 10, 5000, 1 << 14])
+def test_srs_table_path_vs_oracle(oracle, n):
+    """Commit through the SRS window table (one bucket set for all windows) vs the oracle, incl. edge inputs."""
+    zkb.lib().zkb_srs_set_precompute(1)
+    _, g = _bases_known_dlog(n, 70 + n)
+    g[3] = 0                       # identity base
+    g[5] = g[4]                    # repeated base
+    s = random_field(n, 71 + n)
+    s[0] = 0
+    s[1] = mont([1])[0]
+    s[2] = mont([R.FR - 1])[0]
+    s[5] = s[4]
+    k = max(6, (n - 1).bit_length())
+    gp = np.zeros((1 << k, 8), dtype=np.uint64)
+    gp[:n] = g
+    params = zkb.ParamsKZG(k, gp)
+    assert (params.commit(s) == oracle.best_multiexp(s, g)).all()
+    assert (params.commit(s[: n // 2]) == oracle.best_multiexp(s[: n // 2], g[: n // 2])).all()
+    off = n // 3
+    assert (params.commit_range(off, s[off:]) == oracle.best_multiexp(s[off:], g[off:])).all()
     params.close()
 
 

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--c", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--dist", default="U", choices=["U", "W", "E"])
+    ap.add_argument("--no-table", action="store_true")
     args = ap.parse_args()
     import torch
 
@@ -45,6 +46,7 @@ def main():
     zkb.prof.enable(True)
     if args.op == "msm":
         lib.zkb_msm_set_params(args.c, args.chunk)
+        lib.zkb_srs_set_precompute(0 if args.no_table else 1)
         s = random_field(n, 1)
         if args.dist == "E":
             s[:] = s[0]
@@ -76,6 +78,9 @@ def main():
         cb, nw, ch = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
         lib.zkb_msm_get_params(n, ctypes.byref(cb), ctypes.byref(nw), ctypes.byref(ch))
         res.update(c=cb.value, windows=nw.value, chunk=ch.value, dist=args.dist)
+        tc, tb = ctypes.c_uint32(), ctypes.c_uint64()
+        lib.zkb_srs_precompute(params.handle_g, ctypes.byref(tc), ctypes.byref(tb))
+        res.update(table_c=tc.value, table_GiB=tb.value / 2**30)
         for name in ("msm_digits", "msm_sort", "msm_accumulate", "msm_reduce"):
             ms, k = zkb.prof.get(name)
             res[name] = ms / max(k, 1)

@@ -52,6 +52,8 @@ def load() -> ctypes.CDLL:
         "zkb_msm_g1_srs_range": [u64, sz, u64p, sz, u64p],
         "zkb_msm_g1_srs_batch": [u64, u64pp, sz, sz, u64p],
         "zkb_g1_sum": [u64p, sz, u64p],
+        "zkb_srs_set_precompute": [ci],
+        "zkb_srs_precompute": [u64, ctypes.POINTER(u32), ctypes.POINTER(u64)],
         "zkb_g1_fixed_base_mul": [u64p, sz, u64p],
         "zkb_ntt_fr": [u64p, u64p, u32],
         "zkb_ntt_fr_batch": [u64pp, sz, u64p, u32],

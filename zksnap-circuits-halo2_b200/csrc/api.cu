@@ -1,5 +1,6 @@
 // api.cu — the C ABI of libzkb200.so (include/zkb200.h): context, SRS registry, host-buffer and device-buffer
 // entry points.  No CPU fallback lives here: every compute call requires an initialised CUDA device.
+#include <cstdlib>
 #include <cstring>
 
 #include "msm_host.hpp"
@@ -119,7 +120,45 @@ static Fr fr_pow2_inv_host(uint32_t k) {  // (2^k)^-1
 struct Srs {
     DevBuf bases;
     size_t n = 0;
+    // window table T[w][i] = 2^(c w) P_i, built lazily on the first commit (kept for the life of the handle)
+    DevBuf table;
+    uint32_t table_c = 0, table_nwin = 0;
+    bool table_failed = false;
 };
+static int g_precompute = -1;  // -1: read ZKB_SRS_PRECOMPUTE on first use (default on), 0 off, 1 on
+
+static bool precompute_enabled() {
+    if (g_precompute < 0) {
+        const char* e = getenv("ZKB_SRS_PRECOMPUTE");
+        g_precompute = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_precompute == 1;
+}
+
+// Build (once) the window table of an SRS; returns false when disabled or when it does not fit comfortably in HBM.
+static bool srs_table_ready(Srs* s, cudaStream_t stream) {
+    if (s->table_c) return true;
+    if (!precompute_enabled() || s->table_failed || s->n < 64 || ctx().msm_c_override) return false;
+    MsmGeometry g = msm_geometry(s->n, 0, 0, true);
+    size_t bytes = (size_t)g.nwin * s->n * 64;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 3 || (uint64_t)g.nwin * s->n >= (1ull << 31)) {
+        cudaGetLastError();
+        s->table_failed = true;
+        return false;
+    }
+    if (s->table.reserve(bytes) != ZKB_OK) { s->table_failed = true; return false; }
+    if (srs_table_build(s->bases.as<uint4>(), s->n, g.c, g.nwin, s->table.as<uint4>(), stream) != ZKB_OK ||
+        cudaStreamSynchronize(stream) != cudaSuccess) {
+        cudaGetLastError();
+        s->table.release();
+        s->table_failed = true;
+        return false;
+    }
+    s->table_c = g.c;
+    s->table_nwin = g.nwin;
+    return true;
+}
 static std::map<uint64_t, Srs*>& srs_map() {
     static std::map<uint64_t, Srs*> m;
     return m;
@@ -238,14 +277,22 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
     return ZKB_OK;
 }
 
-static int msm_with_bases(const uint4* d_bases, const uint64_t* scalars, size_t n, uint64_t out[12]) {
+// MSM of device scalars against srs[offset .. offset+n), through the window table when available
+static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t out[12]) {
+    if (srs_table_ready(srs, stream)) {
+        MsmTable t{srs->table.as<uint4>() + 4 * offset, srs->n, srs->table_c, srs->table_nwin};
+        return msm_run(d_scalars, nullptr, n, stream, out, &t);
+    }
+    return msm_run(d_scalars, srs->bases.as<uint4>() + 4 * offset, n, stream, out);
+}
+
+static int upload_scalars(const uint64_t* scalars, size_t n) {
     Ctx& c = ctx();
     HostIo& h = hostio();
-    if (n == 0) { msm_identity_out(out); return ZKB_OK; }
     ZKB_TRY(check_ptr(scalars, "scalars"));
     ZKB_TRY(h.scalars.reserve(n * 32));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
-    return msm_run(h.scalars.as<uint4>(), d_bases, n, c.stream, out);
+    return ZKB_OK;
 }
 
 static int find_srs(uint64_t handle, Srs** out) {
@@ -301,7 +348,7 @@ void zkb_shutdown(void) {
     if (!c.inited) return;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
-    for (auto& kv : srs_map()) { kv.second->bases.release(); delete kv.second; }
+    for (auto& kv : srs_map()) { kv.second->bases.release(); kv.second->table.release(); delete kv.second; }
     srs_map().clear();
     ntt_clear_plans();
     msm_release_workspace();
@@ -327,7 +374,8 @@ int zkb_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_
     HostIo& h = hostio();
     ZKB_TRY(h.bases.reserve(n * 64));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, bases, n * 64, cudaMemcpyHostToDevice, ctx().stream));
-    return msm_with_bases(h.bases.as<uint4>(), scalars, n, out_jac);
+    ZKB_TRY(upload_scalars(scalars, n));
+    return msm_run(h.scalars.as<uint4>(), h.bases.as<uint4>(), n, ctx().stream, out_jac);
 }
 
 int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle) {
@@ -355,6 +403,7 @@ int zkb_srs_release(uint64_t handle) {
     cudaSetDevice(ctx().device);
     cudaDeviceSynchronize();
     s->bases.release();
+    s->table.release();
     delete s;
     srs_map().erase(handle);
     return ZKB_OK;
@@ -370,7 +419,9 @@ int zkb_msm_g1_srs_range(uint64_t handle, size_t offset, const uint64_t* scalars
         set_error("MSM range [%zu, %zu) exceeds the registered SRS length %zu", offset, offset + n, s->n);
         return ZKB_ERR_ARG;
     }
-    return msm_with_bases(s->bases.as<uint4>() + 4 * offset, scalars, n, out_jac);
+    if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
+    ZKB_TRY(upload_scalars(scalars, n));
+    return msm_srs_dev(s, offset, hostio().scalars.as<uint4>(), n, ctx().stream, out_jac);
 }
 
 int zkb_msm_g1_srs(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
@@ -393,7 +444,23 @@ int zkb_msm_g1_srs_dev(uint64_t handle, size_t offset, const void* d_scalars, si
     ZKB_TRY(find_srs(handle, &s));
     if (offset > s->n || n > s->n - offset) { set_error("MSM range exceeds the registered SRS length %zu", s->n); return ZKB_ERR_ARG; }
     if (n) ZKB_TRY(check_ptr(d_scalars, "d_scalars"));
-    return msm_run(reinterpret_cast<const uint4*>(d_scalars), s->bases.as<uint4>() + 4 * offset, n, (cudaStream_t)stream, out_jac);
+    return msm_srs_dev(s, offset, reinterpret_cast<const uint4*>(d_scalars), n, (cudaStream_t)stream, out_jac);
+}
+
+int zkb_srs_set_precompute(int on) {
+    g_precompute = on ? 1 : 0;
+    return ZKB_OK;
+}
+
+int zkb_srs_precompute(uint64_t handle, uint32_t* window_bits, uint64_t* table_bytes) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    bool ok = srs_table_ready(s, ctx().stream);
+    if (window_bits) *window_bits = ok ? s->table_c : 0;
+    if (table_bytes) *table_bytes = ok ? (uint64_t)s->table_nwin * s->n * 64 : 0;
+    return ZKB_OK;
 }
 
 int zkb_g1_sum(const uint64_t* points_jac, size_t count, uint64_t out_jac[12]) {

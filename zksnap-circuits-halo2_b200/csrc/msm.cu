@@ -22,6 +22,10 @@ __global__ void __launch_bounds__(128) msm_sum_groups_kernel(const MsmSumArgs a)
     msm_sum_groups_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+__global__ void __launch_bounds__(128) srs_table_kernel(const SrsTableArgs a) {
+    srs_table_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 __global__ void __launch_bounds__(128) g1_fixed_base_mul_kernel(const FixedBaseArgs a) {
     g1_fixed_base_mul_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -85,6 +89,18 @@ int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cuda
     return ZKB_OK;
 }
 
+// rows 1..W-1 of the SRS window table: row w = 2^c * row (w-1); row 0 is a copy of the bases
+int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin, uint4* d_table, cudaStream_t s) {
+    ZKB_CUDA_TRY(cudaMemcpyAsync(d_table, d_bases, n * 64, cudaMemcpyDeviceToDevice, s));
+    for (uint32_t w = 1; w < nwin; ++w) {
+        SrsTableArgs a{d_table + 4 * n * (uint64_t)(w - 1), d_table + 4 * n * (uint64_t)w, n, c};
+        srs_table_kernel<<<blocks_for(n, 128), 128, 0, s>>>(a);
+        count_launch();
+        ZKB_CUDA_TRY(cudaGetLastError());
+    }
+    return ZKB_OK;
+}
+
 MsmWorkspace& msm_workspace() {
     static MsmWorkspace w;
     return w;
@@ -120,11 +136,13 @@ static void xyzz_to_out(const XYZZ& p, uint64_t out[12]) {
 
 void msm_identity_out(uint64_t out[12]) { xyzz_to_out(XYZZ::identity(), out); }
 
-int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t out_jac[12]) {
+int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t out_jac[12],
+            const MsmTable* table) {
     if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
     Ctx& c = ctx();
     MsmWorkspace& w = msm_workspace();
-    const MsmGeometry g = msm_geometry(n, c.msm_c_override, c.msm_chunk_override);
+    const MsmGeometry g = table ? msm_geometry(n, table->c, c.msm_chunk_override, true)
+                                : msm_geometry(n, c.msm_c_override, c.msm_chunk_override);
     const uint64_t total = (uint64_t)g.nwin * n;
     if (total >= (1ull << 31)) { set_error("MSM too large for 32-bit sort indices: n=%zu windows=%u", (size_t)n, g.nwin); return ZKB_ERR_ARG; }
 
@@ -147,7 +165,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_TRY(w.pv[i].reserve(2 * t0 * 128));
     }
     const uint64_t J0 = 1ull << (g.c - 1 - g.log_m);
-    for (int i = 0; i < 2; ++i) ZKB_TRY(w.seg[i].reserve((size_t)g.nwin * J0 * 128));
+    for (int i = 0; i < 2; ++i) ZKB_TRY(w.seg[i].reserve((size_t)g.bucket_sets * J0 * 128));
     if (!w.h_sums) ZKB_CUDA_TRY(cudaMallocHost(&w.h_sums, 64 * 128));
 
     // ---- 1. digits
@@ -156,7 +174,9 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         MsmDigitArgs a{};
         a.scalars = d_scalars; a.n = n; a.c = g.c; a.nwin = g.nwin;
         a.keys = w.keys[0].as<uint32_t>(); a.vals = w.vals[0].as<uint32_t>();
-        a.invalid_key = g.invalid_key; a.index_base = 0;
+        a.invalid_key = g.invalid_key;
+        a.table_mode = table ? 1 : 0;
+        a.row_stride = table ? table->row_stride : 0;
         msm_digits_kernel<<<blocks_for(n, 256), 256, 0, s>>>(a);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
@@ -183,7 +203,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             const bool last = level > 0 && count <= g.last_max;
             a.keys = level == 0 ? sk : w.pk[pp ^ 1].as<uint32_t>();
             a.vals = sv;
-            a.bases = d_bases;
+            a.bases = table ? table->rows : d_bases;
             a.pin = w.pv[pp ^ 1].as<uint4>();
             a.count = count;
             a.chunk = last ? (uint32_t)count : (level == 0 ? g.chunk0 : g.chunk_up);
@@ -208,17 +228,17 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
     {
         ProfScope prof("msm_reduce", s);
         MsmReduceArgs r{};
-        r.buckets = w.buckets.as<uint4>(); r.c = g.c; r.nwin = g.nwin; r.log_m = g.log_m;
+        r.buckets = w.buckets.as<uint4>(); r.c = g.c; r.nwin = g.bucket_sets; r.log_m = g.log_m;
         r.seg_out = w.seg[0].as<uint4>();
         uint64_t J = J0;
-        msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.nwin * J, 128), 128, 0, s>>>(r);
+        msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.bucket_sets * J, 128), 128, 0, s>>>(r);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
         int cur = 0;
         while (J > 1) {
             uint32_t grp = J >= g.sum_group ? g.sum_group : (uint32_t)J;
             uint64_t Jn = J / grp;
-            MsmSumArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), (uint64_t)g.nwin * Jn, grp};
+            MsmSumArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), (uint64_t)g.bucket_sets * Jn, grp};
             msm_sum_groups_kernel<<<blocks_for(sa.out_count, 128), 128, 0, s>>>(sa);
             count_launch();
             ZKB_CUDA_TRY(cudaGetLastError());
@@ -228,11 +248,11 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         sums = w.seg[cur].as<uint4>();
     }
     // ---- 5. window sums to the host, Horner + normalisation there
-    ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, sums, (size_t)g.nwin * 128, cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, sums, (size_t)g.bucket_sets * 128, cudaMemcpyDeviceToHost, s));
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
     XYZZ hs[64];
-    for (uint32_t i = 0; i < g.nwin; ++i) hs[i] = XYZZ::load(reinterpret_cast<const uint4*>(w.h_sums) + 8 * i);
-    XYZZ res = msm_combine_windows(hs, g.nwin, g.c);
+    for (uint32_t i = 0; i < g.bucket_sets; ++i) hs[i] = XYZZ::load(reinterpret_cast<const uint4*>(w.h_sums) + 8 * i);
+    XYZZ res = msm_combine_windows(hs, g.bucket_sets, g.c);
     xyzz_to_out(res, out_jac);
     return ZKB_OK;
 }

@@ -31,8 +31,9 @@ struct MsmDigitArgs {
     uint32_t nwin;         // W, W*c >= 255
     uint32_t* keys;        // [W*n], window-major
     uint32_t* vals;
-    uint32_t invalid_key;  // W << (c-1)
-    uint32_t index_base;   // added to the point index (for range-sharded bases)
+    uint32_t invalid_key;  // number of buckets: W << (c-1), or 1 << (c-1) in table mode
+    uint32_t table_mode;   // 1: bases are the precomputed rows T[w][i] = 2^(c w) P_i, all windows share one bucket set
+    uint64_t row_stride;   // table mode: points per row (the registered SRS length)
 };
 
 ZKB_HD uint32_t msm_extract_bits(const Fr& s, uint32_t bit, uint32_t c) {  // c <= 24
@@ -53,9 +54,16 @@ ZKB_HD void msm_digits_thread(const MsmDigitArgs& a, uint64_t i) {
         uint32_t neg = v > half;
         uint32_t mag = neg ? (1u << a.c) - v : v;
         carry = neg;
-        uint32_t key = mag ? (w << (a.c - 1)) + (mag - 1) : a.invalid_key;
+        uint32_t key, idx;
+        if (a.table_mode) {
+            key = mag ? mag - 1 : a.invalid_key;
+            idx = (uint32_t)((uint64_t)w * a.row_stride + i);
+        } else {
+            key = mag ? (w << (a.c - 1)) + (mag - 1) : a.invalid_key;
+            idx = (uint32_t)i;
+        }
         a.keys[(uint64_t)w * a.n + i] = key;
-        a.vals[(uint64_t)w * a.n + i] = (uint32_t)(i + a.index_base) | (neg << 31);
+        a.vals[(uint64_t)w * a.n + i] = idx | (neg << 31);
     }
 }
 
@@ -215,6 +223,26 @@ ZKB_HD_NOINLINE XYZZ msm_combine_windows(const XYZZ* sums, uint32_t nwin, uint32
         xyzz_add(acc, sums[w]);
     }
     return acc;
+}
+
+// ---- SRS window table: next[i] = 2^c * prev[i] (affine in, affine out) — built once per registered SRS so that every
+// window of every scalar can share ONE bucket set (no per-window reduction, no Horner fold) ------------------------------------
+struct SrsTableArgs {
+    const uint4* prev;  // n affine points
+    uint4* next;        // n affine points
+    uint64_t n;
+    uint32_t c;
+};
+ZKB_HD void srs_table_thread(const SrsTableArgs& a, uint64_t i) {
+    if (i >= a.n) return;
+    Affine p = affine_load(a.prev + 4 * i);
+    if (!p.is_identity()) {
+        XYZZ acc = xyzz_double_affine(p.x, p.y);
+        for (uint32_t k = 1; k < a.c; ++k) acc = xyzz_double(acc);
+        p = xyzz_to_affine(acc);
+    }
+    p.x.store(a.next + 4 * i);
+    p.y.store(a.next + 4 * i + 2);
 }
 
 // ---- fixed-base multiples of the generator: out[i] = [s_i] G (affine) — ParamsKZG::setup building block, and the

@@ -15,8 +15,19 @@ MsmWorkspace& msm_workspace();
 void msm_release_workspace();
 void msm_identity_out(uint64_t out[12]);
 
-// sum_i scalars[i] * bases[i]; device pointers; synchronises `s`; result normalised (z = R) on the host
-int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t out_jac[12]);
+// precomputed SRS window table: rows[w * row_stride + i] = 2^(c w) * P_i
+struct MsmTable {
+    const uint4* rows;     // already offset to the first point of the MSM range
+    uint64_t row_stride;   // registered SRS length
+    uint32_t c;
+    uint32_t nwin;
+};
+
+// sum_i scalars[i] * bases[i]; device pointers; synchronises `s`; result normalised (z = R) on the host.
+// With `table` the bases come from the window table and all windows share one bucket set.
+int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t out_jac[12],
+            const MsmTable* table = nullptr);
+int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin, uint4* d_table, cudaStream_t s);
 int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cudaStream_t s);
 int measure_imad_peak(double* macs_per_s);
 int g1_sum_host(const uint64_t* pts, size_t count, uint64_t out[12]);

@@ -6,8 +6,9 @@ namespace zkb {
 
 struct MsmGeometry {
     uint32_t c;            // window bits
-    uint32_t nwin;         // W = ceil(255 / c)
-    uint32_t nbuckets;     // W << (c-1)
+    uint32_t nwin;         // W = ceil(255 / c) digit windows per scalar
+    uint32_t bucket_sets;  // W, or 1 when the SRS window table is used (all windows share one bucket set)
+    uint32_t nbuckets;     // bucket_sets << (c-1)
     uint32_t invalid_key;  // == nbuckets
     uint32_t key_bits;     // radix-sort bits covering [0, invalid_key]
     uint32_t chunk0;       // entries per thread, level 0
@@ -29,13 +30,26 @@ inline uint32_t msm_pick_window(uint64_t n) {
     return best_c;
 }
 
-inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0) {
+// table mode: one reduction for all windows: W * n mixed adds + ~2.8 * 2^(c-1)
+inline uint32_t msm_pick_window_table(uint64_t n) {
+    double best = 1e300;
+    uint32_t best_c = 8;
+    for (uint32_t c = 4; c <= 22; ++c) {
+        uint32_t w = (255 + c - 1) / c;
+        double cost = (double)w * (double)n + 2.8 * (double)(1ull << (c - 1));
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0, bool table = false) {
     MsmGeometry g{};
-    g.c = c_override ? c_override : msm_pick_window(n ? n : 1);
+    g.c = c_override ? c_override : (table ? msm_pick_window_table(n ? n : 1) : msm_pick_window(n ? n : 1));
     if (g.c < 2) g.c = 2;
     if (g.c > 22) g.c = 22;
     g.nwin = (255 + g.c - 1) / g.c;
-    g.nbuckets = g.nwin << (g.c - 1);
+    g.bucket_sets = table ? 1 : g.nwin;
+    g.nbuckets = g.bucket_sets << (g.c - 1);
     g.invalid_key = g.nbuckets;
     g.key_bits = 1;
     while ((1ull << g.key_bits) <= g.invalid_key) ++g.key_bits;
