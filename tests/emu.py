@@ -64,6 +64,17 @@ def msm(scalars, bases, c=0, chunk=0, table=False):
     return out
 
 
+def msm_batch(scalar_cols, bases, c=0, chunk=0, table=False, dev_final=False):
+    s = np.ascontiguousarray(scalar_cols, dtype=np.uint64)
+    ncols, n = s.shape[0], s.shape[1]
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros((ncols, 12), dtype=np.uint64)
+    rc = lib().zkb_emu_msm_batch(_p(s), _p(b), ctypes.c_uint64(n), ctypes.c_uint32(ncols), ctypes.c_uint32(c), ctypes.c_uint32(chunk),
+                                 _p(out), ctypes.c_int(int(table)), ctypes.c_int(int(dev_final)))
+    assert rc == 0
+    return out
+
+
 def fixed_base_mul(scalars):
     s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
     out = np.zeros((s.shape[0], 8), dtype=np.uint64)

@@ -145,3 +145,26 @@ def test_msm_witness_like_distribution(oracle):
     s = mont(vals)
     b = _bases(oracle, n, 11)
     assert (emu.msm(s, b) == oracle.best_multiexp(s, b)).all()
+
+
+@pytest.mark.parametrize("n,ncols,c,chunk,table,dev_final", [(50, 3, 0, 0, False, False), (50, 3, 4, 4, True, False),
+                                                             (128, 9, 0, 0, True, True), (128, 9, 5, 7, False, True),
+                                                             (1, 2, 0, 0, True, False)])
+def test_msm_batched_columns_and_table(oracle, n, ncols, c, chunk, table, dev_final):
+    """Several scalar columns against the same bases in one pass (column folded into the bucket key), with and
+    without the SRS window table, host and device finalisation."""
+    b = _bases(oracle, n, n + 5)
+    cols = np.stack([random_field(n, 100 + i) for i in range(ncols)])
+    cols[0, :] = 0
+    got = emu.msm_batch(cols, b, c, chunk, table, dev_final)
+    for i in range(ncols):
+        assert (got[i] == oracle.best_multiexp(cols[i], b)).all()
+
+
+@pytest.mark.parametrize("n,c,chunk", [(5, 3, 2), (300, 5, 8), (700, 0, 0)])
+def test_msm_srs_window_table(oracle, n, c, chunk):
+    s = random_field(n, n)
+    b = _bases(oracle, n, n + 5)
+    if n >= 64:
+        s[3] = 0; b[7] = 0; s[9] = s[8]; b[9] = b[8]
+    assert (emu.msm(s, b, c, chunk, table=True) == oracle.best_multiexp(s, b)).all()

@@ -250,6 +250,23 @@ def test_srs_table_path_vs_oracle(oracle, n):
     params.close()
 
 
+@pytest.mark.parametrize("k,ncols,precompute", [(10, 20, 1), (10, 20, 0), (13, 9, 1), (6, 3, 1), (12, 40, 1)])
+def test_commit_batch_one_pass(oracle, k, ncols, precompute):
+    """zkb_msm_g1_srs_batch: all columns in one digit/sort/accumulate pass, device finalisation for >= 8 columns."""
+    zkb.lib().zkb_srs_set_precompute(precompute)
+    n = 1 << k
+    _, g = _bases_known_dlog(n, 90 + k)
+    params = zkb.ParamsKZG(k, g)
+    cols = [random_field(n, 900 + i) for i in range(ncols)]
+    cols[0][:] = 0                 # an all-zero column commits to the identity
+    cols[1][:] = cols[1][0]        # all-equal scalars
+    got = params.commit_batch(cols)
+    for i, p in enumerate(cols):
+        assert (got[i] == oracle.best_multiexp(p, g)).all(), i
+    params.close()
+    zkb.lib().zkb_srs_set_precompute(1)
+
+
 # ---- BASELINE.json full sizes: size-independent properties -------------------------------------------------------------------
 @pytest.mark.parametrize("k", [22, 24])
 def test_ntt_full_size_roundtrip_and_linearity(oracle, k):

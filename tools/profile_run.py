@@ -24,7 +24,7 @@ from util import random_field  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["msm", "ntt", "c2e"])
+    ap.add_argument("op", choices=["msm", "ntt", "c2e", "msmbatch"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--cols", type=int, default=1)
     ap.add_argument("--reps", type=int, default=3)
@@ -85,6 +85,22 @@ def main():
             ms, k = zkb.prof.get(name)
             res[name] = ms / max(k, 1)
         res["Mpts_per_s"] = n / (res["ms"] * 1e-3) / 1e6
+    elif args.op == "msmbatch":
+        lib.zkb_srs_set_precompute(0 if args.no_table else 1)
+        bases = zkb.g1_fixed_base_mul(random_field(n, 2))
+        params = zkb.ParamsKZG(args.log_n, bases)
+        cols = [random_field(n, 10 + i) for i in range(args.cols)]
+        times = []
+        for i in range(args.reps + 1):
+            t = time.perf_counter()
+            out = params.commit_batch(cols)
+            times.append(time.perf_counter() - t)
+        res["ms_e2e"] = 1e3 * min(times[1:])
+        res["Mpts_per_s_e2e"] = n * args.cols / min(times[1:]) / 1e6
+        t = time.perf_counter()
+        for c in cols[:4]:
+            params.commit(c)
+        res["ms_per_single_commit"] = 1e3 * (time.perf_counter() - t) / 4
     else:
         k = args.log_n
         ek = k + 2 if args.op == "c2e" else k

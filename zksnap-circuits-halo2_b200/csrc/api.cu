@@ -278,12 +278,13 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
 }
 
 // MSM of device scalars against srs[offset .. offset+n), through the window table when available
-static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t out[12]) {
+static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t* out,
+                       uint32_t ncols = 1) {
     if (srs_table_ready(srs, stream)) {
         MsmTable t{srs->table.as<uint4>() + 4 * offset, srs->n, srs->table_c, srs->table_nwin};
-        return msm_run(d_scalars, nullptr, n, stream, out, &t);
+        return msm_run(d_scalars, nullptr, n, stream, out, &t, ncols);
     }
-    return msm_run(d_scalars, srs->bases.as<uint4>() + 4 * offset, n, stream, out);
+    return msm_run(d_scalars, srs->bases.as<uint4>() + 4 * offset, n, stream, out, nullptr, ncols);
 }
 
 static int upload_scalars(const uint64_t* scalars, size_t n) {
@@ -431,8 +432,30 @@ int zkb_msm_g1_srs(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t 
 int zkb_msm_g1_srs_batch(uint64_t handle, const uint64_t* const* scalars, size_t ncols, size_t n, uint64_t* out_jac) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
-    if (ncols) { ZKB_TRY(check_ptr(scalars, "scalars")); ZKB_TRY(check_ptr(out_jac, "out_jac")); }
-    for (size_t i = 0; i < ncols; ++i) ZKB_TRY(zkb_msm_g1_srs_range(handle, 0, scalars[i], n, out_jac + 12 * i));
+    if (ncols == 0) return ZKB_OK;
+    ZKB_TRY(check_ptr(scalars, "scalars"));
+    ZKB_TRY(check_ptr(out_jac, "out_jac"));
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    if (n > s->n) { set_error("MSM length %zu exceeds the registered SRS length %zu", n, s->n); return ZKB_ERR_ARG; }
+    if (n == 0) { for (size_t i = 0; i < ncols; ++i) msm_identity_out(out_jac + 12 * i); return ZKB_OK; }
+    for (size_t i = 0; i < ncols; ++i) ZKB_TRY(check_ptr(scalars[i], "scalars column"));
+    // all columns of a group are digit-decomposed, sorted and accumulated in ONE pass (column folded into the bucket
+    // key); groups bound the sort size to 2^28 (key, index) pairs
+    const size_t per_col = n * 16;  // generous bound on windows per scalar
+    size_t group = ((size_t)1 << 28) / per_col;
+    if (group < 1) group = 1;
+    if (group > 4096) group = 4096;
+    Ctx& c = ctx();
+    HostIo& h = hostio();
+    for (size_t c0 = 0; c0 < ncols; c0 += group) {
+        size_t nc = ncols - c0 < group ? ncols - c0 : group;
+        ZKB_TRY(h.scalars.reserve(nc * n * 32));
+        for (size_t i = 0; i < nc; ++i)
+            ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h.scalars.p) + i * n * 32, scalars[c0 + i], n * 32,
+                                         cudaMemcpyHostToDevice, c.stream));
+        ZKB_TRY(msm_srs_dev(s, 0, h.scalars.as<uint4>(), n, c.stream, out_jac + 12 * c0, (uint32_t)nc));
+    }
     return ZKB_OK;
 }
 

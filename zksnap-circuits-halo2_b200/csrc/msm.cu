@@ -1,6 +1,8 @@
 // msm.cu — kernels and host driver of the G1 MSM (see msm.cuh for the algorithm).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstring>
+
 #include "msm_host.hpp"
 
 namespace zkb {
@@ -20,6 +22,10 @@ __global__ void __launch_bounds__(128) msm_reduce_segment_kernel(const MsmReduce
 
 __global__ void __launch_bounds__(128) msm_sum_groups_kernel(const MsmSumArgs a) {
     msm_sum_groups_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(128) msm_finalize_kernel(const MsmFinalArgs a) {
+    msm_finalize_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(128) srs_table_kernel(const SrsTableArgs a) {
@@ -115,7 +121,7 @@ void msm_release_workspace() {
     for (auto& b : w.seg) b.release();
     w.sort_tmp.release();
     w.buckets.release();
-    if (w.h_sums) { cudaFreeHost(w.h_sums); w.h_sums = nullptr; }
+    if (w.h_sums) { cudaFreeHost(w.h_sums); w.h_sums = nullptr; w.h_sums_cap = 0; }
 }
 
 static void xyzz_to_out(const XYZZ& p, uint64_t out[12]) {
@@ -136,15 +142,19 @@ static void xyzz_to_out(const XYZZ& p, uint64_t out[12]) {
 
 void msm_identity_out(uint64_t out[12]) { xyzz_to_out(XYZZ::identity(), out); }
 
-int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t out_jac[12],
-            const MsmTable* table) {
-    if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
+int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t* out_jac,
+            const MsmTable* table, uint32_t ncols) {
+    if (ncols == 0) return ZKB_OK;
+    if (n == 0) { for (uint32_t k = 0; k < ncols; ++k) msm_identity_out(out_jac + 12 * k); return ZKB_OK; }
     Ctx& c = ctx();
     MsmWorkspace& w = msm_workspace();
-    const MsmGeometry g = table ? msm_geometry(n, table->c, c.msm_chunk_override, true)
-                                : msm_geometry(n, c.msm_c_override, c.msm_chunk_override);
-    const uint64_t total = (uint64_t)g.nwin * n;
-    if (total >= (1ull << 31)) { set_error("MSM too large for 32-bit sort indices: n=%zu windows=%u", (size_t)n, g.nwin); return ZKB_ERR_ARG; }
+    const MsmGeometry g = table ? msm_geometry(n, table->c, c.msm_chunk_override, true, ncols)
+                                : msm_geometry(n, c.msm_c_override, c.msm_chunk_override, false, ncols);
+    const uint64_t total = (uint64_t)g.nwin * n * ncols;
+    if (total >= (1ull << 31) || (uint64_t)g.total_sets << (g.c - 1) >= (1ull << 31)) {
+        set_error("MSM batch too large for 32-bit sort keys: n=%zu cols=%u windows=%u", (size_t)n, ncols, g.nwin);
+        return ZKB_ERR_ARG;
+    }
 
     // ---- workspace
     for (int i = 0; i < 2; ++i) {
@@ -165,19 +175,26 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_TRY(w.pv[i].reserve(2 * t0 * 128));
     }
     const uint64_t J0 = 1ull << (g.c - 1 - g.log_m);
-    for (int i = 0; i < 2; ++i) ZKB_TRY(w.seg[i].reserve((size_t)g.bucket_sets * J0 * 128));
-    if (!w.h_sums) ZKB_CUDA_TRY(cudaMallocHost(&w.h_sums, 64 * 128));
+    for (int i = 0; i < 2; ++i) ZKB_TRY(w.seg[i].reserve((size_t)g.total_sets * J0 * 128));
+    const size_t host_bytes = (size_t)g.total_sets * 128 > (size_t)ncols * 96 ? (size_t)g.total_sets * 128 : (size_t)ncols * 96;
+    if (w.h_sums_cap < host_bytes) {
+        if (w.h_sums) cudaFreeHost(w.h_sums);
+        w.h_sums = nullptr;
+        w.h_sums_cap = 0;
+        ZKB_CUDA_TRY(cudaMallocHost(&w.h_sums, host_bytes));
+        w.h_sums_cap = host_bytes;
+    }
 
     // ---- 1. digits
     {
         ProfScope prof("msm_digits", s);
         MsmDigitArgs a{};
-        a.scalars = d_scalars; a.n = n; a.c = g.c; a.nwin = g.nwin;
+        a.scalars = d_scalars; a.n = n; a.ncols = ncols; a.sets_per_col = g.bucket_sets; a.c = g.c; a.nwin = g.nwin;
         a.keys = w.keys[0].as<uint32_t>(); a.vals = w.vals[0].as<uint32_t>();
         a.invalid_key = g.invalid_key;
         a.table_mode = table ? 1 : 0;
         a.row_stride = table ? table->row_stride : 0;
-        msm_digits_kernel<<<blocks_for(n, 256), 256, 0, s>>>(a);
+        msm_digits_kernel<<<blocks_for(n * ncols, 256), 256, 0, s>>>(a);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
     }
@@ -223,22 +240,22 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             ++level;
         }
     }
-    // ---- 4. bucket reduction
+    // ---- 4. bucket reduction: one weighted sum per bucket set
     const uint4* sums;
+    int cur = 0;
     {
         ProfScope prof("msm_reduce", s);
         MsmReduceArgs r{};
-        r.buckets = w.buckets.as<uint4>(); r.c = g.c; r.nwin = g.bucket_sets; r.log_m = g.log_m;
+        r.buckets = w.buckets.as<uint4>(); r.c = g.c; r.nwin = g.total_sets; r.log_m = g.log_m;
         r.seg_out = w.seg[0].as<uint4>();
         uint64_t J = J0;
-        msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.bucket_sets * J, 128), 128, 0, s>>>(r);
+        msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.total_sets * J, 128), 128, 0, s>>>(r);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
-        int cur = 0;
         while (J > 1) {
             uint32_t grp = J >= g.sum_group ? g.sum_group : (uint32_t)J;
             uint64_t Jn = J / grp;
-            MsmSumArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), (uint64_t)g.bucket_sets * Jn, grp};
+            MsmSumArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), (uint64_t)g.total_sets * Jn, grp};
             msm_sum_groups_kernel<<<blocks_for(sa.out_count, 128), 128, 0, s>>>(sa);
             count_launch();
             ZKB_CUDA_TRY(cudaGetLastError());
@@ -247,13 +264,28 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         }
         sums = w.seg[cur].as<uint4>();
     }
-    // ---- 5. window sums to the host, Horner + normalisation there
-    ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, sums, (size_t)g.bucket_sets * 128, cudaMemcpyDeviceToHost, s));
+    // ---- 5. fold the per-set sums and normalise: on the host for a few columns (north_star: "tiny bucket sums combined
+    // on the host"), on the device for wide batches where hundreds of host inversions would dominate
+    if (ncols >= 8) {
+        ProfScope prof("msm_reduce", s);
+        MsmFinalArgs f{sums, ncols, g.bucket_sets, g.c, w.seg[cur ^ 1].as<uint4>()};
+        msm_finalize_kernel<<<blocks_for(ncols, 32), 32, 0, s>>>(f);
+        count_launch();
+        ZKB_CUDA_TRY(cudaGetLastError());
+        ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, f.out, (size_t)ncols * 96, cudaMemcpyDeviceToHost, s));
+        ZKB_CUDA_TRY(cudaStreamSynchronize(s));
+        memcpy(out_jac, w.h_sums, (size_t)ncols * 96);
+        return ZKB_OK;
+    }
+    ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, sums, (size_t)g.total_sets * 128, cudaMemcpyDeviceToHost, s));
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
-    XYZZ hs[64];
-    for (uint32_t i = 0; i < g.bucket_sets; ++i) hs[i] = XYZZ::load(reinterpret_cast<const uint4*>(w.h_sums) + 8 * i);
-    XYZZ res = msm_combine_windows(hs, g.bucket_sets, g.c);
-    xyzz_to_out(res, out_jac);
+    for (uint32_t col = 0; col < ncols; ++col) {
+        XYZZ hs[64];
+        for (uint32_t i = 0; i < g.bucket_sets; ++i)
+            hs[i] = XYZZ::load(reinterpret_cast<const uint4*>(w.h_sums) + 8 * ((size_t)col * g.bucket_sets + i));
+        XYZZ res = msm_combine_windows(hs, g.bucket_sets, g.c);
+        xyzz_to_out(res, out_jac + 12 * col);
+    }
     return ZKB_OK;
 }
 

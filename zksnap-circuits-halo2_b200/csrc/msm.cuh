@@ -25,11 +25,13 @@ namespace zkb {
 constexpr uint32_t MSM_INVALID_KEY = 0xffffffffu;
 
 struct MsmDigitArgs {
-    const uint4* scalars;  // n Montgomery Fr
-    uint64_t n;
+    const uint4* scalars;  // ncols columns of n Montgomery Fr, column-major contiguous
+    uint64_t n;            // points per column
+    uint32_t ncols;        // independent MSMs against the same bases (the prover's per-column commits) in one pass
+    uint32_t sets_per_col; // bucket sets per column: W, or 1 in table mode
     uint32_t c;            // window bits
     uint32_t nwin;         // W, W*c >= 255
-    uint32_t* keys;        // [W*n], window-major
+    uint32_t* keys;        // [W * ncols * n], window-major
     uint32_t* vals;
     uint32_t invalid_key;  // number of buckets: W << (c-1), or 1 << (c-1) in table mode
     uint32_t table_mode;   // 1: bases are the precomputed rows T[w][i] = 2^(c w) P_i, all windows share one bucket set
@@ -44,9 +46,12 @@ ZKB_HD uint32_t msm_extract_bits(const Fr& s, uint32_t bit, uint32_t c) {  // c 
     return (uint32_t)(v >> sh) & ((1u << c) - 1);
 }
 
-ZKB_HD void msm_digits_thread(const MsmDigitArgs& a, uint64_t i) {
-    if (i >= a.n) return;
-    Fr s = fp_from_mont(fr_load2(a.scalars, i));
+ZKB_HD void msm_digits_thread(const MsmDigitArgs& a, uint64_t t) {
+    const uint64_t total = a.n * a.ncols;
+    if (t >= total) return;
+    const uint32_t col = (uint32_t)(t / a.n);
+    const uint64_t i = t - (uint64_t)col * a.n;
+    Fr s = fp_from_mont(fr_load2(a.scalars, t));
     uint32_t carry = 0;
     const uint32_t half = 1u << (a.c - 1);
     for (uint32_t w = 0; w < a.nwin; ++w) {
@@ -54,16 +59,11 @@ ZKB_HD void msm_digits_thread(const MsmDigitArgs& a, uint64_t i) {
         uint32_t neg = v > half;
         uint32_t mag = neg ? (1u << a.c) - v : v;
         carry = neg;
-        uint32_t key, idx;
-        if (a.table_mode) {
-            key = mag ? mag - 1 : a.invalid_key;
-            idx = (uint32_t)((uint64_t)w * a.row_stride + i);
-        } else {
-            key = mag ? (w << (a.c - 1)) + (mag - 1) : a.invalid_key;
-            idx = (uint32_t)i;
-        }
-        a.keys[(uint64_t)w * a.n + i] = key;
-        a.vals[(uint64_t)w * a.n + i] = idx | (neg << 31);
+        const uint32_t set = col * a.sets_per_col + (a.table_mode ? 0u : w);
+        const uint32_t key = mag ? (set << (a.c - 1)) + (mag - 1) : a.invalid_key;
+        const uint32_t idx = a.table_mode ? (uint32_t)((uint64_t)w * a.row_stride + i) : (uint32_t)i;
+        a.keys[(uint64_t)w * total + t] = key;
+        a.vals[(uint64_t)w * total + t] = idx | (neg << 31);
     }
 }
 
@@ -223,6 +223,31 @@ ZKB_HD_NOINLINE XYZZ msm_combine_windows(const XYZZ* sums, uint32_t nwin, uint32
         xyzz_add(acc, sums[w]);
     }
     return acc;
+}
+
+// ---- device-side finalisation for batches: column col folds its `sets` window sums (Horner, c doublings per window)
+// and normalises to the G1 output encoding (x, y, R) / identity (0, R, 0) -------------------------------------------------
+struct MsmFinalArgs {
+    const uint4* sums;   // XYZZ [ncols * sets]
+    uint32_t ncols, sets, c;
+    uint4* out;          // ncols x 96 B
+};
+ZKB_HD void msm_finalize_thread(const MsmFinalArgs& a, uint64_t col) {
+    if (col >= a.ncols) return;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t w = a.sets; w-- > 0;) {
+        if (w + 1 < a.sets)
+            for (uint32_t i = 0; i < a.c; ++i) acc = xyzz_double(acc);
+        xyzz_add(acc, msm_load_xyzz(a.sums, col * a.sets + w));
+    }
+    uint4* o = a.out + 6 * col;
+    Fq one = Fq::one();
+    if (acc.is_identity()) {
+        Fq::zero().store(o); one.store(o + 2); Fq::zero().store(o + 4);
+        return;
+    }
+    Affine r = xyzz_to_affine(acc);
+    r.x.store(o); r.y.store(o + 2); one.store(o + 4);
 }
 
 // ---- SRS window table: next[i] = 2^c * prev[i] (affine in, affine out) — built once per registered SRS so that every

@@ -8,7 +8,8 @@ namespace zkb {
 
 struct MsmWorkspace {
     DevBuf keys[2], vals[2], sort_tmp, buckets, pk[2], pv[2], seg[2];
-    void* h_sums = nullptr;  // pinned, 64 XYZZ
+    void* h_sums = nullptr;  // pinned staging for the per-set sums / finished results
+    size_t h_sums_cap = 0;
 };
 
 MsmWorkspace& msm_workspace();
@@ -25,8 +26,10 @@ struct MsmTable {
 
 // sum_i scalars[i] * bases[i]; device pointers; synchronises `s`; result normalised (z = R) on the host.
 // With `table` the bases come from the window table and all windows share one bucket set.
-int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t out_jac[12],
-            const MsmTable* table = nullptr);
+// `ncols` independent scalar columns (column-major contiguous) against the same bases are accumulated in ONE pass
+// (column index folded into the bucket key); out_jac receives ncols x 12 limbs.
+int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t* out_jac,
+            const MsmTable* table = nullptr, uint32_t ncols = 1);
 int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin, uint4* d_table, cudaStream_t s);
 int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cudaStream_t s);
 int measure_imad_peak(double* macs_per_s);

@@ -7,8 +7,10 @@ namespace zkb {
 struct MsmGeometry {
     uint32_t c;            // window bits
     uint32_t nwin;         // W = ceil(255 / c) digit windows per scalar
-    uint32_t bucket_sets;  // W, or 1 when the SRS window table is used (all windows share one bucket set)
-    uint32_t nbuckets;     // bucket_sets << (c-1)
+    uint32_t bucket_sets;  // per column: W, or 1 when the SRS window table is used (all windows share one bucket set)
+    uint32_t ncols;        // columns accumulated in one pass
+    uint32_t total_sets;   // ncols * bucket_sets
+    uint32_t nbuckets;     // total_sets << (c-1)
     uint32_t invalid_key;  // == nbuckets
     uint32_t key_bits;     // radix-sort bits covering [0, invalid_key]
     uint32_t chunk0;       // entries per thread, level 0
@@ -42,14 +44,18 @@ inline uint32_t msm_pick_window_table(uint64_t n) {
     return best_c;
 }
 
-inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0, bool table = false) {
+// n = points per column.  For a batch of ncols columns the bucket array holds ncols * bucket_sets sets.
+inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0, bool table = false,
+                                uint32_t ncols = 1) {
     MsmGeometry g{};
+    g.ncols = ncols ? ncols : 1;
     g.c = c_override ? c_override : (table ? msm_pick_window_table(n ? n : 1) : msm_pick_window(n ? n : 1));
     if (g.c < 2) g.c = 2;
     if (g.c > 22) g.c = 22;
     g.nwin = (255 + g.c - 1) / g.c;
     g.bucket_sets = table ? 1 : g.nwin;
-    g.nbuckets = g.bucket_sets << (g.c - 1);
+    g.total_sets = g.bucket_sets * g.ncols;
+    g.nbuckets = g.total_sets << (g.c - 1);
     g.invalid_key = g.nbuckets;
     g.key_bits = 1;
     while ((1ull << g.key_bits) <= g.invalid_key) ++g.key_bits;
