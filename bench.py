@@ -201,13 +201,13 @@ def main():
         if rc != 0:
             raise RuntimeError(lib.zkb_last_error().decode())
 
+    zdist = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+
     def fold(result):
+        """host fold of the per-rank partial sums (96 B each) — the only inter-GPU exchange of a sharded MSM"""
         if world == 1:
             return result
-        t = torch.from_numpy(result.view(np.int64).copy()).to(dev)
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        return zkb.g1_sum(np.stack([p.cpu().numpy().view(np.uint64) for p in parts]))
+        return zkb.g1_sum(zdist.all_gather_g1(result, device=dev))
 
     # ---- warm-up + correctness of the measured configuration (rank-local known-dlog check on the first step) ------------
     for _ in range(args.warmup):
