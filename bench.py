@@ -153,6 +153,14 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    wd = int(os.environ.get("ZKB_BENCH_WATCHDOG", "0"))
+    if wd:  # debugging aid: dump all Python stacks and exit if the run exceeds `wd` seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
+
+    def note(msg):
+        if os.environ.get("ZKB_BENCH_VERBOSE"):
+            print("[bench] " + msg, file=sys.stderr, flush=True)
 
     import torch
     import torch.distributed as dist
@@ -209,6 +217,7 @@ def main():
             return result
         return zkb.g1_sum(zdist.all_gather_g1(result, device=dev))
 
+    note("inputs ready")
     # ---- warm-up + correctness of the measured configuration (rank-local known-dlog check on the first step) ------------
     for _ in range(args.warmup):
         step_dev()
@@ -218,6 +227,7 @@ def main():
     want = coracle.g1_mul(coracle.g1_generator(), ip)
     parity = bool((out[:8] == want).all())
 
+    note("warm-up + parity done")
     # ---- timed: device-resident ------------------------------------------------------------------------------------------
     zkb.prof.enable(True)
     zkb.prof.reset()
@@ -247,6 +257,7 @@ def main():
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
+    note("device-resident timing done")
     # ---- timed: end to end through the host-buffer ABI ---------------------------------------------------------------------
     for _ in range(2):
         step_e2e()
@@ -263,6 +274,7 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * n * args.steps / e2e_s
 
+    note("e2e timing done")
     # ---- integer-pipe peak (measured here) and the roofline of the dominant kernel -----------------------------------------
     peak = ctypes.c_double(0)
     lib.zkb_measure_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
@@ -299,6 +311,7 @@ def main():
             if rc != 0:
                 raise RuntimeError(lib.zkb_last_error().decode())
 
+        note("ntt inputs ready")
         for _ in range(args.warmup):
             ntt_step()
         barrier()
@@ -312,6 +325,7 @@ def main():
         launches += zkb.launch_count() - launches1
         alg_bytes = 64.0 * N * cols
         gbs = alg_bytes / (nms * 1e-3) / 1e9
+        note("ntt device timing done")
         # e2e: host columns through zkb_ntt_fr_batch (H2D + kernels + D2H)
         cols_np = [a_np[i * N:(i + 1) * N] for i in range(cols)]
         ptrs = (ctypes.POINTER(ctypes.c_uint64) * cols)(*[ctypes.cast(h_a.data_ptr() + i * N * 32, ctypes.POINTER(ctypes.c_uint64)) for i in range(cols)])
@@ -331,6 +345,7 @@ def main():
                                 "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound, see DESIGN.md"}}
         del cols_np
 
+    note("ntt done")
     # ---- CPU baseline on this box (rank 0, N=1 only) ---------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:

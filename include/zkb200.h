@@ -126,6 +126,42 @@ int zkb_coeff_to_extended_dev(const void* d_in, void* d_out, void* d_scratch, si
 int zkb_extended_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, uint32_t extended_k, void* stream);
 int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, void* stream);
 
+/* ---- one NTT sharded over the GPUs of a box ("single NTT larger than one GPU's share") ------------
+ * One process per GPU.  Rank r holds the contiguous slice [r N/G, (r+1) N/G) of the natural-order input and receives
+ * the same slice of the natural-order output of best_fft(a, omega, log_n).  The exchange is not a separate collective:
+ * pass 0 of the NTT gathers its tiles from every rank's HBM and the last pass scatters its results to the owning rank,
+ * both over NVLink peer mappings (CUDA IPC), with device-side barriers in between.
+ *   zkb_dist_create   allocates this rank's symmetric slices (input, work, output: 3 x 2^max_log_n/world x 32 B) and
+ *                     returns an opaque blob of ZKB_DIST_HANDLE_BYTES to be all-gathered by the caller (any transport:
+ *                     torch.distributed, MPI, a file);
+ *   zkb_dist_connect  maps every peer's slices from the gathered blobs (world x ZKB_DIST_HANDLE_BYTES, rank order).
+ * All ranks must call the zkb_dist_ntt_* functions collectively, in the same order.  world is 1, 2, 4 or 8; the transform
+ * needs at least two passes (log_n >= 11).  A rank that never arrives makes the others fail with ZKB_ERR_CUDA after a
+ * bounded wait instead of hanging the GPU. */
+#define ZKB_DIST_HANDLE_BYTES 256
+int zkb_dist_create(int rank, int world, uint32_t max_log_n, uint8_t* handle_out);
+int zkb_dist_connect(const uint8_t* all_handles);
+int zkb_dist_destroy(void);
+/* host slices (N/world x 4 u64 each); synchronous */
+int zkb_dist_ntt_fr(const uint64_t* in_slice, uint64_t* out_slice, const uint64_t omega[4], uint32_t log_n);
+/* device slices; NULL d_in_slice / d_out_slice = use the symmetric slices directly (zkb_dist_buffers).  Asynchronous on
+ * `stream`; call zkb_dist_status(stream) to synchronise and learn whether every barrier completed. */
+int zkb_dist_ntt_fr_dev(const void* d_in_slice, void* d_out_slice, const uint64_t omega[4], uint32_t log_n, void* stream);
+int zkb_dist_buffers(void** d_in_slice, void** d_out_slice, size_t* slice_bytes);
+int zkb_dist_status(void* stream);
+
+/* ---- host memory and the transfer scheduler --------------------------------------------------------------------
+ * The host-buffer batch entry points (zkb_*_batch, and the single-column forms through them) run a three-stream
+ * pipeline: column group i+1 is copied host->device while group i computes and group i-1 is copied device->host.
+ * Caller memory that is page-locked (cudaMallocHost, or registered with zkb_host_register — e.g. the prover's
+ * long-lived advice / extended-polynomial Vecs) is DMA'd directly; pageable memory is staged through internal
+ * pinned buffers by a pool of host threads (ZKB_STAGE_THREADS, default min(8, cores/2)). */
+int zkb_host_register(void* ptr, size_t bytes);
+int zkb_host_unregister(void* ptr);
+/* depth: column groups in flight, 1 = serial, 0 = default (3); group_bytes: output bytes per group, 0 = automatic
+ * (a quarter of the batch, clamped to [8 MiB, 256 MiB]). */
+int zkb_pipeline_set(int depth, size_t group_bytes);
+
 /* ---- tuning and measurement -------------------------------------------------------------------------------- */
 
 /* MSM window bits / level-0 chunk length override (0 = automatic). */
@@ -133,7 +169,7 @@ int zkb_msm_set_params(uint32_t window_bits, uint32_t chunk);
 int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, uint32_t* chunk);
 
 /* Per-kernel CUDA-event timers.  Names: "msm_digits", "msm_sort", "msm_accumulate", "msm_reduce",
- * "ntt_pass".  zkb_prof_get returns the summed milliseconds and launch count since the last reset. */
+ * "ntt_pass", "dist_ntt_pass0", "dist_ntt_middle", "dist_ntt_final", "dist_barrier".  zkb_prof_get returns the summed milliseconds and launch count since the last reset. */
 int zkb_prof_enable(int on);
 int zkb_prof_reset(void);
 int zkb_prof_get(const char* name, double* total_ms, uint64_t* launches);

@@ -80,3 +80,29 @@ def fixed_base_mul(scalars):
     out = np.zeros((s.shape[0], 8), dtype=np.uint64)
     lib().zkb_emu_fixed_base_mul(_p(s), ctypes.c_uint64(s.shape[0]), _p(out))
     return out
+
+
+def ntt_dist_phase(phase, rank, log_g, log_n, omega, A, W, O):
+    """One phase of the sharded NTT for `rank`; A/W/O are lists (one per rank) of (N/G, 4) uint64 slices (any memory,
+    e.g. numpy views of POSIX shared memory)."""
+    G = 1 << log_g
+    arr = lambda bufs: (_u64p * G)(*[b.ctypes.data_as(_u64p) for b in bufs])
+    rc = lib().zkb_emu_ntt_dist_phase(ctypes.c_int(phase), ctypes.c_uint32(rank), ctypes.c_uint32(log_g), ctypes.c_uint32(log_n),
+                                      _p(np.ascontiguousarray(omega, dtype=np.uint64)), arr(A), arr(W), arr(O))
+    return rc
+
+
+def ntt_dist(a, log_n, omega, log_g):
+    """Whole sharded NTT in one process: every rank's pass 0, barrier, every rank's remaining passes."""
+    G = 1 << log_g
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    sl = a.shape[0] // G
+    A = [a[r * sl:(r + 1) * sl].copy() for r in range(G)]
+    W = [np.zeros((sl, 4), dtype=np.uint64) for _ in range(G)]
+    O = [np.zeros((sl, 4), dtype=np.uint64) for _ in range(G)]
+    for phase in (0, 1):
+        for r in range(G):
+            rc = ntt_dist_phase(phase, r, log_g, log_n, omega, A, W, O)
+            if rc != 0:
+                return rc, None
+    return 0, np.concatenate(O)

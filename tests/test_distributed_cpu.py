@@ -61,3 +61,67 @@ def test_point_range_partition():
             for (o1, l1), (o2, _) in zip(spans, spans[1:]):
                 assert o1 + l1 == o2
     assert zd.columns_for_rank(5, 1, 2) == [1, 3]
+
+
+# ---- one NTT sharded over 2 ranks: the kernels' distributed addressing, run by the CPU emulator in two gloo processes whose
+# slices live in POSIX shared memory (the stand-in for CUDA IPC peer mappings); gloo barriers replace the device barriers ----
+def _sharded_ntt_worker(rank, world, port, k, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from multiprocessing import shared_memory
+
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    import emu
+    from oracle import coracle
+    from util import random_field
+
+    zd = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+    coracle.build()
+    a = random_field(1 << k, 900 + k)
+    w = coracle.fr_omega(k)
+    off, ln = zd.ntt_slice(k, rank, world)
+    mine = [shared_memory.SharedMemory(create=True, size=ln * 32) for _ in range(3)]  # A, W, O slices of this rank
+    names = [None] * world
+    dist.all_gather_object(names, [m.name for m in mine])
+    peers = [[shared_memory.SharedMemory(name=nm) for nm in names[r]] if r != rank else mine for r in range(world)]
+    A, W, O = ([np.ndarray((ln, 4), dtype=np.uint64, buffer=peers[r][b].buf) for r in range(world)] for b in range(3))
+    A[rank][:] = a[off:off + ln]
+    log_g = world.bit_length() - 1
+    dist.barrier()                                                    # every rank's input slice is in place
+    rc0 = emu.ntt_dist_phase(0, rank, log_g, k, w, A, W, O)           # pass 0: peer loads + peer stores
+    dist.barrier()
+    rc1 = emu.ntt_dist_phase(1, rank, log_g, k, w, A, W, O)           # local passes + scattering final pass
+    dist.barrier()
+    ret[rank] = (rc0, rc1, bool((O[rank] == coracle.best_fft(a, w, k)[off:off + ln]).all()))
+    dist.barrier()
+    del A, W, O
+    for r in range(world):
+        if r != rank:
+            for m in peers[r]:
+                m.close()
+    for m in mine:
+        m.close()
+        m.unlink()
+    dist.destroy_process_group()
+
+
+def test_sharded_ntt_two_ranks_shared_memory():
+    import torch.multiprocessing as mp
+
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_ntt_worker, args=(world, port, 13, ret), nprocs=world, join=True)
+    assert all(ret[r] == (0, 0, True) for r in range(world)), dict(ret)
+
+
+def test_ntt_slice_partition():
+    zd = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+    for k in (3, 11, 20):
+        for world in (1, 2, 4, 8):
+            spans = [zd.ntt_slice(k, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(l for _, l in spans) == 1 << k
+            assert all(o1 + l1 == o2 for (o1, l1), (o2, _) in zip(spans, spans[1:]))

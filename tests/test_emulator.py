@@ -168,3 +168,19 @@ def test_msm_srs_window_table(oracle, n, c, chunk):
     if n >= 64:
         s[3] = 0; b[7] = 0; s[9] = s[8]; b[9] = b[8]
     assert (emu.msm(s, b, c, chunk, table=True) == oracle.best_multiexp(s, b)).all()
+
+
+# ---- distributed NTT: one transform sharded over G ranks (peer memory emulated by per-rank arrays) ---------------------
+@pytest.mark.parametrize("k,log_g", [(11, 1), (12, 2), (13, 3), (16, 1), (17, 3), (19, 2), (20, 3)])
+def test_ntt_dist_matches_best_fft(oracle, k, log_g):
+    a = random_field(1 << k, 700 + k)
+    w = oracle.fr_omega(k)
+    rc, got = emu.ntt_dist(a, k, w, log_g)
+    assert rc == 0
+    assert (got == oracle.best_fft(a, w, k)).all()
+
+
+def test_ntt_dist_rejects_single_pass():
+    a = random_field(1 << 8, 1)
+    rc, _ = emu.ntt_dist(a, 8, np.zeros(4, dtype=np.uint64), 1)
+    assert rc == -2

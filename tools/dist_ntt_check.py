@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Sharded-NTT parity and timing under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_ntt_check.py --log-n 16 20 24 26 [--time]
+
+Parity: every rank builds the same seeded 2^log_n vector, passes its contiguous slice to ShardedNtt.best_fft_slice and
+compares the returned slice with (a) the single-GPU zkb.best_fft of the whole vector (log_n <= 24) and (b) the C oracle
+(log_n <= 20).  Timing (--time): device-resident zkb_dist_ntt_fr_dev on the symmetric slices, CUDA events, max over ranks,
+next to the single-GPU time of the same transform.  Prints one JSON line per size on rank 0.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log-n", type=int, nargs="+", default=[16, 20])
+    ap.add_argument("--time", action="store_true")
+    ap.add_argument("--iters", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from util import random_field
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    zkb = importlib.import_module("zksnap-circuits-halo2_b200")
+    zdist = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+    zkb.init(local)
+    lib = zkb.lib()
+    sh = zdist.ShardedNtt(max(args.log_n), device=dev)
+    ok_all = True
+    for k in args.log_n:
+        n = 1 << k
+        a = random_field(n, 4000 + k)
+        w = zkb.omega(k)
+        off, ln = zdist.ntt_slice(k, rank, world)
+        got = sh.best_fft_slice(a[off:off + ln], w, k)
+        checks = {}
+        if k <= 24:
+            full = a.copy()
+            zkb.best_fft(full, w, k)
+            checks["single_gpu"] = bool((got == full[off:off + ln]).all())
+        if k <= 20:
+            from oracle import coracle
+            coracle.build()
+            checks["oracle"] = bool((got == coracle.best_fft(a, w, k)[off:off + ln]).all())
+        ok = all(checks.values())
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+        ok_all &= ok
+        line = {"op": "dist_best_fft", "log_n": k, "world": world, "parity": ok, "checks": sorted(checks)}
+        if args.time:
+            stream = torch.cuda.current_stream()
+            sp = ctypes.c_void_p(stream.cuda_stream)
+            wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            zkb.prof.enable(True)
+            for it in range(3 + args.iters):
+                if it == 3:
+                    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                    zkb.prof.reset()
+                    e0.record(stream)
+                rc = lib.zkb_dist_ntt_fr_dev(None, None, wp, k, sp)
+                assert rc == 0, lib.zkb_last_error()
+            e1.record(stream)
+            assert lib.zkb_dist_status(sp) == 0, lib.zkb_last_error()
+            ms = e0.elapsed_time(e1) / args.iters
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            parts = {nm: zkb.prof.get(nm)[0] / args.iters for nm in ("dist_ntt_pass0", "dist_ntt_middle", "dist_ntt_final", "dist_barrier")}
+            zkb.prof.enable(False)
+            line.update({"ms": float(tt.item()), "elems_per_s": n / (float(tt.item()) * 1e-3), "rank0_ms": parts,
+                         "nvlink_bytes_per_rank": int(3 * (world - 1) / world * ln * 32)})
+            if k <= 26 and rank == 0:  # single-GPU time of the same transform for comparison
+                d = torch.empty(n * 4, dtype=torch.int64, device=dev)
+                s = torch.empty_like(d)
+                for it in range(2 + args.iters):
+                    if it == 2:
+                        torch.cuda.synchronize()
+                        e0.record(stream)
+                    lib.zkb_ntt_fr_dev(ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(s.data_ptr()), 1, wp, k, sp)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                line["single_gpu_ms"] = e0.elapsed_time(e1) / args.iters
+                del d, s
+            dist.barrier()
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    sh.close()
+    dist.destroy_process_group()
+    return 0 if ok_all else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

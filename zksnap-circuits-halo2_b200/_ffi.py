@@ -69,6 +69,16 @@ def load() -> ctypes.CDLL:
         "zkb_coeff_to_extended_dev": [vp, vp, vp, sz, u32, u32, vp],
         "zkb_extended_to_coeff_dev": [vp, vp, sz, u32, u32, vp],
         "zkb_lagrange_to_coeff_dev": [vp, vp, sz, u32, vp],
+        "zkb_dist_create": [ci, ci, u32, ctypes.POINTER(ctypes.c_uint8)],
+        "zkb_dist_connect": [ctypes.POINTER(ctypes.c_uint8)],
+        "zkb_dist_destroy": [],
+        "zkb_dist_ntt_fr": [u64p, u64p, u64p, u32],
+        "zkb_dist_ntt_fr_dev": [vp, vp, u64p, u32, vp],
+        "zkb_dist_buffers": [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(sz)],
+        "zkb_dist_status": [vp],
+        "zkb_host_register": [vp, sz],
+        "zkb_host_unregister": [vp],
+        "zkb_pipeline_set": [ci, sz],
         "zkb_msm_set_params": [u32, u32],
         "zkb_msm_get_params": [sz, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)],
         "zkb_prof_enable": [ci],

@@ -1,7 +1,9 @@
 // api.cu — the C ABI of libzkb200.so (include/zkb200.h): context, SRS registry, host-buffer and device-buffer
 // entry points.  No CPU fallback lives here: every compute call requires an initialised CUDA device.
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "msm_host.hpp"
 #include "ntt_host.hpp"
@@ -236,6 +238,159 @@ static int domain_op_dev(DomainOp op, const uint4* d_in, uint4* d_a, uint4* d_b,
     return ntt_run(*plan, io, s);
 }
 
+// ---- host-buffer scheduler (north_star item 4): pinned staging, three streams, column groups in flight ---------------------
+// The host-buffer entry points are synchronous (halo2 semantics), so the overlap lives inside one batched call: the
+// columns are cut into groups; group i+1 is copied host->device on `s_h2d` while group i runs on the compute stream
+// and group i-1 is copied device->host on `s_d2h` (PCIe is full duplex).  Pageable caller memory (a Rust Vec) is
+// staged through per-slot pinned buffers by a small pool of host threads; pinned / registered caller memory is
+// DMA'd directly.
+struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    uint64_t gen = 0;
+    unsigned pending = 0;
+    bool quit = false;
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t bytes = 0;
+    unsigned nparts = 0;
+
+    void start() {
+        if (!workers.empty()) return;
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned n = hw / 2;
+        if (n < 1) n = 1;
+        if (n > 8) n = 8;
+        const char* e = getenv("ZKB_STAGE_THREADS");
+        if (e && atoi(e) > 0) n = (unsigned)atoi(e);
+        nparts = n;
+        for (unsigned i = 1; i < n; ++i) workers.emplace_back([this, i] { loop(i); });
+    }
+    void part(unsigned i) {
+        size_t per = ((bytes / nparts) + 4095) & ~(size_t)4095;
+        size_t lo = (size_t)i * per, hi = lo + per;
+        if (lo >= bytes) return;
+        if (hi > bytes) hi = bytes;
+        memcpy(dst + lo, src + lo, hi - lo);
+    }
+    void loop(unsigned i) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_go.wait(lk, [&] { return quit || gen != seen; });
+                if (quit) return;
+                seen = gen;
+            }
+            part(i);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    void copy(void* d, const void* s, size_t n) {
+        if (n < (4u << 20)) { memcpy(d, s, n); return; }
+        start();
+        if (nparts <= 1) { memcpy(d, s, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            dst = (char*)d; src = (const char*)s; bytes = n;
+            pending = nparts - 1;
+            ++gen;
+        }
+        cv_go.notify_all();
+        part(0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~HostPool() { stop(); }
+    void stop() {
+        if (workers.empty()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv_go.notify_all();
+        for (auto& t : workers) t.join();
+        workers.clear();
+        quit = false;
+    }
+};
+static HostPool& host_pool() {
+    static HostPool p;
+    return p;
+}
+
+struct PinBuf {  // grow-only pinned host buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ZKB_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ZKB_ERR_OOM; }
+        cap = bytes;
+        return ZKB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr int PIPE_SLOTS = 3;
+struct PipeSlot {
+    DevBuf x, y, in;
+    PinBuf h_in, h_out;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+    bool busy = false;
+    // deferred copy-out of a pageable group
+    size_t c0 = 0, nc = 0;
+};
+struct Pipeline {
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    PipeSlot slot[PIPE_SLOTS];
+    bool ready = false;
+    size_t group_bytes_override = 0;  // 0 = automatic
+    int depth = PIPE_SLOTS;           // 1 = serial (for A/B measurements)
+};
+static Pipeline& pipeline() {
+    static Pipeline p;
+    return p;
+}
+static int pipeline_init() {
+    Pipeline& pl = pipeline();
+    if (pl.ready) return ZKB_OK;
+    ZKB_CUDA_TRY(cudaStreamCreateWithFlags(&pl.s_h2d, cudaStreamNonBlocking));
+    ZKB_CUDA_TRY(cudaStreamCreateWithFlags(&pl.s_d2h, cudaStreamNonBlocking));
+    for (auto& s : pl.slot) {
+        ZKB_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        ZKB_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        ZKB_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+    }
+    pl.ready = true;
+    return ZKB_OK;
+}
+static void pipeline_release() {
+    Pipeline& pl = pipeline();
+    if (!pl.ready) return;
+    for (auto& s : pl.slot) {
+        s.x.release(); s.y.release(); s.in.release(); s.h_in.release(); s.h_out.release();
+        cudaEventDestroy(s.ev_h2d); cudaEventDestroy(s.ev_comp); cudaEventDestroy(s.ev_d2h);
+        s.busy = false;
+    }
+    cudaStreamDestroy(pl.s_h2d);
+    cudaStreamDestroy(pl.s_d2h);
+    pl.ready = false;
+    host_pool().stop();
+}
+
+// true when the driver can DMA straight from/to this host pointer (cudaMallocHost / cudaHostRegister memory)
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 // host-buffer flavour: columns are separate host arrays
 static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k, uint32_t ek,
                           const uint64_t* omega_user) {
@@ -249,30 +404,90 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
         ZKB_TRY(check_ptr(in[cidx], "input column"));
         ZKB_TRY(check_ptr(out[cidx], "output column"));
     }
+    if (ncols == 0) return ZKB_OK;
+    ZKB_TRY(pipeline_init());
     Ctx& c = ctx();
-    HostIo& h = hostio();
+    Pipeline& pl = pipeline();
     const uint64_t N = 1ull << log_n, in_len = op == OP_C2E ? (1ull << k) : N;
-    // bound staging to ~2 GiB per buffer
-    size_t per = (size_t)((2ull << 30) / (N * 32));
+    const size_t col_out = (size_t)N * 32, col_in = (size_t)in_len * 32;
+    // group size: about a quarter of the batch, between 8 MiB and 256 MiB of output per group
+    size_t target = pl.group_bytes_override ? pl.group_bytes_override : (ncols * col_out) / 4;
+    if (!pl.group_bytes_override) {
+        if (target < ((size_t)8 << 20)) target = (size_t)8 << 20;
+        if (target > ((size_t)256 << 20)) target = (size_t)256 << 20;
+    }
+    size_t per = target / col_out;
     if (per < 1) per = 1;
     if (per > 4096) per = 4096;
-    for (size_t c0 = 0; c0 < ncols; c0 += per) {
-        size_t nc = ncols - c0 < per ? ncols - c0 : per;
-        ZKB_TRY(h.x.reserve(nc * N * 32));
-        ZKB_TRY(h.y.reserve(nc * N * 32));
-        uint4* d_in = h.x.as<uint4>();
-        if (op == OP_C2E) {
-            ZKB_TRY(h.in.reserve(nc * in_len * 32));
-            d_in = h.in.as<uint4>();
+    const int depth = pl.depth < 1 ? 1 : (pl.depth > PIPE_SLOTS ? PIPE_SLOTS : pl.depth);
+    std::vector<uint8_t> pinned_in(ncols), pinned_out(ncols);
+    for (size_t i = 0; i < ncols; ++i) {
+        pinned_in[i] = host_ptr_is_pinned(in[i]);
+        pinned_out[i] = (const void*)in[i] == (const void*)out[i] ? pinned_in[i] : host_ptr_is_pinned(out[i]);
+    }
+
+    // wait for a slot's device->host copies and hand pageable columns back to the caller
+    auto finish = [&](PipeSlot& s) -> int {
+        if (!s.busy) return ZKB_OK;
+        ZKB_CUDA_TRY(cudaEventSynchronize(s.ev_d2h));
+        for (size_t i = 0; i < s.nc; ++i)
+            if (!pinned_out[s.c0 + i]) host_pool().copy(out[s.c0 + i], (char*)s.h_out.p + i * col_out, col_out);
+        s.busy = false;
+        return ZKB_OK;
+    };
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(pl.s_h2d); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(pl.s_d2h);
+        for (auto& s : pl.slot) s.busy = false;
+        return rc;
+    };
+
+    static const bool trace = getenv("ZKB_TRACE") != nullptr;
+    size_t g = 0;
+    for (size_t c0 = 0; c0 < ncols; c0 += per, ++g) {
+        const size_t nc = ncols - c0 < per ? ncols - c0 : per;
+        PipeSlot& s = pl.slot[g % depth];
+        if (trace) fprintf(stderr, "[zkb] pipeline group %zu: columns [%zu, %zu) slot %zu\n", g, c0, c0 + nc, g % depth);
+        int rc = finish(s);
+        if (rc == ZKB_OK) rc = s.x.reserve(nc * col_out);
+        if (rc == ZKB_OK) rc = s.y.reserve(nc * col_out);
+        if (rc == ZKB_OK && op == OP_C2E) rc = s.in.reserve(nc * col_in);
+        bool any_pg_in = false, any_pg_out = false;
+        for (size_t i = 0; i < nc; ++i) { any_pg_in |= !pinned_in[c0 + i]; any_pg_out |= !pinned_out[c0 + i]; }
+        if (rc == ZKB_OK && any_pg_in) rc = s.h_in.reserve(nc * col_in);
+        if (rc == ZKB_OK && any_pg_out) rc = s.h_out.reserve(nc * col_out);
+        if (rc != ZKB_OK) return fail(rc);
+        char* d_in = op == OP_C2E ? (char*)s.in.p : (char*)s.x.p;
+        cudaError_t e = cudaSuccess;
+        for (size_t i = 0; i < nc && e == cudaSuccess; ++i) {
+            const void* src = in[c0 + i];
+            if (!pinned_in[c0 + i]) {
+                host_pool().copy((char*)s.h_in.p + i * col_in, src, col_in);
+                src = (char*)s.h_in.p + i * col_in;
+            }
+            e = cudaMemcpyAsync(d_in + i * col_in, src, col_in, cudaMemcpyHostToDevice, pl.s_h2d);
         }
-        for (size_t i = 0; i < nc; ++i)
-            ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(d_in) + i * in_len * 32, in[c0 + i], in_len * 32,
-                                         cudaMemcpyHostToDevice, c.stream));
-        ZKB_TRY(domain_op_dev(op, d_in, h.x.as<uint4>(), h.y.as<uint4>(), nc, k, ek, omega_user, c.stream));
-        for (size_t i = 0; i < nc; ++i)
-            ZKB_CUDA_TRY(cudaMemcpyAsync(out[c0 + i], reinterpret_cast<char*>(h.x.p) + i * N * 32, N * 32,
-                                         cudaMemcpyDeviceToHost, c.stream));
-        ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        if (e == cudaSuccess) e = cudaEventRecord(s.ev_h2d, pl.s_h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, s.ev_h2d, 0);
+        if (e != cudaSuccess) { set_error("host->device staging failed: %s", cudaGetErrorString(e)); return fail(ZKB_ERR_CUDA); }
+        rc = domain_op_dev(op, reinterpret_cast<const uint4*>(d_in), s.x.as<uint4>(), s.y.as<uint4>(), nc, k, ek, omega_user, c.stream);
+        if (rc != ZKB_OK) return fail(rc);
+        e = cudaEventRecord(s.ev_comp, c.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(pl.s_d2h, s.ev_comp, 0);
+        for (size_t i = 0; i < nc && e == cudaSuccess; ++i) {
+            void* dst = pinned_out[c0 + i] ? (void*)out[c0 + i] : (void*)((char*)s.h_out.p + i * col_out);
+            e = cudaMemcpyAsync(dst, (char*)s.x.p + i * col_out, col_out, cudaMemcpyDeviceToHost, pl.s_d2h);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(s.ev_d2h, pl.s_d2h);
+        if (e != cudaSuccess) { set_error("device->host staging failed: %s", cudaGetErrorString(e)); return fail(ZKB_ERR_CUDA); }
+        s.busy = true;
+        s.c0 = c0;
+        s.nc = nc;
+    }
+    // drain in submission order
+    for (size_t i = 0; i < (size_t)depth; ++i) {
+        PipeSlot& s = pl.slot[(g + i) % depth];
+        int rc = finish(s);
+        if (rc != ZKB_OK) return fail(rc);
     }
     return ZKB_OK;
 }
@@ -349,12 +564,14 @@ void zkb_shutdown(void) {
     if (!c.inited) return;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    dist_shutdown();
     for (auto& kv : srs_map()) { kv.second->bases.release(); kv.second->table.release(); delete kv.second; }
     srs_map().clear();
     ntt_clear_plans();
     msm_release_workspace();
     HostIo& h = hostio();
     h.scalars.release(); h.bases.release(); h.x.release(); h.y.release(); h.in.release();
+    pipeline_release();
     for (auto& kv : c.timers)
         for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     c.timers.clear();
@@ -575,6 +792,30 @@ int zkb_extended_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint3
 }
 int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, void* stream) {
     return dev_common(OP_L2C, d_data, d_data, d_scratch, ncols, k, k, nullptr, stream);
+}
+
+// ---- host memory / scheduler controls ---------------------------------------------------------------------------------------
+int zkb_host_register(void* ptr, size_t bytes) {
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(ptr, "ptr"));
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return ZKB_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return ZKB_ERR_CUDA; }
+    return ZKB_OK;
+}
+int zkb_host_unregister(void* ptr) {
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(ptr, "ptr"));
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostUnregister failed: %s", cudaGetErrorString(e)); return ZKB_ERR_CUDA; }
+    return ZKB_OK;
+}
+int zkb_pipeline_set(int depth, size_t group_bytes) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    if (depth < 0 || depth > PIPE_SLOTS) { set_error("pipeline depth must be in [0, %d] (0 = default)", PIPE_SLOTS); return ZKB_ERR_ARG; }
+    pipeline().depth = depth ? depth : PIPE_SLOTS;
+    pipeline().group_bytes_override = group_bytes;
+    return ZKB_OK;
 }
 
 // ---- tuning / measurement ----------------------------------------------------------------------------------------------------

@@ -78,7 +78,8 @@ template <int LOGR>
 static void emu_run_pass(const NttPassArgs& a, uint32_t nthreads, uint64_t nctas, uint32_t cols, size_t smem_bytes) {
     std::vector<uint4> sm(smem_bytes / 16);
     for (uint32_t col = 0; col < cols; ++col)
-        for (uint64_t cta = 0; cta < nctas; ++cta) {
+        for (uint64_t cta_local = 0; cta_local < nctas; ++cta_local) {
+            const uint64_t cta = ntt_dist_cta(a, cta_local);
             for (uint32_t t = 0; t < nthreads; ++t) ntt_phase_load<LOGR>(a, sm.data(), t, nthreads, cta, col);
             int left = LOGR;
             while (left > 0) {
@@ -139,6 +140,43 @@ EMU_EXPORT int zkb_emu_ntt(const uint64_t* in, uint64_t in_len, uint64_t* out, u
                 if (out_scale3) { a.out_scale[m][2 * i] = (uint32_t)out_scale3[4 * m + i]; a.out_scale[m][2 * i + 1] = (uint32_t)(out_scale3[4 * m + i] >> 32); }
             }
         emu_dispatch_pass(a, g.lr[p], ntt_cta_threads(g, p), ntt_cta_count(g, p), cols, ntt_cta_smem_bytes(g, p));
+    }
+    return 0;
+}
+
+
+// ---- distributed NTT (one transform sharded over 2^log_g ranks, peer memory emulated by plain pointers) -----------
+// phase 0: pass 0 of `rank` (loads from every rank's A slice, stores to every rank's W slice);
+// phase 1: the remaining passes of `rank` (middle passes local in W, final pass scatters to every rank's O slice).
+// The caller provides the barrier between the phases (a loop over ranks in one process, or a gloo barrier between
+// processes sharing the slices through POSIX shared memory).
+EMU_EXPORT int zkb_emu_ntt_dist_phase(int phase, uint32_t rank, uint32_t log_g, uint32_t log_n, const uint64_t* omega,
+                                      uint64_t* const* A, uint64_t* const* W, uint64_t* const* O) {
+    if (log_n < 1 || log_n > 28 || log_g > 3) return -1;
+    const uint64_t N = 1ull << log_n;
+    NttGeometry g = ntt_geometry(log_n);
+    if (!ntt_dist_supported(g, log_g)) return -2;
+    Fr w = fr_from_u64(omega);
+    std::vector<uint4> tw_lo, tw_hi, tw_r[NTT_MAX_PASSES];
+    pow_table(tw_lo, w, 1ull << g.tw_h, 0);
+    pow_table(tw_hi, w, N >> g.tw_h ? N >> g.tw_h : 1, g.tw_h);
+    for (uint32_t p = 0; p < g.npass; ++p) pow_table(tw_r[p], w, 1ull << g.lr[p], log_n - g.lr[p]);
+    for (uint32_t p = 0; p < g.npass; ++p) {
+        if ((phase == 0) != (p == 0)) continue;
+        NttPassArgs a{};
+        bool fin = p + 1 == g.npass;
+        a.log_n = log_n; a.npass = g.npass; a.pass = p;
+        for (uint32_t q = 0; q < g.npass; ++q) a.lr[q] = g.lr[q];
+        a.log_t = g.log_t[p];
+        a.is_final = fin;
+        a.tw_r = tw_r[p].data(); a.tw_hi = tw_hi.data(); a.tw_lo = tw_lo.data(); a.tw_h = g.tw_h;
+        a.in_len = N;
+        a.dist_log_g = log_g; a.dist_rank = rank; a.dist_log_slice = log_n - log_g;
+        for (uint32_t r = 0; r < (1u << log_g); ++r) {
+            a.peer_src[r] = reinterpret_cast<const uint4*>(p == 0 ? A[r] : W[r]);
+            a.peer_dst[r] = reinterpret_cast<uint4*>(fin ? O[r] : W[r]);
+        }
+        emu_dispatch_pass(a, g.lr[p], ntt_cta_threads(g, p), ntt_cta_count(g, p) >> log_g, 1, ntt_cta_smem_bytes(g, p));
     }
     return 0;
 }

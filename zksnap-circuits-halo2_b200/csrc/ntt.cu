@@ -34,7 +34,7 @@ static int launch_pass(const NttPassArgs& a, dim3 grid, uint32_t threads, size_t
     return ZKB_OK;
 }
 
-static int dispatch_pass(uint32_t logr, const NttPassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
+int ntt_launch_pass(uint32_t logr, const NttPassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
     switch (logr) {
 #define C(L) case L: return launch_pass<L>(a, grid, threads, smem, s);
         C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10)
@@ -123,7 +123,7 @@ int ntt_run(const NttPlan& plan, const NttIo& io, cudaStream_t s) {
                 a.out_scale[m][i] = io.out_scale ? io.out_scale[m].l[i] : 0;
             }
         dim3 grid((unsigned)ntt_cta_count(g, p), (unsigned)io.cols);
-        ZKB_TRY(dispatch_pass(g.lr[p], a, grid, ntt_cta_threads(g, p), ntt_cta_smem_bytes(g, p), s));
+        ZKB_TRY(ntt_launch_pass(g.lr[p], a, grid, ntt_cta_threads(g, p), ntt_cta_smem_bytes(g, p), s));
     }
     return ZKB_OK;
 }

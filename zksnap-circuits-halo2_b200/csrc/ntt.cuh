@@ -30,6 +30,7 @@
 namespace zkb {
 
 constexpr int NTT_MAX_PASSES = 4;
+constexpr int NTT_MAX_RANKS = 8;
 
 struct NttPassArgs {
     const uint4* src;     // column 0 of the input  (element = 2 x uint4)
@@ -53,6 +54,14 @@ struct NttPassArgs {
     uint32_t out_scale_on;    // last pass: multiply by out_scale[i % 3]
     uint32_t in_scale[3][8];
     uint32_t out_scale[3][8];
+    // distributed mode (one NTT sharded over 2^dist_log_g GPUs, rank r owns the contiguous slice
+    // [r * 2^dist_log_slice, (r+1) * 2^dist_log_slice) of every buffer): loads and stores address element gi through
+    // peer_src/peer_dst[gi >> dist_log_slice] — peer HBM mapped over NVLink (CUDA IPC).  src/dst are unused.
+    uint32_t dist_log_g;      // 0 = single GPU
+    uint32_t dist_rank;
+    uint32_t dist_log_slice;
+    const uint4* peer_src[NTT_MAX_RANKS];
+    uint4* peer_dst[NTT_MAX_RANKS];
 };
 
 // shared memory is split in two planes (low / high 16 bytes) so a warp's 128-bit accesses are conflict-free
@@ -66,6 +75,34 @@ ZKB_HD Fr fr_from_words(const uint32_t (&w)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.l[i] = w[i];
     return r;
+}
+
+// ---- element addressing (single GPU: column-major batch; distributed: owner slice over peer memory) -----------
+ZKB_HD const uint4* ntt_src_elem(const NttPassArgs& a, uint32_t col, uint64_t gi) {
+    if (a.dist_log_g) return a.peer_src[gi >> a.dist_log_slice] + 2 * (gi & ((1ull << a.dist_log_slice) - 1));
+    return a.src + 2 * (a.src_col_stride * col + gi);
+}
+ZKB_HD uint4* ntt_dst_elem(const NttPassArgs& a, uint32_t col, uint64_t go) {
+    if (a.dist_log_g) return a.peer_dst[go >> a.dist_log_slice] + 2 * (go & ((1ull << a.dist_log_slice) - 1));
+    return a.dst + 2 * (a.dst_col_stride * col + go);
+}
+
+// Distributed mode: CTA `local` of this rank's grid -> CTA index of the single-GPU enumeration.
+//   pass 0        : any split of the lo tiles works (every CTA reads all ranks); contiguous share.
+//   middle passes : after pass 0 rank r holds k_1 in [r R_1/G, (r+1) R_1/G) — the leading part of the stored hi
+//                   index, i.e. a contiguous CTA range: these passes touch local memory only.
+//   final pass    : CTAs enumerate K = k_1 + R_1 * rest (k_1 least significant); the rank's share is the K with
+//                   k_1 in its block.  Its stores scatter to every rank's output slice (natural order).
+ZKB_HD uint64_t ntt_dist_cta(const NttPassArgs& a, uint64_t local) {
+    if (!a.dist_log_g) return local;
+    if (!a.is_final) {
+        const uint64_t per_rank = ((1ull << a.log_n) >> (a.lr[a.pass] + a.log_t)) >> a.dist_log_g;
+        return (uint64_t)a.dist_rank * per_rank + local;
+    }
+    const uint32_t log_b = a.lr[0] - a.dist_log_g - a.log_t;  // T-wide k_1 tiles per rank
+    const uint64_t k1_tile = local & ((1ull << log_b) - 1), rest = local >> log_b;
+    const uint64_t K0 = ((uint64_t)a.dist_rank << (a.lr[0] - a.dist_log_g)) + (k1_tile << a.log_t) + (rest << a.lr[0]);
+    return K0 >> a.log_t;
 }
 
 // ---- geometry helpers ---------------------------------------------------------------------------------
@@ -128,7 +165,6 @@ ZKB_HD void ntt_phase_load(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32
     const uint32_t E = R << a.log_t;
     uint4* lo = sm;
     uint4* hi = sm + ntt_sm_plane<LOGR>(a);
-    const uint4* src = a.src + 2 * a.src_col_stride * col;
 
     uint32_t log_stride = 0;  // log2 S_p
     for (uint32_t q = a.pass + 1; q < a.npass; ++q) log_stride += a.lr[q];
@@ -162,7 +198,7 @@ ZKB_HD void ntt_phase_load(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32
         }
         Fr v;
         if (gi < a.in_len) {
-            v = fr_load2(src, gi);
+            v = fr_load2(ntt_src_elem(a, col, gi), 0);
             if (a.in_scale_on) {
                 uint32_t m = (uint32_t)(gi % 3);
                 if (m) v = fp_mul(v, fr_from_words(a.in_scale[m]));
@@ -256,7 +292,6 @@ ZKB_HD void ntt_phase_store(const NttPassArgs& a, const uint4* sm, uint32_t tid,
     const uint32_t E = R << a.log_t;
     const uint4* lo = sm;
     const uint4* hi = sm + ntt_sm_plane<LOGR>(a);
-    uint4* dst = a.dst + 2 * a.dst_col_stride * col;
 
     uint32_t log_stride = 0;
     for (uint32_t q = a.pass + 1; q < a.npass; ++q) log_stride += a.lr[q];
@@ -279,7 +314,7 @@ ZKB_HD void ntt_phase_store(const NttPassArgs& a, const uint4* sm, uint32_t tid,
         if (!a.is_final) go = base + ((uint64_t)k << log_stride) + c;
         else go = K0 + c + ((uint64_t)k << log_q);
         if (a.is_final && a.out_scale_on) v = fp_mul(v, fr_from_words(a.out_scale[go % 3]));
-        fr_store2(dst, go, v);
+        fr_store2(ntt_dst_elem(a, col, go), 0, v);
     }
 }
 
@@ -290,6 +325,7 @@ ZKB_HD int ntt_num_rounds(int logr) { return (logr + 2) / 3; }
 template <int LOGR, class Barrier>
 ZKB_HD void ntt_cta_program(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32_t nthreads, uint64_t cta,
                             uint32_t col, Barrier& bar) {
+    cta = ntt_dist_cta(a, cta);
     ntt_phase_load<LOGR>(a, sm, tid, nthreads, cta, col);
     bar.sync();
     int left = LOGR;

@@ -29,5 +29,8 @@ struct NttIo {
 int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPlan** out);
 int ntt_run(const NttPlan& plan, const NttIo& io, cudaStream_t s);
 void ntt_clear_plans();
+// one pass of the multi-pass NTT (grid.x CTAs of R*T elements, grid.y columns); used by the sharded driver in dist.cu
+int ntt_launch_pass(uint32_t logr, const NttPassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s);
+void dist_shutdown();
 
 }  // namespace zkb

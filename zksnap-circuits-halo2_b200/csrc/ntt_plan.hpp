@@ -41,6 +41,17 @@ inline NttGeometry ntt_geometry(uint32_t log_n) {
     return g;
 }
 
+// One transform sharded over 2^log_g GPUs (ntt.cuh "distributed mode"): needs >= 2 passes (pass 0 is the exchange
+// step), at least one pass-0 tile per rank, and T-wide k_1 tiles of the final pass inside one rank's k_1 block.
+inline bool ntt_dist_supported(const NttGeometry& g, uint32_t log_g) {
+    if (log_g == 0) return true;
+    if (log_g > 3 || g.npass < 2) return false;
+    uint32_t log_s1 = g.log_n - g.lr[0];
+    if (log_s1 < g.log_t[0] + log_g) return false;
+    if (g.lr[0] < log_g + g.log_t[g.npass - 1]) return false;
+    return true;
+}
+
 inline uint32_t ntt_cta_threads(const NttGeometry& g, uint32_t p) {
     uint32_t e = 1u << (g.lr[p] + g.log_t[p]);
     uint32_t t = e / 8;

@@ -64,3 +64,50 @@ def sharded_columns(cols: list, op: Callable[[list], list], group=None) -> dict[
     mine = columns_for_rank(len(cols), rank, world)
     out = op([cols[i] for i in mine]) if mine else []
     return dict(zip(mine, out))
+
+
+# ---- one NTT sharded over the ranks --------------------------------------------------------------
+def ntt_slice(log_n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous natural-order slice [offset, offset+len) of a 2^log_n transform owned by `rank` (input and output)."""
+    assert world & (world - 1) == 0 and (1 << log_n) >= world, "world must be a power of two not larger than the transform"
+    ln = (1 << log_n) // world
+    return rank * ln, ln
+
+
+class ShardedNtt:
+    """best_fft of one vector sharded over the process group: rank r passes a[r N/G : (r+1) N/G] and receives the same
+    slice of the result.  The exchange runs inside the NTT kernels over NVLink peer mappings (csrc/dist.cu); the process
+    group is used once, to all-gather the CUDA IPC handles."""
+
+    def __init__(self, max_log_n: int, group=None, device=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+
+        self.lib = halo2.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = 256  # ZKB_DIST_HANDLE_BYTES
+        blob = (ctypes.c_uint8 * nbytes)()
+        halo2.check(self.lib.zkb_dist_create(self.rank, self.world, max_log_n, blob))
+        t = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).clone()
+        if device is not None:
+            t = t.to(device)
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t, group=group)
+        allb = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        buf = (ctypes.c_uint8 * len(allb)).from_buffer_copy(allb)
+        halo2.check(self.lib.zkb_dist_connect(buf))
+        self.max_log_n = max_log_n
+
+    def best_fft_slice(self, a_slice: np.ndarray, omega_: np.ndarray, log_n: int) -> np.ndarray:
+        a = np.ascontiguousarray(a_slice, dtype=np.uint64).reshape(-1, 4)
+        _, ln = ntt_slice(log_n, self.rank, self.world)
+        assert a.shape[0] == ln, "assertion failed: slice.len() == (1 << log_n) / world"
+        out = np.empty_like(a)
+        w = np.ascontiguousarray(omega_, dtype=np.uint64).reshape(4)
+        halo2.check(self.lib.zkb_dist_ntt_fr(halo2._p(a), halo2._p(out), halo2._p(w), log_n))
+        return out
+
+    def close(self) -> None:
+        self.lib.zkb_dist_destroy()
