@@ -34,6 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 LOG_N_MSM = int(os.environ.get("ZKB_BENCH_LOG_N", "24"))
 NTT_LOG_N = int(os.environ.get("ZKB_BENCH_NTT_LOG_N", "22"))
 NTT_COLS = int(os.environ.get("ZKB_BENCH_NTT_COLS", "16"))
+SHARDED_LOG_N = int(os.environ.get("ZKB_BENCH_SHARDED_LOG_N", "26"))
 CPU_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_CPU_LOG_N", "20"))
 METRIC = "BN254 G1 MSM throughput (2^%d points per GPU, SRS resident)" % LOG_N_MSM
 
@@ -198,6 +199,12 @@ def main():
     outp = out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
     c_bits, n_win, chunk = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
     lib.zkb_msm_get_params(n, ctypes.byref(c_bits), ctypes.byref(n_win), ctypes.byref(chunk))
+    # the commit runs through the SRS window table, whose window width is chosen by its own cost model: report that one
+    t_bits, t_bytes = ctypes.c_uint32(), ctypes.c_uint64()
+    lib.zkb_srs_precompute(params.handle_g, ctypes.byref(t_bits), ctypes.byref(t_bytes))
+    if t_bits.value:
+        c_bits.value = t_bits.value
+        n_win.value = (255 + t_bits.value - 1) // t_bits.value
 
     def step_dev():
         rc = lib.zkb_msm_g1_srs_dev(params.handle_g, 0, ctypes.c_void_p(d_scal.data_ptr()), n, outp, sptr)
@@ -345,6 +352,55 @@ def main():
                                 "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound, see DESIGN.md"}}
         del cols_np
 
+    # ---- N > 1: one 2^26 NTT sharded over the ranks (exchange fused into the NTT passes over NVLink peer memory) ----------------
+    sharded_obj = None
+    if world > 1 and not args.skip_ntt and (world & (world - 1)) == 0 and world <= 8:
+        k = SHARDED_LOG_N
+        sh = zdist.ShardedNtt(k, device=dev)
+        off, ln = zdist.ntt_slice(k, rank, world)
+        w = zkb.omega(k)
+        wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+        # parity of the measured configuration, size-independent: NTT(delta_0) = (1, 1, ..., 1)
+        d_in = torch.zeros(ln * 4, dtype=torch.int64, device=dev)
+        one = torch.from_numpy(np.array([0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f],
+                                        dtype=np.uint64).view(np.int64)).to(dev)
+        if rank == 0:
+            d_in[:4] = one
+        d_out = torch.empty_like(d_in)
+        rc = lib.zkb_dist_ntt_fr_dev(ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr()), wp, k, sptr)
+        if rc != 0 or lib.zkb_dist_status(sptr) != 0:
+            raise RuntimeError(lib.zkb_last_error().decode())
+        sh_ok = bool((d_out.view(-1, 4) == one).all().item())
+        g = torch.Generator(device=dev)
+        g.manual_seed(0xD157 + rank)
+        d_in = torch.randint(0, 1 << 60, (ln * 4,), dtype=torch.int64, device=dev, generator=g)
+        lib.zkb_dist_ntt_fr_dev(ctypes.c_void_p(d_in.data_ptr()), None, wp, k, sptr)  # loads the symmetric input slice
+        for _ in range(args.warmup):
+            lib.zkb_dist_ntt_fr_dev(None, None, wp, k, sptr)
+        barrier()
+        launches2 = zkb.launch_count()
+        e0.record(stream)
+        for _ in range(args.steps):
+            lib.zkb_dist_ntt_fr_dev(None, None, wp, k, sptr)
+        e1.record(stream)
+        if lib.zkb_dist_status(sptr) != 0:
+            raise RuntimeError(lib.zkb_last_error().decode())
+        barrier()
+        sms = e0.elapsed_time(e1) / args.steps
+        launches += zkb.launch_count() - launches2
+        t = torch.tensor([sms, 0.0 if sh_ok else 1.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms, sh_ok = float(t[0].item()), t[1].item() == 0.0
+        N = 1 << k
+        sharded_obj = {"workload": "one best_fft of 2^%d sharded over %d GPUs (contiguous slices in, contiguous slices out)" % (k, world),
+                       "value": N / (sms * 1e-3), "unit": "elems/s", "ms_per_step": sms, "parity_checked": sh_ok,
+                       "exchange": "fused into NTT pass 0 (peer loads+stores) and the final pass (peer stores) over NVLink; device-side barriers",
+                       "nvlink_bytes_per_gpu_per_step": int(3 * (world - 1) / world * ln * 32),
+                       "roofline": {"bound": "hbm", "achieved": 64.0 * N / (sms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
+                                    "frac": 64.0 * N / (sms * 1e-3) / 1e9 / (hbm_peak * world)}}
+        parity = parity and sh_ok
+        sh.close()
+        del d_in, d_out
     note("ntt done")
     # ---- CPU baseline on this box (rank 0, N=1 only) ---------------------------------------------------------------------------
     cpu = None
@@ -360,11 +416,11 @@ def main():
             "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
             "config": {"workload": "msm_g1_2^%d_uniform_per_gpu" % LOG_N_MSM, "sharding": "srs_point_range_per_rank, host fold",
                        "l2": "inputs_exceed_l2 (512 MiB scalars + 1 GiB bases per step)", "window_bits": c_bits.value,
-                       "chunk": chunk.value},
+                       "windows": n_win.value, "srs_window_table_bytes": int(t_bytes.value), "chunk": chunk.value},
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": n * 32 * world,
                     "d2h_bytes_per_step": n_win.value * 128 * world, "timer": "wall clock around the C-ABI call (includes host fold)"},
             "gpu_launches": int(launches), "parity_checked": parity, "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clock_info, "ntt": ntt_obj,
+            "clocks": clock_info, "ntt": ntt_obj, "sharded_ntt": sharded_obj,
         }
         print(json.dumps(line))
     params.close()

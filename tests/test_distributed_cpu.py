@@ -110,6 +110,10 @@ def _sharded_ntt_worker(rank, world, port, k, ret):
 def test_sharded_ntt_two_ranks_shared_memory():
     import torch.multiprocessing as mp
 
+    import emu
+    from oracle import coracle
+    emu.build()       # compile once in the parent so the two ranks do not race on the shared objects
+    coracle.build()
     world = 2
     port = 31500 + (os.getpid() % 2000)
     mgr = mp.Manager()

@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Measurement sweeps of SURVEY.md §8(d) on one B200 (device-resident kernels, CUDA events; host-ABI variants where stated).
+
+  python tools/sweep.py --out gpurun_out/sweep.jsonl [--sections msm ntt shapes replay] [--max-log-n 26]
+
+Sections
+  msm     BN254 G1 MSM, n = 2^16 .. 2^max, uniform scalars against a resident SRS (window table on); witness-like (W) and
+          all-equal (E) scalar distributions at 2^22 / 2^24; per-kernel split from the library's CUDA-event timers.
+  ntt     best_fft, log n in {18,20,22,24,26} x cols in {1,4,16,64} (capped by memory); coeff_to_extended (k -> k+2),
+          extended_to_coeff and lagrange_to_coeff at the prover's sizes.
+  shapes  circuit-shaped batches: voter (2^13 x 256 and 2^15 x 423 columns: batched commits + batched iNTT + coset NTT),
+          state-transition (2^15 x 8).
+  replay  the wrapper prover's op sequence at k = 22 (22 MSMs of 2^22, 13 iNTTs of 2^22, 16 coset NTTs
+          2^22 -> 2^24, 1 iNTT of 2^24) replayed in prover order: "kernel" (operands resident in HBM) and "dropin"
+          (every op through the host-buffer C ABI with pinned host operands, PCIe included).
+Each result is one JSON line.  Bases are [b_i]G with known discrete logs; every MSM size is parity-checked against
+(sum s_i b_i) G by the oracle (checker, outside the timed region).
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from util import random_field  # noqa: E402
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+def witness_like(s, seed):
+    """distribution W of SURVEY.md §8d: 50 % zero, 25 % < 2^16, 20 % < 2^88, 5 % uniform (canonical integers are fine:
+    the library converts from Montgomery form, so these are 'some' field elements with that digit sparsity only if
+    given in Montgomery form — we convert the small values to Montgomery form with the oracle)."""
+    from oracle import coracle
+    n = s.shape[0]
+    rng = np.random.default_rng(seed)
+    u = rng.random(n)
+    v = np.zeros_like(s)
+    small = (u >= 0.5) & (u < 0.75)
+    v[small, 0] = rng.integers(0, 1 << 16, size=int(small.sum()), dtype=np.uint64)
+    mid = (u >= 0.75) & (u < 0.95)
+    v[mid, 0] = rng.integers(0, 2**64, size=int(mid.sum()), dtype=np.uint64)
+    v[mid, 1] = rng.integers(0, 1 << 24, size=int(mid.sum()), dtype=np.uint64)
+    out = coracle.fr_to_mont(v)
+    big = u >= 0.95
+    out[big] = s[big]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    ap.add_argument("--sections", nargs="+", default=["msm", "ntt", "shapes", "replay"])
+    ap.add_argument("--max-log-n", type=int, default=26)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    from oracle import coracle
+
+    coracle.build()
+    zkb = importlib.import_module("zksnap-circuits-halo2_b200")
+    zkb.init(0)
+    lib = zkb.lib()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    fout = open(args.out, "a")
+    peak = ctypes.c_double(0)
+    lib.zkb_measure_imad_peak(ctypes.byref(peak))
+    hbm = 6459.6
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        hbm = float(json.load(open(pk))["hbm_gbs"])
+
+    def emit(obj):
+        line = json.dumps(obj)
+        print(line, flush=True)
+        fout.write(line + "\n")
+        fout.flush()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=args.reps, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    def dptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    # ---- MSM ------------------------------------------------------------------------------------------------------------
+    if "msm" in args.sections or "replay" in args.sections or "shapes" in args.sections:
+        kmax = args.max_log_n if "msm" in args.sections else 22
+        t = time.perf_counter()
+        dlog_all = random_field(1 << kmax, 0xB45E)
+        bases_all = zkb.g1_fixed_base_mul(dlog_all)
+        emit({"op": "setup_bases", "log_n": kmax, "s": time.perf_counter() - t})
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(u64p)
+
+    def msm_case(k, dist, params, scal):
+        n = 1 << k
+        d_s = torch.from_numpy(scal.view(np.int64)).to(dev)
+
+        def run():
+            rc = lib.zkb_msm_g1_srs_dev(params.handle_g, 0, dptr(d_s), n, outp, sptr)
+            assert rc == 0, lib.zkb_last_error()
+
+        run()
+        want = coracle.g1_mul(coracle.g1_generator(), coracle.fr_inner_product(scal, dlog_all[:n]))
+        ok = bool((out[:8] == want).all())
+        zkb.prof.enable(True)
+        zkb.prof.reset()
+        ms = timed(run, warm=1)
+        parts = {}
+        for name in ("msm_digits", "msm_sort", "msm_accumulate", "msm_reduce"):
+            t_ms, cnt = zkb.prof.get(name)
+            parts[name] = t_ms / max(cnt, 1)
+        zkb.prof.enable(False)
+        cb, nw, ch = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        tc, tb = ctypes.c_uint32(), ctypes.c_uint64()
+        lib.zkb_srs_precompute(params.handle_g, ctypes.byref(tc), ctypes.byref(tb))
+        c = tc.value
+        if not c:
+            lib.zkb_msm_get_params(n, ctypes.byref(cb), ctypes.byref(nw), ctypes.byref(ch))
+            c = cb.value
+        W = (255 + c - 1) // c
+        alg = n * W * 10 * 128
+        acc = parts["msm_accumulate"]
+        emit({"op": "msm", "log_n": k, "dist": dist, "ms": ms, "pts_per_s": n / (ms * 1e-3), "parity": ok, "window_bits": c,
+              "windows": W, "table_GiB": tb.value / 2**30, "kernels_ms": parts,
+              "accumulate_frac_of_imad_peak": alg / (acc * 1e-3) / peak.value if acc else None})
+        del d_s
+
+    if "msm" in args.sections:
+        for k in range(16, args.max_log_n + 1, 2):
+            n = 1 << k
+            params = zkb.ParamsKZG(k, bases_all[:n])
+            s = random_field(n, 0x5EED0000 + k)
+            msm_case(k, "U", params, s)
+            if k in (22, 24):
+                msm_case(k, "W", params, witness_like(s, k))
+                e = s.copy()
+                e[:] = s[0]
+                msm_case(k, "E", params, e)
+            params.close()
+            del s
+
+    # ---- NTT ------------------------------------------------------------------------------------------------------------
+    def ntt_case(op, k, cols):
+        ek = k + 2 if op in ("coeff_to_extended", "extended_to_coeff") else k
+        n, N = 1 << k, 1 << ek
+        in_len = n if op == "coeff_to_extended" else N
+        need = (in_len + 2 * N) * cols * 32
+        free_b, _ = torch.cuda.mem_get_info()
+        if need > 0.8 * free_b or N * cols > (1 << 30):
+            return
+        g = torch.Generator(device=dev)
+        g.manual_seed(0xF0F0 + k)
+        d_in = torch.randint(0, 1 << 62, (in_len * cols * 4,), dtype=torch.int64, device=dev, generator=g)
+        d_in[3::4] &= (1 << 60) - 1  # top limb < 2^60: every element < r (valid canonical Montgomery residues)
+        d_o = torch.empty(N * cols * 4, dtype=torch.int64, device=dev)
+        d_s = torch.empty_like(d_o)
+        w = zkb.omega(ek)
+        wp = w.ctypes.data_as(u64p)
+        if op == "best_fft":
+            fn = lambda: lib.zkb_ntt_fr_dev(dptr(d_in), dptr(d_s), cols, wp, k, sptr)
+            alg = 64.0 * N * cols
+        elif op == "lagrange_to_coeff":
+            fn = lambda: lib.zkb_lagrange_to_coeff_dev(dptr(d_in), dptr(d_s), cols, k, sptr)
+            alg = 64.0 * N * cols
+        elif op == "coeff_to_extended":
+            fn = lambda: lib.zkb_coeff_to_extended_dev(dptr(d_in), dptr(d_o), dptr(d_s), cols, k, ek, sptr)
+            alg = 160.0 * n * cols
+        else:
+            fn = lambda: lib.zkb_extended_to_coeff_dev(dptr(d_in), dptr(d_s), cols, k, ek, sptr)
+            alg = 224.0 * n * cols
+        assert fn() == 0, lib.zkb_last_error()
+        ms = timed(fn)
+        emit({"op": op, "log_n": k, "extended_log_n": ek, "cols": cols, "ms": ms, "elems_per_s": N * cols / (ms * 1e-3),
+              "alg_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / hbm,
+              "modmul_per_s": 0.5 * ek * N * cols / (ms * 1e-3)})
+        del d_in, d_o, d_s
+        torch.cuda.empty_cache()
+
+    if "ntt" in args.sections:
+        for k in (18, 20, 22, 24, 26):
+            if k > args.max_log_n:
+                continue
+            for cols in (1, 4, 16, 64):
+                ntt_case("best_fft", k, cols)
+        for k in (13, 15, 20, 22):
+            ntt_case("coeff_to_extended", k, 16 if k >= 20 else 256)
+            ntt_case("extended_to_coeff", k, 1)
+            ntt_case("lagrange_to_coeff", k, 16 if k >= 20 else 256)
+
+    # ---- circuit-shaped batches (host ABI, pinned operands: what the shim would call) ---------------------------------------
+    def pinned(a):
+        return torch.from_numpy(a.view(np.int64)).pin_memory()
+
+    def col_ptrs(t, ncols, stride_bytes):
+        return (u64p * ncols)(*[ctypes.cast(t.data_ptr() + i * stride_bytes, u64p) for i in range(ncols)])
+
+    if "shapes" in args.sections:
+        for name, k, ncols in (("voter_bench_k13", 13, 256), ("voter_full_k15", 15, 423), ("state_transition_k15", 15, 8)):
+            n = 1 << k
+            params = zkb.ParamsKZG(k, bases_all[:n], bases_all[:n])
+            h = pinned(random_field(n * ncols, 77 + k))
+            ptrs = col_ptrs(h, ncols, n * 32)
+            outs = np.zeros((ncols, 12), dtype=np.uint64)
+            h_ext = torch.empty(4 * n * ncols * 4, dtype=torch.int64).pin_memory()
+            eptrs = col_ptrs(h_ext, ncols, 4 * n * 32)
+            res = {"op": "shape", "name": name, "log_n": k, "cols": ncols}
+            for label, fn in (
+                ("commit_lagrange_batch", lambda: lib.zkb_msm_g1_srs_batch(params.handle_g_lagrange, ptrs, ncols, n, outs.ctypes.data_as(u64p))),
+                ("lagrange_to_coeff_batch", lambda: lib.zkb_lagrange_to_coeff_batch(ptrs, ncols, k)),
+                ("coeff_to_extended_batch", lambda: lib.zkb_coeff_to_extended_batch(ptrs, eptrs, ncols, k, k + 2)),
+            ):
+                assert fn() == 0, lib.zkb_last_error()
+                best = 1e30
+                for _ in range(args.reps):
+                    t = time.perf_counter()
+                    assert fn() == 0
+                    best = min(best, time.perf_counter() - t)
+                res[label + "_ms"] = best * 1e3
+            res["commits_per_s"] = ncols / (res["commit_lagrange_batch_ms"] * 1e-3)
+            res["msm_pts_per_s"] = ncols * n / (res["commit_lagrange_batch_ms"] * 1e-3)
+            emit(res)
+            params.close()
+            del h, h_ext
+
+    # ---- wrapper prover replay at k = 22 -------------------------------------------------------------------------------------
+    if "replay" in args.sections:
+        k, ek = 22, 24
+        n, N = 1 << k, 1 << ek
+        n_msm, n_intt, n_c2e = 22, 13, 16
+        params = zkb.ParamsKZG(k, bases_all[:n], bases_all[:n])
+        cols = random_field(n * 4, 0x22)          # four distinct columns reused round-robin (host memory bound)
+        h_cols = pinned(cols).view(-1)
+        d_cols = h_cols.to(dev)
+        d_work = torch.empty(n * n_c2e * 4, dtype=torch.int64, device=dev)
+        d_ext = torch.empty(N * 4 * 4, dtype=torch.int64, device=dev)      # 4 extended columns in flight
+        d_scr = torch.empty_like(d_ext)
+
+        def kernel_replay():
+            for i in range(n_msm):   # advice / lookup / permutation / vanishing / h-piece / multiopen commits
+                h = params.handle_g_lagrange if i < 12 else params.handle_g
+                assert lib.zkb_msm_g1_srs_dev(h, 0, ctypes.c_void_p(d_cols.data_ptr() + (i % 4) * n * 32), n, outp, sptr) == 0
+            d_work[: n * 4 * 4].copy_(d_cols)
+            for i in range(0, n_intt, 4):  # lagrange_to_coeff of the committed columns, 4 at a time
+                nc = min(4, n_intt - i)
+                assert lib.zkb_lagrange_to_coeff_dev(dptr(d_work), dptr(d_scr), nc, k, sptr) == 0
+            for i in range(0, n_c2e, 4):   # evaluate_h: coeff_to_extended of every polynomial
+                assert lib.zkb_coeff_to_extended_dev(dptr(d_cols), dptr(d_ext), dptr(d_scr), 4, k, ek, sptr) == 0
+            assert lib.zkb_extended_to_coeff_dev(dptr(d_ext), dptr(d_scr), 1, k, ek, sptr) == 0  # h poly
+
+        ms = timed(kernel_replay, reps=2)
+        emit({"op": "wrapper_k22_replay", "mode": "kernel (operands resident in HBM)", "ms": ms,
+              "ops": {"msm_2^22": n_msm, "intt_2^22": n_intt, "coset_ntt_2^22_to_2^24": n_c2e, "intt_2^24": 1}})
+
+        h_ext = torch.empty(N * 4 * 4, dtype=torch.int64).pin_memory()
+        in4 = col_ptrs(h_cols, 4, n * 32)
+        out4 = col_ptrs(h_ext, 4, N * 32)
+
+        def dropin_replay():
+            for i in range(n_msm):
+                h = params.handle_g_lagrange if i < 12 else params.handle_g
+                assert lib.zkb_msm_g1_srs(h, ctypes.cast(h_cols.data_ptr() + (i % 4) * n * 32, u64p), n, outp) == 0
+            for i in range(0, n_intt, 4):
+                nc = min(4, n_intt - i)
+                assert lib.zkb_lagrange_to_coeff_batch(in4, nc, k) == 0
+            for i in range(0, n_c2e, 4):
+                assert lib.zkb_coeff_to_extended_batch(in4, out4, 4, k, ek) == 0
+            assert lib.zkb_extended_to_coeff(ctypes.cast(h_ext.data_ptr(), u64p), k, ek) == 0
+
+        dropin_replay()
+        best = 1e30
+        for _ in range(2):
+            t = time.perf_counter()
+            dropin_replay()
+            best = min(best, time.perf_counter() - t)
+        h2d = n_msm * n * 32 + n_intt * n * 32 + n_c2e * n * 32 + N * 32
+        d2h = n_intt * n * 32 + n_c2e * N * 32 + N * 32
+        emit({"op": "wrapper_k22_replay", "mode": "dropin (host-buffer C ABI, pinned operands, PCIe included)", "ms": best * 1e3,
+              "h2d_bytes": h2d, "d2h_bytes": d2h})
+        params.close()
+    fout.close()
+
+
+if __name__ == "__main__":
+    main()

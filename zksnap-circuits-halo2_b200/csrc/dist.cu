@@ -130,6 +130,7 @@ static int dist_ntt_dev(const void* d_in, void* d_out, const uint64_t omega[4], 
         a.is_final = fin ? 1 : 0;
         a.tw_r = plan->tw_r[p].as<uint4>(); a.tw_hi = plan->tw_hi.as<uint4>(); a.tw_lo = plan->tw_lo.as<uint4>();
         a.tw_h = g.tw_h;
+        a.tw_pass = (plan->has_tw_pass && p > 0) ? plan->tw_pass[p].as<uint4>() : nullptr;
         a.in_len = N;
         a.dist_log_g = d.log_g; a.dist_rank = (uint32_t)d.rank; a.dist_log_slice = log_n - d.log_g;
         for (int r = 0; r < d.world; ++r) {

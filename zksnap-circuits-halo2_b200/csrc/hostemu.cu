@@ -107,6 +107,15 @@ static void pow_table(std::vector<uint4>& out, const Fr& omega, uint64_t count, 
     for (uint64_t t = 0; t < count; ++t) fr_store2(out.data(), t, fp_pow_u64(omega, t << shift));
 }
 
+// per-pass inter-pass twiddle table, same entry function as the device kernel
+static void pass_table(std::vector<uint4>& out, const std::vector<uint4>& tw_hi, const std::vector<uint4>& tw_lo, uint32_t tw_h,
+                       uint32_t log_r, uint32_t shift, uint64_t count) {
+    out.resize(2 * count);
+    for (uint64_t t = 0; t < count; ++t) fr_store2(out.data(), t, ntt_pass_twiddle(tw_hi.data(), tw_lo.data(), tw_h, log_r, shift, t));
+}
+static bool g_emu_pass_tables = true;
+EMU_EXPORT void zkb_emu_set_pass_tables(int on) { g_emu_pass_tables = on != 0; }
+
 // in: cols x in_len elements (column stride in_len); out: cols x 2^log_n.  *_scale3: 3x4 u64 Montgomery or NULL.
 EMU_EXPORT int zkb_emu_ntt(const uint64_t* in, uint64_t in_len, uint64_t* out, uint32_t log_n, const uint64_t* omega,
                            const uint64_t* in_scale3, const uint64_t* out_scale3, uint32_t cols) {
@@ -131,6 +140,13 @@ EMU_EXPORT int zkb_emu_ntt(const uint64_t* in, uint64_t in_len, uint64_t* out, u
         a.log_t = g.log_t[p];
         a.is_final = fin;
         a.tw_r = tw_r[p].data(); a.tw_hi = tw_hi.data(); a.tw_lo = tw_lo.data(); a.tw_h = g.tw_h;
+        std::vector<uint4> tw_pass;
+        if (p > 0 && g_emu_pass_tables) {
+            uint32_t log_q = 0;
+            for (uint32_t q = 0; q <= p; ++q) log_q += g.lr[q];
+            pass_table(tw_pass, tw_hi, tw_lo, g.tw_h, g.lr[p], log_n - log_q, 1ull << log_q);
+            a.tw_pass = tw_pass.data();
+        }
         a.in_len = p == 0 ? in_len : N;
         a.in_scale_on = (p == 0 && in_scale3) ? 1 : 0;
         a.out_scale_on = (fin && out_scale3) ? 1 : 0;
@@ -170,6 +186,13 @@ EMU_EXPORT int zkb_emu_ntt_dist_phase(int phase, uint32_t rank, uint32_t log_g, 
         a.log_t = g.log_t[p];
         a.is_final = fin;
         a.tw_r = tw_r[p].data(); a.tw_hi = tw_hi.data(); a.tw_lo = tw_lo.data(); a.tw_h = g.tw_h;
+        std::vector<uint4> tw_pass;
+        if (p > 0 && g_emu_pass_tables) {
+            uint32_t log_q = 0;
+            for (uint32_t q = 0; q <= p; ++q) log_q += g.lr[q];
+            pass_table(tw_pass, tw_hi, tw_lo, g.tw_h, g.lr[p], log_n - log_q, 1ull << log_q);
+            a.tw_pass = tw_pass.data();
+        }
         a.in_len = N;
         a.dist_log_g = log_g; a.dist_rank = rank; a.dist_log_slice = log_n - log_g;
         for (uint32_t r = 0; r < (1u << log_g); ++r) {

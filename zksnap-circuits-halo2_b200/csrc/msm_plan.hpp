@@ -1,6 +1,7 @@
 // msm_plan.hpp — host-side geometry of the Pippenger pipeline (shared by the CUDA driver and the CPU emulator).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 namespace zkb {
 
@@ -62,10 +63,13 @@ inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t ch
     g.chunk0 = chunk_override ? chunk_override : 128;
     g.chunk_up = 32;
     g.last_max = 64;
-    // segments: keep >= ~32 segments per window when the window has that many buckets, m <= 128
+    // bucket reduction: ~2^15 segment threads keep the SMs busy while the per-thread chain (2m adds + the (c-1)-bit offset
+    // multiplication) stays short; measured on B200 (profiles/r1_tuning.txt): 2^19 buckets -> m = 16, 2^21 -> m = 64.
     uint32_t lb = g.c - 1;
-    g.log_m = lb > 12 ? 7 : (lb > 5 ? lb - 5 : 0);
-    g.sum_group = 32;
+    g.log_m = lb > 18 ? (lb - 15 > 7 ? 7 : lb - 15) : (lb > 6 ? 3 : 0);
+    g.sum_group = 8;
+    if (const char* e = getenv("ZKB_MSM_LOG_M")) { uint32_t v = (uint32_t)atoi(e); if (v <= lb) g.log_m = v; }
+    if (const char* e = getenv("ZKB_MSM_SUM_GROUP")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2) g.sum_group = v; }
     return g;
 }
 

@@ -1,4 +1,6 @@
 // ntt.cu — kernels and host driver of the Fr NTT (see ntt.cuh for the algorithm).
+#include <cstdlib>
+
 #include "ntt_host.hpp"
 
 namespace zkb {
@@ -19,6 +21,14 @@ __global__ void ntt_pow_table_kernel(uint4* out, Fr omega, uint64_t count, uint3
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     fr_store2(out, t, fp_pow_u64(omega, t << shift));
+}
+
+// out[t] = omega_N^((r*K) << shift), t = K * R + r
+__global__ void ntt_pass_table_kernel(uint4* out, const uint4* tw_hi, const uint4* tw_lo, uint32_t tw_h, uint32_t log_r,
+                                      uint32_t shift, uint64_t count) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    fr_store2(out, t, ntt_pass_twiddle(tw_hi, tw_lo, tw_h, log_r, shift, t));
 }
 
 template <int LOGR>
@@ -73,6 +83,27 @@ int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPla
     for (uint32_t q = 0; q < p->geom.npass && rc == ZKB_OK; ++q)
         rc = build_table(p->tw_r[q], p->omega, 1ull << p->geom.lr[q], log_n - p->geom.lr[q], s);
     if (rc != ZKB_OK) { delete p; return rc; }
+    // per-pass inter-pass twiddle tables (one lookup + one product per element instead of two); sizes Q_{p+1} * 32 B, the last
+    // one N * 32 B.  Skipped (the two-level tables remain) when disabled or when HBM is short.
+    {
+        const char* e = getenv("ZKB_NTT_PASS_TABLES");
+        size_t free_b = 0, total_b = 0;
+        bool want = !(e && e[0] == '0') && p->geom.npass > 1 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && N * 32 * 2 < free_b / 4;
+        cudaGetLastError();
+        uint32_t log_q = p->geom.lr[0];
+        for (uint32_t q = 1; q < p->geom.npass && want; ++q) {
+            log_q += p->geom.lr[q];  // log2 Q_{q+1}
+            const uint64_t count = 1ull << log_q;
+            if (p->tw_pass[q].reserve(count * 32) != ZKB_OK) { want = false; break; }
+            ntt_pass_table_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(p->tw_pass[q].as<uint4>(), p->tw_hi.as<uint4>(),
+                                                                                p->tw_lo.as<uint4>(), p->geom.tw_h, p->geom.lr[q],
+                                                                                log_n - log_q, count);
+            count_launch();
+            if (cudaGetLastError() != cudaSuccess) { want = false; break; }
+        }
+        if (!want) for (auto& b : p->tw_pass) b.release();
+        p->has_tw_pass = want;
+    }
     // tables are built on `s`; later launches may use another stream, so make them visible now
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
     cache[{log_n, key}] = p;
@@ -85,6 +116,7 @@ void ntt_clear_plans() {
         kv.second->tw_lo.release();
         kv.second->tw_hi.release();
         for (auto& b : kv.second->tw_r) b.release();
+        for (auto& b : kv.second->tw_pass) b.release();
         delete kv.second;
     }
     plan_cache().clear();
@@ -114,6 +146,7 @@ int ntt_run(const NttPlan& plan, const NttIo& io, cudaStream_t s) {
         a.is_final = fin ? 1 : 0;
         a.tw_r = plan.tw_r[p].as<uint4>(); a.tw_hi = plan.tw_hi.as<uint4>(); a.tw_lo = plan.tw_lo.as<uint4>();
         a.tw_h = g.tw_h;
+        a.tw_pass = (plan.has_tw_pass && p > 0) ? plan.tw_pass[p].as<uint4>() : nullptr;
         a.in_len = p == 0 ? io.in_len : N;
         a.in_scale_on = (p == 0 && io.in_scale) ? 1 : 0;
         a.out_scale_on = (fin && io.out_scale) ? 1 : 0;

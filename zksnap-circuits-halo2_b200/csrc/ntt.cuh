@@ -48,6 +48,8 @@ struct NttPassArgs {
     const uint4* tw_hi;       // omega_N^(t << tw_h)
     const uint4* tw_lo;       // omega_N^t, t < 2^tw_h
     uint32_t tw_h;
+    const uint4* tw_pass;     // optional: the inter-pass twiddles of THIS pass, omega_N^((r*K) << shift) at [K * R + r]
+                              // (Q_p * R_p entries): one lookup and one product instead of the hi/lo pair
     // fusions
     uint64_t in_len;          // first pass: elements >= in_len read as zero (in_len == N otherwise)
     uint32_t in_scale_on;     // first pass: multiply by in_scale[i % 3]
@@ -156,6 +158,16 @@ ZKB_HD uint32_t ntt_sm_plane(const NttPassArgs& a) {  // uint4 elements per plan
     return a.is_final ? ((R + 1) << a.log_t) : (R << a.log_t);
 }
 
+// entry t = K * R + r of pass p's twiddle table: omega_N^((r*K) << shift), from the two-level power tables
+ZKB_HD Fr ntt_pass_twiddle(const uint4* tw_hi, const uint4* tw_lo, uint32_t tw_h, uint32_t log_r, uint32_t shift, uint64_t t) {
+    const uint64_t K = t >> log_r, r = t & ((1ull << log_r) - 1);
+    const uint64_t e = (r * K) << shift;
+    const uint64_t eh = e >> tw_h, el = e & ((1ull << tw_h) - 1);
+    Fr v = fr_load2(tw_lo, el);
+    if (eh) v = fp_mul(v, fr_load2(tw_hi, eh));
+    return v;
+}
+
 // ---- phase 1: global -> shared, with zero-extension, coset scale and inter-pass twiddle ------------------
 template <int LOGR>
 ZKB_HD void ntt_phase_load(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32_t nthreads, uint64_t cta,
@@ -207,10 +219,14 @@ ZKB_HD void ntt_phase_load(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32
             v = Fr::zero();
         }
         if (a.pass > 0) {
-            uint64_t e = ((uint64_t)r * K) << tw_shift;  // < N
-            uint64_t eh = e >> a.tw_h, el = e & ((1ull << a.tw_h) - 1);
-            if (eh) v = fp_mul(v, fr_load2(a.tw_hi, eh));
-            if (el) v = fp_mul(v, fr_load2(a.tw_lo, el));
+            if (a.tw_pass) {
+                if (r && K) v = fp_mul(v, fr_load2(a.tw_pass, (K << LOGR) + r));
+            } else {
+                uint64_t e = ((uint64_t)r * K) << tw_shift;  // < N
+                uint64_t eh = e >> a.tw_h, el = e & ((1ull << a.tw_h) - 1);
+                if (eh) v = fp_mul(v, fr_load2(a.tw_hi, eh));
+                if (el) v = fp_mul(v, fr_load2(a.tw_lo, el));
+            }
         }
         sm_store(lo, hi, ntt_sm_index<LOGR>(a, r, c), v);
     }

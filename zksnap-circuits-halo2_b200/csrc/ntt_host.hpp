@@ -13,6 +13,8 @@ struct NttPlan {
     Fr omega;
     DevBuf tw_lo, tw_hi;
     DevBuf tw_r[NTT_MAX_PASSES];
+    DevBuf tw_pass[NTT_MAX_PASSES];  // per-pass inter-pass twiddle tables ([K][r]); empty when they did not fit
+    bool has_tw_pass = false;
 };
 
 struct NttIo {
