@@ -161,6 +161,11 @@ int zkb_host_unregister(void* ptr);
 /* depth: column groups in flight, 1 = serial, 0 = default (3); group_bytes: output bytes per group, 0 = automatic
  * (a quarter of the batch, clamped to [8 MiB, 256 MiB]). */
 int zkb_pipeline_set(int depth, size_t group_bytes);
+/* Host-scalar commits (zkb_msm_g1_srs / _range) of >= 2^21 points against an SRS with a window table are cut into
+ * point-range slices: slice i+1 is uploaded while slice i runs its digit / sort / accumulate kernels; later slices fill
+ * a scratch bucket array that is folded into the main one, and the last one reduces.  slices: 0 = automatic (2 for
+ * page-locked scalars, 4 for pageable ones, more above 2^24 points), 1 = upload everything first. */
+int zkb_msm_set_slices(int slices);
 
 /* ---- tuning and measurement -------------------------------------------------------------------------------- */
 

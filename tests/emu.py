@@ -64,6 +64,17 @@ def msm(scalars, bases, c=0, chunk=0, table=False):
     return out
 
 
+def msm_sliced(scalars, bases, slices, c=0, chunk=0):
+    """table-mode MSM run as `slices` point-range slices adding into one bucket array (the pipelined host commit)"""
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(12, dtype=np.uint64)
+    rc = lib().zkb_emu_msm_sliced(_p(s), _p(b), ctypes.c_uint64(s.shape[0]), ctypes.c_uint32(c), ctypes.c_uint32(chunk),
+                                  ctypes.c_uint32(slices), _p(out))
+    assert rc == 0
+    return out
+
+
 def msm_batch(scalar_cols, bases, c=0, chunk=0, table=False, dev_final=False):
     s = np.ascontiguousarray(scalar_cols, dtype=np.uint64)
     ncols, n = s.shape[0], s.shape[1]

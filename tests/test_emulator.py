@@ -170,6 +170,17 @@ def test_msm_srs_window_table(oracle, n, c, chunk):
     assert (emu.msm(s, b, c, chunk, table=True) == oracle.best_multiexp(s, b)).all()
 
 
+@pytest.mark.parametrize("n,slices,c,chunk", [(300, 4, 5, 8), (301, 3, 6, 4), (700, 4, 0, 0), (64, 7, 4, 2)])
+def test_msm_point_range_slices_share_buckets(oracle, n, slices, c, chunk):
+    """The pipelined host commit: slices of the point range are digit-decomposed / sorted / accumulated one after the
+    other, later slices ADD into the bucket array (rmw), one reduction at the end."""
+    s = random_field(n, 3 * n)
+    b = _bases(oracle, n, n + 9)
+    s[5] = 0; b[11] = 0; s[n - 1] = s[0]; b[n - 1] = b[0]   # same point and scalar in the first and last slice
+    s[n // 2:] = s[n // 2]                                   # a long single-bucket run inside later slices
+    assert (emu.msm_sliced(s, b, slices, c, chunk) == oracle.best_multiexp(s, b)).all()
+
+
 # ---- distributed NTT: one transform sharded over G ranks (peer memory emulated by per-rank arrays) ---------------------
 @pytest.mark.parametrize("k,log_g", [(11, 1), (12, 2), (13, 3), (16, 1), (17, 3), (19, 2), (20, 3)])
 def test_ntt_dist_matches_best_fft(oracle, k, log_g):

@@ -400,3 +400,34 @@ def test_sharded_ntt_two_gpus():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 3 and all(l["parity"] for l in lines)
+
+
+@pytest.mark.parametrize("slices,n,register", [(3, 5000, False), (4, 1 << 14, True), (7, 100, False), (1, 5000, False)])
+def test_commit_point_range_slices(oracle, slices, n, register):
+    """Pipelined host-scalar commit: `slices` point-range slices uploaded while the previous one computes, all adding into
+    one bucket array (pageable scalars go through the pinned staging ring, registered ones are DMA'd directly)."""
+    import ctypes
+    lib = zkb.lib()
+    zkb.lib().zkb_srs_set_precompute(1)
+    _, g = _bases_known_dlog(n, 4000 + n)
+    s = random_field(n, 4001 + n)
+    s[3] = 0
+    s[n // 2:] = s[n // 2]          # one long bucket run spanning later slices
+    g[n - 1] = g[0]; s[n - 1] = s[0]
+    k = max(6, (n - 1).bit_length())
+    gp = np.zeros((1 << k, 8), dtype=np.uint64)
+    gp[:n] = g
+    params = zkb.ParamsKZG(k, gp)
+    want = oracle.best_multiexp(s, g)
+    assert lib.zkb_msm_set_slices(slices) == 0
+    try:
+        if register:
+            assert lib.zkb_host_register(ctypes.c_void_p(s.ctypes.data), s.nbytes) == 0
+        assert (params.commit(s) == want).all()
+        off = n // 5
+        assert (params.commit_range(off, s[off:]) == oracle.best_multiexp(s[off:], g[off:])).all()
+    finally:
+        if register:
+            lib.zkb_host_unregister(ctypes.c_void_p(s.ctypes.data))
+        lib.zkb_msm_set_slices(0)
+        params.close()

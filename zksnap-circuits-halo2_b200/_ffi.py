@@ -79,6 +79,7 @@ def load() -> ctypes.CDLL:
         "zkb_host_register": [vp, sz],
         "zkb_host_unregister": [vp],
         "zkb_pipeline_set": [ci, sz],
+        "zkb_msm_set_slices": [ci],
         "zkb_msm_set_params": [u32, u32],
         "zkb_msm_get_params": [sz, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)],
         "zkb_prof_enable": [ci],

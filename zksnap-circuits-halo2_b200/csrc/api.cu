@@ -167,8 +167,24 @@ static std::map<uint64_t, Srs*>& srs_map() {
 }
 static uint64_t g_next_handle = 1;
 
+struct PinBuf {  // grow-only pinned host buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ZKB_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ZKB_ERR_OOM; }
+        cap = bytes;
+        return ZKB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct HostIo {  // device staging for the host-buffer entry points
     DevBuf scalars, bases, x, y, in;
+    PinBuf stage[2];            // pinned staging of pageable scalar slices
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 static HostIo& hostio() {
     static HostIo h;
@@ -322,20 +338,6 @@ static HostPool& host_pool() {
     static HostPool p;
     return p;
 }
-
-struct PinBuf {  // grow-only pinned host buffer
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes) {
-        if (bytes <= cap) return ZKB_OK;
-        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-        cudaError_t e = cudaMallocHost(&p, bytes);
-        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return ZKB_ERR_OOM; }
-        cap = bytes;
-        return ZKB_OK;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
 
 constexpr int PIPE_SLOTS = 3;
 struct PipeSlot {
@@ -494,11 +496,12 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
 
 // MSM of device scalars against srs[offset .. offset+n), through the window table when available
 static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t* out,
-                       uint32_t ncols = 1) {
+                       uint32_t ncols = 1, uint32_t phase = MSM_WHOLE) {
     if (srs_table_ready(srs, stream)) {
         MsmTable t{srs->table.as<uint4>() + 4 * offset, srs->n, srs->table_c, srs->table_nwin};
-        return msm_run(d_scalars, nullptr, n, stream, out, &t, ncols);
+        return msm_run(d_scalars, nullptr, n, stream, out, &t, ncols, phase);
     }
+    if (phase != MSM_WHOLE) { set_error("sliced MSM needs the SRS window table"); return ZKB_ERR_ARG; }
     return msm_run(d_scalars, srs->bases.as<uint4>() + 4 * offset, n, stream, out, nullptr, ncols);
 }
 
@@ -508,6 +511,69 @@ static int upload_scalars(const uint64_t* scalars, size_t n) {
     ZKB_TRY(check_ptr(scalars, "scalars"));
     ZKB_TRY(h.scalars.reserve(n * 32));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    return ZKB_OK;
+}
+
+// Host scalars -> MSM against srs[offset .. offset+n).  Large commits are cut into point-range slices whose upload
+// (through pinned staging when the caller's memory is pageable) overlaps the previous slice's digit / sort / accumulate
+// kernels; the slices add into one bucket array and the last one reduces (msm_run `phase`).
+static int g_msm_slices = 0;  // 0 = automatic
+static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t n, uint64_t* out_jac) {
+    Ctx& c = ctx();
+    HostIo& h = hostio();
+    ZKB_TRY(check_ptr(scalars, "scalars"));
+    // automatic slice count (profiles/r1_tuning.txt): two slices hide half of a pinned upload at +1.5 ms of accumulate time
+    // (shorter bucket runs); pageable memory is staged by host threads at a fraction of PCIe speed, so four slices
+    const bool pinned = host_ptr_is_pinned(scalars);
+    size_t slices = 1;
+    if (g_msm_slices > 0) slices = (size_t)g_msm_slices;
+    else if (n >= ((size_t)1 << 21)) {
+        slices = n >> 23;
+        if (slices < 2) slices = 2;
+        if (slices > 8) slices = 8;
+        if (!pinned && slices < 4) slices = 4;
+    }
+    if (slices > 1 && !srs_table_ready(srs, c.stream)) slices = 1;
+    if (slices > n) slices = 1;
+    if (slices == 1) {
+        ZKB_TRY(upload_scalars(scalars, n));
+        return msm_srs_dev(srs, offset, h.scalars.as<uint4>(), n, c.stream, out_jac);
+    }
+    ZKB_TRY(pipeline_init());
+    Pipeline& pl = pipeline();
+    ZKB_TRY(h.scalars.reserve(n * 32));
+    const size_t per = (n + slices - 1) / slices;
+    if (!pinned) {
+        for (auto& b : h.stage) ZKB_TRY(b.reserve(per * 32));
+        for (auto& e : h.stage_ev)
+            if (!e) ZKB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(pl.s_h2d); cudaStreamSynchronize(c.stream);
+        return rc;
+    };
+    for (size_t sidx = 0, lo = 0; lo < n; ++sidx, lo += per) {
+        const size_t cnt = n - lo < per ? n - lo : per;
+        const void* src = scalars + 4 * lo;
+        PipeSlot& ev = pl.slot[sidx % PIPE_SLOTS];  // only the events of the slot are used here
+        if (!pinned) {
+            PinBuf& st = h.stage[sidx & 1];
+            if (sidx >= 2) {  // the upload that last read this staging buffer must be done
+                cudaError_t e = cudaEventSynchronize(h.stage_ev[sidx & 1]);
+                if (e != cudaSuccess) { set_error("staging wait failed: %s", cudaGetErrorString(e)); return fail(ZKB_ERR_CUDA); }
+            }
+            host_pool().copy(st.p, src, cnt * 32);
+            src = st.p;
+        }
+        cudaError_t e = cudaMemcpyAsync((char*)h.scalars.p + lo * 32, src, cnt * 32, cudaMemcpyHostToDevice, pl.s_h2d);
+        if (e == cudaSuccess && !pinned) e = cudaEventRecord(h.stage_ev[sidx & 1], pl.s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ev.ev_h2d, pl.s_h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, ev.ev_h2d, 0);
+        if (e != cudaSuccess) { set_error("scalar upload failed: %s", cudaGetErrorString(e)); return fail(ZKB_ERR_CUDA); }
+        const uint32_t phase = (lo == 0 ? MSM_FIRST : 0u) | (lo + cnt == n ? MSM_LAST : 0u);
+        int rc = msm_srs_dev(srs, offset + lo, h.scalars.as<uint4>() + 2 * lo, cnt, c.stream, out_jac, 1, phase);
+        if (rc != ZKB_OK) return fail(rc);
+    }
     return ZKB_OK;
 }
 
@@ -571,6 +637,8 @@ void zkb_shutdown(void) {
     msm_release_workspace();
     HostIo& h = hostio();
     h.scalars.release(); h.bases.release(); h.x.release(); h.y.release(); h.in.release();
+    for (auto& b : h.stage) b.release();
+    for (auto& e : h.stage_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     pipeline_release();
     for (auto& kv : c.timers)
         for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -638,8 +706,7 @@ int zkb_msm_g1_srs_range(uint64_t handle, size_t offset, const uint64_t* scalars
         return ZKB_ERR_ARG;
     }
     if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
-    ZKB_TRY(upload_scalars(scalars, n));
-    return msm_srs_dev(s, offset, hostio().scalars.as<uint4>(), n, ctx().stream, out_jac);
+    return msm_srs_host(s, offset, scalars, n, out_jac);
 }
 
 int zkb_msm_g1_srs(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
@@ -808,6 +875,11 @@ int zkb_host_unregister(void* ptr) {
     ZKB_TRY(check_ptr(ptr, "ptr"));
     cudaError_t e = cudaHostUnregister(ptr);
     if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostUnregister failed: %s", cudaGetErrorString(e)); return ZKB_ERR_CUDA; }
+    return ZKB_OK;
+}
+int zkb_msm_set_slices(int slices) {
+    if (slices < 0 || slices > 64) { set_error("slices must be in [0, 64] (0 = automatic)"); return ZKB_ERR_ARG; }
+    g_msm_slices = slices;
     return ZKB_OK;
 }
 int zkb_pipeline_set(int depth, size_t group_bytes) {

@@ -16,6 +16,10 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const MsmAccArgs a)
     msm_accumulate_thread<LEVEL0>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+__global__ void __launch_bounds__(128) msm_merge_kernel(const MsmMergeArgs a) {
+    msm_merge_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 __global__ void __launch_bounds__(128) msm_reduce_segment_kernel(const MsmReduceArgs a) {
     msm_reduce_segment_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -143,8 +147,9 @@ static void xyzz_to_out(const XYZZ& p, uint64_t out[12]) {
 void msm_identity_out(uint64_t out[12]) { xyzz_to_out(XYZZ::identity(), out); }
 
 int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t* out_jac,
-            const MsmTable* table, uint32_t ncols) {
+            const MsmTable* table, uint32_t ncols, uint32_t phase) {
     if (ncols == 0) return ZKB_OK;
+    if (phase != MSM_WHOLE && (!table || ncols != 1 || n == 0)) { set_error("sliced MSM needs the SRS window table"); return ZKB_ERR_ARG; }
     if (n == 0) { for (uint32_t k = 0; k < ncols; ++k) msm_identity_out(out_jac + 12 * k); return ZKB_OK; }
     Ctx& c = ctx();
     MsmWorkspace& w = msm_workspace();
@@ -168,7 +173,10 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, s));
     }
     ZKB_TRY(w.sort_tmp.reserve(sort_bytes));
-    ZKB_TRY(w.buckets.reserve((size_t)g.nbuckets * 128));
+    const size_t bucket_bytes = (size_t)g.nbuckets * 128;
+    ZKB_TRY(w.buckets.reserve(phase == MSM_WHOLE ? bucket_bytes : 2 * bucket_bytes));  // sliced: main + scratch array
+    uint4* const bucket_main = w.buckets.as<uint4>();
+    uint4* const bucket_acc = (phase & MSM_FIRST) ? bucket_main : bucket_main + 8 * (size_t)g.nbuckets;
     const uint64_t t0 = (total + g.chunk0 - 1) / g.chunk0;
     for (int i = 0; i < 2; ++i) {
         ZKB_TRY(w.pk[i].reserve(2 * t0 * 4));
@@ -212,7 +220,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
     // ---- 3. accumulate (levels)
     {
         ProfScope prof("msm_accumulate", s);
-        ZKB_CUDA_TRY(cudaMemsetAsync(w.buckets.p, 0, (size_t)g.nbuckets * 128, s));
+        ZKB_CUDA_TRY(cudaMemsetAsync(bucket_acc, 0, bucket_bytes, s));
         uint64_t count = total;
         int level = 0, pp = 0;
         while (count > 0) {
@@ -226,7 +234,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             a.chunk = last ? (uint32_t)count : (level == 0 ? g.chunk0 : g.chunk_up);
             a.invalid_key = g.invalid_key;
             a.last_level = last ? 1 : 0;
-            a.buckets = w.buckets.as<uint4>();
+            a.buckets = bucket_acc;
             a.pkeys_out = w.pk[pp].as<uint32_t>();
             a.pvals_out = w.pv[pp].as<uint4>();
             const uint64_t nthreads = (count + a.chunk - 1) / a.chunk;
@@ -240,13 +248,21 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             ++level;
         }
     }
+    if (!(phase & MSM_FIRST)) {  // fold this slice's buckets into the main array
+        ProfScope prof("msm_accumulate", s);
+        MsmMergeArgs m{bucket_main, bucket_acc, g.nbuckets};
+        msm_merge_kernel<<<blocks_for(g.nbuckets, 128), 128, 0, s>>>(m);
+        count_launch();
+        ZKB_CUDA_TRY(cudaGetLastError());
+    }
+    if (!(phase & MSM_LAST)) return ZKB_OK;
     // ---- 4. bucket reduction: one weighted sum per bucket set
     const uint4* sums;
     int cur = 0;
     {
         ProfScope prof("msm_reduce", s);
         MsmReduceArgs r{};
-        r.buckets = w.buckets.as<uint4>(); r.c = g.c; r.nwin = g.total_sets; r.log_m = g.log_m;
+        r.buckets = bucket_main; r.c = g.c; r.nwin = g.total_sets; r.log_m = g.log_m;
         r.seg_out = w.seg[0].as<uint4>();
         uint64_t J = J0;
         msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.total_sets * J, 128), 128, 0, s>>>(r);

@@ -138,6 +138,24 @@ ZKB_HD void msm_accumulate_thread(const MsmAccArgs& a, uint64_t t) {
     }
 }
 
+// ---- slice merge: main[b] += part[b] -----------------------------------------------------------------------------------
+// A pipelined host-scalar commit runs as point-range slices; every slice after the first accumulates into a scratch bucket
+// array which is then folded into the main one by this uniform kernel (one thread per bucket).  Doing the add inside the
+// accumulate kernel instead was measured at +20 ms per doubling of the slice count (the run-end path diverges the warp).
+struct MsmMergeArgs {
+    uint4* main;
+    const uint4* part;
+    uint64_t nbuckets;
+};
+ZKB_HD void msm_merge_thread(const MsmMergeArgs& a, uint64_t b) {
+    if (b >= a.nbuckets) return;
+    XYZZ p = msm_load_xyzz(a.part, b);
+    if (p.is_identity()) return;
+    XYZZ m = msm_load_xyzz(a.main, b);
+    xyzz_add(m, p);
+    msm_store_xyzz(a.main, b, m);
+}
+
 // ---- bucket reduction ------------------------------------------------------------------------------------------------
 struct MsmReduceArgs {
     const uint4* buckets;   // XYZZ [nwin << (c-1)]

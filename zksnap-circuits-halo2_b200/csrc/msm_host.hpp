@@ -28,8 +28,12 @@ struct MsmTable {
 // With `table` the bases come from the window table and all windows share one bucket set.
 // `ncols` independent scalar columns (column-major contiguous) against the same bases are accumulated in ONE pass
 // (column index folded into the bucket key); out_jac receives ncols x 12 limbs.
+// `phase`: a pipelined MSM is run as point-range slices that share one bucket array (table mode, same c): the first
+// slice (MSM_FIRST) clears the buckets, later ones add into them, the last one (MSM_LAST) reduces and synchronises;
+// slices without MSM_LAST return after enqueueing their kernels.
+enum : uint32_t { MSM_FIRST = 1, MSM_LAST = 2, MSM_WHOLE = 3 };
 int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t* out_jac,
-            const MsmTable* table = nullptr, uint32_t ncols = 1);
+            const MsmTable* table = nullptr, uint32_t ncols = 1, uint32_t phase = MSM_WHOLE);
 int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin, uint4* d_table, cudaStream_t s);
 int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cudaStream_t s);
 int measure_imad_peak(double* macs_per_s);

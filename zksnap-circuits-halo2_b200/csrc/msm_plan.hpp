@@ -60,7 +60,12 @@ inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t ch
     g.invalid_key = g.nbuckets;
     g.key_bits = 1;
     while ((1ull << g.key_bits) <= g.invalid_key) ++g.key_bits;
-    g.chunk0 = chunk_override ? chunk_override : 128;
+    // level-0 chunk: 128 entries per thread when that still yields >= ~2 waves of threads (148 SMs x 512), shorter chunks
+    // (shorter dependent chains, more threads) for small MSMs, which are otherwise latency bound
+    uint32_t ch = 128;
+    const uint64_t total = (uint64_t)g.nwin * (n ? n : 1) * g.ncols;
+    while (ch > 16 && total / ch < 147456) ch >>= 1;
+    g.chunk0 = chunk_override ? chunk_override : ch;
     g.chunk_up = 32;
     g.last_max = 64;
     // bucket reduction: ~2^15 segment threads keep the SMs busy while the per-thread chain (2m adds + the (c-1)-bit offset
