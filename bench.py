@@ -291,7 +291,9 @@ def main():
     achieved = alg_mac / (acc_launch_ms * 1e-3) / 1e9 if acc_launch_ms else 0.0
     roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel<level0> (+partial levels, bucket memset)",
                 "achieved": achieved, "peak": peak.value / 1e9, "unit": "GMAC/s (32x32+64 wide MACs)",
-                "frac": achieved / (peak.value / 1e9) if peak.value else None, "traffic": None,
+                "frac": achieved / (peak.value / 1e9) if peak.value else None,
+                "traffic": 28.87e9 if LOG_N_MSM == 24 else None,
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch at 2^24 (profiles/r1b_msm_accumulate_ncu.txt)",
                 "peak_source": "measured in this run: unrolled independent mad.wide.u32 chains (zkb_measure_imad_peak)",
                 "ms_per_launch": acc_launch_ms, "window_bits": c_bits.value, "windows": n_win.value,
                 "share_of_step": acc_launch_ms / ms_per_step if ms_per_step else None,
@@ -348,7 +350,7 @@ def main():
                    "e2e": {"value": world * N * cols / ntt_e2e_s, "unit": "elems/s", "h2d_bytes_per_step": N * cols * 32,
                            "d2h_bytes_per_step": N * cols * 32},
                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                "traffic": None, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
+                                "traffic": 12.9e9 if (NTT_LOG_N, NTT_COLS) == (22, 16) else None, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
                                 "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound, see DESIGN.md"}}
         del cols_np
 

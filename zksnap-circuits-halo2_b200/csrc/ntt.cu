@@ -5,12 +5,15 @@
 
 namespace zkb {
 
+#ifndef ZKB_NTT_MIN_CTAS
+#define ZKB_NTT_MIN_CTAS 4
+#endif
 struct CtaBarrier {
     __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
 template <int LOGR>
-__global__ void __launch_bounds__(128, 4) ntt_pass_kernel(const NttPassArgs a) {
+__global__ void __launch_bounds__(128, ZKB_NTT_MIN_CTAS) ntt_pass_kernel(const NttPassArgs a) {
     extern __shared__ uint4 ntt_smem[];
     CtaBarrier bar;
     ntt_cta_program<LOGR>(a, ntt_smem, threadIdx.x, blockDim.x, (uint64_t)blockIdx.x, blockIdx.y, bar);
