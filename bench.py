@@ -46,9 +46,10 @@ def random_field(n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  Started before the warm-up (nvidia-smi needs a
+    moment to come up), rows are time-stamped and only those inside the timed window(s) are used."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -56,11 +57,12 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.windows = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -69,30 +71,44 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 8:
-                continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(pred):
+            sm, mx, reasons = [], [], set()
+            for t, r in self.rows:
+                if len(r) < 9 or not pred(t):
+                    continue
+                try:
+                    sm.append(float(r[2])); mx.append(float(r[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        # a row printed at wall time t describes the ~50 ms before it
+        sm, mx, reasons = collect(lambda t: any(t0 <= t <= t1 + 0.1 for t0, t1 in self.windows))
+        scope = "timed windows"
+        if not sm:
+            sm, mx, reasons = collect(lambda t: True)
+            scope = "whole run (no sample fell inside the timed windows)"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def cpu_baseline_msm(log_n: int, repeats: int = 1):
@@ -225,6 +241,8 @@ def main():
         return zkb.g1_sum(zdist.all_gather_g1(result, device=dev))
 
     note("inputs ready")
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     # ---- warm-up + correctness of the measured configuration (rank-local known-dlog check on the first step) ------------
     for _ in range(args.warmup):
         step_dev()
@@ -239,9 +257,8 @@ def main():
     zkb.prof.enable(True)
     zkb.prof.reset()
     launches0 = zkb.launch_count()
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    t_win0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -249,7 +266,7 @@ def main():
         total = fold(out)
     e1.record(stream)
     barrier()
-    clock_info = clocks.stop()
+    clocks.window(t_win0, time.time())
     ms = e0.elapsed_time(e1)
     launches = zkb.launch_count() - launches0
     acc_ms, acc_calls = zkb.prof.get("msm_accumulate")
@@ -269,12 +286,15 @@ def main():
     for _ in range(2):
         step_e2e()
     barrier()
+    t_win0 = time.time()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
         total = fold(out)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks.window(t_win0, time.time())
+    clock_info = clocks.stop()
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

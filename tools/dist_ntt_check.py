@@ -46,7 +46,7 @@ def main():
     ok_all = True
     for k in args.log_n:
         n = 1 << k
-        a = random_field(n, 4000 + k)
+        a = random_field(n, 4000 + k) if k <= 26 else np.tile(random_field(1 << 26, 4000 + k), (1 << (k - 26), 1))
         w = zkb.omega(k)
         off, ln = zdist.ntt_slice(k, rank, world)
         got = sh.best_fft_slice(a[off:off + ln], w, k)
@@ -59,6 +59,23 @@ def main():
             from oracle import coracle
             coracle.build()
             checks["oracle"] = bool((got == coracle.best_fft(a, w, k)[off:off + ln]).all())
+        # size-independent property (the only check above 2^24): a 2-sparse input a*delta_j1 + b*delta_j2 must give
+        # out[i] = a w^(i j1) + b w^(i j2), evaluated with Python integers at sampled positions of this rank's slice
+        from oracle import pyref as R
+        from util import limbs_to_int
+        j1, j2 = 12345 % n, n - 7
+        sp = np.zeros((ln, 4), dtype=np.uint64)
+        for j, src in ((j1, a[1]), (j2, a[2])):
+            if off <= j < off + ln:
+                sp[j - off] = src
+        got_sp = sh.best_fft_slice(sp, w, k)
+        wint = R.omega_for(k)
+        a1, a2 = R.from_mont(limbs_to_int(a[1]), R.FR), R.from_mont(limbs_to_int(a[2]), R.FR)
+        good = True
+        for i in (off, off + 1, off + ln // 2 + 3, off + ln - 1):
+            want = (a1 * pow(wint, i * j1, R.FR) + a2 * pow(wint, i * j2, R.FR)) % R.FR
+            good &= R.from_mont(limbs_to_int(got_sp[i - off]), R.FR) == want
+        checks["two_sparse_definition"] = bool(good)
         ok = all(checks.values())
         t = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
