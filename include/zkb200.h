@@ -84,9 +84,27 @@ int zkb_srs_precompute(uint64_t handle, uint32_t* window_bits, uint64_t* table_b
 /* Host-side combination of partial results (multi-GPU point-range shards): out = sum of `count` Jacobian points. */
 int zkb_g1_sum(const uint64_t* points_jac, size_t count, uint64_t out_jac[12]);
 
-/* out[i] = [s_i] G as G1Affine (n x 8) — the fixed-base multiples ParamsKZG::setup computes for g[i] = [tau^i]G;
- * also used to synthesise bases with known discrete logs. */
+/* out[i] = [s_i] G as G1Affine (n x 8) — the fixed-base multiples ParamsKZG::setup computes; also used to synthesise
+ * bases with known discrete logs.  16-bit windows over a table of multiples of G resident in HBM (64 MiB, built on first
+ * use), <= 16 mixed additions per scalar, batched normalisation.  The _naive form is the plain double-and-add kernel the
+ * table itself is built with (an independent path, kept for cross-checks). */
 int zkb_g1_fixed_base_mul(const uint64_t* scalars, size_t n, uint64_t* out_affine);
+int zkb_g1_fixed_base_mul_naive(const uint64_t* scalars, size_t n, uint64_t* out_affine);
+
+/* halo2curves Curve::batch_normalize: n Jacobian G1 (n x 12) -> n G1Affine (n x 8), identity -> (0, 0); one field
+ * inversion per 16 points (Montgomery's trick).  The step before commitments are written to the transcript. */
+int zkb_g1_batch_normalize(const uint64_t* points_jac, size_t n, uint64_t* out_affine);
+
+/* ---- ParamsKZG::<Bn256>::setup(k, rng) — the G1 side (reference call sites: /root/reference/voter/benches/
+ * voter_circuit.rs:60, aggregator/benches/state_transition_circuit.rs:64).  s is the toxic-waste scalar the Rust side
+ * samples (Montgomery Fr);  g[i] = [s^i] G  and  g_lagrange[i] = [l_i(s)] G,  l_i(s) = omega^i (s^n - 1) / (n (s - omega^i)),
+ * n = 2^k.  Either output may be NULL.  Fails with ZKB_ERR_ARG if s is an n-th root of unity (upstream panics there).
+ * The G2 elements of the params ([1]G2, [s]G2) are two scalar multiplications and stay on the host.
+ * zkb_kzg_setup_resident leaves the arrays in HBM and returns SRS handles (as from zkb_srs_register) — nothing crosses
+ * PCIe; zkb_srs_download copies a registered SRS back when the caller wants to serialise it. */
+int zkb_kzg_setup(uint32_t k, const uint64_t s[4], uint64_t* g_out, uint64_t* g_lagrange_out);
+int zkb_kzg_setup_resident(uint32_t k, const uint64_t s[4], uint64_t* handle_g, uint64_t* handle_g_lagrange);
+int zkb_srs_download(uint64_t handle, uint64_t* bases_out, size_t n);
 
 /* ---- NTT: halo2_proofs::arithmetic::best_fft and EvaluationDomain::{lagrange_to_coeff, coeff_to_extended,
  *      extended_to_coeff} ----------------------------------------------------------------------------------- */

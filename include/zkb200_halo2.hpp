@@ -42,6 +42,13 @@ inline void best_fft(std::vector<Fr>& a, const Fr& omega, uint32_t log_n) {
     check(zkb_ntt_fr(a[0].data(), omega.data(), log_n), "best_fft");
 }
 
+// group::Curve::batch_normalize(&[G1], &mut [G1Affine])
+inline std::vector<G1Affine> batch_normalize(const std::vector<G1>& p) {
+    std::vector<G1Affine> q(p.size());
+    check(zkb_g1_batch_normalize(p.empty() ? nullptr : p[0].data(), p.size(), q.empty() ? nullptr : q[0].data()), "batch_normalize");
+    return q;
+}
+
 // poly::EvaluationDomain<Fr>
 class EvaluationDomain {
    public:
@@ -87,6 +94,15 @@ class ParamsKZG {
         check(zkb_srs_register(g[0].data(), g.size(), &h_g_), "ParamsKZG (g)");
         check(zkb_srs_register(g_lagrange[0].data(), g_lagrange.size(), &h_gl_), "ParamsKZG (g_lagrange)");
     }
+    // ParamsKZG::setup(k, rng), G1 side: `s` is the scalar the caller sampled; g and g_lagrange are generated in HBM
+    static ParamsKZG setup(uint32_t k, const Fr& s) {
+        ParamsKZG p(k);
+        check(zkb_kzg_setup_resident(k, s.data(), &p.h_g_, &p.h_gl_), "ParamsKZG::setup");
+        return p;
+    }
+    ParamsKZG(ParamsKZG&& o) noexcept : k_(o.k_), h_g_(o.h_g_), h_gl_(o.h_gl_) { o.h_g_ = o.h_gl_ = 0; }
+    std::vector<G1Affine> get_g() const { return download(h_g_); }
+    std::vector<G1Affine> get_g_lagrange() const { return download(h_gl_); }
     ParamsKZG(const ParamsKZG&) = delete;
     ParamsKZG& operator=(const ParamsKZG&) = delete;
     ~ParamsKZG() {
@@ -99,6 +115,12 @@ class ParamsKZG {
     G1 commit_lagrange(const std::vector<Fr>& poly) const { return msm(h_gl_, poly); }
 
    private:
+    explicit ParamsKZG(uint32_t k) : k_(k) {}
+    std::vector<G1Affine> download(uint64_t h) const {
+        std::vector<G1Affine> out(size_t(1) << k_);
+        check(zkb_srs_download(h, out[0].data(), out.size()), "get_g");
+        return out;
+    }
     G1 msm(uint64_t h, const std::vector<Fr>& poly) const {
         G1 out{};
         check(zkb_msm_g1_srs(h, poly.empty() ? nullptr : poly[0].data(), poly.size(), out.data()), "commit");

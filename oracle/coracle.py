@@ -171,6 +171,29 @@ def g1_fixed_base_mul(scalars_mont: np.ndarray, threads: int = 0) -> np.ndarray:
     return o
 
 
+def g1_batch_normalize(jac: np.ndarray) -> np.ndarray:
+    j = np.ascontiguousarray(jac, dtype=np.uint64).reshape(-1, 12)
+    o = _new(j.shape[0], 8)
+    lib().zko_g1_batch_normalize(_p(j), ctypes.c_size_t(j.shape[0]), _p(o))
+    return o
+
+
+def fr_eval_polynomial(coeffs: np.ndarray, x: np.ndarray) -> np.ndarray:
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    o = _new(4)
+    lib().zko_fr_eval_polynomial(_p(c), ctypes.c_size_t(c.shape[0]), _p(np.ascontiguousarray(x, dtype=np.uint64)), _p(o))
+    return o
+
+
+def kzg_setup(k: int, s_mont: np.ndarray, threads: int = 0):
+    """ParamsKZG::setup, G1 side: (g, g_lagrange), each (2^k, 8)."""
+    g, gl = _new(1 << k, 8), _new(1 << k, 8)
+    rc = lib().zko_kzg_setup(ctypes.c_uint(k), _p(np.ascontiguousarray(s_mont, dtype=np.uint64)), _p(g), _p(gl), ctypes.c_int(threads))
+    if rc:
+        raise ValueError("s is an n-th root of unity")
+    return g, gl
+
+
 def msm_naive(scalars_mont: np.ndarray, bases_aff: np.ndarray) -> np.ndarray:
     s = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
     b = np.ascontiguousarray(bases_aff, dtype=np.uint64).reshape(-1, 8)

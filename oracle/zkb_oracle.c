@@ -25,6 +25,10 @@
  *   halo2_proofs::poly::EvaluationDomain::{lagrange_to_coeff, coeff_to_extended,
  *       extended_to_coeff}                                                            -> zko_*
  *   ParamsKZG::setup's g[i] = [s^i]G (fixed-base scalar mul)                           -> zko_g1_fixed_base_mul
+ *   ParamsKZG::setup (G1 side): g[i] = [s^i]G, g_lagrange[i] = [l_i(s)]G with
+ *       l_i(s) = omega^i (s^n - 1) / (n (s - omega^i))                                 -> zko_kzg_setup
+ *   Curve::batch_normalize (Montgomery's trick)                                        -> zko_g1_batch_normalize
+ *   arithmetic::eval_polynomial (Horner)                                               -> zko_fr_eval_polynomial
  */
 #include <math.h>
 #include <stdint.h>
@@ -587,6 +591,58 @@ EXPORT void zko_g1_fixed_base_mul(const u64 *scalars_mont, size_t n, u64 *out_af
     parallel_for(n, threads, fbm_range, &c);
     g1j_batch_normalize((g1a *)out_aff, c.tmp, n);
     free(c.tmp);
+}
+
+
+/* Curve::batch_normalize: n Jacobian points -> affine, identity -> (0,0) */
+EXPORT void zko_g1_batch_normalize(const u64 *jac, size_t n, u64 *out_aff) {
+    g1j_batch_normalize((g1a *)out_aff, (const g1j *)jac, n);
+}
+
+/* arithmetic::eval_polynomial: sum_i coeffs[i] x^i by Horner; Montgomery in, Montgomery out */
+EXPORT void zko_fr_eval_polynomial(const u64 *coeffs, size_t n, const u64 *x, u64 *out) {
+    fe acc;
+    memset(&acc, 0, sizeof(acc));
+    for (size_t i = n; i-- > 0;) {
+        f_mul(&FR, &acc, &acc, CFE(x));
+        f_add(&FR, &acc, &acc, CFE(coeffs + 4 * i));
+    }
+    *(fe *)out = acc;
+}
+
+/* ParamsKZG::setup, G1 side (halo2-axiom poly/kzg/commitment.rs; reference call sites voter_circuit.rs:60,
+ * state_transition_circuit.rs:64): every scalar by the definition (one exponentiation / inversion per index), every
+ * point by double-and-add.  Returns 1 if s is an n-th root of unity (upstream panics). */
+EXPORT int zko_kzg_setup(unsigned k, const u64 *s_mont, u64 *g_out, u64 *gl_out, int threads) {
+    size_t n = (size_t)1 << k;
+    fe s = *CFE(s_mont);
+    fe *sc = (fe *)malloc(n * sizeof(fe));
+    if (g_out) {
+        fe p = FR.r;
+        for (size_t i = 0; i < n; ++i) { sc[i] = p; f_mul(&FR, &p, &p, &s); }
+        zko_g1_fixed_base_mul((const u64 *)sc, n, g_out, threads);
+    }
+    if (gl_out) {
+        fe omega, sn = s, nf = FR.r, ninv, c, one = FR.r;
+        fr_omega(k, &omega);
+        for (unsigned i = 0; i < k; ++i) { f_sqr(&FR, &sn, &sn); f_dbl(&FR, &nf, &nf); }
+        f_inv(&FR, &ninv, &nf);
+        f_sub(&FR, &c, &sn, &one);
+        f_mul(&FR, &c, &c, &ninv);
+        fe w = FR.r;
+        for (size_t i = 0; i < n; ++i) {
+            fe d, dinv;
+            f_sub(&FR, &d, &s, &w);
+            if (fe_is_zero(&d)) { free(sc); return 1; }
+            f_inv(&FR, &dinv, &d);
+            f_mul(&FR, &sc[i], &w, &c);
+            f_mul(&FR, &sc[i], &sc[i], &dinv);
+            f_mul(&FR, &w, &w, &omega);
+        }
+        zko_g1_fixed_base_mul((const u64 *)sc, n, gl_out, threads);
+    }
+    free(sc);
+    return 0;
 }
 
 /* naive sum of double-and-add products (ground truth for tiny n) */

@@ -30,6 +30,14 @@ extern "C" {
     pub fn zkb_lagrange_to_coeff(a: *mut u64, k: u32) -> c_int;
     pub fn zkb_coeff_to_extended(input: *const u64, out: *mut u64, k: u32, extended_k: u32) -> c_int;
     pub fn zkb_extended_to_coeff(a: *mut u64, k: u32, extended_k: u32) -> c_int;
+    pub fn zkb_lagrange_to_coeff_batch(cols: *const *mut u64, ncols: size_t, k: u32) -> c_int;
+    pub fn zkb_coeff_to_extended_batch(input: *const *const u64, out: *const *mut u64, ncols: size_t, k: u32, extended_k: u32) -> c_int;
+    pub fn zkb_g1_batch_normalize(points_jac: *const u64, n: size_t, out_affine: *mut u64) -> c_int;
+    pub fn zkb_kzg_setup(k: u32, s: *const u64, g_out: *mut u64, g_lagrange_out: *mut u64) -> c_int;
+    pub fn zkb_kzg_setup_resident(k: u32, s: *const u64, handle_g: *mut u64, handle_g_lagrange: *mut u64) -> c_int;
+    pub fn zkb_srs_download(handle: u64, bases_out: *mut u64, n: size_t) -> c_int;
+    pub fn zkb_host_register(ptr: *mut c_void, bytes: size_t) -> c_int;
+    pub fn zkb_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn zkb_msm_g1_srs_dev(handle: u64, offset: size_t, d_scalars: *const c_void, n: size_t, out_jac: *mut u64, stream: *mut c_void) -> c_int;
 }
 
@@ -122,4 +130,62 @@ pub fn extended_to_coeff(mut values: Vec<Fr>, k: u32, extended_k: u32, quotient_
     check(unsafe { zkb_extended_to_coeff(values.as_mut_ptr() as *mut u64, k, extended_k) }, "extended_to_coeff");
     values.truncate(((1u64 << k) * quotient_poly_degree) as usize);
     values
+}
+
+/// The evaluate_h loop of `create_proof`: `coeff_to_extended` of many polynomials in one call, so that the upload of
+/// polynomial i+1, the coset NTT of polynomial i and the download of polynomial i-1 overlap (three-stream scheduler).
+pub fn coeff_to_extended_batch(polys: &[&[Fr]], k: u32, extended_k: u32) -> Vec<Vec<Fr>> {
+    let n_ext = 1usize << extended_k;
+    assert!(polys.iter().all(|p| p.len() == 1 << k));
+    let mut outs: Vec<Vec<Fr>> = polys.iter().map(|_| Vec::with_capacity(n_ext)).collect();
+    let ins: Vec<*const u64> = polys.iter().map(|p| p.as_ptr() as *const u64).collect();
+    let ptrs: Vec<*mut u64> = outs.iter_mut().map(|o| o.as_mut_ptr() as *mut u64).collect();
+    check(unsafe { zkb_coeff_to_extended_batch(ins.as_ptr(), ptrs.as_ptr(), polys.len(), k, extended_k) }, "coeff_to_extended_batch");
+    for o in outs.iter_mut() {
+        unsafe { o.set_len(n_ext) };
+    }
+    outs
+}
+
+/// Drop-in body for `halo2curves::group::Curve::batch_normalize(&[G1], &mut [G1Affine])`.
+pub fn batch_normalize(p: &[G1], q: &mut [G1Affine]) {
+    assert_eq!(p.len(), q.len());
+    check(unsafe { zkb_g1_batch_normalize(p.as_ptr() as *const u64, p.len(), q.as_mut_ptr() as *mut u64) }, "batch_normalize");
+}
+
+/// The G1 side of `ParamsKZG::<Bn256>::setup(k, rng)`: the caller samples `s` exactly as upstream does
+/// (`let s = <E::Scalar>::random(rng);`), the arrays are generated in HBM and registered as resident SRS handles.
+pub fn kzg_setup_resident(k: u32, s: Fr) -> (ResidentSrs, ResidentSrs) {
+    let (mut hg, mut hgl) = (0u64, 0u64);
+    check(unsafe { zkb_kzg_setup_resident(k, &s as *const Fr as *const u64, &mut hg, &mut hgl) }, "ParamsKZG::setup");
+    (ResidentSrs { handle: hg, len: 1 << k }, ResidentSrs { handle: hgl, len: 1 << k })
+}
+
+impl ResidentSrs {
+    /// Copy the resident bases back (`ParamsKZG::write`, `get_g()`).
+    pub fn download(&self) -> Vec<G1Affine> {
+        let mut out = Vec::<G1Affine>::with_capacity(self.len);
+        check(unsafe { zkb_srs_download(self.handle, out.as_mut_ptr() as *mut u64, self.len) }, "srs_download");
+        unsafe { out.set_len(self.len) };
+        out
+    }
+}
+
+/// Page-locks a long-lived `Vec<Fr>` (advice column, extended polynomial) for its lifetime so the transfer scheduler
+/// DMAs it directly instead of staging it through pinned buffers.
+pub struct PinnedVec {
+    pub values: Vec<Fr>,
+}
+
+impl PinnedVec {
+    pub fn new(mut values: Vec<Fr>) -> Self {
+        check(unsafe { zkb_host_register(values.as_mut_ptr() as *mut c_void, values.len() * 32) }, "host_register");
+        Self { values }
+    }
+}
+
+impl Drop for PinnedVec {
+    fn drop(&mut self) {
+        unsafe { zkb_host_unregister(self.values.as_mut_ptr() as *mut c_void) };
+    }
 }

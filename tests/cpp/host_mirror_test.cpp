@@ -54,6 +54,23 @@ int main(int argc, char** argv) {
     for (int i = 8; i < 24; ++i)
         for (int j = 0; j < 4; ++j)
             if (back[i][j]) return fail("coset round trip tail");
+    // ParamsKZG::setup on the device + commit in both bases: commit(coeffs) == commit_lagrange(evaluations)
+    {
+        halo2::Fr s;
+        std::memcpy(s.data(), in[6], 32);  // "sampled" scalar 7
+        halo2::ParamsKZG params = halo2::ParamsKZG::setup(3, s);
+        auto g = params.get_g();
+        const uint64_t gen_x[4] = {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL};  // R mod p
+        if (std::memcmp(g[0].data(), gen_x, 32) != 0) return fail("g[0] must be the generator (1, 2)");
+        halo2::G1 cm = params.commit(c);
+        std::vector<halo2::Fr> ev = c;
+        halo2::best_fft(ev, w3, 3);  // coeff_to_lagrange
+        halo2::G1 cl = params.commit_lagrange(ev);
+        if (std::memcmp(cm.data(), cl.data(), 96) != 0) return fail("commit(coeffs) != commit_lagrange(evals)");
+        std::vector<halo2::G1> pts{cm, cl};
+        auto aff = halo2::batch_normalize(pts);
+        if (std::memcmp(aff[0].data(), cm.data(), 64) != 0) return fail("batch_normalize of a z = R point");
+    }
     std::printf("gpu ok\n");
     return 0;
 }

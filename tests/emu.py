@@ -117,3 +117,27 @@ def ntt_dist(a, log_n, omega, log_g):
             if rc != 0:
                 return rc, None
     return 0, np.concatenate(O)
+
+
+def fixed_base_window(scalars):
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((s.shape[0], 8), dtype=np.uint64)
+    lib().zkb_emu_fixed_base_window(_p(s), ctypes.c_uint64(s.shape[0]), _p(out), ctypes.c_uint32(0))
+    return out
+
+
+def batch_normalize(jac):
+    j = np.ascontiguousarray(jac, dtype=np.uint64).reshape(-1, 12)
+    out = np.zeros((j.shape[0], 8), dtype=np.uint64)
+    lib().zkb_emu_batch_normalize(_p(j), ctypes.c_uint64(j.shape[0]), _p(out))
+    return out
+
+
+def setup_scalars(kind, n, s, omega=None, c=None):
+    """kind 0: s^i; kind 1: Lagrange-basis scalars l_i(s) = omega^i c / (s - omega^i)"""
+    out = np.zeros((n, 4), dtype=np.uint64)
+    z = np.zeros(4, dtype=np.uint64)
+    rc = lib().zkb_emu_setup_scalars(ctypes.c_int(kind), ctypes.c_uint64(n), _p(np.ascontiguousarray(s, dtype=np.uint64)),
+                                     _p(np.ascontiguousarray(omega if omega is not None else z, dtype=np.uint64)),
+                                     _p(np.ascontiguousarray(c if c is not None else z, dtype=np.uint64)), _p(out))
+    return rc, out

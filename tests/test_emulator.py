@@ -195,3 +195,48 @@ def test_ntt_dist_rejects_single_pass():
     a = random_field(1 << 8, 1)
     rc, _ = emu.ntt_dist(a, 8, np.zeros(4, dtype=np.uint64), 1)
     assert rc == -2
+
+
+# ---- setup.cuh: windowed fixed-base multiplication, batched normalisation, SRS scalars -------------------------------------------
+def test_fixed_base_window_matches_oracle(oracle):
+    s = random_field(40, 77)
+    s[0] = 0
+    s[1] = mont([1])[0]
+    s[2] = mont([R.FR - 1])[0]
+    s[3] = mont([1 << 240])[0]          # only the top window
+    s[4] = mont([0xFFFF])[0]            # the last entry of the first window
+    assert (emu.fixed_base_window(s) == oracle.g1_fixed_base_mul(s)).all()
+
+
+def test_batch_normalize_matches_oracle(oracle):
+    n = 37  # not a multiple of the per-thread batch
+    aff = oracle.g1_fixed_base_mul(random_field(n, 5))
+    z = random_field(n, 6, FQ_LIMBS)
+    jac = np.zeros((n, 12), dtype=np.uint64)
+    z2 = oracle.vec_op("fq", "mul", z, z)
+    jac[:, :4] = oracle.vec_op("fq", "mul", aff[:, :4], z2)
+    jac[:, 4:8] = oracle.vec_op("fq", "mul", aff[:, 4:], oracle.vec_op("fq", "mul", z2, z))
+    jac[:, 8:] = z
+    jac[7, 8:] = 0       # identities inside a batch
+    jac[16, 8:] = 0
+    want = oracle.g1_batch_normalize(jac)
+    assert not want[7].any() and (want[0] == aff[0]).all()
+    assert (emu.batch_normalize(jac) == want).all()
+
+
+@pytest.mark.parametrize("k", [1, 5, 7])
+def test_setup_scalars_by_definition(k):
+    n = 1 << k
+    s = 0x0123456789ABCDEF0F1E2D3C4B5A6978 + k
+    sm = mont([s])[0]
+    rc, pw = emu.setup_scalars(0, n, sm)
+    assert rc == 0 and [R.from_mont(limbs_to_int(x), R.FR) for x in pw] == [pow(s, i, R.FR) for i in range(n)]
+    w = R.omega_for(k)
+    c = (pow(s, n, R.FR) - 1) * pow(n, R.FR - 2, R.FR) % R.FR
+    rc, lg = emu.setup_scalars(1, n, sm, mont([w])[0], mont([c])[0])
+    want = [pow(w, i, R.FR) * c % R.FR * pow((s - pow(w, i, R.FR)) % R.FR, R.FR - 2, R.FR) % R.FR for i in range(n)]
+    assert rc == 0 and [R.from_mont(limbs_to_int(x), R.FR) for x in lg] == want
+    assert sum(want) % R.FR == 1
+    # s inside the domain: reported (upstream panics on the failed inversion)
+    rc, _ = emu.setup_scalars(1, n, mont([pow(w, n - 1, R.FR)])[0], mont([w])[0], mont([c])[0])
+    assert rc == 1

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import pyref as R
-from util import int_to_limbs, ints_to_limbs, limbs_to_int, random_field
+from util import FQ_LIMBS, int_to_limbs, ints_to_limbs, limbs_to_int, random_field
 
 pytestmark = pytest.mark.gpu
 
@@ -431,3 +431,65 @@ def test_commit_point_range_slices(oracle, slices, n, register):
             lib.zkb_host_unregister(ctypes.c_void_p(s.ctypes.data))
         lib.zkb_msm_set_slices(0)
         params.close()
+
+
+# ---- ParamsKZG::setup, fixed-base windows, batch_normalize -------------------------------------
+def test_fixed_base_windowed_vs_naive_vs_oracle(oracle):
+    s = random_field(3000, 81)
+    s[0] = 0
+    s[1] = mont([1])[0]
+    s[2] = mont([R.FR - 1])[0]
+    s[3] = mont([1 << 240])[0]
+    s[4] = mont([0xFFFF])[0]
+    fast = zkb.g1_fixed_base_mul(s)
+    assert (fast == zkb.g1_fixed_base_mul_naive(s)).all()
+    assert (fast[:200] == oracle.g1_fixed_base_mul(s[:200])).all()
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 1000])
+def test_batch_normalize_vs_oracle(oracle, n):
+    aff = zkb.g1_fixed_base_mul(random_field(n, 5 + n))
+    z = random_field(n, 6 + n, FQ_LIMBS)
+    z2 = oracle.vec_op("fq", "mul", z, z)
+    jac = np.zeros((n, 12), dtype=np.uint64)
+    jac[:, :4] = oracle.vec_op("fq", "mul", aff[:, :4], z2)
+    jac[:, 4:8] = oracle.vec_op("fq", "mul", aff[:, 4:], oracle.vec_op("fq", "mul", z2, z))
+    jac[:, 8:] = z
+    if n > 10:
+        jac[7, 8:] = 0
+        aff[7] = 0
+    got = zkb.batch_normalize(jac)
+    assert (got == oracle.g1_batch_normalize(jac)).all() and (got == aff).all()
+
+
+def test_kzg_setup_vs_oracle(oracle):
+    k = 6
+    s = random_field(1, 2026)[0]
+    g, gl = oracle.kzg_setup(k, s)
+    params = zkb.ParamsKZG.setup(k, s)
+    assert (params.get_g() == g).all()
+    assert (params.get_g_lagrange() == gl).all()
+    poly = random_field(1 << k, 9)
+    assert (params.commit(poly) == oracle.best_multiexp(poly, g)).all()
+    params.close()
+    # s inside the domain is refused like upstream's panic
+    w = zkb.omega(k)
+    with pytest.raises(zkb.ZkbError):
+        zkb.ParamsKZG.setup(k, w)
+
+
+@pytest.mark.parametrize("k", [16, 20])
+def test_kzg_setup_commit_consistency_full_size(oracle, k):
+    """Size-independent KZG invariants tying setup, MSM and NTT together: commit(p) = [p(s)]G, and the commitment of the
+    evaluations in the Lagrange basis equals the commitment of the coefficients in the monomial basis."""
+    n = 1 << k
+    s = random_field(1, 31 + k)[0]
+    params = zkb.ParamsKZG.setup(k, s)
+    coeffs = random_field(n, 32 + k)
+    c1 = params.commit(coeffs)
+    ps = oracle.fr_eval_polynomial(coeffs, s)
+    assert (c1[:8] == oracle.g1_mul(oracle.g1_generator(), ps)).all()
+    d = zkb.EvaluationDomain(4, k)
+    evals = d.coeff_to_lagrange(coeffs)
+    assert (params.commit_lagrange(evals) == c1).all()
+    params.close()

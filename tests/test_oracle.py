@@ -189,3 +189,47 @@ def test_msm_edge_cases(oracle):
     s = fr_mont([12345] * 64)
     out = oracle.best_multiexp(s, np.tile(g, (64, 1)))
     assert R.g1_jacobian_decode([int(x) for x in out]) == R.g1_mul(R.G1_GENERATOR, 12345 * 64)
+
+
+# ---- ParamsKZG::setup (G1 side), batch_normalize, eval_polynomial: oracle vs first principles ---------------------------------
+def test_kzg_setup_oracle_by_definition(oracle):
+    """g[i] = [s^i]G and g_lagrange[i] = [l_i(s)]G with l_i(s) = omega^i (s^n - 1) / (n (s - omega^i)), recomputed with
+    Python integers; the Lagrange basis sums to one, so sum_i g_lagrange[i] = G; a commitment equals [p(s)]G in both bases."""
+    k, n = 3, 8
+    s = 0x1234567890ABCDEF1122334455667788
+    g, gl = oracle.kzg_setup(k, ints_to_limbs([R.to_mont(s, R.FR)])[0])
+    G = (1, 2)
+    w = R.omega_for(k)
+    c = (pow(s, n, R.FR) - 1) * pow(n, R.FR - 2, R.FR) % R.FR
+    for i in range(n):
+        assert R.g1_affine_decode([int(x) for x in g[i]]) == R.g1_mul(G, pow(s, i, R.FR))
+        li = pow(w, i, R.FR) * c % R.FR * pow((s - pow(w, i, R.FR)) % R.FR, R.FR - 2, R.FR) % R.FR
+        assert R.g1_affine_decode([int(x) for x in gl[i]]) == R.g1_mul(G, li)
+    acc = None
+    for i in range(n):
+        acc = R.g1_add(acc, R.g1_affine_decode([int(x) for x in gl[i]]))
+    assert acc == G
+    # KZG consistency: commit(coeffs) = [p(s)]G = commit_lagrange(evaluations over the domain)
+    coeffs = [3, 1, 4, 1, 5, 9, 2, 6]
+    ps = sum(cf * pow(s, i, R.FR) for i, cf in enumerate(coeffs)) % R.FR
+    cm = ints_to_limbs([R.to_mont(x, R.FR) for x in coeffs])
+    assert R.g1_jacobian_decode([int(x) for x in oracle.best_multiexp(cm, g)]) == R.g1_mul(G, ps)
+    evals = oracle.coeff_to_lagrange(cm, k)
+    assert (oracle.best_multiexp(evals, gl) == oracle.best_multiexp(cm, g)).all()
+    assert R.from_mont(limbs_to_int(oracle.fr_eval_polynomial(cm, ints_to_limbs([R.to_mont(s, R.FR)])[0])), R.FR) == ps
+
+
+def test_batch_normalize_oracle(oracle):
+    pts = []
+    want = []
+    for i, z in enumerate([1, 5, 0, 0xABCDEF, R.FQ - 1]):
+        P = R.g1_mul((1, 2), 7 + 13 * i)
+        if z == 0:
+            pts.append([0] * 4 + R.fq_encode(1) + [0] * 4)
+            want.append(None)
+            continue
+        x, y = P
+        pts.append(R.fq_encode(x * z * z % R.FQ) + R.fq_encode(y * z * z * z % R.FQ) + R.fq_encode(z))
+        want.append(P)
+    got = oracle.g1_batch_normalize(np.array(pts, dtype=np.uint64))
+    assert [R.g1_affine_decode([int(v) for v in row]) for row in got] == want

@@ -15,10 +15,12 @@ three benches.  Arrays are numpy uint64 in halo2curves' memory layout (Montgomer
 from .halo2 import (  # noqa: F401
     EvaluationDomain,
     ParamsKZG,
+    batch_normalize,
     best_fft,
     best_multiexp,
     device_count,
     g1_fixed_base_mul,
+    g1_fixed_base_mul_naive,
     g1_sum,
     init,
     launch_count,
@@ -30,6 +32,6 @@ from .halo2 import (  # noqa: F401
 from ._ffi import ZkbError, header_symbols  # noqa: F401
 
 __all__ = [
-    "EvaluationDomain", "ParamsKZG", "best_fft", "best_multiexp", "device_count", "g1_fixed_base_mul", "g1_sum",
+    "EvaluationDomain", "ParamsKZG", "batch_normalize", "best_fft", "best_multiexp", "device_count", "g1_fixed_base_mul", "g1_fixed_base_mul_naive", "g1_sum",
     "init", "launch_count", "lib", "omega", "prof", "shutdown", "ZkbError", "header_symbols",
 ]

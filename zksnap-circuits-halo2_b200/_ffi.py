@@ -55,6 +55,11 @@ def load() -> ctypes.CDLL:
         "zkb_srs_set_precompute": [ci],
         "zkb_srs_precompute": [u64, ctypes.POINTER(u32), ctypes.POINTER(u64)],
         "zkb_g1_fixed_base_mul": [u64p, sz, u64p],
+        "zkb_g1_fixed_base_mul_naive": [u64p, sz, u64p],
+        "zkb_g1_batch_normalize": [u64p, sz, u64p],
+        "zkb_kzg_setup": [u32, u64p, u64p, u64p],
+        "zkb_kzg_setup_resident": [u32, u64p, ctypes.POINTER(u64), ctypes.POINTER(u64)],
+        "zkb_srs_download": [u64, u64p, sz],
         "zkb_ntt_fr": [u64p, u64p, u32],
         "zkb_ntt_fr_batch": [u64pp, sz, u64p, u32],
         "zkb_lagrange_to_coeff": [u64p, u32],

@@ -631,6 +631,7 @@ void zkb_shutdown(void) {
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     dist_shutdown();
+    setup_release();
     for (auto& kv : srs_map()) { kv.second->bases.release(); kv.second->table.release(); delete kv.second; }
     srs_map().clear();
     ntt_clear_plans();
@@ -776,7 +777,7 @@ int zkb_g1_sum(const uint64_t* points_jac, size_t count, uint64_t out_jac[12]) {
     return g1_sum_host(points_jac, count, out_jac);
 }
 
-int zkb_g1_fixed_base_mul(const uint64_t* scalars, size_t n, uint64_t* out_affine) {
+static int fixed_base_host(const uint64_t* scalars, size_t n, uint64_t* out_affine, bool windowed) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
     if (n == 0) return ZKB_OK;
@@ -787,9 +788,89 @@ int zkb_g1_fixed_base_mul(const uint64_t* scalars, size_t n, uint64_t* out_affin
     ZKB_TRY(h.scalars.reserve(n * 32));
     ZKB_TRY(h.bases.reserve(n * 64));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
-    ZKB_TRY(g1_fixed_base_mul_dev(h.scalars.as<uint4>(), n, h.bases.as<uint4>(), c.stream));
+    if (windowed) ZKB_TRY(g1_fixed_base_window_dev(h.scalars.as<uint4>(), n, h.bases.as<uint4>(), c.stream));
+    else ZKB_TRY(g1_fixed_base_mul_dev(h.scalars.as<uint4>(), n, h.bases.as<uint4>(), c.stream));
     ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
     ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return ZKB_OK;
+}
+int zkb_g1_fixed_base_mul(const uint64_t* scalars, size_t n, uint64_t* out_affine) {
+    return fixed_base_host(scalars, n, out_affine, true);
+}
+int zkb_g1_fixed_base_mul_naive(const uint64_t* scalars, size_t n, uint64_t* out_affine) {
+    return fixed_base_host(scalars, n, out_affine, false);
+}
+
+int zkb_g1_batch_normalize(const uint64_t* points_jac, size_t n, uint64_t* out_affine) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (n == 0) return ZKB_OK;
+    ZKB_TRY(check_ptr(points_jac, "points_jac"));
+    ZKB_TRY(check_ptr(out_affine, "out_affine"));
+    HostIo& h = hostio();
+    Ctx& c = ctx();
+    ZKB_TRY(h.x.reserve(n * 96));
+    ZKB_TRY(h.bases.reserve(n * 64));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(h.x.p, points_jac, n * 96, cudaMemcpyHostToDevice, c.stream));
+    ZKB_TRY(g1_batch_to_affine_dev(h.x.as<uint4>(), n, h.bases.as<uint4>(), true, c.stream));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
+    ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return ZKB_OK;
+}
+
+// ---- ParamsKZG::setup ----------------------------------------------------------------------------------------------------------
+static int kzg_setup_common(uint32_t k, const uint64_t* s, uint64_t* g_out, uint64_t* gl_out, uint64_t* hg, uint64_t* hgl) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(s, "s"));
+    if (k < 1 || k > 28) { set_error("k %u out of range [1, 28]", k); return ZKB_ERR_ARG; }
+    const size_t n = (size_t)1 << k;
+    Ctx& c = ctx();
+    Srs* sg = nullptr;
+    Srs* sgl = nullptr;
+    auto make = [&](Srs** out) -> int {
+        Srs* p = new Srs();
+        p->n = n;
+        int rc = p->bases.reserve(n * 64);
+        if (rc != ZKB_OK) { delete p; return rc; }
+        *out = p;
+        return ZKB_OK;
+    };
+    const bool want_g = g_out || hg, want_gl = gl_out || hgl;
+    int rc = ZKB_OK;
+    if (want_g) rc = make(&sg);
+    if (rc == ZKB_OK && want_gl) rc = make(&sgl);
+    if (rc == ZKB_OK) rc = kzg_setup_dev(k, s, sg ? sg->bases.as<uint4>() : nullptr, sgl ? sgl->bases.as<uint4>() : nullptr, c.stream);
+    if (rc == ZKB_OK && g_out && cudaMemcpyAsync(g_out, sg->bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    if (rc == ZKB_OK && gl_out && cudaMemcpyAsync(gl_out, sgl->bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    if (rc == ZKB_OK && cudaStreamSynchronize(c.stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    if (rc == ZKB_ERR_CUDA) { set_error("ParamsKZG::setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    auto finish = [&](Srs* p, uint64_t* handle) {
+        if (!p) return;
+        if (rc == ZKB_OK && handle) { *handle = g_next_handle++; srs_map()[*handle] = p; }
+        else { p->bases.release(); delete p; }
+    };
+    finish(sg, hg);
+    finish(sgl, hgl);
+    return rc;
+}
+int zkb_kzg_setup(uint32_t k, const uint64_t s[4], uint64_t* g_out, uint64_t* g_lagrange_out) {
+    if (!g_out && !g_lagrange_out) { set_error("both outputs are NULL"); return ZKB_ERR_ARG; }
+    return kzg_setup_common(k, s, g_out, g_lagrange_out, nullptr, nullptr);
+}
+int zkb_kzg_setup_resident(uint32_t k, const uint64_t s[4], uint64_t* handle_g, uint64_t* handle_g_lagrange) {
+    if (!handle_g && !handle_g_lagrange) { set_error("both handles are NULL"); return ZKB_ERR_ARG; }
+    return kzg_setup_common(k, s, nullptr, nullptr, handle_g, handle_g_lagrange);
+}
+int zkb_srs_download(uint64_t handle, uint64_t* bases_out, size_t n) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    if (n > s->n) { set_error("SRS holds %zu points, %zu requested", s->n, n); return ZKB_ERR_ARG; }
+    if (n == 0) return ZKB_OK;
+    ZKB_TRY(check_ptr(bases_out, "bases_out"));
+    ZKB_CUDA_TRY(cudaMemcpy(bases_out, s->bases.p, n * 64, cudaMemcpyDeviceToHost));
     return ZKB_OK;
 }
 

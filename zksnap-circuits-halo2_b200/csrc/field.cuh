@@ -426,6 +426,13 @@ ZKB_HD_NOINLINE Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
 using Fr = Fp<FrParams>;
 using Fq = Fp<FqParams>;
 
+ZKB_HD Fr fr_from_words(const uint32_t (&w)[8]) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = w[i];
+    return r;
+}
+
 // element idx of an array of 32-byte field elements addressed as uint4 pairs
 ZKB_HD Fr fr_from_u4(uint4 a, uint4 b) {
     Fr r;

@@ -99,16 +99,25 @@ int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cuda
     return ZKB_OK;
 }
 
-// rows 1..W-1 of the SRS window table: row w = 2^c * row (w-1); row 0 is a copy of the bases
+// rows 1..W-1 of the SRS window table: row w = 2^c * row (w-1); row 0 is a copy of the bases.  The running row is kept in
+// XYZZ (scratch, n x 128 B) and each finished row is normalised to affine with one inversion per 16 points.
 int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin, uint4* d_table, cudaStream_t s) {
     ZKB_CUDA_TRY(cudaMemcpyAsync(d_table, d_bases, n * 64, cudaMemcpyDeviceToDevice, s));
-    for (uint32_t w = 1; w < nwin; ++w) {
-        SrsTableArgs a{d_table + 4 * n * (uint64_t)(w - 1), d_table + 4 * n * (uint64_t)w, n, c};
+    if (nwin < 2) return ZKB_OK;
+    DevBuf scratch;
+    ZKB_TRY(scratch.reserve(n * 128));
+    int rc = ZKB_OK;
+    for (uint32_t w = 1; w < nwin && rc == ZKB_OK; ++w) {
+        SrsTableArgs a{d_bases, scratch.as<uint4>(), n, c, w == 1 ? 1u : 0u};
         srs_table_kernel<<<blocks_for(n, 128), 128, 0, s>>>(a);
         count_launch();
-        ZKB_CUDA_TRY(cudaGetLastError());
+        if (cudaGetLastError() != cudaSuccess) { rc = ZKB_ERR_CUDA; break; }
+        rc = g1_batch_to_affine_dev(scratch.as<uint4>(), n, d_table + 4 * n * (uint64_t)w, false, s);
     }
-    return ZKB_OK;
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == ZKB_OK) rc = ZKB_ERR_CUDA;
+    scratch.release();
+    if (rc != ZKB_OK) { cudaGetLastError(); set_error("SRS window table build failed"); }
+    return rc;
 }
 
 MsmWorkspace& msm_workspace() {

@@ -271,21 +271,28 @@ ZKB_HD void msm_finalize_thread(const MsmFinalArgs& a, uint64_t col) {
 // ---- SRS window table: next[i] = 2^c * prev[i] (affine in, affine out) — built once per registered SRS so that every
 // window of every scalar can share ONE bucket set (no per-window reduction, no Horner fold) ------------------------------------
 struct SrsTableArgs {
-    const uint4* prev;  // n affine points
-    uint4* next;        // n affine points
+    const uint4* bases;  // n affine points (row 0), read when first != 0
+    uint4* acc;          // n XYZZ points, updated in place: acc[i] = 2^c * (first ? bases[i] : acc[i])
     uint64_t n;
     uint32_t c;
+    uint32_t first;
 };
+// One row step of the table build; the XYZZ row is then converted to affine by the batched normalisation kernel
+// (setup.cuh: one inversion per 16 points instead of one per point — the row build was 2.4x slower with per-point inversions).
 ZKB_HD void srs_table_thread(const SrsTableArgs& a, uint64_t i) {
     if (i >= a.n) return;
-    Affine p = affine_load(a.prev + 4 * i);
-    if (!p.is_identity()) {
-        XYZZ acc = xyzz_double_affine(p.x, p.y);
-        for (uint32_t k = 1; k < a.c; ++k) acc = xyzz_double(acc);
-        p = xyzz_to_affine(acc);
+    XYZZ acc;
+    uint32_t left = a.c;
+    if (a.first) {
+        Affine p = affine_load(a.bases + 4 * i);
+        if (p.is_identity()) { XYZZ::identity().store(a.acc + 8 * i); return; }
+        acc = xyzz_double_affine(p.x, p.y);
+        --left;
+    } else {
+        acc = msm_load_xyzz(a.acc, i);
     }
-    p.x.store(a.next + 4 * i);
-    p.y.store(a.next + 4 * i + 2);
+    for (uint32_t k = 0; k < left; ++k) acc = xyzz_double(acc);
+    msm_store_xyzz(a.acc, i, acc);
 }
 
 // ---- fixed-base multiples of the generator: out[i] = [s_i] G (affine) — ParamsKZG::setup building block, and the

@@ -35,7 +35,12 @@ enum : uint32_t { MSM_FIRST = 1, MSM_LAST = 2, MSM_WHOLE = 3 };
 int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t* out_jac,
             const MsmTable* table = nullptr, uint32_t ncols = 1, uint32_t phase = MSM_WHOLE);
 int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin, uint4* d_table, cudaStream_t s);
-int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cudaStream_t s);
+int g1_fixed_base_mul_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cudaStream_t s);       // naive double-and-add
+// setup.cu
+int g1_fixed_base_window_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, cudaStream_t s);  // 16-bit windows over a table of G
+int g1_batch_to_affine_dev(const uint4* d_in, uint64_t n, uint4* d_out, bool jacobian, cudaStream_t s);
+int kzg_setup_dev(uint32_t k, const uint64_t s_mont[4], uint4* d_g, uint4* d_gl, cudaStream_t st);
+void setup_release();
 int measure_imad_peak(double* macs_per_s);
 int g1_sum_host(const uint64_t* pts, size_t count, uint64_t out[12]);
 

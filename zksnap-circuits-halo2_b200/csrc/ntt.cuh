@@ -72,12 +72,6 @@ ZKB_HD void sm_store(uint4* lo, uint4* hi, uint32_t i, const Fr& v) {
     lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
-ZKB_HD Fr fr_from_words(const uint32_t (&w)[8]) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.l[i] = w[i];
-    return r;
-}
 
 // ---- element addressing (single GPU: column-major batch; distributed: owner slice over peer memory) -----------
 ZKB_HD const uint4* ntt_src_elem(const NttPassArgs& a, uint32_t col, uint64_t gi) {

@@ -91,6 +91,22 @@ def g1_fixed_base_mul(scalars: np.ndarray) -> np.ndarray:
     return out
 
 
+def g1_fixed_base_mul_naive(scalars: np.ndarray) -> np.ndarray:
+    """The plain double-and-add kernel (independent of the windowed table path)."""
+    s = _fr(scalars, "scalars")
+    out = np.zeros((s.shape[0], 8), dtype=np.uint64)
+    check(lib().zkb_g1_fixed_base_mul_naive(_p(s), s.shape[0], _p(out)))
+    return out
+
+
+def batch_normalize(points_jac: np.ndarray) -> np.ndarray:
+    """halo2curves Curve::batch_normalize(&[G1], &mut [G1Affine])."""
+    p = np.ascontiguousarray(points_jac, dtype=np.uint64).reshape(-1, 12)
+    out = np.zeros((p.shape[0], 8), dtype=np.uint64)
+    check(lib().zkb_g1_batch_normalize(_p(p), p.shape[0], _p(out)))
+    return out
+
+
 # ---- halo2_proofs::poly::EvaluationDomain ------------------------------------------------------------------------------
 class EvaluationDomain:
     """EvaluationDomain::<Fr>::new(j, k): j = cs.degree(), n = 2^k."""
@@ -174,6 +190,27 @@ class ParamsKZG:
             assert gl.shape[0] == self.n
             self._h_gl = ctypes.c_uint64(0)
             check(lib().zkb_srs_register(_p(gl), gl.shape[0], ctypes.byref(self._h_gl)))
+
+    @classmethod
+    def setup(cls, k: int, s: np.ndarray) -> "ParamsKZG":
+        """ParamsKZG::<Bn256>::setup(k, rng) with the sampled scalar `s` passed in (Montgomery Fr): g and g_lagrange are
+        generated on the device and stay resident — nothing crosses PCIe.  (g2, s_g2 stay on the host side.)"""
+        self = cls.__new__(cls)
+        self.k, self.n = k, 1 << k
+        self._h_g, self._h_gl = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        sv = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        check(lib().zkb_kzg_setup_resident(k, _p(sv), ctypes.byref(self._h_g), ctypes.byref(self._h_gl)))
+        return self
+
+    def get_g(self) -> np.ndarray:
+        out = np.zeros((self.n, 8), dtype=np.uint64)
+        check(lib().zkb_srs_download(self._h_g, _p(out), self.n))
+        return out
+
+    def get_g_lagrange(self) -> np.ndarray:
+        out = np.zeros((self.n, 8), dtype=np.uint64)
+        check(lib().zkb_srs_download(self._h_gl, _p(out), self.n))
+        return out
 
     def _commit(self, h, poly: np.ndarray) -> np.ndarray:
         s = _fr(poly, "poly")
