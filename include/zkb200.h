@@ -144,6 +144,38 @@ int zkb_coeff_to_extended_dev(const void* d_in, void* d_out, void* d_scratch, si
 int zkb_extended_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, uint32_t extended_k, void* stream);
 int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint32_t k, void* stream);
 
+/* ---- polynomials resident in HBM ------------------------------------------------------
+ * The prover commits, transforms and evaluates each polynomial several times.  Under a handle it is uploaded once and the
+ * chain  commit_lagrange -> lagrange_to_coeff -> commit -> coeff_to_extended -> eval_polynomial -> kate_division  runs
+ * without PCIe traffic; only 96-byte commitments and 32-byte evaluations come back.  Fixed / permutation polynomials of the
+ * proving key can stay resident across proofs the same way.  Handles are process-wide; every op is ordered on the library
+ * stream, downloads synchronise.
+ *   zkb_poly_commit              ParamsKZG::commit / commit_lagrange of the resident values against a registered SRS
+ *   zkb_poly_lagrange_to_coeff   EvaluationDomain::lagrange_to_coeff, in place   (2^k elements)
+ *   zkb_poly_coeff_to_lagrange   EvaluationDomain::coeff_to_lagrange, in place
+ *   zkb_poly_coeff_to_extended   EvaluationDomain::coeff_to_extended -> new handle with 2^extended_k elements
+ *   zkb_poly_extended_to_coeff   EvaluationDomain::extended_to_coeff, in place over 2^extended_k elements
+ *   zkb_poly_eval                arithmetic::eval_polynomial(poly, x)
+ *   zkb_poly_kate_division       arithmetic::kate_division(poly, b): new handle with len - 1 coefficients of poly / (X - b)
+ *   zkb_poly_batch_invert        ff::BatchInvert over the values, in place (zeros stay zero) */
+int zkb_poly_upload(const uint64_t* values, size_t n, uint64_t* handle);
+int zkb_poly_alloc(size_t n, uint64_t* handle); /* zero-filled */
+int zkb_poly_len(uint64_t handle, size_t* n);
+int zkb_poly_download(uint64_t handle, uint64_t* out, size_t n);
+int zkb_poly_free(uint64_t handle);
+int zkb_poly_commit(uint64_t srs_handle, uint64_t poly, uint64_t out_jac[12]);
+int zkb_poly_lagrange_to_coeff(uint64_t poly, uint32_t k);
+int zkb_poly_coeff_to_lagrange(uint64_t poly, uint32_t k);
+int zkb_poly_coeff_to_extended(uint64_t poly, uint32_t k, uint32_t extended_k, uint64_t* out_handle);
+int zkb_poly_extended_to_coeff(uint64_t poly, uint32_t k, uint32_t extended_k);
+int zkb_poly_eval(uint64_t poly, const uint64_t x[4], uint64_t out[4]);
+int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_handle);
+int zkb_poly_batch_invert(uint64_t poly);
+/* host-buffer forms of the three helpers (upload + op + download) */
+int zkb_fr_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
+int zkb_fr_kate_division(const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* out /* n - 1 */);
+int zkb_fr_batch_invert(uint64_t* values, size_t n);
+
 /* ---- one NTT sharded over the GPUs of a box ("single NTT larger than one GPU's share") ------------
  * One process per GPU.  Rank r holds the contiguous slice [r N/G, (r+1) N/G) of the natural-order input and receives
  * the same slice of the natural-order output of best_fft(a, omega, log_n).  The exchange is not a separate collective:

@@ -185,6 +185,19 @@ def fr_eval_polynomial(coeffs: np.ndarray, x: np.ndarray) -> np.ndarray:
     return o
 
 
+def fr_kate_division(coeffs: np.ndarray, b: np.ndarray) -> np.ndarray:
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    o = _new(max(c.shape[0] - 1, 0), 4)
+    lib().zko_fr_kate_division(_p(c), ctypes.c_size_t(c.shape[0]), _p(np.ascontiguousarray(b, dtype=np.uint64)), _p(o))
+    return o
+
+
+def fr_batch_invert(a: np.ndarray) -> np.ndarray:
+    a = np.array(a, dtype=np.uint64, copy=True).reshape(-1, 4)
+    lib().zko_fr_batch_invert(_p(a), ctypes.c_size_t(a.shape[0]))
+    return a
+
+
 def kzg_setup(k: int, s_mont: np.ndarray, threads: int = 0):
     """ParamsKZG::setup, G1 side: (g, g_lagrange), each (2^k, 8)."""
     g, gl = _new(1 << k, 8), _new(1 << k, 8)

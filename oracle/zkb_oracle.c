@@ -29,6 +29,8 @@
  *       l_i(s) = omega^i (s^n - 1) / (n (s - omega^i))                                 -> zko_kzg_setup
  *   Curve::batch_normalize (Montgomery's trick)                                        -> zko_g1_batch_normalize
  *   arithmetic::eval_polynomial (Horner)                                               -> zko_fr_eval_polynomial
+ *   arithmetic::kate_division(a, b): q_{n-2} = a_{n-1}, q_{i-1} = a_i + b q_i            -> zko_fr_kate_division
+ *   ff::BatchInvert (zeros are skipped and stay zero)                                   -> zko_fr_batch_invert
  */
 #include <math.h>
 #include <stdint.h>
@@ -608,6 +610,27 @@ EXPORT void zko_fr_eval_polynomial(const u64 *coeffs, size_t n, const u64 *x, u6
         f_add(&FR, &acc, &acc, CFE(coeffs + 4 * i));
     }
     *(fe *)out = acc;
+}
+
+
+/* arithmetic::kate_division: a has n coefficients, out receives the n-1 coefficients of a(X) / (X - b) */
+EXPORT void zko_fr_kate_division(const u64 *a, size_t n, const u64 *b, u64 *out) {
+    if (n < 2) return;
+    fe q = *CFE(a + 4 * (n - 1));
+    ((fe *)out)[n - 2] = q;
+    for (size_t i = n - 2; i >= 1; --i) {
+        f_mul(&FR, &q, &q, CFE(b));
+        f_add(&FR, &q, &q, CFE(a + 4 * i));
+        ((fe *)out)[i - 1] = q;
+    }
+}
+
+/* ff::BatchInvert: element-wise inverse in place, zeros untouched (each element inverted on its own here) */
+EXPORT void zko_fr_batch_invert(u64 *a, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        fe *v = (fe *)(a + 4 * i);
+        if (!fe_is_zero(v)) f_inv(&FR, v, v);
+    }
 }
 
 /* ParamsKZG::setup, G1 side (halo2-axiom poly/kzg/commitment.rs; reference call sites voter_circuit.rs:60,

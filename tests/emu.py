@@ -141,3 +141,23 @@ def setup_scalars(kind, n, s, omega=None, c=None):
                                      _p(np.ascontiguousarray(omega if omega is not None else z, dtype=np.uint64)),
                                      _p(np.ascontiguousarray(c if c is not None else z, dtype=np.uint64)), _p(out))
     return rc, out
+
+
+def poly_eval(a, x):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().zkb_emu_poly_eval(_p(a), ctypes.c_uint64(a.shape[0]), _p(np.ascontiguousarray(x, dtype=np.uint64)), _p(out))
+    return out
+
+
+def kate_division(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((a.shape[0] - 1, 4), dtype=np.uint64)
+    lib().zkb_emu_kate_division(_p(a), ctypes.c_uint64(a.shape[0]), _p(np.ascontiguousarray(b, dtype=np.uint64)), _p(out))
+    return out
+
+
+def batch_invert(a):
+    a = np.array(a, dtype=np.uint64, copy=True).reshape(-1, 4)
+    lib().zkb_emu_batch_invert(_p(a), ctypes.c_uint64(a.shape[0]))
+    return a

@@ -240,3 +240,22 @@ def test_setup_scalars_by_definition(k):
     # s inside the domain: reported (upstream panics on the failed inversion)
     rc, _ = emu.setup_scalars(1, n, mont([pow(w, n - 1, R.FR)])[0], mont([w])[0], mont([c])[0])
     assert rc == 1
+
+
+# ---- poly.cuh: eval_polynomial, kate_division, batch inversion (multi-level chunking) ----------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4096, 4097, 70000])
+def test_poly_eval_and_kate_division(oracle, n):
+    a = random_field(n, 500 + n)
+    x = random_field(1, 501 + n)[0]
+    assert (emu.poly_eval(a, x) == oracle.fr_eval_polynomial(a, x)).all()
+    if n >= 2:
+        assert (emu.kate_division(a, x) == oracle.fr_kate_division(a, x)).all()
+
+
+def test_batch_invert(oracle):
+    a = random_field(100, 9)
+    a[0] = 0
+    a[31] = 0
+    a[32] = 0
+    a[99] = mont([1])[0]
+    assert (emu.batch_invert(a) == oracle.fr_batch_invert(a)).all()

@@ -493,3 +493,90 @@ def test_kzg_setup_commit_consistency_full_size(oracle, k):
     evals = d.coeff_to_lagrange(coeffs)
     assert (params.commit_lagrange(evals) == c1).all()
     params.close()
+
+
+def test_entry_points_are_thread_safe(oracle):
+    """SURVEY.md §8b threading: rayon closures / two provers in one process may call concurrently — results must not mix."""
+    import threading
+    k = 12
+    n = 1 << k
+    _, g = _bases_known_dlog(n, 606)
+    params = zkb.ParamsKZG(k, g)
+    d = zkb.EvaluationDomain(4, k)
+    polys = [random_field(n, 610 + i) for i in range(6)]
+    want_c = [oracle.best_multiexp(p, g) for p in polys]
+    want_e = [oracle.coeff_to_extended(p, k, d.extended_k) for p in polys]
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(3):
+                assert (params.commit(polys[i]) == want_c[i]).all()
+                assert (d.coeff_to_extended(polys[i]) == want_e[i]).all()
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(polys))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    params.close()
+    assert not errs, errs
+
+
+# ---- resident polynomials and the Fr vector helpers (SURVEY.md §8f rows 1, 3, 4) ---------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4096, 4097, 100000])
+def test_eval_polynomial_and_kate_division_vs_oracle(oracle, n):
+    a = random_field(n, 700 + n)
+    x = random_field(1, 701 + n)[0]
+    assert (zkb.eval_polynomial(a, x) == oracle.fr_eval_polynomial(a, x)).all()
+    if n >= 2:
+        assert (zkb.kate_division(a, x) == oracle.fr_kate_division(a, x)).all()
+
+
+def test_batch_invert_vs_oracle(oracle):
+    a = random_field(5000, 19)
+    a[0] = 0
+    a[31:34] = 0
+    a[4999] = mont([1])[0]
+    assert (zkb.batch_invert(a) == oracle.fr_batch_invert(a)).all()
+
+
+def test_resident_polynomial_chain(oracle):
+    """The prover's chain on one advice column without leaving HBM: commit_lagrange, lagrange_to_coeff, commit,
+    coeff_to_extended, eval at x, kate_division by x, commit of the quotient — each step against the oracle."""
+    k = 12
+    n = 1 << k
+    s = random_field(1, 77)[0]
+    params = zkb.ParamsKZG.setup(k, s)
+    g, gl = params.get_g(), params.get_g_lagrange()
+    d = zkb.EvaluationDomain(4, k)
+    evals = random_field(n, 78)
+    p = zkb.Polynomial(evals)
+    assert len(p) == n
+    assert (p.commit(params, lagrange=True) == oracle.best_multiexp(evals, gl)).all()
+    coeffs = oracle.lagrange_to_coeff(evals, k)
+    p.lagrange_to_coeff(d)
+    assert (p.to_host() == coeffs).all()
+    assert (p.commit(params) == oracle.best_multiexp(coeffs, g)).all()
+    ext = p.coeff_to_extended(d)
+    assert (ext.to_host() == oracle.coeff_to_extended(coeffs, k, d.extended_k)).all()
+    ext.extended_to_coeff(d)
+    assert (ext.to_host()[:n] == coeffs).all()
+    x = random_field(1, 79)[0]
+    assert (p.eval(x) == oracle.fr_eval_polynomial(coeffs, x)).all()
+    q = p.kate_division(x)
+    assert len(q) == n - 1
+    qh = oracle.fr_kate_division(coeffs, x)
+    assert (q.to_host() == qh).all()
+    assert (q.commit(params) == oracle.best_multiexp(qh, g[: n - 1])).all()
+    # KZG opening identity in the exponent: [p(s) - p(x)]G = [(s - x) q(s)]G, checked in the scalar field with the oracle
+    ps, px, qs = (oracle.fr_eval_polynomial(c, s) for c in (coeffs, None, qh)) if False else (
+        oracle.fr_eval_polynomial(coeffs, s), oracle.fr_eval_polynomial(coeffs, x), oracle.fr_eval_polynomial(qh, s))
+    lhs = oracle.vec_op("fr", "sub", ps.reshape(1, 4), px.reshape(1, 4))
+    rhs = oracle.vec_op("fr", "mul", oracle.vec_op("fr", "sub", s.reshape(1, 4), x.reshape(1, 4)), qs.reshape(1, 4))
+    assert (lhs == rhs).all()
+    for h in (p, ext, q):
+        h.free()
+    params.close()

@@ -233,3 +233,22 @@ def test_batch_normalize_oracle(oracle):
         want.append(P)
     got = oracle.g1_batch_normalize(np.array(pts, dtype=np.uint64))
     assert [R.g1_affine_decode([int(v) for v in row]) for row in got] == want
+
+
+def test_kate_division_and_batch_invert_oracle(oracle):
+    """kate_division by the definition a(X) = q(X) (X - b) + a(b) with Python integers; BatchInvert leaves zeros."""
+    a = [5, 0, 7, 11, 13, 2, 9]
+    b = 0xDEADBEEF12345
+    q = [R.from_mont(limbs_to_int(x), R.FR) for x in oracle.fr_kate_division(ints_to_limbs([R.to_mont(x, R.FR) for x in a]),
+                                                                              ints_to_limbs([R.to_mont(b, R.FR)])[0])]
+    assert len(q) == len(a) - 1
+    rem = sum(c * pow(b, i, R.FR) for i, c in enumerate(a)) % R.FR
+    prod = [0] * len(a)
+    for i, c in enumerate(q):            # q(X) * (X - b)
+        prod[i + 1] = (prod[i + 1] + c) % R.FR
+        prod[i] = (prod[i] - c * b) % R.FR
+    prod[0] = (prod[0] + rem) % R.FR
+    assert prod == [x % R.FR for x in a]
+    v = [3, 0, R.FR - 1, 12345]
+    inv = [R.from_mont(limbs_to_int(x), R.FR) for x in oracle.fr_batch_invert(ints_to_limbs([R.to_mont(x, R.FR) for x in v]))]
+    assert inv == [pow(3, R.FR - 2, R.FR), 0, R.FR - 1, pow(12345, R.FR - 2, R.FR)]

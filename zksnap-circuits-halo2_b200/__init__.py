@@ -14,6 +14,10 @@ three benches.  Arrays are numpy uint64 in halo2curves' memory layout (Montgomer
 """
 from .halo2 import (  # noqa: F401
     EvaluationDomain,
+    Polynomial,
+    batch_invert,
+    eval_polynomial,
+    kate_division,
     ParamsKZG,
     batch_normalize,
     best_fft,
@@ -32,6 +36,6 @@ from .halo2 import (  # noqa: F401
 from ._ffi import ZkbError, header_symbols  # noqa: F401
 
 __all__ = [
-    "EvaluationDomain", "ParamsKZG", "batch_normalize", "best_fft", "best_multiexp", "device_count", "g1_fixed_base_mul", "g1_fixed_base_mul_naive", "g1_sum",
+    "EvaluationDomain", "ParamsKZG", "Polynomial", "batch_invert", "eval_polynomial", "kate_division", "batch_normalize", "best_fft", "best_multiexp", "device_count", "g1_fixed_base_mul", "g1_fixed_base_mul_naive", "g1_sum",
     "init", "launch_count", "lib", "omega", "prof", "shutdown", "ZkbError", "header_symbols",
 ]

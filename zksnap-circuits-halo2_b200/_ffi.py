@@ -74,6 +74,22 @@ def load() -> ctypes.CDLL:
         "zkb_coeff_to_extended_dev": [vp, vp, vp, sz, u32, u32, vp],
         "zkb_extended_to_coeff_dev": [vp, vp, sz, u32, u32, vp],
         "zkb_lagrange_to_coeff_dev": [vp, vp, sz, u32, vp],
+        "zkb_poly_upload": [u64p, sz, ctypes.POINTER(u64)],
+        "zkb_poly_alloc": [sz, ctypes.POINTER(u64)],
+        "zkb_poly_len": [u64, ctypes.POINTER(sz)],
+        "zkb_poly_download": [u64, u64p, sz],
+        "zkb_poly_free": [u64],
+        "zkb_poly_commit": [u64, u64, u64p],
+        "zkb_poly_lagrange_to_coeff": [u64, u32],
+        "zkb_poly_coeff_to_lagrange": [u64, u32],
+        "zkb_poly_coeff_to_extended": [u64, u32, u32, ctypes.POINTER(u64)],
+        "zkb_poly_extended_to_coeff": [u64, u32, u32],
+        "zkb_poly_eval": [u64, u64p, u64p],
+        "zkb_poly_kate_division": [u64, u64p, ctypes.POINTER(u64)],
+        "zkb_poly_batch_invert": [u64],
+        "zkb_fr_eval_polynomial": [u64p, sz, u64p, u64p],
+        "zkb_fr_kate_division": [u64p, sz, u64p, u64p],
+        "zkb_fr_batch_invert": [u64p, sz],
         "zkb_dist_create": [ci, ci, u32, ctypes.POINTER(ctypes.c_uint8)],
         "zkb_dist_connect": [ctypes.POINTER(ctypes.c_uint8)],
         "zkb_dist_destroy": [],

@@ -584,6 +584,21 @@ static int find_srs(uint64_t handle, Srs** out) {
     return ZKB_OK;
 }
 
+// hooks for poly.cu (polynomials resident under handles)
+int srs_msm_dev_by_handle(uint64_t srs_handle, const uint4* d_scalars, size_t n, cudaStream_t s, uint64_t* out) {
+    Srs* srs;
+    ZKB_TRY(find_srs(srs_handle, &srs));
+    if (n > srs->n) { set_error("MSM length %zu exceeds the registered SRS length %zu", n, srs->n); return ZKB_ERR_ARG; }
+    if (n == 0) { msm_identity_out(out); return ZKB_OK; }
+    return msm_srs_dev(srs, 0, d_scalars, n, s, out);
+}
+int domain_dev_by_op(int op, const uint4* d_in, uint4* d_a, uint4* d_b, size_t ncols, uint32_t k, uint32_t ek, cudaStream_t s) {
+    static const DomainOp ops[5] = {OP_FFT, OP_L2C, OP_C2L, OP_C2E, OP_E2C};
+    if (op < 1 || op > 4) { set_error("bad domain op"); return ZKB_ERR_ARG; }
+    return domain_op_dev(ops[op], d_in, d_a, d_b, ncols, k, ek, nullptr, s);
+}
+void poly_release_all();
+
 }  // namespace zkb
 
 using namespace zkb;
@@ -632,6 +647,7 @@ void zkb_shutdown(void) {
     cudaDeviceSynchronize();
     dist_shutdown();
     setup_release();
+    poly_release_all();
     for (auto& kv : srs_map()) { kv.second->bases.release(); kv.second->table.release(); delete kv.second; }
     srs_map().clear();
     ntt_clear_plans();

@@ -1,0 +1,324 @@
+// poly.cu — polynomials resident in HBM (handles) and the Fr vector kernels of poly.cuh.
+//
+// The prover's polynomials (advice columns, permutation / lookup products, the quotient pieces) are committed, moved
+// between bases and evaluated several times each.  Keeping them in HBM under a handle turns
+//   commit_lagrange -> lagrange_to_coeff -> coeff_to_extended -> eval_polynomial -> kate_division -> commit
+// into device-only steps: one upload per polynomial, 96-byte commitments and 32-byte evaluations coming back
+// (coset-resident pipeline, eval / division helpers, proving-key residency).
+#include <cstring>
+
+#include "msm_host.hpp"
+#include "ntt_host.hpp"
+#include "poly.cuh"
+
+namespace zkb {
+
+__global__ void __launch_bounds__(128) poly_eval_chunk_kernel(const PolyEvalArgs a) {
+    poly_eval_chunk_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) kate_expand_kernel(const KateExpandArgs a) {
+    kate_expand_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) fr_batch_invert_kernel(const BatchInvertArgs a) {
+    fr_batch_invert_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+static inline unsigned nblk(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+static inline uint64_t chunks(uint64_t n) { return (n + POLY_CHUNK - 1) / POLY_CHUNK; }
+
+static Fr fr_of(const uint64_t* p) {
+    Fr r;
+    for (int i = 0; i < 4; ++i) { r.l[2 * i] = (uint32_t)p[i]; r.l[2 * i + 1] = (uint32_t)(p[i] >> 32); }
+    return r;
+}
+static void words_of(const Fr& v, uint32_t (&o)[8]) {
+    for (int i = 0; i < 8; ++i) o[i] = v.l[i];
+}
+static Fr pow_chunk(Fr x) {  // x^POLY_CHUNK, POLY_CHUNK = 2^6
+    for (uint32_t c = POLY_CHUNK; c > 1; c >>= 1) x = fp_sqr(x);
+    return x;
+}
+
+struct PolyWs {
+    DevBuf tmp;
+    void* h_out = nullptr;  // pinned 32 B
+};
+static PolyWs& poly_ws() {
+    static PolyWs w;
+    return w;
+}
+
+// sum_i a[i] x^i -> d_out (one Fr on the device)
+static int poly_eval_dev(const uint4* d_a, uint64_t n, Fr x, uint4* d_tmp, uint4** d_result, cudaStream_t s) {
+    const uint4* cur = d_a;
+    uint4* out = d_tmp;
+    for (;;) {
+        const uint64_t t = chunks(n);
+        PolyEvalArgs a{};
+        a.a = cur; a.n = n; a.out = out;
+        words_of(x, a.x);
+        poly_eval_chunk_kernel<<<nblk(t, 128), 128, 0, s>>>(a);
+        count_launch();
+        ZKB_CUDA_TRY(cudaGetLastError());
+        if (t == 1) { *d_result = out; return ZKB_OK; }
+        cur = out;
+        out += 2 * t;
+        n = t;
+        x = pow_chunk(x);
+    }
+}
+
+// Q_j = sum_{i>j} a_i b^(i-j-1) for j = 0..n-1 (Q_{n-1} = 0) -> d_q; d_tmp needs 2 * (chunks(n) + chunks(chunks(n)) + ...) Fr
+static int kate_q_dev(const uint4* d_a, uint64_t n, Fr b, uint4* d_q, uint4* d_tmp, cudaStream_t s) {
+    const uint64_t t = chunks(n);
+    const uint4* carry = nullptr;
+    if (t > 1) {
+        uint4* S = d_tmp;
+        uint4* K = d_tmp + 2 * t;
+        PolyEvalArgs e{};
+        e.a = d_a; e.n = n; e.out = S;
+        words_of(b, e.x);
+        poly_eval_chunk_kernel<<<nblk(t, 128), 128, 0, s>>>(e);
+        count_launch();
+        ZKB_CUDA_TRY(cudaGetLastError());
+        ZKB_TRY(kate_q_dev(S, t, pow_chunk(b), K, d_tmp + 4 * t, s));
+        carry = K;
+    }
+    KateExpandArgs x{};
+    x.a = d_a; x.n = n; x.carry = carry; x.q = d_q;
+    words_of(b, x.b);
+    kate_expand_kernel<<<nblk(t, 128), 128, 0, s>>>(x);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+static size_t poly_tmp_bytes(uint64_t n) {  // generous: 4 Fr per chunk on every level
+    size_t total = 0;
+    for (uint64_t t = chunks(n); ; t = chunks(t)) {
+        total += 4 * t * 32;
+        if (t <= 1) break;
+    }
+    return total + 256;
+}
+
+// ---- registry ----------------------------------------------------------------------------------------------------------------
+struct Poly {
+    DevBuf buf;
+    uint64_t n = 0;
+};
+static std::map<uint64_t, Poly*>& poly_map() {
+    static std::map<uint64_t, Poly*> m;
+    return m;
+}
+static uint64_t g_next_poly = 1;
+
+static int find_poly(uint64_t h, Poly** out) {
+    auto it = poly_map().find(h);
+    if (it == poly_map().end()) { set_error("unknown polynomial handle %llu", (unsigned long long)h); return ZKB_ERR_HANDLE; }
+    *out = it->second;
+    return ZKB_OK;
+}
+static int new_poly(uint64_t n, Poly** out, uint64_t* handle) {
+    Poly* p = new Poly();
+    p->n = n;
+    int rc = p->buf.reserve(n ? n * 32 : 32);
+    if (rc != ZKB_OK) { delete p; return rc; }
+    *handle = g_next_poly++;
+    poly_map()[*handle] = p;
+    *out = p;
+    return ZKB_OK;
+}
+void poly_release_all() {
+    for (auto& kv : poly_map()) { kv.second->buf.release(); delete kv.second; }
+    poly_map().clear();
+    PolyWs& w = poly_ws();
+    w.tmp.release();
+    if (w.h_out) cudaFreeHost(w.h_out);
+    w.h_out = nullptr;
+}
+
+int srs_msm_dev_by_handle(uint64_t srs_handle, const uint4* d_scalars, size_t n, cudaStream_t s, uint64_t* out);  // api.cu
+int domain_dev_by_op(int op, const uint4* d_in, uint4* d_a, uint4* d_b, size_t ncols, uint32_t k, uint32_t ek, cudaStream_t s);  // api.cu
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+int zkb_poly_upload(const uint64_t* values, size_t n, uint64_t* handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!handle || (n && !values)) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(new_poly(n, &p, handle));
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(p->buf.p, values, n * 32, cudaMemcpyHostToDevice, ctx().stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);  // the caller may reuse `values` on return
+        if (e != cudaSuccess) { set_error("polynomial upload failed: %s", cudaGetErrorString(e)); return ZKB_ERR_CUDA; }
+    }
+    return ZKB_OK;
+}
+
+int zkb_poly_alloc(size_t n, uint64_t* handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!handle) { set_error("handle is NULL"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(new_poly(n, &p, handle));
+    ZKB_CUDA_TRY(cudaMemsetAsync(p->buf.p, 0, n ? n * 32 : 32, ctx().stream));
+    return ZKB_OK;
+}
+
+int zkb_poly_len(uint64_t handle, size_t* n) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    Poly* p;
+    ZKB_TRY(find_poly(handle, &p));
+    if (n) *n = p->n;
+    return ZKB_OK;
+}
+
+int zkb_poly_download(uint64_t handle, uint64_t* out, size_t n) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Poly* p;
+    ZKB_TRY(find_poly(handle, &p));
+    if (n > p->n) { set_error("polynomial holds %zu elements, %zu requested", (size_t)p->n, n); return ZKB_ERR_ARG; }
+    if (n == 0) return ZKB_OK;
+    if (!out) { set_error("out is NULL"); return ZKB_ERR_ARG; }
+    ZKB_CUDA_TRY(cudaMemcpyAsync(out, p->buf.p, n * 32, cudaMemcpyDeviceToHost, ctx().stream));
+    ZKB_CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+    return ZKB_OK;
+}
+
+int zkb_poly_free(uint64_t handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    Poly* p;
+    ZKB_TRY(find_poly(handle, &p));
+    cudaSetDevice(ctx().device);
+    cudaStreamSynchronize(ctx().stream);
+    p->buf.release();
+    delete p;
+    poly_map().erase(handle);
+    return ZKB_OK;
+}
+
+int zkb_poly_commit(uint64_t srs_handle, uint64_t poly, uint64_t out_jac[12]) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!out_jac) { set_error("out_jac is NULL"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    return srs_msm_dev_by_handle(srs_handle, p->buf.as<uint4>(), p->n, ctx().stream, out_jac);
+}
+
+// op: 1 lagrange_to_coeff, 2 coeff_to_lagrange, 4 extended_to_coeff — in place on the handle
+static int poly_domain_inplace(int op, uint64_t poly, uint32_t k, uint32_t ek) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    const uint64_t N = 1ull << (op == 4 ? ek : k);
+    if (p->n != N) { set_error("polynomial holds %zu elements, the domain needs %zu", (size_t)p->n, (size_t)N); return ZKB_ERR_ARG; }
+    PolyWs& w = poly_ws();
+    ZKB_TRY(w.tmp.reserve(N * 32));
+    return domain_dev_by_op(op, p->buf.as<uint4>(), p->buf.as<uint4>(), w.tmp.as<uint4>(), 1, k, ek, ctx().stream);
+}
+int zkb_poly_lagrange_to_coeff(uint64_t poly, uint32_t k) { return poly_domain_inplace(1, poly, k, k); }
+int zkb_poly_coeff_to_lagrange(uint64_t poly, uint32_t k) { return poly_domain_inplace(2, poly, k, k); }
+int zkb_poly_extended_to_coeff(uint64_t poly, uint32_t k, uint32_t extended_k) { return poly_domain_inplace(4, poly, k, extended_k); }
+
+int zkb_poly_coeff_to_extended(uint64_t poly, uint32_t k, uint32_t extended_k, uint64_t* out_handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!out_handle) { set_error("out_handle is NULL"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (extended_k < k || extended_k > 28 || p->n != (1ull << k)) { set_error("polynomial length / domain mismatch"); return ZKB_ERR_ARG; }
+    const uint64_t N = 1ull << extended_k;
+    PolyWs& w = poly_ws();
+    ZKB_TRY(w.tmp.reserve(N * 32));
+    Poly* e;
+    ZKB_TRY(new_poly(N, &e, out_handle));
+    int rc = domain_dev_by_op(3, p->buf.as<uint4>(), e->buf.as<uint4>(), w.tmp.as<uint4>(), 1, k, extended_k, ctx().stream);
+    if (rc != ZKB_OK) { e->buf.release(); delete e; poly_map().erase(*out_handle); *out_handle = 0; }
+    return rc;
+}
+
+int zkb_poly_eval(uint64_t poly, const uint64_t x[4], uint64_t out[4]) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!x || !out) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (p->n == 0) { memset(out, 0, 32); return ZKB_OK; }
+    PolyWs& w = poly_ws();
+    ZKB_TRY(w.tmp.reserve(poly_tmp_bytes(p->n)));
+    if (!w.h_out) ZKB_CUDA_TRY(cudaMallocHost(&w.h_out, 64));
+    uint4* d_res = nullptr;
+    ZKB_TRY(poly_eval_dev(p->buf.as<uint4>(), p->n, fr_of(x), w.tmp.as<uint4>(), &d_res, ctx().stream));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_out, d_res, 32, cudaMemcpyDeviceToHost, ctx().stream));
+    ZKB_CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+    memcpy(out, w.h_out, 32);
+    return ZKB_OK;
+}
+
+int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!b || !out_handle) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (p->n < 1) { set_error("kate_division of an empty polynomial"); return ZKB_ERR_ARG; }
+    PolyWs& w = poly_ws();
+    ZKB_TRY(w.tmp.reserve(poly_tmp_bytes(p->n)));
+    Poly* q;
+    ZKB_TRY(new_poly(p->n, &q, out_handle));  // Q_0 .. Q_{n-1}; the quotient is the first n-1 of them (Q_{n-1} = 0)
+    int rc = kate_q_dev(p->buf.as<uint4>(), p->n, fr_of(b), q->buf.as<uint4>(), w.tmp.as<uint4>(), ctx().stream);
+    if (rc != ZKB_OK) { q->buf.release(); delete q; poly_map().erase(*out_handle); *out_handle = 0; return rc; }
+    q->n = p->n - 1;  // upstream returns a.len() - 1 coefficients
+    return ZKB_OK;
+}
+
+int zkb_poly_batch_invert(uint64_t poly) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (p->n == 0) return ZKB_OK;
+    BatchInvertArgs a{p->buf.as<uint4>(), p->n};
+    fr_batch_invert_kernel<<<nblk((p->n + INV_CHUNK - 1) / INV_CHUNK, 128), 128, 0, ctx().stream>>>(a);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+// host-buffer conveniences (upload + op + download), for callers that do not keep polynomials resident
+int zkb_fr_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]) {
+    uint64_t h = 0;
+    ZKB_TRY(zkb_poly_upload(coeffs, n, &h));
+    int rc = zkb_poly_eval(h, x, out);
+    zkb_poly_free(h);
+    return rc;
+}
+int zkb_fr_kate_division(const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* out) {
+    if (n < 1) { set_error("kate_division of an empty polynomial"); return ZKB_ERR_ARG; }
+    uint64_t h = 0, q = 0;
+    ZKB_TRY(zkb_poly_upload(coeffs, n, &h));
+    int rc = zkb_poly_kate_division(h, b, &q);
+    if (rc == ZKB_OK) rc = zkb_poly_download(q, out, n - 1);
+    zkb_poly_free(h);
+    if (q) zkb_poly_free(q);
+    return rc;
+}
+int zkb_fr_batch_invert(uint64_t* values, size_t n) {
+    uint64_t h = 0;
+    ZKB_TRY(zkb_poly_upload(values, n, &h));
+    int rc = zkb_poly_batch_invert(h);
+    if (rc == ZKB_OK) rc = zkb_poly_download(h, values, n);
+    zkb_poly_free(h);
+    return rc;
+}
+
+}  // extern "C"

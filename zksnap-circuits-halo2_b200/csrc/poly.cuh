@@ -1,0 +1,81 @@
+// poly.cuh — Fr vector kernels either side of the commits, device code as per-thread functions.
+//
+// Restates (on the device) three halo2-axiom `arithmetic` helpers the prover calls on every committed polynomial
+// (sources un-vendored; the maths fixes the results uniquely, the field being exact):
+//   eval_polynomial(poly, x)          sum_i a_i x^i                       — evaluations written to the transcript
+//   kate_division(a, b)               quotient of a(X) / (X - b)           — GWC / SHPLONK witness polynomials
+//   BatchInvert (ff::BatchInvert)     element-wise inverse, zeros stay 0  — permutation / lookup grand products
+// All three are chunked: a thread owns POLY_CHUNK consecutive coefficients; chunk results are combined by applying the
+// same routine one level up (x -> x^CHUNK), so a 2^22 polynomial takes four short launches.
+#pragma once
+#include "setup.cuh"
+
+namespace zkb {
+
+constexpr uint32_t POLY_CHUNK = 64;
+
+struct PolyEvalArgs {
+    const uint4* a;   // n coefficients
+    uint64_t n;
+    uint4* out;       // ceil(n / POLY_CHUNK) partial values: out[t] = sum_j a[t C + j] x^j
+    uint32_t x[8];    // Montgomery Fr
+};
+ZKB_HD void poly_eval_chunk_thread(const PolyEvalArgs& p, uint64_t t) {
+    const uint64_t lo = t * POLY_CHUNK;
+    if (lo >= p.n) return;
+    const uint64_t hi = lo + POLY_CHUNK < p.n ? lo + POLY_CHUNK : p.n;
+    const Fr x = fr_from_words(p.x);
+    Fr acc = fr_load2(p.a, hi - 1);
+    for (uint64_t i = hi - 1; i-- > lo;) acc = fp_add(fp_mul(acc, x), fr_load2(p.a, i));
+    fr_store2(p.out, t, acc);
+}
+
+// Q_{i-1} = a_i + b Q_i inside chunk t, started from the carry K_t = Q at the chunk's last index
+// (K of the last chunk is 0): writes Q_i for every index of the chunk.
+struct KateExpandArgs {
+    const uint4* a;      // n coefficients
+    uint64_t n;
+    const uint4* carry;  // ceil(n / POLY_CHUNK) values K_t, or NULL when there is a single chunk (K = 0)
+    uint4* q;            // n values Q_0 .. Q_{n-1} (Q_{n-1} = 0); the quotient is q[0 .. n-2]
+    uint32_t b[8];
+};
+ZKB_HD void kate_expand_thread(const KateExpandArgs& p, uint64_t t) {
+    const uint64_t lo = t * POLY_CHUNK;
+    if (lo >= p.n) return;
+    const uint64_t hi = lo + POLY_CHUNK < p.n ? lo + POLY_CHUNK : p.n;
+    const Fr b = fr_from_words(p.b);
+    Fr q = p.carry ? fr_load2(p.carry, t) : Fr::zero();
+    fr_store2(p.q, hi - 1, q);
+    for (uint64_t i = hi - 1; i > lo; --i) {
+        q = fp_add(fr_load2(p.a, i), fp_mul(b, q));
+        fr_store2(p.q, i - 1, q);
+    }
+}
+
+// in place: a[i] <- a[i]^-1, zeros untouched; one Fermat inversion per POLY_CHUNK / 2 elements
+constexpr uint32_t INV_CHUNK = 32;
+struct BatchInvertArgs {
+    uint4* a;
+    uint64_t n;
+};
+ZKB_HD void fr_batch_invert_thread(const BatchInvertArgs& p, uint64_t t) {
+    const uint64_t lo = t * INV_CHUNK;
+    if (lo >= p.n) return;
+    const uint64_t hi = lo + INV_CHUNK < p.n ? lo + INV_CHUNK : p.n;
+    Fr pre[INV_CHUNK];
+    Fr acc = Fr::one();
+    for (uint64_t i = lo; i < hi; ++i) {
+        pre[i - lo] = acc;
+        const Fr v = fr_load2(p.a, i);
+        if (!v.is_zero()) acc = fp_mul(acc, v);
+    }
+    Fr inv = fp_inv(acc);
+    for (uint64_t i = hi; i-- > lo;) {
+        const Fr v = fr_load2(p.a, i);
+        if (v.is_zero()) continue;
+        fr_store2(p.a, i, fp_mul(inv, pre[i - lo]));
+        inv = fp_mul(inv, v);
+    }
+}
+
+}  // namespace zkb

@@ -107,6 +107,101 @@ def batch_normalize(points_jac: np.ndarray) -> np.ndarray:
     return out
 
 
+def eval_polynomial(poly: np.ndarray, point: np.ndarray) -> np.ndarray:
+    """arithmetic::eval_polynomial(poly: &[Fr], point: Fr) -> Fr"""
+    a = _fr(poly, "poly")
+    out = np.zeros(4, dtype=np.uint64)
+    check(lib().zkb_fr_eval_polynomial(_p(a), a.shape[0], _p(np.ascontiguousarray(point, dtype=np.uint64).reshape(4)), _p(out)))
+    return out
+
+
+def kate_division(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """arithmetic::kate_division(a, b): the len-1 coefficients of a(X) / (X - b) (remainder discarded, as upstream)."""
+    v = _fr(a, "a")
+    assert v.shape[0] >= 1
+    out = np.zeros((v.shape[0] - 1, 4), dtype=np.uint64)
+    check(lib().zkb_fr_kate_division(_p(v), v.shape[0], _p(np.ascontiguousarray(b, dtype=np.uint64).reshape(4)), _p(out)))
+    return out
+
+
+def batch_invert(values: np.ndarray) -> np.ndarray:
+    """ff::BatchInvert: element-wise inverse, zeros stay zero."""
+    v = np.array(_fr(values, "values"), copy=True)
+    check(lib().zkb_fr_batch_invert(_p(v), v.shape[0]))
+    return v
+
+
+class Polynomial:
+    """A polynomial (or column of evaluations) resident in HBM: uploaded once, then committed / transformed / evaluated on
+    the device (the prover's commit_lagrange -> lagrange_to_coeff -> coeff_to_extended -> eval -> kate_division chain)."""
+
+    def __init__(self, values: np.ndarray | None = None, _handle: int | None = None):
+        self._h = ctypes.c_uint64(0)
+        if _handle is not None:
+            self._h.value = _handle
+        else:
+            v = _fr(values, "values")
+            check(lib().zkb_poly_upload(_p(v), v.shape[0], ctypes.byref(self._h)))
+
+    def __len__(self) -> int:
+        n = ctypes.c_size_t(0)
+        check(lib().zkb_poly_len(self._h, ctypes.byref(n)))
+        return n.value
+
+    def to_host(self) -> np.ndarray:
+        out = np.zeros((len(self), 4), dtype=np.uint64)
+        check(lib().zkb_poly_download(self._h, _p(out), out.shape[0]))
+        return out
+
+    def commit(self, params: "ParamsKZG", lagrange: bool = False) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        h = params.handle_g_lagrange if lagrange else params.handle_g
+        check(lib().zkb_poly_commit(h, self._h, _p(out)))
+        return out
+
+    def lagrange_to_coeff(self, domain: "EvaluationDomain") -> "Polynomial":
+        check(lib().zkb_poly_lagrange_to_coeff(self._h, domain.k))
+        return self
+
+    def coeff_to_lagrange(self, domain: "EvaluationDomain") -> "Polynomial":
+        check(lib().zkb_poly_coeff_to_lagrange(self._h, domain.k))
+        return self
+
+    def coeff_to_extended(self, domain: "EvaluationDomain") -> "Polynomial":
+        h = ctypes.c_uint64(0)
+        check(lib().zkb_poly_coeff_to_extended(self._h, domain.k, domain.extended_k, ctypes.byref(h)))
+        return Polynomial(_handle=h.value)
+
+    def extended_to_coeff(self, domain: "EvaluationDomain") -> "Polynomial":
+        check(lib().zkb_poly_extended_to_coeff(self._h, domain.k, domain.extended_k))
+        return self
+
+    def eval(self, point: np.ndarray) -> np.ndarray:
+        out = np.zeros(4, dtype=np.uint64)
+        check(lib().zkb_poly_eval(self._h, _p(np.ascontiguousarray(point, dtype=np.uint64).reshape(4)), _p(out)))
+        return out
+
+    def kate_division(self, b: np.ndarray) -> "Polynomial":
+        h = ctypes.c_uint64(0)
+        check(lib().zkb_poly_kate_division(self._h, _p(np.ascontiguousarray(b, dtype=np.uint64).reshape(4)), ctypes.byref(h)))
+        return Polynomial(_handle=h.value)
+
+    def batch_invert(self) -> "Polynomial":
+        check(lib().zkb_poly_batch_invert(self._h))
+        return self
+
+    def free(self) -> None:
+        if self._h.value:
+            lib().zkb_poly_free(self._h)
+            self._h.value = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 # ---- halo2_proofs::poly::EvaluationDomain ------------------------------------------------------------------------------
 class EvaluationDomain:
     """EvaluationDomain::<Fr>::new(j, k): j = cs.degree(), n = 2^k."""
