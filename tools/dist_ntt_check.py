@@ -104,6 +104,22 @@ def main():
             zkb.prof.enable(False)
             line.update({"ms": float(tt.item()), "elems_per_s": n / (float(tt.item()) * 1e-3), "rank0_ms": parts,
                          "nvlink_bytes_per_rank": int(3 * (world - 1) / world * ln * 32)})
+            # what an NCCL-based exchange would cost on top of the local passes: the sharded transform moves each slice three
+            # times (gather for pass 0, scatter of pass 0, scatter of the last pass); time ONE all_to_all_single of the slice
+            buf_in = torch.empty(ln * 4, dtype=torch.int64, device=dev)
+            buf_out = torch.empty_like(buf_in)
+            for it in range(2 + args.iters):
+                if it == 2:
+                    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                    e0.record(stream)
+                dist.all_to_all_single(buf_out, buf_in)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            a2a = torch.tensor([e0.elapsed_time(e1) / args.iters], device=dev, dtype=torch.float64)
+            dist.all_reduce(a2a, op=dist.ReduceOp.MAX)
+            line["nccl_all_to_all_single_ms"] = float(a2a.item())
+            line["nccl_three_exchanges_ms"] = 3 * float(a2a.item())
+            del buf_in, buf_out
             if k <= 26 and rank == 0:  # single-GPU time of the same transform for comparison
                 d = torch.empty(n * 4, dtype=torch.int64, device=dev)
                 s = torch.empty_like(d)

@@ -111,7 +111,7 @@ static int dist_ntt_dev(const void* d_in, void* d_out, const uint64_t omega[4], 
     if (!d.connected) { set_error("zkb_dist_connect has not been called"); return ZKB_ERR_ARG; }
     if (log_n > d.max_log_n) { set_error("log_n %u exceeds the dist context's max_log_n %u", log_n, d.max_log_n); return ZKB_ERR_ARG; }
     NttPlan* plan = nullptr;
-    ZKB_TRY(ntt_get_plan(log_n, omega, s, &plan));
+    ZKB_TRY(ntt_get_plan(log_n, omega, s, &plan, true));  // small radix first: wide tiles for the exchange pass
     const NttGeometry& g = plan->geom;
     if (d.log_g == 0 || !ntt_dist_supported(g, d.log_g)) {
         set_error("a 2^%u NTT cannot be sharded over %d ranks (needs >= 2 passes and tiles inside a rank's share)", log_n, d.world);

@@ -170,7 +170,7 @@ EMU_EXPORT int zkb_emu_ntt_dist_phase(int phase, uint32_t rank, uint32_t log_g, 
                                       uint64_t* const* A, uint64_t* const* W, uint64_t* const* O) {
     if (log_n < 1 || log_n > 28 || log_g > 3) return -1;
     const uint64_t N = 1ull << log_n;
-    NttGeometry g = ntt_geometry(log_n);
+    NttGeometry g = ntt_geometry(log_n, true);
     if (!ntt_dist_supported(g, log_g)) return -2;
     Fr w = fr_from_u64(omega);
     std::vector<uint4> tw_lo, tw_hi, tw_r[NTT_MAX_PASSES];

@@ -57,7 +57,7 @@ int ntt_launch_pass(uint32_t logr, const NttPassArgs& a, dim3 grid, uint32_t thr
 }
 
 // ---- plan cache: twiddle tables for (log_n, omega) ---------------------------------------------------------------
-static std::map<std::pair<uint32_t, std::array<uint64_t, 4>>, NttPlan*>& plan_cache() {
+static std::map<std::pair<uint32_t, std::array<uint64_t, 4>>, NttPlan*>& plan_cache() {  // key.first = log_n | small_first << 8
     static std::map<std::pair<uint32_t, std::array<uint64_t, 4>>, NttPlan*> m;
     return m;
 }
@@ -71,14 +71,15 @@ static int build_table(DevBuf& buf, const Fr& w, uint64_t count, uint32_t shift,
     return ZKB_OK;
 }
 
-int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPlan** out) {
+int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPlan** out, bool small_first) {
     if (log_n < 1 || log_n > 28) { set_error("log_n %u out of range [1, 28]", log_n); return ZKB_ERR_ARG; }
     std::array<uint64_t, 4> key{omega[0], omega[1], omega[2], omega[3]};
     auto& cache = plan_cache();
-    auto it = cache.find({log_n, key});
+    const uint32_t ckey = log_n | (small_first ? 256u : 0u);
+    auto it = cache.find({ckey, key});
     if (it != cache.end()) { *out = it->second; return ZKB_OK; }
     NttPlan* p = new NttPlan();
-    p->geom = ntt_geometry(log_n);
+    p->geom = ntt_geometry(log_n, small_first);
     for (int i = 0; i < 4; ++i) { p->omega.l[2 * i] = (uint32_t)omega[i]; p->omega.l[2 * i + 1] = (uint32_t)(omega[i] >> 32); }
     const uint64_t N = 1ull << log_n;
     int rc = build_table(p->tw_lo, p->omega, 1ull << p->geom.tw_h, 0, s);
@@ -109,7 +110,7 @@ int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPla
     }
     // tables are built on `s`; later launches may use another stream, so make them visible now
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
-    cache[{log_n, key}] = p;
+    cache[{ckey, key}] = p;
     *out = p;
     return ZKB_OK;
 }

@@ -28,7 +28,7 @@ struct NttIo {
     const Fr* out_scale = nullptr;  // 3 constants or NULL
 };
 
-int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPlan** out);
+int ntt_get_plan(uint32_t log_n, const uint64_t omega[4], cudaStream_t s, NttPlan** out, bool small_first = false);
 int ntt_run(const NttPlan& plan, const NttIo& io, cudaStream_t s);
 void ntt_clear_plans();
 // one pass of the multi-pass NTT (grid.x CTAs of R*T elements, grid.y columns); used by the sharded driver in dist.cu

@@ -1,6 +1,7 @@
 // ntt_plan.hpp — host-side geometry of the multi-pass NTT (shared by the CUDA driver and the CPU emulator).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 #include "ntt.cuh"
 
@@ -14,8 +15,11 @@ struct NttGeometry {
     uint32_t tw_h;
 };
 
-// R <= 2^10 in a single pass, otherwise ceil(log_n / 9) passes with radices as equal as possible
-inline NttGeometry ntt_geometry(uint32_t log_n) {
+// R <= 2^10 in a single pass, otherwise ceil(log_n / 9) passes with radices as equal as possible.
+// small_first: the smaller radices go to the first passes — used by the sharded NTT, whose pass 0 gathers its rows from
+// peer HBM over NVLink: a smaller R_1 means wider tiles (T = 1024 / R_1 adjacent columns), i.e. 128-256 byte row segments
+// instead of 64 (profiles/r1_dist_ntt_8gpu.txt).
+inline NttGeometry ntt_geometry(uint32_t log_n, bool small_first = false) {
     NttGeometry g{};
     g.log_n = log_n;
     if (log_n <= 10) {
@@ -24,7 +28,23 @@ inline NttGeometry ntt_geometry(uint32_t log_n) {
     } else {
         g.npass = (log_n + 8) / 9;
         uint32_t base = log_n / g.npass, rem = log_n % g.npass;
-        for (uint32_t p = 0; p < g.npass; ++p) g.lr[p] = base + (p < rem ? 1 : 0);
+        for (uint32_t p = 0; p < g.npass; ++p) g.lr[p] = base + ((small_first ? p >= g.npass - rem : p < rem) ? 1 : 0);
+    }
+    // experiment hook: ZKB_NTT_GEOM="8,10,8" forces the radices of the transform whose log_n equals their sum
+    if (const char* e = getenv("ZKB_NTT_GEOM")) {
+        uint32_t lr[NTT_MAX_PASSES] = {0, 0, 0, 0}, np = 0, sum = 0;
+        for (const char* c = e; *c && np < NTT_MAX_PASSES;) {
+            lr[np] = (uint32_t)strtoul(c, nullptr, 10);
+            sum += lr[np++];
+            while (*c && *c != ',') ++c;
+            if (*c == ',') ++c;
+        }
+        bool ok = sum == log_n && np >= 1;
+        for (uint32_t p = 0; p < np; ++p) ok = ok && lr[p] >= 1 && lr[p] <= 10;
+        if (ok) {
+            g.npass = np;
+            for (uint32_t p = 0; p < NTT_MAX_PASSES; ++p) g.lr[p] = p < np ? lr[p] : 0;
+        }
     }
     g.tw_h = (log_n + 1) / 2;
     for (uint32_t p = 0; p < g.npass; ++p) {
