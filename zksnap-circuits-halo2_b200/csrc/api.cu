@@ -522,19 +522,27 @@ static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t
     Ctx& c = ctx();
     HostIo& h = hostio();
     ZKB_TRY(check_ptr(scalars, "scalars"));
-    // automatic slice count (profiles/r1_tuning.txt): two slices hide half of a pinned upload at +1.5 ms of accumulate time
-    // (shorter bucket runs); pageable memory is staged by host threads at a fraction of PCIe speed, so four slices
+    // Slice boundaries (profiles/r1_tuning.txt §3).  Explicit count: equal slices.  Automatic: a SHORT first slice (its upload
+    // is the only exposed one) and growing later ones, so most of the points still sit in long bucket runs; pageable memory is
+    // staged by host threads at a fraction of PCIe speed, so it gets one more, even shorter, leading slice.
     const bool pinned = host_ptr_is_pinned(scalars);
-    size_t slices = 1;
-    if (g_msm_slices > 0) slices = (size_t)g_msm_slices;
-    else if (n >= ((size_t)1 << 21)) {
-        slices = n >> 23;
-        if (slices < 2) slices = 2;
-        if (slices > 8) slices = 8;
-        if (!pinned && slices < 4) slices = 4;
+    std::vector<size_t> bounds;  // exclusive upper ends
+    if (g_msm_slices > 1) {
+        const size_t per = (n + g_msm_slices - 1) / g_msm_slices;
+        for (size_t hi = per; hi < n; hi += per) bounds.push_back(hi);
+    } else if (g_msm_slices == 0 && n >= ((size_t)1 << 21)) {
+        const bool big = n >= ((size_t)1 << 23);
+        if (pinned) {
+            if (big) { bounds.push_back(n / 8); bounds.push_back(n / 2); }
+            else bounds.push_back(n / 4);
+        } else {
+            if (big) { bounds.push_back(n / 16); bounds.push_back(n / 4); bounds.push_back(n / 8 * 5); }
+            else { bounds.push_back(n / 8); bounds.push_back(n / 2); }
+        }
     }
-    if (slices > 1 && !srs_table_ready(srs, c.stream)) slices = 1;
-    if (slices > n) slices = 1;
+    bounds.push_back(n);
+    if (bounds.size() > 1 && !srs_table_ready(srs, c.stream)) { bounds.clear(); bounds.push_back(n); }
+    const size_t slices = bounds.size();
     if (slices == 1) {
         ZKB_TRY(upload_scalars(scalars, n));
         return msm_srs_dev(srs, offset, h.scalars.as<uint4>(), n, c.stream, out_jac);
@@ -542,7 +550,8 @@ static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t
     ZKB_TRY(pipeline_init());
     Pipeline& pl = pipeline();
     ZKB_TRY(h.scalars.reserve(n * 32));
-    const size_t per = (n + slices - 1) / slices;
+    size_t per = 0;  // largest slice
+    for (size_t i = 0, lo = 0; i < slices; lo = bounds[i++]) per = bounds[i] - lo > per ? bounds[i] - lo : per;
     if (!pinned) {
         for (auto& b : h.stage) ZKB_TRY(b.reserve(per * 32));
         for (auto& e : h.stage_ev)
@@ -552,8 +561,8 @@ static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t
         cudaStreamSynchronize(pl.s_h2d); cudaStreamSynchronize(c.stream);
         return rc;
     };
-    for (size_t sidx = 0, lo = 0; lo < n; ++sidx, lo += per) {
-        const size_t cnt = n - lo < per ? n - lo : per;
+    for (size_t sidx = 0, lo = 0; sidx < slices; lo = bounds[sidx++]) {
+        const size_t cnt = bounds[sidx] - lo;
         const void* src = scalars + 4 * lo;
         PipeSlot& ev = pl.slot[sidx % PIPE_SLOTS];  // only the events of the slot are used here
         if (!pinned) {
