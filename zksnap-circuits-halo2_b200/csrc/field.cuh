@@ -25,8 +25,12 @@
 #else
 #define ZKB_HD inline
 #define ZKB_HD_NOINLINE inline
+#ifndef __host__
 #define __host__
+#endif
+#ifndef __device__
 #define __device__
+#endif
 #endif
 
 namespace zkb {
