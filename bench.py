@@ -35,7 +35,8 @@ LOG_N_MSM = int(os.environ.get("ZKB_BENCH_LOG_N", "24"))
 NTT_LOG_N = int(os.environ.get("ZKB_BENCH_NTT_LOG_N", "22"))
 NTT_COLS = int(os.environ.get("ZKB_BENCH_NTT_COLS", "16"))
 SHARDED_LOG_N = int(os.environ.get("ZKB_BENCH_SHARDED_LOG_N", "26"))
-CPU_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_CPU_LOG_N", "20"))
+CPU_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_CPU_LOG_N", "24"))   # cpu_baseline leg: the full workload once, ~10 s on 16 threads
+REF_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_REF_LOG_N", "22"))   # --impl reference: bounded sample per step
 METRIC = "BN254 G1 MSM throughput (2^%d points per GPU, SRS resident)" % LOG_N_MSM
 
 
@@ -138,20 +139,20 @@ def run_reference(args):
     ts = []
     cores = 0
     for i in range(args.warmup + args.steps):
-        v, cores, dt = cpu_baseline_msm(CPU_SAMPLE_LOG_N)
+        v, cores, dt = cpu_baseline_msm(REF_SAMPLE_LOG_N)
         if i >= args.warmup:
             ts.append(dt)
-    n = 1 << CPU_SAMPLE_LOG_N
+    n = 1 << REF_SAMPLE_LOG_N
     value = n * len(ts) / sum(ts)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (254-bit Montgomery)",
         "data": "synthetic",
-        "config": {"workload": "msm_g1_2^%d_uniform" % LOG_N_MSM, "sample": "2^%d points per step" % CPU_SAMPLE_LOG_N},
+        "config": {"workload": "msm_g1_2^%d_uniform" % LOG_N_MSM, "sample": "2^%d points per step" % REF_SAMPLE_LOG_N},
         "cpu_baseline": {"value": value, "unit": "pts/s", "cores": cores, "kind": "port",
                          "sample": "best_multiexp restatement (C, pthreads; not rayon) on 2^%d uniform points per step"
-                                   % CPU_SAMPLE_LOG_N},
+                                   % REF_SAMPLE_LOG_N},
         "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
