@@ -309,19 +309,24 @@ ZKB_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
           "=r"(borrow)
         : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
           "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-    asm("add.cc.u32  %0, %8,  %16;\n\t"
-        "addc.cc.u32 %1, %9,  %17;\n\t"
-        "addc.cc.u32 %2, %10, %18;\n\t"
-        "addc.cc.u32 %3, %11, %19;\n\t"
-        "addc.cc.u32 %4, %12, %20;\n\t"
-        "addc.cc.u32 %5, %13, %21;\n\t"
-        "addc.cc.u32 %6, %14, %22;\n\t"
-        "addc.u32    %7, %15, %23;\n\t"
-        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
-          "=r"(r.l[7])
-        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
-          "r"(P::M(0) & borrow), "r"(P::M(1) & borrow), "r"(P::M(2) & borrow), "r"(P::M(3) & borrow),
-          "r"(P::M(4) & borrow), "r"(P::M(5) & borrow), "r"(P::M(6) & borrow), "r"(P::M(7) & borrow));
+    // conditional + M as a predicated carry chain (no masking instructions)
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %8, 0;\n\t"
+        "@p add.cc.u32  %0, %0, %9;\n\t"
+        "@p addc.cc.u32 %1, %1, %10;\n\t"
+        "@p addc.cc.u32 %2, %2, %11;\n\t"
+        "@p addc.cc.u32 %3, %3, %12;\n\t"
+        "@p addc.cc.u32 %4, %4, %13;\n\t"
+        "@p addc.cc.u32 %5, %5, %14;\n\t"
+        "@p addc.cc.u32 %6, %6, %15;\n\t"
+        "@p addc.u32    %7, %7, %16;\n\t"
+        "}\n\t"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7])
+        : "r"(borrow), "r"(P::M(0)), "r"(P::M(1)), "r"(P::M(2)), "r"(P::M(3)), "r"(P::M(4)), "r"(P::M(5)), "r"(P::M(6)),
+          "r"(P::M(7)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
 #endif
     return r;
 }
