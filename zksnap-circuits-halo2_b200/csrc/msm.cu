@@ -7,8 +7,45 @@
 
 namespace zkb {
 
+// One scalar per thread.  The entries of a warp are written contiguously: warp-level exclusive scan of the per-thread
+// counts, one atomicAdd per warp on the global entry counter.  STAGED: the warp's entries go through shared memory so the
+// global stores are coalesced (nwin <= 24, i.e. every MSM of more than a few thousand points); otherwise each thread writes
+// its own short run directly.
+constexpr uint32_t MSM_DIGIT_STAGE_WINDOWS = 24;
+template <bool STAGED, uint32_t CT_C>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const MsmDigitArgs a) {
-    msm_digits_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    extern __shared__ uint32_t digit_smem[];  // STAGED: per warp nwin * 32 keys, then nwin * 32 values
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < a.n * a.ncols;
+    Fr s = Fr::zero();
+    if (live) s = fp_from_mont(fr_load2(a.scalars, t));
+    uint32_t cnt = 0;
+    if (live) msm_digits_foreach<CT_C>(a, t, s, [&](uint32_t, uint32_t) { ++cnt; });
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && warp_total) base = atomicAdd(a.counter, (unsigned long long)warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t off = incl - cnt;
+    if (STAGED) {
+        const uint32_t per_warp = a.nwin * 32;
+        uint32_t* sk = digit_smem + (threadIdx.x >> 5) * 2 * per_warp;
+        uint32_t* sv = sk + per_warp;
+        if (live && cnt) msm_digits_foreach<CT_C>(a, t, s, [&](uint32_t k, uint32_t v) { sk[off] = k; sv[off] = v; ++off; });
+        __syncwarp();
+        for (uint32_t j = lane; j < warp_total; j += 32) {
+            a.keys[base + j] = sk[j];
+            a.vals[base + j] = sv[j];
+        }
+    } else {
+        if (live && cnt) msm_digits_foreach<CT_C>(a, t, s, [&](uint32_t k, uint32_t v) { a.keys[base + off] = k; a.vals[base + off] = v; ++off; });
+    }
 }
 
 template <bool LEVEL0>
@@ -133,6 +170,7 @@ void msm_release_workspace() {
     for (auto& b : w.pv) b.release();
     for (auto& b : w.seg) b.release();
     w.sort_tmp.release();
+    w.counter.release();
     w.buckets.release();
     if (w.h_sums) { cudaFreeHost(w.h_sums); w.h_sums = nullptr; w.h_sums_cap = 0; }
 }
@@ -182,15 +220,11 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, s));
     }
     ZKB_TRY(w.sort_tmp.reserve(sort_bytes));
+    ZKB_TRY(w.counter.reserve(8));
     const size_t bucket_bytes = (size_t)g.nbuckets * 128;
     ZKB_TRY(w.buckets.reserve(phase == MSM_WHOLE ? bucket_bytes : 2 * bucket_bytes));  // sliced: main + scratch array
     uint4* const bucket_main = w.buckets.as<uint4>();
     uint4* const bucket_acc = (phase & MSM_FIRST) ? bucket_main : bucket_main + 8 * (size_t)g.nbuckets;
-    const uint64_t t0 = (total + g.chunk0 - 1) / g.chunk0;
-    for (int i = 0; i < 2; ++i) {
-        ZKB_TRY(w.pk[i].reserve(2 * t0 * 4));
-        ZKB_TRY(w.pv[i].reserve(2 * t0 * 128));
-    }
     const uint64_t J0 = 1ull << (g.c - 1 - g.log_m);
     for (int i = 0; i < 2; ++i) ZKB_TRY(w.seg[i].reserve((size_t)g.total_sets * J0 * 128));
     const size_t host_bytes = (size_t)g.total_sets * 128 > (size_t)ncols * 96 ? (size_t)g.total_sets * 128 : (size_t)ncols * 96;
@@ -208,12 +242,31 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         MsmDigitArgs a{};
         a.scalars = d_scalars; a.n = n; a.ncols = ncols; a.sets_per_col = g.bucket_sets; a.c = g.c; a.nwin = g.nwin;
         a.keys = w.keys[0].as<uint32_t>(); a.vals = w.vals[0].as<uint32_t>();
+        a.counter = reinterpret_cast<unsigned long long*>(w.counter.p);
         a.invalid_key = g.invalid_key;
         a.table_mode = table ? 1 : 0;
         a.row_stride = table ? table->row_stride : 0;
-        msm_digits_kernel<<<blocks_for(n * ncols, 256), 256, 0, s>>>(a);
+        ZKB_CUDA_TRY(cudaMemsetAsync(w.counter.p, 0, 8, s));
+        const unsigned nb = blocks_for(n * ncols, 256);
+        const size_t sm = (size_t)g.nwin * 32 * 2 * 4 * 8;
+        switch (g.nwin <= MSM_DIGIT_STAGE_WINDOWS ? g.c : 0u) {  // the window widths large MSMs use are compiled in
+#define ZKB_DIGITS_CASE(C) case C: msm_digits_kernel<true, C><<<nb, 256, sm, s>>>(a); break;
+            ZKB_DIGITS_CASE(16) ZKB_DIGITS_CASE(17) ZKB_DIGITS_CASE(18) ZKB_DIGITS_CASE(19)
+            ZKB_DIGITS_CASE(20) ZKB_DIGITS_CASE(21) ZKB_DIGITS_CASE(22)
+#undef ZKB_DIGITS_CASE
+            case 0: msm_digits_kernel<false, 0><<<nb, 256, 0, s>>>(a); break;
+            default: msm_digits_kernel<true, 0><<<nb, 256, sm, s>>>(a); break;
+        }
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
+    }
+    // the number of non-zero digits decides the size of everything downstream (a witness column has few)
+    uint64_t valid = 0;
+    {
+        unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(w.h_sums);
+        ZKB_CUDA_TRY(cudaMemcpyAsync(h_cnt, w.counter.p, 8, cudaMemcpyDeviceToHost, s));
+        ZKB_CUDA_TRY(cudaStreamSynchronize(s));
+        valid = *h_cnt;
     }
     // ---- 2. sort
     const uint32_t* sk;
@@ -222,15 +275,27 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ProfScope prof("msm_sort", s);
         cub::DoubleBuffer<uint32_t> dk(w.keys[0].as<uint32_t>(), w.keys[1].as<uint32_t>());
         cub::DoubleBuffer<uint32_t> dv(w.vals[0].as<uint32_t>(), w.vals[1].as<uint32_t>());
-        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp.p, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, s));
+        uint32_t kb = 1;  // keys are < nbuckets now (no "invalid" key)
+        while ((1ull << kb) < g.nbuckets) ++kb;
+        if (valid) ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp.p, sort_bytes, dk, dv, (int)valid, 0, (int)kb, s));
         sk = dk.Current();
         sv = dv.Current();
+    }
+    uint32_t chunk0 = g.chunk0;
+    if (!c.msm_chunk_override)
+        while (chunk0 > 16 && valid / chunk0 < 147456) chunk0 >>= 1;  // few entries: shorter chains, more threads
+    {
+        const uint64_t t0 = (valid + chunk0 - 1) / chunk0 + 1;  // level-0 threads: two partial entries each
+        for (int i = 0; i < 2; ++i) {
+            ZKB_TRY(w.pk[i].reserve(2 * t0 * 4));
+            ZKB_TRY(w.pv[i].reserve(2 * t0 * 128));
+        }
     }
     // ---- 3. accumulate (levels)
     {
         ProfScope prof("msm_accumulate", s);
         ZKB_CUDA_TRY(cudaMemsetAsync(bucket_acc, 0, bucket_bytes, s));
-        uint64_t count = total;
+        uint64_t count = valid;
         int level = 0, pp = 0;
         while (count > 0) {
             MsmAccArgs a{};
@@ -240,7 +305,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             a.bases = table ? table->rows : d_bases;
             a.pin = w.pv[pp ^ 1].as<uint4>();
             a.count = count;
-            a.chunk = last ? (uint32_t)count : (level == 0 ? g.chunk0 : g.chunk_up);
+            a.chunk = last ? (uint32_t)count : (level == 0 ? chunk0 : g.chunk_up);
             a.invalid_key = g.invalid_key;
             a.last_level = last ? 1 : 0;
             a.buckets = bucket_acc;

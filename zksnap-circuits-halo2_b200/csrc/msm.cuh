@@ -31,8 +31,9 @@ struct MsmDigitArgs {
     uint32_t sets_per_col; // bucket sets per column: W, or 1 in table mode
     uint32_t c;            // window bits
     uint32_t nwin;         // W, W*c >= 255
-    uint32_t* keys;        // [W * ncols * n], window-major
+    uint32_t* keys;        // [<= W * ncols * n] compacted: only non-zero digits, in arbitrary order
     uint32_t* vals;
+    unsigned long long* counter;  // number of entries written (device)
     uint32_t invalid_key;  // number of buckets: W << (c-1), or 1 << (c-1) in table mode
     uint32_t table_mode;   // 1: bases are the precomputed rows T[w][i] = 2^(c w) P_i, all windows share one bucket set
     uint64_t row_stride;   // table mode: points per row (the registered SRS length)
@@ -46,24 +47,49 @@ ZKB_HD uint32_t msm_extract_bits(const Fr& s, uint32_t bit, uint32_t c) {  // c 
     return (uint32_t)(v >> sh) & ((1u << c) - 1);
 }
 
-ZKB_HD void msm_digits_thread(const MsmDigitArgs& a, uint64_t t) {
-    const uint64_t total = a.n * a.ncols;
-    if (t >= total) return;
+constexpr uint32_t MSM_MAX_WINDOWS = 128;  // c >= 2
+
+// Digits of scalar t: fills (key, value) for every NON-ZERO digit and returns how many there are.  Zero digits (half of a
+// witness column is zeros, most of the rest are small values) produce no entry at all, so they are neither sorted nor
+// visited by the accumulation.
+// calls f(key, value) for every non-zero signed digit of the canonical scalar s (scalar index t).
+// CT_C > 0: window width known at compile time (the loop unrolls, limb indices become constants and `s` stays in
+// registers); CT_C == 0: runtime a.c / a.nwin.
+template <uint32_t CT_C, class F>
+ZKB_HD void msm_digits_foreach(const MsmDigitArgs& a, uint64_t t, const Fr& s, F&& f) {
     const uint32_t col = (uint32_t)(t / a.n);
     const uint64_t i = t - (uint64_t)col * a.n;
-    Fr s = fp_from_mont(fr_load2(a.scalars, t));
+    const uint32_t c = CT_C ? CT_C : a.c;
+    const uint32_t nwin = CT_C ? (255 + CT_C - 1) / CT_C : a.nwin;
     uint32_t carry = 0;
-    const uint32_t half = 1u << (a.c - 1);
-    for (uint32_t w = 0; w < a.nwin; ++w) {
-        uint32_t v = msm_extract_bits(s, w * a.c, a.c) + carry;
+    const uint32_t half = 1u << (c - 1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t w = 0; w < nwin; ++w) {
+        uint32_t v = msm_extract_bits(s, w * c, c) + carry;
         uint32_t neg = v > half;
-        uint32_t mag = neg ? (1u << a.c) - v : v;
+        uint32_t mag = neg ? (1u << c) - v : v;
         carry = neg;
+        if (!mag) continue;
         const uint32_t set = col * a.sets_per_col + (a.table_mode ? 0u : w);
-        const uint32_t key = mag ? (set << (a.c - 1)) + (mag - 1) : a.invalid_key;
         const uint32_t idx = a.table_mode ? (uint32_t)((uint64_t)w * a.row_stride + i) : (uint32_t)i;
-        a.keys[(uint64_t)w * total + t] = key;
-        a.vals[(uint64_t)w * total + t] = idx | (neg << 31);
+        f((set << (c - 1)) + (mag - 1), idx | (neg << 31));
+    }
+}
+
+ZKB_HD uint32_t msm_digits_compute(const MsmDigitArgs& a, uint64_t t, uint32_t* keys, uint32_t* vals) {
+    const Fr s = fp_from_mont(fr_load2(a.scalars, t));
+    uint32_t cnt = 0;
+    msm_digits_foreach<0>(a, t, s, [&](uint32_t k, uint32_t v) { keys[cnt] = k; vals[cnt] = v; ++cnt; });
+    return cnt;
+}
+
+// writes the entries of one scalar at [base, base + cnt)
+ZKB_HD void msm_digits_emit(const MsmDigitArgs& a, uint64_t base, const uint32_t* keys, const uint32_t* vals, uint32_t cnt) {
+    for (uint32_t j = 0; j < cnt; ++j) {
+        a.keys[base + j] = keys[j];
+        a.vals[base + j] = vals[j];
     }
 }
 

@@ -7,7 +7,7 @@
 namespace zkb {
 
 struct MsmWorkspace {
-    DevBuf keys[2], vals[2], sort_tmp, buckets, pk[2], pv[2], seg[2];
+    DevBuf keys[2], vals[2], sort_tmp, counter, buckets, pk[2], pv[2], seg[2];
     void* h_sums = nullptr;  // pinned staging for the per-set sums / finished results
     size_t h_sums_cap = 0;
 };
