@@ -259,3 +259,49 @@ def test_batch_invert(oracle):
     a[32] = 0
     a[99] = mont([1])[0]
     assert (emu.batch_invert(a) == oracle.fr_batch_invert(a)).all()
+
+
+# ---- property-based differential tests (hypothesis): device limb arithmetic vs Python integers, edge-biased inputs -----------------
+try:
+    from hypothesis import given, settings, strategies as st
+
+    def _elems(mod):
+        edge = [0, 1, 2, mod - 1, mod - 2, (1 << 253), (1 << 128) - 1, (1 << 128), (1 << 64) - 1, (1 << 32) - 1, mod >> 1]
+        return st.one_of(st.sampled_from(edge), st.integers(min_value=0, max_value=mod - 1))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.tuples(_elems(R.FR), _elems(R.FR)), min_size=1, max_size=8))
+    def test_fr_ops_property(pairs):
+        a = ints_to_limbs([x for x, _ in pairs])
+        b = ints_to_limbs([y for _, y in pairs])
+        rinv = pow(1 << 256, R.FR - 2, R.FR)
+        assert limbs_to_ints_(emu.vec_op("fr", "mul", a, b)) == [x * y * rinv % R.FR for x, y in pairs]
+        assert limbs_to_ints_(emu.vec_op("fr", "add", a, b)) == [(x + y) % R.FR for x, y in pairs]
+        assert limbs_to_ints_(emu.vec_op("fr", "sub", a, b)) == [(x - y) % R.FR for x, y in pairs]
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.tuples(_elems(R.FQ), _elems(R.FQ)), min_size=1, max_size=8))
+    def test_fq_ops_property(pairs):
+        a = ints_to_limbs([x for x, _ in pairs])
+        b = ints_to_limbs([y for _, y in pairs])
+        rinv = pow(1 << 256, R.FQ - 2, R.FQ)
+        assert limbs_to_ints_(emu.vec_op("fq", "mul", a, b)) == [x * y * rinv % R.FQ for x, y in pairs]
+        assert limbs_to_ints_(emu.vec_op("fq", "add", a, b)) == [(x + y) % R.FQ for x, y in pairs]
+        assert limbs_to_ints_(emu.vec_op("fq", "sub", a, b)) == [(x - y) % R.FQ for x, y in pairs]
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(min_value=1, max_value=9), st.integers(min_value=0, max_value=2**32 - 1))
+    def test_ntt_property_inverse_roundtrip(k, seed):
+        """NTT(omega) then NTT(omega^-1) returns n * a for random sizes / seeds (checked with Python integers)."""
+        n = 1 << k
+        a = random_field(n, seed)
+        w = R.omega_for(k)
+        f = emu.ntt(a, k, mont([w])[0])
+        b = emu.ntt(f, k, mont([pow(w, R.FR - 2, R.FR)])[0])
+        want = [R.to_mont(n * R.from_mont(limbs_to_int(x), R.FR) % R.FR, R.FR) for x in a]
+        assert limbs_to_ints_(b) == want
+
+    def limbs_to_ints_(a):
+        return [limbs_to_int(r) for r in np.asarray(a).reshape(-1, 4)]
+except ImportError:  # hypothesis is part of the image; keep the module importable without it
+    pass

@@ -23,6 +23,27 @@ __global__ void __launch_bounds__(128) fr_batch_invert_kernel(const BatchInvertA
     fr_batch_invert_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+// element-wise field op on the real PTX carry chains: out[i] = a[i] (op) b[i]; field 0 Fr / 1 Fq; op 0 mul, 1 add, 2 sub, 3 sqr,
+// 4 neg, 5 double, 6 from_mont(a).  A self-test hook (the CPU emulator runs the portable twins of the chains, not the PTX).
+template <class P>
+__device__ __forceinline__ Fp<P> field_op(int op, const Fp<P>& x, const Fp<P>& y) {
+    switch (op) {
+        case 0: return fp_mul(x, y);
+        case 1: return fp_add(x, y);
+        case 2: return fp_sub(x, y);
+        case 3: return fp_sqr(x);
+        case 4: return fp_neg(x);
+        case 5: return fp_dbl(x);
+        default: return fp_from_mont(x);
+    }
+}
+__global__ void __launch_bounds__(128) field_vec_op_kernel(int field, int op, const uint4* a, const uint4* b, uint4* out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (field == 0) field_op<FrParams>(op, Fr::load(a + 2 * i), Fr::load(b + 2 * i)).store(out + 2 * i);
+    else field_op<FqParams>(op, Fq::load(a + 2 * i), Fq::load(b + 2 * i)).store(out + 2 * i);
+}
+
 static inline unsigned nblk(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline uint64_t chunks(uint64_t n) { return (n + POLY_CHUNK - 1) / POLY_CHUNK; }
 
@@ -291,6 +312,27 @@ int zkb_poly_batch_invert(uint64_t poly) {
     fr_batch_invert_kernel<<<nblk((p->n + INV_CHUNK - 1) / INV_CHUNK, 128), 128, 0, ctx().stream>>>(a);
     count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (field < 0 || field > 1 || op < 0 || op > 6) { set_error("bad field / op"); return ZKB_ERR_ARG; }
+    if (n == 0) return ZKB_OK;
+    if (!a || !b || !out) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    PolyWs& w = poly_ws();
+    ZKB_TRY(w.tmp.reserve(3 * n * 32));
+    char* d = reinterpret_cast<char*>(w.tmp.p);
+    cudaStream_t s = ctx().stream;
+    ZKB_CUDA_TRY(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, s));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, s));
+    field_vec_op_kernel<<<nblk(n, 128), 128, 0, s>>>(field, op, reinterpret_cast<const uint4*>(d), reinterpret_cast<const uint4*>(d + n * 32),
+                                                     reinterpret_cast<uint4*>(d + 2 * n * 32), n);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    ZKB_CUDA_TRY(cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA_TRY(cudaStreamSynchronize(s));
     return ZKB_OK;
 }
 
