@@ -105,6 +105,11 @@ int zkb_g1_batch_normalize(const uint64_t* points_jac, size_t n, uint64_t* out_a
 int zkb_kzg_setup(uint32_t k, const uint64_t s[4], uint64_t* g_out, uint64_t* g_lagrange_out);
 int zkb_kzg_setup_resident(uint32_t k, const uint64_t s[4], uint64_t* handle_g, uint64_t* handle_g_lagrange);
 int zkb_srs_download(uint64_t handle, uint64_t* bases_out, size_t n);
+/* best_fft with G = G1 (halo2's FftGroup impl for curve points): out[i] = sum_j [omega^(i j)] P_j, affine in / affine out,
+ * log_n <= 26.  zkb_srs_g_to_lagrange is halo2_proofs::arithmetic::g_to_lagrange on a resident SRS: g_lagrange =
+ * (1/n) * inverse G1 FFT of g[..2^k] — for params read from a file that carries only the monomial basis. */
+int zkb_g1_ntt(const uint64_t* points_affine, uint64_t* out_affine, const uint64_t omega[4], uint32_t log_n);
+int zkb_srs_g_to_lagrange(uint64_t handle_g, uint32_t k, uint64_t* handle_g_lagrange);
 
 /* ---- NTT: halo2_proofs::arithmetic::best_fft and EvaluationDomain::{lagrange_to_coeff, coeff_to_extended,
  *      extended_to_coeff} ----------------------------------------------------------------------------------- */

@@ -198,6 +198,14 @@ def fr_batch_invert(a: np.ndarray) -> np.ndarray:
     return a
 
 
+def g1_fft_naive(points_aff: np.ndarray, omega: np.ndarray) -> np.ndarray:
+    """best_fft with G = G1 by the DFT definition (O(n^2) scalar multiplications)."""
+    p = np.ascontiguousarray(points_aff, dtype=np.uint64).reshape(-1, 8)
+    o = _new(p.shape[0], 8)
+    lib().zko_g1_fft_naive(_p(p), ctypes.c_size_t(p.shape[0]), _p(np.ascontiguousarray(omega, dtype=np.uint64)), _p(o))
+    return o
+
+
 def kzg_setup(k: int, s_mont: np.ndarray, threads: int = 0):
     """ParamsKZG::setup, G1 side: (g, g_lagrange), each (2^k, 8)."""
     g, gl = _new(1 << k, 8), _new(1 << k, 8)

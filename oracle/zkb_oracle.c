@@ -31,6 +31,7 @@
  *   arithmetic::eval_polynomial (Horner)                                               -> zko_fr_eval_polynomial
  *   arithmetic::kate_division(a, b): q_{n-2} = a_{n-1}, q_{i-1} = a_i + b q_i            -> zko_fr_kate_division
  *   ff::BatchInvert (zeros are skipped and stay zero)                                   -> zko_fr_batch_invert
+ *   best_fft with G = G1 (FftGroup for curve points), by the DFT definition             -> zko_g1_fft_naive
  */
 #include <math.h>
 #include <stdint.h>
@@ -631,6 +632,31 @@ EXPORT void zko_fr_batch_invert(u64 *a, size_t n) {
         fe *v = (fe *)(a + 4 * i);
         if (!fe_is_zero(v)) f_inv(&FR, v, v);
     }
+}
+
+
+/* best_fft::<Fr, G1> by the definition: out[i] = sum_j [omega^(i j)] P_j   (O(n^2) scalar multiplications; tiny n only) */
+EXPORT void zko_g1_fft_naive(const u64 *points_aff, size_t n, const u64 *omega_mont, u64 *out_aff) {
+    const g1a *P = (const g1a *)points_aff;
+    g1j *res = (g1j *)malloc((n ? n : 1) * sizeof(g1j));
+    fe wi = FR.r; /* omega^i */
+    for (size_t i = 0; i < n; ++i) {
+        g1j acc;
+        g1j_set_identity(&acc);
+        fe wij = FR.r; /* omega^(i j) */
+        for (size_t j = 0; j < n; ++j) {
+            fe sc;
+            f_from_mont(&FR, &sc, &wij);
+            g1j t;
+            g1_mul_canon(&t, &P[j], &sc);
+            g1j_add(&acc, &acc, &t);
+            f_mul(&FR, &wij, &wij, &wi);
+        }
+        res[i] = acc;
+        f_mul(&FR, &wi, &wi, CFE(omega_mont));
+    }
+    g1j_batch_normalize((g1a *)out_aff, res, n);
+    free(res);
 }
 
 /* ParamsKZG::setup, G1 side (halo2-axiom poly/kzg/commitment.rs; reference call sites voter_circuit.rs:60,

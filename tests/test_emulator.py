@@ -305,3 +305,24 @@ try:
         return [limbs_to_int(r) for r in np.asarray(a).reshape(-1, 4)]
 except ImportError:  # hypothesis is part of the image; keep the module importable without it
     pass
+
+
+@pytest.mark.parametrize("k", [0, 1, 3, 4])
+def test_g1_fft_matches_definition(oracle, k):
+    n = 1 << k
+    pts = oracle.g1_fixed_base_mul(random_field(n, 60 + k))
+    if n >= 8:
+        pts[3] = 0           # identity input
+        pts[5] = pts[4]      # repeated point
+    w = oracle.fr_omega(k)
+    assert (emu.g1_fft(pts, k, w) == oracle.g1_fft_naive(pts, w)).all()
+
+
+def test_g_to_lagrange_equals_direct_lagrange_srs(oracle):
+    """g_to_lagrange(g) = (1/n) iFFT_G1(g) must reproduce the g_lagrange that setup computes from s directly."""
+    k = 3
+    s = random_field(1, 88)[0]
+    g, gl = oracle.kzg_setup(k, s)
+    w_inv = oracle.fr_inv(oracle.fr_omega(k))
+    n_inv = oracle.fr_inv(mont([1 << k])[0])
+    assert (emu.g1_fft(g, k, w_inv, n_inv) == gl).all()

@@ -613,3 +613,29 @@ def test_device_field_ops_vs_python_integers(field, mod):
             from oracle import coracle
             coracle.build()
             assert (out == coracle.vec_op("fr" if field == 0 else "fq", {0: "mul", 1: "add", 2: "sub"}[op], a, b)).all()
+
+
+# ---- best_fft over G1 and g_to_lagrange ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [0, 1, 4, 5])
+def test_g1_fft_vs_definition(oracle, k):
+    n = 1 << k
+    pts = zkb.g1_fixed_base_mul(random_field(n, 160 + k))
+    if n >= 8:
+        pts[3] = 0
+        pts[5] = pts[4]
+    w = zkb.omega(k)
+    assert (zkb.best_fft_g1(pts, w, k) == oracle.g1_fft_naive(pts, w)).all()
+
+
+@pytest.mark.parametrize("k", [6, 12])
+def test_g_to_lagrange_equals_setup_lagrange(k):
+    """Two independent device paths to the Lagrange-basis SRS: the inverse G1 FFT of g (g_to_lagrange) and the direct
+    [l_i(s)]G of ParamsKZG::setup must agree point for point; commit_lagrange through either gives the same commitment."""
+    s = random_field(1, 900 + k)[0]
+    a = zkb.ParamsKZG.setup(k, s)
+    b = zkb.ParamsKZG.from_g(k, a.get_g())
+    assert (b.get_g_lagrange() == a.get_g_lagrange()).all()
+    ev = random_field(1 << k, 901 + k)
+    assert (a.commit_lagrange(ev) == b.commit_lagrange(ev)).all()
+    a.close()
+    b.close()

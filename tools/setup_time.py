@@ -20,3 +20,13 @@ for k in (16, 20, 22, 24):
     p.close()
     print({"k": k, "fixed_base_first_s": round(t1, 4), "fixed_base_s": round(t2, 4), "naive_s": tn and round(tn, 4), "kzg_setup_resident_s": round(ts, 4),
            "srs_table_build_s": round(tt, 4), "table_c": cb.value, "table_GiB": tb.value / 2**30}, flush=True)
+# g_to_lagrange (inverse G1 FFT) on a resident SRS
+for k in (12, 16, 18):
+    s = random_field(1, k)[0]
+    p = zkb.ParamsKZG.setup(k, s)
+    h = ctypes.c_uint64(0)
+    t = time.perf_counter(); rc = lib.zkb_srs_g_to_lagrange(p.handle_g, k, ctypes.byref(h)); tt = time.perf_counter() - t
+    assert rc == 0
+    lib.zkb_srs_release(h)
+    p.close()
+    print({"k": k, "g_to_lagrange_s": round(tt, 4)}, flush=True)

@@ -60,6 +60,8 @@ def load() -> ctypes.CDLL:
         "zkb_kzg_setup": [u32, u64p, u64p, u64p],
         "zkb_kzg_setup_resident": [u32, u64p, ctypes.POINTER(u64), ctypes.POINTER(u64)],
         "zkb_srs_download": [u64, u64p, sz],
+        "zkb_g1_ntt": [u64p, u64p, u64p, u32],
+        "zkb_srs_g_to_lagrange": [u64, u32, ctypes.POINTER(u64)],
         "zkb_ntt_fr": [u64p, u64p, u32],
         "zkb_ntt_fr_batch": [u64pp, sz, u64p, u32],
         "zkb_lagrange_to_coeff": [u64p, u32],

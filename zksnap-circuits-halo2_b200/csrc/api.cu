@@ -887,6 +887,48 @@ int zkb_kzg_setup_resident(uint32_t k, const uint64_t s[4], uint64_t* handle_g, 
     if (!handle_g && !handle_g_lagrange) { set_error("both handles are NULL"); return ZKB_ERR_ARG; }
     return kzg_setup_common(k, s, nullptr, nullptr, handle_g, handle_g_lagrange);
 }
+// best_fft::<Fr, G1>(a, omega, log_n): affine in, affine out (host buffers)
+int zkb_g1_ntt(const uint64_t* points_affine, uint64_t* out_affine, const uint64_t omega[4], uint32_t log_n) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(points_affine, "points_affine"));
+    ZKB_TRY(check_ptr(out_affine, "out_affine"));
+    ZKB_TRY(check_ptr(omega, "omega"));
+    if (log_n > 26) { set_error("log_n %u out of range [0, 26]", log_n); return ZKB_ERR_ARG; }
+    const size_t n = (size_t)1 << log_n;
+    HostIo& h = hostio();
+    Ctx& c = ctx();
+    ZKB_TRY(h.bases.reserve(n * 64));
+    ZKB_TRY(h.x.reserve(n * 64));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, points_affine, n * 64, cudaMemcpyHostToDevice, c.stream));
+    ZKB_TRY(g1_fft_dev(h.bases.as<uint4>(), h.x.as<uint4>(), log_n, fr_from_limbs64(omega), nullptr, c.stream));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.x.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
+    ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return ZKB_OK;
+}
+
+// halo2_proofs::arithmetic::g_to_lagrange(g, k): g_lagrange = (1/n) * iFFT_G1(g) — derives the Lagrange-basis SRS from the
+// monomial one when only g is known (an SRS file without g_lagrange); resident in, resident out.
+int zkb_srs_g_to_lagrange(uint64_t handle_g, uint32_t k, uint64_t* handle_g_lagrange) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(handle_g_lagrange, "handle_g_lagrange"));
+    Srs* g;
+    ZKB_TRY(find_srs(handle_g, &g));
+    if (k > 26 || g->n < ((size_t)1 << k)) { set_error("SRS holds %zu points, 2^%u needed", g->n, k); return ZKB_ERR_ARG; }
+    const size_t n = (size_t)1 << k;
+    Srs* gl = new Srs();
+    gl->n = n;
+    int rc = gl->bases.reserve(n * 64);
+    const Fr omega_inv = fr_inv_host(fr_omega_host(k)), n_inv = fr_pow2_inv_host(k);
+    if (rc == ZKB_OK) rc = g1_fft_dev(g->bases.as<uint4>(), gl->bases.as<uint4>(), k, omega_inv, &n_inv, ctx().stream);
+    if (rc == ZKB_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) { set_error("g_to_lagrange failed"); rc = ZKB_ERR_CUDA; }
+    if (rc != ZKB_OK) { cudaGetLastError(); gl->bases.release(); delete gl; return rc; }
+    *handle_g_lagrange = g_next_handle++;
+    srs_map()[*handle_g_lagrange] = gl;
+    return ZKB_OK;
+}
+
 int zkb_srs_download(uint64_t handle, uint64_t* bases_out, size_t n) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());

@@ -23,6 +23,22 @@ __global__ void __launch_bounds__(128) lagrange_scalars_kernel(const LagrangeSca
     lagrange_scalars_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+__global__ void __launch_bounds__(128) g1_bitrev_kernel(const G1BitrevArgs a) {
+    g1_bitrev_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) g1_fft_stage_kernel(const G1FftStageArgs a) {
+    g1_fft_stage_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) fr_pow_canon_kernel(const FrPowCanonArgs a) {
+    fr_pow_canon_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) g1_scale_kernel(const G1ScaleArgs a) {
+    g1_scale_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) g1_lift_kernel(const G1LiftArgs a) {
+    g1_lift_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 static inline unsigned nblocks(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 struct SetupWs {
@@ -138,5 +154,44 @@ int kzg_setup_dev(uint32_t k, const uint64_t s_mont[4], uint4* d_g, uint4* d_gl,
     }
     return ZKB_OK;
 }
+
+// best_fft over G1: d_aff_in n affine points -> d_aff_out n affine points, out[i] = sum_j [omega^(i j)] in[j], optionally
+// followed by the scalar `scale` (canonical-ised here) on every output — g_to_lagrange = (omega^-1, 1/n).
+int g1_fft_dev(const uint4* d_aff_in, uint4* d_aff_out, uint32_t log_n, const Fr& omega, const Fr* scale, cudaStream_t st) {
+    SetupWs& w = setup_ws();
+    const uint64_t n = 1ull << log_n;
+    ZKB_TRY(w.xyzz.reserve(n * 128));
+    ZKB_TRY(w.scalars.reserve((n / 2 ? n / 2 : 1) * 32));
+    uint4* a = w.xyzz.as<uint4>();
+    G1LiftArgs la{d_aff_in, a, n};
+    g1_lift_kernel<<<nblocks(n, 128), 128, 0, st>>>(la);
+    count_launch();
+    if (log_n >= 1) {
+        FrPowCanonArgs pa{};
+        pa.out = w.scalars.as<uint4>(); pa.n = n / 2;
+        fr_words(omega, pa.w);
+        fr_pow_canon_kernel<<<nblocks((n / 2 + SETUP_CHUNK - 1) / SETUP_CHUNK, 128), 128, 0, st>>>(pa);
+        count_launch();
+        G1BitrevArgs ba{a, log_n};
+        g1_bitrev_kernel<<<nblocks(n, 128), 128, 0, st>>>(ba);
+        count_launch();
+        for (uint32_t stage = 1; stage <= log_n; ++stage) {
+            G1FftStageArgs sa{a, w.scalars.as<uint4>(), log_n, stage};
+            g1_fft_stage_kernel<<<nblocks(n / 2, 128), 128, 0, st>>>(sa);
+            count_launch();
+        }
+    }
+    if (scale) {
+        G1ScaleArgs ga{};
+        ga.a = a; ga.n = n;
+        fr_words(fp_from_mont(*scale), ga.k);
+        g1_scale_kernel<<<nblocks(n, 128), 128, 0, st>>>(ga);
+        count_launch();
+    }
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return g1_batch_to_affine_dev(a, n, d_aff_out, false, st);
+}
+
+Fr fr_from_limbs_u64(const uint64_t* p) { return fr_from_u64x4(p); }
 
 }  // namespace zkb

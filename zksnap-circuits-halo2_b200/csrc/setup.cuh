@@ -178,3 +178,104 @@ ZKB_HD void lagrange_scalars_thread(const LagrangeScalarArgs& a, uint64_t t) {
 }
 
 }  // namespace zkb
+
+// ---- best_fft over G1 (halo2's FftGroup impl for curve points) — used by g_to_lagrange -------------------------------------------
+// Radix-2 decimation in time on XYZZ points, one butterfly per thread and one launch per stage: the work is the scalar
+// multiplication by the twiddle (~4300 Fq products per butterfly), so memory layout is irrelevant here.
+namespace zkb {
+
+// [k]P for a canonical 254-bit scalar k (8 limbs), double-and-add from the top bit
+ZKB_HD_NOINLINE XYZZ xyzz_mul_scalar(const XYZZ& p, const Fr& k) {
+    XYZZ r = XYZZ::identity();
+    if (p.is_identity()) return r;
+    for (int i = 253; i >= 0; --i) {
+        r = xyzz_double(r);
+        if ((k.l[i >> 5] >> (i & 31)) & 1) xyzz_add(r, p);
+    }
+    return r;
+}
+ZKB_HD XYZZ xyzz_neg(const XYZZ& p) {
+    XYZZ r = p;
+    if (!p.is_identity()) r.y = fp_neg(p.y);
+    return r;
+}
+
+// a[i] <-> a[bitreverse(i)] (thread i swaps when i < rev)
+struct G1BitrevArgs {
+    uint4* a;  // n XYZZ
+    uint32_t log_n;
+};
+ZKB_HD void g1_bitrev_thread(const G1BitrevArgs& p, uint64_t i) {
+    const uint64_t n = 1ull << p.log_n;
+    if (i >= n) return;
+    uint64_t r = 0;
+    for (uint32_t b = 0; b < p.log_n; ++b) r |= ((i >> b) & 1) << (p.log_n - 1 - b);
+    if (i < r) {
+        XYZZ x = XYZZ::load(p.a + 8 * i), y = XYZZ::load(p.a + 8 * r);
+        y.store(p.a + 8 * i);
+        x.store(p.a + 8 * r);
+    }
+}
+
+// stage s (m = 2^s): butterfly t = (block k, offset j < m/2):  u = a[k m + j], v = w^(j n / m) a[k m + j + m/2]
+struct G1FftStageArgs {
+    uint4* a;             // n XYZZ
+    const uint4* tw;      // omega^t as CANONICAL integers, t < n/2
+    uint32_t log_n, stage;
+};
+ZKB_HD void g1_fft_stage_thread(const G1FftStageArgs& p, uint64_t t) {
+    const uint64_t half_n = 1ull << (p.log_n - 1);
+    if (t >= half_n) return;
+    const uint32_t log_half_m = p.stage - 1;
+    const uint64_t j = t & ((1ull << log_half_m) - 1), k = t >> log_half_m;
+    const uint64_t i0 = (k << p.stage) + j, i1 = i0 + (1ull << log_half_m);
+    XYZZ u = XYZZ::load(p.a + 8 * i0), v = XYZZ::load(p.a + 8 * i1);
+    if (j) v = xyzz_mul_scalar(v, fr_load2(p.tw, j << (p.log_n - p.stage)));
+    XYZZ s = u;
+    xyzz_add(s, v);
+    xyzz_add(u, xyzz_neg(v));
+    s.store(p.a + 8 * i0);
+    u.store(p.a + 8 * i1);
+}
+
+// tw[t] = omega^t as canonical integers (chunks of SETUP_CHUNK per thread)
+struct FrPowCanonArgs {
+    uint4* out;
+    uint64_t n;
+    uint32_t w[8];
+};
+ZKB_HD void fr_pow_canon_thread(const FrPowCanonArgs& a, uint64_t t) {
+    const uint64_t lo = t * SETUP_CHUNK;
+    if (lo >= a.n) return;
+    const Fr w = fr_from_words(a.w);
+    Fr p = fp_pow_u64(w, lo);
+    for (uint64_t i = lo; i < lo + SETUP_CHUNK && i < a.n; ++i) {
+        fr_store2(a.out, i, fp_from_mont(p));
+        p = fp_mul(p, w);
+    }
+}
+
+// a[i] <- [k] a[i] (the 1/n of an inverse transform), affine or XYZZ input -> XYZZ in place
+struct G1ScaleArgs {
+    uint4* a;       // n XYZZ
+    uint64_t n;
+    uint32_t k[8];  // canonical scalar
+};
+ZKB_HD void g1_scale_thread(const G1ScaleArgs& p, uint64_t i) {
+    if (i >= p.n) return;
+    xyzz_mul_scalar(XYZZ::load(p.a + 8 * i), fr_from_words(p.k)).store(p.a + 8 * i);
+}
+
+// affine (64 B) -> XYZZ (128 B)
+struct G1LiftArgs {
+    const uint4* in;
+    uint4* out;
+    uint64_t n;
+};
+ZKB_HD void g1_lift_thread(const G1LiftArgs& p, uint64_t i) {
+    if (i >= p.n) return;
+    Affine a = affine_load(p.in + 4 * i);
+    XYZZ::from_affine(a).store(p.out + 8 * i);
+}
+
+}  // namespace zkb

@@ -99,6 +99,15 @@ def g1_fixed_base_mul_naive(scalars: np.ndarray) -> np.ndarray:
     return out
 
 
+def best_fft_g1(points_affine: np.ndarray, omega_: np.ndarray, log_n: int) -> np.ndarray:
+    """best_fft::<Fr, G1>(a, omega, log_n) on affine points (returns the transformed points, normalised)."""
+    p = np.ascontiguousarray(points_affine, dtype=np.uint64).reshape(-1, 8)
+    assert p.shape[0] == 1 << log_n, "assertion failed: a.len() == 1 << log_n"
+    out = np.zeros_like(p)
+    check(lib().zkb_g1_ntt(_p(p), _p(out), _p(np.ascontiguousarray(omega_, dtype=np.uint64).reshape(4)), log_n))
+    return out
+
+
 def batch_normalize(points_jac: np.ndarray) -> np.ndarray:
     """halo2curves Curve::batch_normalize(&[G1], &mut [G1Affine])."""
     p = np.ascontiguousarray(points_jac, dtype=np.uint64).reshape(-1, 12)
@@ -295,6 +304,15 @@ class ParamsKZG:
         self._h_g, self._h_gl = ctypes.c_uint64(0), ctypes.c_uint64(0)
         sv = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
         check(lib().zkb_kzg_setup_resident(k, _p(sv), ctypes.byref(self._h_g), ctypes.byref(self._h_gl)))
+        return self
+
+    @classmethod
+    def from_g(cls, k: int, g: np.ndarray) -> "ParamsKZG":
+        """Params from the monomial basis only (an SRS file without g_lagrange): g_lagrange = g_to_lagrange(g, k) on the
+        device (inverse G1 FFT and 1/n)."""
+        self = cls(k, g)
+        self._h_gl = ctypes.c_uint64(0)
+        check(lib().zkb_srs_g_to_lagrange(self._h_g, k, ctypes.byref(self._h_gl)))
         return self
 
     def get_g(self) -> np.ndarray:
