@@ -238,7 +238,8 @@ int zkb_prof_get(const char* name, double* total_ms, uint64_t* launches);
 int zkb_measure_imad_peak(double* wide_macs_per_s);
 /* Device self-test of the field arithmetic (halo2curves bn256::{Fr, Fq} mul / add / sub / square / neg / double / to_repr):
  * out[i] = a[i] (op) b[i] on the GPU's PTX carry chains.  field: 0 Fr, 1 Fq; op: 0 mul, 1 add, 2 sub, 3 sqr(a), 4 neg(a),
- * 5 double(a), 6 from-Montgomery(a).  Montgomery limbs in and out. */
+ * 5 double(a), 6 from-Montgomery(a); 7 / 8 / 9: the lazy mul / add / sub used inside the bucket accumulation and the NTT
+ * butterflies (inputs only < 2M, result reduced for comparison), 10: the raw lazy product (must be < 2M).  Montgomery limbs. */
 int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Kernels launched by this library since load (the bench's gpu_launches claim). */
 uint64_t zkb_launch_count(void);

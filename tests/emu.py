@@ -36,7 +36,7 @@ def vec_op(field, op, a, b):
     a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
     b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
     o = np.zeros_like(a)
-    lib().zkb_emu_vec_op(ctypes.c_int(0 if field == "fr" else 1), ctypes.c_int({"mul": 0, "add": 1, "sub": 2}[op]),
+    lib().zkb_emu_vec_op(ctypes.c_int(0 if field == "fr" else 1), ctypes.c_int({"mul": 0, "add": 1, "sub": 2, "mul_lazy": 4, "add_lazy": 5, "sub_lazy": 6, "is_zero_lazy": 7, "mul_lazy_raw": 8}[op]),
                          _p(a), _p(b), _p(o), ctypes.c_size_t(a.shape[0]))
     return o
 

@@ -326,3 +326,30 @@ def test_g_to_lagrange_equals_direct_lagrange_srs(oracle):
     w_inv = oracle.fr_inv(oracle.fr_omega(k))
     n_inv = oracle.fr_inv(mont([1 << k])[0])
     assert (emu.g1_fft(g, k, w_inv, n_inv) == gl).all()
+
+
+# ---- lazy field arithmetic (values only < 2M): the forms used inside the bucket accumulation and the NTT butterflies -------------
+try:
+    from hypothesis import given, settings, strategies as st
+
+    def _lazy_elems(mod):
+        edge = [0, 1, mod - 1, mod, mod + 1, 2 * mod - 1, 2 * mod - 2, (1 << 254), (1 << 254) - 1, mod >> 1, mod + (mod >> 1)]
+        return st.one_of(st.sampled_from([e for e in edge if e < 2 * mod]), st.integers(min_value=0, max_value=2 * mod - 1))
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.sampled_from(["fr", "fq"]), st.lists(st.tuples(st.integers(0, 10**9), st.integers(0, 10**9)), min_size=1, max_size=1),
+           st.data())
+    def test_lazy_field_ops_property(field, _unused, data):
+        mod = R.FR if field == "fr" else R.FQ
+        pairs = data.draw(st.lists(st.tuples(_lazy_elems(mod), _lazy_elems(mod)), min_size=1, max_size=8))
+        a = ints_to_limbs([x for x, _ in pairs])
+        b = ints_to_limbs([y for _, y in pairs])
+        rinv = pow(1 << 256, mod - 2, mod)
+        assert limbs_to_ints_(emu.vec_op(field, "mul_lazy", a, b)) == [x * y * rinv % mod for x, y in pairs]
+        assert limbs_to_ints_(emu.vec_op(field, "add_lazy", a, b)) == [(x + y) % mod for x, y in pairs]
+        assert limbs_to_ints_(emu.vec_op(field, "sub_lazy", a, b)) == [(x - y) % mod for x, y in pairs]
+        raw = limbs_to_ints_(emu.vec_op(field, "mul_lazy_raw", a, b))
+        assert all(v < 2 * mod and v % mod == x * y * rinv % mod for v, (x, y) in zip(raw, pairs))   # the lazy invariant
+        assert [int(v) for v in emu.vec_op(field, "is_zero_lazy", a, b)[:, 0]] == [1 if x % mod == 0 else 0 for x, _ in pairs]
+except ImportError:
+    pass

@@ -600,7 +600,8 @@ def test_device_field_ops_vs_python_integers(field, mod):
     p = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
     rinv = pow(1 << 256, mod - 2, mod)
     ops = {0: lambda x, y: x * y * rinv % mod, 1: lambda x, y: (x + y) % mod, 2: lambda x, y: (x - y) % mod,
-           3: lambda x, y: x * x * rinv % mod, 4: lambda x, y: (-x) % mod, 5: lambda x, y: 2 * x % mod, 6: lambda x, y: x * rinv % mod}
+           3: lambda x, y: x * x * rinv % mod, 4: lambda x, y: (-x) % mod, 5: lambda x, y: 2 * x % mod, 6: lambda x, y: x * rinv % mod,
+           7: lambda x, y: x * y * rinv % mod, 8: lambda x, y: (x + y) % mod, 9: lambda x, y: (x - y) % mod}   # lazy forms, reduced
     check_idx = list(range(m * m)) + list(range(m * m, n, 997))      # all edge pairs + a 1000-element sample in Python
     ai = [limbs_to_int(a[i]) for i in check_idx]
     bi = [limbs_to_int(b[i]) for i in check_idx]
@@ -609,10 +610,29 @@ def test_device_field_ops_vs_python_integers(field, mod):
         got = [limbs_to_int(out[i]) for i in check_idx]
         assert got == [f(x, y) for x, y in zip(ai, bi)], op
         # the whole 2^20 vector against the C oracle for the three binary ops
-        if op < 3:
+        if op < 3 or op in (7, 8, 9):
             from oracle import coracle
             coracle.build()
-            assert (out == coracle.vec_op("fr" if field == 0 else "fq", {0: "mul", 1: "add", 2: "sub"}[op], a, b)).all()
+            assert (out == coracle.vec_op("fr" if field == 0 else "fq", {0: "mul", 1: "add", 2: "sub", 7: "mul", 8: "add", 9: "sub"}[op], a, b)).all()
+    # lazy inputs proper (values in [M, 2M)): a + M and b + M are the same residues in lazy form; the raw lazy product stays < 2M
+    def plus_mod(v):
+        w = v.copy()
+        carry = np.zeros(v.shape[0], dtype=np.uint64)
+        for j in range(4):
+            t = w[:, j] + limbs[j]
+            c1 = (t < w[:, j]).astype(np.uint64)
+            t2 = t + carry
+            c2 = (t2 < t).astype(np.uint64)
+            w[:, j] = t2
+            carry = c1 + c2
+        return w
+    la, lb = plus_mod(a), plus_mod(b)
+    for op, f in ((7, ops[7]), (8, ops[8]), (9, ops[9])):
+        assert lib.zkb_field_vec_op(field, op, p(la), p(lb), p(out), n) == 0
+        assert [limbs_to_int(out[i]) for i in check_idx] == [f(x, y) for x, y in zip(ai, bi)], ("lazy inputs", op)
+    assert lib.zkb_field_vec_op(field, 10, p(la), p(lb), p(out), n) == 0
+    raw = [limbs_to_int(out[i]) for i in check_idx]
+    assert all(v < 2 * mod and v % mod == x * y * rinv % mod for v, x, y in zip(raw, ai, bi))
 
 
 # ---- best_fft over G1 and g_to_lagrange ----------------------------------------------------------------------------------------------

@@ -100,6 +100,40 @@ ZKB_HD void xyzz_add_mixed(XYZZ& acc, const Fq& x2, const Fq& y2) {
     acc.zzz = fp_mul(acc.zzz, ppp);
 }
 
+// The same mixed addition on a LAZY accumulator: coordinates are only < 2p (congruent mod p), every product skips its final
+// conditional subtraction (-17 of 184 instructions each) and add/sub work mod 2p; (x2, y2) is canonical.  A computed ZZ is
+// never congruent to 0 (it is a product of non-zero factors), so the all-zero identity test stays valid.  Callers make
+// the accumulator canonical (xyzz_canon) before it leaves the thread.
+ZKB_HD void xyzz_add_mixed_lazy(XYZZ& acc, const Fq& x2, const Fq& y2) {
+    if (acc.is_identity()) {
+        acc.x = x2; acc.y = y2; acc.zz = Fq::one(); acc.zzz = Fq::one();
+        return;
+    }
+    Fq u2 = fp_mul_lazy(x2, acc.zz);
+    Fq s2 = fp_mul_lazy(y2, acc.zzz);
+    Fq p = fp_sub_lazy(u2, acc.x);
+    Fq r = fp_sub_lazy(s2, acc.y);
+    if (fp_is_zero_lazy(p)) {
+        if (fp_is_zero_lazy(r)) acc = xyzz_double_affine(x2, y2);
+        else acc = XYZZ::identity();
+        return;
+    }
+    Fq pp = fp_mul_lazy(p, p);
+    Fq ppp = fp_mul_lazy(p, pp);
+    Fq q = fp_mul_lazy(acc.x, pp);
+    Fq x3 = fp_sub_lazy(fp_sub_lazy(fp_mul_lazy(r, r), ppp), fp_add_lazy(q, q));
+    Fq y3 = fp_sub_lazy(fp_mul_lazy(r, fp_sub_lazy(q, x3)), fp_mul_lazy(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = fp_mul_lazy(acc.zz, pp);
+    acc.zzz = fp_mul_lazy(acc.zzz, ppp);
+}
+ZKB_HD XYZZ xyzz_canon(const XYZZ& p) {
+    XYZZ r;
+    r.x = fp_canon(p.x); r.y = fp_canon(p.y); r.zz = fp_canon(p.zz); r.zzz = fp_canon(p.zzz);
+    return r;
+}
+
 // acc += b   [add-2008-s]
 ZKB_HD void xyzz_add(XYZZ& acc, const XYZZ& b) {
     if (b.is_identity()) return;

@@ -234,13 +234,19 @@ struct Fp {
     }
 };
 
-// r = (t >= M) ? t - M : t      (t < 2M)
-template <class P>
+// limb i of K * M (K = 1 or 2; 2M < 2^255 still fits eight limbs)
+template <class P, int K>
+__host__ __device__ constexpr uint32_t mod_k(int i) {
+    return K == 1 ? P::M(i) : ((P::M(i) << 1) | (i ? P::M(i - 1) >> 31 : 0u));
+}
+
+// r = (t >= K M) ? t - K M : t      (t < 2 K M)
+template <class P, int K = 1>
 ZKB_HD void reduce_once(uint32_t (&t)[8]) {
     uint32_t s[8], borrow;
 #if !defined(__CUDA_ARCH__)
     uint32_t mm[8];
-    for (int i = 0; i < 8; ++i) mm[i] = P::M(i);
+    for (int i = 0; i < 8; ++i) mm[i] = mod_k<P, K>(i);
     borrow = host_sub8(s, t, mm);
 #else
     asm("sub.cc.u32  %0, %9,  %17;\n\t"
@@ -254,15 +260,16 @@ ZKB_HD void reduce_once(uint32_t (&t)[8]) {
         "subc.u32    %8, 0, 0;\n\t"
         : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]),
           "=r"(borrow)
-        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(P::M(0)),
-          "r"(P::M(1)), "r"(P::M(2)), "r"(P::M(3)), "r"(P::M(4)), "r"(P::M(5)), "r"(P::M(6)), "r"(P::M(7)));
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(mod_k<P, K>(0)),
+          "r"(mod_k<P, K>(1)), "r"(mod_k<P, K>(2)), "r"(mod_k<P, K>(3)), "r"(mod_k<P, K>(4)), "r"(mod_k<P, K>(5)), "r"(mod_k<P, K>(6)), "r"(mod_k<P, K>(7)));
 #endif
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = borrow ? t[i] : s[i];
 }
 
-template <class P>
-ZKB_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+// K = 1: canonical in, canonical out.  K = 2 ("lazy"): inputs in [0, 2M), output in [0, 2M), congruent mod M.
+template <class P, int K>
+ZKB_HD Fp<P> fp_add_k(const Fp<P>& a, const Fp<P>& b) {
     uint32_t t[8];
 #if !defined(__CUDA_ARCH__)
     host_add8(t, a.l, b.l);
@@ -279,7 +286,7 @@ ZKB_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
         : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
           "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
 #endif
-    reduce_once<P>(t);
+    reduce_once<P, K>(t);
     Fp<P> r;
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.l[i] = t[i];
@@ -287,13 +294,18 @@ ZKB_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
 }
 
 template <class P>
-ZKB_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+ZKB_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) { return fp_add_k<P, 1>(a, b); }
+template <class P>
+ZKB_HD Fp<P> fp_add_lazy(const Fp<P>& a, const Fp<P>& b) { return fp_add_k<P, 2>(a, b); }
+
+template <class P, int K>
+ZKB_HD Fp<P> fp_sub_k(const Fp<P>& a, const Fp<P>& b) {
     uint32_t t[8], borrow;
     Fp<P> r;
 #if !defined(__CUDA_ARCH__)
     borrow = host_sub8(t, a.l, b.l);
     uint32_t mm[8];
-    for (int i = 0; i < 8; ++i) mm[i] = P::M(i) & borrow;
+    for (int i = 0; i < 8; ++i) mm[i] = mod_k<P, K>(i) & borrow;
     host_add8(r.l, t, mm);
 #else
     asm("sub.cc.u32  %0, %9,  %17;\n\t"
@@ -323,13 +335,18 @@ ZKB_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
         "@p addc.u32    %7, %7, %16;\n\t"
         "}\n\t"
         : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7])
-        : "r"(borrow), "r"(P::M(0)), "r"(P::M(1)), "r"(P::M(2)), "r"(P::M(3)), "r"(P::M(4)), "r"(P::M(5)), "r"(P::M(6)),
-          "r"(P::M(7)));
+        : "r"(borrow), "r"(mod_k<P, K>(0)), "r"(mod_k<P, K>(1)), "r"(mod_k<P, K>(2)), "r"(mod_k<P, K>(3)), "r"(mod_k<P, K>(4)), "r"(mod_k<P, K>(5)), "r"(mod_k<P, K>(6)),
+          "r"(mod_k<P, K>(7)));
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.l[i] = t[i];
 #endif
     return r;
 }
+
+template <class P>
+ZKB_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) { return fp_sub_k<P, 1>(a, b); }
+template <class P>
+ZKB_HD Fp<P> fp_sub_lazy(const Fp<P>& a, const Fp<P>& b) { return fp_sub_k<P, 2>(a, b); }
 
 template <class P>
 ZKB_HD Fp<P> fp_neg(const Fp<P>& a) {
@@ -341,9 +358,11 @@ ZKB_HD Fp<P> fp_dbl(const Fp<P>& a) {
     return fp_add<P>(a, a);
 }
 
-// Montgomery product a*b*2^-256 mod M, canonical.
-template <class P>
-ZKB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+// Montgomery product a*b*2^-256 mod M.  REDUCE: canonical result (inputs may be lazy, i.e. < 2M: 4M^2/2^256 + M < 2M since
+// 4M < 2^256).  !REDUCE ("lazy"): the final conditional subtraction is skipped and the result is only < 2M — valid input for
+// the next lazy product, lazy add/sub (mod 2M) and for the canonical routines' products.
+template <class P, bool REDUCE>
+ZKB_HD Fp<P> fp_mul_k(const Fp<P>& a, const Fp<P>& b) {
     uint32_t E[8], O[8];
     // row 0: plain 32x32->64 products into aligned pairs
 #pragma unroll
@@ -394,11 +413,36 @@ ZKB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
         : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(E[1]),
           "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]));
 #endif
-    reduce_once<P>(t);
+    if (REDUCE) reduce_once<P>(t);
     Fp<P> r;
 #pragma unroll
     for (int k = 0; k < 8; ++k) r.l[k] = t[k];
     return r;
+}
+
+template <class P>
+ZKB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul_k<P, true>(a, b); }
+template <class P>
+ZKB_HD Fp<P> fp_mul_lazy(const Fp<P>& a, const Fp<P>& b) { return fp_mul_k<P, false>(a, b); }
+// lazy value (< 2M) -> canonical
+template <class P>
+ZKB_HD Fp<P> fp_canon(const Fp<P>& a) {
+    uint32_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = a.l[i];
+    reduce_once<P>(t);
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    return r;
+}
+// a == 0 mod M for a lazy value (< 2M): a is 0 or M
+template <class P>
+ZKB_HD bool fp_is_zero_lazy(const Fp<P>& a) {
+    uint32_t z = 0, m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { z |= a.l[i]; m |= a.l[i] ^ P::M(i); }
+    return z == 0 || m == 0;
 }
 
 template <class P>

@@ -34,18 +34,25 @@ static Fq fq_from_u64(const uint64_t* p) {
     return r;
 }
 
-// field: 0 Fr, 1 Fq; op: 0 mul, 1 add, 2 sub
+// field: 0 Fr, 1 Fq; op: 0 mul, 1 add, 2 sub; lazy forms (inputs < 2M, result made canonical for comparison):
+// 4 canon(mul_lazy), 5 canon(add_lazy), 6 canon(sub_lazy), 7 is_zero_lazy(a) (0/1 in limb 0), 8 raw mul_lazy (must be < 2M)
+template <class F>
+static F emu_field_op(int op, const F& x, const F& y) {
+    switch (op) {
+        case 0: return fp_mul(x, y);
+        case 1: return fp_add(x, y);
+        case 2: return fp_sub(x, y);
+        case 4: return fp_canon(fp_mul_lazy(x, y));
+        case 5: return fp_canon(fp_add_lazy(x, y));
+        case 6: return fp_canon(fp_sub_lazy(x, y));
+        case 7: { F r = F::zero(); r.l[0] = fp_is_zero_lazy(x) ? 1u : 0u; return r; }
+        default: return fp_mul_lazy(x, y);
+    }
+}
 EMU_EXPORT void zkb_emu_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
     for (size_t i = 0; i < n; ++i) {
-        if (field == 0) {
-            Fr x = fr_from_u64(a + 4 * i), y = fr_from_u64(b + 4 * i);
-            Fr r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
-            f_to_u64(r, o + 4 * i);
-        } else {
-            Fq x = fq_from_u64(a + 4 * i), y = fq_from_u64(b + 4 * i);
-            Fq r = op == 0 ? fp_mul(x, y) : op == 1 ? fp_add(x, y) : fp_sub(x, y);
-            f_to_u64(r, o + 4 * i);
-        }
+        if (field == 0) f_to_u64(emu_field_op(op, fr_from_u64(a + 4 * i), fr_from_u64(b + 4 * i)), o + 4 * i);
+        else f_to_u64(emu_field_op(op, fq_from_u64(a + 4 * i), fq_from_u64(b + 4 * i)), o + 4 * i);
     }
 }
 

@@ -121,6 +121,8 @@ ZKB_HD void msm_accumulate_thread(const MsmAccArgs& a, uint64_t t) {
     uint32_t runs_done = 0;       // completed runs before the current one
     uint32_t head_key = MSM_INVALID_KEY, tail_key = MSM_INVALID_KEY;
     XYZZ tail = XYZZ::identity();
+    // level 0 keeps the accumulator lazy (coordinates < 2p, see xyzz_add_mixed_lazy); it becomes canonical when it leaves
+    auto out = [](const XYZZ& p) { return LEVEL0 ? xyzz_canon(p) : p; };
 
     for (uint64_t i = lo; i < hi; ++i) {
         uint32_t k = a.keys[i];
@@ -131,10 +133,10 @@ ZKB_HD void msm_accumulate_thread(const MsmAccArgs& a, uint64_t t) {
         if (k != cur) {
             if (cur != MSM_INVALID_KEY) {
                 if (runs_done == 0) {                      // first run of the chunk: may continue to the left
-                    if (a.last_level) msm_store_xyzz(a.buckets, cur, acc);
-                    else { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, acc); }
+                    if (a.last_level) msm_store_xyzz(a.buckets, cur, out(acc));
+                    else { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, out(acc)); }
                 } else {
-                    msm_store_xyzz(a.buckets, cur, acc);   // strictly interior run == complete bucket
+                    msm_store_xyzz(a.buckets, cur, out(acc));   // strictly interior run == complete bucket
                 }
                 ++runs_done;
             }
@@ -146,16 +148,16 @@ ZKB_HD void msm_accumulate_thread(const MsmAccArgs& a, uint64_t t) {
             Affine p = affine_load(a.bases + 4 * (uint64_t)(v & 0x7fffffffu));
             if (!p.is_identity()) {
                 if (v >> 31) p.y = fp_neg(p.y);
-                xyzz_add_mixed(acc, p.x, p.y);
+                xyzz_add_mixed_lazy(acc, p.x, p.y);
             }
         } else {
             xyzz_add(acc, msm_load_xyzz(a.pin, i));
         }
     }
     if (cur != MSM_INVALID_KEY) {
-        if (a.last_level) msm_store_xyzz(a.buckets, cur, acc);
-        else if (runs_done == 0) { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, acc); }
-        else { tail_key = cur; tail = acc; }
+        if (a.last_level) msm_store_xyzz(a.buckets, cur, out(acc));
+        else if (runs_done == 0) { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, out(acc)); }
+        else { tail_key = cur; tail = out(acc); }
     }
     if (!a.last_level) {
         a.pkeys_out[2 * t] = head_key;

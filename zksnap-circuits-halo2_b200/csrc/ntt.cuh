@@ -21,6 +21,9 @@
 // coeff_to_extended); last pass can scale by c[i mod 3] (1/N and the inverse coset shift of extended_to_coeff,
 // or the plain 1/N of lagrange_to_coeff).
 //
+// Arithmetic inside and between the passes is LAZY: values are only < 2r (congruent mod r), products skip their final
+// conditional subtraction and add/sub work mod 2r (field.cuh); the last pass stores canonical values.
+//
 // Every phase is a __host__ __device__ function of (cta, tid): the kernels in ntt.cu call them with
 // __syncthreads() in between, and the CPU emulator (hostemu.cu, test infrastructure) runs the very same code
 // thread by thread so index logic is checked without a GPU.
@@ -207,19 +210,19 @@ ZKB_HD void ntt_phase_load(const NttPassArgs& a, uint4* sm, uint32_t tid, uint32
             v = fr_load2(ntt_src_elem(a, col, gi), 0);
             if (a.in_scale_on) {
                 uint32_t m = (uint32_t)(gi % 3);
-                if (m) v = fp_mul(v, fr_from_words(a.in_scale[m]));
+                if (m) v = fp_mul_lazy(v, fr_from_words(a.in_scale[m]));
             }
         } else {
             v = Fr::zero();
         }
         if (a.pass > 0) {
             if (a.tw_pass) {
-                if (r && K) v = fp_mul(v, fr_load2(a.tw_pass, (K << LOGR) + r));
+                if (r && K) v = fp_mul_lazy(v, fr_load2(a.tw_pass, (K << LOGR) + r));
             } else {
                 uint64_t e = ((uint64_t)r * K) << tw_shift;  // < N
                 uint64_t eh = e >> a.tw_h, el = e & ((1ull << a.tw_h) - 1);
-                if (eh) v = fp_mul(v, fr_load2(a.tw_hi, eh));
-                if (el) v = fp_mul(v, fr_load2(a.tw_lo, el));
+                if (eh) v = fp_mul_lazy(v, fr_load2(a.tw_hi, eh));
+                if (el) v = fp_mul_lazy(v, fr_load2(a.tw_lo, el));
             }
         }
         sm_store(lo, hi, ntt_sm_index<LOGR>(a, r, c), v);
@@ -250,20 +253,20 @@ ZKB_HD void ntt_phase_round(const NttPassArgs& a, uint4* sm, uint32_t tid, uint3
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)j << log_sub), c));
             const Fr w1 = fr_load2(a.tw_r, R / 8), w2 = fr_load2(a.tw_r, R / 4), w3 = fr_load2(a.tw_r, 3 * (R / 8));
-            Fr a0 = fp_add(x[0], x[4]), a1 = fp_add(x[1], x[5]), a2 = fp_add(x[2], x[6]), a3 = fp_add(x[3], x[7]);
-            Fr b0 = fp_sub(x[0], x[4]);
-            Fr b1 = fp_mul(fp_sub(x[1], x[5]), w1);
-            Fr b2 = fp_mul(fp_sub(x[2], x[6]), w2);
-            Fr b3 = fp_mul(fp_sub(x[3], x[7]), w3);
-            Fr c0 = fp_add(a0, a2), c1 = fp_add(a1, a3), d0 = fp_sub(a0, a2), d1 = fp_mul(fp_sub(a1, a3), w2);
-            Fr e0 = fp_add(b0, b2), e1 = fp_add(b1, b3), f0 = fp_sub(b0, b2), f1 = fp_mul(fp_sub(b1, b3), w2);
-            x[0] = fp_add(c0, c1); x[4] = fp_sub(c0, c1);
-            x[2] = fp_add(d0, d1); x[6] = fp_sub(d0, d1);
-            x[1] = fp_add(e0, e1); x[5] = fp_sub(e0, e1);
-            x[3] = fp_add(f0, f1); x[7] = fp_sub(f0, f1);
+            Fr a0 = fp_add_lazy(x[0], x[4]), a1 = fp_add_lazy(x[1], x[5]), a2 = fp_add_lazy(x[2], x[6]), a3 = fp_add_lazy(x[3], x[7]);
+            Fr b0 = fp_sub_lazy(x[0], x[4]);
+            Fr b1 = fp_mul_lazy(fp_sub_lazy(x[1], x[5]), w1);
+            Fr b2 = fp_mul_lazy(fp_sub_lazy(x[2], x[6]), w2);
+            Fr b3 = fp_mul_lazy(fp_sub_lazy(x[3], x[7]), w3);
+            Fr c0 = fp_add_lazy(a0, a2), c1 = fp_add_lazy(a1, a3), d0 = fp_sub_lazy(a0, a2), d1 = fp_mul_lazy(fp_sub_lazy(a1, a3), w2);
+            Fr e0 = fp_add_lazy(b0, b2), e1 = fp_add_lazy(b1, b3), f0 = fp_sub_lazy(b0, b2), f1 = fp_mul_lazy(fp_sub_lazy(b1, b3), w2);
+            x[0] = fp_add_lazy(c0, c1); x[4] = fp_sub_lazy(c0, c1);
+            x[2] = fp_add_lazy(d0, d1); x[6] = fp_sub_lazy(d0, d1);
+            x[1] = fp_add_lazy(e0, e1); x[5] = fp_sub_lazy(e0, e1);
+            x[3] = fp_add_lazy(f0, f1); x[7] = fp_sub_lazy(f0, f1);
             if (log_sub > 0 && i > 0) {
 #pragma unroll
-                for (int p = 1; p < 8; ++p) x[p] = fp_mul(x[p], fr_load2(a.tw_r, (uint64_t)(i * p) << tw_step));
+                for (int p = 1; p < 8; ++p) x[p] = fp_mul_lazy(x[p], fr_load2(a.tw_r, (uint64_t)(i * p) << tw_step));
             }
 #pragma unroll
             for (int p = 0; p < 8; ++p) sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)p << log_sub), c), x[p]);
@@ -272,21 +275,21 @@ ZKB_HD void ntt_phase_round(const NttPassArgs& a, uint4* sm, uint32_t tid, uint3
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)j << log_sub), c));
             const Fr w4 = fr_load2(a.tw_r, R / 4);
-            Fr a0 = fp_add(x[0], x[2]), a1 = fp_add(x[1], x[3]), d0 = fp_sub(x[0], x[2]);
-            Fr d1 = fp_mul(fp_sub(x[1], x[3]), w4);
-            x[0] = fp_add(a0, a1); x[2] = fp_sub(a0, a1);
-            x[1] = fp_add(d0, d1); x[3] = fp_sub(d0, d1);
+            Fr a0 = fp_add_lazy(x[0], x[2]), a1 = fp_add_lazy(x[1], x[3]), d0 = fp_sub_lazy(x[0], x[2]);
+            Fr d1 = fp_mul_lazy(fp_sub_lazy(x[1], x[3]), w4);
+            x[0] = fp_add_lazy(a0, a1); x[2] = fp_sub_lazy(a0, a1);
+            x[1] = fp_add_lazy(d0, d1); x[3] = fp_sub_lazy(d0, d1);
             if (log_sub > 0 && i > 0) {
 #pragma unroll
-                for (int p = 1; p < 4; ++p) x[p] = fp_mul(x[p], fr_load2(a.tw_r, (uint64_t)(i * p) << tw_step));
+                for (int p = 1; p < 4; ++p) x[p] = fp_mul_lazy(x[p], fr_load2(a.tw_r, (uint64_t)(i * p) << tw_step));
             }
 #pragma unroll
             for (int p = 0; p < 4; ++p) sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0 + ((uint32_t)p << log_sub), c), x[p]);
         } else {
             Fr x0 = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0, c));
             Fr x1 = sm_load(lo, hi, ntt_sm_index<LOGR>(a, p0 + (1u << log_sub), c));
-            Fr y0 = fp_add(x0, x1), y1 = fp_sub(x0, x1);
-            if (log_sub > 0 && i > 0) y1 = fp_mul(y1, fr_load2(a.tw_r, (uint64_t)i << tw_step));
+            Fr y0 = fp_add_lazy(x0, x1), y1 = fp_sub_lazy(x0, x1);
+            if (log_sub > 0 && i > 0) y1 = fp_mul_lazy(y1, fr_load2(a.tw_r, (uint64_t)i << tw_step));
             sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0, c), y0);
             sm_store(lo, hi, ntt_sm_index<LOGR>(a, p0 + (1u << log_sub), c), y1);
         }
@@ -323,7 +326,9 @@ ZKB_HD void ntt_phase_store(const NttPassArgs& a, const uint4* sm, uint32_t tid,
         uint64_t go;
         if (!a.is_final) go = base + ((uint64_t)k << log_stride) + c;
         else go = K0 + c + ((uint64_t)k << log_q);
-        if (a.is_final && a.out_scale_on) v = fp_mul(v, fr_from_words(a.out_scale[go % 3]));
+        // values travel between the passes in lazy form (< 2r); the last pass makes them canonical — through the scaling
+        // product when there is one, else explicitly
+        if (a.is_final) v = a.out_scale_on ? fp_mul(v, fr_from_words(a.out_scale[go % 3])) : fp_canon(v);
         fr_store2(ntt_dst_elem(a, col, go), 0, v);
     }
 }

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) fr_batch_invert_kernel(const BatchInvertA
 }
 
 // element-wise field op on the real PTX carry chains: out[i] = a[i] (op) b[i]; field 0 Fr / 1 Fq; op 0 mul, 1 add, 2 sub, 3 sqr,
-// 4 neg, 5 double, 6 from_mont(a).  A self-test hook (the CPU emulator runs the portable twins of the chains, not the PTX).
+// 4 neg, 5 double, 6 from_mont(a), 7-9 canon(mul/add/sub lazy), 10 raw lazy product.  A self-test hook (the CPU emulator runs the portable twins of the chains, not the PTX).
 template <class P>
 __device__ __forceinline__ Fp<P> field_op(int op, const Fp<P>& x, const Fp<P>& y) {
     switch (op) {
@@ -34,7 +34,11 @@ __device__ __forceinline__ Fp<P> field_op(int op, const Fp<P>& x, const Fp<P>& y
         case 3: return fp_sqr(x);
         case 4: return fp_neg(x);
         case 5: return fp_dbl(x);
-        default: return fp_from_mont(x);
+        case 6: return fp_from_mont(x);
+        case 7: return fp_canon(fp_mul_lazy(x, y));   // lazy forms: inputs < 2M, result made canonical for comparison
+        case 8: return fp_canon(fp_add_lazy(x, y));
+        case 9: return fp_canon(fp_sub_lazy(x, y));
+        default: return fp_mul_lazy(x, y);            // raw lazy product (must be < 2M)
     }
 }
 __global__ void __launch_bounds__(128) field_vec_op_kernel(int field, int op, const uint4* a, const uint4* b, uint4* out, uint64_t n) {
@@ -318,7 +322,7 @@ int zkb_poly_batch_invert(uint64_t poly) {
 int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
-    if (field < 0 || field > 1 || op < 0 || op > 6) { set_error("bad field / op"); return ZKB_ERR_ARG; }
+    if (field < 0 || field > 1 || op < 0 || op > 10) { set_error("bad field / op"); return ZKB_ERR_ARG; }
     if (n == 0) return ZKB_OK;
     if (!a || !b || !out) { set_error("NULL argument"); return ZKB_ERR_ARG; }
     PolyWs& w = poly_ws();
