@@ -314,7 +314,7 @@ def main():
                 "achieved": achieved, "peak": peak.value / 1e9, "unit": "GMAC/s (32x32+64 wide MACs)",
                 "frac": achieved / (peak.value / 1e9) if peak.value else None,
                 "traffic": 28.87e9 if LOG_N_MSM == 24 else None,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch at 2^24 (profiles/r1b_msm_accumulate_ncu.txt)",
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch at 2^24 (profiles/r1c_msm_accumulate_ncu.txt)",
                 "peak_source": "measured in this run: unrolled independent mad.wide.u32 chains (zkb_measure_imad_peak)",
                 "ms_per_launch": acc_launch_ms, "window_bits": c_bits.value, "windows": n_win.value,
                 "share_of_step": acc_launch_ms / ms_per_step if ms_per_step else None,
