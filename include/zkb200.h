@@ -162,7 +162,10 @@ int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint3
  *   zkb_poly_extended_to_coeff   EvaluationDomain::extended_to_coeff, in place over 2^extended_k elements
  *   zkb_poly_eval                arithmetic::eval_polynomial(poly, x)
  *   zkb_poly_kate_division       arithmetic::kate_division(poly, b): new handle with len - 1 coefficients of poly / (X - b)
- *   zkb_poly_batch_invert        ff::BatchInvert over the values, in place (zeros stay zero) */
+ *   zkb_poly_batch_invert        ff::BatchInvert over the values, in place (zeros stay zero)
+ *   zkb_poly_mul                 poly[i] *= other[i]
+ *   zkb_poly_prefix_product      in place z[0] = 1, z[i] = prod_{j<i} v[j] — with batch_invert and mul, the grand products
+ *                                z of the permutation and lookup arguments (numerators * inverted denominators, scanned) */
 int zkb_poly_upload(const uint64_t* values, size_t n, uint64_t* handle);
 int zkb_poly_alloc(size_t n, uint64_t* handle); /* zero-filled */
 int zkb_poly_len(uint64_t handle, size_t* n);
@@ -176,6 +179,8 @@ int zkb_poly_extended_to_coeff(uint64_t poly, uint32_t k, uint32_t extended_k);
 int zkb_poly_eval(uint64_t poly, const uint64_t x[4], uint64_t out[4]);
 int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_handle);
 int zkb_poly_batch_invert(uint64_t poly);
+int zkb_poly_mul(uint64_t poly, uint64_t other);
+int zkb_poly_prefix_product(uint64_t poly);
 /* host-buffer forms of the three helpers (upload + op + download) */
 int zkb_fr_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
 int zkb_fr_kate_division(const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* out /* n - 1 */);

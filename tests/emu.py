@@ -168,3 +168,9 @@ def g1_fft(points_aff, log_n, omega, scale=None):
     lib().zkb_emu_g1_fft(_p(p), ctypes.c_uint32(log_n), _p(np.ascontiguousarray(omega, dtype=np.uint64)),
                          _p(np.ascontiguousarray(scale, dtype=np.uint64)) if scale is not None else None, _p(out))
     return out
+
+
+def prefix_product(a):
+    a = np.array(a, dtype=np.uint64, copy=True).reshape(-1, 4)
+    lib().zkb_emu_prefix_product(_p(a), ctypes.c_uint64(a.shape[0]))
+    return a

@@ -353,3 +353,15 @@ try:
         assert [int(v) for v in emu.vec_op(field, "is_zero_lazy", a, b)[:, 0]] == [1 if x % mod == 0 else 0 for x, _ in pairs]
 except ImportError:
     pass
+
+
+@pytest.mark.parametrize("n", [1, 2, 64, 65, 4097])
+def test_prefix_product_by_definition(n):
+    a = random_field(n, 800 + n)
+    vals = [R.from_mont(limbs_to_int(x), R.FR) for x in a]
+    want, acc = [], 1
+    for v in vals:
+        want.append(acc)
+        acc = acc * v % R.FR
+    got = [R.from_mont(limbs_to_int(x), R.FR) for x in emu.prefix_product(a)]
+    assert got == want

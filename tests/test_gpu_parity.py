@@ -659,3 +659,56 @@ def test_g_to_lagrange_equals_setup_lagrange(k):
     assert (a.commit_lagrange(ev) == b.commit_lagrange(ev)).all()
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("n", [1, 64, 65, 4097, 200000])
+def test_grand_product_pieces(oracle, n):
+    """The permutation / lookup grand product z[i] = prod_{j<i} num[j] / den[j] from its device pieces (batch_invert, mul,
+    prefix_product on resident handles) against the oracle's element-wise ops and a Python scan on a sample."""
+    num, den = random_field(n, 810 + n), random_field(n, 811 + n)
+    if n > 10:
+        den[3] = mont([1])[0]
+    d = zkb.Polynomial(den).batch_invert()
+    z = zkb.Polynomial(num).mul(d)
+    ratio = oracle.vec_op("fr", "mul", num, oracle.fr_batch_invert(den))
+    assert (z.to_host() == ratio).all()
+    got = z.prefix_product().to_host()
+    m = min(n, 300)
+    acc, want = 1, []
+    rinv_vals = [R.from_mont(limbs_to_int(x), R.FR) for x in ratio[:m]]
+    for v in rinv_vals:
+        want.append(acc)
+        acc = acc * v % R.FR
+    assert [R.from_mont(limbs_to_int(x), R.FR) for x in got[:m]] == want
+    # the whole vector: z[i+1] = z[i] * ratio[i]
+    assert (got[1:] == oracle.vec_op("fr", "mul", got[:-1], ratio[:-1])).all() and limbs_to_int(got[0]) == R.FR_R
+    d.free()
+    z.free()
+
+
+def test_shutdown_and_reinit_in_subprocess():
+    """zkb_shutdown releases everything (SRS tables, plans, pipeline, staging pool, polynomials); a second init works."""
+    import subprocess
+    import sys
+    code = (
+        "import importlib, sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from util import random_field\n"
+        "zkb = importlib.import_module('zksnap-circuits-halo2_b200')\n"
+        "outs = []\n"
+        "for rep in range(2):\n"
+        "    zkb.init(0)\n"
+        "    k = 12; s = random_field(1, 5)[0]\n"
+        "    p = zkb.ParamsKZG.setup(k, s)\n"
+        "    poly = random_field(1 << k, 6)\n"
+        "    c = p.commit(poly)\n"
+        "    d = zkb.EvaluationDomain(4, k)\n"
+        "    e = d.coeff_to_extended_batch([poly, poly])[1]\n"
+        "    h = zkb.Polynomial(poly); ev = h.eval(s)\n"
+        "    outs.append((c.tobytes(), e.tobytes(), ev.tobytes()))\n"
+        "    zkb.shutdown()\n"
+        "assert outs[0] == outs[1]\n"
+        "print('reinit ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "reinit ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

@@ -48,6 +48,16 @@ __global__ void __launch_bounds__(128) field_vec_op_kernel(int field, int op, co
     else field_op<FqParams>(op, Fq::load(a + 2 * i), Fq::load(b + 2 * i)).store(out + 2 * i);
 }
 
+__global__ void __launch_bounds__(128) poly_mul_kernel(const PolyMulArgs a) {
+    poly_mul_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) scan_chunk_product_kernel(const ScanChunkArgs a) {
+    scan_chunk_product_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) scan_expand_kernel(const ScanExpandArgs a) {
+    scan_expand_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 static inline unsigned nblk(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline uint64_t chunks(uint64_t n) { return (n + POLY_CHUNK - 1) / POLY_CHUNK; }
 
@@ -113,6 +123,27 @@ static int kate_q_dev(const uint4* d_a, uint64_t n, Fr b, uint4* d_q, uint4* d_t
     x.a = d_a; x.n = n; x.carry = carry; x.q = d_q;
     words_of(b, x.b);
     kate_expand_kernel<<<nblk(t, 128), 128, 0, s>>>(x);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+// z[i] = prod_{j < i} v[j]; d_z may alias d_v; d_tmp as for kate_q_dev
+static int prefix_product_dev(const uint4* d_v, uint64_t n, uint4* d_z, uint4* d_tmp, cudaStream_t s) {
+    const uint64_t t = chunks(n);
+    const uint4* carry = nullptr;
+    if (t > 1) {
+        uint4* P = d_tmp;          // chunk products
+        uint4* C = d_tmp + 2 * t;  // their exclusive prefix products
+        ScanChunkArgs c{d_v, n, P};
+        scan_chunk_product_kernel<<<nblk(t, 128), 128, 0, s>>>(c);
+        count_launch();
+        ZKB_CUDA_TRY(cudaGetLastError());
+        ZKB_TRY(prefix_product_dev(P, t, C, d_tmp + 4 * t, s));
+        carry = C;
+    }
+    ScanExpandArgs x{d_v, n, carry, d_z};
+    scan_expand_kernel<<<nblk(t, 128), 128, 0, s>>>(x);
     count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
     return ZKB_OK;
@@ -317,6 +348,32 @@ int zkb_poly_batch_invert(uint64_t poly) {
     count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
     return ZKB_OK;
+}
+
+int zkb_poly_mul(uint64_t poly, uint64_t other) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Poly *p, *q;
+    ZKB_TRY(find_poly(poly, &p));
+    ZKB_TRY(find_poly(other, &q));
+    if (p->n != q->n) { set_error("element-wise product of %zu and %zu elements", (size_t)p->n, (size_t)q->n); return ZKB_ERR_ARG; }
+    if (p->n == 0) return ZKB_OK;
+    PolyMulArgs a{p->buf.as<uint4>(), q->buf.as<uint4>(), p->n};
+    poly_mul_kernel<<<nblk(p->n, 128), 128, 0, ctx().stream>>>(a);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+int zkb_poly_prefix_product(uint64_t poly) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (p->n == 0) return ZKB_OK;
+    PolyWs& w = poly_ws();
+    ZKB_TRY(w.tmp.reserve(poly_tmp_bytes(p->n)));
+    return prefix_product_dev(p->buf.as<uint4>(), p->n, p->buf.as<uint4>(), w.tmp.as<uint4>(), ctx().stream);
 }
 
 int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {

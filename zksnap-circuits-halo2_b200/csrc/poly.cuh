@@ -78,4 +78,49 @@ ZKB_HD void fr_batch_invert_thread(const BatchInvertArgs& p, uint64_t t) {
     }
 }
 
+// ---- element-wise product and prefix products: the grand products of the permutation / lookup arguments -----------------------
+// z[0] = 1, z[i] = prod_{j < i} v[j]  (halo2's `iter::once(one).chain(values).scan(one, |s, v| { *s *= v; Some(*s) })`),
+// as a chunked scan: chunk products, the same scan one level up on the chunk products, then the in-chunk expansion.
+struct PolyMulArgs {
+    uint4* a;         // a[i] <- a[i] * b[i]
+    const uint4* b;
+    uint64_t n;
+};
+ZKB_HD void poly_mul_thread(const PolyMulArgs& p, uint64_t i) {
+    if (i >= p.n) return;
+    fr_store2(p.a, i, fp_mul(fr_load2(p.a, i), fr_load2(p.b, i)));
+}
+
+struct ScanChunkArgs {
+    const uint4* v;   // n values
+    uint64_t n;
+    uint4* prod;      // ceil(n / POLY_CHUNK) chunk products
+};
+ZKB_HD void scan_chunk_product_thread(const ScanChunkArgs& p, uint64_t t) {
+    const uint64_t lo = t * POLY_CHUNK;
+    if (lo >= p.n) return;
+    const uint64_t hi = lo + POLY_CHUNK < p.n ? lo + POLY_CHUNK : p.n;
+    Fr acc = fr_load2(p.v, lo);
+    for (uint64_t i = lo + 1; i < hi; ++i) acc = fp_mul_lazy(acc, fr_load2(p.v, i));
+    fr_store2(p.prod, t, fp_canon(acc));
+}
+
+struct ScanExpandArgs {
+    const uint4* v;       // n values
+    uint64_t n;
+    const uint4* carry;   // exclusive prefix products of the chunk products (carry[t] = product of all chunks before t), or NULL
+    uint4* z;             // n outputs: z[i] = prod_{j < i} v[j]
+};
+ZKB_HD void scan_expand_thread(const ScanExpandArgs& p, uint64_t t) {
+    const uint64_t lo = t * POLY_CHUNK;
+    if (lo >= p.n) return;
+    const uint64_t hi = lo + POLY_CHUNK < p.n ? lo + POLY_CHUNK : p.n;
+    Fr acc = p.carry ? fr_load2(p.carry, t) : Fr::one();
+    for (uint64_t i = lo; i < hi; ++i) {
+        const Fr v = fr_load2(p.v, i);  // read before the store: z may alias v
+        fr_store2(p.z, i, acc);
+        acc = fp_mul(acc, v);
+    }
+}
+
 }  // namespace zkb

@@ -199,6 +199,15 @@ class Polynomial:
         check(lib().zkb_poly_batch_invert(self._h))
         return self
 
+    def mul(self, other: "Polynomial") -> "Polynomial":
+        check(lib().zkb_poly_mul(self._h, other._h))
+        return self
+
+    def prefix_product(self) -> "Polynomial":
+        """z[0] = 1, z[i] = prod_{j<i} v[j] (the scan that builds the permutation / lookup grand products)"""
+        check(lib().zkb_poly_prefix_product(self._h))
+        return self
+
     def free(self) -> None:
         if self._h.value:
             lib().zkb_poly_free(self._h)
