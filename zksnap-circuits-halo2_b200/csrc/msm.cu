@@ -305,7 +305,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             a.bases = table ? table->rows : d_bases;
             a.pin = w.pv[pp ^ 1].as<uint4>();
             a.count = count;
-            a.chunk = last ? (uint32_t)count : (level == 0 ? chunk0 : g.chunk_up);
+            a.chunk = last ? (uint32_t)count : (level == 0 ? chunk0 : msm_chunk_up(count, g.chunk_up));
             a.invalid_key = g.invalid_key;
             a.last_level = last ? 1 : 0;
             a.buckets = bucket_acc;

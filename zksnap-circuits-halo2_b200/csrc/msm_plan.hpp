@@ -45,6 +45,11 @@ inline uint32_t msm_pick_window_table(uint64_t n) {
     return best_c;
 }
 
+// entries per thread at partial levels >= 1: long chunks while the level is large enough to be throughput bound (fewer
+// levels, less total work), short ones when only a few thousand partials remain and the dependent chain of full additions
+// (~4 us each) is what the MSM waits for — this tail was ~0.5 ms of a 1.3 ms 2^16-point MSM
+inline uint32_t msm_chunk_up(uint64_t count, uint32_t chunk_up_large) { return count >= (1u << 20) ? chunk_up_large : 8; }
+
 // n = points per column.  For a batch of ncols columns the bucket array holds ncols * bucket_sets sets.
 inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0, bool table = false,
                                 uint32_t ncols = 1) {
@@ -67,7 +72,7 @@ inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t ch
     while (ch > 16 && total / ch < 147456) ch >>= 1;
     g.chunk0 = chunk_override ? chunk_override : ch;
     g.chunk_up = 32;
-    g.last_max = 64;
+    g.last_max = 16;
     // bucket reduction: ~2^15 segment threads keep the SMs busy while the per-thread chain (2m adds + the (c-1)-bit offset
     // multiplication) stays short; measured on B200 (profiles/r1_tuning.txt): 2^19 buckets -> m = 16, 2^21 -> m = 64.
     uint32_t lb = g.c - 1;
