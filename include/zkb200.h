@@ -215,7 +215,8 @@ int zkb_dist_status(void* stream);
  * pipeline: column group i+1 is copied host->device while group i computes and group i-1 is copied device->host.
  * Caller memory that is page-locked (cudaMallocHost, or registered with zkb_host_register — e.g. the prover's
  * long-lived advice / extended-polynomial Vecs) is DMA'd directly; pageable memory is staged through internal
- * pinned buffers by a pool of host threads (ZKB_STAGE_THREADS, default min(8, cores/2)). */
+ * pinned buffers by two pools of host threads (stage-in on the calling thread, stage-out on a drainer thread so that the two host
+ * copies overlap; ZKB_STAGE_THREADS threads per pool, default clamp(cores/4, 2, 8)). */
 int zkb_host_register(void* ptr, size_t bytes);
 int zkb_host_unregister(void* ptr);
 /* depth: column groups in flight, 1 = serial, 0 = default (3); group_bytes: output bytes per group, 0 = automatic

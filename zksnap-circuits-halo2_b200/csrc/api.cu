@@ -3,6 +3,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <thread>
 
 #include "msm_host.hpp"
@@ -275,8 +276,8 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
     void start() {
         if (!workers.empty()) return;
         unsigned hw = std::thread::hardware_concurrency();
-        unsigned n = hw / 2;
-        if (n < 1) n = 1;
+        unsigned n = hw / 4;  // two pools (stage-in, stage-out) share the cores with the caller's own threads
+        if (n < 2) n = 2;
         if (n > 8) n = 8;
         const char* e = getenv("ZKB_STAGE_THREADS");
         if (e && atoi(e) > 0) n = (unsigned)atoi(e);
@@ -334,9 +335,84 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
         quit = false;
     }
 };
-static HostPool& host_pool() {
+static HostPool& host_pool() {  // stage-in copies (caller's thread + workers)
     static HostPool p;
     return p;
+}
+static HostPool& out_pool() {   // stage-out copies (drainer thread + workers)
+    static HostPool p;
+    return p;
+}
+
+// Copy-out of pageable results runs on its own thread: it waits for a group's device->host event and scatters the pinned
+// staging buffer into the caller's arrays while the calling thread is already staging the next group in — without it the two
+// host copies serialise and a pageable batch runs at half the speed of a page-locked one (tools/ntt_e2e_ab.py).
+struct Drainer {
+    struct Copy { void* dst; const void* src; size_t bytes; };
+    struct Job { cudaEvent_t ev; std::vector<Copy> copies; uint64_t id; };
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<Job> q;
+    uint64_t next_id = 1, done_id = 0;
+    bool quit = false, failed = false;
+    int device = 0;
+
+    void start(int dev) {
+        if (th.joinable()) return;
+        device = dev;
+        th = std::thread([this] { loop(); });
+    }
+    void loop() {
+        cudaSetDevice(device);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return quit || !q.empty(); });
+                if (q.empty()) return;
+                j = std::move(q.front());
+                q.pop_front();
+            }
+            bool ok = cudaEventSynchronize(j.ev) == cudaSuccess;
+            if (ok) for (auto& c : j.copies) out_pool().copy(c.dst, c.src, c.bytes);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!ok) failed = true;
+                done_id = j.id;
+            }
+            cv_done.notify_all();
+        }
+    }
+    uint64_t submit(cudaEvent_t ev, std::vector<Copy>&& copies) {
+        std::lock_guard<std::mutex> lk(mu);
+        const uint64_t id = next_id++;
+        q.push_back(Job{ev, std::move(copies), id});
+        cv_job.notify_one();
+        return id;
+    }
+    bool wait(uint64_t id) {  // false if any job failed
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return done_id >= id; });
+        bool ok = !failed;
+        return ok;
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv_job.notify_all();
+        th.join();
+        quit = false;
+        failed = false;
+    }
+    ~Drainer() { stop(); }
+};
+static Drainer& drainer() {
+    static Drainer d;
+    return d;
 }
 
 constexpr int PIPE_SLOTS = 3;
@@ -347,6 +423,7 @@ struct PipeSlot {
     bool busy = false;
     // deferred copy-out of a pageable group
     size_t c0 = 0, nc = 0;
+    uint64_t drain_ticket = 0;  // non-zero: the drainer thread copies this group out
 };
 struct Pipeline {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -383,7 +460,9 @@ static void pipeline_release() {
     cudaStreamDestroy(pl.s_h2d);
     cudaStreamDestroy(pl.s_d2h);
     pl.ready = false;
+    drainer().stop();
     host_pool().stop();
+    out_pool().stop();
 }
 
 // true when the driver can DMA straight from/to this host pointer (cudaMallocHost / cudaHostRegister memory)
@@ -431,15 +510,23 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
     // wait for a slot's device->host copies and hand pageable columns back to the caller
     auto finish = [&](PipeSlot& s) -> int {
         if (!s.busy) return ZKB_OK;
-        ZKB_CUDA_TRY(cudaEventSynchronize(s.ev_d2h));
-        for (size_t i = 0; i < s.nc; ++i)
-            if (!pinned_out[s.c0 + i]) host_pool().copy(out[s.c0 + i], (char*)s.h_out.p + i * col_out, col_out);
+        if (s.drain_ticket) {
+            const bool ok = drainer().wait(s.drain_ticket);
+            s.drain_ticket = 0;
+            if (!ok) { set_error("device->host copy failed in the drainer thread"); return ZKB_ERR_CUDA; }
+        } else {
+            ZKB_CUDA_TRY(cudaEventSynchronize(s.ev_d2h));
+        }
         s.busy = false;
         return ZKB_OK;
     };
     auto fail = [&](int rc) {
         cudaStreamSynchronize(pl.s_h2d); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(pl.s_d2h);
-        for (auto& s : pl.slot) s.busy = false;
+        for (auto& s : pl.slot) {
+            if (s.drain_ticket) drainer().wait(s.drain_ticket);
+            s.drain_ticket = 0;
+            s.busy = false;
+        }
         return rc;
     };
 
@@ -484,6 +571,13 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
         s.busy = true;
         s.c0 = c0;
         s.nc = nc;
+        if (any_pg_out) {  // hand the scatter of the pageable columns to the drainer thread
+            std::vector<Drainer::Copy> copies;
+            for (size_t i = 0; i < nc; ++i)
+                if (!pinned_out[c0 + i]) copies.push_back({(void*)out[c0 + i], (char*)s.h_out.p + i * col_out, col_out});
+            drainer().start(c.device);
+            s.drain_ticket = drainer().submit(s.ev_d2h, std::move(copies));
+        }
     }
     // drain in submission order
     for (size_t i = 0; i < (size_t)depth; ++i) {
