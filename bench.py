@@ -247,7 +247,9 @@ def main():
     # ---- warm-up + correctness of the measured configuration (rank-local known-dlog check on the first step) ------------
     for _ in range(args.warmup):
         step_dev()
-    from oracle import coracle  # checker only, outside the timed region
+    # checker leg (the oracle, like the cpu_baseline leg below; outside every timed region): the bases are [b_i]G, so the
+    # measured configuration must return [sum s_i b_i]G
+    from oracle import coracle
 
     ip = coracle.fr_inner_product(scal_np, dlog)
     want = coracle.g1_mul(coracle.g1_generator(), ip)

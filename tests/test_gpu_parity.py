@@ -395,7 +395,7 @@ def test_sharded_ntt_two_gpus():
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(root, "tools", "dist_ntt_check.py"), "--log-n", "11", "16", "20"]
+           "--master-port", "29517", os.path.join(root, "tests", "tools", "dist_ntt_check.py"), "--log-n", "11", "16", "20"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]

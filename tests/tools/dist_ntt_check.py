@@ -2,7 +2,7 @@
 """Sharded-NTT parity and timing under torchrun (one process per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29511 \
-        tools/dist_ntt_check.py --log-n 16 20 24 26 [--time]
+        tests/tools/dist_ntt_check.py --log-n 16 20 24 26 [--time]
 
 Parity: every rank builds the same seeded 2^log_n vector, passes its contiguous slice to ShardedNtt.best_fft_slice and
 compares the returned slice with (a) the single-GPU zkb.best_fft of the whole vector (log_n <= 24) and (b) the C oracle
@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small-size pass over every kernel family for compute-sanitizer (one tool per gpurun call):
-   compute-sanitizer --tool memcheck python tools/sanitize_small.py
+   compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py
 Every result is still compared with the oracle, so a sanitizer-clean run is also a parity run."""
 import importlib
 import os
@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import coracle  # noqa: E402

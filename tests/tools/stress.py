@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Randomised differential stress run on one GPU (not part of the test suite: minutes, not seconds).
-   python tools/stress.py [--seconds 120] [--seed 1]
+   python tests/tools/stress.py [--seconds 120] [--seed 1]
 Random sizes / ops / column counts / scalar distributions / tuning overrides, every result compared with the C oracle."""
 import argparse
 import ctypes
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import coracle  # noqa: E402

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measurement sweeps of SURVEY.md §8(d) on one B200 (device-resident kernels, CUDA events; host-ABI variants where stated).
 
-  python tools/sweep.py --out gpurun_out/sweep.jsonl [--sections msm ntt shapes replay] [--max-log-n 26]
+  python tests/tools/sweep.py --out gpurun_out/sweep.jsonl [--sections msm ntt shapes replay] [--max-log-n 26]
 
 Sections
   msm     BN254 G1 MSM, n = 2^16 .. 2^max, uniform scalars against a resident SRS (window table on); witness-like (W) and
@@ -26,7 +26,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from util import random_field  # noqa: E402
