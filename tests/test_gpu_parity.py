@@ -712,3 +712,41 @@ def test_shutdown_and_reinit_in_subprocess():
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "reinit ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_error_paths_return_codes_and_leave_the_library_usable(oracle):
+    """C functions return negative codes + a message (the shim panics on them, like the reference's unwrap/expect); a failed
+    call must not poison later ones."""
+    import ctypes
+    lib = zkb.lib()
+    u64p_ = ctypes.POINTER(ctypes.c_uint64)
+    out = np.zeros(12, dtype=np.uint64)
+    s = random_field(16, 1)
+    ERR_ARG, ERR_HANDLE = -1, -5
+    assert lib.zkb_msm_g1_srs(123456789, s.ctypes.data_as(u64p_), 16, out.ctypes.data_as(u64p_)) == ERR_HANDLE
+    assert b"unknown SRS handle" in lib.zkb_last_error()
+    assert lib.zkb_srs_release(987654321) == ERR_HANDLE
+    assert lib.zkb_poly_free(555) == ERR_HANDLE
+    assert lib.zkb_ntt_fr(s.ctypes.data_as(u64p_), zkb.omega(4).ctypes.data_as(u64p_), 0) == ERR_ARG        # log_n out of range
+    assert lib.zkb_ntt_fr(s.ctypes.data_as(u64p_), zkb.omega(4).ctypes.data_as(u64p_), 29) == ERR_ARG
+    assert lib.zkb_ntt_fr(None, zkb.omega(4).ctypes.data_as(u64p_), 4) == ERR_ARG                             # NULL data
+    assert lib.zkb_coeff_to_extended(s.ctypes.data_as(u64p_), s.ctypes.data_as(u64p_), 4, 3) == ERR_ARG       # extended_k < k
+    assert lib.zkb_msm_g1(s.ctypes.data_as(u64p_), None, 16, out.ctypes.data_as(u64p_)) == ERR_ARG
+    assert lib.zkb_msm_set_params(40, 0) == ERR_ARG
+    assert lib.zkb_kzg_setup(0, s.ctypes.data_as(u64p_), None, None) == ERR_ARG
+    _, g = _bases_known_dlog(16, 3)
+    params = zkb.ParamsKZG(4, g)
+    assert lib.zkb_msm_g1_srs(params.handle_g, random_field(17, 2).ctypes.data_as(u64p_), 17, out.ctypes.data_as(u64p_)) == ERR_ARG
+    assert lib.zkb_msm_g1_srs_range(params.handle_g, 10, s.ctypes.data_as(u64p_), 10, out.ctypes.data_as(u64p_)) == ERR_ARG
+    p = zkb.Polynomial(s)
+    h = ctypes.c_uint64(0)
+    assert lib.zkb_poly_coeff_to_extended(p._h, 5, 7, ctypes.byref(h)) == ERR_ARG                              # 16 elements != 2^5
+    assert lib.zkb_poly_lagrange_to_coeff(p._h, 3) == ERR_ARG
+    # everything still works afterwards
+    assert (params.commit(s) == oracle.best_multiexp(s, g)).all()
+    a = s.copy()
+    zkb.best_fft(a, zkb.omega(4), 4)
+    assert (a == oracle.best_fft(s, zkb.omega(4), 4)).all()
+    assert (p.lagrange_to_coeff(zkb.EvaluationDomain(4, 4)).to_host() == oracle.lagrange_to_coeff(s, 4)).all()
+    p.free()
+    params.close()
