@@ -163,6 +163,9 @@ int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint3
  *   zkb_poly_eval                arithmetic::eval_polynomial(poly, x)
  *   zkb_poly_kate_division       arithmetic::kate_division(poly, b): new handle with len - 1 coefficients of poly / (X - b)
  *   zkb_poly_batch_invert        ff::BatchInvert over the values, in place (zeros stay zero)
+ *   zkb_poly_scale_add           poly[i] = poly[i] * k + other[i] (other = 0: scale only) — the multiopen provers' Horner fold
+ *                                of their query polynomials with powers of a challenge
+ *   zkb_poly_add_const           coefficient 0 += c — f(X) - f(x) ahead of kate_division
  *   zkb_poly_mul                 poly[i] *= other[i]
  *   zkb_poly_prefix_product      in place z[0] = 1, z[i] = prod_{j<i} v[j] — with batch_invert and mul, the grand products
  *                                z of the permutation and lookup arguments (numerators * inverted denominators, scanned) */
@@ -180,6 +183,8 @@ int zkb_poly_eval(uint64_t poly, const uint64_t x[4], uint64_t out[4]);
 int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_handle);
 int zkb_poly_batch_invert(uint64_t poly);
 int zkb_poly_mul(uint64_t poly, uint64_t other);
+int zkb_poly_scale_add(uint64_t poly, const uint64_t k[4], uint64_t other);
+int zkb_poly_add_const(uint64_t poly, const uint64_t c[4]);
 int zkb_poly_prefix_product(uint64_t poly);
 /* host-buffer forms of the three helpers (upload + op + download) */
 int zkb_fr_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);

@@ -750,3 +750,40 @@ def test_error_paths_return_codes_and_leave_the_library_usable(oracle):
     assert (p.lagrange_to_coeff(zkb.EvaluationDomain(4, 4)).to_host() == oracle.lagrange_to_coeff(s, 4)).all()
     p.free()
     params.close()
+
+
+def test_gwc_witness_polynomial_on_resident_handles(oracle):
+    """A GWC-style opening witness built without leaving HBM: fold three polynomials with powers of v (scale_add), subtract the
+    folded evaluation (add_const), divide by (X - x) (kate_division), commit — against the same steps done with the oracle;
+    the quotient is exact, so q(X) (X - x) reproduces the folded polynomial."""
+    k = 11
+    n = 1 << k
+    s = random_field(1, 301)[0]
+    params = zkb.ParamsKZG.setup(k, s)
+    polys = [random_field(n, 310 + i) for i in range(3)]
+    v, x = random_field(2, 320)
+    acc = zkb.Polynomial(polys[0])
+    folded = polys[0]
+    for p in polys[1:]:
+        h = zkb.Polynomial(p)
+        acc.scale_add(v, h)
+        h.free()
+        folded = oracle.vec_op("fr", "add", oracle.vec_op("fr", "mul", folded, np.tile(v, (n, 1))), p)
+    assert (acc.to_host() == folded).all()
+    ev = acc.eval(x)
+    assert (ev == oracle.fr_eval_polynomial(folded, x)).all()
+    neg = oracle.vec_op("fr", "sub", np.zeros((1, 4), dtype=np.uint64), ev.reshape(1, 4))[0]
+    acc.add_const(neg)
+    shifted = folded.copy()
+    shifted[0] = oracle.vec_op("fr", "add", folded[:1], neg.reshape(1, 4))[0]
+    assert (acc.to_host() == shifted).all()
+    q = acc.kate_division(x)
+    qh = oracle.fr_kate_division(shifted, x)
+    assert (q.to_host() == qh).all()
+    assert (oracle.fr_eval_polynomial(shifted, x) == 0).all()          # x is a root, so the division is exact
+    assert (q.commit(params) == oracle.best_multiexp(qh, params.get_g()[: n - 1])).all()
+    acc.scale_add(v)                                                    # scale only
+    assert (acc.to_host() == oracle.vec_op("fr", "mul", shifted, np.tile(v, (n, 1)))).all()
+    for hnd in (acc, q):
+        hnd.free()
+    params.close()

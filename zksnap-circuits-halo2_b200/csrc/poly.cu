@@ -51,6 +51,12 @@ __global__ void __launch_bounds__(128) field_vec_op_kernel(int field, int op, co
 __global__ void __launch_bounds__(128) poly_mul_kernel(const PolyMulArgs a) {
     poly_mul_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
+__global__ void __launch_bounds__(128) poly_scale_add_kernel(const PolyScaleAddArgs a) {
+    poly_scale_add_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void poly_add_const_kernel(uint4* a, Fr c) {  // a[0] += c
+    fr_store2(a, 0, fp_add(fr_load2(a, 0), c));
+}
 __global__ void __launch_bounds__(128) scan_chunk_product_kernel(const ScanChunkArgs a) {
     scan_chunk_product_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -360,6 +366,42 @@ int zkb_poly_mul(uint64_t poly, uint64_t other) {
     if (p->n == 0) return ZKB_OK;
     PolyMulArgs a{p->buf.as<uint4>(), q->buf.as<uint4>(), p->n};
     poly_mul_kernel<<<nblk(p->n, 128), 128, 0, ctx().stream>>>(a);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+// poly <- poly * k + other   (other == 0: poly <- poly * k); lengths must agree
+int zkb_poly_scale_add(uint64_t poly, const uint64_t k[4], uint64_t other) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!k) { set_error("k is NULL"); return ZKB_ERR_ARG; }
+    Poly* p;
+    Poly* q = nullptr;
+    ZKB_TRY(find_poly(poly, &p));
+    if (other) {
+        ZKB_TRY(find_poly(other, &q));
+        if (q->n != p->n) { set_error("scale_add of %zu and %zu elements", (size_t)p->n, (size_t)q->n); return ZKB_ERR_ARG; }
+    }
+    if (p->n == 0) return ZKB_OK;
+    PolyScaleAddArgs a{};
+    a.acc = p->buf.as<uint4>(); a.other = q ? q->buf.as<uint4>() : nullptr; a.n = p->n;
+    words_of(fr_of(k), a.k);
+    poly_scale_add_kernel<<<nblk(p->n, 128), 128, 0, ctx().stream>>>(a);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+// coefficient 0 += c   (f(X) - f(x) before kate_division: pass c = -f(x))
+int zkb_poly_add_const(uint64_t poly, const uint64_t c[4]) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!c) { set_error("c is NULL"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (p->n == 0) { set_error("empty polynomial"); return ZKB_ERR_ARG; }
+    poly_add_const_kernel<<<1, 1, 0, ctx().stream>>>(p->buf.as<uint4>(), fr_of(c));
     count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
     return ZKB_OK;

@@ -91,6 +91,20 @@ ZKB_HD void poly_mul_thread(const PolyMulArgs& p, uint64_t i) {
     fr_store2(p.a, i, fp_mul(fr_load2(p.a, i), fr_load2(p.b, i)));
 }
 
+// acc[i] <- acc[i] * k + other[i]   (Horner over polynomials: the multiopen provers fold their queries with powers of v)
+struct PolyScaleAddArgs {
+    uint4* acc;
+    const uint4* other;   // may be NULL: acc[i] <- acc[i] * k
+    uint64_t n;
+    uint32_t k[8];
+};
+ZKB_HD void poly_scale_add_thread(const PolyScaleAddArgs& p, uint64_t i) {
+    if (i >= p.n) return;
+    Fr v = fp_mul_lazy(fr_load2(p.acc, i), fr_from_words(p.k));
+    if (p.other) v = fp_add_lazy(v, fr_load2(p.other, i));
+    fr_store2(p.acc, i, fp_canon(v));
+}
+
 struct ScanChunkArgs {
     const uint4* v;   // n values
     uint64_t n;

@@ -203,6 +203,15 @@ class Polynomial:
         check(lib().zkb_poly_mul(self._h, other._h))
         return self
 
+    def scale_add(self, k: np.ndarray, other: "Polynomial | None" = None) -> "Polynomial":
+        """self <- self * k + other (Horner fold of query polynomials in the multiopen provers)"""
+        check(lib().zkb_poly_scale_add(self._h, _p(np.ascontiguousarray(k, dtype=np.uint64).reshape(4)), other._h if other else 0))
+        return self
+
+    def add_const(self, c: np.ndarray) -> "Polynomial":
+        check(lib().zkb_poly_add_const(self._h, _p(np.ascontiguousarray(c, dtype=np.uint64).reshape(4))))
+        return self
+
     def prefix_product(self) -> "Polynomial":
         """z[0] = 1, z[i] = prod_{j<i} v[j] (the scan that builds the permutation / lookup grand products)"""
         check(lib().zkb_poly_prefix_product(self._h))
