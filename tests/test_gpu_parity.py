@@ -787,3 +787,32 @@ def test_gwc_witness_polynomial_on_resident_handles(oracle):
     for hnd in (acc, q):
         hnd.free()
     params.close()
+
+
+def test_srs_table_automatic_policy(oracle):
+    """Default policy: the SRS window table is built once a handle has served 96 commitments (ski-rental); before and after,
+    through single and batched commits, every result equals the oracle's."""
+    import ctypes
+    lib = zkb.lib()
+    lib.zkb_srs_set_precompute(2)
+    try:
+        k, n = 8, 256
+        _, g = _bases_known_dlog(n, 4242)
+        params = zkb.ParamsKZG(k, g)
+        bits, nbytes, commits = ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_uint64()
+        polys = [random_field(n, 4300 + i) for i in range(6)]
+        want = [oracle.best_multiexp(p, g) for p in polys]
+        for i in range(95):
+            assert (params.commit(polys[i % 6]) == want[i % 6]).all()
+        lib.zkb_srs_table_info(params.handle_g, ctypes.byref(bits), ctypes.byref(nbytes), ctypes.byref(commits))
+        assert bits.value == 0 and commits.value == 95
+        got = params.commit_batch(polys)          # 6 more commitments: crosses the threshold
+        for i in range(6):
+            assert (got[i] == want[i]).all()
+        lib.zkb_srs_table_info(params.handle_g, ctypes.byref(bits), ctypes.byref(nbytes), ctypes.byref(commits))
+        assert bits.value > 0 and nbytes.value > 0 and commits.value == 101
+        for i in range(6):
+            assert (params.commit(polys[i]) == want[i]).all()
+        params.close()
+    finally:
+        lib.zkb_srs_set_precompute(1)

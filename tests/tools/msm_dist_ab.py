@@ -10,6 +10,7 @@ from oracle import coracle
 coracle.build()
 zkb = importlib.import_module("zksnap-circuits-halo2_b200")
 zkb.init(0); lib = zkb.lib()
+lib.zkb_srs_set_precompute(1)
 dev = torch.device("cuda", 0); stream = torch.cuda.current_stream(); sptr = ctypes.c_void_p(stream.cuda_stream)
 out = np.zeros(12, dtype=np.uint64); outp = out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

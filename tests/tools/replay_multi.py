@@ -47,6 +47,7 @@ def main():
     zd = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
     zkb.init(local)
     lib = zkb.lib()
+    lib.zkb_srs_set_precompute(1)  # steady state: the SRS window table is built up front
     coracle.build()
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)

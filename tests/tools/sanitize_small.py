@@ -17,6 +17,7 @@ from util import random_field  # noqa: E402
 coracle.build()
 zkb = importlib.import_module("zksnap-circuits-halo2_b200")
 zkb.init(0)
+zkb.lib().zkb_srs_set_precompute(1)  # eager SRS window table: the table path is part of the pass
 for k in (3, 9, 10, 11, 13):          # 1-pass, 2-pass geometries
     a = random_field(1 << k, k)
     w = zkb.omega(k)

@@ -68,6 +68,7 @@ def main():
     zkb = importlib.import_module("zksnap-circuits-halo2_b200")
     zkb.init(0)
     lib = zkb.lib()
+    lib.zkb_srs_set_precompute(1)  # steady state: the SRS window table is built up front
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)

@@ -6,6 +6,7 @@ from util import random_field
 import torch
 zkb = importlib.import_module("zksnap-circuits-halo2_b200")
 zkb.init(0); lib = zkb.lib()
+lib.zkb_srs_set_precompute(1)  # slices need the SRS window table: build it up front
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 n = 1 << k
 bases = zkb.g1_fixed_base_mul(random_field(n, 2))

@@ -54,6 +54,7 @@ def load() -> ctypes.CDLL:
         "zkb_g1_sum": [u64p, sz, u64p],
         "zkb_srs_set_precompute": [ci],
         "zkb_srs_precompute": [u64, ctypes.POINTER(u32), ctypes.POINTER(u64)],
+        "zkb_srs_table_info": [u64, ctypes.POINTER(u32), ctypes.POINTER(u64), ctypes.POINTER(u64)],
         "zkb_g1_fixed_base_mul": [u64p, sz, u64p],
         "zkb_g1_fixed_base_mul_naive": [u64p, sz, u64p],
         "zkb_g1_batch_normalize": [u64p, sz, u64p],

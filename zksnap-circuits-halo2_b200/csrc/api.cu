@@ -127,21 +127,29 @@ struct Srs {
     DevBuf table;
     uint32_t table_c = 0, table_nwin = 0;
     bool table_failed = false;
+    uint64_t commits = 0;  // commitments served so far (automatic mode decides on this)
 };
-static int g_precompute = -1;  // -1: read ZKB_SRS_PRECOMPUTE on first use (default on), 0 off, 1 on
+// SRS window-table policy: 0 off, 1 eager (build on the first commit), 2 automatic (default): build once the handle has served
+// PRECOMPUTE_AFTER commitments.  A table-mode commit is ~18 % faster (2^22: 11.5 vs 14.0 ms) and the build costs ~100 commits'
+// worth of that gain at every size (2^22: 0.33 s), so a process that proves once should not pay for it while a long-running
+// prover should — buying after that many "rents" is the 2-competitive ski-rental rule.  zkb_srs_precompute forces the build.
+static int g_precompute = -1;  // -1: read ZKB_SRS_PRECOMPUTE on first use
+constexpr uint64_t PRECOMPUTE_AFTER = 96;
 
-static bool precompute_enabled() {
+static int precompute_mode() {
     if (g_precompute < 0) {
         const char* e = getenv("ZKB_SRS_PRECOMPUTE");
-        g_precompute = (e && e[0] == '0') ? 0 : 1;
+        g_precompute = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
     }
-    return g_precompute == 1;
+    return g_precompute;
 }
 
 // Build (once) the window table of an SRS; returns false when disabled or when it does not fit comfortably in HBM.
-static bool srs_table_ready(Srs* s, cudaStream_t stream) {
+static bool srs_table_ready(Srs* s, cudaStream_t stream, bool force = false) {
     if (s->table_c) return true;
-    if (!precompute_enabled() || s->table_failed || s->n < 64 || ctx().msm_c_override) return false;
+    const int mode = precompute_mode();
+    if (mode == 0 || s->table_failed || s->n < 64 || ctx().msm_c_override) return false;
+    if (!force && mode == 2 && s->commits < PRECOMPUTE_AFTER) return false;
     MsmGeometry g = msm_geometry(s->n, 0, 0, true);
     size_t bytes = (size_t)g.nwin * s->n * 64;
     size_t free_b = 0, total_b = 0;
@@ -591,6 +599,7 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
 // MSM of device scalars against srs[offset .. offset+n), through the window table when available
 static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t* out,
                        uint32_t ncols = 1, uint32_t phase = MSM_WHOLE) {
+    if (phase & MSM_LAST) srs->commits += ncols;
     if (srs_table_ready(srs, stream)) {
         MsmTable t{srs->table.as<uint4>() + 4 * offset, srs->n, srs->table_c, srs->table_nwin};
         return msm_run(d_scalars, nullptr, n, stream, out, &t, ncols, phase);
@@ -874,8 +883,9 @@ int zkb_msm_g1_srs_dev(uint64_t handle, size_t offset, const void* d_scalars, si
     return msm_srs_dev(s, offset, reinterpret_cast<const uint4*>(d_scalars), n, (cudaStream_t)stream, out_jac);
 }
 
-int zkb_srs_set_precompute(int on) {
-    g_precompute = on ? 1 : 0;
+int zkb_srs_set_precompute(int mode) {
+    if (mode < 0 || mode > 2) { set_error("mode must be 0 (off), 1 (eager) or 2 (automatic)"); return ZKB_ERR_ARG; }
+    g_precompute = mode;
     return ZKB_OK;
 }
 
@@ -884,9 +894,19 @@ int zkb_srs_precompute(uint64_t handle, uint32_t* window_bits, uint64_t* table_b
     ZKB_TRY(require_init());
     Srs* s;
     ZKB_TRY(find_srs(handle, &s));
-    bool ok = srs_table_ready(s, ctx().stream);
+    bool ok = srs_table_ready(s, ctx().stream, true);
     if (window_bits) *window_bits = ok ? s->table_c : 0;
     if (table_bytes) *table_bytes = ok ? (uint64_t)s->table_nwin * s->n * 64 : 0;
+    return ZKB_OK;
+}
+
+int zkb_srs_table_info(uint64_t handle, uint32_t* window_bits, uint64_t* table_bytes, uint64_t* commits) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    Srs* s;
+    ZKB_TRY(find_srs(handle, &s));
+    if (window_bits) *window_bits = s->table_c;
+    if (table_bytes) *table_bytes = s->table_c ? (uint64_t)s->table_nwin * s->n * 64 : 0;
+    if (commits) *commits = s->commits;
     return ZKB_OK;
 }
 
