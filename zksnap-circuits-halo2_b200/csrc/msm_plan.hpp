@@ -76,7 +76,10 @@ inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t ch
     // bucket reduction: ~2^15 segment threads keep the SMs busy while the per-thread chain (2m adds + the (c-1)-bit offset
     // multiplication) stays short; measured on B200 (profiles/r1_tuning.txt): 2^19 buckets -> m = 16, 2^21 -> m = 64.
     uint32_t lb = g.c - 1;
-    g.log_m = lb > 18 ? (lb - 15 > 7 ? 7 : lb - 15) : (lb > 6 ? 3 : 0);
+    uint32_t total_log = lb;  // log2 of all buckets of all sets (rounded down)
+    while ((1ull << (total_log + 1)) <= ((uint64_t)g.total_sets << lb)) ++total_log;
+    g.log_m = total_log > 18 ? (total_log - 15 > 7 ? 7 : total_log - 15) : (lb > 6 ? 3 : 0);
+    if (g.log_m > lb) g.log_m = lb;
     g.sum_group = 8;
     if (const char* e = getenv("ZKB_MSM_LOG_M")) { uint32_t v = (uint32_t)atoi(e); if (v <= lb) g.log_m = v; }
     if (const char* e = getenv("ZKB_MSM_SUM_GROUP")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2) g.sum_group = v; }
