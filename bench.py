@@ -318,6 +318,9 @@ def main():
                 "traffic": 28.87e9 if LOG_N_MSM == 24 else None,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch at 2^24 (profiles/r1c_msm_accumulate_ncu.txt)",
                 "peak_source": "measured in this run: unrolled independent mad.wide.u32 chains (zkb_measure_imad_peak)",
+                "hbm_view": ({"achieved": 28.87e9 / (acc_launch_ms * 1e-3) / 1e9, "unit": "GB/s",
+                              "note": "measured DRAM traffic of the same launch / its duration: the kernel is not HBM bound"}
+                             if (LOG_N_MSM == 24 and acc_launch_ms) else None),
                 "ms_per_launch": acc_launch_ms, "window_bits": c_bits.value, "windows": n_win.value,
                 "share_of_step": acc_launch_ms / ms_per_step if ms_per_step else None,
                 "other_ms": {"digits": dig_ms / max(acc_calls, 1), "sort": sort_ms / max(acc_calls, 1), "reduce": red_ms / max(acc_calls, 1)}}
