@@ -365,3 +365,44 @@ def test_prefix_product_by_definition(n):
         acc = acc * v % R.FR
     got = [R.from_mont(limbs_to_int(x), R.FR) for x in emu.prefix_product(a)]
     assert got == want
+
+
+# ---- tests/golden/widened_kats.json through the device code's per-thread functions --------------------------------------------
+import json  # noqa: E402
+import os  # noqa: E402
+
+WGOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "widened_kats.json")))
+
+
+def _h(x):
+    return int(x, 16)
+
+
+def _unmont(a):
+    return [R.from_mont(limbs_to_int(r), R.FR) for r in np.asarray(a).reshape(-1, 4)]
+
+
+def _aff(p):
+    return np.array(R.g1_affine_encode((_h(p[0]), _h(p[1])) if p else None), dtype=np.uint64)
+
+
+def test_widened_golden_vectors_through_device_code():
+    c = WGOLD["poly"]
+    a, b = mont([_h(x) for x in c["coeffs"]]), mont([_h(c["point"])])[0]
+    assert _unmont(emu.poly_eval(a, b)) == [_h(c["eval"])]
+    assert _unmont(emu.kate_division(a, b)) == [_h(x) for x in c["kate_quotient"]]
+    c = WGOLD["batch_invert"]
+    assert _unmont(emu.batch_invert(mont([_h(x) for x in c["in"]]))) == [_h(x) for x in c["out"]]
+    c = WGOLD["prefix_product"]
+    assert _unmont(emu.prefix_product(mont([_h(x) for x in c["in"]]))) == [_h(x) for x in c["out"]]
+    c = WGOLD["batch_normalize"]
+    jac = np.array([sum((R.fq_encode(_h(x)) for x in row), []) for row in c["jacobian"]], dtype=np.uint64)
+    assert (emu.batch_normalize(jac) == np.array([_aff(p) for p in c["affine"]])).all()
+    c = WGOLD["g1_fft"]
+    got = emu.g1_fft(np.array([_aff(p) for p in c["in"]]), c["k"], mont([_h(c["omega"])])[0])
+    assert (got == np.array([_aff(p) for p in c["out"]])).all()
+    c = WGOLD["kzg_setup"]
+    s = _h(c["s"])
+    n = 1 << c["k"]
+    rc, pw = emu.setup_scalars(0, n, mont([s])[0])
+    assert rc == 0 and (emu.fixed_base_window(pw) == np.array([_aff(p) for p in c["g"]])).all()

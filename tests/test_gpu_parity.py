@@ -816,3 +816,45 @@ def test_srs_table_automatic_policy(oracle):
         params.close()
     finally:
         lib.zkb_srs_set_precompute(1)
+
+
+# ---- tests/golden/widened_kats.json: the widened rows against vectors made from Python integers by the definitions ------------
+WGOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "widened_kats.json")))
+
+
+def _h(x):
+    return int(x, 16)
+
+
+def _aff_or_id(p):
+    return aff((_h(p[0]), _h(p[1])) if p else None)
+
+
+def test_widened_golden_kzg_setup():
+    c = WGOLD["kzg_setup"]
+    params = zkb.ParamsKZG.setup(c["k"], mont([_h(c["s"])])[0])
+    assert (params.get_g() == np.array([_aff_or_id(p) for p in c["g"]])).all()
+    assert (params.get_g_lagrange() == np.array([_aff_or_id(p) for p in c["g_lagrange"]])).all()
+    params.close()
+
+
+def test_widened_golden_poly_and_scans():
+    c = WGOLD["poly"]
+    a, b = mont([_h(x) for x in c["coeffs"]]), mont([_h(c["point"])])[0]
+    assert unmont(zkb.eval_polynomial(a, b)) == [_h(c["eval"])]
+    assert unmont(zkb.kate_division(a, b)) == [_h(x) for x in c["kate_quotient"]]
+    c = WGOLD["batch_invert"]
+    assert unmont(zkb.batch_invert(mont([_h(x) for x in c["in"]]))) == [_h(x) for x in c["out"]]
+    c = WGOLD["prefix_product"]
+    p = zkb.Polynomial(mont([_h(x) for x in c["in"]]))
+    assert unmont(p.prefix_product().to_host()) == [_h(x) for x in c["out"]]
+    p.free()
+
+
+def test_widened_golden_batch_normalize_and_g1_fft():
+    c = WGOLD["batch_normalize"]
+    jac = np.array([sum((R.fq_encode(_h(x)) for x in row), []) for row in c["jacobian"]], dtype=np.uint64)
+    assert (zkb.batch_normalize(jac) == np.array([_aff_or_id(p) for p in c["affine"]])).all()
+    c = WGOLD["g1_fft"]
+    got = zkb.best_fft_g1(np.array([_aff_or_id(p) for p in c["in"]]), mont([_h(c["omega"])])[0], c["k"])
+    assert (got == np.array([_aff_or_id(p) for p in c["out"]])).all()

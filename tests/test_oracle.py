@@ -252,3 +252,51 @@ def test_kate_division_and_batch_invert_oracle(oracle):
     v = [3, 0, R.FR - 1, 12345]
     inv = [R.from_mont(limbs_to_int(x), R.FR) for x in oracle.fr_batch_invert(ints_to_limbs([R.to_mont(x, R.FR) for x in v]))]
     assert inv == [pow(3, R.FR - 2, R.FR), 0, R.FR - 1, pow(12345, R.FR - 2, R.FR)]
+
+
+# ---- tests/golden/widened_kats.json: the widened rows against vectors made from Python integers by the definitions ------------
+WGOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "widened_kats.json")))
+
+
+def _h(x):
+    return int(x, 16)
+
+
+def _aff_or_id(p):
+    return aff_mont((_h(p[0]), _h(p[1])) if p else None)
+
+
+def test_widened_golden_kzg_setup(oracle):
+    c = WGOLD["kzg_setup"]
+    g, gl = oracle.kzg_setup(c["k"], fr_mont([_h(c["s"])])[0])
+    assert (g == np.array([_aff_or_id(p) for p in c["g"]])).all()
+    assert (gl == np.array([_aff_or_id(p) for p in c["g_lagrange"]])).all()
+
+
+def test_widened_golden_poly(oracle):
+    c = WGOLD["poly"]
+    a, b = fr_mont([_h(x) for x in c["coeffs"]]), fr_mont([_h(c["point"])])[0]
+    assert fr_unmont(oracle.fr_eval_polynomial(a, b)) == [_h(c["eval"])]
+    assert fr_unmont(oracle.fr_kate_division(a, b)) == [_h(x) for x in c["kate_quotient"]]
+
+
+def test_widened_golden_batch_invert_and_scan(oracle):
+    c = WGOLD["batch_invert"]
+    assert fr_unmont(oracle.fr_batch_invert(fr_mont([_h(x) for x in c["in"]]))) == [_h(x) for x in c["out"]]
+    # the scan has no oracle entry point of its own: z[i+1] = z[i] * v[i] with the oracle's product
+    c = WGOLD["prefix_product"]
+    v, z = fr_mont([_h(x) for x in c["in"]]), fr_mont([_h(x) for x in c["out"]])
+    assert _h(c["out"][0]) == 1 and (oracle.vec_op("fr", "mul", z[:-1], v[:-1]) == z[1:]).all()
+
+
+def test_widened_golden_batch_normalize(oracle):
+    c = WGOLD["batch_normalize"]
+    jac = np.array([sum((R.fq_encode(_h(x)) for x in row), []) for row in c["jacobian"]], dtype=np.uint64)
+    assert (oracle.g1_batch_normalize(jac) == np.array([_aff_or_id(p) for p in c["affine"]])).all()
+
+
+def test_widened_golden_g1_fft(oracle):
+    c = WGOLD["g1_fft"]
+    pts = np.array([_aff_or_id(p) for p in c["in"]])
+    got = oracle.g1_fft_naive(pts, fr_mont([_h(c["omega"])])[0])
+    assert (got == np.array([_aff_or_id(p) for p in c["out"]])).all()
