@@ -196,6 +196,83 @@ int zkb_fr_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4]
 int zkb_fr_kate_division(const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* out /* n - 1 */);
 int zkb_fr_batch_invert(uint64_t* values, size_t n);
 
+/* ---- quotient evaluation on resident cosets ---------------------------------------------------
+ * halo2-axiom `plonk/evaluation.rs` (un-vendored; reached from create_proof, /root/reference/aggregator/src/wrapper.rs:129-137)
+ * compiles the custom gates and the lookup input / table expressions into a `GraphEvaluator`: constants, rotations and a
+ * list of calculations over value sources, and `evaluate_h` runs it for every row of the extended domain,
+ *     values[idx] = graph.evaluate(&mut data, fixed, advice, instance, challenges, &beta, &gamma, &theta, &y, &values[idx],
+ *                                  idx, rot_scale, isize)
+ * with rotated rows read at (idx + rotation * rot_scale).rem_euclid(isize).  zkb_graph_evaluate is that loop over polynomials
+ * resident in HBM, so the extended cosets never cross PCIe.  The structures carry the GraphEvaluator's own fields:
+ *   zkb_value_source   ValueSource::{Constant(i), Intermediate(i), Fixed(col, rot), Advice(col, rot), Instance(col, rot),
+ *                      Challenge(i), Beta, Gamma, Theta, Y, PreviousValue}; `rotation` indexes `rotations`
+ *   zkb_calculation    Calculation::{Add, Sub, Mul, Square, Double, Negate, Store} writing intermediate `target`;
+ *                      Horner(start, parts, factor) is passed as one ZKB_CALC_STORE of `start` followed by one
+ *                      ZKB_CALC_MUL_ADD (target = a * b + c: a = Intermediate(target), b = factor, c = part) per part.
+ * The result of a row is the target of the last calculation (zero for an empty graph), written to `values`; PreviousValue
+ * reads values[idx] before it is overwritten.  Every polynomial must hold exactly the same power-of-two number of elements
+ * (the extended domain, isize).  An intermediate must be written before it is read.  Other terms of h(X) (permutation and
+ * lookup products, with l_0, l_last, l_active, the sigma cosets and the coset of X held as fixed columns) are graphs over
+ * the same sources. */
+#define ZKB_SRC_CONSTANT 0
+#define ZKB_SRC_INTERMEDIATE 1
+#define ZKB_SRC_FIXED 2
+#define ZKB_SRC_ADVICE 3
+#define ZKB_SRC_INSTANCE 4
+#define ZKB_SRC_CHALLENGE 5
+#define ZKB_SRC_BETA 6
+#define ZKB_SRC_GAMMA 7
+#define ZKB_SRC_THETA 8
+#define ZKB_SRC_Y 9
+#define ZKB_SRC_PREVIOUS 10
+typedef struct zkb_value_source {
+    uint32_t kind;     /* ZKB_SRC_* */
+    uint32_t index;    /* constant / intermediate / column / challenge index */
+    uint32_t rotation; /* index into `rotations` (columns only) */
+} zkb_value_source;
+#define ZKB_CALC_ADD 0
+#define ZKB_CALC_SUB 1
+#define ZKB_CALC_MUL 2
+#define ZKB_CALC_SQUARE 3
+#define ZKB_CALC_DOUBLE 4
+#define ZKB_CALC_NEGATE 5
+#define ZKB_CALC_STORE 6
+#define ZKB_CALC_MUL_ADD 7
+typedef struct zkb_calculation {
+    uint32_t op;     /* ZKB_CALC_* */
+    uint32_t target; /* intermediate written */
+    zkb_value_source a, b, c;
+} zkb_calculation;
+typedef struct zkb_graph {
+    const zkb_calculation* calculations;
+    size_t num_calculations;
+    uint32_t num_intermediates;
+    const uint64_t* constants; /* num_constants x 4, Montgomery Fr */
+    size_t num_constants;
+    const int32_t* rotations;
+    size_t num_rotations;
+} zkb_graph;
+typedef struct zkb_graph_inputs {
+    const uint64_t* fixed;    /* polynomial handles, one per column */
+    size_t num_fixed;
+    const uint64_t* advice;
+    size_t num_advice;
+    const uint64_t* instance;
+    size_t num_instance;
+    const uint64_t* challenges; /* num_challenges x 4 */
+    size_t num_challenges;
+    const uint64_t* beta; /* 4 u64 each; may be NULL when the graph does not use the source */
+    const uint64_t* gamma;
+    const uint64_t* theta;
+    const uint64_t* y;
+    int32_t rot_scale; /* 1 << (extended_k - k) */
+} zkb_graph_inputs;
+/* values: polynomial handle of isize elements, read as PreviousValue and overwritten with the row results. */
+int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, uint64_t values);
+/* What the last zkb_graph_evaluate was lowered to: device instructions, shared-memory slots after liveness analysis,
+ * distinct polynomials read, algorithmic bytes per row (32 x (polynomials read + previous value + result)). */
+int zkb_graph_last_info(uint32_t* instructions, uint32_t* slots, uint32_t* polys_read, uint32_t* bytes_per_row);
+
 /* ---- one NTT sharded over the GPUs of a box ("single NTT larger than one GPU's share") ------------
  * One process per GPU.  Rank r holds the contiguous slice [r N/G, (r+1) N/G) of the natural-order input and receives
  * the same slice of the natural-order output of best_fft(a, omega, log_n).  The exchange is not a separate collective:
@@ -245,7 +322,7 @@ int zkb_msm_set_params(uint32_t window_bits, uint32_t chunk);
 int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, uint32_t* chunk);
 
 /* Per-kernel CUDA-event timers.  Names: "msm_digits", "msm_sort", "msm_accumulate", "msm_reduce",
- * "ntt_pass", "dist_ntt_pass0", "dist_ntt_middle", "dist_ntt_final", "dist_barrier".  zkb_prof_get returns the summed milliseconds and launch count since the last reset. */
+ * "ntt_pass", "graph_evaluate", "dist_ntt_pass0", "dist_ntt_middle", "dist_ntt_final", "dist_barrier".  zkb_prof_get returns the summed milliseconds and launch count since the last reset. */
 int zkb_prof_enable(int on);
 int zkb_prof_reset(void);
 int zkb_prof_get(const char* name, double* total_ms, uint64_t* launches);

@@ -231,3 +231,40 @@ def best_multiexp(scalars_mont: np.ndarray, bases_aff: np.ndarray, threads: int 
     o = _new(12)
     lib().zko_best_multiexp(_p(s), _p(b), ctypes.c_size_t(s.shape[0]), ctypes.c_int(threads), _p(o))
     return o
+
+
+def graph_evaluate(calcs: np.ndarray, num_intermediates: int, constants: np.ndarray, rotations, fixed, advice, instance,
+                   challenges, beta, gamma, theta, y, rot_scale: int, values: np.ndarray, threads: int = 0) -> np.ndarray:
+    """GraphEvaluator::evaluate for every row (evaluate_h's loop).  calcs: (ncalc, 11) uint32 in zkb_calculation's layout;
+    columns: lists of (isize, 4) arrays; scalars (4,) or None; values: previous values, a new array is returned."""
+    calcs = np.ascontiguousarray(calcs, dtype=np.uint32).reshape(-1, 11)
+    consts = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+    rots = np.ascontiguousarray(rotations, dtype=np.int32)
+    out = np.array(values, dtype=np.uint64, copy=True).reshape(-1, 4)
+    keep = []
+
+    def table(cols):
+        arrs = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4) for c in cols]
+        keep.append(arrs)
+        for a in arrs:
+            assert a.shape[0] == out.shape[0]
+        t = (_u64p * max(len(arrs), 1))(*[_p(a) for a in arrs])
+        keep.append(t)
+        return t
+
+    def scalar(s):
+        if s is None:
+            return None
+        a = np.ascontiguousarray(s, dtype=np.uint64).reshape(-1)
+        keep.append(a)
+        return _p(a)
+
+    ch = np.ascontiguousarray(challenges if challenges is not None else np.zeros((0, 4)), dtype=np.uint64).reshape(-1, 4)
+    rc = lib().zko_graph_evaluate(calcs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.c_size_t(calcs.shape[0]),
+                                  ctypes.c_uint32(num_intermediates), _p(consts) if consts.size else None,
+                                  rots.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), table(fixed), table(advice), table(instance),
+                                  _p(ch) if ch.size else None, scalar(beta), scalar(gamma), scalar(theta), scalar(y),
+                                  ctypes.c_int32(rot_scale), _p(out), ctypes.c_size_t(out.shape[0]), ctypes.c_int(threads))
+    if rc != 0:
+        raise ValueError("malformed graph")
+    return out

@@ -32,6 +32,8 @@
  *   arithmetic::kate_division(a, b): q_{n-2} = a_{n-1}, q_{i-1} = a_i + b q_i            -> zko_fr_kate_division
  *   ff::BatchInvert (zeros are skipped and stay zero)                                   -> zko_fr_batch_invert
  *   best_fft with G = G1 (FftGroup for curve points), by the DFT definition             -> zko_g1_fft_naive
+ *   plonk::evaluation::GraphEvaluator::evaluate in evaluate_h's row loop (intermediates
+ *       numbered as upstream numbers them, rotated rows by rem_euclid)                  -> zko_graph_evaluate
  */
 #include <math.h>
 #include <stdint.h>
@@ -632,6 +634,89 @@ EXPORT void zko_fr_batch_invert(u64 *a, size_t n) {
         fe *v = (fe *)(a + 4 * i);
         if (!fe_is_zero(v)) f_inv(&FR, v, v);
     }
+}
+
+
+/* plonk::evaluation::GraphEvaluator::evaluate for every row idx of the extended domain, as evaluate_h calls it:
+ *   values[idx] = graph.evaluate(data, fixed, advice, instance, challenges, beta, gamma, theta, y, &values[idx], idx, rot_scale, isize)
+ * calcs: ncalc x 11 u32 = { op, target, a.kind, a.index, a.rotation, b.(3), c.(3) }  (the layout of zkb_calculation)
+ *   op: 0 Add 1 Sub 2 Mul 3 Square 4 Double 5 Negate 6 Store 7 one Horner step (target = a * b + c)
+ *   kind: 0 Constant 1 Intermediate 2 Fixed 3 Advice 4 Instance 5 Challenge 6 Beta 7 Gamma 8 Theta 9 Y 10 PreviousValue
+ * Every intermediate starts at zero (upstream's EvaluationData::intermediates), one array per row; the row's result is the
+ * target of the last calculation, or zero for an empty graph.  Returns -1 on a malformed graph. */
+typedef struct {
+    const uint32_t *calcs; size_t ncalc; uint32_t nint;
+    const fe *constants; const int32_t *rotations;
+    const fe *const *fixed; const fe *const *advice; const fe *const *instance;
+    const fe *challenges; const fe *beta, *gamma, *theta, *y;
+    int64_t rot_scale; fe *values; int64_t isize; int bad;
+} graph_ctx;
+static const fe *graph_get(const graph_ctx *g, const uint32_t *src, const fe *inter, const fe *prev, int64_t idx) {
+    const uint32_t kind = src[0], index = src[1];
+    int64_t row = 0;
+    if (kind >= 2 && kind <= 4) {   /* get_rotation_idx: (idx + rot * rot_scale).rem_euclid(isize) */
+        row = (idx + (int64_t)g->rotations[src[2]] * g->rot_scale) % g->isize;
+        if (row < 0) row += g->isize;
+    }
+    switch (kind) {
+        case 0: return &g->constants[index];
+        case 1: return &inter[index];
+        case 2: return &g->fixed[index][row];
+        case 3: return &g->advice[index][row];
+        case 4: return &g->instance[index][row];
+        case 5: return &g->challenges[index];
+        case 6: return g->beta;
+        case 7: return g->gamma;
+        case 8: return g->theta;
+        case 9: return g->y;
+        case 10: return prev;
+        default: return NULL;
+    }
+}
+static void graph_range(size_t lo, size_t hi, void *p) {
+    graph_ctx *g = (graph_ctx *)p;
+    fe *inter = (fe *)calloc(g->nint ? g->nint : 1, sizeof(fe));
+    for (size_t idx = lo; idx < hi; ++idx) {
+        memset(inter, 0, (g->nint ? g->nint : 1) * sizeof(fe));
+        const fe prev = g->values[idx];
+        for (size_t i = 0; i < g->ncalc; ++i) {
+            const uint32_t *c = g->calcs + 11 * i;
+            const fe *a = graph_get(g, c + 2, inter, &prev, (int64_t)idx);
+            const fe *b = graph_get(g, c + 5, inter, &prev, (int64_t)idx);
+            const fe *d = graph_get(g, c + 8, inter, &prev, (int64_t)idx);
+            fe r;
+            switch (c[0]) {
+                case 0: f_add(&FR, &r, a, b); break;
+                case 1: f_sub(&FR, &r, a, b); break;
+                case 2: f_mul(&FR, &r, a, b); break;
+                case 3: f_sqr(&FR, &r, a); break;
+                case 4: f_dbl(&FR, &r, a); break;
+                case 5: f_neg(&FR, &r, a); break;
+                case 6: r = *a; break;
+                case 7: f_mul(&FR, &r, a, b); f_add(&FR, &r, &r, d); break;
+                default: g->bad = 1; r = *a; break;
+            }
+            inter[c[1]] = r;
+        }
+        if (g->ncalc) g->values[idx] = inter[g->calcs[11 * (g->ncalc - 1) + 1]];
+        else memset(&g->values[idx], 0, sizeof(fe));
+    }
+    free(inter);
+}
+EXPORT int zko_graph_evaluate(const uint32_t *calcs, size_t ncalc, uint32_t num_intermediates, const u64 *constants,
+                              const int32_t *rotations, const u64 *const *fixed, const u64 *const *advice,
+                              const u64 *const *instance, const u64 *challenges, const u64 *beta, const u64 *gamma,
+                              const u64 *theta, const u64 *y, int32_t rot_scale, u64 *values, size_t isize, int threads) {
+    for (size_t i = 0; i < ncalc; ++i) {
+        if (calcs[11 * i] > 7 || calcs[11 * i + 1] >= num_intermediates) return -1;
+        for (int k = 0; k < 3; ++k)
+            if (calcs[11 * i + 2 + 3 * k] > 10) return -1;
+    }
+    graph_ctx g = { calcs, ncalc, num_intermediates, (const fe *)constants, rotations, (const fe *const *)fixed,
+                    (const fe *const *)advice, (const fe *const *)instance, (const fe *)challenges, (const fe *)beta,
+                    (const fe *)gamma, (const fe *)theta, (const fe *)y, rot_scale, (fe *)values, (int64_t)isize, 0 };
+    parallel_for(isize, resolve_threads(threads), graph_range, &g);
+    return g.bad ? -1 : 0;
 }
 
 

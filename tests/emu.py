@@ -174,3 +174,17 @@ def prefix_product(a):
     a = np.array(a, dtype=np.uint64, copy=True).reshape(-1, 4)
     lib().zkb_emu_prefix_product(_p(a), ctypes.c_uint64(a.shape[0]))
     return a
+
+
+def graph_evaluate(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, rot_scale, values, cta_threads=0):
+    """graph: evaluation.GraphEvaluator; columns: lists of (isize, 4) host arrays (passed as addresses where the product takes
+    handles).  Returns (new values, info = [instructions, slots, polys])."""
+    keep = [[np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4) for c in cols] for cols in (fixed, advice, instance)]
+    out = np.array(values, dtype=np.uint64, copy=True).reshape(-1, 4)
+    g, kg = graph.c_graph()
+    inp, ki = graph.c_inputs(*[[a.ctypes.data for a in cols] for cols in keep], challenges, beta, gamma, theta, y, rot_scale)
+    info = (ctypes.c_uint32 * 3)()
+    rc = lib().zkb_emu_graph_evaluate(ctypes.byref(g), ctypes.byref(inp), _p(out), ctypes.c_uint64(out.shape[0]),
+                                      ctypes.c_uint32(cta_threads), info)
+    del kg, ki
+    return rc, out, list(info)

@@ -1,0 +1,152 @@
+"""Quotient-evaluation test cases: halo2 `Expression`s evaluated BY THE DEFINITION with Python integers, and builders for the
+graphs the three implementations (oracle, emulator, CUDA) are checked with.
+
+`eval_expr` is the meaning of an expression at a row of the extended domain (a column query reads the row
+(idx + rotation * rot_scale) mod isize); `custom_gates_value` is what halo2-axiom's evaluate_h computes for the custom gates,
+value = previous; for each gate polynomial: value = value * y + gate(row).  Neither knows anything about GraphEvaluator."""
+import importlib
+import random
+
+import numpy as np
+
+from oracle import pyref as R
+from util import ints_to_limbs, limbs_to_int
+
+ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
+P = R.FR
+
+
+def eval_expr(e, cols, challenges, idx, rot_scale, isize):
+    t = e[0]
+    if t == "const":
+        return e[1] % P
+    if t in ("fixed", "advice", "instance"):
+        return cols[t][e[1]][(idx + e[2] * rot_scale) % isize]
+    if t == "challenge":
+        return challenges[e[1]]
+    if t == "neg":
+        return -eval_expr(e[1], cols, challenges, idx, rot_scale, isize) % P
+    if t == "sum":
+        return (eval_expr(e[1], cols, challenges, idx, rot_scale, isize) + eval_expr(e[2], cols, challenges, idx, rot_scale, isize)) % P
+    if t == "prod":
+        return eval_expr(e[1], cols, challenges, idx, rot_scale, isize) * eval_expr(e[2], cols, challenges, idx, rot_scale, isize) % P
+    if t == "scaled":
+        return eval_expr(e[1], cols, challenges, idx, rot_scale, isize) * e[2] % P
+    raise ValueError(t)
+
+
+def custom_gates_value(gates, cols, challenges, y, prev, idx, rot_scale, isize):
+    v = prev
+    for g in gates:
+        v = (v * y + eval_expr(g, cols, challenges, idx, rot_scale, isize)) % P
+    return v
+
+
+# halo2-base's only custom gate (FlexGateConfig): q * (a + b * c - d) with a, b, c, d = advice at rotations 0, 1, 2, 3
+def halo2_base_gate(advice_col=0, selector_col=0):
+    a, b, c, d = (("advice", advice_col, r) for r in range(4))
+    return ("prod", ("fixed", selector_col, 0), ("sum", ("sum", a, ("prod", b, c)), ("neg", d)))
+
+
+def random_expr(rnd, depth, ncols, nchal):
+    if depth == 0 or rnd.random() < 0.15:
+        k = rnd.randrange(6)
+        if k == 0:
+            return ("const", rnd.choice([0, 1, 2, P - 1, rnd.randrange(P)]))
+        if k == 1 and nchal:
+            return ("challenge", rnd.randrange(nchal))
+        kind = rnd.choice(["fixed", "advice", "advice", "instance"])
+        return (kind, rnd.randrange(ncols[kind]), rnd.choice([0, 0, 1, -1, 2, 3, -2]))
+    k = rnd.randrange(8)
+    if k == 0:
+        return ("neg", random_expr(rnd, depth - 1, ncols, nchal))
+    if k == 1:
+        return ("scaled", random_expr(rnd, depth - 1, ncols, nchal), rnd.choice([0, 1, 2, rnd.randrange(P)]))
+    if k in (2, 3, 4):
+        return ("sum", random_expr(rnd, depth - 1, ncols, nchal), random_expr(rnd, depth - 1, ncols, nchal))
+    if k == 5:
+        x = random_expr(rnd, depth - 1, ncols, nchal)
+        return ("prod", x, x)  # Square
+    return ("prod", random_expr(rnd, depth - 1, ncols, nchal), random_expr(rnd, depth - 1, ncols, nchal))
+
+
+def build_custom_gates(gates):
+    """evaluate_h's `custom_gates` evaluator: every gate polynomial compiled, then Horner(PreviousValue, parts, Y)."""
+    g = ev.GraphEvaluator()
+    parts = [g.add_expression(e) for e in gates]
+    g.add_horner(ev.ValueSource(ev.PREVIOUS), parts, ev.ValueSource(ev.Y))
+    return g
+
+
+def mont(xs):
+    return ints_to_limbs([R.to_mont(x, P) for x in xs])
+
+
+def unmont(a):
+    return [R.from_mont(limbs_to_int(r), P) for r in np.asarray(a).reshape(-1, 4)]
+
+
+def random_case(seed, isize, rot_scale, ngates=3, depth=4, ncols=None, nchal=2):
+    """-> dict with integer columns / scalars, the gate expressions and the compiled graph"""
+    rnd = random.Random(seed)
+    ncols = ncols or {"fixed": 2, "advice": 3, "instance": 1}
+    cols = {k: [[rnd.randrange(P) for _ in range(isize)] for _ in range(n)] for k, n in ncols.items()}
+    cols["fixed"][0][1 % isize] = 0
+    cols["advice"][0][0] = P - 1
+    gates = [halo2_base_gate()] + [random_expr(rnd, depth, ncols, nchal) for _ in range(ngates - 1)]
+    return dict(isize=isize, rot_scale=rot_scale, cols=cols, challenges=[rnd.randrange(P) for _ in range(nchal)], y=rnd.randrange(P),
+                prev=[rnd.randrange(P) for _ in range(isize)], gates=gates, graph=build_custom_gates(gates))
+
+
+def case_expected(c, rows=None):
+    rows = range(c["isize"]) if rows is None else rows
+    return [custom_gates_value(c["gates"], c["cols"], c["challenges"], c["y"], c["prev"][i], i, c["rot_scale"], c["isize"]) for i in rows]
+
+
+def case_arrays(c):
+    """Montgomery limb arrays of a case: (fixed, advice, instance lists, challenges, y, prev)"""
+    return ([mont(col) for col in c["cols"]["fixed"]], [mont(col) for col in c["cols"]["advice"]],
+            [mont(col) for col in c["cols"]["instance"]], mont(c["challenges"]), mont([c["y"]])[0], mont(c["prev"]))
+
+
+def golden_cases():
+    """tests/golden/graph_kats.json back as cases (gate expressions as nested tuples, integers parsed)."""
+    import json
+    import os
+
+    def tup(e):
+        return tuple(tup(x) if isinstance(x, list) else x for x in e)
+
+    cases = []
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "graph_kats.json"))):
+        gates = [tup(g) for g in c["gates"]]
+        cases.append(dict(isize=c["isize"], rot_scale=c["rot_scale"], gates=gates, graph=build_custom_gates(gates),
+                          cols={k: [[int(x, 16) for x in col] for col in v] for k, v in c["cols"].items()},
+                          challenges=[int(x, 16) for x in c["challenges"]], y=int(c["y"], 16), prev=[int(x, 16) for x in c["prev"]],
+                          expected=[int(x, 16) for x in c["expected"]]))
+    return cases
+
+
+def permutation_term_graph(ncols):
+    """One chunk of the permutation argument's h(X) term, written directly as calculations over value sources:
+        l_active * ( z(wX) * prod_i (col_i + beta * sigma_i + gamma)  -  z(X) * prod_i (col_i + delta^i * beta * X + gamma) )
+    fixed columns: 0 = l_active, 1 = coset of X, 2 .. 2+ncols-1 = sigma cosets; advice: 0 = z, 1 .. ncols = the columns;
+    constants carry delta^i.  -> (graph, delta)"""
+    V = ev.ValueSource
+    g = ev.GraphEvaluator()
+    r0, r1 = g.add_rotation(0), g.add_rotation(1)
+    delta = pow(7, 1 << 28, P)  # halo2curves Fr::DELTA = GENERATOR^(2^S)
+    beta, gamma = V(ev.BETA), V(ev.GAMMA)
+    left = g.add_calculation(ev.STORE, V(ev.ADVICE, 0, r1))
+    right = g.add_calculation(ev.STORE, V(ev.ADVICE, 0, r0))
+    bx = g.add_calculation(ev.MUL, beta, V(ev.FIXED, 1, r0))
+    for i in range(ncols):
+        col = V(ev.ADVICE, 1 + i, r0)
+        t = g.add_calculation(ev.MUL, beta, V(ev.FIXED, 2 + i, r0))
+        t = g.add_calculation(ev.ADD, g.add_calculation(ev.ADD, col, t), gamma)
+        left = g.add_calculation(ev.MUL, left, t)
+        u = g.add_calculation(ev.MUL, bx, g.add_constant(pow(delta, i, P)))
+        u = g.add_calculation(ev.ADD, g.add_calculation(ev.ADD, col, u), gamma)
+        right = g.add_calculation(ev.MUL, right, u)
+    g.add_calculation(ev.MUL, g.add_calculation(ev.SUB, left, right), V(ev.FIXED, 0, r0))
+    return g, delta

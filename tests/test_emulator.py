@@ -406,3 +406,65 @@ def test_widened_golden_vectors_through_device_code():
     n = 1 << c["k"]
     rc, pw = emu.setup_scalars(0, n, mont([s])[0])
     assert rc == 0 and (emu.fixed_base_window(pw) == np.array([_aff(p) for p in c["g"]])).all()
+
+
+# ---- quotient evaluation: the lowered program (graph_plan.hpp) run by the device's per-thread interpreter (graph.cuh) -----------
+import graph_cases as GC  # noqa: E402
+
+
+def _emu_graph(c, cta_threads=0):
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    return emu.graph_evaluate(c["graph"], fx, ad, ins, ch, None, None, None, y, c["rot_scale"], prev, cta_threads)
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_graph_evaluate_golden(i):
+    c = GC.golden_cases()[i]
+    rc, out, _ = _emu_graph(c)
+    assert rc == 0 and GC.unmont(out) == c["expected"]
+
+
+@pytest.mark.parametrize("seed,isize,rot_scale,threads", [(21, 1, 1, 0), (22, 4, 1, 32), (23, 256, 4, 64), (24, 512, 8, 0), (25, 128, 2, 128)])
+def test_graph_evaluate_matches_oracle(oracle, seed, isize, rot_scale, threads):
+    c = GC.random_case(seed, isize, rot_scale, ngates=5, depth=5)
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                 None, None, None, y, rot_scale, prev)
+    rc, out, info = _emu_graph(c, threads)
+    assert rc == 0 and (out == want).all()
+    assert info[0] < len(g.calculations) and info[1] < g.num_intermediates   # Stores propagated; liveness: fewer slots than intermediates
+
+
+def test_graph_slot_allocation_and_errors(oracle):
+    ev = GC.ev
+    V = ev.ValueSource
+    col = random_field(8, 5)
+    # a long chain t_{i+1} = t_i^2 + col needs two slots however long it is
+    g = ev.GraphEvaluator()
+    t = g.add_calculation(ev.STORE, V(ev.ADVICE, 0, g.add_rotation(0)))
+    for _ in range(40):
+        t = g.add_calculation(ev.ADD, g.add_calculation(ev.SQUARE, t), V(ev.ADVICE, 0, 0))
+    rc, out, info = emu.graph_evaluate(g, [], [col], [], None, None, None, None, None, 1, np.zeros((8, 4), dtype=np.uint64))
+    assert rc == 0 and info[1] <= 2 and info[2] == 1
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, [], [col], [], None,
+                                 None, None, None, None, 1, np.zeros((8, 4), dtype=np.uint64))
+    assert (out == want).all()
+    # the same column passed under two kinds is read through one pointer
+    g2 = ev.GraphEvaluator()
+    g2.add_calculation(ev.MUL, V(ev.ADVICE, 0, g2.add_rotation(0)), V(ev.FIXED, 0, g2.add_rotation(-1)))
+    rc, out, info = emu.graph_evaluate(g2, [col], [col], [], None, None, None, None, None, 1, np.zeros((8, 4), dtype=np.uint64))
+    assert rc == 0 and info[2] == 1 and (out == oracle.vec_op("fr", "mul", col, np.roll(col, 1, axis=0))).all()
+    # an empty graph writes zeros
+    rc, out, _ = emu.graph_evaluate(ev.GraphEvaluator(), [], [], [], None, None, None, None, None, 1, random_field(8, 6))
+    assert rc == 0 and not out.any()
+    # malformed: intermediate read before it is written, column out of range, scalar missing, non-power-of-two domain
+    bad = ev.GraphEvaluator()
+    bad.num_intermediates = 2
+    bad.calculations.append((ev.ADD, 0, V(ev.INTERMEDIATE, 1), V(ev.CONSTANT, 1), V(ev.CONSTANT, 0)))
+    assert emu.graph_evaluate(bad, [], [], [], None, None, None, None, None, 1, np.zeros((8, 4), dtype=np.uint64))[0] != 0
+    assert emu.graph_evaluate(g2, [], [col], [], None, None, None, None, None, 1, np.zeros((8, 4), dtype=np.uint64))[0] != 0
+    g3 = ev.GraphEvaluator()
+    g3.add_calculation(ev.STORE, V(ev.Y))
+    assert emu.graph_evaluate(g3, [], [], [], None, None, None, None, None, 1, np.zeros((8, 4), dtype=np.uint64))[0] != 0
+    assert emu.graph_evaluate(g, [], [col[:6]], [], None, None, None, None, None, 1, np.zeros((6, 4), dtype=np.uint64))[0] != 0

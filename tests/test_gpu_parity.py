@@ -858,3 +858,109 @@ def test_widened_golden_batch_normalize_and_g1_fft():
     c = WGOLD["g1_fft"]
     got = zkb.best_fft_g1(np.array([_aff_or_id(p) for p in c["in"]]), mont([_h(c["omega"])])[0], c["k"])
     assert (got == np.array([_aff_or_id(p) for p in c["out"]])).all()
+
+
+# ---- quotient evaluation on resident cosets: zkb_graph_evaluate vs the oracle and the definition -----------
+import graph_cases as GC  # noqa: E402
+
+
+def _gpu_graph(c):
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    cols = [[zkb.Polynomial(a) for a in group] for group in (fx, ad, ins)]
+    values = zkb.Polynomial(prev)
+    c["graph"].evaluate(values, *cols, challenges=ch, y=y, rot_scale=c["rot_scale"])
+    out = values.to_host()
+    for p in [values] + sum(cols, []):
+        p.free()
+    return out
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_graph_evaluate_golden(i):
+    c = GC.golden_cases()[i]
+    assert GC.unmont(_gpu_graph(c)) == c["expected"]
+
+
+@pytest.mark.parametrize("seed,isize,rot_scale,ngates,depth", [(31, 1, 1, 3, 4), (32, 2, 1, 3, 4), (33, 64, 4, 4, 5), (34, 1 << 12, 4, 6, 6),
+                                                               (35, 1 << 15, 8, 12, 6), (36, 1 << 10, 2, 40, 5)])
+def test_graph_evaluate_vs_oracle(oracle, seed, isize, rot_scale, ngates, depth):
+    c = GC.random_case(seed, isize, rot_scale, ngates=ngates, depth=depth)
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                 None, None, None, y, rot_scale, prev)
+    assert (_gpu_graph(c) == want).all()
+    info = g.last_info()
+    assert info["instructions"] < len(g.calculations) and info["slots"] < max(g.num_intermediates, 2)
+
+
+def test_graph_permutation_term_vs_oracle(oracle):
+    ncols, isize, rs = 4, 1 << 12, 4
+    g, _ = GC.permutation_term_graph(ncols)
+    fixed = [random_field(isize, 600 + i) for i in range(2 + ncols)]
+    advice = [random_field(isize, 620 + i) for i in range(1 + ncols)]
+    beta, gamma = random_field(2, 640)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fixed, advice, [], None,
+                                 beta, gamma, None, None, rs, np.zeros((isize, 4), dtype=np.uint64))
+    values = zkb.Polynomial(np.zeros((isize, 4), dtype=np.uint64))
+    g.evaluate(values, [zkb.Polynomial(a) for a in fixed], [zkb.Polynomial(a) for a in advice], beta=beta, gamma=gamma, rot_scale=rs)
+    assert (values.to_host() == want).all()
+
+
+def test_graph_evaluate_errors_leave_library_usable():
+    ev = GC.ev
+    V = ev.ValueSource
+    a, b = zkb.Polynomial(random_field(64, 1)), zkb.Polynomial(random_field(32, 2))
+    g = ev.GraphEvaluator()
+    g.add_calculation(ev.MUL, V(ev.ADVICE, 0, g.add_rotation(0)), V(ev.ADVICE, 1, 0))
+    out = zkb.Polynomial(np.zeros((64, 4), dtype=np.uint64))
+    with pytest.raises(zkb.ZkbError):      # column of another size
+        g.evaluate(out, advice=[a, b])
+    with pytest.raises(zkb.ZkbError):      # values is also a column
+        g.evaluate(a, advice=[a, a])
+    with pytest.raises(zkb.ZkbError):      # column index out of range
+        g.evaluate(out, advice=[a])
+    bad = ev.GraphEvaluator()
+    bad.num_intermediates = 2
+    bad.calculations.append((ev.ADD, 0, V(ev.INTERMEDIATE, 1), V(ev.CONSTANT, 1), V(ev.CONSTANT, 0)))
+    with pytest.raises(zkb.ZkbError):      # intermediate read before it is written
+        bad.evaluate(out)
+    g.evaluate(out, advice=[a, a])         # and a good call still works: out = a * a
+    sq = ev.GraphEvaluator()
+    sq.add_calculation(ev.SQUARE, V(ev.ADVICE, 0, sq.add_rotation(0)))
+    out2 = zkb.Polynomial(np.zeros((64, 4), dtype=np.uint64))
+    sq.evaluate(out2, advice=[a])
+    assert (out.to_host() == out2.to_host()).all()
+
+
+def test_graph_evaluate_full_size_gate(oracle):
+    """The wrapper's extended domain (k = 22 -> 2^24 rows, rot_scale 4) with halo2-base's gate q (a + b c - d): 64 sampled rows
+    against Python integers, and linearity in the selector column over the whole vector (oracle element-wise add)."""
+    isize, rs = 1 << 24, 4
+    adv = random_field(isize, 7001)
+    q1, q2 = random_field(isize, 7002), random_field(isize, 7003)
+    q12 = oracle.vec_op("fr", "add", q1, q2)
+    g = GC.build_custom_gates([GC.halo2_base_gate()])
+    y = random_field(1, 7004)[0]
+    A = zkb.Polynomial(adv)
+    outs = []
+    for q in (q1, q2, q12):
+        Q = zkb.Polynomial(q)
+        v = zkb.Polynomial(np.zeros((isize, 4), dtype=np.uint64))
+        g.evaluate(v, fixed=[Q], advice=[A], y=y, rot_scale=rs)
+        outs.append(v.to_host())
+        Q.free()
+        v.free()
+    assert (oracle.vec_op("fr", "add", outs[0], outs[1]) == outs[2]).all()
+    rng = np.random.default_rng(5)
+    rows = [0, 1, isize - 1, isize - 4, isize - 13] + [int(x) for x in rng.integers(0, isize, 59)]
+    ai = lambda r: R.from_mont(limbs_to_int(adv[r % isize]), R.FR)  # noqa: E731
+    for r in rows:
+        want = R.from_mont(limbs_to_int(q1[r]), R.FR) * (ai(r) + ai(r + rs) * ai(r + 2 * rs) - ai(r + 3 * rs)) % R.FR
+        assert R.from_mont(limbs_to_int(outs[0][r]), R.FR) == want
+    # previous value: a second pass over the result adds prev * y
+    v = zkb.Polynomial(outs[0])
+    Q = zkb.Polynomial(q2)
+    g.evaluate(v, fixed=[Q], advice=[A], y=y, rot_scale=rs)
+    got = v.to_host()
+    assert (got == oracle.vec_op("fr", "add", oracle.vec_op("fr", "mul", outs[0], np.tile(y, (isize, 1))), outs[1])).all()

@@ -300,3 +300,72 @@ def test_widened_golden_g1_fft(oracle):
     pts = np.array([_aff_or_id(p) for p in c["in"]])
     got = oracle.g1_fft_naive(pts, fr_mont([_h(c["omega"])])[0])
     assert (got == np.array([_aff_or_id(p) for p in c["out"]])).all()
+
+
+# ---- quotient evaluation (GraphEvaluator::evaluate in evaluate_h's row loop): oracle vs the expressions' definition ------------
+import graph_cases as GC  # noqa: E402
+
+
+def _oracle_graph(oracle, c, threads=0):
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    return oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                 None, None, None, y, c["rot_scale"], prev, threads)
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_graph_evaluate_golden(oracle, i):
+    c = GC.golden_cases()[i]
+    assert GC.unmont(_oracle_graph(oracle, c)) == c["expected"]
+
+
+@pytest.mark.parametrize("seed,isize,rot_scale", [(11, 1, 1), (12, 2, 1), (13, 64, 4), (14, 128, 2), (15, 32, 8)])
+def test_graph_evaluate_oracle_vs_definition(oracle, seed, isize, rot_scale):
+    c = GC.random_case(seed, isize, rot_scale, ngates=4, depth=5)
+    assert GC.unmont(_oracle_graph(oracle, c, threads=3)) == GC.case_expected(c)
+
+
+def test_graph_compile_rules():
+    """add_expression's special cases (upstream evaluation.rs): zero / one / two, a + (-b) -> Sub, x * x -> Square,
+    identical calculations are shared."""
+    ev = GC.ev
+    g = ev.GraphEvaluator()
+    a, b = ("advice", 0, 0), ("advice", 0, 1)
+    assert g.add_expression(("prod", ("const", 0), a)) == ev.ValueSource(ev.CONSTANT, 0)
+    ra = g.add_expression(a)
+    assert g.add_expression(("prod", ("const", 1), a)) == ra and g.add_expression(("sum", a, ("const", 0))) == ra
+    n = len(g.calculations)
+    assert g.add_expression(a) == ra and len(g.calculations) == n            # de-duplicated
+    g.add_expression(("prod", ("const", 2), a))
+    assert g.calculations[-1][0] == ev.DOUBLE
+    g.add_expression(("prod", a, a))
+    assert g.calculations[-1][0] == ev.SQUARE
+    g.add_expression(("sum", a, ("neg", b)))
+    assert g.calculations[-1][0] == ev.SUB and g.calculations[-1][2] == ra
+    g.add_expression(("sum", ("const", 0), ("neg", b)))
+    assert g.calculations[-1][0] == ev.NEGATE
+    assert g.add_expression(("scaled", a, 1)) == ra and g.add_expression(("scaled", a, 0)) == ev.ValueSource(ev.CONSTANT, 0)
+    assert g.add_expression(("neg", ("const", 5))) == ev.ValueSource(ev.CONSTANT, g.constants.index(R.FR - 5))
+    assert g.rotations == [0, 1] and g.constants[:3] == [0, 1, 2]
+
+
+def test_graph_permutation_term_oracle_vs_definition(oracle):
+    """The permutation argument's product term as a graph over beta / gamma / fixed / advice sources, against the formula."""
+    import random
+    rnd = random.Random(77)
+    ncols, isize, rs = 3, 32, 4
+    g, delta = GC.permutation_term_graph(ncols)
+    fixed = [[rnd.randrange(R.FR) for _ in range(isize)] for _ in range(2 + ncols)]
+    advice = [[rnd.randrange(R.FR) for _ in range(isize)] for _ in range(1 + ncols)]
+    beta, gamma = rnd.randrange(R.FR), rnd.randrange(R.FR)
+    got = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, [GC.mont(c) for c in fixed],
+                                [GC.mont(c) for c in advice], [], None, GC.mont([beta])[0], GC.mont([gamma])[0], None, None, rs,
+                                np.zeros((isize, 4), dtype=np.uint64))
+    want = []
+    for i in range(isize):
+        left, right = advice[0][(i + rs) % isize], advice[0][i]
+        for j in range(ncols):
+            left = left * (advice[1 + j][i] + beta * fixed[2 + j][i] + gamma) % R.FR
+            right = right * (advice[1 + j][i] + pow(delta, j, R.FR) * beta * fixed[1][i] + gamma) % R.FR
+        want.append((left - right) * fixed[0][i] % R.FR)
+    assert GC.unmont(got) == want

@@ -4,6 +4,8 @@
   python tools/profile_run.py msm --log-n 22 [--c 17 --chunk 128] [--reps 3]
   python tools/profile_run.py ntt --log-n 22 --cols 4 [--reps 3]
   python tools/profile_run.py c2e --log-n 20 --cols 4         (coeff_to_extended k -> k+2)
+  python tools/profile_run.py graph --log-n 24 --cols 1       (quotient evaluation: halo2-base gate on `cols` advice columns,
+                                                               2^log_n extended rows, rot_scale 4)
 Prints one JSON line with CUDA-event timings (per-kernel timers from the library's profiler).
 """
 import argparse
@@ -24,7 +26,7 @@ from util import random_field  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["msm", "ntt", "c2e", "msmbatch"])
+    ap.add_argument("op", choices=["msm", "ntt", "c2e", "msmbatch", "graph"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--cols", type=int, default=1)
     ap.add_argument("--reps", type=int, default=3)
@@ -85,6 +87,33 @@ def main():
             ms, k = zkb.prof.get(name)
             res[name] = ms / max(k, 1)
         res["Mpts_per_s"] = n / (res["ms"] * 1e-3) / 1e6
+    elif args.op == "graph":
+        # evaluate_h's custom-gate pass for halo2-base: per advice column one gate q_i (a + b c - d), a..d = rotations 0..3 of the
+        # column, folded with y from the previous value — on polynomials resident in HBM
+        ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
+        g = ev.GraphEvaluator()
+        parts = []
+        for i in range(args.cols):
+            a, b, c, d = (("advice", i, r) for r in range(4))
+            parts.append(g.add_expression(("prod", ("fixed", i, 0), ("sum", ("sum", a, ("prod", b, c)), ("neg", d)))))
+        g.add_horner(ev.ValueSource(ev.PREVIOUS), parts, ev.ValueSource(ev.Y))
+        adv = [zkb.Polynomial(random_field(n, 40 + i)) for i in range(args.cols)]
+        sel = [zkb.Polynomial(random_field(n, 80 + i)) for i in range(args.cols)]
+        values = zkb.Polynomial(random_field(n, 7))
+        y = random_field(1, 8)[0]
+        for i in range(args.reps + 1):
+            if i == 1:
+                zkb.prof.reset()
+            g.evaluate(values, fixed=sel, advice=adv, y=y, rot_scale=4)
+        values.to_host()[:1]
+        ms, k = zkb.prof.get("graph_evaluate")
+        info = g.last_info()
+        res["ms"] = ms / max(k, 1)
+        res.update(info)
+        res["Mrows_per_s"] = n / (res["ms"] * 1e-3) / 1e6
+        res["alg_GBps"] = info["bytes_per_row"] * n / (res["ms"] * 1e-3) / 1e9
+        res["hbm_frac_of_6459.6"] = res["alg_GBps"] / 6459.6
+        res["modmul_per_row"] = 2 * args.cols + args.cols
     elif args.op == "msmbatch":
         lib.zkb_srs_set_precompute(0 if args.no_table else 1)
         bases = zkb.g1_fixed_base_mul(random_field(n, 2))

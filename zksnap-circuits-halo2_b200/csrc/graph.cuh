@@ -1,0 +1,78 @@
+// graph.cuh — quotient evaluation: halo2's GraphEvaluator run for every row of the extended domain.
+//
+// Restates (on the device) the row loop of halo2-axiom `plonk/evaluation.rs::evaluate_h` over a compiled `GraphEvaluator`
+// (source un-vendored; the field is exact, so the values are fixed by the calculations).  One thread owns one row and runs the
+// lowered program of graph_plan.hpp: operands come from the scalar table, from a polynomial at a rotated row, from the row's
+// previous value or from a slot; results go to a slot.  Slots live in shared memory as two 16-byte planes per slot with the
+// thread index innermost, so every access is a conflict-free 128-bit LDS/STS; the program is staged in shared memory once per
+// CTA and read uniformly.  HBM traffic is one 32-byte read per (polynomial, rotation) — rotated rows of one column fall in
+// lines the neighbouring threads fetch anyway — plus one 32-byte write: the kernel is HBM-bound for halo2-base's gate
+// q (a + b c - d) and turns integer-bound as the number of products per row grows past ~20.
+#pragma once
+#include "field.cuh"
+#include "graph_plan.hpp"
+
+namespace zkb {
+
+struct GraphArgs {
+    const uint4* prog;          // ninstr device instructions (global copy; the kernel stages them in shared memory)
+    uint32_t ninstr;
+    uint32_t result_slot;       // G_RESULT_ZERO: empty graph, the row's value is zero
+    const uint4* scalars;       // scalar table, 32 B each
+    const uint4* const* polys;  // distinct polynomials, isize elements each
+    const uint32_t* rot_off;    // row offset per rotation index
+    uint4* values;              // isize elements: previous value in, result out
+    uint64_t isize;             // power of two
+};
+
+ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint4* slots, uint32_t stride, uint32_t lane) {
+    const uint32_t kind = w >> 30, ix = w & (G_MAX_INDEX - 1);
+    switch (kind) {
+        case G_SCALAR: return fr_load2(g.scalars, ix);
+        case G_SLOT: return fr_from_u4(slots[(2 * ix) * stride + lane], slots[(2 * ix + 1) * stride + lane]);
+        case G_POLY: {
+            const uint64_t row = (idx + g.rot_off[(w >> 20) & (G_MAX_ROT - 1)]) & (g.isize - 1);
+            return fr_load2(g.polys[ix], row);
+        }
+        default: return fr_load2(g.values, idx);
+    }
+}
+
+// prog: where the thread reads instructions from (shared memory on the device); slots: the CTA's slot planes,
+// stride = threads per CTA, lane = thread index in the CTA.
+ZKB_HD void graph_eval_thread(const GraphArgs& g, const uint4* prog, uint64_t idx, uint4* slots, uint32_t stride, uint32_t lane) {
+    if (idx >= g.isize) return;
+    for (uint32_t i = 0; i < g.ninstr; ++i) {
+        const uint4 ins = prog[i];
+        const uint32_t op = ins.x & 0xFF, dst = ins.x >> 8;
+        const Fr a = graph_operand(g, ins.y, idx, slots, stride, lane);
+        Fr r;
+        if (op == ZKB_CALC_MUL || op == ZKB_CALC_SQUARE || op == ZKB_CALC_MUL_ADD) {
+            const Fr b = op == ZKB_CALC_SQUARE ? a : graph_operand(g, ins.z, idx, slots, stride, lane);
+            r = fp_mul(a, b);
+            if (op == ZKB_CALC_MUL_ADD) r = fp_add(r, graph_operand(g, ins.w, idx, slots, stride, lane));
+        } else if (op == ZKB_CALC_ADD || op == ZKB_CALC_DOUBLE) {
+            r = fp_add(a, op == ZKB_CALC_DOUBLE ? a : graph_operand(g, ins.z, idx, slots, stride, lane));
+        } else if (op == ZKB_CALC_SUB) {
+            r = fp_sub(a, graph_operand(g, ins.z, idx, slots, stride, lane));
+        } else if (op == ZKB_CALC_NEGATE) {
+            r = fp_neg(a);
+        } else {
+            r = a;  // ZKB_CALC_STORE
+        }
+        slots[(2 * dst) * stride + lane] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
+        slots[(2 * dst + 1) * stride + lane] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+    }
+    if (g.result_slot == G_RESULT_ZERO) { fr_store2(g.values, idx, Fr::zero()); return; }
+    g.values[2 * idx] = slots[(2 * g.result_slot) * stride + lane];
+    g.values[2 * idx + 1] = slots[(2 * g.result_slot + 1) * stride + lane];
+}
+
+// threads per CTA for a graph with `nslots` slots: the widest CTA whose slots fit in shared memory next to the program
+inline uint32_t graph_cta_threads(uint32_t nslots, uint32_t ninstr, size_t smem_limit) {
+    for (uint32_t t = 128; t >= 32; t >>= 1)
+        if ((size_t)nslots * 32 * t + (size_t)ninstr * 16 <= smem_limit) return t;
+    return 0;
+}
+
+}  // namespace zkb

@@ -1,0 +1,232 @@
+// graph_plan.hpp — host-side lowering of a halo2 GraphEvaluator (zkb_graph, include/zkb200.h) to the device program run by
+// graph.cuh.  Host-only; shared by the product (poly.cu) and the CPU emulator (hostemu.cu).
+//
+// halo2-axiom's `plonk/evaluation.rs` (un-vendored) numbers its intermediates in SSA fashion — one per calculation — so a
+// gate set with a few hundred calculations would need a few hundred 32-byte values per row.  The lowering
+//   * folds every scalar source (constants, challenges, beta, gamma, theta, y) into one table,
+//   * folds the three column arrays into one table of distinct polynomials (a handle used twice is read through one pointer),
+//   * turns rotations into row offsets (rotation * rot_scale).rem_euclid(isize),
+//   * and assigns intermediates to SLOTS by liveness (a slot is released after the last read of its intermediate), so the
+//     per-row state is the graph's maximum number of simultaneously live values — what the kernel keeps in shared memory.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkb200.h"
+
+namespace zkb {
+
+// device instruction: x = op | slot << 8, y / z / w = operand words
+// operand word: kind << 30 | rotation index << 20 | index      (kind: 0 scalar table, 1 slot, 2 polynomial, 3 previous value)
+constexpr uint32_t G_SCALAR = 0, G_SLOT = 1, G_POLY = 2, G_PREV = 3;
+constexpr uint32_t G_MAX_INDEX = 1u << 20, G_MAX_ROT = 1u << 10;
+constexpr uint32_t G_RESULT_ZERO = 0xFFFFFFFFu;
+
+struct GraphInstrWord {
+    uint32_t op_slot, a, b, c;
+};
+
+struct GraphPlan {
+    std::vector<GraphInstrWord> prog;
+    std::vector<uint64_t> scalars;       // 4 u64 each
+    std::vector<uint64_t> poly_handles;  // distinct, in first-use order
+    std::vector<uint32_t> rot_off;       // per rotation index: (rotation * rot_scale) mod isize
+    uint32_t nslots = 0;
+    uint32_t result_slot = G_RESULT_ZERO;  // slot holding the row's result after the last instruction
+    bool uses_prev = false;
+};
+
+inline uint32_t graph_num_operands(uint32_t op) {
+    switch (op) {
+        case ZKB_CALC_ADD: case ZKB_CALC_SUB: case ZKB_CALC_MUL: return 2;
+        case ZKB_CALC_SQUARE: case ZKB_CALC_DOUBLE: case ZKB_CALC_NEGATE: case ZKB_CALC_STORE: return 1;
+        case ZKB_CALC_MUL_ADD: return 3;
+        default: return 0;
+    }
+}
+
+// Copy propagation ahead of the lowering.  Upstream emits one `Store` per column query and starts every Horner with a Store of
+// its start value; on the device a Store is a round trip through shared memory.
+//   * Store(x) into an intermediate that is written once (and is not the graph's result) makes that intermediate an alias of x
+//     when x is a scalar, a column query, the previous value or another write-once intermediate: readers use x directly;
+//   * Store(x) into t immediately followed by t = t * f + p (the first Horner step) becomes t = x * f + p.
+// The values of all remaining intermediates are unchanged.  Malformed graphs are passed through for graph_lower to report.
+inline std::vector<zkb_calculation> graph_simplify(const zkb_graph& g) {
+    const size_t nc = g.num_calculations;
+    const uint32_t ni = g.num_intermediates;
+    std::vector<zkb_calculation> out;
+    if (!g.calculations) return out;
+    std::vector<uint32_t> writes(ni, 0);
+    for (size_t i = 0; i < nc; ++i) {
+        if (g.calculations[i].target >= ni || graph_num_operands(g.calculations[i].op) == 0)
+            return std::vector<zkb_calculation>(g.calculations, g.calculations + nc);
+        ++writes[g.calculations[i].target];
+    }
+    std::vector<int8_t> has_alias(ni, 0), written(ni, 0);
+    std::vector<zkb_value_source> alias(ni);
+    auto resolve = [&](zkb_value_source s) {
+        if (s.kind == ZKB_SRC_INTERMEDIATE && s.index < ni && has_alias[s.index]) return alias[s.index];
+        return s;
+    };
+    auto reads = [](const zkb_value_source& s, uint32_t t) { return s.kind == ZKB_SRC_INTERMEDIATE && s.index == t; };
+    out.reserve(nc);
+    for (size_t i = 0; i < nc; ++i) {
+        zkb_calculation c = g.calculations[i];
+        const uint32_t nop = graph_num_operands(c.op);
+        zkb_value_source* s[3] = {&c.a, &c.b, &c.c};
+        for (uint32_t k = 0; k < nop; ++k) *s[k] = resolve(*s[k]);
+        for (uint32_t k = nop; k < 3; ++k) *s[k] = zkb_value_source{ZKB_SRC_CONSTANT, 0, 0};
+        if (c.op == ZKB_CALC_STORE && i + 1 < nc) {
+            const bool src_stable = c.a.kind != ZKB_SRC_INTERMEDIATE || (c.a.index < ni && writes[c.a.index] == 1 && written[c.a.index]);
+            if (writes[c.target] == 1 && src_stable) {
+                has_alias[c.target] = 1;
+                written[c.target] = 1;
+                alias[c.target] = c.a;
+                continue;
+            }
+            const zkb_calculation& nx = g.calculations[i + 1];
+            if (nx.op == ZKB_CALC_MUL_ADD && nx.target == c.target && reads(nx.a, c.target) && !reads(nx.b, c.target) &&
+                !reads(nx.c, c.target) && !reads(c.a, c.target)) {
+                zkb_calculation m = nx;
+                m.a = c.a;
+                m.b = resolve(m.b);
+                m.c = resolve(m.c);
+                out.push_back(m);
+                written[c.target] = 1;
+                ++i;
+                continue;
+            }
+        }
+        out.push_back(c);
+        written[c.target] = 1;
+    }
+    return out;
+}
+
+// Returns "" on success, otherwise what is wrong with the graph / inputs.
+inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, uint64_t isize, GraphPlan& plan) {
+    plan = GraphPlan();
+    if (isize == 0 || (isize & (isize - 1)) || isize > (1ull << 28)) return "the extended domain size must be a power of two <= 2^28";
+    if (g.num_calculations && !g.calculations) return "calculations is NULL";
+    if (g.num_constants && !g.constants) return "constants is NULL";
+    if (g.num_rotations && !g.rotations) return "rotations is NULL";
+    if (g.num_rotations > G_MAX_ROT) return "too many rotations";
+    if (g.num_intermediates > G_MAX_INDEX || g.num_calculations > (1u << 24)) return "graph too large";
+    if ((in.num_fixed && !in.fixed) || (in.num_advice && !in.advice) || (in.num_instance && !in.instance) ||
+        (in.num_challenges && !in.challenges))
+        return "a column / challenge array is NULL";
+
+    for (size_t r = 0; r < g.num_rotations; ++r) {
+        int64_t o = ((int64_t)g.rotations[r] * (int64_t)in.rot_scale) % (int64_t)isize;
+        if (o < 0) o += (int64_t)isize;
+        plan.rot_off.push_back((uint32_t)o);
+    }
+
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> scalar_ix;  // (kind, index) -> table entry
+    std::map<uint64_t, uint32_t> poly_ix;
+    auto scalar = [&](uint32_t kind, uint32_t index, const uint64_t* v) {
+        auto key = std::make_pair(kind, index);
+        auto it = scalar_ix.find(key);
+        if (it != scalar_ix.end()) return it->second;
+        uint32_t id = (uint32_t)(plan.scalars.size() / 4);
+        plan.scalars.insert(plan.scalars.end(), v, v + 4);
+        scalar_ix[key] = id;
+        return id;
+    };
+
+    const std::vector<zkb_calculation> calcs = graph_simplify(g);
+    const size_t nc = calcs.size();
+    const uint32_t ni = g.num_intermediates;
+    // last read of every intermediate (the result of the last calculation is read "after the end")
+    std::vector<int64_t> last_read(ni, -1);
+    for (size_t i = 0; i < nc; ++i) {
+        const zkb_calculation& c = calcs[i];
+        const uint32_t nop = graph_num_operands(c.op);
+        if (nop == 0) return "unknown calculation at " + std::to_string(i);
+        if (c.target >= ni) return "calculation " + std::to_string(i) + " writes an intermediate out of range";
+        const zkb_value_source* s[3] = {&c.a, &c.b, &c.c};
+        for (uint32_t k = 0; k < nop; ++k)
+            if (s[k]->kind == ZKB_SRC_INTERMEDIATE) {
+                if (s[k]->index >= ni) return "calculation " + std::to_string(i) + " reads an intermediate out of range";
+                last_read[s[k]->index] = (int64_t)i;
+            }
+    }
+    if (nc) last_read[calcs[nc - 1].target] = (int64_t)nc;
+
+    std::vector<int32_t> slot_of(ni, -1);
+    std::vector<uint32_t> free_slots;
+    uint32_t error_at = 0;
+    std::string err;
+    auto operand = [&](const zkb_value_source& s, size_t i) -> uint32_t {
+        auto fail = [&](const char* what) { if (err.empty()) { err = std::string(what) + " (calculation " + std::to_string(i) + ")"; error_at = (uint32_t)i; } return 0u; };
+        switch (s.kind) {
+            case ZKB_SRC_CONSTANT:
+                if (s.index >= g.num_constants) return fail("constant out of range");
+                return G_SCALAR << 30 | scalar(s.kind, s.index, g.constants + 4 * (size_t)s.index);
+            case ZKB_SRC_CHALLENGE:
+                if (s.index >= in.num_challenges) return fail("challenge out of range");
+                return G_SCALAR << 30 | scalar(s.kind, s.index, in.challenges + 4 * (size_t)s.index);
+            case ZKB_SRC_BETA: if (!in.beta) return fail("beta is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.beta);
+            case ZKB_SRC_GAMMA: if (!in.gamma) return fail("gamma is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.gamma);
+            case ZKB_SRC_THETA: if (!in.theta) return fail("theta is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.theta);
+            case ZKB_SRC_Y: if (!in.y) return fail("y is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.y);
+            case ZKB_SRC_INTERMEDIATE:
+                if (slot_of[s.index] < 0) return fail("intermediate read before it is written");
+                return G_SLOT << 30 | (uint32_t)slot_of[s.index];
+            case ZKB_SRC_FIXED: case ZKB_SRC_ADVICE: case ZKB_SRC_INSTANCE: {
+                const uint64_t* cols = s.kind == ZKB_SRC_FIXED ? in.fixed : s.kind == ZKB_SRC_ADVICE ? in.advice : in.instance;
+                const size_t ncols = s.kind == ZKB_SRC_FIXED ? in.num_fixed : s.kind == ZKB_SRC_ADVICE ? in.num_advice : in.num_instance;
+                if (s.index >= ncols) return fail("column out of range");
+                if (s.rotation >= g.num_rotations) return fail("rotation index out of range");
+                const uint64_t h = cols[s.index];
+                auto it = poly_ix.find(h);
+                uint32_t id;
+                if (it == poly_ix.end()) {
+                    id = (uint32_t)plan.poly_handles.size();
+                    plan.poly_handles.push_back(h);
+                    poly_ix[h] = id;
+                } else id = it->second;
+                if (id >= G_MAX_INDEX) return fail("too many polynomials");
+                return G_POLY << 30 | s.rotation << 20 | id;
+            }
+            case ZKB_SRC_PREVIOUS: plan.uses_prev = true; return G_PREV << 30;
+            default: return fail("unknown value source");
+        }
+    };
+
+    plan.prog.reserve(nc);
+    for (size_t i = 0; i < nc; ++i) {
+        const zkb_calculation& c = calcs[i];
+        const uint32_t nop = graph_num_operands(c.op);
+        const zkb_value_source* s[3] = {&c.a, &c.b, &c.c};
+        GraphInstrWord w{0, 0, 0, 0};
+        uint32_t* dst[3] = {&w.a, &w.b, &w.c};
+        for (uint32_t k = 0; k < nop; ++k) *dst[k] = operand(*s[k], i);
+        if (!err.empty()) return err;
+        // operands are in registers before the store: intermediates read here for the last time give their slot back first
+        for (uint32_t k = 0; k < nop; ++k)
+            if (s[k]->kind == ZKB_SRC_INTERMEDIATE && s[k]->index != c.target && last_read[s[k]->index] == (int64_t)i &&
+                slot_of[s[k]->index] >= 0) {
+                free_slots.push_back((uint32_t)slot_of[s[k]->index]);
+                slot_of[s[k]->index] = -1;
+            }
+        if (slot_of[c.target] < 0) {
+            if (!free_slots.empty()) { slot_of[c.target] = (int32_t)free_slots.back(); free_slots.pop_back(); }
+            else slot_of[c.target] = (int32_t)plan.nslots++;
+        }
+        w.op_slot = c.op | (uint32_t)slot_of[c.target] << 8;
+        plan.prog.push_back(w);
+        if (last_read[c.target] <= (int64_t)i) {  // never read again: the value is dead (or re-written later)
+            free_slots.push_back((uint32_t)slot_of[c.target]);
+            slot_of[c.target] = -1;
+        }
+    }
+    (void)error_at;
+    if (nc) plan.result_slot = (uint32_t)slot_of[calcs[nc - 1].target];
+    if (plan.nslots >= (1u << 20)) return "too many live intermediates";
+    return "";
+}
+
+}  // namespace zkb

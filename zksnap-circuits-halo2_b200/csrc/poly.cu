@@ -9,6 +9,7 @@
 
 #include "msm_host.hpp"
 #include "ntt_host.hpp"
+#include "graph.cuh"
 #include "poly.cuh"
 
 namespace zkb {
@@ -64,6 +65,20 @@ __global__ void __launch_bounds__(128) scan_expand_kernel(const ScanExpandArgs a
     scan_expand_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+// one thread per row of the extended domain; dynamic shared memory: slot planes (nslots x 2 x blockDim uint4), then the program
+__global__ void __launch_bounds__(128) graph_evaluate_kernel(const GraphArgs g, uint32_t nslots, uint32_t stage_prog) {
+    extern __shared__ uint4 graph_smem[];
+    uint4* slots = graph_smem;
+    const uint4* prog = g.prog;
+    if (stage_prog) {
+        uint4* sp = graph_smem + (size_t)2 * nslots * blockDim.x;
+        for (uint32_t i = threadIdx.x; i < g.ninstr; i += blockDim.x) sp[i] = g.prog[i];
+        __syncthreads();
+        prog = sp;
+    }
+    graph_eval_thread(g, prog, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, slots, blockDim.x, threadIdx.x);
+}
+
 static inline unsigned nblk(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline uint64_t chunks(uint64_t n) { return (n + POLY_CHUNK - 1) / POLY_CHUNK; }
 
@@ -84,6 +99,10 @@ struct PolyWs {
     DevBuf tmp;
     void* h_out = nullptr;  // pinned 32 B
 };
+static DevBuf& graph_ws() {
+    static DevBuf b;
+    return b;
+}
 static PolyWs& poly_ws() {
     static PolyWs w;
     return w;
@@ -196,6 +215,7 @@ void poly_release_all() {
     poly_map().clear();
     PolyWs& w = poly_ws();
     w.tmp.release();
+    graph_ws().release();
     if (w.h_out) cudaFreeHost(w.h_out);
     w.h_out = nullptr;
 }
@@ -416,6 +436,82 @@ int zkb_poly_prefix_product(uint64_t poly) {
     PolyWs& w = poly_ws();
     ZKB_TRY(w.tmp.reserve(poly_tmp_bytes(p->n)));
     return prefix_product_dev(p->buf.as<uint4>(), p->n, p->buf.as<uint4>(), w.tmp.as<uint4>(), ctx().stream);
+}
+
+// ---- quotient evaluation: GraphEvaluator::evaluate for every row (graph.cuh, graph_plan.hpp) --------------------------------------
+struct GraphInfo { uint32_t instructions = 0, slots = 0, polys = 0, bytes_per_row = 0; };
+static GraphInfo g_graph_info;
+constexpr size_t GRAPH_STAGE_PROG_BYTES = 32 << 10;
+
+int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, uint64_t values) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!graph || !inputs) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    Poly* out;
+    ZKB_TRY(find_poly(values, &out));
+    const uint64_t isize = out->n;
+    GraphPlan plan;
+    const std::string err = graph_lower(*graph, *inputs, isize, plan);
+    if (!err.empty()) { set_error("graph: %s", err.c_str()); return ZKB_ERR_ARG; }
+    std::vector<const uint4*> ptrs;
+    for (uint64_t h : plan.poly_handles) {
+        Poly* p;
+        ZKB_TRY(find_poly(h, &p));
+        if (p->n != isize) { set_error("graph: polynomial %llu holds %zu elements, values holds %zu", (unsigned long long)h, (size_t)p->n, (size_t)isize); return ZKB_ERR_ARG; }
+        if (p == out) { set_error("graph: values is also read as a column (rows are not evaluated in order)"); return ZKB_ERR_ARG; }
+        ptrs.push_back(p->buf.as<uint4>());
+    }
+    const uint32_t ninstr = (uint32_t)plan.prog.size();
+    const bool stage = (size_t)ninstr * 16 <= GRAPH_STAGE_PROG_BYTES;
+    int smem_limit = 0;
+    ZKB_CUDA_TRY(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device));
+    const uint32_t threads = graph_cta_threads(plan.nslots, stage ? ninstr : 0, (size_t)smem_limit);
+    if (threads == 0) { set_error("graph: %u live intermediates do not fit in shared memory", plan.nslots); return ZKB_ERR_ARG; }
+    const size_t smem = (size_t)plan.nslots * 32 * threads + (stage ? (size_t)ninstr * 16 : 0);
+
+    // one upload: program | scalars | rotation offsets | polynomial pointers (stream-ordered after the previous evaluation)
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t o_prog = 0, o_sc = up16(o_prog + (size_t)ninstr * 16), o_rot = up16(o_sc + plan.scalars.size() * 8),
+                 o_ptr = up16(o_rot + plan.rot_off.size() * 4), total = up16(o_ptr + ptrs.size() * 8) + 16;
+    std::vector<unsigned char> host(total, 0);
+    if (ninstr) memcpy(host.data() + o_prog, plan.prog.data(), (size_t)ninstr * 16);
+    if (!plan.scalars.empty()) memcpy(host.data() + o_sc, plan.scalars.data(), plan.scalars.size() * 8);
+    if (!plan.rot_off.empty()) memcpy(host.data() + o_rot, plan.rot_off.data(), plan.rot_off.size() * 4);
+    if (!ptrs.empty()) memcpy(host.data() + o_ptr, ptrs.data(), ptrs.size() * 8);
+    cudaStream_t s = ctx().stream;
+    ZKB_TRY(graph_ws().reserve(total));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(graph_ws().p, host.data(), total, cudaMemcpyHostToDevice, s));  // pageable source: staged before return
+    char* d = reinterpret_cast<char*>(graph_ws().p);
+    GraphArgs a{};
+    a.prog = reinterpret_cast<const uint4*>(d + o_prog);
+    a.ninstr = ninstr;
+    a.result_slot = plan.result_slot;
+    a.scalars = reinterpret_cast<const uint4*>(d + o_sc);
+    a.polys = reinterpret_cast<const uint4* const*>(d + o_ptr);
+    a.rot_off = reinterpret_cast<const uint32_t*>(d + o_rot);
+    a.values = out->buf.as<uint4>();
+    a.isize = isize;
+    if (smem > 48 * 1024) ZKB_CUDA_TRY(cudaFuncSetAttribute(graph_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope prof("graph_evaluate", s);
+        graph_evaluate_kernel<<<nblk(isize, threads), threads, smem, s>>>(a, plan.nslots, stage ? 1u : 0u);
+    }
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    g_graph_info.instructions = ninstr;
+    g_graph_info.slots = plan.nslots;
+    g_graph_info.polys = (uint32_t)ptrs.size();
+    g_graph_info.bytes_per_row = 32 * ((uint32_t)ptrs.size() + (plan.uses_prev ? 1 : 0) + 1);
+    return ZKB_OK;
+}
+
+int zkb_graph_last_info(uint32_t* instructions, uint32_t* slots, uint32_t* polys_read, uint32_t* bytes_per_row) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    if (instructions) *instructions = g_graph_info.instructions;
+    if (slots) *slots = g_graph_info.slots;
+    if (polys_read) *polys_read = g_graph_info.polys;
+    if (bytes_per_row) *bytes_per_row = g_graph_info.bytes_per_row;
+    return ZKB_OK;
 }
 
 int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
