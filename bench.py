@@ -9,6 +9,8 @@ value  : points/s, whole job, scalars already in HBM, timed with CUDA events on 
 e2e    : the same through the host-buffer C ABI call (zkb_msm_g1_srs): pinned host scalars -> H2D -> kernels ->
          window sums D2H -> host fold, wall clock (the host fold is part of the call).
 ntt    : secondary object: batched 2^22 Fr NTT (16 columns) elements/s and its HBM roofline.
+quotient: secondary object: evaluate_h's custom-gate pass (halo2-base gate on 4 advice columns, 2^24 extended rows resident in HBM)
+         rows/s and its HBM roofline.
 `--impl reference` times the CPU restatement of halo2's best_multiexp (oracle/, all host threads) on a bounded
 sample of the same workload; the reference itself is Rust with un-vendored dependencies and cannot be built
 in this image (DESIGN.md "Oracle").
@@ -34,6 +36,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 LOG_N_MSM = int(os.environ.get("ZKB_BENCH_LOG_N", "24"))
 NTT_LOG_N = int(os.environ.get("ZKB_BENCH_NTT_LOG_N", "22"))
 NTT_COLS = int(os.environ.get("ZKB_BENCH_NTT_COLS", "16"))
+QUOT_LOG_N = int(os.environ.get("ZKB_BENCH_QUOT_LOG_N", "24"))   # extended domain of the wrapper circuit (k = 22, extended_k = 24)
+QUOT_COLS = int(os.environ.get("ZKB_BENCH_QUOT_COLS", "4"))
 SHARDED_LOG_N = int(os.environ.get("ZKB_BENCH_SHARDED_LOG_N", "26"))
 CPU_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_CPU_LOG_N", "24"))   # cpu_baseline leg: the full workload once, ~10 s on 16 threads
 REF_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_REF_LOG_N", "22"))   # --impl reference: bounded sample per step
@@ -380,6 +384,63 @@ def main():
                                 "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound, see DESIGN.md"}}
         del cols_np
 
+    # ---- secondary: quotient evaluation on resident cosets (GraphEvaluator row loop) ------------------------
+    quot_obj = None
+    if not args.skip_ntt:
+        ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
+        rows, qc, rs = 1 << QUOT_LOG_N, QUOT_COLS, 4
+        gr = ev.GraphEvaluator()
+        parts = []
+        for i in range(qc):   # halo2-base: q_i * (a + b * c - d), a..d = advice column i at rotations 0..3
+            a_, b_, c_, d_ = (("advice", i, r) for r in range(4))
+            parts.append(gr.add_expression(("prod", ("fixed", i, 0), ("sum", ("sum", a_, ("prod", b_, c_)), ("neg", d_)))))
+        gr.add_horner(ev.ValueSource(ev.PREVIOUS), parts, ev.ValueSource(ev.Y))
+        adv_np, sel_np = random_field(rows, 0x9A7E + rank), random_field(rows, 0x5E1 + rank)
+        y_np = random_field(1, 0x77)[0]
+        adv = [zkb.Polynomial(adv_np) for _ in range(qc)]   # same values, distinct HBM buffers: the traffic is real
+        sel = [zkb.Polynomial(sel_np) for _ in range(qc)]
+        vals = zkb.Polynomial(np.zeros((rows, 4), dtype=np.uint64))
+        note("quotient inputs ready")
+        gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
+        # parity of the measured configuration on sampled rows, Python integers (previous value 0):
+        # value = gate * (y^(qc-1) + ... + 1), gate = q (a + b c - d)
+        FRM = ev.FR
+        Rinv = pow(1 << 256, FRM - 2, FRM)
+        li = lambda v: sum(int(v[j]) << (64 * j) for j in range(4)) * Rinv % FRM  # noqa: E731
+        got = vals.to_host()
+        yv = li(y_np)
+        ysum = sum(pow(yv, j, FRM) for j in range(qc)) % FRM
+        q_ok = True
+        for r in [0, 1, rows - 1, rows - 5, rows // 3, rows // 2 + 7]:
+            av = [li(adv_np[(r + j * rs) % rows]) for j in range(4)]
+            q_ok &= li(got[r]) == li(sel_np[r]) * (av[0] + av[1] * av[2] - av[3]) % FRM * ysum % FRM
+        del got
+        for _ in range(args.warmup):
+            gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
+        barrier()
+        launches3 = zkb.launch_count()
+        zkb.prof.enable(True)
+        zkb.prof.reset()
+        for _ in range(args.steps):
+            gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
+        barrier()
+        qms, qk = zkb.prof.get("graph_evaluate")   # CUDA events around the kernel on the library stream
+        qms /= max(qk, 1)
+        zkb.prof.enable(False)
+        launches += zkb.launch_count() - launches3
+        info = gr.last_info()
+        qgbs = info["bytes_per_row"] * rows / (qms * 1e-3) / 1e9
+        quot_obj = {"workload": "evaluate_h custom gates: halo2-base gate q(a+bc-d) on %d advice columns, 2^%d extended rows, rot_scale %d, resident in HBM" % (qc, QUOT_LOG_N, rs),
+                    "value": world * rows / (qms * 1e-3), "unit": "rows/s", "ms_per_step": qms, "parity_checked": bool(q_ok),
+                    "lowered": info, "modmul_per_row": 3 * qc,
+                    "roofline": {"bound": "hbm", "achieved": qgbs, "peak": hbm_peak, "unit": "GB/s", "frac": qgbs / hbm_peak,
+                                 "traffic": None, "note": "32 B x (polynomials read + previous value + result) per row; integer-issue bound, see DESIGN.md"}}
+        parity = parity and bool(q_ok)
+        for p_ in adv + sel + [vals]:
+            p_.free()
+        del adv_np, sel_np
+        note("quotient done")
+
     # ---- N > 1: one 2^26 NTT sharded over the ranks (exchange fused into the NTT passes over NVLink peer memory) ----------------
     sharded_obj = None
     if world > 1 and not args.skip_ntt and (world & (world - 1)) == 0 and world <= 8:
@@ -448,7 +509,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": n * 32 * world,
                     "d2h_bytes_per_step": n_win.value * 128 * world, "timer": "wall clock around the C-ABI call (includes host fold)"},
             "gpu_launches": int(launches), "parity_checked": parity, "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clock_info, "ntt": ntt_obj, "sharded_ntt": sharded_obj,
+            "clocks": clock_info, "ntt": ntt_obj, "quotient": quot_obj, "sharded_ntt": sharded_obj,
         }
         print(json.dumps(line))
     params.close()

@@ -6,6 +6,8 @@
 //   halo2_proofs::arithmetic::best_multiexp / best_fft
 //   halo2_proofs::poly::EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff}
 //   halo2_proofs::poly::kzg::commitment::ParamsKZG::{commit, commit_lagrange}
+//   halo2_proofs::plonk::evaluation::GraphEvaluator::{add_rotation, add_constant, add_calculation, evaluate}  (row loop of
+//       evaluate_h over polynomials resident in HBM)
 //
 // Types are the in-memory layouts of halo2curves::bn256 (Montgomery limbs).
 #pragma once
@@ -128,6 +130,105 @@ class ParamsKZG {
     }
     uint32_t k_;
     uint64_t h_g_ = 0, h_gl_ = 0;
+};
+
+// A polynomial / column of evaluations resident in HBM (zkb_poly_*): uploaded once, used by handle.
+class Polynomial {
+   public:
+    explicit Polynomial(const std::vector<Fr>& values) { check(zkb_poly_upload(values.empty() ? nullptr : values[0].data(), values.size(), &h_), "Polynomial"); }
+    static Polynomial zeros(size_t n) { Polynomial p; check(zkb_poly_alloc(n, &p.h_), "Polynomial::zeros"); return p; }
+    Polynomial(Polynomial&& o) noexcept : h_(o.h_) { o.h_ = 0; }
+    Polynomial(const Polynomial&) = delete;
+    Polynomial& operator=(const Polynomial&) = delete;
+    ~Polynomial() { if (h_) zkb_poly_free(h_); }
+    uint64_t handle() const { return h_; }
+    size_t len() const { size_t n = 0; check(zkb_poly_len(h_, &n), "len"); return n; }
+    std::vector<Fr> to_vec() const {
+        std::vector<Fr> out(len());
+        check(zkb_poly_download(h_, out.empty() ? nullptr : out[0].data(), out.size()), "to_vec");
+        return out;
+    }
+    void mul(const Polynomial& other) { check(zkb_poly_mul(h_, other.h_), "mul"); }
+
+   private:
+    Polynomial() = default;
+    uint64_t h_ = 0;
+};
+
+// plonk::evaluation::{ValueSource, Calculation, GraphEvaluator}.  `evaluate` is evaluate_h's row loop
+//   values[idx] = graph.evaluate(&mut data, fixed, advice, instance, challenges, &beta, &gamma, &theta, &y, &values[idx], idx, rot_scale, isize)
+// for every idx, on the device.  Horner(start, parts, factor) = Store(start) + one MulAdd per part (add_horner).
+struct ValueSource {
+    static zkb_value_source Constant(uint32_t i) { return {ZKB_SRC_CONSTANT, i, 0}; }
+    static zkb_value_source Intermediate(uint32_t i) { return {ZKB_SRC_INTERMEDIATE, i, 0}; }
+    static zkb_value_source Fixed(uint32_t col, uint32_t rot) { return {ZKB_SRC_FIXED, col, rot}; }
+    static zkb_value_source Advice(uint32_t col, uint32_t rot) { return {ZKB_SRC_ADVICE, col, rot}; }
+    static zkb_value_source Instance(uint32_t col, uint32_t rot) { return {ZKB_SRC_INSTANCE, col, rot}; }
+    static zkb_value_source Challenge(uint32_t i) { return {ZKB_SRC_CHALLENGE, i, 0}; }
+    static zkb_value_source Beta() { return {ZKB_SRC_BETA, 0, 0}; }
+    static zkb_value_source Gamma() { return {ZKB_SRC_GAMMA, 0, 0}; }
+    static zkb_value_source Theta() { return {ZKB_SRC_THETA, 0, 0}; }
+    static zkb_value_source Y() { return {ZKB_SRC_Y, 0, 0}; }
+    static zkb_value_source PreviousValue() { return {ZKB_SRC_PREVIOUS, 0, 0}; }
+};
+
+class GraphEvaluator {
+   public:
+    std::vector<Fr> constants;
+    std::vector<int32_t> rotations;
+    std::vector<zkb_calculation> calculations;
+    uint32_t num_intermediates = 0;
+
+    uint32_t add_rotation(int32_t rotation) {
+        for (size_t i = 0; i < rotations.size(); ++i)
+            if (rotations[i] == rotation) return uint32_t(i);
+        rotations.push_back(rotation);
+        return uint32_t(rotations.size() - 1);
+    }
+    zkb_value_source add_constant(const Fr& c) {
+        for (size_t i = 0; i < constants.size(); ++i)
+            if (constants[i] == c) return ValueSource::Constant(uint32_t(i));
+        constants.push_back(c);
+        return ValueSource::Constant(uint32_t(constants.size() - 1));
+    }
+    // op: ZKB_CALC_{ADD, SUB, MUL, SQUARE, DOUBLE, NEGATE, STORE}; an identical earlier calculation is reused
+    zkb_value_source add_calculation(uint32_t op, zkb_value_source a, zkb_value_source b = {ZKB_SRC_CONSTANT, 0, 0}) {
+        auto same = [](const zkb_value_source& x, const zkb_value_source& y) { return x.kind == y.kind && x.index == y.index && x.rotation == y.rotation; };
+        for (const auto& c : calculations)
+            if (c.op == op && op != ZKB_CALC_MUL_ADD && same(c.a, a) && same(c.b, b)) return ValueSource::Intermediate(c.target);
+        calculations.push_back({op, num_intermediates, a, b, {ZKB_SRC_CONSTANT, 0, 0}});
+        return ValueSource::Intermediate(num_intermediates++);
+    }
+    zkb_value_source add_horner(zkb_value_source start, const std::vector<zkb_value_source>& parts, zkb_value_source factor) {
+        const uint32_t t = num_intermediates++;
+        calculations.push_back({ZKB_CALC_STORE, t, start, {ZKB_SRC_CONSTANT, 0, 0}, {ZKB_SRC_CONSTANT, 0, 0}});
+        for (const auto& p : parts) calculations.push_back({ZKB_CALC_MUL_ADD, t, ValueSource::Intermediate(t), factor, p});
+        return ValueSource::Intermediate(t);
+    }
+
+    struct Scalars {
+        const Fr* beta = nullptr;
+        const Fr* gamma = nullptr;
+        const Fr* theta = nullptr;
+        const Fr* y = nullptr;
+    };
+    void evaluate(Polynomial& values, const std::vector<const Polynomial*>& fixed, const std::vector<const Polynomial*>& advice,
+                  const std::vector<const Polynomial*>& instance, const std::vector<Fr>& challenges, const Scalars& sc,
+                  int32_t rot_scale) const {
+        auto handles = [](const std::vector<const Polynomial*>& v) {
+            std::vector<uint64_t> h;
+            for (auto* p : v) h.push_back(p->handle());
+            return h;
+        };
+        const std::vector<uint64_t> f = handles(fixed), a = handles(advice), in = handles(instance);
+        zkb_graph g{calculations.data(), calculations.size(), num_intermediates, constants.empty() ? nullptr : constants[0].data(),
+                    constants.size(), rotations.data(), rotations.size()};
+        zkb_graph_inputs inp{f.data(), f.size(), a.data(), a.size(), in.data(), in.size(),
+                             challenges.empty() ? nullptr : challenges[0].data(), challenges.size(),
+                             sc.beta ? sc.beta->data() : nullptr, sc.gamma ? sc.gamma->data() : nullptr,
+                             sc.theta ? sc.theta->data() : nullptr, sc.y ? sc.y->data() : nullptr, rot_scale};
+        check(zkb_graph_evaluate(&g, &inp, values.handle()), "GraphEvaluator::evaluate");
+    }
 };
 
 }  // namespace halo2

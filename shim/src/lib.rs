@@ -38,7 +38,52 @@ extern "C" {
     pub fn zkb_srs_download(handle: u64, bases_out: *mut u64, n: size_t) -> c_int;
     pub fn zkb_host_register(ptr: *mut c_void, bytes: size_t) -> c_int;
     pub fn zkb_host_unregister(ptr: *mut c_void) -> c_int;
+    pub fn zkb_graph_evaluate(graph: *const zkb_graph, inputs: *const zkb_graph_inputs, values: u64) -> c_int;
     pub fn zkb_msm_g1_srs_dev(handle: u64, offset: size_t, d_scalars: *const c_void, n: size_t, out_jac: *mut u64, stream: *mut c_void) -> c_int;
+}
+
+/// `plonk::evaluation::ValueSource` / `Calculation` / `GraphEvaluator` as the C ABI reads them (include/zkb200.h).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct zkb_value_source {
+    pub kind: u32,     // ZKB_SRC_*: 0 Constant 1 Intermediate 2 Fixed 3 Advice 4 Instance 5 Challenge 6 Beta 7 Gamma 8 Theta 9 Y 10 PreviousValue
+    pub index: u32,
+    pub rotation: u32, // index into `rotations`
+}
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct zkb_calculation {
+    pub op: u32,       // ZKB_CALC_*: 0 Add 1 Sub 2 Mul 3 Square 4 Double 5 Negate 6 Store 7 MulAdd (one Horner step)
+    pub target: u32,
+    pub a: zkb_value_source,
+    pub b: zkb_value_source,
+    pub c: zkb_value_source,
+}
+#[repr(C)]
+pub struct zkb_graph {
+    pub calculations: *const zkb_calculation,
+    pub num_calculations: size_t,
+    pub num_intermediates: u32,
+    pub constants: *const u64,
+    pub num_constants: size_t,
+    pub rotations: *const i32,
+    pub num_rotations: size_t,
+}
+#[repr(C)]
+pub struct zkb_graph_inputs {
+    pub fixed: *const u64,
+    pub num_fixed: size_t,
+    pub advice: *const u64,
+    pub num_advice: size_t,
+    pub instance: *const u64,
+    pub num_instance: size_t,
+    pub challenges: *const u64,
+    pub num_challenges: size_t,
+    pub beta: *const u64,
+    pub gamma: *const u64,
+    pub theta: *const u64,
+    pub y: *const u64,
+    pub rot_scale: i32,
 }
 
 #[inline]
@@ -188,4 +233,19 @@ impl Drop for PinnedVec {
     fn drop(&mut self) {
         unsafe { zkb_host_unregister(self.values.as_mut_ptr() as *mut c_void) };
     }
+}
+
+/// The row loop of `evaluate_h` over a compiled `GraphEvaluator`, on extended cosets resident in HBM (polynomial handles):
+/// `values[idx] = graph.evaluate(.., &values[idx], idx, rot_scale, isize)` for every row.
+#[allow(clippy::too_many_arguments)]
+pub fn graph_evaluate(graph: &zkb_graph, fixed: &[u64], advice: &[u64], instance: &[u64], challenges: &[Fr], beta: &Fr, gamma: &Fr,
+                      theta: &Fr, y: &Fr, rot_scale: i32, values: u64) {
+    let inputs = zkb_graph_inputs {
+        fixed: fixed.as_ptr(), num_fixed: fixed.len(), advice: advice.as_ptr(), num_advice: advice.len(),
+        instance: instance.as_ptr(), num_instance: instance.len(),
+        challenges: challenges.as_ptr() as *const u64, num_challenges: challenges.len(),
+        beta: beta as *const Fr as *const u64, gamma: gamma as *const Fr as *const u64,
+        theta: theta as *const Fr as *const u64, y: y as *const Fr as *const u64, rot_scale,
+    };
+    check(unsafe { zkb_graph_evaluate(graph, &inputs, values) }, "graph_evaluate");
 }

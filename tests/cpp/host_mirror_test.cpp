@@ -71,6 +71,44 @@ int main(int argc, char** argv) {
         auto aff = halo2::batch_normalize(pts);
         if (std::memcmp(aff[0].data(), cm.data(), 64) != 0) return fail("batch_normalize of a z = R point");
     }
+    // GraphEvaluator over resident polynomials: values = advice[0](row) * advice[0](row + 1), rot_scale 1, against the
+    // element-wise product of the column with its rotated copy (zkb_poly_mul)
+    {
+        halo2::Polynomial col(c);
+        std::vector<halo2::Fr> rot(8);
+        for (int i = 0; i < 8; ++i) rot[i] = c[(i + 1) % 8];
+        halo2::Polynomial want(c), rotp(rot);
+        want.mul(rotp);
+        halo2::GraphEvaluator g;
+        const uint32_t r0 = g.add_rotation(0), r1 = g.add_rotation(1);
+        auto x = g.add_calculation(ZKB_CALC_STORE, halo2::ValueSource::Advice(0, r0));
+        g.add_calculation(ZKB_CALC_MUL, x, halo2::ValueSource::Advice(0, r1));
+        halo2::Polynomial values = halo2::Polynomial::zeros(8);
+        g.evaluate(values, {}, {&col}, {}, {}, {}, 1);
+        if (values.to_vec() != want.to_vec()) return fail("GraphEvaluator product of rotations");
+        // Horner from the previous value: values = values * y + col  (y = 2)
+        halo2::GraphEvaluator h;
+        h.add_horner(halo2::ValueSource::PreviousValue(), {halo2::ValueSource::Advice(0, h.add_rotation(0))}, halo2::ValueSource::Y());
+        halo2::Fr two;
+        std::memcpy(two.data(), in[1], 32);
+        halo2::GraphEvaluator::Scalars sc;
+        sc.y = &two;
+        halo2::Polynomial v2(c);                        // previous = col -> 2 col + col = 3 col
+        h.evaluate(v2, {}, {&col}, {}, {}, sc, 1);
+        halo2::GraphEvaluator t;                        // 3 * col through a constant
+        halo2::Fr three;
+        std::memcpy(three.data(), in[2], 32);
+        t.add_calculation(ZKB_CALC_MUL, t.add_constant(three), halo2::ValueSource::Advice(0, t.add_rotation(0)));
+        halo2::Polynomial v3 = halo2::Polynomial::zeros(8);
+        t.evaluate(v3, {}, {&col}, {}, {}, {}, 1);
+        if (v2.to_vec() != v3.to_vec()) return fail("GraphEvaluator Horner from the previous value");
+        try {
+            halo2::Polynomial small = halo2::Polynomial::zeros(4);
+            g.evaluate(small, {}, {&col}, {}, {}, {}, 1);
+            return fail("a column of another size must throw");
+        } catch (const std::runtime_error&) {
+        }
+    }
     std::printf("gpu ok\n");
     return 0;
 }

@@ -5,9 +5,10 @@
 // lowered program of graph_plan.hpp: operands come from the scalar table, from a polynomial at a rotated row, from the row's
 // previous value or from a slot; results go to a slot.  Slots live in shared memory as two 16-byte planes per slot with the
 // thread index innermost, so every access is a conflict-free 128-bit LDS/STS; the program is staged in shared memory once per
-// CTA and read uniformly.  HBM traffic is one 32-byte read per (polynomial, rotation) — rotated rows of one column fall in
-// lines the neighbouring threads fetch anyway — plus one 32-byte write: the kernel is HBM-bound for halo2-base's gate
-// q (a + b c - d) and turns integer-bound as the number of products per row grows past ~20.
+// CTA and read uniformly.  Slot values are kept lazy (< 2r; fp_*_lazy), the stored result is canonical.  HBM traffic is one
+// 32-byte read per polynomial — rotated rows of one column fall in lines the neighbouring threads fetch anyway — plus one
+// 32-byte write (ncu: DRAM bytes = algorithmic bytes), but already halo2-base's gate q (a + b c - d), three products per row for
+// 128 bytes, keeps the multiply pipe 84 % busy at a third of the HBM rate: like the NTT, this kernel is integer-bound.
 #pragma once
 #include "field.cuh"
 #include "graph_plan.hpp"
@@ -49,14 +50,14 @@ ZKB_HD void graph_eval_thread(const GraphArgs& g, const uint4* prog, uint64_t id
         Fr r;
         if (op == ZKB_CALC_MUL || op == ZKB_CALC_SQUARE || op == ZKB_CALC_MUL_ADD) {
             const Fr b = op == ZKB_CALC_SQUARE ? a : graph_operand(g, ins.z, idx, slots, stride, lane);
-            r = fp_mul(a, b);
-            if (op == ZKB_CALC_MUL_ADD) r = fp_add(r, graph_operand(g, ins.w, idx, slots, stride, lane));
+            r = fp_mul_lazy(a, b);
+            if (op == ZKB_CALC_MUL_ADD) r = fp_add_lazy(r, graph_operand(g, ins.w, idx, slots, stride, lane));
         } else if (op == ZKB_CALC_ADD || op == ZKB_CALC_DOUBLE) {
-            r = fp_add(a, op == ZKB_CALC_DOUBLE ? a : graph_operand(g, ins.z, idx, slots, stride, lane));
+            r = fp_add_lazy(a, op == ZKB_CALC_DOUBLE ? a : graph_operand(g, ins.z, idx, slots, stride, lane));
         } else if (op == ZKB_CALC_SUB) {
-            r = fp_sub(a, graph_operand(g, ins.z, idx, slots, stride, lane));
+            r = fp_sub_lazy(a, graph_operand(g, ins.z, idx, slots, stride, lane));
         } else if (op == ZKB_CALC_NEGATE) {
-            r = fp_neg(a);
+            r = fp_sub_lazy(Fr::zero(), a);
         } else {
             r = a;  // ZKB_CALC_STORE
         }
@@ -64,8 +65,7 @@ ZKB_HD void graph_eval_thread(const GraphArgs& g, const uint4* prog, uint64_t id
         slots[(2 * dst + 1) * stride + lane] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
     }
     if (g.result_slot == G_RESULT_ZERO) { fr_store2(g.values, idx, Fr::zero()); return; }
-    g.values[2 * idx] = slots[(2 * g.result_slot) * stride + lane];
-    g.values[2 * idx + 1] = slots[(2 * g.result_slot + 1) * stride + lane];
+    fr_store2(g.values, idx, fp_canon(fr_from_u4(slots[(2 * g.result_slot) * stride + lane], slots[(2 * g.result_slot + 1) * stride + lane])));
 }
 
 // threads per CTA for a graph with `nslots` slots: the widest CTA whose slots fit in shared memory next to the program

@@ -139,47 +139,36 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
     const std::vector<zkb_calculation> calcs = graph_simplify(g);
     const size_t nc = calcs.size();
     const uint32_t ni = g.num_intermediates;
-    // last read of every intermediate (the result of the last calculation is read "after the end")
-    std::vector<int64_t> last_read(ni, -1);
-    for (size_t i = 0; i < nc; ++i) {
-        const zkb_calculation& c = calcs[i];
-        const uint32_t nop = graph_num_operands(c.op);
-        if (nop == 0) return "unknown calculation at " + std::to_string(i);
-        if (c.target >= ni) return "calculation " + std::to_string(i) + " writes an intermediate out of range";
-        const zkb_value_source* s[3] = {&c.a, &c.b, &c.c};
-        for (uint32_t k = 0; k < nop; ++k)
-            if (s[k]->kind == ZKB_SRC_INTERMEDIATE) {
-                if (s[k]->index >= ni) return "calculation " + std::to_string(i) + " reads an intermediate out of range";
-                last_read[s[k]->index] = (int64_t)i;
-            }
-    }
-    if (nc) last_read[calcs[nc - 1].target] = (int64_t)nc;
 
-    std::vector<int32_t> slot_of(ni, -1);
-    std::vector<uint32_t> free_slots;
-    uint32_t error_at = 0;
+    // ---- SSA: every write of an intermediate makes a new VALUE; operands become device words or value ids ------------------------
+    struct Node {
+        uint32_t op;
+        uint32_t word[3];   // device operand word, valid when val[k] < 0
+        int32_t val[3];     // value id read, or -1
+        uint32_t nop;
+        bool live;
+    };
+    std::vector<Node> nodes(nc);           // node i defines value i
+    std::vector<int32_t> cur_val(ni, -1);  // value currently held by each intermediate
     std::string err;
+    auto fail = [&](const char* what, size_t i) { if (err.empty()) err = std::string(what) + " (calculation " + std::to_string(i) + ")"; return 0u; };
     auto operand = [&](const zkb_value_source& s, size_t i) -> uint32_t {
-        auto fail = [&](const char* what) { if (err.empty()) { err = std::string(what) + " (calculation " + std::to_string(i) + ")"; error_at = (uint32_t)i; } return 0u; };
         switch (s.kind) {
             case ZKB_SRC_CONSTANT:
-                if (s.index >= g.num_constants) return fail("constant out of range");
+                if (s.index >= g.num_constants) return fail("constant out of range", i);
                 return G_SCALAR << 30 | scalar(s.kind, s.index, g.constants + 4 * (size_t)s.index);
             case ZKB_SRC_CHALLENGE:
-                if (s.index >= in.num_challenges) return fail("challenge out of range");
+                if (s.index >= in.num_challenges) return fail("challenge out of range", i);
                 return G_SCALAR << 30 | scalar(s.kind, s.index, in.challenges + 4 * (size_t)s.index);
-            case ZKB_SRC_BETA: if (!in.beta) return fail("beta is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.beta);
-            case ZKB_SRC_GAMMA: if (!in.gamma) return fail("gamma is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.gamma);
-            case ZKB_SRC_THETA: if (!in.theta) return fail("theta is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.theta);
-            case ZKB_SRC_Y: if (!in.y) return fail("y is NULL"); return G_SCALAR << 30 | scalar(s.kind, 0, in.y);
-            case ZKB_SRC_INTERMEDIATE:
-                if (slot_of[s.index] < 0) return fail("intermediate read before it is written");
-                return G_SLOT << 30 | (uint32_t)slot_of[s.index];
+            case ZKB_SRC_BETA: if (!in.beta) return fail("beta is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.beta);
+            case ZKB_SRC_GAMMA: if (!in.gamma) return fail("gamma is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.gamma);
+            case ZKB_SRC_THETA: if (!in.theta) return fail("theta is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.theta);
+            case ZKB_SRC_Y: if (!in.y) return fail("y is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.y);
             case ZKB_SRC_FIXED: case ZKB_SRC_ADVICE: case ZKB_SRC_INSTANCE: {
                 const uint64_t* cols = s.kind == ZKB_SRC_FIXED ? in.fixed : s.kind == ZKB_SRC_ADVICE ? in.advice : in.instance;
                 const size_t ncols = s.kind == ZKB_SRC_FIXED ? in.num_fixed : s.kind == ZKB_SRC_ADVICE ? in.num_advice : in.num_instance;
-                if (s.index >= ncols) return fail("column out of range");
-                if (s.rotation >= g.num_rotations) return fail("rotation index out of range");
+                if (s.index >= ncols) return fail("column out of range", i);
+                if (s.rotation >= g.num_rotations) return fail("rotation index out of range", i);
                 const uint64_t h = cols[s.index];
                 auto it = poly_ix.find(h);
                 uint32_t id;
@@ -188,43 +177,131 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
                     plan.poly_handles.push_back(h);
                     poly_ix[h] = id;
                 } else id = it->second;
-                if (id >= G_MAX_INDEX) return fail("too many polynomials");
+                if (id >= G_MAX_INDEX) return fail("too many polynomials", i);
                 return G_POLY << 30 | s.rotation << 20 | id;
             }
             case ZKB_SRC_PREVIOUS: plan.uses_prev = true; return G_PREV << 30;
-            default: return fail("unknown value source");
+            default: return fail("unknown value source", i);
         }
     };
-
-    plan.prog.reserve(nc);
     for (size_t i = 0; i < nc; ++i) {
         const zkb_calculation& c = calcs[i];
-        const uint32_t nop = graph_num_operands(c.op);
+        Node& n = nodes[i];
+        n.op = c.op;
+        n.nop = graph_num_operands(c.op);
+        n.live = false;
+        if (n.nop == 0) return "unknown calculation at " + std::to_string(i);
+        if (c.target >= ni) return "calculation " + std::to_string(i) + " writes an intermediate out of range";
         const zkb_value_source* s[3] = {&c.a, &c.b, &c.c};
-        GraphInstrWord w{0, 0, 0, 0};
-        uint32_t* dst[3] = {&w.a, &w.b, &w.c};
-        for (uint32_t k = 0; k < nop; ++k) *dst[k] = operand(*s[k], i);
-        if (!err.empty()) return err;
-        // operands are in registers before the store: intermediates read here for the last time give their slot back first
-        for (uint32_t k = 0; k < nop; ++k)
-            if (s[k]->kind == ZKB_SRC_INTERMEDIATE && s[k]->index != c.target && last_read[s[k]->index] == (int64_t)i &&
-                slot_of[s[k]->index] >= 0) {
-                free_slots.push_back((uint32_t)slot_of[s[k]->index]);
-                slot_of[s[k]->index] = -1;
+        for (uint32_t k = 0; k < 3; ++k) { n.word[k] = 0; n.val[k] = -1; }
+        for (uint32_t k = 0; k < n.nop; ++k) {
+            if (s[k]->kind == ZKB_SRC_INTERMEDIATE) {
+                if (s[k]->index >= ni) return "calculation " + std::to_string(i) + " reads an intermediate out of range";
+                if (cur_val[s[k]->index] < 0) return "intermediate read before it is written (calculation " + std::to_string(i) + ")";
+                n.val[k] = cur_val[s[k]->index];
+            } else {
+                n.word[k] = operand(*s[k], i);
             }
-        if (slot_of[c.target] < 0) {
-            if (!free_slots.empty()) { slot_of[c.target] = (int32_t)free_slots.back(); free_slots.pop_back(); }
-            else slot_of[c.target] = (int32_t)plan.nslots++;
         }
-        w.op_slot = c.op | (uint32_t)slot_of[c.target] << 8;
-        plan.prog.push_back(w);
-        if (last_read[c.target] <= (int64_t)i) {  // never read again: the value is dead (or re-written later)
-            free_slots.push_back((uint32_t)slot_of[c.target]);
-            slot_of[c.target] = -1;
+        if (!err.empty()) return err;
+        cur_val[c.target] = (int32_t)i;
+    }
+    if (nc == 0) return "";
+    const int32_t result_val = (int32_t)nc - 1;
+
+    // ---- dead values (never reach the result) are not computed --------------------------------------------------------------------
+    nodes[result_val].live = true;
+    for (size_t i = nc; i-- > 0;)
+        if (nodes[i].live)
+            for (uint32_t k = 0; k < nodes[i].nop; ++k)
+                if (nodes[i].val[k] >= 0) nodes[nodes[i].val[k]].live = true;
+    plan.uses_prev = false;
+    for (size_t i = 0; i < nc; ++i)
+        if (nodes[i].live)
+            for (uint32_t k = 0; k < nodes[i].nop; ++k)
+                if (nodes[i].val[k] < 0 && nodes[i].word[k] >> 30 == G_PREV) plan.uses_prev = true;
+
+    // ---- order + slots.  emit(order) assigns slots by liveness: a value's slot is released at its last reader, before the reader's
+    // own result is placed (operands are in registers before the store).  Two orders are tried: the graph's own, and a list
+    // schedule that, among the ready calculations, prefers the one releasing the most values (ties: the graph's order) — upstream
+    // computes every gate first and folds them with Horner afterwards, which keeps one value per gate alive; folding each gate as
+    // soon as it is complete needs only the deepest gate's values.  The order with fewer slots is used.
+    std::vector<uint32_t> uses(nc, 0);
+    for (size_t i = 0; i < nc; ++i)
+        if (nodes[i].live)
+            for (uint32_t k = 0; k < nodes[i].nop; ++k)
+                if (nodes[i].val[k] >= 0) ++uses[nodes[i].val[k]];
+    auto emit = [&](const std::vector<uint32_t>& order, std::vector<GraphInstrWord>* prog, uint32_t* result_slot) {
+        std::vector<uint32_t> left(uses);
+        std::vector<int32_t> slot_of(nc, -1);
+        std::vector<uint32_t> free_slots;
+        uint32_t nslots = 0;
+        for (uint32_t i : order) {
+            const Node& n = nodes[i];
+            GraphInstrWord w{0, 0, 0, 0};
+            uint32_t* dst[3] = {&w.a, &w.b, &w.c};
+            for (uint32_t k = 0; k < n.nop; ++k) *dst[k] = n.val[k] >= 0 ? (G_SLOT << 30 | (uint32_t)slot_of[n.val[k]]) : n.word[k];
+            for (uint32_t k = 0; k < n.nop; ++k)
+                if (n.val[k] >= 0 && --left[n.val[k]] == 0) free_slots.push_back((uint32_t)slot_of[n.val[k]]);
+            if (!free_slots.empty()) { slot_of[i] = (int32_t)free_slots.back(); free_slots.pop_back(); }
+            else slot_of[i] = (int32_t)nslots++;
+            w.op_slot = n.op | (uint32_t)slot_of[i] << 8;
+            if (prog) prog->push_back(w);
+        }
+        if (result_slot) *result_slot = (uint32_t)slot_of[result_val];
+        return nslots;
+    };
+    std::vector<uint32_t> natural;
+    for (size_t i = 0; i < nc; ++i)
+        if (nodes[i].live) natural.push_back((uint32_t)i);
+    std::vector<uint32_t> best = natural;
+    uint32_t best_slots = emit(natural, nullptr, nullptr);
+    if (natural.size() <= 8192 && best_slots > 2) {
+        std::vector<uint32_t> left(uses), pending(nc, 0), sched;
+        std::vector<std::vector<uint32_t>> readers(nc);
+        for (uint32_t i : natural) {
+            const Node& n = nodes[i];
+            for (uint32_t k = 0; k < n.nop; ++k)
+                if (n.val[k] >= 0) {
+                    bool dup = false;
+                    for (uint32_t q = 0; q < k; ++q) dup |= n.val[q] == n.val[k];
+                    if (!dup) { ++pending[i]; readers[n.val[k]].push_back(i); }
+                }
+        }
+        std::vector<uint32_t> ready;
+        for (uint32_t i : natural)
+            if (pending[i] == 0) ready.push_back(i);
+        while (!ready.empty()) {
+            size_t pick = 0;
+            int pick_score = -100;
+            for (size_t r = 0; r < ready.size(); ++r) {
+                const Node& n = nodes[ready[r]];
+                int kills = 0;
+                for (uint32_t k = 0; k < n.nop; ++k)
+                    if (n.val[k] >= 0) {
+                        uint32_t same = 0;
+                        for (uint32_t q = 0; q < n.nop; ++q) same += n.val[q] == n.val[k];
+                        bool first = true;
+                        for (uint32_t q = 0; q < k; ++q) first &= n.val[q] != n.val[k];
+                        if (first && left[n.val[k]] == same) ++kills;
+                    }
+                if (kills > pick_score || (kills == pick_score && ready[r] < ready[pick])) { pick = r; pick_score = kills; }
+            }
+            const uint32_t i = ready[pick];
+            ready.erase(ready.begin() + (long)pick);
+            sched.push_back(i);
+            for (uint32_t k = 0; k < nodes[i].nop; ++k)
+                if (nodes[i].val[k] >= 0) --left[nodes[i].val[k]];
+            for (uint32_t r : readers[i])
+                if (--pending[r] == 0) ready.push_back(r);
+        }
+        if (sched.size() == natural.size()) {
+            const uint32_t s2 = emit(sched, nullptr, nullptr);
+            if (s2 < best_slots) { best = sched; best_slots = s2; }
         }
     }
-    (void)error_at;
-    if (nc) plan.result_slot = (uint32_t)slot_of[calcs[nc - 1].target];
+    plan.prog.reserve(best.size());
+    plan.nslots = emit(best, &plan.prog, &plan.result_slot);
     if (plan.nslots >= (1u << 20)) return "too many live intermediates";
     return "";
 }
