@@ -127,11 +127,11 @@ def golden_cases():
     return cases
 
 
-def permutation_term_graph(ncols):
+def permutation_term_graph(ncols, fold=False):
     """One chunk of the permutation argument's h(X) term, written directly as calculations over value sources:
         l_active * ( z(wX) * prod_i (col_i + beta * sigma_i + gamma)  -  z(X) * prod_i (col_i + delta^i * beta * X + gamma) )
     fixed columns: 0 = l_active, 1 = coset of X, 2 .. 2+ncols-1 = sigma cosets; advice: 0 = z, 1 .. ncols = the columns;
-    constants carry delta^i.  -> (graph, delta)"""
+    constants carry delta^i.  fold: the term is folded into the previous value with y.  -> (graph, delta)"""
     V = ev.ValueSource
     g = ev.GraphEvaluator()
     r0, r1 = g.add_rotation(0), g.add_rotation(1)
@@ -148,5 +148,7 @@ def permutation_term_graph(ncols):
         u = g.add_calculation(ev.MUL, bx, g.add_constant(pow(delta, i, P)))
         u = g.add_calculation(ev.ADD, g.add_calculation(ev.ADD, col, u), gamma)
         right = g.add_calculation(ev.MUL, right, u)
-    g.add_calculation(ev.MUL, g.add_calculation(ev.SUB, left, right), V(ev.FIXED, 0, r0))
+    term = g.add_calculation(ev.MUL, g.add_calculation(ev.SUB, left, right), V(ev.FIXED, 0, r0))
+    if fold:   # h = h * y + term, as evaluate_h folds every term into the running value
+        g.add_horner(V(ev.PREVIOUS), [term], V(ev.Y))
     return g, delta

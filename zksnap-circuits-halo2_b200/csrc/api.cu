@@ -27,6 +27,8 @@ Ctx& ctx() {
     return c;
 }
 
+void poly_pool_flush();  // poly.cu
+
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return ZKB_OK;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
@@ -36,6 +38,11 @@ int DevBuf::reserve(size_t bytes) {
         cudaGetLastError();
         e = cudaMalloc(&p, bytes);
         want = bytes;
+    }
+    if (e != cudaSuccess) {  // give back the cached polynomial buffers (poly.cu) and try once more
+        cudaGetLastError();
+        poly_pool_flush();
+        e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -5,6 +5,7 @@
 //   commit_lagrange -> lagrange_to_coeff -> coeff_to_extended -> eval_polynomial -> kate_division -> commit
 // into device-only steps: one upload per polynomial, 96-byte commitments and 32-byte evaluations coming back
 // (coset-resident pipeline, eval / division helpers, proving-key residency).
+#include <cstdlib>
 #include <cstring>
 
 #include "msm_host.hpp"
@@ -194,6 +195,59 @@ static std::map<uint64_t, Poly*>& poly_map() {
 }
 static uint64_t g_next_poly = 1;
 
+// Buffer pool.  The prover allocates and frees polynomials of two or three sizes (2^k, 2^extended_k) all the time, and
+// cudaMalloc / cudaFree of half a gigabyte cost a device synchronisation each.  Freed buffers are kept (up to a quarter of the
+// device memory, ZKB_POLY_POOL_MB overrides, 0 disables) and handed out again; every polynomial op runs on the library stream,
+// so reuse is ordered after the last use.  Any failed allocation in the library empties the pool and retries (DevBuf::reserve).
+struct PolyPool {
+    std::multimap<size_t, void*> free;  // capacity -> buffer
+    size_t bytes = 0;
+    size_t limit = ~(size_t)0;          // resolved on first use
+};
+static PolyPool& poly_pool() {
+    static PolyPool p;
+    return p;
+}
+void poly_pool_flush() {
+    PolyPool& pool = poly_pool();
+    for (auto& kv : pool.free) cudaFree(kv.second);
+    pool.free.clear();
+    pool.bytes = 0;
+}
+static size_t poly_pool_limit() {
+    PolyPool& pool = poly_pool();
+    if (pool.limit == ~(size_t)0) {
+        const char* e = getenv("ZKB_POLY_POOL_MB");
+        size_t fr = 0, total = 0;
+        if (e) pool.limit = (size_t)strtoull(e, nullptr, 10) << 20;
+        else pool.limit = cudaMemGetInfo(&fr, &total) == cudaSuccess ? total / 4 : 0;
+    }
+    return pool.limit;
+}
+static int pool_alloc(DevBuf& b, size_t bytes) {
+    PolyPool& pool = poly_pool();
+    auto it = pool.free.lower_bound(bytes);
+    if (it != pool.free.end() && it->first <= bytes + bytes / 4 + 4096) {
+        b.p = it->second;
+        b.cap = it->first;
+        pool.bytes -= it->first;
+        pool.free.erase(it);
+        return ZKB_OK;
+    }
+    return b.reserve(bytes);
+}
+static void pool_release(DevBuf& b) {
+    PolyPool& pool = poly_pool();
+    if (b.p && pool.bytes + b.cap <= poly_pool_limit()) {
+        pool.free.emplace(b.cap, b.p);
+        pool.bytes += b.cap;
+        b.p = nullptr;
+        b.cap = 0;
+        return;
+    }
+    b.release();
+}
+
 static int find_poly(uint64_t h, Poly** out) {
     auto it = poly_map().find(h);
     if (it == poly_map().end()) { set_error("unknown polynomial handle %llu", (unsigned long long)h); return ZKB_ERR_HANDLE; }
@@ -203,7 +257,7 @@ static int find_poly(uint64_t h, Poly** out) {
 static int new_poly(uint64_t n, Poly** out, uint64_t* handle) {
     Poly* p = new Poly();
     p->n = n;
-    int rc = p->buf.reserve(n ? n * 32 : 32);
+    int rc = pool_alloc(p->buf, n ? n * 32 : 32);
     if (rc != ZKB_OK) { delete p; return rc; }
     *handle = g_next_poly++;
     poly_map()[*handle] = p;
@@ -213,6 +267,7 @@ static int new_poly(uint64_t n, Poly** out, uint64_t* handle) {
 void poly_release_all() {
     for (auto& kv : poly_map()) { kv.second->buf.release(); delete kv.second; }
     poly_map().clear();
+    poly_pool_flush();
     PolyWs& w = poly_ws();
     w.tmp.release();
     graph_ws().release();
@@ -279,8 +334,8 @@ int zkb_poly_free(uint64_t handle) {
     Poly* p;
     ZKB_TRY(find_poly(handle, &p));
     cudaSetDevice(ctx().device);
-    cudaStreamSynchronize(ctx().stream);
-    p->buf.release();
+    if (poly_pool_limit() == 0) cudaStreamSynchronize(ctx().stream);
+    pool_release(p->buf);  // stream-ordered reuse; a buffer that does not fit in the pool is cudaFree'd (which synchronises)
     delete p;
     poly_map().erase(handle);
     return ZKB_OK;
@@ -324,7 +379,7 @@ int zkb_poly_coeff_to_extended(uint64_t poly, uint32_t k, uint32_t extended_k, u
     Poly* e;
     ZKB_TRY(new_poly(N, &e, out_handle));
     int rc = domain_dev_by_op(3, p->buf.as<uint4>(), e->buf.as<uint4>(), w.tmp.as<uint4>(), 1, k, extended_k, ctx().stream);
-    if (rc != ZKB_OK) { e->buf.release(); delete e; poly_map().erase(*out_handle); *out_handle = 0; }
+    if (rc != ZKB_OK) { pool_release(e->buf); delete e; poly_map().erase(*out_handle); *out_handle = 0; }
     return rc;
 }
 
@@ -358,7 +413,7 @@ int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_han
     Poly* q;
     ZKB_TRY(new_poly(p->n, &q, out_handle));  // Q_0 .. Q_{n-1}; the quotient is the first n-1 of them (Q_{n-1} = 0)
     int rc = kate_q_dev(p->buf.as<uint4>(), p->n, fr_of(b), q->buf.as<uint4>(), w.tmp.as<uint4>(), ctx().stream);
-    if (rc != ZKB_OK) { q->buf.release(); delete q; poly_map().erase(*out_handle); *out_handle = 0; return rc; }
+    if (rc != ZKB_OK) { pool_release(q->buf); delete q; poly_map().erase(*out_handle); *out_handle = 0; return rc; }
     q->n = p->n - 1;  // upstream returns a.len() - 1 coefficients
     return ZKB_OK;
 }
