@@ -434,7 +434,8 @@ def main():
                     "value": world * rows / (qms * 1e-3), "unit": "rows/s", "ms_per_step": qms, "parity_checked": bool(q_ok),
                     "lowered": info, "modmul_per_row": 3 * qc,
                     "roofline": {"bound": "hbm", "achieved": qgbs, "peak": hbm_peak, "unit": "GB/s", "frac": qgbs / hbm_peak,
-                                 "traffic": None, "note": "32 B x (polynomials read + previous value + result) per row; integer-issue bound, see DESIGN.md"}}
+                                 "traffic": 5.362e9 if (QUOT_LOG_N, QUOT_COLS) == (24, 4) else None,   # ncu, profiles/r1d_graph_ncu.txt
+                                 "note": "32 B x (polynomials read + previous value + result) per row; integer-issue bound, see DESIGN.md"}}
         parity = parity and bool(q_ok)
         for p_ in adv + sel + [vals]:
             p_.free()

@@ -152,3 +152,75 @@ def permutation_term_graph(ncols, fold=False):
     if fold:   # h = h * y + term, as evaluate_h folds every term into the running value
         g.add_horner(V(ev.PREVIOUS), [term], V(ev.Y))
     return g, delta
+
+
+def lookup_terms_graph(input_exprs, table_exprs, z_col, a_perm_col, s_perm_col):
+    """The five h(X) terms of one lookup argument as ONE graph, each folded into the previous value with y:
+        l_0 (1 - z)                 l_last (z^2 - z)
+        l_active ( z(wX) (A' + beta) (S' + gamma) - z(X) (A + beta) (S + gamma) )
+        l_0 (A' - S')               l_active (A' - S') (A' - A'(w^-1 X))
+    A, S = the input / table expressions compressed with theta (Horner), as upstream's lookup GraphEvaluator computes them.
+    fixed columns: 0 = l_0, 1 = l_last, 2 = l_active; advice columns z_col, a_perm_col, s_perm_col hold z, A', S'."""
+    V = ev.ValueSource
+    g = ev.GraphEvaluator()
+    theta, beta, gamma = V(ev.THETA), V(ev.BETA), V(ev.GAMMA)
+    one = g.add_constant(1)
+
+    def compress(exprs):
+        parts = [g.add_expression(e) for e in exprs]
+        return g.add_horner(g.add_constant(0), parts, theta)
+
+    A, S = compress(input_exprs), compress(table_exprs)
+    r0, r1, rm1 = g.add_rotation(0), g.add_rotation(1), g.add_rotation(-1)
+    l0, llast, lact = V(ev.FIXED, 0, r0), V(ev.FIXED, 1, r0), V(ev.FIXED, 2, r0)
+    z, zw = V(ev.ADVICE, z_col, r0), V(ev.ADVICE, z_col, r1)
+    ap, apm, sp = V(ev.ADVICE, a_perm_col, r0), V(ev.ADVICE, a_perm_col, rm1), V(ev.ADVICE, s_perm_col, r0)
+    c = g.add_calculation
+    t1 = c(ev.MUL, l0, c(ev.SUB, one, z))
+    t2 = c(ev.MUL, llast, c(ev.SUB, c(ev.SQUARE, z), z))
+    left = c(ev.MUL, c(ev.MUL, zw, c(ev.ADD, ap, beta)), c(ev.ADD, sp, gamma))
+    right = c(ev.MUL, c(ev.MUL, z, c(ev.ADD, A, beta)), c(ev.ADD, S, gamma))
+    t3 = c(ev.MUL, lact, c(ev.SUB, left, right))
+    d = c(ev.SUB, ap, sp)
+    t4 = c(ev.MUL, l0, d)
+    t5 = c(ev.MUL, lact, c(ev.MUL, d, c(ev.SUB, ap, apm)))
+    g.add_horner(V(ev.PREVIOUS), [t1, t2, t3, t4, t5], V(ev.Y))
+    return g
+
+
+def lookup_terms_expected(input_exprs, table_exprs, z_col, a_perm_col, s_perm_col, cols, theta, beta, gamma, y, prev, rot_scale, isize):
+    """The same five terms from their formulas with Python integers."""
+    out = []
+    for i in range(isize):
+        def comp(exprs):
+            v = 0
+            for e in exprs:
+                v = (v * theta + eval_expr(e, cols, [], i, rot_scale, isize)) % P
+            return v
+        A, S = comp(input_exprs), comp(table_exprs)
+        adv, fx = cols["advice"], cols["fixed"]
+        z, zw = adv[z_col][i], adv[z_col][(i + rot_scale) % isize]
+        ap, apm, sp = adv[a_perm_col][i], adv[a_perm_col][(i - rot_scale) % isize], adv[s_perm_col][i]
+        l0, llast, lact = fx[0][i], fx[1][i], fx[2][i]
+        terms = [l0 * (1 - z), llast * (z * z - z),
+                 lact * (zw * (ap + beta) * (sp + gamma) - z * (A + beta) * (S + gamma)),
+                 l0 * (ap - sp), lact * (ap - sp) * (ap - apm)]
+        v = prev[i]
+        for t in terms:
+            v = (v * y + t) % P
+        out.append(v)
+    return out
+
+
+def lookup_case(seed, isize, rot_scale):
+    rnd = random.Random(seed)
+    cols = {"fixed": [[rnd.randrange(P) for _ in range(isize)] for _ in range(4)],      # l_0, l_last, l_active, a table column
+            "advice": [[rnd.randrange(P) for _ in range(isize)] for _ in range(5)],     # two inputs, z, A', S'
+            "instance": []}
+    inputs = [("advice", 0, 0), ("prod", ("advice", 1, 0), ("advice", 0, 1))]
+    table = [("fixed", 3, 0), ("scaled", ("fixed", 3, -1), 3)]
+    sc = dict(theta=rnd.randrange(P), beta=rnd.randrange(P), gamma=rnd.randrange(P), y=rnd.randrange(P))
+    prev = [rnd.randrange(P) for _ in range(isize)]
+    g = lookup_terms_graph(inputs, table, 2, 3, 4)
+    want = lookup_terms_expected(inputs, table, 2, 3, 4, cols, sc["theta"], sc["beta"], sc["gamma"], sc["y"], prev, rot_scale, isize)
+    return g, cols, sc, prev, want

@@ -964,3 +964,12 @@ def test_graph_evaluate_full_size_gate(oracle):
     g.evaluate(v, fixed=[Q], advice=[A], y=y, rot_scale=rs)
     got = v.to_host()
     assert (got == oracle.vec_op("fr", "add", oracle.vec_op("fr", "mul", outs[0], np.tile(y, (isize, 1))), outs[1])).all()
+
+
+def test_graph_lookup_terms_vs_definition():
+    g, cols, sc, prev, want = GC.lookup_case(93, 1 << 10, 4)
+    values = zkb.Polynomial(GC.mont(prev))
+    g.evaluate(values, [zkb.Polynomial(GC.mont(c)) for c in cols["fixed"]], [zkb.Polynomial(GC.mont(c)) for c in cols["advice"]],
+               beta=GC.mont([sc["beta"]])[0], gamma=GC.mont([sc["gamma"]])[0], theta=GC.mont([sc["theta"]])[0], y=GC.mont([sc["y"]])[0],
+               rot_scale=4)
+    assert GC.unmont(values.to_host()) == want

@@ -369,3 +369,13 @@ def test_graph_permutation_term_oracle_vs_definition(oracle):
             right = right * (advice[1 + j][i] + pow(delta, j, R.FR) * beta * fixed[1][i] + gamma) % R.FR
         want.append((left - right) * fixed[0][i] % R.FR)
     assert GC.unmont(got) == want
+
+
+def test_graph_lookup_terms_oracle_vs_definition(oracle):
+    """All five h(X) terms of a lookup argument (theta-compressed input / table, beta, gamma, rotations +1 and -1) as one graph."""
+    g, cols, sc, prev, want = GC.lookup_case(91, 64, 4)
+    got = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations,
+                                [GC.mont(c) for c in cols["fixed"]], [GC.mont(c) for c in cols["advice"]], [], None,
+                                GC.mont([sc["beta"]])[0], GC.mont([sc["gamma"]])[0], GC.mont([sc["theta"]])[0], GC.mont([sc["y"]])[0],
+                                4, GC.mont(prev))
+    assert GC.unmont(got) == want
