@@ -15,7 +15,7 @@ s = random_field(n, 1)
 h = torch.from_numpy(s.view(np.int64)).pin_memory()
 out = np.zeros(12, dtype=np.uint64); outp = out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
 ref = None
-for slices in (1, 2, 0, 0):
+for slices in (1, 2, 0, 0, 3, 4, 6, 8):
     lib.zkb_msm_set_slices(slices)
     for pin in (True, False):
         ptr = ctypes.cast(h.data_ptr(), ctypes.POINTER(ctypes.c_uint64)) if pin else s.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))

@@ -605,11 +605,11 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
 
 // MSM of device scalars against srs[offset .. offset+n), through the window table when available
 static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t* out,
-                       uint32_t ncols = 1, uint32_t phase = MSM_WHOLE) {
+                       uint32_t ncols = 1, uint32_t phase = MSM_WHOLE, cudaEvent_t input_ready = nullptr) {
     if (phase & MSM_LAST) srs->commits += ncols;
     if (srs_table_ready(srs, stream)) {
         MsmTable t{srs->table.as<uint4>() + 4 * offset, srs->n, srs->table_c, srs->table_nwin};
-        return msm_run(d_scalars, nullptr, n, stream, out, &t, ncols, phase);
+        return msm_run(d_scalars, nullptr, n, stream, out, &t, ncols, phase, input_ready);
     }
     if (phase != MSM_WHOLE) { set_error("sliced MSM needs the SRS window table"); return ZKB_ERR_ARG; }
     return msm_run(d_scalars, srs->bases.as<uint4>() + 4 * offset, n, stream, out, nullptr, ncols);
@@ -690,7 +690,7 @@ static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, ev.ev_h2d, 0);
         if (e != cudaSuccess) { set_error("scalar upload failed: %s", cudaGetErrorString(e)); return fail(ZKB_ERR_CUDA); }
         const uint32_t phase = (lo == 0 ? MSM_FIRST : 0u) | (lo + cnt == n ? MSM_LAST : 0u);
-        int rc = msm_srs_dev(srs, offset + lo, h.scalars.as<uint4>() + 2 * lo, cnt, c.stream, out_jac, 1, phase);
+        int rc = msm_srs_dev(srs, offset + lo, h.scalars.as<uint4>() + 2 * lo, cnt, c.stream, out_jac, 1, phase, pinned ? ev.ev_h2d : nullptr);
         if (rc != ZKB_OK) return fail(rc);
     }
     return ZKB_OK;

@@ -1,6 +1,7 @@
 // msm.cu — kernels and host driver of the G1 MSM (see msm.cuh for the algorithm).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "msm_host.hpp"
@@ -159,6 +160,11 @@ int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin,
 
 MsmWorkspace& msm_workspace() {
     static MsmWorkspace w;
+    static bool init = false;
+    if (!init) {
+        init = true;
+        if (const char* e = getenv("ZKB_MSM_OVERLAP")) w.overlap = atoi(e);
+    }
     return w;
 }
 
@@ -169,10 +175,17 @@ void msm_release_workspace() {
     for (auto& b : w.pk) b.release();
     for (auto& b : w.pv) b.release();
     for (auto& b : w.seg) b.release();
-    w.sort_tmp.release();
-    w.counter.release();
+    for (auto& b : w.sort_tmp) b.release();
+    for (auto& b : w.counter) b.release();
     w.buckets.release();
     if (w.h_sums) { cudaFreeHost(w.h_sums); w.h_sums = nullptr; w.h_sums_cap = 0; }
+    if (w.h_cnt) { cudaFreeHost(w.h_cnt); w.h_cnt = nullptr; }
+    if (w.aux) { cudaStreamDestroy(w.aux); w.aux = nullptr; }
+    for (int i = 0; i < 2; ++i) {
+        if (w.ev_sorted[i]) { cudaEventDestroy(w.ev_sorted[i]); w.ev_sorted[i] = nullptr; }
+        if (w.ev_acc[i]) { cudaEventDestroy(w.ev_acc[i]); w.ev_acc[i] = nullptr; }
+        w.acc_pending[i] = false;
+    }
 }
 
 static void xyzz_to_out(const XYZZ& p, uint64_t out[12]) {
@@ -194,7 +207,7 @@ static void xyzz_to_out(const XYZZ& p, uint64_t out[12]) {
 void msm_identity_out(uint64_t out[12]) { xyzz_to_out(XYZZ::identity(), out); }
 
 int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream_t s, uint64_t* out_jac,
-            const MsmTable* table, uint32_t ncols, uint32_t phase) {
+            const MsmTable* table, uint32_t ncols, uint32_t phase, cudaEvent_t input_ready) {
     if (ncols == 0) return ZKB_OK;
     if (phase != MSM_WHOLE && (!table || ncols != 1 || n == 0)) { set_error("sliced MSM needs the SRS window table"); return ZKB_ERR_ARG; }
     if (n == 0) { for (uint32_t k = 0; k < ncols; ++k) msm_identity_out(out_jac + 12 * k); return ZKB_OK; }
@@ -208,19 +221,40 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         return ZKB_ERR_ARG;
     }
 
+    // ---- slices: digits + sort of this slice run on the aux stream (buffer set = slice parity) so that they overlap the previous
+    // slice's accumulation on `s`; the accumulation waits for the sort through an event, and a buffer set is not rewritten before
+    // the accumulation that read it (two slices ago) has finished.
+    if (!w.h_cnt) ZKB_CUDA_TRY(cudaMallocHost(&w.h_cnt, 16));
+    if (phase & MSM_FIRST) { w.slice_ix = 0; w.acc_pending[0] = w.acc_pending[1] = false; }
+    const bool overlap = phase != MSM_WHOLE && w.overlap && input_ready;
+    if (overlap && !w.aux) {
+        ZKB_CUDA_TRY(cudaStreamCreateWithFlags(&w.aux, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            ZKB_CUDA_TRY(cudaEventCreateWithFlags(&w.ev_sorted[i], cudaEventDisableTiming));
+            ZKB_CUDA_TRY(cudaEventCreateWithFlags(&w.ev_acc[i], cudaEventDisableTiming));
+        }
+    }
+    const int set = overlap ? (int)(w.slice_ix++ & 1) : 0;
+    cudaStream_t sp = overlap ? w.aux : s;   // the prepare stream
+    DevBuf* const keys = &w.keys[2 * set];
+    DevBuf* const vals = &w.vals[2 * set];
     // ---- workspace
     for (int i = 0; i < 2; ++i) {
-        ZKB_TRY(w.keys[i].reserve(total * 4));
-        ZKB_TRY(w.vals[i].reserve(total * 4));
+        ZKB_TRY(keys[i].reserve(total * 4));
+        ZKB_TRY(vals[i].reserve(total * 4));
     }
     size_t sort_bytes = 0;
     {
-        cub::DoubleBuffer<uint32_t> dk(w.keys[0].as<uint32_t>(), w.keys[1].as<uint32_t>());
-        cub::DoubleBuffer<uint32_t> dv(w.vals[0].as<uint32_t>(), w.vals[1].as<uint32_t>());
-        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, s));
+        cub::DoubleBuffer<uint32_t> dk(keys[0].as<uint32_t>(), keys[1].as<uint32_t>());
+        cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
+        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, sp));
     }
-    ZKB_TRY(w.sort_tmp.reserve(sort_bytes));
-    ZKB_TRY(w.counter.reserve(8));
+    ZKB_TRY(w.sort_tmp[set].reserve(sort_bytes));
+    ZKB_TRY(w.counter[set].reserve(8));
+    if (overlap) {
+        ZKB_CUDA_TRY(cudaStreamWaitEvent(sp, input_ready, 0));
+        if (w.acc_pending[set]) ZKB_CUDA_TRY(cudaStreamWaitEvent(sp, w.ev_acc[set], 0));
+    }
     const size_t bucket_bytes = (size_t)g.nbuckets * 128;
     ZKB_TRY(w.buckets.reserve(phase == MSM_WHOLE ? bucket_bytes : 2 * bucket_bytes));  // sliced: main + scratch array
     uint4* const bucket_main = w.buckets.as<uint4>();
@@ -238,24 +272,24 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
 
     // ---- 1. digits
     {
-        ProfScope prof("msm_digits", s);
+        ProfScope prof("msm_digits", sp);
         MsmDigitArgs a{};
         a.scalars = d_scalars; a.n = n; a.ncols = ncols; a.sets_per_col = g.bucket_sets; a.c = g.c; a.nwin = g.nwin;
-        a.keys = w.keys[0].as<uint32_t>(); a.vals = w.vals[0].as<uint32_t>();
-        a.counter = reinterpret_cast<unsigned long long*>(w.counter.p);
+        a.keys = keys[0].as<uint32_t>(); a.vals = vals[0].as<uint32_t>();
+        a.counter = reinterpret_cast<unsigned long long*>(w.counter[set].p);
         a.invalid_key = g.invalid_key;
         a.table_mode = table ? 1 : 0;
         a.row_stride = table ? table->row_stride : 0;
-        ZKB_CUDA_TRY(cudaMemsetAsync(w.counter.p, 0, 8, s));
+        ZKB_CUDA_TRY(cudaMemsetAsync(w.counter[set].p, 0, 8, sp));
         const unsigned nb = blocks_for(n * ncols, 256);
         const size_t sm = (size_t)g.nwin * 32 * 2 * 4 * 8;
         switch (g.nwin <= MSM_DIGIT_STAGE_WINDOWS ? g.c : 0u) {  // the window widths large MSMs use are compiled in
-#define ZKB_DIGITS_CASE(C) case C: msm_digits_kernel<true, C><<<nb, 256, sm, s>>>(a); break;
+#define ZKB_DIGITS_CASE(C) case C: msm_digits_kernel<true, C><<<nb, 256, sm, sp>>>(a); break;
             ZKB_DIGITS_CASE(16) ZKB_DIGITS_CASE(17) ZKB_DIGITS_CASE(18) ZKB_DIGITS_CASE(19)
             ZKB_DIGITS_CASE(20) ZKB_DIGITS_CASE(21) ZKB_DIGITS_CASE(22)
 #undef ZKB_DIGITS_CASE
-            case 0: msm_digits_kernel<false, 0><<<nb, 256, 0, s>>>(a); break;
-            default: msm_digits_kernel<true, 0><<<nb, 256, sm, s>>>(a); break;
+            case 0: msm_digits_kernel<false, 0><<<nb, 256, 0, sp>>>(a); break;
+            default: msm_digits_kernel<true, 0><<<nb, 256, sm, sp>>>(a); break;
         }
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
@@ -263,23 +297,27 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
     // the number of non-zero digits decides the size of everything downstream (a witness column has few)
     uint64_t valid = 0;
     {
-        unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(w.h_sums);
-        ZKB_CUDA_TRY(cudaMemcpyAsync(h_cnt, w.counter.p, 8, cudaMemcpyDeviceToHost, s));
-        ZKB_CUDA_TRY(cudaStreamSynchronize(s));
+        unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(w.h_cnt) + set;
+        ZKB_CUDA_TRY(cudaMemcpyAsync(h_cnt, w.counter[set].p, 8, cudaMemcpyDeviceToHost, sp));
+        ZKB_CUDA_TRY(cudaStreamSynchronize(sp));   // overlap: waits for this slice's digits only, not for the accumulation on `s`
         valid = *h_cnt;
     }
     // ---- 2. sort
     const uint32_t* sk;
     const uint32_t* sv;
     {
-        ProfScope prof("msm_sort", s);
-        cub::DoubleBuffer<uint32_t> dk(w.keys[0].as<uint32_t>(), w.keys[1].as<uint32_t>());
-        cub::DoubleBuffer<uint32_t> dv(w.vals[0].as<uint32_t>(), w.vals[1].as<uint32_t>());
+        ProfScope prof("msm_sort", sp);
+        cub::DoubleBuffer<uint32_t> dk(keys[0].as<uint32_t>(), keys[1].as<uint32_t>());
+        cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
         uint32_t kb = 1;  // keys are < nbuckets now (no "invalid" key)
         while ((1ull << kb) < g.nbuckets) ++kb;
-        if (valid) ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp.p, sort_bytes, dk, dv, (int)valid, 0, (int)kb, s));
+        if (valid) ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp[set].p, sort_bytes, dk, dv, (int)valid, 0, (int)kb, sp));
         sk = dk.Current();
         sv = dv.Current();
+    }
+    if (overlap) {
+        ZKB_CUDA_TRY(cudaEventRecord(w.ev_sorted[set], sp));
+        ZKB_CUDA_TRY(cudaStreamWaitEvent(s, w.ev_sorted[set], 0));
     }
     uint32_t chunk0 = g.chunk0;
     if (!c.msm_chunk_override)
@@ -328,6 +366,10 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         msm_merge_kernel<<<blocks_for(g.nbuckets, 128), 128, 0, s>>>(m);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
+    }
+    if (overlap) {
+        ZKB_CUDA_TRY(cudaEventRecord(w.ev_acc[set], s));
+        w.acc_pending[set] = true;
     }
     if (!(phase & MSM_LAST)) return ZKB_OK;
     // ---- 4. bucket reduction: one weighted sum per bucket set
