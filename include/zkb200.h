@@ -113,6 +113,12 @@ int zkb_srs_download(uint64_t handle, uint64_t* bases_out, size_t n);
 /* best_fft with G = G1 (halo2's FftGroup impl for curve points): out[i] = sum_j [omega^(i j)] P_j, affine in / affine out,
  * log_n <= 26.  zkb_srs_g_to_lagrange is halo2_proofs::arithmetic::g_to_lagrange on a resident SRS: g_lagrange =
  * (1/n) * inverse G1 FFT of g[..2^k] — for params read from a file that carries only the monomial basis. */
+/* SRS file -> HBM without a host copy of the arrays: n raw G1Affine (64 B each, Montgomery limbs — the element encoding of
+ * halo2's SerdeFormat::RawBytes / RawBytesUnchecked) are read from `path` at byte `offset` through two pinned staging buffers
+ * and registered as an SRS handle.  check_points != 0 verifies on the device that every point is the identity or has canonical
+ * coordinates on y^2 = x^3 + 3 (what RawBytes checks and RawBytesUnchecked skips).  The container layout (ParamsKZG::write:
+ * u32 k, g[2^k], g_lagrange[2^k], then the G2 elements) stays with the caller, who passes the offsets. */
+int zkb_srs_load_file(const char* path, uint64_t offset, size_t n, int check_points, uint64_t* handle);
 int zkb_g1_ntt(const uint64_t* points_affine, uint64_t* out_affine, const uint64_t omega[4], uint32_t log_n);
 int zkb_srs_g_to_lagrange(uint64_t handle_g, uint32_t k, uint64_t* handle_g_lagrange);
 

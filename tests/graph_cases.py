@@ -224,3 +224,45 @@ def lookup_case(seed, isize, rot_scale):
     g = lookup_terms_graph(inputs, table, 2, 3, 4)
     want = lookup_terms_expected(inputs, table, 2, 3, 4, cols, sc["theta"], sc["beta"], sc["gamma"], sc["y"], prev, rot_scale, isize)
     return g, cols, sc, prev, want
+
+
+def random_program(seed, max_len=60):
+    """A raw calculation list over 1 fixed + 2 advice columns and beta / gamma / theta / y / previous value: intermediates are
+    re-written, Stores copy intermediates, some values are dead, Horner steps appear anywhere.  -> (graph, rot_scale)"""
+    V = ev.ValueSource
+    rnd = random.Random(seed)
+    rs = rnd.choice([1, 2, 4])
+    g = ev.GraphEvaluator()
+    for r in (0, 1, -1, 3):
+        g.add_rotation(r)
+    for _ in range(3):
+        g.add_constant(rnd.randrange(P))
+    nint = rnd.randrange(2, 9)
+    g.num_intermediates = nint
+    written = []
+
+    def src():
+        k = rnd.randrange(10)
+        if k < 4 and written:
+            return V(ev.INTERMEDIATE, rnd.choice(written))
+        if k < 6:
+            return V(ev.ADVICE, rnd.randrange(2), rnd.randrange(4))
+        if k == 6:
+            return V(ev.FIXED, 0, rnd.randrange(4))
+        if k == 7:
+            return V(ev.CONSTANT, rnd.randrange(len(g.constants)))
+        if k == 8:
+            return V(rnd.choice([ev.BETA, ev.GAMMA, ev.THETA, ev.Y]))
+        return V(ev.PREVIOUS)
+
+    z = V(ev.CONSTANT, 0)
+    for _ in range(rnd.randrange(1, max_len)):
+        op = rnd.choice([ev.ADD, ev.SUB, ev.MUL, ev.MUL, ev.SQUARE, ev.DOUBLE, ev.NEGATE, ev.STORE, ev.STORE, ev.MUL_ADD])
+        t = rnd.randrange(nint)
+        a, b, c = src(), src(), src()
+        if op == ev.MUL_ADD and t in written and rnd.random() < 0.7:
+            a = V(ev.INTERMEDIATE, t)     # a Horner step
+        g.calculations.append((op, t, a, b if op in (ev.ADD, ev.SUB, ev.MUL, ev.MUL_ADD) else z, c if op == ev.MUL_ADD else z))
+        if t not in written:
+            written.append(t)
+    return g, rs

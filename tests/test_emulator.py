@@ -484,48 +484,13 @@ def test_graph_lowering_random_programs(oracle, seed):
     Horner steps in odd places — through copy propagation, SSA renaming, dead-value removal, scheduling and slot allocation,
     against the oracle's direct evaluation (one array cell per intermediate, no lowering)."""
     import random
-    ev = GC.ev
-    V = ev.ValueSource
-    rnd = random.Random(1000 + seed)
-    isize, rs = 32, rnd.choice([1, 2, 4])
-    g = ev.GraphEvaluator()
-    for r in (0, 1, -1, 3):
-        g.add_rotation(r)
-    for _ in range(3):
-        g.add_constant(rnd.randrange(R.FR))
-    nint = rnd.randrange(2, 9)
-    g.num_intermediates = nint
-    written = []
-
-    def src():
-        k = rnd.randrange(10)
-        if k < 4 and written:
-            return V(ev.INTERMEDIATE, rnd.choice(written))
-        if k < 6:
-            return V(ev.ADVICE, rnd.randrange(2), rnd.randrange(4))
-        if k == 6:
-            return V(ev.FIXED, 0, rnd.randrange(4))
-        if k == 7:
-            return V(ev.CONSTANT, rnd.randrange(len(g.constants)))
-        if k == 8:
-            return V(rnd.choice([ev.BETA, ev.GAMMA, ev.THETA, ev.Y]))
-        return V(ev.PREVIOUS)
-
-    z = V(ev.CONSTANT, 0)
-    for _ in range(rnd.randrange(1, 60)):
-        op = rnd.choice([ev.ADD, ev.SUB, ev.MUL, ev.MUL, ev.SQUARE, ev.DOUBLE, ev.NEGATE, ev.STORE, ev.STORE, ev.MUL_ADD])
-        t = rnd.randrange(nint)
-        a, b, c = src(), src(), src()
-        if op == ev.MUL_ADD and t in written and rnd.random() < 0.7:
-            a = V(ev.INTERMEDIATE, t)     # a Horner step
-        g.calculations.append((op, t, a, b if op in (ev.ADD, ev.SUB, ev.MUL, ev.MUL_ADD) else z, c if op == ev.MUL_ADD else z))
-        if t not in written:
-            written.append(t)
+    g, rs = GC.random_program(1000 + seed)
+    isize = 32
     fixed, advice = [random_field(isize, 3000 + seed)], [random_field(isize, 3100 + seed + i) for i in range(2)]
     sc = random_field(4, 3200 + seed)
     prev = random_field(isize, 3300 + seed)
-    want = oracle.graph_evaluate(g.calc_array(), nint, GC.mont(g.constants), g.rotations, fixed, advice, [], None,
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fixed, advice, [], None,
                                  sc[0], sc[1], sc[2], sc[3], rs, prev)
-    rc, out, info = emu.graph_evaluate(g, fixed, advice, [], None, sc[0], sc[1], sc[2], sc[3], rs, prev, rnd.choice([0, 32, 64]))
+    rc, out, info = emu.graph_evaluate(g, fixed, advice, [], None, sc[0], sc[1], sc[2], sc[3], rs, prev, random.Random(seed).choice([0, 32, 64]))
     assert rc == 0 and (out == want).all()
     assert info[0] <= len(g.calculations)

@@ -973,3 +973,35 @@ def test_graph_lookup_terms_vs_definition():
                beta=GC.mont([sc["beta"]])[0], gamma=GC.mont([sc["gamma"]])[0], theta=GC.mont([sc["theta"]])[0], y=GC.mont([sc["y"]])[0],
                rot_scale=4)
     assert GC.unmont(values.to_host()) == want
+
+
+def test_params_read_from_file_into_hbm(oracle, tmp_path):
+    """ParamsKZG::read (RawBytes layout): the SRS goes from the file to HBM through pinned staging; commitments equal those of
+    the params the file was written from; a corrupted point is refused with checks on and accepted unchecked."""
+    k = 10
+    s = random_field(1, 4242)[0]
+    a = zkb.ParamsKZG.setup(k, s)
+    path = str(tmp_path / "kzg_bn254_10.srs")
+    a.write(path)
+    assert os.path.getsize(path) == 4 + 2 * (64 << k) + 256
+    b = zkb.ParamsKZG.read(path)
+    assert b.k == k and (b.get_g() == a.get_g()).all() and (b.get_g_lagrange() == a.get_g_lagrange()).all()
+    poly = random_field(1 << k, 4243)
+    assert (b.commit(poly) == oracle.best_multiexp(poly, a.get_g())).all()
+    assert (b.commit_lagrange(poly) == a.commit_lagrange(poly)).all()
+    b.close()
+    raw = bytearray(open(path, "rb").read())
+    raw[4 + 64 * 17 + 3] ^= 0x40            # one bit of g[17].x
+    open(path, "wb").write(raw)
+    with pytest.raises(zkb.ZkbError):
+        zkb.ParamsKZG.read(path)
+    c = zkb.ParamsKZG.read(path, check_points=False)
+    c.close()
+    raw[4 + 64 * 17: 4 + 64 * 18] = bytes([0xFF]) * 64     # non-canonical limbs
+    open(path, "wb").write(raw)
+    with pytest.raises(zkb.ZkbError):
+        zkb.ParamsKZG.read(path)
+    open(path, "wb").write(raw[:1000])                       # truncated
+    with pytest.raises(zkb.ZkbError):
+        zkb.ParamsKZG.read(path)
+    a.close()

@@ -36,7 +36,7 @@ def main():
     it = 0
     while time.time() < t_end:
         it += 1
-        kind = rng.choice(["ntt", "domain", "msm", "commit", "batch", "poly"])
+        kind = rng.choice(["ntt", "domain", "msm", "commit", "batch", "poly", "graph"])
         counts[kind] = counts.get(kind, 0) + 1
         seed = int(rng.integers(1, 1 << 30))
         if kind == "ntt":
@@ -94,6 +94,29 @@ def main():
                         assert (got[i] == coracle.best_multiexp(c, b)).all(), ("batch", n, nc, i, seed)
                 params.close()
                 lib.zkb_srs_set_precompute(1)
+        elif kind == "graph":
+            # quotient evaluation: a random raw program (re-written intermediates, dead values, Horner steps) or a random gate
+            # set, on a random power-of-two domain, through zkb_graph_evaluate vs the oracle's direct evaluation
+            import graph_cases as GC
+            isize = 1 << int(rng.integers(0, 15))
+            if rng.random() < 0.5:
+                g, rs = GC.random_program(seed, max_len=int(rng.integers(2, 200)))
+                nfix, nadv, nins, chal = 1, 2, 0, None
+            else:
+                c = GC.random_case(seed, 1, 1, ngates=int(rng.integers(1, 12)), depth=int(rng.integers(2, 7)))
+                g, rs, nfix, nadv, nins = c["graph"], int(rng.choice([1, 2, 4, 8])), 2, 3, 1
+                chal = random_field(2, seed + 50)
+            cols = [[random_field(isize, seed + 10 * q + i) for i in range(m)] for q, m in enumerate((nfix, nadv, nins))]
+            sc = random_field(4, seed + 60)
+            prev = random_field(isize, seed + 61)
+            want = coracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, cols[0], cols[1], cols[2],
+                                          chal, sc[0], sc[1], sc[2], sc[3], rs, prev)
+            handles = [[zkb.Polynomial(a) for a in grp] for grp in cols]
+            values = zkb.Polynomial(prev)
+            g.evaluate(values, *handles, challenges=chal, beta=sc[0], gamma=sc[1], theta=sc[2], y=sc[3], rot_scale=rs)
+            assert (values.to_host() == want).all(), ("graph", isize, seed)
+            for p_ in [values] + sum(handles, []):
+                p_.free()
         else:
             n = int(rng.integers(1, 50000))
             a = random_field(n, seed)

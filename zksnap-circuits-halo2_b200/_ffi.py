@@ -48,6 +48,7 @@ def load() -> ctypes.CDLL:
         "zkb_msm_g1": [u64p, u64p, sz, u64p],
         "zkb_srs_register": [u64p, sz, u64p],
         "zkb_srs_release": [u64],
+        "zkb_srs_load_file": [ctypes.c_char_p, u64, sz, ci, u64p],
         "zkb_msm_g1_srs": [u64, u64p, sz, u64p],
         "zkb_msm_g1_srs_range": [u64, sz, u64p, sz, u64p],
         "zkb_msm_g1_srs_batch": [u64, u64pp, sz, sz, u64p],

@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libzkb200.so (include/zkb200.h): context, SRS registry, host-buffer and device-buffer
 // entry points.  No CPU fallback lives here: every compute call requires an initialised CUDA device.
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -816,6 +817,70 @@ int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle) {
     *handle = g_next_handle++;
     srs_map()[*handle] = s;
     return ZKB_OK;
+}
+
+// n raw G1Affine (64 B each, Montgomery limbs — what SerdeFormat::RawBytes / RawBytesUnchecked write) from `path` at byte
+// `offset` straight into HBM: read(2) into one pinned buffer while the other one is in flight to the device.
+int zkb_srs_load_file(const char* path, uint64_t offset, size_t n, int check_points, uint64_t* handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    ZKB_TRY(check_ptr(handle, "handle"));
+    ZKB_TRY(check_ptr(path, "path"));
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s", path); return ZKB_ERR_ARG; }
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    if (fseeko(f, 0, SEEK_END) != 0) { set_error("cannot seek in %s", path); return ZKB_ERR_ARG; }
+    const uint64_t fsize = (uint64_t)ftello(f);
+    if (offset > fsize || (uint64_t)n * 64 > fsize - offset) {
+        set_error("%s holds %llu bytes, %zu points at offset %llu need %llu", path, (unsigned long long)fsize, n,
+                  (unsigned long long)offset, (unsigned long long)(offset + (uint64_t)n * 64));
+        return ZKB_ERR_ARG;
+    }
+    if (fseeko(f, (off_t)offset, SEEK_SET) != 0) { set_error("cannot seek in %s", path); return ZKB_ERR_ARG; }
+    Srs* s = new Srs();
+    s->n = n;
+    int rc = s->bases.reserve(n ? n * 64 : 64);
+    if (rc != ZKB_OK) { delete s; return rc; }
+    const size_t chunk = (size_t)32 << 20;
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = ctx().stream;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; ++i) {
+            if (pin[i]) cudaFreeHost(pin[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+        if (code != ZKB_OK) { s->bases.release(); delete s; }
+        return code;
+    };
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMallocHost(&pin[i], chunk) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pinned staging allocation failed");
+            return cleanup(ZKB_ERR_OOM);
+        }
+    }
+    const size_t total = n * 64;
+    for (size_t done = 0, i = 0; done < total; ++i) {
+        const size_t len = total - done < chunk ? total - done : chunk;
+        if (i >= 2 && cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { set_error("SRS upload failed"); return cleanup(ZKB_ERR_CUDA); }
+        if (fread(pin[i & 1], 1, len, f) != len) { set_error("short read from %s", path); return cleanup(ZKB_ERR_ARG); }
+        cudaError_t e = cudaMemcpyAsync((char*)s->bases.p + done, pin[i & 1], len, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
+        if (e != cudaSuccess) { set_error("SRS upload failed: %s", cudaGetErrorString(e)); return cleanup(ZKB_ERR_CUDA); }
+        done += len;
+    }
+    if (check_points) {
+        uint64_t bad = 0;
+        rc = g1_check_on_curve_dev(s->bases.as<uint4>(), n, &bad, st);
+        if (rc != ZKB_OK) return cleanup(rc);
+        if (bad) { set_error("%s: %llu of %zu points are not on the curve", path, (unsigned long long)bad, n); return cleanup(ZKB_ERR_ARG); }
+    }
+    rc = cleanup(ZKB_OK);
+    *handle = g_next_handle++;
+    srs_map()[*handle] = s;
+    return rc;
 }
 
 int zkb_srs_release(uint64_t handle) {

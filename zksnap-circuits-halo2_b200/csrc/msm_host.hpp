@@ -54,6 +54,7 @@ int g1_fixed_base_window_dev(const uint4* d_scalars, uint64_t n, uint4* d_out, c
 int g1_batch_to_affine_dev(const uint4* d_in, uint64_t n, uint4* d_out, bool jacobian, cudaStream_t s);
 int kzg_setup_dev(uint32_t k, const uint64_t s_mont[4], uint4* d_g, uint4* d_gl, cudaStream_t st);
 int g1_fft_dev(const uint4* d_aff_in, uint4* d_aff_out, uint32_t log_n, const Fr& omega, const Fr* scale, cudaStream_t st);
+int g1_check_on_curve_dev(const uint4* d_aff, uint64_t n, uint64_t* bad, cudaStream_t s);
 void setup_release();
 int measure_imad_peak(double* macs_per_s);
 int g1_sum_host(const uint64_t* pts, size_t count, uint64_t out[12]);

@@ -51,6 +51,35 @@ static SetupWs& setup_ws() {
     static SetupWs w;
     return w;
 }
+__global__ void __launch_bounds__(128) g1_on_curve_kernel(const OnCurveArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i >= a.n || g1_affine_is_valid(affine_load(a.pts + 4 * i));
+    const unsigned bad = __popc(__ballot_sync(0xFFFFFFFFu, !ok));
+    if (bad && (threadIdx.x & 31) == 0) atomicAdd(a.bad, (unsigned long long)bad);
+}
+
+// number of points of d_aff[0..n) that are neither the identity nor canonical points of the curve -> *bad (synchronises `s`)
+int g1_check_on_curve_dev(const uint4* d_aff, uint64_t n, uint64_t* bad, cudaStream_t s) {
+    *bad = 0;
+    if (n == 0) return ZKB_OK;
+    unsigned long long* d_bad = nullptr;
+    ZKB_CUDA_TRY(cudaMalloc(&d_bad, 8));
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, 8, s);
+    if (e == cudaSuccess) {
+        OnCurveArgs a{d_aff, n, d_bad};
+        g1_on_curve_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_bad, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) { set_error("on-curve check failed: %s", cudaGetErrorString(e)); return ZKB_ERR_CUDA; }
+    *bad = h;
+    return ZKB_OK;
+}
+
 void setup_release() {
     SetupWs& w = setup_ws();
     w.table.release(); w.xyzz.release(); w.scalars.release(); w.points.release();

@@ -177,6 +177,20 @@ ZKB_HD void lagrange_scalars_thread(const LagrangeScalarArgs& a, uint64_t t) {
     }
 }
 
+// ---- points read from a file: canonical coordinates on y^2 = x^3 + 3 (or the identity (0, 0)), as SerdeFormat::RawBytes checks ---
+struct OnCurveArgs {
+    const uint4* pts;              // n affine points, 64 B each
+    uint64_t n;
+    unsigned long long* bad;       // number of points that fail
+};
+ZKB_HD bool g1_affine_is_valid(const Affine& p) {
+    if (p.is_identity()) return true;
+    if (!(fp_canon(p.x) == p.x) || !(fp_canon(p.y) == p.y)) return false;   // a limb pattern >= p is not a field element
+    const Fq one = Fq::one();
+    const Fq b = fp_add(fp_add(one, one), one);
+    return fp_sqr(p.y) == fp_add(fp_mul(fp_sqr(p.x), p.x), b);
+}
+
 }  // namespace zkb
 
 // ---- best_fft over G1 (halo2's FftGroup impl for curve points) — used by g_to_lagrange -------------------------------------------

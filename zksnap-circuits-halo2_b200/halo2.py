@@ -325,6 +325,37 @@ class ParamsKZG:
         return self
 
     @classmethod
+    def read(cls, path: str, check_points: bool = True) -> "ParamsKZG":
+        """ParamsKZG::read_custom(reader, SerdeFormat::RawBytes) for the G1 side, straight from the file into HBM
+        (the `kzg_bn254_{k}.srs` files of the reference's demo, /root/reference: app/src/.../worker.js:218-225 and
+        snark-verifier-sdk's gen_srs).  Layout [UPSTREAM-UNVERIFIED: halo2-axiom is not vendored] as ParamsKZG::write_custom
+        writes it: u32 little-endian k, g[2^k], g_lagrange[2^k] as raw 64-byte G1Affine (Montgomery limbs), then g2 and s_g2
+        (raw G2Affine, 128 bytes each), which stay on the host and are not read here.  check_points=False is
+        SerdeFormat::RawBytesUnchecked."""
+        with open(path, "rb") as f:
+            head = f.read(4)
+        if len(head) != 4:
+            raise ValueError("params file too short")
+        k = int.from_bytes(head, "little")
+        if not 0 < k <= 28:
+            raise ValueError(f"params file claims k = {k}")
+        self = cls.__new__(cls)
+        self.k, self.n = k, 1 << k
+        self._h_g, self._h_gl = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(lib().zkb_srs_load_file(path.encode(), 4, self.n, int(check_points), ctypes.byref(self._h_g)))
+        check(lib().zkb_srs_load_file(path.encode(), 4 + self.n * 64, self.n, int(check_points), ctypes.byref(self._h_gl)))
+        return self
+
+    def write(self, path: str, g2: bytes = bytes(128), s_g2: bytes = bytes(128)) -> None:
+        """The same layout back to a file (G2 elements supplied by the caller, who holds them on the host)."""
+        with open(path, "wb") as f:
+            f.write(self.k.to_bytes(4, "little"))
+            f.write(self.get_g().tobytes())
+            f.write(self.get_g_lagrange().tobytes())
+            f.write(g2)
+            f.write(s_g2)
+
+    @classmethod
     def from_g(cls, k: int, g: np.ndarray) -> "ParamsKZG":
         """Params from the monomial basis only (an SRS file without g_lagrange): g_lagrange = g_to_lagrange(g, k) on the
         device (inverse G1 FFT and 1/n)."""
