@@ -1005,3 +1005,31 @@ def test_params_read_from_file_into_hbm(oracle, tmp_path):
     with pytest.raises(zkb.ZkbError):
         zkb.ParamsKZG.read(path)
     a.close()
+
+
+def test_quotient_pipeline_polynomial_identity():
+    """What evaluate_h relies on, end to end on resident polynomials: with A = coeff_to_extended(a), Q = coeff_to_extended(q) and
+    rot_scale = 2^(extended_k - k), the row-wise gate value q (a + a(wX) a(w^2 X) - a(w^3 X)) on the extended coset IS the coset
+    evaluation of that polynomial: extended_to_coeff of the values gives a polynomial G of degree < 3n with
+    G(x) = q(x) (a(x) + a(w x) a(w^2 x) - a(w^3 x)) at a random x (Python integers combine the device evaluations)."""
+    k = 16
+    n = 1 << k
+    d = zkb.EvaluationDomain(4, k)
+    a, q = random_field(n, 9101), random_field(n, 9102)
+    pa, pq = zkb.Polynomial(a), zkb.Polynomial(q)
+    A, Q = pa.coeff_to_extended(d), pq.coeff_to_extended(d)
+    g = GC.build_custom_gates([GC.halo2_base_gate()])
+    values = zkb.Polynomial(np.zeros((d.extended_len(), 4), dtype=np.uint64))
+    g.evaluate(values, fixed=[Q], advice=[A], y=random_field(1, 9103)[0], rot_scale=1 << (d.extended_k - k))
+    values.extended_to_coeff(d)
+    full = values.to_host()
+    G = full[: 3 * n]
+    assert not full[3 * n:].any()        # degree < 3n: the values were the coset evaluations of a low-degree polynomial
+    x = random_field(1, 9104)[0]
+    xi = unmont(x)[0]
+    w = R.omega_for(k)
+    at = [unmont(pa.eval(mont([xi * pow(w, r, R.FR) % R.FR])[0]))[0] for r in range(4)]
+    want = unmont(pq.eval(x))[0] * (at[0] + at[1] * at[2] - at[3]) % R.FR
+    assert unmont(zkb.eval_polynomial(G, x))[0] == want
+    for p in (pa, pq, A, Q, values):
+        p.free()
