@@ -7,6 +7,8 @@
 //   C2 = params.commit(coeffs)                              must equal C1 (same polynomial in the two bases of the SRS)
 //   ext = domain.coeff_to_extended(coeffs)                  evaluate_h input
 //   back = domain.extended_to_coeff(ext)                    h-poly path; must return the coefficients
+//   h = custom_gates.evaluate(...) for every row            evaluate_h on the resident coset (GraphEvaluator), then
+//   extended_to_coeff(h)                                    must have degree < 3n: the rows were a polynomial's coset evaluations
 //
 //   g++ -std=c++17 -O2 -I include examples/prover_ops.cpp -L zksnap-circuits-halo2_b200 -lzkb200 \
 //       -Wl,-rpath,$PWD/zksnap-circuits-halo2_b200 -o examples/prover_ops && examples/prover_ops [k]
@@ -61,10 +63,37 @@ int main(int argc, char** argv) {
             if (back[i] != coeffs[i]) { std::printf("FAIL: extended_to_coeff(coeff_to_extended(p)) != p at %zu\n", i); return 1; }
         for (size_t i = n; i < back.size(); ++i)
             if (back[i] != halo2::Fr{0, 0, 0, 0}) { std::printf("FAIL: non-zero high coefficient %zu\n", i); return 1; }
+        // quotient evaluation on the coset kept in HBM: halo2-base's gate q (a + b c - d), a..d = the advice column at rotations
+        // 0..3, with the column itself standing in for the selector; rot_scale = 2^(extended_k - k)
+        double t_q0 = now_ms();
+        {
+            halo2::Polynomial coset(ext);
+            halo2::Polynomial h = halo2::Polynomial::zeros(domain.extended_len());
+            halo2::GraphEvaluator g;
+            using VS = halo2::ValueSource;
+            const uint32_t r0 = g.add_rotation(0), r1 = g.add_rotation(1), r2 = g.add_rotation(2), r3 = g.add_rotation(3);
+            auto bc = g.add_calculation(ZKB_CALC_MUL, VS::Advice(0, r1), VS::Advice(0, r2));
+            auto sum = g.add_calculation(ZKB_CALC_ADD, VS::Advice(0, r0), bc);
+            auto diff = g.add_calculation(ZKB_CALC_SUB, sum, VS::Advice(0, r3));
+            auto gate = g.add_calculation(ZKB_CALC_MUL, VS::Fixed(0, r0), diff);
+            g.add_horner(VS::PreviousValue(), {gate}, VS::Y());
+            halo2::GraphEvaluator::Scalars sc;
+            sc.y = &s;
+            g.evaluate(h, {&coset}, {&coset}, {}, {}, sc, int32_t(1) << (domain.extended_k() - k));
+            halo2::check(zkb_poly_extended_to_coeff(h.handle(), k, domain.extended_k()), "extended_to_coeff(h)");
+            auto hc = h.to_vec();
+            bool nonzero = false;
+            for (size_t i = 0; i < 3 * n; ++i) nonzero |= hc[i] != halo2::Fr{0, 0, 0, 0};
+            if (!nonzero) { std::printf("FAIL: h is zero\n"); return 1; }
+            for (size_t i = 3 * n; i < hc.size(); ++i)
+                if (hc[i] != halo2::Fr{0, 0, 0, 0}) { std::printf("FAIL: h has degree >= 3n (coefficient %zu)\n", i); return 1; }
+        }
+        const double t_quot = now_ms() - t_q0;
         auto aff = halo2::batch_normalize({c1});
         const char* names[6] = {"setup", "commit_lagrange", "lagrange_to_coeff", "commit", "coeff_to_extended", "extended_to_coeff"};
         std::printf("k=%u ok (commitment x limb0 = %016llx); ms warm (first call):", k, (unsigned long long)aff[0][0]);
-        for (int i = 0; i < 6; ++i) std::printf(" %s %.2f (%.0f)%s", names[i], warm[i], cold[i], i < 5 ? "," : "\n");
+        for (int i = 0; i < 6; ++i) std::printf(" %s %.2f (%.0f),", names[i], warm[i], cold[i]);
+        std::printf(" quotient upload+evaluate+extended_to_coeff+download %.2f\n", t_quot);
     } catch (const std::exception& e) {
         std::printf("error: %s\n", e.what());
         return 2;

@@ -185,6 +185,9 @@ int zkb_poly_alloc(size_t n, uint64_t* handle); /* zero-filled */
 int zkb_poly_len(uint64_t handle, size_t* n);
 int zkb_poly_download(uint64_t handle, uint64_t* out, size_t n);
 int zkb_poly_free(uint64_t handle);
+/* new handle with a copy of poly[offset .. offset + n) — the pieces of h(X) after extended_to_coeff (n coefficients each), which the
+ * prover commits and opens one by one */
+int zkb_poly_slice(uint64_t poly, size_t offset, size_t n, uint64_t* out_handle);
 int zkb_poly_commit(uint64_t srs_handle, uint64_t poly, uint64_t out_jac[12]);
 int zkb_poly_lagrange_to_coeff(uint64_t poly, uint32_t k);
 int zkb_poly_coeff_to_lagrange(uint64_t poly, uint32_t k);

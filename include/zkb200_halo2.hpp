@@ -149,6 +149,7 @@ class Polynomial {
         return out;
     }
     void mul(const Polynomial& other) { check(zkb_poly_mul(h_, other.h_), "mul"); }
+    Polynomial slice(size_t offset, size_t n) const { Polynomial p; check(zkb_poly_slice(h_, offset, n, &p.h_), "slice"); return p; }
 
    private:
     Polynomial() = default;

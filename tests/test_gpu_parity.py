@@ -1033,3 +1033,25 @@ def test_quotient_pipeline_polynomial_identity():
     assert unmont(zkb.eval_polynomial(G, x))[0] == want
     for p in (pa, pq, A, Q, values):
         p.free()
+
+
+def test_h_pieces_sliced_committed_and_opened_on_the_device(oracle):
+    """After the quotient evaluation and extended_to_coeff, h(X) is cut into pieces of n coefficients that are committed and
+    evaluated one by one: Polynomial.slice keeps that in HBM."""
+    k = 10
+    n = 1 << k
+    params = zkb.ParamsKZG.setup(k, random_field(1, 9301)[0])
+    g = params.get_g()
+    h = random_field(4 * n, 9302)
+    H = zkb.Polynomial(h)
+    x = random_field(1, 9303)[0]
+    for i in range(3):
+        piece = H.slice(i * n, n)
+        assert len(piece) == n and (piece.to_host() == h[i * n:(i + 1) * n]).all()
+        assert (piece.commit(params) == oracle.best_multiexp(h[i * n:(i + 1) * n], g)).all()
+        assert (piece.eval(x) == oracle.fr_eval_polynomial(h[i * n:(i + 1) * n], x)).all()
+        piece.free()
+    assert len(H.slice(4 * n, 0)) == 0
+    with pytest.raises(zkb.ZkbError):
+        H.slice(3 * n, n + 1)
+    params.close()

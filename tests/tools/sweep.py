@@ -358,8 +358,6 @@ def main():
                 assert lib.zkb_poly_commit(params.handle_g_lagrange, h, outp) == 0
                 assert lib.zkb_poly_lagrange_to_coeff(h, k) == 0
                 polys.append(h)
-            for i in range(n_msm - n_intt - 6):
-                assert lib.zkb_poly_commit(params.handle_g, polys[i % n_intt], outp) == 0
             ext = []
             for i in range(n_c2e):          # 16 cosets of 2^24, resident (8 GiB)
                 e = h64(0)
@@ -373,6 +371,10 @@ def main():
                 perm.evaluate(values, fixed=[ext[8], ext[9], ext[10 + c % 4], ext[12 + c % 4]], advice=[ext[c], ext[2 * c % 8], ext[(2 * c + 1) % 8]],
                               beta=yv[1], gamma=yv[2], y=yv[0], rot_scale=4)
             assert lib.zkb_poly_extended_to_coeff(values._h, k, ek) == 0
+            for i in range(n_msm - n_intt - 6):   # the h pieces: n coefficients each, sliced and committed in HBM
+                piece = values.slice(i * n, n)
+                assert lib.zkb_poly_commit(params.handle_g, piece._h, outp) == 0
+                piece.free()
             for i in range(30):
                 assert lib.zkb_poly_eval(polys[i % n_intt], xp, ev.ctypes.data_as(u64p)) == 0
             for i in range(6):

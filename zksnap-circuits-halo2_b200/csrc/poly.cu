@@ -341,6 +341,27 @@ int zkb_poly_free(uint64_t handle) {
     return ZKB_OK;
 }
 
+// new handle holding poly[offset .. offset + n): the pieces of h(X) after extended_to_coeff (committed and opened one by one)
+int zkb_poly_slice(uint64_t poly, size_t offset, size_t n, uint64_t* out_handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!out_handle) { set_error("out_handle is NULL"); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (offset > p->n || n > p->n - offset) { set_error("slice [%zu, %zu) of a polynomial with %zu elements", offset, offset + n, (size_t)p->n); return ZKB_ERR_ARG; }
+    Poly* q;
+    ZKB_TRY(new_poly(n, &q, out_handle));
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(q->buf.p, p->buf.as<char>() + offset * 32, n * 32, cudaMemcpyDeviceToDevice, ctx().stream);
+        if (e != cudaSuccess) {
+            set_error("slice copy failed: %s", cudaGetErrorString(e));
+            pool_release(q->buf); delete q; poly_map().erase(*out_handle); *out_handle = 0;
+            return ZKB_ERR_CUDA;
+        }
+    }
+    return ZKB_OK;
+}
+
 int zkb_poly_commit(uint64_t srs_handle, uint64_t poly, uint64_t out_jac[12]) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());

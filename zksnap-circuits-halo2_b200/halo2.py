@@ -162,6 +162,12 @@ class Polynomial:
         check(lib().zkb_poly_download(self._h, _p(out), out.shape[0]))
         return out
 
+    def slice(self, offset: int, n: int) -> "Polynomial":
+        """A new resident polynomial holding self[offset : offset + n] (the pieces of h(X) after extended_to_coeff)."""
+        h = ctypes.c_uint64(0)
+        check(lib().zkb_poly_slice(self._h, offset, n, ctypes.byref(h)))
+        return Polynomial(_handle=h.value)
+
     def commit(self, params: "ParamsKZG", lagrange: bool = False) -> np.ndarray:
         out = np.zeros(12, dtype=np.uint64)
         h = params.handle_g_lagrange if lagrange else params.handle_g
