@@ -15,27 +15,32 @@
 
 namespace zkb {
 
+struct GraphQuery {
+    const uint4* poly;   // isize elements
+    uint64_t off;        // (rotation * rot_scale) mod isize
+};
+
 struct GraphArgs {
     const uint4* prog;          // ninstr device instructions (global copy; the kernel stages them in shared memory)
     uint32_t ninstr;
-    uint32_t result_slot;       // G_RESULT_ZERO: empty graph, the row's value is zero
+    uint32_t result_slot;       // G_RESULT_ZERO: empty graph, the row's value is zero; otherwise the last instruction's result
     const uint4* scalars;       // scalar table, 32 B each
-    const uint4* const* polys;  // distinct polynomials, isize elements each
-    const uint32_t* rot_off;    // row offset per rotation index
+    const GraphQuery* queries;  // distinct (polynomial, row offset) pairs
     uint4* values;              // isize elements: previous value in, result out
     uint64_t isize;             // power of two
 };
 
-ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint4* slots, uint32_t stride, uint32_t lane) {
-    const uint32_t kind = w >> 30, ix = w & (G_MAX_INDEX - 1);
+ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint4* slots, uint32_t stride, uint32_t lane, const Fr& acc) {
+    const uint32_t kind = w >> G_KIND_SHIFT, ix = w & (G_MAX_INDEX - 1);
     switch (kind) {
         case G_SCALAR: return fr_load2(g.scalars, ix);
         case G_SLOT: return fr_from_u4(slots[(2 * ix) * stride + lane], slots[(2 * ix + 1) * stride + lane]);
         case G_POLY: {
-            const uint64_t row = (idx + g.rot_off[(w >> 20) & (G_MAX_ROT - 1)]) & (g.isize - 1);
-            return fr_load2(g.polys[ix], row);
+            const GraphQuery q = g.queries[ix];
+            return fr_load2(q.poly, (idx + q.off) & (g.isize - 1));
         }
-        default: return fr_load2(g.values, idx);
+        case G_PREV: return fr_load2(g.values, idx);
+        default: return acc;
     }
 }
 
@@ -43,29 +48,33 @@ ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint
 // stride = threads per CTA, lane = thread index in the CTA.
 ZKB_HD void graph_eval_thread(const GraphArgs& g, const uint4* prog, uint64_t idx, uint4* slots, uint32_t stride, uint32_t lane) {
     if (idx >= g.isize) return;
+    Fr acc = Fr::zero();   // the previous instruction's result
     for (uint32_t i = 0; i < g.ninstr; ++i) {
         const uint4 ins = prog[i];
-        const uint32_t op = ins.x & 0xFF, dst = ins.x >> 8;
-        const Fr a = graph_operand(g, ins.y, idx, slots, stride, lane);
+        const uint32_t op = ins.x & 0x7F, dst = ins.x >> 8;
+        const Fr a = graph_operand(g, ins.y, idx, slots, stride, lane, acc);
         Fr r;
         if (op == ZKB_CALC_MUL || op == ZKB_CALC_SQUARE || op == ZKB_CALC_MUL_ADD) {
-            const Fr b = op == ZKB_CALC_SQUARE ? a : graph_operand(g, ins.z, idx, slots, stride, lane);
+            const Fr b = op == ZKB_CALC_SQUARE ? a : graph_operand(g, ins.z, idx, slots, stride, lane, acc);
             r = fp_mul_lazy(a, b);
-            if (op == ZKB_CALC_MUL_ADD) r = fp_add_lazy(r, graph_operand(g, ins.w, idx, slots, stride, lane));
+            if (op == ZKB_CALC_MUL_ADD) r = fp_add_lazy(r, graph_operand(g, ins.w, idx, slots, stride, lane, acc));
         } else if (op == ZKB_CALC_ADD || op == ZKB_CALC_DOUBLE) {
-            r = fp_add_lazy(a, op == ZKB_CALC_DOUBLE ? a : graph_operand(g, ins.z, idx, slots, stride, lane));
+            r = fp_add_lazy(a, op == ZKB_CALC_DOUBLE ? a : graph_operand(g, ins.z, idx, slots, stride, lane, acc));
         } else if (op == ZKB_CALC_SUB) {
-            r = fp_sub_lazy(a, graph_operand(g, ins.z, idx, slots, stride, lane));
+            r = fp_sub_lazy(a, graph_operand(g, ins.z, idx, slots, stride, lane, acc));
         } else if (op == ZKB_CALC_NEGATE) {
             r = fp_sub_lazy(Fr::zero(), a);
         } else {
             r = a;  // ZKB_CALC_STORE
         }
-        slots[(2 * dst) * stride + lane] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
-        slots[(2 * dst + 1) * stride + lane] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+        if (!(ins.x & G_NOSTORE)) {
+            slots[(2 * dst) * stride + lane] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
+            slots[(2 * dst + 1) * stride + lane] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+        }
+        acc = r;
     }
-    if (g.result_slot == G_RESULT_ZERO) { fr_store2(g.values, idx, Fr::zero()); return; }
-    fr_store2(g.values, idx, fp_canon(fr_from_u4(slots[(2 * g.result_slot) * stride + lane], slots[(2 * g.result_slot + 1) * stride + lane])));
+    // the row's result is the last instruction's (every other value is one of its ancestors); zero for an empty graph
+    fr_store2(g.values, idx, g.result_slot == G_RESULT_ZERO ? Fr::zero() : fp_canon(acc));
 }
 
 // threads per CTA for a graph with `nslots` slots: the widest CTA whose slots fit in shared memory next to the program

@@ -7,7 +7,9 @@
 //   * folds the three column arrays into one table of distinct polynomials (a handle used twice is read through one pointer),
 //   * turns rotations into row offsets (rotation * rot_scale).rem_euclid(isize),
 //   * and assigns intermediates to SLOTS by liveness (a slot is released after the last read of its intermediate), so the
-//     per-row state is the graph's maximum number of simultaneously live values — what the kernel keeps in shared memory.
+//     per-row state is the graph's maximum number of simultaneously live values — what the kernel keeps in shared memory;
+//     a value read only by the very next instruction never gets a slot: it stays in registers (halo2-base's gate is one such
+//     chain from the first product to the Horner fold and needs no shared memory at all).
 #pragma once
 #include <cstdint>
 #include <map>
@@ -18,10 +20,12 @@
 
 namespace zkb {
 
-// device instruction: x = op | slot << 8, y / z / w = operand words
-// operand word: kind << 30 | rotation index << 20 | index      (kind: 0 scalar table, 1 slot, 2 polynomial, 3 previous value)
-constexpr uint32_t G_SCALAR = 0, G_SLOT = 1, G_POLY = 2, G_PREV = 3;
-constexpr uint32_t G_MAX_INDEX = 1u << 20, G_MAX_ROT = 1u << 10;
+// device instruction: x = op | G_NOSTORE | slot << 8, y / z / w = operand words
+// operand word: kind << 29 | index   (kind: 0 scalar table, 1 slot, 2 column query = (polynomial, row offset) pair, 3 previous
+//                                     value, 4 the previous instruction's result, still in registers)
+constexpr uint32_t G_SCALAR = 0, G_SLOT = 1, G_POLY = 2, G_PREV = 3, G_ACC = 4;
+constexpr uint32_t G_KIND_SHIFT = 29, G_MAX_INDEX = 1u << 20, G_MAX_ROT = 1u << 10;
+constexpr uint32_t G_NOSTORE = 0x80;   // the result is consumed by the next instruction only (or is the row's result): no slot
 constexpr uint32_t G_RESULT_ZERO = 0xFFFFFFFFu;
 
 struct GraphInstrWord {
@@ -33,8 +37,9 @@ struct GraphPlan {
     std::vector<uint64_t> scalars;       // 4 u64 each
     std::vector<uint64_t> poly_handles;  // distinct, in first-use order
     std::vector<uint32_t> rot_off;       // per rotation index: (rotation * rot_scale) mod isize
+    std::vector<std::pair<uint32_t, uint32_t>> queries;  // distinct (polynomial, row offset) pairs the program reads
     uint32_t nslots = 0;
-    uint32_t result_slot = G_RESULT_ZERO;  // slot holding the row's result after the last instruction
+    uint32_t result_slot = G_RESULT_ZERO;  // 0: the row's result is the last instruction's; G_RESULT_ZERO: empty graph
     bool uses_prev = false;
 };
 
@@ -126,6 +131,7 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
 
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> scalar_ix;  // (kind, index) -> table entry
     std::map<uint64_t, uint32_t> poly_ix;
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> query_ix;
     auto scalar = [&](uint32_t kind, uint32_t index, const uint64_t* v) {
         auto key = std::make_pair(kind, index);
         auto it = scalar_ix.find(key);
@@ -156,14 +162,14 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
         switch (s.kind) {
             case ZKB_SRC_CONSTANT:
                 if (s.index >= g.num_constants) return fail("constant out of range", i);
-                return G_SCALAR << 30 | scalar(s.kind, s.index, g.constants + 4 * (size_t)s.index);
+                return G_SCALAR << G_KIND_SHIFT | scalar(s.kind, s.index, g.constants + 4 * (size_t)s.index);
             case ZKB_SRC_CHALLENGE:
                 if (s.index >= in.num_challenges) return fail("challenge out of range", i);
-                return G_SCALAR << 30 | scalar(s.kind, s.index, in.challenges + 4 * (size_t)s.index);
-            case ZKB_SRC_BETA: if (!in.beta) return fail("beta is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.beta);
-            case ZKB_SRC_GAMMA: if (!in.gamma) return fail("gamma is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.gamma);
-            case ZKB_SRC_THETA: if (!in.theta) return fail("theta is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.theta);
-            case ZKB_SRC_Y: if (!in.y) return fail("y is NULL", i); return G_SCALAR << 30 | scalar(s.kind, 0, in.y);
+                return G_SCALAR << G_KIND_SHIFT | scalar(s.kind, s.index, in.challenges + 4 * (size_t)s.index);
+            case ZKB_SRC_BETA: if (!in.beta) return fail("beta is NULL", i); return G_SCALAR << G_KIND_SHIFT | scalar(s.kind, 0, in.beta);
+            case ZKB_SRC_GAMMA: if (!in.gamma) return fail("gamma is NULL", i); return G_SCALAR << G_KIND_SHIFT | scalar(s.kind, 0, in.gamma);
+            case ZKB_SRC_THETA: if (!in.theta) return fail("theta is NULL", i); return G_SCALAR << G_KIND_SHIFT | scalar(s.kind, 0, in.theta);
+            case ZKB_SRC_Y: if (!in.y) return fail("y is NULL", i); return G_SCALAR << G_KIND_SHIFT | scalar(s.kind, 0, in.y);
             case ZKB_SRC_FIXED: case ZKB_SRC_ADVICE: case ZKB_SRC_INSTANCE: {
                 const uint64_t* cols = s.kind == ZKB_SRC_FIXED ? in.fixed : s.kind == ZKB_SRC_ADVICE ? in.advice : in.instance;
                 const size_t ncols = s.kind == ZKB_SRC_FIXED ? in.num_fixed : s.kind == ZKB_SRC_ADVICE ? in.num_advice : in.num_instance;
@@ -178,9 +184,18 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
                     poly_ix[h] = id;
                 } else id = it->second;
                 if (id >= G_MAX_INDEX) return fail("too many polynomials", i);
-                return G_POLY << 30 | s.rotation << 20 | id;
+                const auto key = std::make_pair(id, plan.rot_off[s.rotation]);
+                auto qt = query_ix.find(key);
+                uint32_t qid;
+                if (qt == query_ix.end()) {
+                    qid = (uint32_t)plan.queries.size();
+                    plan.queries.push_back(key);
+                    query_ix[key] = qid;
+                } else qid = qt->second;
+                if (qid >= G_MAX_INDEX) return fail("too many column queries", i);
+                return G_POLY << G_KIND_SHIFT | qid;
             }
-            case ZKB_SRC_PREVIOUS: plan.uses_prev = true; return G_PREV << 30;
+            case ZKB_SRC_PREVIOUS: plan.uses_prev = true; return G_PREV << G_KIND_SHIFT;
             default: return fail("unknown value source", i);
         }
     };
@@ -219,7 +234,7 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
     for (size_t i = 0; i < nc; ++i)
         if (nodes[i].live)
             for (uint32_t k = 0; k < nodes[i].nop; ++k)
-                if (nodes[i].val[k] < 0 && nodes[i].word[k] >> 30 == G_PREV) plan.uses_prev = true;
+                if (nodes[i].val[k] < 0 && nodes[i].word[k] >> G_KIND_SHIFT == G_PREV) plan.uses_prev = true;
 
     // ---- order + slots.  emit(order) assigns slots by liveness: a value's slot is released at its last reader, before the reader's
     // own result is placed (operands are in registers before the store).  Two orders are tried: the graph's own, and a list
@@ -231,32 +246,49 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
         if (nodes[i].live)
             for (uint32_t k = 0; k < nodes[i].nop; ++k)
                 if (nodes[i].val[k] >= 0) ++uses[nodes[i].val[k]];
-    auto emit = [&](const std::vector<uint32_t>& order, std::vector<GraphInstrWord>* prog, uint32_t* result_slot) {
+    auto emit = [&](const std::vector<uint32_t>& order, std::vector<GraphInstrWord>* prog) {
         std::vector<uint32_t> left(uses);
-        std::vector<int32_t> slot_of(nc, -1);
+        std::vector<int32_t> slot_of(nc, -1);   // -2: forwarded in registers to the next instruction
         std::vector<uint32_t> free_slots;
         uint32_t nslots = 0;
-        for (uint32_t i : order) {
+        for (size_t p = 0; p < order.size(); ++p) {
+            const uint32_t i = order[p];
             const Node& n = nodes[i];
             GraphInstrWord w{0, 0, 0, 0};
             uint32_t* dst[3] = {&w.a, &w.b, &w.c};
-            for (uint32_t k = 0; k < n.nop; ++k) *dst[k] = n.val[k] >= 0 ? (G_SLOT << 30 | (uint32_t)slot_of[n.val[k]]) : n.word[k];
+            for (uint32_t k = 0; k < n.nop; ++k) {
+                if (n.val[k] < 0) *dst[k] = n.word[k];
+                else if (slot_of[n.val[k]] == -2) *dst[k] = G_ACC << G_KIND_SHIFT;
+                else *dst[k] = G_SLOT << G_KIND_SHIFT | (uint32_t)slot_of[n.val[k]];
+            }
             for (uint32_t k = 0; k < n.nop; ++k)
-                if (n.val[k] >= 0 && --left[n.val[k]] == 0) free_slots.push_back((uint32_t)slot_of[n.val[k]]);
-            if (!free_slots.empty()) { slot_of[i] = (int32_t)free_slots.back(); free_slots.pop_back(); }
-            else slot_of[i] = (int32_t)nslots++;
-            w.op_slot = n.op | (uint32_t)slot_of[i] << 8;
+                if (n.val[k] >= 0 && --left[n.val[k]] == 0 && slot_of[n.val[k]] >= 0) free_slots.push_back((uint32_t)slot_of[n.val[k]]);
+            // all readers of this value sit in the next instruction (or it is the row's result): keep it in registers
+            bool forward = (int32_t)i == result_val;
+            if (!forward && p + 1 < order.size()) {
+                uint32_t in_next = 0;
+                const Node& nx = nodes[order[p + 1]];
+                for (uint32_t k = 0; k < nx.nop; ++k) in_next += nx.val[k] == (int32_t)i;
+                forward = in_next == uses[i];
+            }
+            if (forward) {
+                slot_of[i] = -2;
+                w.op_slot = n.op | G_NOSTORE;
+            } else {
+                if (!free_slots.empty()) { slot_of[i] = (int32_t)free_slots.back(); free_slots.pop_back(); }
+                else slot_of[i] = (int32_t)nslots++;
+                w.op_slot = n.op | (uint32_t)slot_of[i] << 8;
+            }
             if (prog) prog->push_back(w);
         }
-        if (result_slot) *result_slot = (uint32_t)slot_of[result_val];
         return nslots;
     };
     std::vector<uint32_t> natural;
     for (size_t i = 0; i < nc; ++i)
         if (nodes[i].live) natural.push_back((uint32_t)i);
     std::vector<uint32_t> best = natural;
-    uint32_t best_slots = emit(natural, nullptr, nullptr);
-    if (natural.size() <= 8192 && best_slots > 2) {
+    uint32_t best_slots = emit(natural, nullptr);
+    if (natural.size() <= 8192 && best_slots > 1) {
         std::vector<uint32_t> left(uses), pending(nc, 0), sched;
         std::vector<std::vector<uint32_t>> readers(nc);
         for (uint32_t i : natural) {
@@ -296,12 +328,13 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
                 if (--pending[r] == 0) ready.push_back(r);
         }
         if (sched.size() == natural.size()) {
-            const uint32_t s2 = emit(sched, nullptr, nullptr);
+            const uint32_t s2 = emit(sched, nullptr);
             if (s2 < best_slots) { best = sched; best_slots = s2; }
         }
     }
     plan.prog.reserve(best.size());
-    plan.nslots = emit(best, &plan.prog, &plan.result_slot);
+    plan.nslots = emit(best, &plan.prog);
+    plan.result_slot = 0;
     if (plan.nslots >= (1u << 20)) return "too many live intermediates";
     return "";
 }

@@ -545,15 +545,16 @@ int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, u
     if (threads == 0) { set_error("graph: %u live intermediates do not fit in shared memory", plan.nslots); return ZKB_ERR_ARG; }
     const size_t smem = (size_t)plan.nslots * 32 * threads + (stage ? (size_t)ninstr * 16 : 0);
 
-    // one upload: program | scalars | rotation offsets | polynomial pointers (stream-ordered after the previous evaluation)
+    // one upload: program | scalars | column queries (stream-ordered after the previous evaluation)
+    std::vector<GraphQuery> queries;
+    for (auto& q : plan.queries) queries.push_back(GraphQuery{ptrs[q.first], q.second});
     auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    const size_t o_prog = 0, o_sc = up16(o_prog + (size_t)ninstr * 16), o_rot = up16(o_sc + plan.scalars.size() * 8),
-                 o_ptr = up16(o_rot + plan.rot_off.size() * 4), total = up16(o_ptr + ptrs.size() * 8) + 16;
+    const size_t o_prog = 0, o_sc = up16(o_prog + (size_t)ninstr * 16), o_q = up16(o_sc + plan.scalars.size() * 8),
+                 total = up16(o_q + queries.size() * sizeof(GraphQuery)) + 16;
     std::vector<unsigned char> host(total, 0);
     if (ninstr) memcpy(host.data() + o_prog, plan.prog.data(), (size_t)ninstr * 16);
     if (!plan.scalars.empty()) memcpy(host.data() + o_sc, plan.scalars.data(), plan.scalars.size() * 8);
-    if (!plan.rot_off.empty()) memcpy(host.data() + o_rot, plan.rot_off.data(), plan.rot_off.size() * 4);
-    if (!ptrs.empty()) memcpy(host.data() + o_ptr, ptrs.data(), ptrs.size() * 8);
+    if (!queries.empty()) memcpy(host.data() + o_q, queries.data(), queries.size() * sizeof(GraphQuery));
     cudaStream_t s = ctx().stream;
     ZKB_TRY(graph_ws().reserve(total));
     ZKB_CUDA_TRY(cudaMemcpyAsync(graph_ws().p, host.data(), total, cudaMemcpyHostToDevice, s));  // pageable source: staged before return
@@ -563,8 +564,7 @@ int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, u
     a.ninstr = ninstr;
     a.result_slot = plan.result_slot;
     a.scalars = reinterpret_cast<const uint4*>(d + o_sc);
-    a.polys = reinterpret_cast<const uint4* const*>(d + o_ptr);
-    a.rot_off = reinterpret_cast<const uint32_t*>(d + o_rot);
+    a.queries = reinterpret_cast<const GraphQuery*>(d + o_q);
     a.values = out->buf.as<uint4>();
     a.isize = isize;
     if (smem > 48 * 1024) ZKB_CUDA_TRY(cudaFuncSetAttribute(graph_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
