@@ -278,6 +278,15 @@ typedef struct zkb_graph_inputs {
 } zkb_graph_inputs;
 /* values: polynomial handle of isize elements, read as PreviousValue and overwritten with the row results. */
 int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, uint64_t values);
+/* Device pointers and the caller's stream (asynchronous): the fixed / advice / instance arrays of `inputs` hold device addresses
+ * (16-byte aligned) instead of handles, d_values holds `rows` elements.  window == 0: the whole domain, rows a power of two,
+ * rotated rows wrap.  window != 0: a ROW WINDOW — one rank's share of the extended domain when the quotient evaluation is
+ * sharded by rows over the GPUs of a box: every column buffer holds halo_lo + rows + halo_hi elements (the last
+ * rows of the previous shard, the shard, the first rows of the next), row i reads element halo_lo + i + rotation * rot_scale,
+ * nothing wraps, and a rotation that reaches outside the halo is ZKB_ERR_ARG.  The halo exchange between neighbouring ranks is
+ * the path's one collective step (zksnap-circuits-halo2_b200/distributed.py: ShardedQuotient). */
+int zkb_graph_evaluate_dev(const zkb_graph* graph, const zkb_graph_inputs* inputs, void* d_values, size_t rows, int window,
+                           size_t halo_lo, size_t halo_hi, void* stream);
 /* What the last zkb_graph_evaluate was lowered to: device instructions, shared-memory slots after liveness analysis,
  * distinct polynomials read, algorithmic bytes per row (32 x (polynomials read + previous value + result)). */
 int zkb_graph_last_info(uint32_t* instructions, uint32_t* slots, uint32_t* polys_read, uint32_t* bytes_per_row);

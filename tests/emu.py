@@ -176,15 +176,16 @@ def prefix_product(a):
     return a
 
 
-def graph_evaluate(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, rot_scale, values, cta_threads=0):
+def graph_evaluate(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, rot_scale, values, cta_threads=0, halo=None):
     """graph: evaluation.GraphEvaluator; columns: lists of (isize, 4) host arrays (passed as addresses where the product takes
-    handles).  Returns (new values, info = [instructions, slots, polys])."""
+    handles).  Returns (rc, new values, info = [instructions, slots, polys])."""
     keep = [[np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, 4) for c in cols] for cols in (fixed, advice, instance)]
     out = np.array(values, dtype=np.uint64, copy=True).reshape(-1, 4)
     g, kg = graph.c_graph()
     inp, ki = graph.c_inputs(*[[a.ctypes.data for a in cols] for cols in keep], challenges, beta, gamma, theta, y, rot_scale)
     info = (ctypes.c_uint32 * 3)()
+    lo, hi = halo if halo is not None else (0xFFFFFFFFFFFFFFFF, 0)   # halo = (halo_lo, halo_hi): row-window mode
     rc = lib().zkb_emu_graph_evaluate(ctypes.byref(g), ctypes.byref(inp), _p(out), ctypes.c_uint64(out.shape[0]),
-                                      ctypes.c_uint32(cta_threads), info)
+                                      ctypes.c_uint32(cta_threads), info, ctypes.c_uint64(lo), ctypes.c_uint64(hi))
     del kg, ki
     return rc, out, list(info)

@@ -129,3 +129,58 @@ def test_ntt_slice_partition():
             spans = [zd.ntt_slice(k, r, world) for r in range(world)]
             assert spans[0][0] == 0 and sum(l for _, l in spans) == 1 << k
             assert all(o1 + l1 == o2 for (o1, l1), (o2, _) in zip(spans, spans[1:]))
+
+
+# ---- quotient evaluation sharded by rows: ring halo exchange over gloo + the device code's row-window mode (CPU emulator) --------
+def _sharded_quotient_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    import emu
+    import graph_cases as GC
+    from oracle import coracle
+
+    zd = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+    isize, rs = 128, 4
+    c = GC.random_case(777, isize, rs, ngates=4, depth=5)   # the same case on every rank; each keeps only its rows
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    want = coracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                  None, None, None, y, rs, prev)
+    off, rows = zd.row_range(isize, rank, world)
+
+    def t(a):
+        return torch.from_numpy(a[off:off + rows].view(np.int64).copy())
+
+    sq = zd.ShardedQuotient(g, rs)
+    values = t(prev)
+
+    def evaluate(v, f, a, i):   # the per-rank call, on the emulator: same lowering, same per-thread interpreter, window mode
+        rc, o, _ = emu.graph_evaluate(g, [x.numpy().view(np.uint64) for x in f], [x.numpy().view(np.uint64) for x in a],
+                                      [x.numpy().view(np.uint64) for x in i], ch, None, None, None, y, rs, v.numpy().view(np.uint64),
+                                      halo=(sq.halo_lo, sq.halo_hi))
+        assert rc == 0
+        v.copy_(torch.from_numpy(o.view(np.int64)))
+
+    sq.run(values, [t(x) for x in fx], [t(x) for x in ad], [t(x) for x in ins], evaluate=evaluate)
+    ret[rank] = bool((values.numpy().view(np.uint64) == want[off:off + rows]).all())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_quotient_two_ranks_gloo():
+    import torch.multiprocessing as mp
+
+    import emu
+    from oracle import coracle
+    emu.build()
+    coracle.build()
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_quotient_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] is True for r in range(world)), dict(ret)

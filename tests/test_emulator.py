@@ -494,3 +494,30 @@ def test_graph_lowering_random_programs(oracle, seed):
     rc, out, info = emu.graph_evaluate(g, fixed, advice, [], None, sc[0], sc[1], sc[2], sc[3], rs, prev, random.Random(seed).choice([0, 32, 64]))
     assert rc == 0 and (out == want).all()
     assert info[0] <= len(g.calculations)
+
+
+@pytest.mark.parametrize("world,seed", [(1, 51), (2, 52), (4, 53), (8, 54)])
+def test_graph_row_windows_match_whole_domain(oracle, world, seed):
+    """Row-window mode (the per-rank call of the row-sharded quotient evaluation): the domain cut into `world` shards, every
+    column padded with the neighbouring shards' rows (cyclically), each window evaluated on its own — the concatenation equals
+    the whole-domain evaluation; a rotation that reaches outside the halo is refused."""
+    isize, rs = 256, 4
+    c = GC.random_case(seed, isize, rs, ngates=4, depth=5)
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                 None, None, None, y, rs, prev)
+    lo, hi = g.rotation_span(rs)
+    assert lo == 2 * rs and hi == 3 * rs          # rotations -2 .. 3
+    rows = isize // world
+    out = np.zeros_like(prev)
+    for r in range(world):
+        idx = np.arange(r * rows - lo, (r + 1) * rows + hi) % isize
+        win = [[col[idx] for col in grp] for grp in (fx, ad, ins)]
+        rc, o, _ = emu.graph_evaluate(g, win[0], win[1], win[2], ch, None, None, None, y, rs, prev[r * rows:(r + 1) * rows], halo=(lo, hi))
+        assert rc == 0
+        out[r * rows:(r + 1) * rows] = o
+    assert (out == want).all()
+    idx = np.arange(-lo, rows + hi - 1) % isize   # one row short at the top
+    win = [[col[idx] for col in grp] for grp in (fx, ad, ins)]
+    assert emu.graph_evaluate(g, win[0], win[1], win[2], ch, None, None, None, y, rs, prev[:rows], halo=(lo, hi - 1))[0] != 0

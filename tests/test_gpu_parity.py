@@ -1055,3 +1055,74 @@ def test_h_pieces_sliced_committed_and_opened_on_the_device(oracle):
     with pytest.raises(zkb.ZkbError):
         H.slice(3 * n, n + 1)
     params.close()
+
+
+def test_graph_evaluate_dev_whole_domain_and_row_window(oracle):
+    """zkb_graph_evaluate_dev on device pointers: whole-domain mode equals the handle path; row-window mode on windows cut by
+    hand (two shards, cyclic halos) equals the whole-domain result; a rotation outside the halo is refused."""
+    import torch
+    dev = torch.device("cuda", 0)
+    isize, rs = 1 << 12, 4
+    c = GC.random_case(4711, isize, rs, ngates=5, depth=5)
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                 None, None, None, y, rs, prev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def dv(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(dev)
+
+    cols = [[dv(a) for a in grp] for grp in (fx, ad, ins)]
+    values = dv(prev)
+    g.evaluate_dev(values.data_ptr(), isize, *[[t.data_ptr() for t in grp] for grp in cols], challenges=ch, y=y, rot_scale=rs, stream=stream)
+    torch.cuda.synchronize()
+    assert (values.cpu().numpy().view(np.uint64) == want).all()
+    lo, hi = g.rotation_span(rs)
+    rows = isize // 2
+    for r in range(2):
+        idx = np.arange(r * rows - lo, (r + 1) * rows + hi) % isize
+        win = [[dv(a[idx]) for a in grp] for grp in (fx, ad, ins)]
+        v = dv(prev[r * rows:(r + 1) * rows])
+        g.evaluate_dev(v.data_ptr(), rows, *[[t.data_ptr() for t in grp] for grp in win], challenges=ch, y=y, rot_scale=rs,
+                       window=True, halo_lo=lo, halo_hi=hi, stream=stream)
+        torch.cuda.synchronize()
+        assert (v.cpu().numpy().view(np.uint64) == want[r * rows:(r + 1) * rows]).all()
+        with pytest.raises(zkb.ZkbError):
+            g.evaluate_dev(v.data_ptr(), rows, *[[t.data_ptr() for t in grp] for grp in win], challenges=ch, y=y, rot_scale=rs,
+                           window=True, halo_lo=lo, halo_hi=hi - 1, stream=stream)
+
+
+def test_sharded_quotient_single_rank_wraps_onto_itself(oracle):
+    """distributed.ShardedQuotient with one rank: the halo exchange is a cyclic copy of the rank's own rows."""
+    import torch
+    zd = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+    dev = torch.device("cuda", 0)
+    isize, rs = 1 << 11, 2
+    c = GC.random_case(4712, isize, rs, ngates=4, depth=5)
+    g = c["graph"]
+    fx, ad, ins, ch, y, prev = GC.case_arrays(c)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, ins, ch,
+                                 None, None, None, y, rs, prev)
+
+    def dv(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(dev)
+
+    values = dv(prev)
+    zd.ShardedQuotient(g, rs).run(values, [dv(a) for a in fx], [dv(a) for a in ad], [dv(a) for a in ins], challenges=ch, y=y)
+    torch.cuda.synchronize()
+    assert (values.cpu().numpy().view(np.uint64) == want).all()
+
+
+def test_sharded_quotient_two_gpus():
+    import subprocess
+    import sys
+    if zkb.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(root, "tests", "tools", "dist_quotient_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 3 and all(l["parity"] for l in lines)

@@ -100,6 +100,7 @@ def load() -> ctypes.CDLL:
         "zkb_fr_kate_division": [u64p, sz, u64p, u64p],
         "zkb_fr_batch_invert": [u64p, sz],
         "zkb_graph_evaluate": [vp, vp, u64],
+        "zkb_graph_evaluate_dev": [vp, vp, vp, sz, ci, sz, sz, vp],
         "zkb_graph_last_info": [ctypes.POINTER(u32)] * 4,
         "zkb_dist_create": [ci, ci, u32, ctypes.POINTER(ctypes.c_uint8)],
         "zkb_dist_connect": [ctypes.POINTER(ctypes.c_uint8)],

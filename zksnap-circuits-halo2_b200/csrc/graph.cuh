@@ -17,7 +17,7 @@ namespace zkb {
 
 struct GraphQuery {
     const uint4* poly;   // isize elements
-    uint64_t off;        // (rotation * rot_scale) mod isize
+    uint64_t off;        // (rotation * rot_scale) mod isize, or halo_lo + rotation * rot_scale in a row window
 };
 
 struct GraphArgs {
@@ -26,8 +26,9 @@ struct GraphArgs {
     uint32_t result_slot;       // G_RESULT_ZERO: empty graph, the row's value is zero; otherwise the last instruction's result
     const uint4* scalars;       // scalar table, 32 B each
     const GraphQuery* queries;  // distinct (polynomial, row offset) pairs
-    uint4* values;              // isize elements: previous value in, result out
-    uint64_t isize;             // power of two
+    uint4* values;              // nrows elements: previous value in, result out
+    uint64_t nrows;             // rows evaluated
+    uint64_t mask;              // whole domain: nrows - 1 (rotated rows wrap); row window: all ones (offsets include the halo)
 };
 
 ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint4* slots, uint32_t stride, uint32_t lane, const Fr& acc) {
@@ -37,7 +38,7 @@ ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint
         case G_SLOT: return fr_from_u4(slots[(2 * ix) * stride + lane], slots[(2 * ix + 1) * stride + lane]);
         case G_POLY: {
             const GraphQuery q = g.queries[ix];
-            return fr_load2(q.poly, (idx + q.off) & (g.isize - 1));
+            return fr_load2(q.poly, (idx + q.off) & g.mask);
         }
         case G_PREV: return fr_load2(g.values, idx);
         default: return acc;
@@ -47,7 +48,7 @@ ZKB_HD Fr graph_operand(const GraphArgs& g, uint32_t w, uint64_t idx, const uint
 // prog: where the thread reads instructions from (shared memory on the device); slots: the CTA's slot planes,
 // stride = threads per CTA, lane = thread index in the CTA.
 ZKB_HD void graph_eval_thread(const GraphArgs& g, const uint4* prog, uint64_t idx, uint4* slots, uint32_t stride, uint32_t lane) {
-    if (idx >= g.isize) return;
+    if (idx >= g.nrows) return;
     Fr acc = Fr::zero();   // the previous instruction's result
     for (uint32_t i = 0; i < g.ninstr; ++i) {
         const uint4 ins = prog[i];

@@ -110,10 +110,20 @@ inline std::vector<zkb_calculation> graph_simplify(const zkb_graph& g) {
     return out;
 }
 
-// Returns "" on success, otherwise what is wrong with the graph / inputs.
-inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, uint64_t isize, GraphPlan& plan) {
+// A WINDOW of rows (one rank's share of the extended domain): every column buffer holds halo_lo rows of the previous
+// shard, the shard's own rows, and halo_hi rows of the next one, so that rotated rows are read without wrapping.
+struct GraphWindow {
+    bool on = false;
+    uint64_t halo_lo = 0, halo_hi = 0;
+};
+
+// Returns "" on success, otherwise what is wrong with the graph / inputs.  isize: rows of the whole domain (wrapping mode) or of
+// the window.
+inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, uint64_t isize, GraphPlan& plan,
+                               const GraphWindow& win = GraphWindow()) {
     plan = GraphPlan();
-    if (isize == 0 || (isize & (isize - 1)) || isize > (1ull << 28)) return "the extended domain size must be a power of two <= 2^28";
+    if (!win.on && (isize == 0 || (isize & (isize - 1)) || isize > (1ull << 28))) return "the extended domain size must be a power of two <= 2^28";
+    if (win.on && (isize == 0 || isize > (1ull << 28) || win.halo_lo > (1u << 20) || win.halo_hi > (1u << 20))) return "bad row window";
     if (g.num_calculations && !g.calculations) return "calculations is NULL";
     if (g.num_constants && !g.constants) return "constants is NULL";
     if (g.num_rotations && !g.rotations) return "rotations is NULL";
@@ -123,9 +133,17 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
         (in.num_challenges && !in.challenges))
         return "a column / challenge array is NULL";
 
+    std::vector<int8_t> rot_in_halo(g.num_rotations, 1);
     for (size_t r = 0; r < g.num_rotations; ++r) {
-        int64_t o = ((int64_t)g.rotations[r] * (int64_t)in.rot_scale) % (int64_t)isize;
-        if (o < 0) o += (int64_t)isize;
+        int64_t o = (int64_t)g.rotations[r] * (int64_t)in.rot_scale;
+        if (win.on) {  // window: index = halo_lo + row + offset, never wraps; a rotation outside the halo is an error if it is read
+            if (o < -(int64_t)win.halo_lo || o > (int64_t)win.halo_hi) rot_in_halo[r] = 0;
+            o += (int64_t)win.halo_lo;
+            if (o < 0) o = 0;
+        } else {
+            o %= (int64_t)isize;
+            if (o < 0) o += (int64_t)isize;
+        }
         plan.rot_off.push_back((uint32_t)o);
     }
 
@@ -175,6 +193,7 @@ inline std::string graph_lower(const zkb_graph& g, const zkb_graph_inputs& in, u
                 const size_t ncols = s.kind == ZKB_SRC_FIXED ? in.num_fixed : s.kind == ZKB_SRC_ADVICE ? in.num_advice : in.num_instance;
                 if (s.index >= ncols) return fail("column out of range", i);
                 if (s.rotation >= g.num_rotations) return fail("rotation index out of range", i);
+                if (!rot_in_halo[s.rotation]) return fail("rotation reaches outside the window's halo", i);
                 const uint64_t h = cols[s.index];
                 auto it = poly_ix.find(h);
                 uint32_t id;

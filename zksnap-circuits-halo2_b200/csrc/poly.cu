@@ -104,6 +104,15 @@ static DevBuf& graph_ws() {
     static DevBuf b;
     return b;
 }
+struct GraphRing {   // upload buffers of zkb_graph_evaluate_dev
+    DevBuf buf[4];
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned next = 0;
+};
+static GraphRing& graph_ring() {
+    static GraphRing r;
+    return r;
+}
 static PolyWs& poly_ws() {
     static PolyWs w;
     return w;
@@ -271,6 +280,10 @@ void poly_release_all() {
     PolyWs& w = poly_ws();
     w.tmp.release();
     graph_ws().release();
+    for (int i = 0; i < 4; ++i) {
+        graph_ring().buf[i].release();
+        if (graph_ring().ev[i]) { cudaEventDestroy(graph_ring().ev[i]); graph_ring().ev[i] = nullptr; }
+    }
     if (w.h_out) cudaFreeHost(w.h_out);
     w.h_out = nullptr;
 }
@@ -519,6 +532,53 @@ struct GraphInfo { uint32_t instructions = 0, slots = 0, polys = 0, bytes_per_ro
 static GraphInfo g_graph_info;
 constexpr size_t GRAPH_STAGE_PROG_BYTES = 32 << 10;
 
+// lowered program + operand tables -> one upload into `ws` and the launch on `s`
+static int graph_launch(const GraphPlan& plan, const std::vector<const uint4*>& ptrs, uint4* d_values, uint64_t nrows, uint64_t mask,
+                        cudaStream_t s, DevBuf& ws) {
+    const uint32_t ninstr = (uint32_t)plan.prog.size();
+    const bool stage = (size_t)ninstr * 16 <= GRAPH_STAGE_PROG_BYTES;
+    int smem_limit = 0;
+    ZKB_CUDA_TRY(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device));
+    const uint32_t threads = graph_cta_threads(plan.nslots, stage ? ninstr : 0, (size_t)smem_limit);
+    if (threads == 0) { set_error("graph: %u live intermediates do not fit in shared memory", plan.nslots); return ZKB_ERR_ARG; }
+    const size_t smem = (size_t)plan.nslots * 32 * threads + (stage ? (size_t)ninstr * 16 : 0);
+
+    // one upload: program | scalars | column queries
+    std::vector<GraphQuery> queries;
+    for (auto& q : plan.queries) queries.push_back(GraphQuery{ptrs[q.first], q.second});
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t o_prog = 0, o_sc = up16(o_prog + (size_t)ninstr * 16), o_q = up16(o_sc + plan.scalars.size() * 8),
+                 total = up16(o_q + queries.size() * sizeof(GraphQuery)) + 16;
+    std::vector<unsigned char> host(total, 0);
+    if (ninstr) memcpy(host.data() + o_prog, plan.prog.data(), (size_t)ninstr * 16);
+    if (!plan.scalars.empty()) memcpy(host.data() + o_sc, plan.scalars.data(), plan.scalars.size() * 8);
+    if (!queries.empty()) memcpy(host.data() + o_q, queries.data(), queries.size() * sizeof(GraphQuery));
+    ZKB_TRY(ws.reserve(total));
+    ZKB_CUDA_TRY(cudaMemcpyAsync(ws.p, host.data(), total, cudaMemcpyHostToDevice, s));  // pageable source: staged before return
+    char* d = reinterpret_cast<char*>(ws.p);
+    GraphArgs a{};
+    a.prog = reinterpret_cast<const uint4*>(d + o_prog);
+    a.ninstr = ninstr;
+    a.result_slot = plan.result_slot;
+    a.scalars = reinterpret_cast<const uint4*>(d + o_sc);
+    a.queries = reinterpret_cast<const GraphQuery*>(d + o_q);
+    a.values = d_values;
+    a.nrows = nrows;
+    a.mask = mask;
+    if (smem > 48 * 1024) ZKB_CUDA_TRY(cudaFuncSetAttribute(graph_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope prof("graph_evaluate", s);
+        graph_evaluate_kernel<<<nblk(nrows, threads), threads, smem, s>>>(a, plan.nslots, stage ? 1u : 0u);
+    }
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    g_graph_info.instructions = ninstr;
+    g_graph_info.slots = plan.nslots;
+    g_graph_info.polys = (uint32_t)ptrs.size();
+    g_graph_info.bytes_per_row = 32 * ((uint32_t)ptrs.size() + (plan.uses_prev ? 1 : 0) + 1);
+    return ZKB_OK;
+}
+
 int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, uint64_t values) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
@@ -537,47 +597,38 @@ int zkb_graph_evaluate(const zkb_graph* graph, const zkb_graph_inputs* inputs, u
         if (p == out) { set_error("graph: values is also read as a column (rows are not evaluated in order)"); return ZKB_ERR_ARG; }
         ptrs.push_back(p->buf.as<uint4>());
     }
-    const uint32_t ninstr = (uint32_t)plan.prog.size();
-    const bool stage = (size_t)ninstr * 16 <= GRAPH_STAGE_PROG_BYTES;
-    int smem_limit = 0;
-    ZKB_CUDA_TRY(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx().device));
-    const uint32_t threads = graph_cta_threads(plan.nslots, stage ? ninstr : 0, (size_t)smem_limit);
-    if (threads == 0) { set_error("graph: %u live intermediates do not fit in shared memory", plan.nslots); return ZKB_ERR_ARG; }
-    const size_t smem = (size_t)plan.nslots * 32 * threads + (stage ? (size_t)ninstr * 16 : 0);
+    return graph_launch(plan, ptrs, out->buf.as<uint4>(), isize, isize - 1, ctx().stream, graph_ws());  // stream-ordered reuse of the upload buffer
+}
 
-    // one upload: program | scalars | column queries (stream-ordered after the previous evaluation)
-    std::vector<GraphQuery> queries;
-    for (auto& q : plan.queries) queries.push_back(GraphQuery{ptrs[q.first], q.second});
-    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    const size_t o_prog = 0, o_sc = up16(o_prog + (size_t)ninstr * 16), o_q = up16(o_sc + plan.scalars.size() * 8),
-                 total = up16(o_q + queries.size() * sizeof(GraphQuery)) + 16;
-    std::vector<unsigned char> host(total, 0);
-    if (ninstr) memcpy(host.data() + o_prog, plan.prog.data(), (size_t)ninstr * 16);
-    if (!plan.scalars.empty()) memcpy(host.data() + o_sc, plan.scalars.data(), plan.scalars.size() * 8);
-    if (!queries.empty()) memcpy(host.data() + o_q, queries.data(), queries.size() * sizeof(GraphQuery));
-    cudaStream_t s = ctx().stream;
-    ZKB_TRY(graph_ws().reserve(total));
-    ZKB_CUDA_TRY(cudaMemcpyAsync(graph_ws().p, host.data(), total, cudaMemcpyHostToDevice, s));  // pageable source: staged before return
-    char* d = reinterpret_cast<char*>(graph_ws().p);
-    GraphArgs a{};
-    a.prog = reinterpret_cast<const uint4*>(d + o_prog);
-    a.ninstr = ninstr;
-    a.result_slot = plan.result_slot;
-    a.scalars = reinterpret_cast<const uint4*>(d + o_sc);
-    a.queries = reinterpret_cast<const GraphQuery*>(d + o_q);
-    a.values = out->buf.as<uint4>();
-    a.isize = isize;
-    if (smem > 48 * 1024) ZKB_CUDA_TRY(cudaFuncSetAttribute(graph_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        ProfScope prof("graph_evaluate", s);
-        graph_evaluate_kernel<<<nblk(isize, threads), threads, smem, s>>>(a, plan.nslots, stage ? 1u : 0u);
+// Device pointers, the caller's stream, and optionally a row WINDOW (one rank's share of the extended domain): the `fixed` /
+// `advice` / `instance` arrays of `inputs` hold device addresses instead of handles.
+int zkb_graph_evaluate_dev(const zkb_graph* graph, const zkb_graph_inputs* inputs, void* d_values, size_t rows, int window,
+                           size_t halo_lo, size_t halo_hi, void* stream) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!graph || !inputs || !d_values) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    GraphWindow win;
+    win.on = window != 0;
+    win.halo_lo = halo_lo;
+    win.halo_hi = halo_hi;
+    if (!win.on && (halo_lo || halo_hi)) { set_error("graph: a halo needs window mode"); return ZKB_ERR_ARG; }
+    GraphPlan plan;
+    const std::string err = graph_lower(*graph, *inputs, rows, plan, win);
+    if (!err.empty()) { set_error("graph: %s", err.c_str()); return ZKB_ERR_ARG; }
+    std::vector<const uint4*> ptrs;
+    for (uint64_t h : plan.poly_handles) {
+        if (!h || (h & 15)) { set_error("graph: column pointers must be non-NULL and 16-byte aligned"); return ZKB_ERR_ARG; }
+        if (h == (uint64_t)(uintptr_t)d_values) { set_error("graph: values is also read as a column (rows are not evaluated in order)"); return ZKB_ERR_ARG; }
+        ptrs.push_back(reinterpret_cast<const uint4*>((uintptr_t)h));
     }
-    count_launch();
-    ZKB_CUDA_TRY(cudaGetLastError());
-    g_graph_info.instructions = ninstr;
-    g_graph_info.slots = plan.nslots;
-    g_graph_info.polys = (uint32_t)ptrs.size();
-    g_graph_info.bytes_per_row = 32 * ((uint32_t)ptrs.size() + (plan.uses_prev ? 1 : 0) + 1);
+    // the upload buffers are shared between calls on arbitrary streams: a ring, each slot reused only after the kernel that read it
+    GraphRing& r = graph_ring();
+    const unsigned k = r.next++ & 3;
+    if (!r.ev[k]) ZKB_CUDA_TRY(cudaEventCreateWithFlags(&r.ev[k], cudaEventDisableTiming));
+    else ZKB_CUDA_TRY(cudaEventSynchronize(r.ev[k]));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    ZKB_TRY(graph_launch(plan, ptrs, reinterpret_cast<uint4*>(d_values), rows, win.on ? ~0ull : (uint64_t)rows - 1, s, r.buf[k]));
+    ZKB_CUDA_TRY(cudaEventRecord(r.ev[k], s));
     return ZKB_OK;
 }
 

@@ -111,3 +111,82 @@ class ShardedNtt:
 
     def close(self) -> None:
         self.lib.zkb_dist_destroy()
+
+
+# ---- quotient evaluation sharded by rows -------------------------------------------------------------------------------------
+def row_range(isize: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous rows [offset, offset + len) of the extended domain owned by `rank` (isize is a power of two, world divides it)."""
+    assert isize % world == 0, "the extended domain must split evenly over the ranks"
+    return rank * (isize // world), isize // world
+
+
+def exchange_halos(slices: list, halo_lo: int, halo_hi: int, group=None) -> list:
+    """Ring halo exchange — the one collective step of the row-sharded quotient evaluation.
+
+    slices: this rank's row slice of every column, torch tensors of shape (rows, 4) int64 (limbs) on the device the process
+    group's backend moves (CUDA for nccl, CPU for gloo).  Returns, per column, a (halo_lo + rows + halo_hi, 4) tensor: the last
+    halo_lo rows of the previous rank's slice, the slice, the first halo_hi rows of the next rank's (the domain is cyclic: rank 0's
+    predecessor is the last rank).  world = 1 wraps onto the slice itself.  All columns travel in two messages per neighbour."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if not slices:
+        return []
+    rows = slices[0].shape[0]
+    assert halo_lo <= rows and halo_hi <= rows, "a halo longer than a shard would need more than the neighbouring rank"
+    head = torch.stack([t[:halo_hi] for t in slices]) if halo_hi else None      # becomes the previous rank's upper halo
+    tail = torch.stack([t[rows - halo_lo:] for t in slices]) if halo_lo else None  # becomes the next rank's lower halo
+    lo = torch.empty_like(tail) if halo_lo else None
+    hi = torch.empty_like(head) if halo_hi else None
+    if world == 1:
+        if halo_lo:
+            lo.copy_(tail)
+        if halo_hi:
+            hi.copy_(head)
+    else:
+        prev, nxt = (rank - 1) % world, (rank + 1) % world
+        ops = []
+        if halo_hi:
+            ops += [dist.P2POp(dist.isend, head.contiguous(), prev, group), dist.P2POp(dist.irecv, hi, nxt, group)]
+        if halo_lo:
+            ops += [dist.P2POp(dist.isend, tail.contiguous(), nxt, group), dist.P2POp(dist.irecv, lo, prev, group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    out = []
+    for c, t in enumerate(slices):
+        parts = ([lo[c]] if halo_lo else []) + [t] + ([hi[c]] if halo_hi else [])
+        out.append(torch.cat(parts).contiguous())
+    return out
+
+
+class ShardedQuotient:
+    """evaluate_h's row loop sharded by rows over the GPUs of a box: rank r owns rows [r N/G, (r+1) N/G) of every extended coset
+    (the layout the sharded NTT leaves its output in) and of h.  Rotated rows near a shard boundary come from the neighbouring rank:
+    one ring halo exchange of max|rotation| x rot_scale rows per column (a few KB against the 32 N/G bytes of a slice), then
+    every rank runs zkb_graph_evaluate_dev on its window.  `evaluate` is the injectable per-rank call (the CPU tests pass the
+    device-code emulator)."""
+
+    def __init__(self, graph, rot_scale: int, group=None):
+        self.graph, self.rot_scale, self.group = graph, rot_scale, group
+        self.halo_lo, self.halo_hi = graph.rotation_span(rot_scale)
+
+    def run(self, values, fixed=(), advice=(), instance=(), evaluate=None, **scalars):
+        """values / columns: this rank's (rows, 4) int64 limb tensors; values is overwritten with the row results."""
+        import torch
+
+        cols = list(fixed) + list(advice) + list(instance)
+        padded = exchange_halos(cols, self.halo_lo, self.halo_hi, self.group)
+        nf, na = len(fixed), len(advice)
+        pf, pa, pi = padded[:nf], padded[nf:nf + na], padded[nf + na:]
+        rows = values.shape[0]
+        if evaluate is None:
+            stream = torch.cuda.current_stream().cuda_stream
+
+            def evaluate(v, f, a, i):
+                self.graph.evaluate_dev(v.data_ptr(), rows, [t.data_ptr() for t in f], [t.data_ptr() for t in a],
+                                        [t.data_ptr() for t in i], rot_scale=self.rot_scale, window=True, halo_lo=self.halo_lo,
+                                        halo_hi=self.halo_hi, stream=stream, **scalars)
+        evaluate(values, pf, pa, pi)
+        return values

@@ -210,6 +210,26 @@ class GraphEvaluator:
         halo2.check(halo2.lib().zkb_graph_evaluate(ctypes.byref(g), ctypes.byref(inp), values._h))
         del keep_g, keep_i
 
+    def evaluate_dev(self, d_values: int, rows: int, fixed=(), advice=(), instance=(), challenges=None, beta=None, gamma=None,
+                     theta=None, y=None, rot_scale: int = 1, window: bool = False, halo_lo: int = 0, halo_hi: int = 0,
+                     stream: int = 0) -> None:
+        """`evaluate` on device pointers and the caller's stream (zkb_graph_evaluate_dev).  Columns are device addresses.
+        window=True: a row window of the extended domain — every column holds halo_lo + rows + halo_hi elements and row i reads
+        element halo_lo + i + rotation * rot_scale (the per-rank call of distributed.ShardedQuotient)."""
+        from . import halo2
+
+        g, keep_g = self.c_graph()
+        inp, keep_i = self.c_inputs(list(fixed), list(advice), list(instance), challenges, beta, gamma, theta, y, rot_scale)
+        halo2.check(halo2.lib().zkb_graph_evaluate_dev(ctypes.byref(g), ctypes.byref(inp), ctypes.c_void_p(d_values), rows,
+                                                       1 if window else 0, halo_lo, halo_hi, ctypes.c_void_p(stream)))
+        del keep_g, keep_i
+
+    def rotation_span(self, rot_scale: int) -> tuple[int, int]:
+        """(halo_lo, halo_hi): how many rows before / after a row its column queries reach."""
+        used = {s.rotation for c in self.calculations for s in c[2:5] if s.kind in (FIXED, ADVICE, INSTANCE)}
+        offs = [self.rotations[r] * rot_scale for r in used] or [0]
+        return max(0, -min(offs)), max(0, max(offs))
+
     @staticmethod
     def last_info() -> dict:
         from . import halo2
