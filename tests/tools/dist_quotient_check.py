@@ -61,6 +61,15 @@ def main():
         sq.run(values, [t(x) for x in fx], [t(x) for x in ad], [t(x) for x in ins], challenges=ch, y=y)
         torch.cuda.synchronize()
         ok = bool((values.cpu().numpy().view(np.uint64) == want[off:off + rows]).all())
+        # the same with the columns living in padded buffers (only halo rows move)
+        def padded(a):
+            buf, view = sq.alloc_column(rows, dev)
+            view.copy_(t(a))
+            return buf
+        values2 = t(prev)
+        sq.run_padded(values2, [padded(x) for x in fx], [padded(x) for x in ad], [padded(x) for x in ins], challenges=ch, y=y)
+        torch.cuda.synchronize()
+        ok &= bool((values2.cpu().numpy().view(np.uint64) == want[off:off + rows]).all())
         flag = torch.tensor([0 if ok else 1], device=dev)
         dist.all_reduce(flag)
         ok = flag.item() == 0
@@ -79,18 +88,22 @@ def main():
         g.add_horner(ev.ValueSource(ev.PREVIOUS), parts, ev.ValueSource(ev.Y))
         off, rows = zd.row_range(isize, rank, world)
         base = torch.from_numpy(random_field(rows, 900 + rank).view(np.int64)).to(dev)
-        adv = [base.clone() for _ in range(qc)]
-        sel = [base.clone() for _ in range(qc)]
-        values = torch.zeros_like(base)
         yv = random_field(1, 77)[0]
         sq = zd.ShardedQuotient(g, rs)
+        adv, sel = [], []
+        for lst in (adv, sel):
+            for _ in range(qc):
+                buf, view = sq.alloc_column(rows, dev)
+                view.copy_(base)
+                lst.append(buf)
+        values = torch.zeros_like(base)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         best = 1e30
         for it in range(args.iters + 2):
             dist.barrier()
             torch.cuda.synchronize()
             e0.record()
-            sq.run(values, sel, adv, [], y=yv)
+            sq.run_padded(values, sel, adv, [], y=yv)
             e1.record()
             torch.cuda.synchronize()
             if it >= 2:

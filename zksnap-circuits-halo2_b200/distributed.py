@@ -161,6 +161,41 @@ def exchange_halos(slices: list, halo_lo: int, halo_hi: int, group=None) -> list
     return out
 
 
+def exchange_halos_inplace(padded: list, halo_lo: int, halo_hi: int, group=None) -> None:
+    """The same exchange for columns that already live in padded buffers (halo_lo + rows + halo_hi, 4): only the halo rows are
+    written, the rows in the middle are never copied.  This is the layout to keep the extended cosets in when the quotient
+    evaluation is row-sharded: the exchange then moves (halo_lo + halo_hi) x 32 bytes per column and nothing else."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if not padded or (halo_lo == 0 and halo_hi == 0):
+        return
+    rows = padded[0].shape[0] - halo_lo - halo_hi
+    assert halo_lo <= rows and halo_hi <= rows
+    head = torch.stack([t[halo_lo:halo_lo + halo_hi] for t in padded]) if halo_hi else None
+    tail = torch.stack([t[halo_lo + rows - halo_lo:halo_lo + rows] for t in padded]) if halo_lo else None
+    lo = torch.empty_like(tail) if halo_lo else None
+    hi = torch.empty_like(head) if halo_hi else None
+    if world == 1:
+        lo, hi = tail, head
+    else:
+        prev, nxt = (rank - 1) % world, (rank + 1) % world
+        ops = []
+        if halo_hi:
+            ops += [dist.P2POp(dist.isend, head, prev, group), dist.P2POp(dist.irecv, hi, nxt, group)]
+        if halo_lo:
+            ops += [dist.P2POp(dist.isend, tail, nxt, group), dist.P2POp(dist.irecv, lo, prev, group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for c, t in enumerate(padded):
+        if halo_lo:
+            t[:halo_lo].copy_(lo[c])
+        if halo_hi:
+            t[halo_lo + rows:].copy_(hi[c])
+
+
 class ShardedQuotient:
     """evaluate_h's row loop sharded by rows over the GPUs of a box: rank r owns rows [r N/G, (r+1) N/G) of every extended coset
     (the layout the sharded NTT leaves its output in) and of h.  Rotated rows near a shard boundary come from the neighbouring rank:
@@ -189,4 +224,24 @@ class ShardedQuotient:
                                         [t.data_ptr() for t in i], rot_scale=self.rot_scale, window=True, halo_lo=self.halo_lo,
                                         halo_hi=self.halo_hi, stream=stream, **scalars)
         evaluate(values, pf, pa, pi)
+        return values
+
+    def alloc_column(self, rows: int, device=None):
+        """(padded buffer, view of its `rows` data rows): produce the coset slice directly into the view (e.g. as the output of
+        the sharded NTT) and pass the padded buffer to run_padded — no copy of the slice is ever made."""
+        import torch
+
+        buf = torch.empty((self.halo_lo + rows + self.halo_hi, 4), dtype=torch.int64, device=device)
+        return buf, buf[self.halo_lo:self.halo_lo + rows]
+
+    def run_padded(self, values, fixed=(), advice=(), instance=(), **scalars):
+        """Columns are padded buffers from alloc_column; only their halo rows are exchanged and written."""
+        import torch
+
+        cols = list(fixed) + list(advice) + list(instance)
+        exchange_halos_inplace(cols, self.halo_lo, self.halo_hi, self.group)
+        rows = values.shape[0]
+        self.graph.evaluate_dev(values.data_ptr(), rows, [t.data_ptr() for t in fixed], [t.data_ptr() for t in advice],
+                                [t.data_ptr() for t in instance], rot_scale=self.rot_scale, window=True, halo_lo=self.halo_lo,
+                                halo_hi=self.halo_hi, stream=torch.cuda.current_stream().cuda_stream, **scalars)
         return values
