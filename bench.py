@@ -491,6 +491,51 @@ def main():
         parity = parity and sh_ok
         sh.close()
         del d_in, d_out
+    # ---- N > 1: the same quotient evaluation sharded by rows (ring halo exchange over NCCL, then the row window on every rank) ------
+    sq_obj = None
+    if world > 1 and not args.skip_ntt and (world & (world - 1)) == 0:
+        try:
+            srows = (1 << QUOT_LOG_N) // world
+            sq = zdist.ShardedQuotient(gr, 4)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(0x51AB)   # the same rows on every rank: the domain is periodic with period srows, so the sharded result
+            base = torch.randint(0, 1 << 60, (srows, 4), dtype=torch.int64, device=dev, generator=gen)  # must equal a wrapping evaluation of one period
+            bufs = []
+            for _ in range(2 * QUOT_COLS):
+                buf, view = sq.alloc_column(srows, dev)
+                view.copy_(base)
+                bufs.append(buf)
+            sel_b, adv_b = bufs[:QUOT_COLS], bufs[QUOT_COLS:]
+            vals_s = torch.zeros_like(base)
+            sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
+            ref_s = torch.zeros_like(base)
+            plain = [base.clone() for _ in range(2)]
+            gr.evaluate_dev(ref_s.data_ptr(), srows, [plain[0].data_ptr()] * QUOT_COLS, [plain[1].data_ptr()] * QUOT_COLS, y=y_np, rot_scale=4,
+                            stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            sq_ok = bool(torch.equal(vals_s, ref_s))
+            for _ in range(args.warmup):
+                sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
+            barrier()
+            launches4 = zkb.launch_count()
+            e0.record(stream)
+            for _ in range(args.steps):
+                sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
+            e1.record(stream)
+            barrier()
+            qsms = e0.elapsed_time(e1) / args.steps
+            launches += zkb.launch_count() - launches4
+            t = torch.tensor([qsms, 0.0 if sq_ok else 1.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            qsms, sq_ok = float(t[0].item()), t[1].item() == 0.0
+            sq_obj = {"workload": "the quotient workload above, 2^%d rows sharded by rows over %d GPUs" % (QUOT_LOG_N, world),
+                      "value": (1 << QUOT_LOG_N) / (qsms * 1e-3), "unit": "rows/s", "ms_per_step": qsms, "parity_checked": sq_ok,
+                      "exchange": "ring halo exchange, %d + %d rows per column over NCCL point-to-point, then zkb_graph_evaluate_dev on the row window" % (sq.halo_lo, sq.halo_hi),
+                      "halo_bytes_per_rank": (sq.halo_lo + sq.halo_hi) * 32 * 2 * QUOT_COLS}
+            parity = parity and sq_ok
+            del bufs, vals_s, ref_s, plain, base
+        except Exception as exc:  # a secondary object must not take the headline line down
+            sq_obj = {"error": repr(exc)[:300]}
     note("ntt done")
     # ---- CPU baseline on this box (rank 0, N=1 only) ---------------------------------------------------------------------------
     cpu = None
@@ -510,7 +555,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": n * 32 * world,
                     "d2h_bytes_per_step": n_win.value * 128 * world, "timer": "wall clock around the C-ABI call (includes host fold)"},
             "gpu_launches": int(launches), "parity_checked": parity, "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clock_info, "ntt": ntt_obj, "quotient": quot_obj, "sharded_ntt": sharded_obj,
+            "clocks": clock_info, "ntt": ntt_obj, "quotient": quot_obj, "sharded_ntt": sharded_obj, "sharded_quotient": sq_obj,
         }
         print(json.dumps(line))
     params.close()
