@@ -10,7 +10,8 @@ e2e    : the same through the host-buffer C ABI call (zkb_msm_g1_srs): pinned ho
          window sums D2H -> host fold, wall clock (the host fold is part of the call).
 ntt    : secondary object: batched 2^22 Fr NTT (16 columns) elements/s and its HBM roofline.
 quotient: secondary object: evaluate_h's custom-gate pass (halo2-base gate on 4 advice columns, 2^24 extended rows resident in HBM)
-         rows/s and its HBM roofline.
+         rows/s and its HBM roofline.  At N > 1 `sharded_quotient` is the same pass sharded by rows (halo exchange over NCCL) and
+         `sharded_ntt` one 2^26 NTT sharded over the ranks.
 `--impl reference` times the CPU restatement of halo2's best_multiexp (oracle/, all host threads) on a bounded
 sample of the same workload; the reference itself is Rust with un-vendored dependencies and cannot be built
 in this image (DESIGN.md "Oracle").
