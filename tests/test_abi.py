@@ -75,3 +75,26 @@ def test_argument_checks_mirror_rust_asserts():
         zkb.best_fft(a, zkb.omega(4), 4)  # a.len() != 1 << log_n
     with pytest.raises(AssertionError):
         zkb.best_multiexp(a, np.zeros((7, 8), dtype=np.uint64))
+
+
+def test_graph_structs_have_the_c_layout(tmp_path):
+    """The ctypes mirrors of zkb_value_source / zkb_calculation / zkb_graph / zkb_graph_inputs (evaluation.py) against what the
+    C compiler lays out for include/zkb200.h — the oracle and the emulator read the same 11-u32 calculation records."""
+    import ctypes
+    import importlib
+    import subprocess
+    ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "zkb200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(zkb_value_source), sizeof(zkb_calculation),'
+                   ' offsetof(zkb_calculation, b), sizeof(zkb_graph), offsetof(zkb_graph, constants), offsetof(zkb_graph, rotations),'
+                   ' sizeof(zkb_graph_inputs), offsetof(zkb_graph_inputs, challenges), offsetof(zkb_graph_inputs, beta),'
+                   ' offsetof(zkb_graph_inputs, rot_scale)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    c = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    py = [ctypes.sizeof(ev.CValueSource), ctypes.sizeof(ev.CCalculation), ev.CCalculation.b.offset, ctypes.sizeof(ev.CGraph),
+          ev.CGraph.constants.offset, ev.CGraph.rotations.offset, ctypes.sizeof(ev.CGraphInputs), ev.CGraphInputs.challenges.offset,
+          ev.CGraphInputs.beta.offset, ev.CGraphInputs.rot_scale.offset]
+    assert c == py and c[0] == 12 and c[1] == 44
