@@ -521,3 +521,16 @@ def test_graph_row_windows_match_whole_domain(oracle, world, seed):
     idx = np.arange(-lo, rows + hi - 1) % isize   # one row short at the top
     win = [[col[idx] for col in grp] for grp in (fx, ad, ins)]
     assert emu.graph_evaluate(g, win[0], win[1], win[2], ch, None, None, None, y, rs, prev[:rows], halo=(lo, hi - 1))[0] != 0
+
+
+def test_eip196_public_vectors_through_device_code():
+    """EIP-196 precompile vectors (tests/golden/eip196_kats.json) through the device MSM code path on the emulator."""
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "eip196_kats.json")))
+    pt = lambda p: np.array(R.g1_affine_encode((int(p[0], 16), int(p[1], 16))), dtype=np.uint64)  # noqa: E731
+    one = mont([1])[0]
+    for c in kat["add"]:
+        out = emu.msm(np.array([one, one]), np.array([pt(c["a"]), pt(c["b"])]))
+        assert R.g1_jacobian_decode([int(x) for x in out]) == (int(c["sum"][0], 16), int(c["sum"][1], 16))
+    for c in kat["mul"]:
+        out = emu.msm(mont([int(c["s"], 16) % R.FR]), np.array([pt(c["p"])]))
+        assert R.g1_jacobian_decode([int(x) for x in out]) == (int(c["out"][0], 16), int(c["out"][1], 16))

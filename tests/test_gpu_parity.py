@@ -1126,3 +1126,27 @@ def test_sharded_quotient_two_gpus():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 3 and all(l["parity"] for l in lines)
+
+
+def test_eip196_public_vectors():
+    """External known answers for the G1 group law (EIP-196 precompile tests, tests/golden/eip196_kats.json) through
+    best_multiexp on the GPU: a 2-point MSM with unit scalars is the addition, a 1-point MSM the scalar multiplication; also
+    through a registered SRS with the window table."""
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "eip196_kats.json")))
+    one = mont([1])[0]
+    for c in kat["add"]:
+        out = zkb.best_multiexp(np.array([one, one]), np.array([aff((int(c["a"][0], 16), int(c["a"][1], 16))), aff((int(c["b"][0], 16), int(c["b"][1], 16)))]))
+        assert R.g1_jacobian_decode([int(x) for x in out]) == (int(c["sum"][0], 16), int(c["sum"][1], 16))
+    for c in kat["mul"]:
+        p = aff((int(c["p"][0], 16), int(c["p"][1], 16)))
+        s = mont([int(c["s"], 16) % R.FR])
+        want = (int(c["out"][0], 16), int(c["out"][1], 16))
+        assert R.g1_jacobian_decode([int(x) for x in zkb.best_multiexp(s, np.array([p]))]) == want
+        g = np.zeros((64, 8), dtype=np.uint64)
+        g[0] = p
+        zkb.lib().zkb_srs_set_precompute(1)
+        params = zkb.ParamsKZG(6, g)
+        sc = np.zeros((64, 4), dtype=np.uint64)
+        sc[0] = s[0]
+        assert R.g1_jacobian_decode([int(x) for x in params.commit(sc)]) == want
+        params.close()
