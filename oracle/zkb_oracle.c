@@ -14,7 +14,8 @@
  *   ParamsKZG::setup     /root/reference/voter/benches/voter_circuit.rs:60
  *
  * PARITY UNPINNED by reference fixtures (the reference holds no golden vectors for this path).  Pinned
- * instead to first-principles KATs and to the independent big-int twin oracle/pyref.py.
+ * instead to first-principles KATs, to the independent big-int twin oracle/pyref.py and, for the
+ * curve arithmetic, to the public EIP-196 (alt_bn128) precompile vectors in tests/golden/eip196_kats.json.
  *
  * Restated upstream functions (sources not on disk):
  *   halo2curves::bn256::{Fr,Fq}            4x64 Montgomery, canonical outputs        -> fr_* / fq_*
