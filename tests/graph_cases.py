@@ -266,3 +266,39 @@ def random_program(seed, max_len=60):
         if t not in written:
             written.append(t)
     return g, rs
+
+
+def permutation_case(seed, isize, rot_scale, ncols=5, chunk_len=2, last_rotation=-4):
+    """The complete permutation argument (evaluation.permutation_graph) on random columns and its value from the formulas with
+    Python integers.  fixed columns: 0 l_0, 1 l_last, 2 l_active, 3 the coset of X, 4.. the sigma cosets; advice columns:
+    0..ncols-1 the permuted columns, then one product coset z_i per set."""
+    rnd = random.Random(seed)
+    nsets = (ncols + chunk_len - 1) // chunk_len
+    cols = {"fixed": [[rnd.randrange(P) for _ in range(isize)] for _ in range(4 + ncols)],
+            "advice": [[rnd.randrange(P) for _ in range(isize)] for _ in range(ncols + nsets)], "instance": []}
+    columns = [("advice", i) for i in range(ncols)]
+    sigmas = [("fixed", 4 + i) for i in range(ncols)]
+    zs = [("advice", ncols + i) for i in range(nsets)]
+    g = ev.permutation_graph(columns, chunk_len, last_rotation, ("fixed", 0), ("fixed", 1), ("fixed", 2), ("fixed", 3), sigmas, zs)
+    sc = dict(beta=rnd.randrange(P), gamma=rnd.randrange(P), y=rnd.randrange(P))
+    prev = [rnd.randrange(P) for _ in range(isize)]
+    fx, adv = cols["fixed"], cols["advice"]
+    want = []
+    for i in range(isize):
+        nxt, lst = (i + rot_scale) % isize, (i + last_rotation * rot_scale) % isize
+        z = [adv[ncols + s] for s in range(nsets)]
+        terms = [(1 - z[0][i]) * fx[0][i], (z[-1][i] * z[-1][i] - z[-1][i]) * fx[1][i]]
+        terms += [(z[s][i] - z[s - 1][lst]) * fx[0][i] for s in range(1, nsets)]
+        j = 0
+        for s in range(nsets):
+            left, right = z[s][nxt], z[s][i]
+            for col in range(s * chunk_len, min((s + 1) * chunk_len, ncols)):
+                left = left * (adv[col][i] + sc["beta"] * fx[4 + j][i] + sc["gamma"]) % P
+                right = right * (adv[col][i] + pow(ev.DELTA, j, P) * sc["beta"] * fx[3][i] + sc["gamma"]) % P
+                j += 1
+            terms.append((left - right) * fx[2][i])
+        v = prev[i]
+        for t in terms:
+            v = (v * sc["y"] + t) % P
+        want.append(v)
+    return g, cols, sc, prev, want

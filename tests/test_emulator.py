@@ -534,3 +534,32 @@ def test_eip196_public_vectors_through_device_code():
     for c in kat["mul"]:
         out = emu.msm(mont([int(c["s"], 16) % R.FR]), np.array([pt(c["p"])]))
         assert R.g1_jacobian_decode([int(x) for x in out]) == (int(c["out"][0], 16), int(c["out"][1], 16))
+
+
+@pytest.mark.parametrize("ncols,chunk_len,isize", [(5, 2, 64), (1, 2, 16), (4, 2, 32), (7, 3, 32)])
+def test_permutation_argument_graph(oracle, ncols, chunk_len, isize):
+    """evaluation.permutation_graph — every h(X) term of the permutation argument (first / last set, set linking at the last
+    usable row, the two products with the running power of delta) — through the oracle and the device code, against the
+    formulas with Python integers."""
+    g, cols, sc, prev, want = GC.permutation_case(60 + ncols, isize, 4, ncols=ncols, chunk_len=chunk_len)
+    fx, ad = [GC.mont(c) for c in cols["fixed"]], [GC.mont(c) for c in cols["advice"]]
+    b, gm, y = (GC.mont([sc[k]])[0] for k in ("beta", "gamma", "y"))
+    got = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fx, ad, [], None, b, gm, None, y, 4, GC.mont(prev))
+    assert GC.unmont(got) == want
+    rc, out, info = emu.graph_evaluate(g, fx, ad, [], None, b, gm, None, y, 4, GC.mont(prev))
+    assert rc == 0 and (out == got).all()
+
+
+def test_lookup_and_custom_gate_builders_match_the_worked_examples(oracle):
+    """evaluation.lookup_graph / custom_gates_graph build the graphs the worked examples in graph_cases build by hand."""
+    ev = GC.ev
+    g1, cols, sc, prev, want = GC.lookup_case(95, 64, 4)
+    inputs = [("advice", 0, 0), ("prod", ("advice", 1, 0), ("advice", 0, 1))]
+    table = [("fixed", 3, 0), ("scaled", ("fixed", 3, -1), 3)]
+    g2 = ev.lookup_graph(inputs, table, ("fixed", 0), ("fixed", 1), ("fixed", 2), ("advice", 2), ("advice", 3), ("advice", 4))
+    rc, out, _ = emu.graph_evaluate(g2, [GC.mont(c) for c in cols["fixed"]], [GC.mont(c) for c in cols["advice"]], [], None,
+                                    GC.mont([sc["beta"]])[0], GC.mont([sc["gamma"]])[0], GC.mont([sc["theta"]])[0], GC.mont([sc["y"]])[0],
+                                    4, GC.mont(prev))
+    assert rc == 0 and GC.unmont(out) == want
+    gates = [GC.halo2_base_gate(0, 0), GC.halo2_base_gate(1, 1)]
+    assert ev.custom_gates_graph(gates).calculations == GC.build_custom_gates(gates).calculations

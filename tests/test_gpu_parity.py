@@ -1150,3 +1150,13 @@ def test_eip196_public_vectors():
         sc[0] = s[0]
         assert R.g1_jacobian_decode([int(x) for x in params.commit(sc)]) == want
         params.close()
+
+
+@pytest.mark.parametrize("ncols,chunk_len,isize", [(5, 2, 1 << 10), (7, 3, 1 << 12)])
+def test_permutation_argument_graph(ncols, chunk_len, isize):
+    """evaluation.permutation_graph (every h(X) term of the permutation argument) on the GPU against the formulas."""
+    g, cols, sc, prev, want = GC.permutation_case(70 + ncols, isize, 4, ncols=ncols, chunk_len=chunk_len)
+    values = zkb.Polynomial(GC.mont(prev))
+    g.evaluate(values, [zkb.Polynomial(GC.mont(c)) for c in cols["fixed"]], [zkb.Polynomial(GC.mont(c)) for c in cols["advice"]],
+               beta=GC.mont([sc["beta"]])[0], gamma=GC.mont([sc["gamma"]])[0], y=GC.mont([sc["y"]])[0], rot_scale=4)
+    assert GC.unmont(values.to_host()) == want

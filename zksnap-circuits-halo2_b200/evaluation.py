@@ -237,3 +237,87 @@ class GraphEvaluator:
         v = [ctypes.c_uint32(0) for _ in range(4)]
         halo2.check(halo2.lib().zkb_graph_last_info(*[ctypes.byref(x) for x in v]))
         return dict(zip(("instructions", "slots", "polys_read", "bytes_per_row"), [x.value for x in v]))
+
+
+# ---- the hand-written terms of evaluate_h as graphs -------------------------------------------------------------------------------
+# Upstream compiles only the custom gates and the lookups' compressed expressions into GraphEvaluators and writes the permutation
+# and lookup product terms out by hand inside evaluate_h's row loop.  On the device they are graphs over the same value sources
+# (every coset a fixed / advice / instance column), folded into the running value exactly as upstream folds them:
+# value = value * y + term, in upstream's order [UPSTREAM-UNVERIFIED: halo2-axiom is not vendored; the terms are those of the
+# halo2 book's permutation and lookup arguments, the order is the one of halo2_proofs 0.3's evaluate_h].
+DELTA = pow(7, 1 << 28, FR)   # halo2curves bn256::Fr::DELTA = MULTIPLICATIVE_GENERATOR^(2^S)
+
+
+def _col(ref, rot_idx: int) -> ValueSource:
+    kind = {"fixed": FIXED, "advice": ADVICE, "instance": INSTANCE}[ref[0]]
+    return ValueSource(kind, ref[1], rot_idx)
+
+
+def permutation_graph(columns: list, chunk_len: int, last_rotation: int, l0, l_last, l_active, x_coset, sigmas: list, zs: list) -> GraphEvaluator:
+    """All h(X) terms of the permutation argument, folded from the previous value with y:
+        l_0 (1 - z_0)
+        l_last (z_last^2 - z_last)
+        l_0 (z_i - z_{i-1}(w^last_rotation X))                                          for every set i > 0
+        l_active ( z_i(wX) prod_j (col_j + beta sigma_j + gamma) - z_i(X) prod_j (col_j + delta^j beta X + gamma) )   for every set
+    columns: the permutation's columns in order, as ("advice" | "fixed" | "instance", index); they are cut into sets of
+    chunk_len = cs.degree() - 2.  l0, l_last, l_active, x_coset (the coset evaluation of the polynomial X, i.e. zeta w^idx), one
+    sigma coset per column and one product coset z_i per set are given the same way; last_rotation = -(blinding_factors + 1).
+    The power of delta keeps running across the sets, as upstream's `current_delta` does."""
+    g = GraphEvaluator()
+    r0, r1, rl = g.add_rotation(0), g.add_rotation(1), g.add_rotation(last_rotation)
+    sets = [columns[i:i + chunk_len] for i in range(0, len(columns), chunk_len)]
+    assert len(zs) == len(sets) and len(sigmas) == len(columns)
+    beta, gamma, one = ValueSource(BETA), ValueSource(GAMMA), ValueSource(CONSTANT, 1)
+    c = g.add_calculation
+    terms = [c(MUL, c(SUB, one, _col(zs[0], r0)), _col(l0, r0))]
+    zl = _col(zs[-1], r0)
+    terms.append(c(MUL, c(SUB, c(SQUARE, zl), zl), _col(l_last, r0)))
+    for i in range(1, len(sets)):
+        terms.append(c(MUL, c(SUB, _col(zs[i], r0), _col(zs[i - 1], rl)), _col(l0, r0)))
+    bx = c(MUL, beta, _col(x_coset, r0))
+    j = 0
+    for i, cols in enumerate(sets):
+        left, right = _col(zs[i], r1), _col(zs[i], r0)
+        for col in cols:
+            v = _col(col, r0)
+            left = c(MUL, left, c(ADD, c(ADD, v, c(MUL, beta, _col(sigmas[j], r0))), gamma))
+            right = c(MUL, right, c(ADD, c(ADD, v, c(MUL, bx, g.add_constant(pow(DELTA, j, FR)))), gamma))
+            j += 1
+        terms.append(c(MUL, c(SUB, left, right), _col(l_active, r0)))
+    g.add_horner(ValueSource(PREVIOUS), terms, ValueSource(Y))
+    return g
+
+
+def lookup_graph(input_exprs: list, table_exprs: list, l0, l_last, l_active, z, permuted_input, permuted_table) -> GraphEvaluator:
+    """All h(X) terms of one lookup argument, folded from the previous value with y:
+        l_0 (1 - z)        l_last (z^2 - z)
+        l_active ( z(wX) (a' + beta) (s' + gamma) - z(X) (A + beta) (S + gamma) )
+        l_0 (a' - s')      l_active (a' - s') (a' - a'(w^-1 X))
+    A, S: the input / table expressions compressed with theta (Horner from zero), as upstream's per-lookup GraphEvaluator does."""
+    g = GraphEvaluator()
+    theta, beta, gamma, one = ValueSource(THETA), ValueSource(BETA), ValueSource(GAMMA), ValueSource(CONSTANT, 1)
+    c = g.add_calculation
+
+    def compress(exprs):
+        return g.add_horner(ValueSource(CONSTANT, 0), [g.add_expression(e) for e in exprs], theta)
+
+    A, S = compress(input_exprs), compress(table_exprs)
+    r0, r1, rm1 = g.add_rotation(0), g.add_rotation(1), g.add_rotation(-1)
+    zz, zw = _col(z, r0), _col(z, r1)
+    ap, apm, sp = _col(permuted_input, r0), _col(permuted_input, rm1), _col(permuted_table, r0)
+    d = c(SUB, ap, sp)
+    terms = [c(MUL, c(SUB, one, zz), _col(l0, r0)),
+             c(MUL, c(SUB, c(SQUARE, zz), zz), _col(l_last, r0)),
+             c(MUL, c(SUB, c(MUL, c(MUL, zw, c(ADD, ap, beta)), c(ADD, sp, gamma)), c(MUL, c(MUL, zz, c(ADD, A, beta)), c(ADD, S, gamma))), _col(l_active, r0)),
+             c(MUL, d, _col(l0, r0)),
+             c(MUL, c(MUL, d, c(SUB, ap, apm)), _col(l_active, r0))]
+    g.add_horner(ValueSource(PREVIOUS), terms, ValueSource(Y))
+    return g
+
+
+def custom_gates_graph(gate_polys: list) -> GraphEvaluator:
+    """evaluate_h's `custom_gates` evaluator: every gate polynomial compiled with add_expression, then
+    Horner(PreviousValue, parts, Y)."""
+    g = GraphEvaluator()
+    g.add_horner(ValueSource(PREVIOUS), [g.add_expression(e) for e in gate_polys], ValueSource(Y))
+    return g
