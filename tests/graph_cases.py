@@ -302,3 +302,28 @@ def permutation_case(seed, isize, rot_scale, ncols=5, chunk_len=2, last_rotation
             v = (v * sc["y"] + t) % P
         want.append(v)
     return g, cols, sc, prev, want
+
+
+def satisfied_gate_witness(k, seed, break_cell=None):
+    """A witness column for halo2-base's gate on n = 2^k rows: the selector is on at rows 0, 4, 8, ... and every gate
+    w[i] + w[i+1] w[i+2] - w[i+3] = 0 holds (break_cell: one cell is changed afterwards).  -> (w, q) as integer lists"""
+    rnd = random.Random(seed)
+    n = 1 << k
+    w, q = [0] * n, [0] * n
+    for j in range(0, n, 4):
+        a, b, c = (rnd.randrange(P) for _ in range(3))
+        w[j:j + 4] = [a, b, c, (a + b * c) % P]
+        q[j] = 1
+    if break_cell is not None:
+        w[break_cell] = (w[break_cell] + 1) % P
+    return w, q
+
+
+def vanishing_inverse_on_coset(k, ek):
+    """1 / (X^n - 1) at the points zeta w_ext^i of the extended coset, i = 0 .. 2^ek - 1 (upstream's t_evaluations, inverted)."""
+    n, N = 1 << k, 1 << ek
+    zeta = pow(7, 2 * (P - 1) // 3, P)   # halo2curves bn256::Fr::ZETA, the coset generator (SURVEY.md §8)
+    w_ext = R.omega_for(ek)
+    period = N // n
+    vals = [pow(pow(zeta, n, P) * pow(w_ext, i * n, P) % P - 1, P - 2, P) for i in range(period)]
+    return [vals[i % period] for i in range(N)]

@@ -563,3 +563,28 @@ def test_lookup_and_custom_gate_builders_match_the_worked_examples(oracle):
     assert rc == 0 and GC.unmont(out) == want
     gates = [GC.halo2_base_gate(0, 0), GC.halo2_base_gate(1, 1)]
     assert ev.custom_gates_graph(gates).calculations == GC.build_custom_gates(gates).calculations
+
+
+def test_quotient_of_a_satisfied_circuit_is_a_polynomial(oracle):
+    """The prover's reason for evaluate_h, end to end on the CPU: a witness that satisfies halo2-base's gate on every row of the
+    domain makes the numerator q (a + b c - d) vanish there, so its coset evaluations — advice and selector through
+    lagrange_to_coeff and coeff_to_extended (oracle), the gate through the device interpreter with rot_scale = 2^(ek - k)
+    (emulator) — divided by X^n - 1 are the coset evaluations of a polynomial of degree < 2n: extended_to_coeff returns zeros
+    from coefficient 2n on.  One wrong witness cell and the high coefficients are no longer zero."""
+    k, ek = 5, 7
+    n = 1 << k
+    g = GC.build_custom_gates([GC.halo2_base_gate()])
+    tinv = GC.vanishing_inverse_on_coset(k, ek)
+    for broken in (None, 9):
+        w, q = GC.satisfied_gate_witness(k, 321, break_cell=broken)
+        W = oracle.coeff_to_extended(oracle.lagrange_to_coeff(GC.mont(w), k), k, ek)
+        Q = oracle.coeff_to_extended(oracle.lagrange_to_coeff(GC.mont(q), k), k, ek)
+        rc, num, _ = emu.graph_evaluate(g, [Q], [W], [], None, None, None, None, GC.mont([1])[0], 1 << (ek - k), np.zeros((1 << ek, 4), dtype=np.uint64))
+        assert rc == 0
+        h_evals = GC.mont([a * b % R.FR for a, b in zip(GC.unmont(num), tinv)])
+        h = GC.unmont(oracle.extended_to_coeff(h_evals, k, ek))
+        assert len(h) >= 3 * n
+        if broken is None:
+            assert any(h[:2 * n]) and not any(h[2 * n:])
+        else:
+            assert any(h[2 * n:])

@@ -1160,3 +1160,29 @@ def test_permutation_argument_graph(ncols, chunk_len, isize):
     g.evaluate(values, [zkb.Polynomial(GC.mont(c)) for c in cols["fixed"]], [zkb.Polynomial(GC.mont(c)) for c in cols["advice"]],
                beta=GC.mont([sc["beta"]])[0], gamma=GC.mont([sc["gamma"]])[0], y=GC.mont([sc["y"]])[0], rot_scale=4)
     assert GC.unmont(values.to_host()) == want
+
+
+def test_quotient_of_a_satisfied_circuit_is_a_polynomial():
+    """evaluate_h's purpose, end to end on resident polynomials: witness and selector (Lagrange) -> lagrange_to_coeff ->
+    coeff_to_extended -> the gate on the coset (rot_scale = 4) -> times 1 / (X^n - 1) -> extended_to_coeff: a satisfying witness
+    gives a quotient of degree < 2n (zeros from coefficient 2n on), one wrong cell does not."""
+    k = 12
+    n = 1 << k
+    d = zkb.EvaluationDomain(4, k)
+    g = GC.build_custom_gates([GC.halo2_base_gate()])
+    T = zkb.Polynomial(GC.mont(GC.vanishing_inverse_on_coset(k, d.extended_k)))
+    one = mont([1])[0]
+    for broken in (None, 1234):
+        w, q = GC.satisfied_gate_witness(k, 654, break_cell=broken)
+        W = zkb.Polynomial(GC.mont(w)).lagrange_to_coeff(d).coeff_to_extended(d)
+        Q = zkb.Polynomial(GC.mont(q)).lagrange_to_coeff(d).coeff_to_extended(d)
+        h = zkb.Polynomial(np.zeros((d.extended_len(), 4), dtype=np.uint64))
+        g.evaluate(h, fixed=[Q], advice=[W], y=one, rot_scale=1 << (d.extended_k - k))
+        h.mul(T).extended_to_coeff(d)
+        coeffs = h.to_host()
+        if broken is None:
+            assert coeffs[:2 * n].any() and not coeffs[2 * n:].any()
+        else:
+            assert coeffs[2 * n:3 * n].any()
+        for p in (W, Q, h):
+            p.free()
