@@ -195,8 +195,11 @@ class GraphEvaluator {
     // op: ZKB_CALC_{ADD, SUB, MUL, SQUARE, DOUBLE, NEGATE, STORE}; an identical earlier calculation is reused
     zkb_value_source add_calculation(uint32_t op, zkb_value_source a, zkb_value_source b = {ZKB_SRC_CONSTANT, 0, 0}) {
         auto same = [](const zkb_value_source& x, const zkb_value_source& y) { return x.kind == y.kind && x.index == y.index && x.rotation == y.rotation; };
-        for (const auto& c : calculations)
-            if (c.op == op && op != ZKB_CALC_MUL_ADD && same(c.a, a) && same(c.b, b)) return ValueSource::Intermediate(c.target);
+        for (size_t i : made_by_add_calculation_) {  // a Horner's Store is not a candidate: its target is rewritten by the steps
+            const auto& c = calculations[i];
+            if (c.op == op && same(c.a, a) && same(c.b, b)) return ValueSource::Intermediate(c.target);
+        }
+        made_by_add_calculation_.push_back(calculations.size());
         calculations.push_back({op, num_intermediates, a, b, {ZKB_SRC_CONSTANT, 0, 0}});
         return ValueSource::Intermediate(num_intermediates++);
     }
@@ -206,6 +209,8 @@ class GraphEvaluator {
         for (const auto& p : parts) calculations.push_back({ZKB_CALC_MUL_ADD, t, ValueSource::Intermediate(t), factor, p});
         return ValueSource::Intermediate(t);
     }
+
+    std::vector<size_t> made_by_add_calculation_;
 
     struct Scalars {
         const Fr* beta = nullptr;

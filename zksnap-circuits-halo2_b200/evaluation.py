@@ -76,6 +76,7 @@ class GraphEvaluator:
         self.rotations: list[int] = []
         self.calculations: list[tuple] = []   # (op, target, a, b, c)
         self.num_intermediates = 0
+        self._existing: dict[tuple, int] = {}  # (op, a, b) -> target of the calculation add_calculation made for it
 
     # ---- upstream's builders ---------------------------------------------------------------------------------------
     def add_rotation(self, rotation: int) -> int:
@@ -93,13 +94,13 @@ class GraphEvaluator:
     def add_calculation(self, op: int, a: ValueSource, b: ValueSource | None = None) -> ValueSource:
         """An identical earlier calculation is reused (upstream's `existing_calculation`)."""
         z = ValueSource(CONSTANT, 0)
-        key = (op, a, b or z, z)
-        for c in self.calculations:
-            if (c[0], c[2], c[3], c[4]) == key and c[0] != MUL_ADD:
-                return ValueSource(INTERMEDIATE, c[1])
+        key = (op, a, b or z)
+        if key in self._existing:
+            return ValueSource(INTERMEDIATE, self._existing[key])
         target = self.num_intermediates
         self.num_intermediates += 1
         self.calculations.append((op, target, a, b or z, z))
+        self._existing[key] = target
         return ValueSource(INTERMEDIATE, target)
 
     def add_horner(self, start: ValueSource, parts: list[ValueSource], factor: ValueSource) -> ValueSource:
