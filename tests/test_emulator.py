@@ -588,3 +588,62 @@ def test_quotient_of_a_satisfied_circuit_is_a_polynomial(oracle):
             assert any(h[:2 * n]) and not any(h[2 * n:])
         else:
             assert any(h[2 * n:])
+
+
+def test_quotient_evaluator_evaluate_h_against_the_formulas(oracle):
+    """evaluation.QuotientEvaluator.evaluate_h — custom gates, then the permutation argument, then a lookup, each folded with y —
+    with the per-graph call run by the emulator, against h computed row by row from the formulas with Python integers and
+    explicit column data (no graphs, no column-layout code)."""
+    import random
+    ev = GC.ev
+    P = R.FR
+    rnd = random.Random(2024)
+    isize, rs, chunk_len, last_rot = 64, 4, 2, -3
+    col = lambda: [rnd.randrange(P) for _ in range(isize)]  # noqa: E731
+    fixed, advice, instance = [col(), col()], [col(), col(), col()], [col()]
+    l0, l_last, l_active, xc = col(), col(), col(), col()
+    perm_cols = [("advice", 0), ("advice", 2), ("instance", 0)]
+    sigmas, zs = [col() for _ in perm_cols], [col(), col()]
+    lz, la, ls = col(), col(), col()
+    gates = [GC.halo2_base_gate(1, 0), ("sum", ("prod", ("advice", 0, -1), ("fixed", 1, 0)), ("neg", ("instance", 0, 2)))]
+    l_in, l_tab = [("advice", 1, 0), ("advice", 2, 1)], [("fixed", 0, 0), ("fixed", 1, -1)]
+    y, beta, gamma, theta = (rnd.randrange(P) for _ in range(4))
+    data = {"fixed": fixed, "advice": advice, "instance": instance}
+    want = []
+    for i in range(isize):
+        at = lambda c, r=0: c[(i + r * rs) % isize]  # noqa: E731
+        v = GC.custom_gates_value(gates, data, [], y, 0, i, rs, isize)
+        pv = [data[k][j] for k, j in perm_cols]
+        terms = [(1 - at(zs[0])) * at(l0), (at(zs[1]) ** 2 - at(zs[1])) * at(l_last), (at(zs[1]) - at(zs[0], last_rot)) * at(l0)]
+        j = 0
+        for s in range(2):
+            left, right = at(zs[s], 1), at(zs[s])
+            for c in pv[s * chunk_len:(s + 1) * chunk_len]:
+                left = left * (at(c) + beta * at(sigmas[j]) + gamma) % P
+                right = right * (at(c) + pow(ev.DELTA, j, P) * beta * at(xc) + gamma) % P
+                j += 1
+            terms.append((left - right) * at(l_active))
+        A = (at(advice[1]) * theta + at(advice[2], 1)) % P
+        S = (at(fixed[0]) * theta + at(fixed[1], -1)) % P
+        d = at(la) - at(ls)
+        terms += [(1 - at(lz)) * at(l0), (at(lz) ** 2 - at(lz)) * at(l_last),
+                  (at(lz, 1) * (at(la) + beta) * (at(ls) + gamma) - at(lz) * (A + beta) * (S + gamma)) * at(l_active),
+                  d * at(l0), d * (at(la) - at(la, -1)) * at(l_active)]
+        for t in terms:
+            v = (v * y + t) % P
+        want.append(v)
+
+    m = GC.mont
+    sc = {k: m([val])[0] for k, val in dict(y=y, beta=beta, gamma=gamma, theta=theta).items()}
+    state = {"values": np.zeros((isize, 4), dtype=np.uint64)}
+
+    def evaluate(graph, values, f, a, i):   # the per-graph call on the emulator (values is the running array)
+        rc, out, _ = emu.graph_evaluate(graph, f, a, i, None, sc["beta"], sc["gamma"], sc["theta"], sc["y"], rs, state["values"])
+        assert rc == 0
+        state["values"] = out
+
+    q = ev.QuotientEvaluator(gates, dict(columns=perm_cols, chunk_len=chunk_len, last_rotation=last_rot), [(l_in, l_tab)])
+    q.evaluate_h(None, [m(c) for c in fixed], [m(c) for c in advice], [m(c) for c in instance], None, sc["y"], sc["beta"], sc["gamma"],
+                 sc["theta"], rs, m(l0), m(l_last), m(l_active), m(xc), [m(c) for c in sigmas], [m(c) for c in zs], [(m(lz), m(la), m(ls))],
+                 evaluate=evaluate)
+    assert GC.unmont(state["values"]) == want

@@ -322,3 +322,45 @@ def custom_gates_graph(gate_polys: list) -> GraphEvaluator:
     g = GraphEvaluator()
     g.add_horner(ValueSource(PREVIOUS), [g.add_expression(e) for e in gate_polys], ValueSource(Y))
     return g
+
+
+class QuotientEvaluator:
+    """`plonk::evaluation::Evaluator` with its `evaluate_h`: the custom gates, then the permutation argument, then every lookup,
+    each folded into the running value with y, over cosets resident in HBM.  Construction compiles the graphs that do not depend
+    on where the auxiliary cosets sit; `evaluate_h` appends l_0 / l_last / l_active / the coset of X / the sigma cosets to the
+    fixed columns and the product / permuted cosets to the advice columns and runs one zkb_graph_evaluate per argument.
+
+    permutation: None or dict(columns=[("advice" | "fixed" | "instance", index), ...], chunk_len=cs.degree() - 2,
+    last_rotation=-(blinding_factors + 1));  lookups: [(input_expressions, table_expressions), ...]."""
+
+    def __init__(self, gate_polys: list, permutation: dict | None = None, lookups: list | tuple = ()):
+        self.custom_gates = custom_gates_graph(gate_polys) if gate_polys else None
+        self.permutation = permutation
+        self.lookups = list(lookups)
+
+    def evaluate_h(self, values, fixed, advice, instance, challenges, y, beta, gamma, theta, rot_scale, l0, l_last, l_active,
+                   x_coset=None, sigma_cosets=(), permutation_product_cosets=(), lookup_cosets=(), evaluate=None):
+        """values: the running h evaluations (start from zeros), overwritten.  lookup_cosets: per lookup (product, permuted
+        input, permuted table).  `evaluate(graph, values, fixed, advice, instance)` is the per-graph call; the default is the
+        device (GraphEvaluator.evaluate on halo2.Polynomial handles)."""
+        if evaluate is None:
+            def evaluate(graph, v, f, a, i):
+                graph.evaluate(v, f, a, i, challenges=challenges, beta=beta, gamma=gamma, theta=theta, y=y, rot_scale=rot_scale)
+        fixed, advice, instance = list(fixed), list(advice), list(instance)
+        if self.custom_gates is not None:
+            evaluate(self.custom_gates, values, fixed, advice, instance)
+        nf, na = len(fixed), len(advice)
+        aux = [l0, l_last, l_active]           # fixed columns nf, nf + 1, nf + 2 for every argument below
+        if self.permutation is not None:
+            p = self.permutation
+            ncols = len(p["columns"])
+            nsets = (ncols + p["chunk_len"] - 1) // p["chunk_len"]
+            assert x_coset is not None and len(sigma_cosets) == ncols and len(permutation_product_cosets) == nsets
+            g = permutation_graph(p["columns"], p["chunk_len"], p["last_rotation"], ("fixed", nf), ("fixed", nf + 1), ("fixed", nf + 2),
+                                  ("fixed", nf + 3), [("fixed", nf + 4 + j) for j in range(ncols)], [("advice", na + s) for s in range(nsets)])
+            evaluate(g, values, fixed + aux + [x_coset] + list(sigma_cosets), advice + list(permutation_product_cosets), instance)
+        assert len(lookup_cosets) == len(self.lookups)
+        for (inputs, table), (z, a_perm, s_perm) in zip(self.lookups, lookup_cosets):
+            g = lookup_graph(inputs, table, ("fixed", nf), ("fixed", nf + 1), ("fixed", nf + 2), ("advice", na), ("advice", na + 1), ("advice", na + 2))
+            evaluate(g, values, fixed + aux, advice + [z, a_perm, s_perm], instance)
+        return values
