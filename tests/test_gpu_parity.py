@@ -1186,3 +1186,35 @@ def test_quotient_of_a_satisfied_circuit_is_a_polynomial():
             assert coeffs[2 * n:3 * n].any()
         for p in (W, Q, h):
             p.free()
+
+
+def test_quotient_evaluator_evaluate_h_on_resident_cosets(oracle):
+    """QuotientEvaluator.evaluate_h on the device (default per-graph call: zkb_graph_evaluate on handles) against the same chain
+    of graphs evaluated by the oracle."""
+    import random
+    ev = GC.ev
+    rnd = random.Random(2025)
+    isize, rs = 1 << 10, 4
+    col = lambda s: random_field(isize, s)  # noqa: E731
+    fixed, advice, instance = [col(1), col(2)], [col(3), col(4), col(5)], [col(6)]
+    l0, l_last, l_active, xc = col(7), col(8), col(9), col(10)
+    perm_cols = [("advice", 0), ("advice", 2), ("instance", 0)]
+    sigmas, zs = [col(11 + i) for i in range(3)], [col(20), col(21)]
+    lz, la, ls = col(30), col(31), col(32)
+    gates = [GC.halo2_base_gate(1, 0), ("sum", ("prod", ("advice", 0, -1), ("fixed", 1, 0)), ("neg", ("instance", 0, 2)))]
+    l_in, l_tab = [("advice", 1, 0), ("advice", 2, 1)], [("fixed", 0, 0), ("fixed", 1, -1)]
+    y, beta, gamma, theta = random_field(4, 40)
+    q = ev.QuotientEvaluator(gates, dict(columns=perm_cols, chunk_len=2, last_rotation=-3), [(l_in, l_tab)])
+    state = {"v": np.zeros((isize, 4), dtype=np.uint64)}
+
+    def oracle_eval(graph, values, f, a, i):
+        state["v"] = oracle.graph_evaluate(graph.calc_array(), graph.num_intermediates, GC.mont(graph.constants), graph.rotations, f, a, i,
+                                           None, beta, gamma, theta, y, rs, state["v"])
+
+    q.evaluate_h(None, fixed, advice, instance, None, y, beta, gamma, theta, rs, l0, l_last, l_active, xc, sigmas, zs, [(lz, la, ls)],
+                 evaluate=oracle_eval)
+    P = zkb.Polynomial
+    values = P(np.zeros((isize, 4), dtype=np.uint64))
+    q.evaluate_h(values, [P(c) for c in fixed], [P(c) for c in advice], [P(c) for c in instance], None, y, beta, gamma, theta, rs,
+                 P(l0), P(l_last), P(l_active), P(xc), [P(c) for c in sigmas], [P(c) for c in zs], [(P(lz), P(la), P(ls))])
+    assert (values.to_host() == state["v"]).all()
