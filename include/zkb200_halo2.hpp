@@ -13,6 +13,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -132,6 +133,86 @@ class ParamsKZG {
     uint64_t h_g_ = 0, h_gl_ = 0;
 };
 
+// ---- host arithmetic on bn256::Fr Montgomery limbs: only for the constants of a graph (negated constants, powers of DELTA) ------
+namespace fr {
+constexpr Fr MOD = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+constexpr Fr R2 = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull};
+constexpr Fr ONE = {0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full};
+constexpr Fr DELTA = {0x9a0c322befd78855ull, 0x46e82d14249b563cull, 0x5983a663e0b0b7a7ull, 0x22ab452baaa111adull};  // 7^(2^28)
+constexpr uint64_t INV = 0xc2e1f593efffffffull;  // -r^-1 mod 2^64
+inline bool geq(const Fr& a, const Fr& b) {
+    for (int i = 3; i >= 0; --i)
+        if (a[i] != b[i]) return a[i] > b[i];
+    return true;
+}
+inline Fr sub_raw(const Fr& a, const Fr& b) {
+    Fr r;
+    unsigned __int128 borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned __int128 d = (unsigned __int128)a[i] - b[i] - borrow;
+        r[i] = (uint64_t)d;
+        borrow = (d >> 64) & 1;
+    }
+    return r;
+}
+inline Fr add(const Fr& a, const Fr& b) {
+    Fr r;
+    unsigned __int128 carry = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned __int128 t = (unsigned __int128)a[i] + b[i] + carry;
+        r[i] = (uint64_t)t;
+        carry = t >> 64;
+    }
+    return geq(r, MOD) ? sub_raw(r, MOD) : r;  // 2r < 2^256: no carry out
+}
+inline Fr neg(const Fr& a) { return a == Fr{0, 0, 0, 0} ? a : sub_raw(MOD, a); }
+inline Fr mul(const Fr& a, const Fr& b) {  // CIOS
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        unsigned __int128 c = 0;
+        for (int j = 0; j < 4; ++j) {
+            c += (unsigned __int128)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        const uint64_t m = t[0] * INV;
+        c = (unsigned __int128)m * MOD[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; ++j) {
+            c += (unsigned __int128)m * MOD[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    Fr r = {t[0], t[1], t[2], t[3]};
+    return (t[4] || geq(r, MOD)) ? sub_raw(r, MOD) : r;
+}
+inline Fr from_u64(uint64_t v) { return mul(Fr{v, 0, 0, 0}, R2); }
+}  // namespace fr
+
+// plonk::Expression without selectors (substituted before evaluate_h runs)
+struct Expression {
+    enum Kind { Constant, Fixed, Advice, Instance, Challenge, Negated, Sum, Product, Scaled } kind;
+    Fr constant{};           // Constant: the value; Scaled: the factor (Montgomery)
+    uint32_t index = 0;      // column / challenge
+    int32_t rotation = 0;
+    std::shared_ptr<const Expression> a, b;
+    using Ptr = std::shared_ptr<const Expression>;
+    static Ptr constant_(const Fr& c) { auto e = std::make_shared<Expression>(); e->kind = Constant; e->constant = c; return e; }
+    static Ptr query(Kind k, uint32_t column, int32_t rot) { auto e = std::make_shared<Expression>(); e->kind = k; e->index = column; e->rotation = rot; return e; }
+    static Ptr challenge(uint32_t i) { auto e = std::make_shared<Expression>(); e->kind = Challenge; e->index = i; return e; }
+    static Ptr neg(Ptr x) { auto e = std::make_shared<Expression>(); e->kind = Negated; e->a = std::move(x); return e; }
+    static Ptr sum(Ptr x, Ptr y) { auto e = std::make_shared<Expression>(); e->kind = Sum; e->a = std::move(x); e->b = std::move(y); return e; }
+    static Ptr product(Ptr x, Ptr y) { auto e = std::make_shared<Expression>(); e->kind = Product; e->a = std::move(x); e->b = std::move(y); return e; }
+    static Ptr scaled(Ptr x, const Fr& f) { auto e = std::make_shared<Expression>(); e->kind = Scaled; e->a = std::move(x); e->constant = f; return e; }
+};
+
 // A polynomial / column of evaluations resident in HBM (zkb_poly_*): uploaded once, used by handle.
 class Polynomial {
    public:
@@ -210,6 +291,68 @@ class GraphEvaluator {
         return ValueSource::Intermediate(t);
     }
 
+
+    // GraphEvaluator::default(): constants [0, 1, 2]
+    static GraphEvaluator with_default_constants() {
+        GraphEvaluator g;
+        g.constants = {Fr{0, 0, 0, 0}, fr::ONE, fr::add(fr::ONE, fr::ONE)};
+        return g;
+    }
+    bool is_constant(const zkb_value_source& v, const Fr& c) const { return v.kind == ZKB_SRC_CONSTANT && constants[v.index] == c; }
+    static bool less(const zkb_value_source& x, const zkb_value_source& y) {
+        if (x.kind != y.kind) return x.kind < y.kind;
+        if (x.index != y.index) return x.index < y.index;
+        return x.rotation < y.rotation;
+    }
+    static bool same_source(const zkb_value_source& x, const zkb_value_source& y) { return x.kind == y.kind && x.index == y.index && x.rotation == y.rotation; }
+    // GraphEvaluator::add_expression with upstream's special cases (0, 1, 2, a + (-b) -> Sub, x * x -> Square, ordered operands);
+    // needs the default constants
+    zkb_value_source add_expression(const Expression& e) {
+        const Fr zero{0, 0, 0, 0}, one = fr::ONE, two = fr::add(fr::ONE, fr::ONE);
+        switch (e.kind) {
+            case Expression::Constant: return add_constant(e.constant);
+            case Expression::Fixed: return add_calculation(ZKB_CALC_STORE, ValueSource::Fixed(e.index, add_rotation(e.rotation)));
+            case Expression::Advice: return add_calculation(ZKB_CALC_STORE, ValueSource::Advice(e.index, add_rotation(e.rotation)));
+            case Expression::Instance: return add_calculation(ZKB_CALC_STORE, ValueSource::Instance(e.index, add_rotation(e.rotation)));
+            case Expression::Challenge: return add_calculation(ZKB_CALC_STORE, ValueSource::Challenge(e.index));
+            case Expression::Negated: {
+                if (e.a->kind == Expression::Constant) return add_constant(fr::neg(e.a->constant));
+                const auto r = add_expression(*e.a);
+                return is_constant(r, zero) ? r : add_calculation(ZKB_CALC_NEGATE, r);
+            }
+            case Expression::Sum: {
+                if (e.b->kind == Expression::Negated || e.a->kind == Expression::Negated) {
+                    const bool b_neg = e.b->kind == Expression::Negated;
+                    const auto rp = add_expression(b_neg ? *e.a : *e.b);
+                    const auto rn = add_expression(b_neg ? *e.b->a : *e.a->a);
+                    if (is_constant(rp, zero)) return add_calculation(ZKB_CALC_NEGATE, rn);
+                    if (is_constant(rn, zero)) return rp;
+                    return add_calculation(ZKB_CALC_SUB, rp, rn);
+                }
+                const auto ra = add_expression(*e.a), rb = add_expression(*e.b);
+                if (is_constant(ra, zero)) return rb;
+                if (is_constant(rb, zero)) return ra;
+                return less(rb, ra) ? add_calculation(ZKB_CALC_ADD, rb, ra) : add_calculation(ZKB_CALC_ADD, ra, rb);
+            }
+            case Expression::Product: {
+                const auto ra = add_expression(*e.a), rb = add_expression(*e.b);
+                if (is_constant(ra, zero) || is_constant(rb, zero)) return ValueSource::Constant(0);
+                if (is_constant(ra, one)) return rb;
+                if (is_constant(rb, one)) return ra;
+                if (is_constant(ra, two)) return add_calculation(ZKB_CALC_DOUBLE, rb);
+                if (is_constant(rb, two)) return add_calculation(ZKB_CALC_DOUBLE, ra);
+                if (same_source(ra, rb)) return add_calculation(ZKB_CALC_SQUARE, ra);
+                return less(rb, ra) ? add_calculation(ZKB_CALC_MUL, rb, ra) : add_calculation(ZKB_CALC_MUL, ra, rb);
+            }
+            case Expression::Scaled: {
+                if (e.constant == zero) return ValueSource::Constant(0);
+                if (e.constant == one) return add_expression(*e.a);
+                const auto cst = add_constant(e.constant);
+                return add_calculation(ZKB_CALC_MUL, add_expression(*e.a), cst);
+            }
+        }
+        throw std::logic_error("unknown expression");
+    }
     std::vector<size_t> made_by_add_calculation_;
 
     struct Scalars {
@@ -236,5 +379,84 @@ class GraphEvaluator {
         check(zkb_graph_evaluate(&g, &inp, values.handle()), "GraphEvaluator::evaluate");
     }
 };
+
+// The custom gates, the permutation argument and one lookup argument as graphs, folded from the previous value with y in
+// upstream's term order (the mirror of zksnap-circuits-halo2_b200/evaluation.py, which documents the formulas).
+struct ColumnRef {
+    uint32_t kind;   // ZKB_SRC_FIXED / ZKB_SRC_ADVICE / ZKB_SRC_INSTANCE
+    uint32_t index;
+    zkb_value_source at(uint32_t rot_idx) const { return {kind, index, rot_idx}; }
+};
+
+inline GraphEvaluator custom_gates_graph(const std::vector<Expression::Ptr>& gate_polys) {
+    GraphEvaluator g = GraphEvaluator::with_default_constants();
+    std::vector<zkb_value_source> parts;
+    for (const auto& e : gate_polys) parts.push_back(g.add_expression(*e));
+    g.add_horner(ValueSource::PreviousValue(), parts, ValueSource::Y());
+    return g;
+}
+
+inline GraphEvaluator permutation_graph(const std::vector<ColumnRef>& columns, size_t chunk_len, int32_t last_rotation, ColumnRef l0,
+                                        ColumnRef l_last, ColumnRef l_active, ColumnRef x_coset, const std::vector<ColumnRef>& sigmas,
+                                        const std::vector<ColumnRef>& zs) {
+    GraphEvaluator g = GraphEvaluator::with_default_constants();
+    const uint32_t r0 = g.add_rotation(0), r1 = g.add_rotation(1), rl = g.add_rotation(last_rotation);
+    const size_t nsets = (columns.size() + chunk_len - 1) / chunk_len;
+    if (zs.size() != nsets || sigmas.size() != columns.size()) throw std::invalid_argument("permutation_graph: one sigma per column, one z per set");
+    const auto beta = ValueSource::Beta(), gamma = ValueSource::Gamma(), one = ValueSource::Constant(1);
+    auto c = [&](uint32_t op, zkb_value_source a, zkb_value_source b = {ZKB_SRC_CONSTANT, 0, 0}) { return g.add_calculation(op, a, b); };
+    std::vector<zkb_value_source> terms;
+    terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, one, zs[0].at(r0)), l0.at(r0)));
+    const auto zl = zs.back().at(r0);
+    terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, c(ZKB_CALC_SQUARE, zl), zl), l_last.at(r0)));
+    for (size_t i = 1; i < nsets; ++i) terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, zs[i].at(r0), zs[i - 1].at(rl)), l0.at(r0)));
+    const auto bx = c(ZKB_CALC_MUL, beta, x_coset.at(r0));
+    Fr delta_pow = fr::ONE;
+    size_t j = 0;
+    for (size_t i = 0; i < nsets; ++i) {
+        auto left = zs[i].at(r1), right = zs[i].at(r0);
+        for (size_t k = i * chunk_len; k < columns.size() && k < (i + 1) * chunk_len; ++k, ++j) {
+            const auto v = columns[k].at(r0);
+            left = c(ZKB_CALC_MUL, left, c(ZKB_CALC_ADD, c(ZKB_CALC_ADD, v, c(ZKB_CALC_MUL, beta, sigmas[j].at(r0))), gamma));
+            right = c(ZKB_CALC_MUL, right, c(ZKB_CALC_ADD, c(ZKB_CALC_ADD, v, c(ZKB_CALC_MUL, bx, g.add_constant(delta_pow))), gamma));
+            delta_pow = fr::mul(delta_pow, fr::DELTA);
+        }
+        terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, left, right), l_active.at(r0)));
+    }
+    g.add_horner(ValueSource::PreviousValue(), terms, ValueSource::Y());
+    return g;
+}
+
+inline GraphEvaluator lookup_graph(const std::vector<Expression::Ptr>& input_exprs, const std::vector<Expression::Ptr>& table_exprs, ColumnRef l0,
+                                   ColumnRef l_last, ColumnRef l_active, ColumnRef z, ColumnRef permuted_input, ColumnRef permuted_table) {
+    GraphEvaluator g = GraphEvaluator::with_default_constants();
+    const auto theta = ValueSource::Theta(), beta = ValueSource::Beta(), gamma = ValueSource::Gamma(), one = ValueSource::Constant(1);
+    auto c = [&](uint32_t op, zkb_value_source a, zkb_value_source b = {ZKB_SRC_CONSTANT, 0, 0}) { return g.add_calculation(op, a, b); };
+    auto compress = [&](const std::vector<Expression::Ptr>& exprs) {
+        std::vector<zkb_value_source> parts;
+        for (const auto& e : exprs) parts.push_back(g.add_expression(*e));
+        return g.add_horner(ValueSource::Constant(0), parts, theta);
+    };
+    const auto A = compress(input_exprs), S = compress(table_exprs);
+    const uint32_t r0 = g.add_rotation(0), r1 = g.add_rotation(1), rm1 = g.add_rotation(-1);
+    const auto zz = z.at(r0), zw = z.at(r1), ap = permuted_input.at(r0), apm = permuted_input.at(rm1), sp = permuted_table.at(r0);
+    const auto d = c(ZKB_CALC_SUB, ap, sp);
+    // one statement per calculation wherever two operands are calculations themselves: C++ leaves the evaluation order of
+    // function arguments open, and the numbering of the intermediates must not depend on the compiler
+    std::vector<zkb_value_source> terms;
+    terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, one, zz), l0.at(r0)));
+    terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, c(ZKB_CALC_SQUARE, zz), zz), l_last.at(r0)));
+    const auto l1 = c(ZKB_CALC_MUL, zw, c(ZKB_CALC_ADD, ap, beta));
+    const auto l2 = c(ZKB_CALC_ADD, sp, gamma);
+    const auto left = c(ZKB_CALC_MUL, l1, l2);
+    const auto r1_ = c(ZKB_CALC_MUL, zz, c(ZKB_CALC_ADD, A, beta));
+    const auto r2_ = c(ZKB_CALC_ADD, S, gamma);
+    const auto right = c(ZKB_CALC_MUL, r1_, r2_);
+    terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_SUB, left, right), l_active.at(r0)));
+    terms.push_back(c(ZKB_CALC_MUL, d, l0.at(r0)));
+    terms.push_back(c(ZKB_CALC_MUL, c(ZKB_CALC_MUL, d, c(ZKB_CALC_SUB, ap, apm)), l_active.at(r0)));
+    g.add_horner(ValueSource::PreviousValue(), terms, ValueSource::Y());
+    return g;
+}
 
 }  // namespace halo2

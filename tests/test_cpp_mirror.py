@@ -52,3 +52,49 @@ def test_cpp_example_prover_ops_gpu():
     exe = _build_example()
     out = subprocess.check_output([exe, "16"], text=True)
     assert "k=16 ok" in out
+
+
+def test_cpp_graph_builders_match_the_python_mirror():
+    """The C++ host mirror's add_expression / custom_gates_graph / permutation_graph / lookup_graph (and its host Fr arithmetic
+    for the constants) produce exactly the graphs of zksnap-circuits-halo2_b200/evaluation.py, which the oracle / emulator / GPU
+    tests pin to the formulas: constants, rotations and every calculation record are compared."""
+    import importlib
+    ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
+    src = os.path.join(ROOT, "tests", "cpp", "graph_mirror_dump.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "graph_mirror_dump")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", PKG, "-lzkb200",
+                           f"-Wl,-rpath,{PKG}"])
+    got, cur = {}, None
+    for line in subprocess.check_output([exe], text=True).splitlines():
+        tag, *rest = line.split()
+        if tag == "graph":
+            cur = got.setdefault(rest[0], {"ni": int(rest[1]), "const": [], "rot": [], "calc": []})
+        elif tag == "const":
+            cur["const"].append([int(x, 16) for x in rest])
+        elif tag == "rot":
+            cur["rot"].append(int(rest[0]))
+        else:
+            cur["calc"].append([int(x) for x in rest])
+
+    def gate(adv, sel):
+        a, b, c, d = (("advice", adv, r) for r in range(4))
+        return ("prod", ("fixed", sel, 0), ("sum", ("sum", a, ("prod", b, c)), ("neg", d)))
+
+    gates = [gate(0, 0), gate(1, 1),
+             ("sum", ("scaled", ("instance", 0, -1), 7), ("neg", ("const", 5))),
+             ("prod", ("const", 2), ("prod", ("advice", 0, 0), ("advice", 0, 0))),
+             ("sum", ("const", 0), ("prod", ("const", 1), ("challenge", 1))),
+             ("sum", ("neg", ("fixed", 1, 2)), ("advice", 2, 0)),
+             ("scaled", ("advice", 1, 1), 1)]
+    want = {"custom_gates": ev.custom_gates_graph(gates),
+            "permutation": ev.permutation_graph([("advice", i) for i in range(5)], 2, -4, ("fixed", 0), ("fixed", 1), ("fixed", 2), ("fixed", 3),
+                                                [("fixed", 4 + i) for i in range(5)], [("advice", 5 + i) for i in range(3)]),
+            "lookup": ev.lookup_graph([("advice", 0, 0), ("prod", ("advice", 1, 0), ("advice", 0, 1))],
+                                      [("fixed", 3, 0), ("scaled", ("fixed", 3, -1), 3)], ("fixed", 0), ("fixed", 1), ("fixed", 2),
+                                      ("advice", 2), ("advice", 3), ("advice", 4))}
+    assert set(got) == set(want)
+    for name, g in want.items():
+        c = got[name]
+        assert c["ni"] == g.num_intermediates and c["rot"] == g.rotations, name
+        assert c["const"] == [[int(x) for x in row] for row in ev._mont_limbs(g.constants)], name
+        assert c["calc"] == [[int(x) for x in row] for row in g.calc_array()], name
