@@ -459,4 +459,69 @@ inline GraphEvaluator lookup_graph(const std::vector<Expression::Ptr>& input_exp
     return g;
 }
 
+// plonk::evaluation::Evaluator::evaluate_h over resident cosets: custom gates, then the permutation argument, then every lookup,
+// each folded into `values` with y (the mirror of evaluation.QuotientEvaluator).  The auxiliary cosets are appended to the column
+// lists: fixed + {l_0, l_last, l_active, X coset, sigmas...}, advice + {z_i...} resp. advice + {z, a', s'} per lookup.
+struct PermutationArgument {
+    std::vector<ColumnRef> columns;
+    size_t chunk_len = 2;          // cs.degree() - 2
+    int32_t last_rotation = -1;    // -(blinding_factors + 1)
+};
+struct LookupArgument {
+    std::vector<Expression::Ptr> input_expressions, table_expressions;
+};
+struct LookupCosets {
+    const Polynomial* product;
+    const Polynomial* permuted_input;
+    const Polynomial* permuted_table;
+};
+class QuotientEvaluator {
+   public:
+    QuotientEvaluator(const std::vector<Expression::Ptr>& gate_polys, const PermutationArgument* permutation, std::vector<LookupArgument> lookups)
+        : has_gates_(!gate_polys.empty()), custom_gates_(gate_polys.empty() ? GraphEvaluator() : custom_gates_graph(gate_polys)),
+          has_permutation_(permutation != nullptr), permutation_(permutation ? *permutation : PermutationArgument()), lookups_(std::move(lookups)) {}
+
+    void evaluate_h(Polynomial& values, std::vector<const Polynomial*> fixed, std::vector<const Polynomial*> advice,
+                    const std::vector<const Polynomial*>& instance, const std::vector<Fr>& challenges, const GraphEvaluator::Scalars& sc,
+                    int32_t rot_scale, const Polynomial& l0, const Polynomial& l_last, const Polynomial& l_active, const Polynomial* x_coset,
+                    const std::vector<const Polynomial*>& sigma_cosets, const std::vector<const Polynomial*>& permutation_product_cosets,
+                    const std::vector<LookupCosets>& lookup_cosets) const {
+        if (has_gates_) custom_gates_.evaluate(values, fixed, advice, instance, challenges, sc, rot_scale);
+        const uint32_t nf = uint32_t(fixed.size()), na = uint32_t(advice.size());
+        std::vector<const Polynomial*> fx = fixed;
+        fx.insert(fx.end(), {&l0, &l_last, &l_active});
+        const ColumnRef L0{ZKB_SRC_FIXED, nf}, LL{ZKB_SRC_FIXED, nf + 1}, LA{ZKB_SRC_FIXED, nf + 2};
+        if (has_permutation_) {
+            const size_t ncols = permutation_.columns.size(), nsets = (ncols + permutation_.chunk_len - 1) / permutation_.chunk_len;
+            if (!x_coset || sigma_cosets.size() != ncols || permutation_product_cosets.size() != nsets)
+                throw std::invalid_argument("evaluate_h: the permutation needs the X coset, one sigma coset per column and one product coset per set");
+            std::vector<ColumnRef> sig, zs;
+            for (uint32_t j = 0; j < ncols; ++j) sig.push_back({ZKB_SRC_FIXED, nf + 4 + j});
+            for (uint32_t i = 0; i < nsets; ++i) zs.push_back({ZKB_SRC_ADVICE, na + i});
+            const GraphEvaluator g = permutation_graph(permutation_.columns, permutation_.chunk_len, permutation_.last_rotation, L0, LL, LA,
+                                                       {ZKB_SRC_FIXED, nf + 3}, sig, zs);
+            std::vector<const Polynomial*> f2 = fx, a2 = advice;
+            f2.push_back(x_coset);
+            f2.insert(f2.end(), sigma_cosets.begin(), sigma_cosets.end());
+            a2.insert(a2.end(), permutation_product_cosets.begin(), permutation_product_cosets.end());
+            g.evaluate(values, f2, a2, instance, challenges, sc, rot_scale);
+        }
+        if (lookup_cosets.size() != lookups_.size()) throw std::invalid_argument("evaluate_h: one coset triple per lookup");
+        for (size_t n = 0; n < lookups_.size(); ++n) {
+            const GraphEvaluator g = lookup_graph(lookups_[n].input_expressions, lookups_[n].table_expressions, L0, LL, LA, {ZKB_SRC_ADVICE, na},
+                                                  {ZKB_SRC_ADVICE, na + 1}, {ZKB_SRC_ADVICE, na + 2});
+            std::vector<const Polynomial*> a2 = advice;
+            a2.insert(a2.end(), {lookup_cosets[n].product, lookup_cosets[n].permuted_input, lookup_cosets[n].permuted_table});
+            g.evaluate(values, fx, a2, instance, challenges, sc, rot_scale);
+        }
+    }
+
+   private:
+    bool has_gates_;
+    GraphEvaluator custom_gates_;
+    bool has_permutation_;
+    PermutationArgument permutation_;
+    std::vector<LookupArgument> lookups_;
+};
+
 }  // namespace halo2

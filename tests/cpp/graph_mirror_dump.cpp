@@ -41,5 +41,9 @@ int main() {
     std::vector<E::Ptr> in = {E::query(E::Advice, 0, 0), E::product(E::query(E::Advice, 1, 0), E::query(E::Advice, 0, 1))};
     std::vector<E::Ptr> tab = {E::query(E::Fixed, 3, 0), E::scaled(E::query(E::Fixed, 3, -1), fr::from_u64(3))};
     dump("lookup", lookup_graph(in, tab, {ZKB_SRC_FIXED, 0}, {ZKB_SRC_FIXED, 1}, {ZKB_SRC_FIXED, 2}, {ZKB_SRC_ADVICE, 2}, {ZKB_SRC_ADVICE, 3}, {ZKB_SRC_ADVICE, 4}));
+    // QuotientEvaluator: construction compiles the gate graph (evaluate_h itself needs a GPU and is exercised there)
+    PermutationArgument perm{cols, 2, -4};
+    QuotientEvaluator q(gates, &perm, {LookupArgument{in, tab}});
+    (void)q;
     return 0;
 }
