@@ -98,3 +98,32 @@ def test_cpp_graph_builders_match_the_python_mirror():
         assert c["ni"] == g.num_intermediates and c["rot"] == g.rotations, name
         assert c["const"] == [[int(x) for x in row] for row in ev._mont_limbs(g.constants)], name
         assert c["calc"] == [[int(x) for x in row] for row in g.calc_array()], name
+
+
+def test_cpp_host_fr_arithmetic_matches_python_integers():
+    """halo2::fr::{mul, add, neg, from_u64} (the host arithmetic behind a graph's constants) on random and edge operands."""
+    import random
+    r = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    R = (1 << 256) % r
+    src = os.path.join(ROOT, "tests", "cpp", "fr_host_arith.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "fr_host_arith")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", PKG, "-lzkb200",
+                           f"-Wl,-rpath,{PKG}"])
+    rnd = random.Random(5)
+    edge = [0, 1, 2, r - 1, r - 2, R, (1 << 64) - 1, 1 << 64, (1 << 128) - 1, 1 << 192, r >> 1, (r >> 1) + 1]
+    vals = edge + [rnd.randrange(r) for _ in range(60)]
+    limbs = lambda x: " ".join("%x" % ((x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF) for i in range(4))  # noqa: E731
+    lines, want = [], []
+    for a in vals:
+        for b in rnd.sample(vals, 6) + [a]:
+            lines.append(f"mul {limbs(a)} {limbs(b)}")
+            want.append(a * b * pow(R, -1, r) % r)       # Montgomery product
+            lines.append(f"add {limbs(a)} {limbs(b)}")
+            want.append((a + b) % r)
+        lines.append(f"neg {limbs(a)} {limbs(0)}")
+        want.append(-a % r)
+        lines.append(f"u64 {limbs(a & 0xFFFFFFFFFFFFFFFF)} {limbs(0)}")
+        want.append((a & 0xFFFFFFFFFFFFFFFF) * R % r)
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    got = [sum(int(x, 16) << (64 * i) for i, x in enumerate(l.split())) for l in out if l.strip()]
+    assert got == want
