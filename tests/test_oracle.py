@@ -405,3 +405,25 @@ def test_eip196_vectors_pin_both_oracles(oracle):
         km = fr_mont([k])[0]
         assert R.g1_affine_decode([int(x) for x in oracle.g1_mul(aff_mont(p), km)]) == out
         assert R.g1_jacobian_decode([int(x) for x in oracle.best_multiexp(np.array([km]), np.array([aff_mont(p)]))]) == out
+
+
+def test_published_halo2curves_montgomery_constants(oracle):
+    """The Montgomery constants published in halo2curves' bn256 fr.rs / fq.rs (INV, R, R2, R3 — written down from memory, the
+    crate is not vendored): they are 2^256, 2^512, 2^768 mod the modulus and -m^-1 mod 2^64, i.e. the in-memory layout this
+    repository assumes (a * 2^256 mod m in four little-endian u64 limbs) is the crate's; the C oracle's to-Montgomery conversion
+    of 1 gives the same R."""
+    fr = dict(inv=0xc2e1f593efffffff,
+              R=[0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f],
+              R2=[0x1bb8e645ae216da7, 0x53fe3ab1e35c59e3, 0x8c49833d53bb8085, 0x0216d0b17f4e44a5],
+              R3=[0x5e94d8e1b4bf0040, 0x2a489cbe1cfbb6b8, 0x893cc664a19fcfed, 0x0cf8594b7fcc657c])
+    fq = dict(inv=0x87d20782e4866389,
+              R=[0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f],
+              R2=[0xf32cfc5b538afa89, 0xb5e71911d44501fb, 0x47ab1eff0a417ff6, 0x06d89f71cab8351f],
+              R3=[0xb1cd6dafda1530df, 0x62f210e6a7283db6, 0xef7f0b0c0ada0afb, 0x20fd6e902d592544])
+    for consts, m in ((fr, R.FR), (fq, R.FQ)):
+        assert consts["inv"] == (-pow(m, -1, 1 << 64)) % (1 << 64)
+        for name, e in (("R", 256), ("R2", 512), ("R3", 768)):
+            assert limbs_to_int(consts[name]) == pow(2, e, m), name
+    one = np.array([[1, 0, 0, 0]], dtype=np.uint64)
+    assert [int(x) for x in oracle.fr_to_mont(one)[0]] == fr["R"]
+    assert [int(x) for x in oracle.vec_op("fq", "mul", np.array([fq["R2"]], dtype=np.uint64), one)[0]] == fq["R"]   # mont(R2, 1) = R
