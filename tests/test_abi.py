@@ -98,3 +98,22 @@ def test_graph_structs_have_the_c_layout(tmp_path):
           ev.CGraph.constants.offset, ev.CGraph.rotations.offset, ctypes.sizeof(ev.CGraphInputs), ev.CGraphInputs.challenges.offset,
           ev.CGraphInputs.beta.offset, ev.CGraphInputs.rot_scale.offset]
     assert c == py and c[0] == 12 and c[1] == 44
+
+
+def test_t_evaluations_inverse_is_the_inverse_of_the_vanishing_polynomial_on_the_coset():
+    """EvaluationDomain.t_evaluations_inverse (host integers, tiled): every entry times (x^n - 1) at its coset point is one."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import pyref as R
+    zkb = importlib.import_module("zksnap-circuits-halo2_b200")
+    for j, k in [(4, 3), (4, 5), (3, 4), (5, 2)]:
+        d = zkb.EvaluationDomain(j, k)
+        t = d.t_evaluations_inverse()
+        assert t.shape == (d.extended_len(), 4)
+        zeta = pow(7, 2 * (R.FR - 1) // 3, R.FR)
+        w = R.omega_for(d.extended_k)
+        for i in range(d.extended_len()):
+            x = zeta * pow(w, i, R.FR) % R.FR
+            ti = R.from_mont(sum(int(v) << (64 * q) for q, v in enumerate(t[i])), R.FR)
+            assert ti * (pow(x, 1 << k, R.FR) - 1) % R.FR == 1

@@ -277,6 +277,27 @@ class EvaluationDomain:
         check(lib().zkb_coeff_to_lagrange(_p(v), self.k))
         return v
 
+    def t_evaluations_inverse(self) -> np.ndarray:
+        """1 / (X^n - 1) on the extended coset zeta <w_ext> (upstream's `t_evaluations`, inverted as divide_by_vanishing_poly uses
+        them): X^n takes only 2^(extended_k - k) distinct values there, so the (extended_len, 4) array is that many Montgomery
+        values tiled.  Host integers; no GPU needed."""
+        r = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+        R = (1 << 256) % r
+        Rinv = pow(R, -1, r)
+        zeta = pow(7, 2 * (r - 1) // 3, r)                                   # Fr::ZETA, the coset generator
+        w = sum(int(x) << (64 * i) for i, x in enumerate(self.get_extended_omega())) * Rinv % r
+        period = 1 << (self.extended_k - self.k)
+        vals = [pow((pow(zeta, self.n, r) * pow(w, i * self.n, r) - 1) % r, -1, r) * R % r for i in range(period)]
+        one_period = np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64)
+        return np.tile(one_period, (self.extended_len() // period, 1))
+
+    def divide_by_vanishing_poly(self, h: "Polynomial") -> "Polynomial":
+        """EvaluationDomain::divide_by_vanishing_poly on a resident polynomial of extended evaluations: h[i] *= 1 / (X^n - 1) at the
+        i-th coset point.  The coset of inverses is uploaded once per domain and kept in HBM."""
+        if getattr(self, "_t_inv", None) is None:
+            self._t_inv = Polynomial(self.t_evaluations_inverse())
+        return h.mul(self._t_inv)
+
     def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
         v = _fr(a)
         assert v.shape[0] == self.n, "assertion failed: a.values.len() == 1 << self.k"
