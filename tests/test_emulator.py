@@ -647,3 +647,23 @@ def test_quotient_evaluator_evaluate_h_against_the_formulas(oracle):
                  sc["theta"], rs, m(l0), m(l_last), m(l_active), m(xc), [m(c) for c in sigmas], [m(c) for c in zs], [(m(lz), m(la), m(ls))],
                  evaluate=evaluate)
     assert GC.unmont(state["values"]) == want
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_graph_row_windows_random_programs(oracle, seed):
+    """Row-window mode on the raw random programs (re-written intermediates, dead values, every scalar source, the previous
+    value): 2 or 4 shards with cyclic halos reproduce the oracle's whole-domain evaluation."""
+    g, rs = GC.random_program(5000 + seed)
+    isize, world = 64, (2, 4)[seed % 2]
+    fixed, advice = [random_field(isize, 6000 + seed)], [random_field(isize, 6100 + seed + i) for i in range(2)]
+    sc = random_field(4, 6200 + seed)
+    prev = random_field(isize, 6300 + seed)
+    want = oracle.graph_evaluate(g.calc_array(), g.num_intermediates, GC.mont(g.constants), g.rotations, fixed, advice, [], None,
+                                 sc[0], sc[1], sc[2], sc[3], rs, prev)
+    lo, hi = g.rotation_span(rs)
+    rows = isize // world
+    for r in range(world):
+        idx = np.arange(r * rows - lo, (r + 1) * rows + hi) % isize
+        rc, o, _ = emu.graph_evaluate(g, [fixed[0][idx]], [a[idx] for a in advice], [], None, sc[0], sc[1], sc[2], sc[3], rs,
+                                      prev[r * rows:(r + 1) * rows], halo=(lo, hi))
+        assert rc == 0 and (o == want[r * rows:(r + 1) * rows]).all()
