@@ -23,7 +23,7 @@
  *
  * All functions return 0 on success or a negative ZKB_ERR_* code; zkb_last_error() gives the thread-local
  * message.  There is no CPU fallback: without a usable CUDA device every compute call fails with
- * ZKB_ERR_NO_DEVICE.  Entry points are thread-safe (serialised per process) and synchronous: host buffers are
+ * ZKB_ERR_NO_DEVICE.  Entry points are thread-safe (serialised per device) and synchronous: host buffers are
  * valid when the call returns.  The *_dev variants take device pointers and a CUDA stream and are
  * asynchronous with respect to the host unless stated otherwise.
  */
@@ -49,9 +49,28 @@ extern "C" {
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------- */
 
-/* Bind this process to one GPU (one process per GPU; ndev must be 0 or 1).  devices == NULL or ndev == 0
- * selects the current CUDA device.  Idempotent. */
+/* Bind this process to 1..8 GPUs of one box.  devices == NULL or ndev == 0 selects the devices named by the environment
+ * variable ZKB_DEVICES ("all" or a list such as "0,1,2,3") or, when it is unset, the current CUDA device — so an
+ * unmodified caller drives the whole box by setting one variable.  Idempotent for the same list.
+ * With several devices the ONE process the reference's prover is (create_proof, /root/reference/aggregator/src/wrapper.rs:
+ * 129-137, chained by gen_recursion_snark, wrapper.rs:869-902) reaches all of them through the same entry points:
+ *   - zkb_srs_register & co. replicate the SRS to every device (peer copies over NVLink);
+ *   - zkb_msm_g1 / zkb_msm_g1_srs / _range shard one commit by SRS point range: each device uploads only its share of the
+ *     scalars over its own PCIe link, the <= 8 partial sums (96 B each) are folded on the host;
+ *   - the *_batch forms (commits and NTT-family ops) split the batch by column, no communication;
+ *   - one large transform (zkb_ntt_fr, zkb_lagrange_to_coeff, zkb_coeff_to_lagrange, zkb_extended_to_coeff of >= 2^22
+ *     elements) is sharded over the devices with the exchange fused into the NTT passes over NVLink peer memory.
+ * Results are bit-identical to the single-device ones.  Polynomial handles, quotient evaluation and the *_dev variants act
+ * on one device: the first of the list (home device), or for *_dev the device that owns the pointer.
+ * The one-process-per-GPU deployment (torchrun, one rank per device, zkb_dist_* over CUDA IPC) remains available. */
 int zkb_init(const int* devices, int ndev);
+/* Thresholds of the multi-device paths, as log2 sizes (0 = default): smallest per-device share of points for which a commit
+ * is sharded (default 16), smallest transform whose batch is split by column (16), smallest single transform sharded over
+ * the devices (22; needs >= 2 NTT passes, i.e. >= 2^11).  Environment: ZKB_MULTI_MIN_SHARE_LOG, ZKB_MULTI_NTT_MIN_LOG,
+ * ZKB_MULTI_DIST_MIN_LOG. */
+int zkb_multi_device_set(int msm_min_share_log, int batch_ntt_min_log, int dist_ntt_min_log);
+/* devices bound by zkb_init, home device first; returns their number (0 before zkb_init) */
+int zkb_bound_devices(int* devices, int capacity);
 void zkb_shutdown(void);
 const char* zkb_last_error(void);
 /* Number of visible CUDA devices (0 if none) — never fails. */
@@ -146,6 +165,11 @@ int zkb_extended_to_coeff(uint64_t* a, uint32_t k, uint32_t extended_k);
 
 /* omega(k) = Fr::ROOT_OF_UNITY^(2^(28-k)) in Montgomery limbs (EvaluationDomain::new) */
 int zkb_fr_omega(uint32_t k, uint64_t out[4]);
+/* The cube root of unity this library uses as the coset generator of the extended domain (EvaluationDomain::g_coset =
+ * Fr::ZETA), Montgomery limbs.  halo2curves releases have shipped either primitive cube root as bn256 Fr::ZETA; the shim
+ * asserts at start-up that this equals the linked crate's constant (coeff_to_extended / extended_to_coeff would otherwise
+ * evaluate on a different coset than the host-side pieces of the prover). */
+int zkb_fr_zeta(uint64_t out[4]);
 
 /* ---- device-resident variants (data already in HBM; `stream` is a cudaStream_t, NULL = default stream) ----- */
 

@@ -141,7 +141,7 @@ def test_msm_vs_oracle(oracle, n):
     assert (got == oracle.best_multiexp(s, bases)).all()
 
 
-@pytest.mark.parametrize("c,chunk", [(4, 8), (7, 3), (11, 64), (16, 256)])
+@pytest.mark.parametrize("c,chunk", [(2, 8), (3, 16), (4, 8), (7, 3), (11, 64), (16, 256)])  # c = 2 / 3: 128 / 85 window sums in the host fold
 def test_msm_window_and_chunk_overrides(oracle, c, chunk):
     n = 3000
     s = random_field(n, 42)
@@ -312,6 +312,82 @@ def test_coeff_to_extended_full_size_roundtrip():
     coeffs = [R.from_mont(limbs_to_int(x), R.FR) for x in a[:8]]
     want = sum(c * pow(R.FR_ZETA, i, R.FR) for i, c in enumerate(coeffs)) % R.FR
     assert R.from_mont(limbs_to_int(e0), R.FR) == want
+
+
+def test_ntt_2_26_single_gpu():
+    """best_fft at the top of BASELINE.json's sweep (2^26, 2 GiB) on one GPU: exact values of a 2-sparse input against the
+    definition at sampled outputs, and NTT -> lagrange_to_coeff round trip of a random vector."""
+    k = 26
+    n = 1 << k
+    w = zkb.omega(k)
+    a = random_field(n, 2600)
+    sp = np.zeros((n, 4), dtype=np.uint64)
+    j1, j2 = 0x2345677 % n, n - 11
+    sp[j1] = a[1]
+    sp[j2] = a[2]
+    zkb.best_fft(sp, w, k)
+    wint = R.omega_for(k)
+    a1, a2 = R.from_mont(limbs_to_int(a[1]), R.FR), R.from_mont(limbs_to_int(a[2]), R.FR)
+    rng = np.random.default_rng(26)
+    for i in [0, 1, 2, n // 2, n // 2 + 3, n - 1] + [int(x) for x in rng.integers(0, n, 26)]:
+        want = (a1 * pow(wint, i * j1, R.FR) + a2 * pow(wint, i * j2, R.FR)) % R.FR
+        assert R.from_mont(limbs_to_int(sp[i]), R.FR) == want, i
+    del sp
+    f = a.copy()
+    zkb.best_fft(f, w, k)
+    assert not (f[:64] == a[:64]).all()
+    back = zkb.EvaluationDomain(2, k).lagrange_to_coeff(f)
+    assert (back == a).all()
+
+
+def test_coeff_to_extended_full_size_vs_horner(oracle):
+    """coeff_to_extended 2^22 -> 2^24 (the wrapper circuit's coset NTT) against Horner evaluation of the 2^22 coefficients at
+    zeta * omega_ext^i for indices spread over the whole extended domain (C oracle's eval_polynomial = upstream's
+    arithmetic::eval_polynomial restated)."""
+    k = 22
+    d = zkb.EvaluationDomain(4, k)
+    a = random_field(1 << k, 2224)
+    ext = d.coeff_to_extended(a)
+    N = 1 << d.extended_k
+    wext = R.omega_for(d.extended_k)
+    rng = np.random.default_rng(2224)
+    idx = [0, 1, 2, 3, N // 4, N // 2 - 1, N // 2, N - 1] + [int(x) for x in rng.integers(0, N, 16)]
+    for i in idx:
+        x = R.FR_ZETA * pow(wext, i, R.FR) % R.FR
+        want = oracle.fr_eval_polynomial(a, mont([x])[0])
+        assert (ext[i] == want).all(), i
+
+
+@pytest.mark.parametrize("dist", ["W", "E"])
+@pytest.mark.parametrize("precompute", [1, 0])
+def test_msm_2_22_witness_like_and_equal_scalars(oracle, dist, precompute):
+    """BASELINE sweep distributions at the wrapper size, known-dlog check: W = witness-like (50 % zero, 25 % < 2^16, 20 % < 2^88,
+    5 % uniform), E = all-equal scalar (every point in the same bucket of every window)."""
+    k = 22
+    n = 1 << k
+    rng = np.random.default_rng(2222)
+    if dist == "E":
+        s = np.tile(random_field(1, 5)[0], (n, 1))
+    else:
+        s = random_field(n, 2223)                       # Montgomery residues of uniform values
+        u = rng.random(n)
+        small = mont([int(x) for x in rng.integers(0, 1 << 16, 4096)])
+        mid = mont([int.from_bytes(rng.bytes(11), "little") for _ in range(4096)])
+        s[u < 0.5] = 0
+        m = (u >= 0.5) & (u < 0.75)
+        s[m] = small[rng.integers(0, 4096, int(m.sum()))]
+        m = (u >= 0.75) & (u < 0.95)
+        s[m] = mid[rng.integers(0, 4096, int(m.sum()))]
+    b, bases = _bases_known_dlog(n, 2225)
+    zkb.lib().zkb_srs_set_precompute(precompute)
+    try:
+        params = zkb.ParamsKZG(k, bases)
+        got = params.commit(s)
+        params.close()
+    finally:
+        zkb.lib().zkb_srs_set_precompute(1)
+    want = oracle.g1_mul(oracle.g1_generator(), oracle.fr_inner_product(s, b))
+    assert (got[:8] == want).all() and limbs_to_int(got[8:]) == R.FQ_R
 
 
 def test_msm_full_size_known_dlog(oracle):

@@ -23,6 +23,7 @@ from .halo2 import (  # noqa: F401
     best_fft,
     best_fft_g1,
     best_multiexp,
+    bound_devices,
     device_count,
     g1_fixed_base_mul,
     g1_fixed_base_mul_naive,
@@ -38,6 +39,6 @@ from ._ffi import ZkbError, header_symbols  # noqa: F401
 from .evaluation import GraphEvaluator, QuotientEvaluator, ValueSource  # noqa: F401
 
 __all__ = [
-    "GraphEvaluator", "QuotientEvaluator", "ValueSource", "EvaluationDomain", "ParamsKZG", "Polynomial", "batch_invert", "eval_polynomial", "kate_division", "batch_normalize", "best_fft", "best_fft_g1", "best_multiexp", "device_count", "g1_fixed_base_mul", "g1_fixed_base_mul_naive", "g1_sum",
+    "GraphEvaluator", "QuotientEvaluator", "ValueSource", "EvaluationDomain", "ParamsKZG", "Polynomial", "batch_invert", "eval_polynomial", "kate_division", "batch_normalize", "best_fft", "best_fft_g1", "best_multiexp", "bound_devices", "device_count", "g1_fixed_base_mul", "g1_fixed_base_mul_naive", "g1_sum",
     "init", "launch_count", "lib", "omega", "prof", "shutdown", "ZkbError", "header_symbols",
 ]

@@ -73,6 +73,9 @@ def load() -> ctypes.CDLL:
         "zkb_coeff_to_extended_batch": [u64pp, u64pp, sz, u32, u32],
         "zkb_extended_to_coeff": [u64p, u32, u32],
         "zkb_fr_omega": [u32, u64p],
+        "zkb_fr_zeta": [u64p],
+        "zkb_bound_devices": [ctypes.POINTER(ci), ci],
+        "zkb_multi_device_set": [ci, ci, ci],
         "zkb_msm_g1_srs_dev": [u64, sz, vp, sz, u64p, vp],
         "zkb_ntt_fr_dev": [vp, vp, sz, u64p, u32, vp],
         "zkb_coeff_to_extended_dev": [vp, vp, vp, sz, u32, u32, vp],

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <thread>
 
 #include "msm_host.hpp"
@@ -23,9 +24,114 @@ void set_error(const char* fmt, ...) {
     g_error = buf;
 }
 
-Ctx& ctx() {
-    static Ctx c;
-    return c;
+// ---- device slots -----------------------------------------------------------------------------------------------------------
+static thread_local int tl_slot = 0;
+static int g_nslots = 0;                      // bound devices
+static int g_slot_device[ZKB_MAX_DEVICES] = {0};
+static std::mutex g_fanout_mu;                // one fan-out at a time (the workers hold one job each)
+
+int cur_slot() { return tl_slot; }
+int device_slots() { return g_nslots; }
+int slot_device(int slot) { return g_slot_device[slot]; }
+
+Ctx& ctx() { return per_device<Ctx>(); }
+
+SlotScope::SlotScope(int slot) : prev(tl_slot) {
+    tl_slot = slot;
+    if (slot != prev) cudaSetDevice(g_slot_device[slot]);
+}
+SlotScope::~SlotScope() {
+    if (tl_slot != prev) cudaSetDevice(g_slot_device[prev]);
+    tl_slot = prev;
+}
+
+int slot_of_device_ptr(const void* p) {
+    if (g_nslots <= 1 || !p) return tl_slot;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return tl_slot; }
+    if (at.type != cudaMemoryTypeDevice) return tl_slot;
+    for (int i = 0; i < g_nslots; ++i)
+        if (g_slot_device[i] == at.device) return i;
+    return tl_slot;
+}
+
+// one worker thread per device slot >= 1: bound to its GPU for life, runs the jobs of run_on_devices
+struct DevWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = false, quit = false;
+    int rc = ZKB_OK;
+    std::string err;
+
+    void start(int slot) {
+        if (th.joinable()) return;
+        quit = false;
+        th = std::thread([this, slot] {
+            tl_slot = slot;
+            cudaSetDevice(g_slot_device[slot]);
+            for (;;) {
+                std::function<int()> j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return quit || has_job; });
+                    if (quit) return;
+                    j = std::move(job);
+                    has_job = false;
+                }
+                g_error.clear();
+                int r = j();
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    rc = r;
+                    err = g_error;
+                    done = true;
+                }
+                cv.notify_all();
+            }
+        });
+    }
+    void post(std::function<int()> j) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = std::move(j);
+            has_job = true;
+            done = false;
+        }
+        cv.notify_all();
+    }
+    int wait(std::string* e) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done; });
+        if (rc != ZKB_OK && e) *e = err;
+        return rc;
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        th.join();
+    }
+};
+static DevWorker g_workers[ZKB_MAX_DEVICES];
+
+int run_on_devices(int count, const std::function<int(int)>& f) {
+    if (count <= 1 || tl_slot != 0) return f(tl_slot);
+    std::lock_guard<std::mutex> fan(g_fanout_mu);
+    for (int i = 1; i < count; ++i) g_workers[i].post([&f, i] { return f(i); });
+    int rc = f(0);
+    std::string first_err = rc != ZKB_OK ? g_error : std::string();
+    for (int i = 1; i < count; ++i) {
+        std::string e;
+        int r = g_workers[i].wait(&e);
+        if (r != ZKB_OK && rc == ZKB_OK) { rc = r; first_err = "device slot " + std::to_string(i) + ": " + e; }
+    }
+    if (rc != ZKB_OK) g_error = first_err;
+    return rc;
 }
 
 void poly_pool_flush();  // poly.cu
@@ -66,6 +172,7 @@ int require_init() {
         cudaSetDevice(c.device);
         return ZKB_OK;
     }
+    if (cur_slot() != 0) { set_error("device slot %d is not initialised", cur_slot()); return ZKB_ERR_NO_DEVICE; }
     return zkb_init(nullptr, 0);
 }
 
@@ -136,6 +243,13 @@ struct Srs {
     uint32_t table_c = 0, table_nwin = 0;
     bool table_failed = false;
     uint64_t commits = 0;  // commitments served so far (automatic mode decides on this)
+    uint64_t plan_n = 0;   // MSM length the window table is tuned for: n, or n / devices when commits are sharded by point range
+};
+// One registered SRS: a replica per device slot (the arrays are small next to 180 GB of HBM: 256 MiB at k = 22), so that one
+// commit can be sharded by point range over the devices and a batch of commits by column, without moving bases per call.
+struct SrsSet {
+    Srs* dev[ZKB_MAX_DEVICES] = {};
+    size_t n = 0;
 };
 // SRS window-table policy: 0 off, 1 eager (build on the first commit), 2 automatic (default): build once the handle has served
 // PRECOMPUTE_AFTER commitments.  A table-mode commit is ~18 % faster (2^22: 11.5 vs 14.0 ms) and the build costs ~100 commits'
@@ -158,7 +272,7 @@ static bool srs_table_ready(Srs* s, cudaStream_t stream, bool force = false) {
     const int mode = precompute_mode();
     if (mode == 0 || s->table_failed || s->n < 64 || ctx().msm_c_override) return false;
     if (!force && mode == 2 && s->commits < PRECOMPUTE_AFTER) return false;
-    MsmGeometry g = msm_geometry(s->n, 0, 0, true);
+    MsmGeometry g = msm_geometry(s->plan_n ? s->plan_n : s->n, 0, 0, true);
     size_t bytes = (size_t)g.nwin * s->n * 64;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 3 || (uint64_t)g.nwin * s->n >= (1ull << 31)) {
@@ -178,11 +292,79 @@ static bool srs_table_ready(Srs* s, cudaStream_t stream, bool force = false) {
     s->table_nwin = g.nwin;
     return true;
 }
-static std::map<uint64_t, Srs*>& srs_map() {
-    static std::map<uint64_t, Srs*> m;
+static std::map<uint64_t, SrsSet*>& srs_map() {
+    static std::map<uint64_t, SrsSet*> m;
     return m;
 }
+static std::mutex g_srs_mu;  // guards srs_map and g_next_handle (entry points of different slots may run concurrently)
 static uint64_t g_next_handle = 1;
+
+// Multi-device thresholds (log2): smallest per-device share of points worth sharding a commit for; smallest transform whose
+// batch is split by column; smallest single transform sharded over the devices.  Environment ZKB_MULTI_MIN_SHARE_LOG /
+// ZKB_MULTI_NTT_MIN_LOG / ZKB_MULTI_DIST_MIN_LOG, or zkb_multi_device_set.
+static int g_multi[3] = {-1, -1, -1};
+static int multi_threshold(int which) {
+    static const char* const names[3] = {"ZKB_MULTI_MIN_SHARE_LOG", "ZKB_MULTI_NTT_MIN_LOG", "ZKB_MULTI_DIST_MIN_LOG"};
+    static const int defaults[3] = {16, 16, 22};
+    if (g_multi[which] < 0) {
+        const char* e = getenv(names[which]);
+        g_multi[which] = e ? atoi(e) : defaults[which];
+        if (g_multi[which] < 1) g_multi[which] = 1;
+    }
+    return g_multi[which];
+}
+static int msm_min_share_log() { return multi_threshold(0); }
+// devices a commit of n points is sharded over (by SRS point range)
+static int msm_fanout(size_t n) {
+    if (g_nslots <= 1 || cur_slot() != 0) return 1;
+    size_t g = n >> msm_min_share_log();
+    if (g > (size_t)g_nslots) g = (size_t)g_nslots;
+    return g < 1 ? 1 : (int)g;
+}
+static void point_range(size_t n, int part, int parts, size_t* off, size_t* len) {
+    const size_t base = n / parts, rem = n % parts;
+    *off = (size_t)part * base + ((size_t)part < rem ? (size_t)part : rem);
+    *len = base + ((size_t)part < rem ? 1 : 0);
+}
+
+// Publishes an SRS that is resident on the calling slot: replicates it to every other device slot (peer copies over NVLink,
+// all devices at once) and returns the handle.  Takes ownership of `home` (released on failure).
+static int srs_publish(Srs* home, uint64_t* handle) {
+    SrsSet* set = new SrsSet();
+    set->n = home->n;
+    const int hs = cur_slot();
+    const size_t bytes = home->n ? home->n * 64 : 64;
+    home->plan_n = (g_nslots > 1 && (home->n >> msm_min_share_log()) >= (size_t)g_nslots) ? home->n / g_nslots : home->n;
+    set->dev[hs] = home;
+    int rc = ZKB_OK;
+    if (g_nslots > 1 && hs == 0) {
+        if (cudaStreamSynchronize(ctx().stream) != cudaSuccess) { cudaGetLastError(); set_error("SRS publish: stream sync failed"); rc = ZKB_ERR_CUDA; }
+        if (rc == ZKB_OK) rc = run_on_devices(g_nslots, [&](int slot) -> int {
+            if (slot == hs) return ZKB_OK;
+            Srs* r = new Srs();
+            r->n = home->n;
+            r->plan_n = home->plan_n;
+            int rr = r->bases.reserve(bytes);
+            if (rr == ZKB_OK && home->n) {
+                cudaError_t e = cudaMemcpyPeer(r->bases.p, slot_device(slot), home->bases.p, slot_device(hs), home->n * 64);
+                if (e != cudaSuccess) { cudaGetLastError(); set_error("SRS replication to device %d failed: %s", slot_device(slot), cudaGetErrorString(e)); rr = ZKB_ERR_CUDA; }
+            }
+            if (rr != ZKB_OK) { r->bases.release(); delete r; return rr; }
+            set->dev[slot] = r;
+            return ZKB_OK;
+        });
+    }
+    if (rc != ZKB_OK) {
+        for (int i = 0; i < ZKB_MAX_DEVICES; ++i)
+            if (set->dev[i]) { SlotScope sc(i); set->dev[i]->bases.release(); delete set->dev[i]; }
+        delete set;
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_srs_mu);
+    *handle = g_next_handle++;
+    srs_map()[*handle] = set;
+    return ZKB_OK;
+}
 
 struct PinBuf {  // grow-only pinned host buffer
     void* p = nullptr;
@@ -203,10 +385,7 @@ struct HostIo {  // device staging for the host-buffer entry points
     PinBuf stage[2];            // pinned staging of pageable scalar slices
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
-static HostIo& hostio() {
-    static HostIo h;
-    return h;
-}
+static HostIo& hostio() { return per_device<HostIo>(); }
 
 static int check_ptr(const void* p, const char* what) {
     if (!p) { set_error("%s is NULL", what); return ZKB_ERR_ARG; }
@@ -298,7 +477,8 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
         const char* e = getenv("ZKB_STAGE_THREADS");
         if (e && atoi(e) > 0) n = (unsigned)atoi(e);
         nparts = n;
-        for (unsigned i = 1; i < n; ++i) workers.emplace_back([this, i] { loop(i); });
+        const uint64_t g0 = gen;  // a pool restarted after zkb_shutdown must not replay the last job of its previous life
+        for (unsigned i = 1; i < n; ++i) workers.emplace_back([this, i, g0] { loop(i, g0); });
     }
     void part(unsigned i) {
         size_t per = ((bytes / nparts) + 4095) & ~(size_t)4095;
@@ -307,8 +487,7 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
         if (hi > bytes) hi = bytes;
         memcpy(dst + lo, src + lo, hi - lo);
     }
-    void loop(unsigned i) {
-        uint64_t seen = 0;
+    void loop(unsigned i, uint64_t seen) {
         for (;;) {
             {
                 std::unique_lock<std::mutex> lk(mu);
@@ -351,14 +530,10 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
         quit = false;
     }
 };
-static HostPool& host_pool() {  // stage-in copies (caller's thread + workers)
-    static HostPool p;
-    return p;
-}
-static HostPool& out_pool() {   // stage-out copies (drainer thread + workers)
-    static HostPool p;
-    return p;
-}
+struct StageInPool : HostPool {};
+static HostPool& host_pool() { return per_device<StageInPool>(); }
+struct StageOutPool : HostPool {};
+static HostPool& out_pool() { return per_device<StageOutPool>(); }
 
 // Copy-out of pageable results runs on its own thread: it waits for a group's device->host event and scatters the pinned
 // staging buffer into the caller's arrays while the calling thread is already staging the next group in — without it the two
@@ -372,14 +547,16 @@ struct Drainer {
     std::deque<Job> q;
     uint64_t next_id = 1, done_id = 0;
     bool quit = false, failed = false;
-    int device = 0;
+    int device = 0, slot = 0;
 
     void start(int dev) {
         if (th.joinable()) return;
         device = dev;
+        slot = cur_slot();
         th = std::thread([this] { loop(); });
     }
     void loop() {
+        tl_slot = slot;  // the stage-out pool of this device
         cudaSetDevice(device);
         for (;;) {
             Job j;
@@ -426,10 +603,7 @@ struct Drainer {
     }
     ~Drainer() { stop(); }
 };
-static Drainer& drainer() {
-    static Drainer d;
-    return d;
-}
+static Drainer& drainer() { return per_device<Drainer>(); }
 
 constexpr int PIPE_SLOTS = 3;
 struct PipeSlot {
@@ -448,10 +622,7 @@ struct Pipeline {
     size_t group_bytes_override = 0;  // 0 = automatic
     int depth = PIPE_SLOTS;           // 1 = serial (for A/B measurements)
 };
-static Pipeline& pipeline() {
-    static Pipeline p;
-    return p;
-}
+static Pipeline& pipeline() { return per_device<Pipeline>(); }
 static int pipeline_init() {
     Pipeline& pl = pipeline();
     if (pl.ready) return ZKB_OK;
@@ -489,8 +660,8 @@ static bool host_ptr_is_pinned(const void* p) {
 }
 
 // host-buffer flavour: columns are separate host arrays
-static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k, uint32_t ek,
-                          const uint64_t* omega_user) {
+static int domain_op_host_one(DomainOp op, const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k, uint32_t ek,
+                              const uint64_t* omega_user) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
     ZKB_TRY(check_ptr(in, "input column array"));
@@ -604,6 +775,53 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
     return ZKB_OK;
 }
 
+int dist_inprocess_ntt_host(const uint64_t* in, uint64_t* out, const uint64_t omega[4], uint32_t log_n, const Fr* out_scale);  // dist.cu
+bool dist_inprocess_supported(uint32_t log_n);
+
+// Host-buffer NTT-family op over all bound devices: a batch is split by column (contiguous column ranges, one per device,
+// each running its own three-stream pipeline over its own PCIe link — no communication); ONE large transform is sharded
+// over the devices with the exchange fused into the NTT passes over NVLink peer memory (dist.cu).
+static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* const* out, size_t ncols, uint32_t k, uint32_t ek,
+                          const uint64_t* omega_user) {
+    const int nd = cur_slot() == 0 ? device_slots() : 1;
+    if (nd <= 1 || ncols == 0 || !in || !out) return domain_op_host_one(op, in, out, ncols, k, ek, omega_user);
+    const uint32_t log_n = (op == OP_C2E || op == OP_E2C) ? ek : k;
+    const int min_cols_log = multi_threshold(1), dist_min_log = multi_threshold(2);
+    if (ncols == 1) {
+        if (op == OP_C2E || (int)log_n < dist_min_log || !dist_inprocess_supported(log_n) || !in[0] || !out[0])
+            return domain_op_host_one(op, in, out, ncols, k, ek, omega_user);
+        std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+        ZKB_TRY(require_init());
+        uint64_t om[4];
+        Fr scale[3];
+        const Fr* out_scale = nullptr;
+        switch (op) {
+            case OP_FFT: ZKB_TRY(check_ptr(omega_user, "omega")); memcpy(om, omega_user, 32); break;
+            case OP_C2L: fr_to_limbs64(fr_omega_host(k), om); break;
+            case OP_L2C:
+                fr_to_limbs64(fr_inv_host(fr_omega_host(k)), om);
+                scale[0] = scale[1] = scale[2] = fr_pow2_inv_host(k);
+                out_scale = scale;
+                break;
+            default: {  // OP_E2C
+                fr_to_limbs64(fr_inv_host(fr_omega_host(ek)), om);
+                Fr ninv = fr_pow2_inv_host(ek), z = fr_zeta(), z2 = fp_sqr(z);
+                scale[0] = ninv; scale[1] = fp_mul(ninv, z2); scale[2] = fp_mul(ninv, z);
+                out_scale = scale;
+            }
+        }
+        return dist_inprocess_ntt_host(in[0], out[0], om, log_n, out_scale);
+    }
+    if ((int)log_n < min_cols_log && ncols < 64) return domain_op_host_one(op, in, out, ncols, k, ek, omega_user);
+    const int g = ncols < (size_t)nd ? (int)ncols : nd;
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);  // lock order: home slot first, then the fan-out
+    return run_on_devices(g, [&](int slot) -> int {
+        size_t c0, nc;
+        point_range(ncols, slot, g, &c0, &nc);
+        return domain_op_host_one(op, in + c0, out + c0, nc, k, ek, omega_user);
+    });
+}
+
 // MSM of device scalars against srs[offset .. offset+n), through the window table when available
 static int msm_srs_dev(Srs* srs, size_t offset, const uint4* d_scalars, size_t n, cudaStream_t stream, uint64_t* out,
                        uint32_t ncols = 1, uint32_t phase = MSM_WHOLE, cudaEvent_t input_ready = nullptr) {
@@ -697,10 +915,20 @@ static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t
     return ZKB_OK;
 }
 
-static int find_srs(uint64_t handle, Srs** out) {
+static int find_srs_set(uint64_t handle, SrsSet** out) {
+    std::lock_guard<std::mutex> lk(g_srs_mu);
     auto it = srs_map().find(handle);
     if (it == srs_map().end()) { set_error("unknown SRS handle %llu", (unsigned long long)handle); return ZKB_ERR_HANDLE; }
     *out = it->second;
+    return ZKB_OK;
+}
+// the replica of a registered SRS on the calling thread's device slot
+static int find_srs(uint64_t handle, Srs** out) {
+    SrsSet* set;
+    ZKB_TRY(find_srs_set(handle, &set));
+    Srs* s = set->dev[cur_slot()];
+    if (!s) { set_error("SRS handle %llu has no replica on device slot %d", (unsigned long long)handle, cur_slot()); return ZKB_ERR_HANDLE; }
+    *out = s;
     return ZKB_OK;
 }
 
@@ -734,20 +962,9 @@ int zkb_device_count(void) {
 const char* zkb_version(void) { return "zkb200 0.1 (sm_100a)"; }
 const char* zkb_last_error(void) { return g_error.c_str(); }
 
-int zkb_init(const int* devices, int ndev) {
+static int init_slot(int slot, int dev) {
+    SlotScope sc(slot);
     Ctx& c = ctx();
-    std::lock_guard<std::recursive_mutex> lock(c.mu);
-    if (ndev < 0 || ndev > 1) { set_error("one process per GPU: ndev must be 0 or 1 (got %d)", ndev); return ZKB_ERR_ARG; }
-    int count = zkb_device_count();
-    if (count == 0) { set_error("no CUDA device visible; libzkb200 has no CPU fallback"); return ZKB_ERR_NO_DEVICE; }
-    int dev = 0;
-    if (devices && ndev == 1) dev = devices[0];
-    else if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
-    if (dev < 0 || dev >= count) { set_error("device %d out of range (count %d)", dev, count); return ZKB_ERR_ARG; }
-    if (c.inited) {
-        if (dev != c.device && devices) { set_error("already bound to device %d", c.device); return ZKB_ERR_ARG; }
-        return ZKB_OK;
-    }
     ZKB_CUDA_TRY(cudaSetDevice(dev));
     cudaDeviceProp prop;
     ZKB_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
@@ -759,7 +976,73 @@ int zkb_init(const int* devices, int ndev) {
     return ZKB_OK;
 }
 
-void zkb_shutdown(void) {
+int zkb_init(const int* devices, int ndev) {
+    Ctx& c = per_device<Ctx>();  // the caller's slot (0 for application threads)
+    std::lock_guard<std::recursive_mutex> lock(c.mu);
+    if (ndev < 0 || ndev > ZKB_MAX_DEVICES) { set_error("ndev must be in [0, %d] (got %d)", ZKB_MAX_DEVICES, ndev); return ZKB_ERR_ARG; }
+    if (cur_slot() != 0) { set_error("zkb_init must be called from an application thread"); return ZKB_ERR_ARG; }
+    int count = zkb_device_count();
+    if (count == 0) { set_error("no CUDA device visible; libzkb200 has no CPU fallback"); return ZKB_ERR_NO_DEVICE; }
+    int list[ZKB_MAX_DEVICES];
+    int n = 0;
+    if (devices && ndev >= 1) {
+        for (int i = 0; i < ndev; ++i) list[n++] = devices[i];
+    } else if (const char* e = getenv("ZKB_DEVICES")) {  // "all" or "0,1,2,3": lets an unmodified caller (zkb_init(NULL, 0)) drive the whole box
+        if (!strcmp(e, "all")) { for (int i = 0; i < count && i < ZKB_MAX_DEVICES; ++i) list[n++] = i; }
+        else for (const char* q = e; *q && n < ZKB_MAX_DEVICES;) {
+            list[n++] = atoi(q);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    }
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        list[n++] = dev;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (list[i] < 0 || list[i] >= count) { set_error("device %d out of range (count %d)", list[i], count); return ZKB_ERR_ARG; }
+        for (int j = 0; j < i; ++j)
+            if (list[j] == list[i]) { set_error("device %d listed twice", list[i]); return ZKB_ERR_ARG; }
+    }
+    if (c.inited) {
+        if (!devices) return ZKB_OK;
+        bool same = n == g_nslots;
+        for (int i = 0; same && i < n; ++i) same = list[i] == g_slot_device[i];
+        if (!same) { set_error("already bound to %d device(s) starting with device %d; call zkb_shutdown first", g_nslots, g_slot_device[0]); return ZKB_ERR_ARG; }
+        return ZKB_OK;
+    }
+    for (int i = 0; i < n; ++i) g_slot_device[i] = list[i];
+    for (int i = 0; i < n; ++i) {
+        int rc = init_slot(i, list[i]);
+        if (rc != ZKB_OK) {
+            for (int j = 0; j < i; ++j) { SlotScope sc(j); Ctx& cj = ctx(); cudaStreamDestroy(cj.stream); cj.stream = nullptr; cj.inited = false; }
+            return rc;
+        }
+    }
+    // all pairs reach each other's HBM over NVLink (SRS replication, the sharded NTT's fused exchange)
+    for (int i = 0; i < n && n > 1; ++i) {
+        SlotScope sc(i);
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(list[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                set_error("device %d cannot map device %d's memory (%s); multi-device mode needs peer access", list[i], list[j], cudaGetErrorString(e));
+                for (int q = 0; q < n; ++q) { SlotScope s2(q); Ctx& cq = ctx(); cudaStreamDestroy(cq.stream); cq.stream = nullptr; cq.inited = false; }
+                return ZKB_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+    }
+    g_nslots = n;
+    for (int i = 1; i < n; ++i) g_workers[i].start(i);
+    cudaSetDevice(list[0]);
+    return ZKB_OK;
+}
+
+// releases everything the calling slot holds on its device
+static void shutdown_slot() {
     Ctx& c = ctx();
     std::lock_guard<std::recursive_mutex> lock(c.mu);
     if (!c.inited) return;
@@ -767,9 +1050,6 @@ void zkb_shutdown(void) {
     cudaDeviceSynchronize();
     dist_shutdown();
     setup_release();
-    poly_release_all();
-    for (auto& kv : srs_map()) { kv.second->bases.release(); kv.second->table.release(); delete kv.second; }
-    srs_map().clear();
     ntt_clear_plans();
     msm_release_workspace();
     HostIo& h = hostio();
@@ -787,6 +1067,38 @@ void zkb_shutdown(void) {
     c.inited = false;
 }
 
+void zkb_shutdown(void) {
+    if (cur_slot() != 0 || g_nslots == 0) return;
+    {
+        std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+        if (!ctx().inited) return;
+        cudaSetDevice(ctx().device);
+        cudaDeviceSynchronize();
+        poly_release_all();
+        std::lock_guard<std::mutex> lk(g_srs_mu);
+        for (auto& kv : srs_map()) {
+            for (int i = 0; i < ZKB_MAX_DEVICES; ++i) {
+                Srs* r = kv.second->dev[i];
+                if (!r) continue;
+                SlotScope sc(i);
+                cudaDeviceSynchronize();
+                r->bases.release(); r->table.release();
+                delete r;
+            }
+            delete kv.second;
+        }
+        srs_map().clear();
+    }
+    const int n = g_nslots;
+    for (int i = n - 1; i >= 1; --i) {
+        g_workers[i].stop();
+        SlotScope sc(i);
+        shutdown_slot();
+    }
+    shutdown_slot();
+    g_nslots = 0;
+}
+
 // ---- MSM ---------------------------------------------------------------------------------------------------------------------
 int zkb_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
@@ -794,11 +1106,25 @@ int zkb_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_
     ZKB_TRY(check_ptr(out_jac, "out_jac"));
     if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
     ZKB_TRY(check_ptr(bases, "bases"));
-    HostIo& h = hostio();
-    ZKB_TRY(h.bases.reserve(n * 64));
-    ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, bases, n * 64, cudaMemcpyHostToDevice, ctx().stream));
-    ZKB_TRY(upload_scalars(scalars, n));
-    return msm_run(h.scalars.as<uint4>(), h.bases.as<uint4>(), n, ctx().stream, out_jac);
+    ZKB_TRY(check_ptr(scalars, "scalars"));
+    auto one = [&](size_t off, size_t len, uint64_t* out) -> int {
+        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+        ZKB_TRY(require_init());
+        HostIo& h = hostio();
+        ZKB_TRY(h.bases.reserve(len * 64));
+        ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, bases + 8 * off, len * 64, cudaMemcpyHostToDevice, ctx().stream));
+        ZKB_TRY(upload_scalars(scalars + 4 * off, len));
+        return msm_run(h.scalars.as<uint4>(), h.bases.as<uint4>(), len, ctx().stream, out);
+    };
+    const int g = msm_fanout(n);
+    if (g <= 1) return one(0, n, out_jac);
+    uint64_t parts[ZKB_MAX_DEVICES][12];
+    ZKB_TRY(run_on_devices(g, [&](int slot) -> int {
+        size_t off, len;
+        point_range(n, slot, g, &off, &len);
+        return one(off, len, parts[slot]);
+    }));
+    return g1_sum_host(&parts[0][0], (size_t)g, out_jac);
 }
 
 int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle) {
@@ -814,9 +1140,7 @@ int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle) {
         cudaError_t e = cudaMemcpy(s->bases.p, bases, n * 64, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { set_error("SRS upload failed: %s", cudaGetErrorString(e)); s->bases.release(); delete s; return ZKB_ERR_CUDA; }
     }
-    *handle = g_next_handle++;
-    srs_map()[*handle] = s;
-    return ZKB_OK;
+    return srs_publish(s, handle);
 }
 
 // n raw G1Affine (64 B each, Montgomery limbs — what SerdeFormat::RawBytes / RawBytesUnchecked write) from `path` at byte
@@ -877,22 +1201,28 @@ int zkb_srs_load_file(const char* path, uint64_t offset, size_t n, int check_poi
         if (rc != ZKB_OK) return cleanup(rc);
         if (bad) { set_error("%s: %llu of %zu points are not on the curve", path, (unsigned long long)bad, n); return cleanup(ZKB_ERR_ARG); }
     }
-    rc = cleanup(ZKB_OK);
-    *handle = g_next_handle++;
-    srs_map()[*handle] = s;
-    return rc;
+    cleanup(ZKB_OK);
+    return srs_publish(s, handle);
 }
 
 int zkb_srs_release(uint64_t handle) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
-    Srs* s;
-    ZKB_TRY(find_srs(handle, &s));
-    cudaSetDevice(ctx().device);
-    cudaDeviceSynchronize();
-    s->bases.release();
-    s->table.release();
-    delete s;
-    srs_map().erase(handle);
+    SrsSet* set;
+    ZKB_TRY(find_srs_set(handle, &set));
+    {
+        std::lock_guard<std::mutex> lk(g_srs_mu);
+        srs_map().erase(handle);
+    }
+    for (int i = 0; i < ZKB_MAX_DEVICES; ++i) {
+        Srs* s = set->dev[i];
+        if (!s) continue;
+        SlotScope sc(i);
+        cudaDeviceSynchronize();
+        s->bases.release();
+        s->table.release();
+        delete s;
+    }
+    delete set;
     return ZKB_OK;
 }
 
@@ -907,11 +1237,66 @@ int zkb_msm_g1_srs_range(uint64_t handle, size_t offset, const uint64_t* scalars
         return ZKB_ERR_ARG;
     }
     if (n == 0) { msm_identity_out(out_jac); return ZKB_OK; }
-    return msm_srs_host(s, offset, scalars, n, out_jac);
+    ZKB_TRY(check_ptr(scalars, "scalars"));
+    // several devices: the commit is sharded by SRS point range, every device uploads only its share of the scalars over its own
+    // PCIe link, and the 96-byte partial results are folded here on the host (north_star: "combined on the host")
+    const int g = msm_fanout(n);
+    if (g <= 1) return msm_srs_host(s, offset, scalars, n, out_jac);
+    SrsSet* set;
+    ZKB_TRY(find_srs_set(handle, &set));
+    uint64_t parts[ZKB_MAX_DEVICES][12];
+    ZKB_TRY(run_on_devices(g, [&](int slot) -> int {
+        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+        ZKB_TRY(require_init());
+        Srs* r = set->dev[slot];
+        if (!r) { set_error("SRS has no replica on device slot %d", slot); return ZKB_ERR_HANDLE; }
+        size_t off, len;
+        point_range(n, slot, g, &off, &len);
+        return msm_srs_host(r, offset + off, scalars + 4 * off, len, parts[slot]);
+    }));
+    return g1_sum_host(&parts[0][0], (size_t)g, out_jac);
 }
 
 int zkb_msm_g1_srs(uint64_t handle, const uint64_t* scalars, size_t n, uint64_t out_jac[12]) {
     return zkb_msm_g1_srs_range(handle, 0, scalars, n, out_jac);
+}
+
+// one device's share of a batch: columns [0, ncols) of `scalars` against the replica `s`
+static int msm_batch_one(Srs* s, const uint64_t* const* scalars, size_t ncols, size_t n, uint64_t* out_jac) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    // all columns of a group are digit-decomposed, sorted and accumulated in ONE pass (column folded into the bucket
+    // key); groups bound the sort size to 2^28 (key, index) pairs, the bucket keys to 31 bits and the bucket arrays to a
+    // quarter of the free HBM (in table mode every column owns 2^(c-1) buckets whatever its length)
+    const size_t per_col = n * 16;  // generous bound on windows per scalar
+    size_t group = ((size_t)1 << 28) / per_col;
+    if (group < 1) group = 1;
+    if (group > 4096) group = 4096;
+    Ctx& c = ctx();
+    HostIo& h = hostio();
+    {
+        const bool table = srs_table_ready(s, c.stream);
+        const MsmGeometry g1 = table ? msm_geometry(n, s->table_c, c.msm_chunk_override, true, 1)
+                                     : msm_geometry(n, c.msm_c_override, c.msm_chunk_override, false, 1);
+        const size_t per_col_buckets = (size_t)g1.bucket_sets << (g1.c - 1);
+        size_t by_keys = (((size_t)1 << 31) - 1) / per_col_buckets;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+        size_t by_mem = (free_b / 4) / (per_col_buckets * 128);
+        if (by_keys < 1) by_keys = 1;
+        if (by_mem < 1) by_mem = 1;
+        if (group > by_keys) group = by_keys;
+        if (group > by_mem) group = by_mem;
+    }
+    for (size_t c0 = 0; c0 < ncols; c0 += group) {
+        size_t nc = ncols - c0 < group ? ncols - c0 : group;
+        ZKB_TRY(h.scalars.reserve(nc * n * 32));
+        for (size_t i = 0; i < nc; ++i)
+            ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h.scalars.p) + i * n * 32, scalars[c0 + i], n * 32,
+                                         cudaMemcpyHostToDevice, c.stream));
+        ZKB_TRY(msm_srs_dev(s, 0, h.scalars.as<uint4>(), n, c.stream, out_jac + 12 * c0, (uint32_t)nc));
+    }
+    return ZKB_OK;
 }
 
 int zkb_msm_g1_srs_batch(uint64_t handle, const uint64_t* const* scalars, size_t ncols, size_t n, uint64_t* out_jac) {
@@ -925,26 +1310,23 @@ int zkb_msm_g1_srs_batch(uint64_t handle, const uint64_t* const* scalars, size_t
     if (n > s->n) { set_error("MSM length %zu exceeds the registered SRS length %zu", n, s->n); return ZKB_ERR_ARG; }
     if (n == 0) { for (size_t i = 0; i < ncols; ++i) msm_identity_out(out_jac + 12 * i); return ZKB_OK; }
     for (size_t i = 0; i < ncols; ++i) ZKB_TRY(check_ptr(scalars[i], "scalars column"));
-    // all columns of a group are digit-decomposed, sorted and accumulated in ONE pass (column folded into the bucket
-    // key); groups bound the sort size to 2^28 (key, index) pairs
-    const size_t per_col = n * 16;  // generous bound on windows per scalar
-    size_t group = ((size_t)1 << 28) / per_col;
-    if (group < 1) group = 1;
-    if (group > 4096) group = 4096;
-    Ctx& c = ctx();
-    HostIo& h = hostio();
-    for (size_t c0 = 0; c0 < ncols; c0 += group) {
-        size_t nc = ncols - c0 < group ? ncols - c0 : group;
-        ZKB_TRY(h.scalars.reserve(nc * n * 32));
-        for (size_t i = 0; i < nc; ++i)
-            ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h.scalars.p) + i * n * 32, scalars[c0 + i], n * 32,
-                                         cudaMemcpyHostToDevice, c.stream));
-        ZKB_TRY(msm_srs_dev(s, 0, h.scalars.as<uint4>(), n, c.stream, out_jac + 12 * c0, (uint32_t)nc));
-    }
-    return ZKB_OK;
+    // several devices: the batch is split by column (contiguous column ranges), no communication
+    int g = cur_slot() == 0 ? device_slots() : 1;
+    if ((size_t)g > ncols) g = (int)ncols;
+    if (g <= 1 || ncols * n < ((size_t)1 << 17)) return msm_batch_one(s, scalars, ncols, n, out_jac);
+    SrsSet* set;
+    ZKB_TRY(find_srs_set(handle, &set));
+    return run_on_devices(g, [&](int slot) -> int {
+        Srs* r = set->dev[slot];
+        if (!r) { set_error("SRS has no replica on device slot %d", slot); return ZKB_ERR_HANDLE; }
+        size_t c0, nc;
+        point_range(ncols, slot, g, &c0, &nc);
+        return msm_batch_one(r, scalars + c0, nc, n, out_jac + 12 * c0);
+    });
 }
 
 int zkb_msm_g1_srs_dev(uint64_t handle, size_t offset, const void* d_scalars, size_t n, uint64_t out_jac[12], void* stream) {
+    SlotScope scope(slot_of_device_ptr(d_scalars));  // several devices in one process: the pointer's owner runs the call
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
     ZKB_TRY(check_ptr(out_jac, "out_jac"));
@@ -966,6 +1348,14 @@ int zkb_srs_precompute(uint64_t handle, uint32_t* window_bits, uint64_t* table_b
     ZKB_TRY(require_init());
     Srs* s;
     ZKB_TRY(find_srs(handle, &s));
+    SrsSet* set;
+    ZKB_TRY(find_srs_set(handle, &set));
+    if (cur_slot() == 0 && device_slots() > 1)   // every replica builds its own table, all devices at once
+        run_on_devices(device_slots(), [&](int slot) -> int {
+            std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+            if (require_init() == ZKB_OK && set->dev[slot]) srs_table_ready(set->dev[slot], ctx().stream, true);
+            return ZKB_OK;
+        });
     bool ok = srs_table_ready(s, ctx().stream, true);
     if (window_bits) *window_bits = ok ? s->table_c : 0;
     if (table_bytes) *table_bytes = ok ? (uint64_t)s->table_nwin * s->n * 64 : 0;
@@ -1058,7 +1448,7 @@ static int kzg_setup_common(uint32_t k, const uint64_t* s, uint64_t* g_out, uint
     if (rc == ZKB_ERR_CUDA) { set_error("ParamsKZG::setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     auto finish = [&](Srs* p, uint64_t* handle) {
         if (!p) return;
-        if (rc == ZKB_OK && handle) { *handle = g_next_handle++; srs_map()[*handle] = p; }
+        if (rc == ZKB_OK && handle) rc = srs_publish(p, handle);
         else { p->bases.release(); delete p; }
     };
     finish(sg, hg);
@@ -1110,9 +1500,7 @@ int zkb_srs_g_to_lagrange(uint64_t handle_g, uint32_t k, uint64_t* handle_g_lagr
     if (rc == ZKB_OK) rc = g1_fft_dev(g->bases.as<uint4>(), gl->bases.as<uint4>(), k, omega_inv, &n_inv, ctx().stream);
     if (rc == ZKB_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) { set_error("g_to_lagrange failed"); rc = ZKB_ERR_CUDA; }
     if (rc != ZKB_OK) { cudaGetLastError(); gl->bases.release(); delete gl; return rc; }
-    *handle_g_lagrange = g_next_handle++;
-    srs_map()[*handle_g_lagrange] = gl;
-    return ZKB_OK;
+    return srs_publish(gl, handle_g_lagrange);
 }
 
 int zkb_srs_download(uint64_t handle, uint64_t* bases_out, size_t n) {
@@ -1164,6 +1552,23 @@ int zkb_extended_to_coeff(uint64_t* a, uint32_t k, uint32_t extended_k) {
     uint64_t* out[1] = {a};
     return domain_op_host(OP_E2C, in, out, 1, k, extended_k, nullptr);
 }
+int zkb_fr_zeta(uint64_t out[4]) {
+    ZKB_TRY(check_ptr(out, "out"));
+    fr_to_limbs64(fr_zeta(), out);
+    return ZKB_OK;
+}
+int zkb_multi_device_set(int msm_min_share_log, int batch_ntt_min_log, int dist_ntt_min_log) {
+    const int v[3] = {msm_min_share_log, batch_ntt_min_log, dist_ntt_min_log};
+    for (int i = 0; i < 3; ++i) {
+        if (v[i] < 0 || v[i] > 40) { set_error("thresholds are log2 sizes in [1, 40], 0 = default"); return ZKB_ERR_ARG; }
+        g_multi[i] = v[i] ? v[i] : -1;
+    }
+    return ZKB_OK;
+}
+int zkb_bound_devices(int* devices, int capacity) {
+    for (int i = 0; i < g_nslots && i < capacity && devices; ++i) devices[i] = g_slot_device[i];
+    return g_nslots;
+}
 int zkb_fr_omega(uint32_t k, uint64_t out[4]) {
     ZKB_TRY(check_ptr(out, "out"));
     if (k > 28) { set_error("k %u exceeds the two-adicity 28", k); return ZKB_ERR_ARG; }
@@ -1173,6 +1578,7 @@ int zkb_fr_omega(uint32_t k, uint64_t out[4]) {
 
 static int dev_common(DomainOp op, const void* d_in, void* d_a, void* d_b, size_t ncols, uint32_t k, uint32_t ek,
                       const uint64_t* omega, void* stream) {
+    SlotScope scope(slot_of_device_ptr(d_a));
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
     ZKB_TRY(check_ptr(d_in, "device input"));
@@ -1273,7 +1679,12 @@ int zkb_prof_get(const char* name, double* total_ms, uint64_t* launches) {
     if (launches) *launches = it->second.launches;
     return ZKB_OK;
 }
-uint64_t zkb_launch_count(void) { return ctx().launches.load(); }
+uint64_t zkb_launch_count(void) {  // all device slots
+    uint64_t total = 0;
+    Ctx* all = per_device_array<Ctx>();
+    for (int i = 0; i < ZKB_MAX_DEVICES; ++i) total += all[i].launches.load();
+    return total;
+}
 int zkb_measure_imad_peak(double* wide_macs_per_s) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());

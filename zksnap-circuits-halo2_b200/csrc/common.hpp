@@ -1,9 +1,15 @@
-// common.hpp — process-wide context of libzkb200: device binding, error reporting, grow-only workspaces,
-// CUDA-event profiling and launch counting.
+// common.hpp — context of libzkb200: device binding, error reporting, grow-only workspaces, CUDA-event profiling and
+// launch counting.
+//
+// One process drives 1..8 GPUs.  Everything that lives on a GPU (streams, workspaces, twiddle plans, SRS replicas, staging
+// pipelines) exists once per DEVICE SLOT; `cur_slot()` is a thread-local index, so the single-device code paths are written
+// once and run unchanged on any slot: the calling thread is slot 0 (the home device), slots 1.. are served by one worker
+// thread each (`run_on_devices`), and `SlotScope` lets a caller's thread act on another slot for device-pointer calls.
 #pragma once
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <functional>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -65,6 +71,30 @@ struct Ctx {
     uint32_t msm_c_override = 0;
     uint32_t msm_chunk_override = 0;
 };
+
+constexpr int ZKB_MAX_DEVICES = 8;
+int cur_slot();                       // device slot of the calling thread (0 = home device)
+int device_slots();                   // number of bound devices (0 before zkb_init)
+int slot_device(int slot);            // CUDA ordinal bound to a slot
+// per-device instance of a (default-constructible) singleton, selected by the calling thread's slot
+template <class T>
+T* per_device_array() {
+    static T inst[ZKB_MAX_DEVICES];
+    return inst;
+}
+template <class T>
+T& per_device() { return per_device_array<T>()[cur_slot()]; }
+// Runs f(slot) for slot = 0 .. count-1: slot 0 on the calling thread, the others on the per-device worker threads, all at the
+// same time.  Returns the first failing slot's code with its error text copied to the caller's thread.
+int run_on_devices(int count, const std::function<int(int)>& f);
+// Makes the calling thread act as `slot` (thread-local slot + cudaSetDevice) until destruction.
+struct SlotScope {
+    int prev;
+    explicit SlotScope(int slot);
+    ~SlotScope();
+};
+// slot that owns a device pointer (0 when there is one device or the pointer is unknown)
+int slot_of_device_ptr(const void* p);
 
 Ctx& ctx();
 int require_init();

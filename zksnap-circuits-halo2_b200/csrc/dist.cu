@@ -1,7 +1,8 @@
 // dist.cu — one NTT sharded over the GPUs of a box: peer HBM over NVLink 5 / NVSwitch (CUDA IPC), exchange fused into the
 // NTT passes, device-side barriers.  SURVEY.md §8(e) row "single NTT larger than one GPU's share".
 //
-// One process per GPU.  Rank r owns the contiguous slice [r N/G, (r+1) N/G) of the natural-order input and receives the
+// One process per GPU (CUDA IPC mappings exchanged by the caller), or one process driving all GPUs (zkb_init with several
+// devices: plain peer access, ranks = device slots, every rank's kernels launched by its own worker thread).  Rank r owns the contiguous slice [r N/G, (r+1) N/G) of the natural-order input and receives the
 // same slice of the natural-order output.  The multi-pass NTT of ntt.cuh is kept as is; only the addressing changes:
 //
 //   pass 0        every CTA gathers its R_1 x T tile from all ranks' input slices (peer loads: the "transpose" of the
@@ -14,6 +15,7 @@
 //   barrier.
 //
 // There is no separate transpose pass and no staging copy: the collective is the kernels' own loads and stores.
+#include <cstdlib>
 #include <cstring>
 
 #include "ntt_host.hpp"
@@ -22,6 +24,7 @@ namespace zkb {
 
 struct DistCtx {
     bool created = false, connected = false;
+    bool inprocess = false;        // peers are other device slots of this process (peer access, no IPC handles)
     int rank = -1, world = 0;
     uint32_t log_g = 0, max_log_n = 0;
     size_t slice_bytes = 0;
@@ -32,10 +35,7 @@ struct DistCtx {
     uint32_t epoch = 0;
     uint32_t* h_status = nullptr;  // pinned mirror of the barrier status word
 };
-static DistCtx& dctx() {
-    static DistCtx d;
-    return d;
-}
+static DistCtx& dctx() { return per_device<DistCtx>(); }
 
 struct DistBarrierArgs {
     uint32_t* peer_flags[NTT_MAX_RANKS];
@@ -59,8 +59,8 @@ __global__ void dist_barrier_kernel(const DistBarrierArgs a) {
         if ((int32_t)(v - a.epoch) >= 0) break;
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > a.timeout_ns) {  // a peer never arrived: report instead of hanging the GPU
-            a.my_flags[NTT_MAX_RANKS] = 1;
+        if (t1 - t0 > a.timeout_ns) {  // a peer never arrived: report instead of hanging the GPU; the NTT passes that follow
+            a.my_flags[NTT_MAX_RANKS] = 1;  // see the status word and return at once, so no half-exchanged data is touched
             break;
         }
         __nanosleep(200);
@@ -76,7 +76,10 @@ static int dist_barrier(cudaStream_t s) {
     a.rank = (uint32_t)d.rank;
     a.world = (uint32_t)d.world;
     a.epoch = ++d.epoch;
-    a.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    // Ranks are independent processes (or threads): a first-call plan build or a large pageable staging copy on one of them can
+    // delay its arrival by seconds.  Default 120 s, ZKB_DIST_TIMEOUT_MS overrides.
+    static const unsigned long long timeout_ms = getenv("ZKB_DIST_TIMEOUT_MS") ? strtoull(getenv("ZKB_DIST_TIMEOUT_MS"), nullptr, 10) : 120000ull;
+    a.timeout_ns = timeout_ms * 1000ull * 1000ull;
     ProfScope prof("dist_barrier", s);
     dist_barrier_kernel<<<1, 32, 0, s>>>(a);
     count_launch();
@@ -89,7 +92,7 @@ static void dist_release() {
     if (!d.created) return;
     cudaDeviceSynchronize();
     for (int r = 0; r < d.world; ++r) {
-        if (r == d.rank || !d.connected) continue;
+        if (r == d.rank || !d.connected || d.inprocess) continue;
         for (int b = 0; b < 3; ++b)
             if (d.peer[b][r]) cudaIpcCloseMemHandle(d.peer[b][r]);
         if (d.peer_flags[r]) cudaIpcCloseMemHandle(d.peer_flags[r]);
@@ -102,11 +105,18 @@ static void dist_release() {
     d = DistCtx();
 }
 
-void dist_shutdown() { dist_release(); }
+struct InprocShared;
+static InprocShared& inproc();
+static void inproc_reset();
+void dist_shutdown() {
+    dist_release();
+    if (cur_slot() == 0) inproc_reset();
+}
 
 // Sharded NTT on device slices.  d_in == NULL: the input is already in the symmetric input slice (zkb_dist_buffers);
 // d_out == NULL: leave the result in the symmetric output slice.
-static int dist_ntt_dev(const void* d_in, void* d_out, const uint64_t omega[4], uint32_t log_n, cudaStream_t s) {
+static int dist_ntt_dev(const void* d_in, void* d_out, const uint64_t omega[4], uint32_t log_n, cudaStream_t s,
+                        const Fr* out_scale = nullptr) {
     DistCtx& d = dctx();
     if (!d.connected) { set_error("zkb_dist_connect has not been called"); return ZKB_ERR_ARG; }
     if (log_n > d.max_log_n) { set_error("log_n %u exceeds the dist context's max_log_n %u", log_n, d.max_log_n); return ZKB_ERR_ARG; }
@@ -132,6 +142,11 @@ static int dist_ntt_dev(const void* d_in, void* d_out, const uint64_t omega[4], 
         a.tw_h = g.tw_h;
         a.tw_pass = (plan->has_tw_pass && p > 0) ? plan->tw_pass[p].as<uint4>() : nullptr;
         a.in_len = N;
+        a.out_scale_on = (fin && out_scale) ? 1 : 0;
+        if (a.out_scale_on)
+            for (int m = 0; m < 3; ++m)
+                for (int i = 0; i < 8; ++i) a.out_scale[m][i] = out_scale[m].l[i];
+        a.dist_abort = d.flags + NTT_MAX_RANKS;
         a.dist_log_g = d.log_g; a.dist_rank = (uint32_t)d.rank; a.dist_log_slice = log_n - d.log_g;
         for (int r = 0; r < d.world; ++r) {
             a.peer_src[r] = reinterpret_cast<const uint4*>(d.peer[p == 0 ? 0 : 1][r]);
@@ -153,10 +168,98 @@ static int dist_check_status(cudaStream_t s) {
     ZKB_CUDA_TRY(cudaMemcpyAsync(d.h_status, d.flags + NTT_MAX_RANKS, 4, cudaMemcpyDeviceToHost, s));
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
     if (*d.h_status) {
-        set_error("distributed barrier timed out: a peer rank never arrived");
+        // reported once: clear the word so that a later collective call (after the late rank has recovered) can succeed
+        cudaMemsetAsync(d.flags + NTT_MAX_RANKS, 0, 4, s);
+        cudaStreamSynchronize(s);
+        set_error("distributed barrier timed out: a peer rank never arrived; the transform was abandoned (its output slice is undefined)");
         return ZKB_ERR_CUDA;
     }
     return ZKB_OK;
+}
+
+// ---- one process, several device slots ----------------------------------------------------------------------------------------
+struct InprocShared {
+    std::mutex mu;
+    uint32_t max_log_n = 0;
+    int world = 0;
+    void* local[ZKB_MAX_DEVICES][3] = {};
+    uint32_t* flags[ZKB_MAX_DEVICES] = {};
+};
+static InprocShared& inproc() {
+    static InprocShared s;
+    return s;
+}
+static void inproc_reset() { inproc().world = 0; inproc().max_log_n = 0; }
+
+// Called on slot 0.  (Re)creates the symmetric slices on every slot when the requested size grows.
+static int dist_inprocess_setup(uint32_t log_n, int world) {
+    InprocShared& sh = inproc();
+    if (sh.world == world && sh.max_log_n >= log_n && dctx().connected && dctx().inprocess) return ZKB_OK;
+    uint32_t log_g = 0;
+    while ((1 << log_g) < world) ++log_g;
+    const uint32_t max_log_n = log_n > sh.max_log_n ? log_n : sh.max_log_n;
+    const size_t slice_bytes = ((size_t)1 << (max_log_n - log_g)) * 32;
+    ZKB_TRY(run_on_devices(world, [&](int slot) -> int {
+        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+        ZKB_TRY(require_init());
+        dist_release();
+        DistCtx& d = dctx();
+        d.rank = slot; d.world = world; d.log_g = log_g; d.max_log_n = max_log_n; d.slice_bytes = slice_bytes;
+        d.created = true; d.inprocess = true;
+        for (int b = 0; b < 3; ++b) {
+            if (cudaMalloc(&d.local[b], slice_bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu) for the dist slice failed", slice_bytes); dist_release(); return ZKB_ERR_OOM; }
+            sh.local[slot][b] = d.local[b];
+        }
+        ZKB_CUDA_TRY(cudaMalloc(&d.flags, 256));
+        ZKB_CUDA_TRY(cudaMemset(d.flags, 0, 256));
+        ZKB_CUDA_TRY(cudaMallocHost(&d.h_status, 64));
+        ZKB_CUDA_TRY(cudaDeviceSynchronize());
+        sh.flags[slot] = d.flags;
+        return ZKB_OK;
+    }));
+    ZKB_TRY(run_on_devices(world, [&](int slot) -> int {
+        DistCtx& d = dctx();
+        for (int r = 0; r < world; ++r) {
+            for (int b = 0; b < 3; ++b) d.peer[b][r] = sh.local[r][b];   // unified addressing + peer access (zkb_init)
+            d.peer_flags[r] = sh.flags[r];
+        }
+        d.connected = true;
+        return ZKB_OK;
+    }));
+    sh.world = world;
+    sh.max_log_n = max_log_n;
+    return ZKB_OK;
+}
+
+// best_fft (optionally with the fused output scaling of lagrange_to_coeff / extended_to_coeff) of ONE host vector over all
+// device slots: slot r uploads the contiguous slice [r N/G, (r+1) N/G) over its own PCIe link, the slots run the sharded NTT
+// together, every slot downloads its slice of the natural-order result.  Called on slot 0 with its mutex held.
+bool dist_inprocess_supported(uint32_t log_n) {
+    int world = 1;
+    while (world * 2 <= device_slots() && world * 2 <= NTT_MAX_RANKS) world *= 2;
+    uint32_t log_g = 0;
+    while ((1 << log_g) < world) ++log_g;
+    return world >= 2 && log_n <= 28 && ntt_dist_supported(ntt_geometry(log_n, true), log_g);
+}
+
+int dist_inprocess_ntt_host(const uint64_t* in, uint64_t* out, const uint64_t omega[4], uint32_t log_n, const Fr* out_scale) {
+    int world = 1;
+    while (world * 2 <= device_slots() && world * 2 <= NTT_MAX_RANKS) world *= 2;
+    uint32_t log_g = 0;
+    while ((1 << log_g) < world) ++log_g;
+    if (world < 2 || !ntt_dist_supported(ntt_geometry(log_n, true), log_g)) { set_error("a 2^%u NTT cannot be sharded over %d devices", log_n, world); return ZKB_ERR_ARG; }
+    ZKB_TRY(dist_inprocess_setup(log_n, world));
+    const size_t slice = ((size_t)1 << (log_n - log_g)) * 32;
+    return run_on_devices(world, [&](int slot) -> int {
+        std::lock_guard<std::recursive_mutex> lk(ctx().mu);
+        ZKB_TRY(require_init());
+        DistCtx& d = dctx();
+        cudaStream_t s = ctx().stream;
+        ZKB_CUDA_TRY(cudaMemcpyAsync(d.local[0], reinterpret_cast<const char*>(in) + (size_t)slot * slice, slice, cudaMemcpyHostToDevice, s));
+        ZKB_TRY(dist_ntt_dev(nullptr, nullptr, omega, log_n, s, out_scale));
+        ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)slot * slice, d.local[2], slice, cudaMemcpyDeviceToHost, s));
+        return dist_check_status(s);
+    });
 }
 
 }  // namespace zkb

@@ -159,10 +159,9 @@ int srs_table_build(const uint4* d_bases, uint64_t n, uint32_t c, uint32_t nwin,
 }
 
 MsmWorkspace& msm_workspace() {
-    static MsmWorkspace w;
-    static bool init = false;
-    if (!init) {
-        init = true;
+    MsmWorkspace& w = per_device<MsmWorkspace>();
+    if (!w.env_read) {
+        w.env_read = true;
         if (const char* e = getenv("ZKB_MSM_OVERLAP")) w.overlap = atoi(e);
     }
     return w;
@@ -412,7 +411,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
     ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, sums, (size_t)g.total_sets * 128, cudaMemcpyDeviceToHost, s));
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
     for (uint32_t col = 0; col < ncols; ++col) {
-        XYZZ hs[64];
+        XYZZ hs[MSM_MAX_WINDOWS];  // c >= 2 gives at most 128 window sums per column
         for (uint32_t i = 0; i < g.bucket_sets; ++i)
             hs[i] = XYZZ::load(reinterpret_cast<const uint4*>(w.h_sums) + 8 * ((size_t)col * g.bucket_sets + i));
         XYZZ res = msm_combine_windows(hs, g.bucket_sets, g.c);

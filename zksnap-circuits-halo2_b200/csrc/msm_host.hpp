@@ -18,6 +18,7 @@ struct MsmWorkspace {
     bool acc_pending[2] = {false, false};  // ev_acc[set] recorded in the current MSM
     uint32_t slice_ix = 0;
     int overlap = 1;         // ZKB_MSM_OVERLAP=0 (environment, read once): run the slices on one stream
+    bool env_read = false;
 };
 
 MsmWorkspace& msm_workspace();

@@ -16,6 +16,7 @@ template <int LOGR>
 __global__ void __launch_bounds__(128, ZKB_NTT_MIN_CTAS) ntt_pass_kernel(const NttPassArgs a) {
     extern __shared__ uint4 ntt_smem[];
     CtaBarrier bar;
+    if (a.dist_abort && *reinterpret_cast<const volatile uint32_t*>(a.dist_abort)) return;  // sharded NTT: a barrier timed out
     ntt_cta_program<LOGR>(a, ntt_smem, threadIdx.x, blockDim.x, (uint64_t)blockIdx.x, blockIdx.y, bar);
 }
 
@@ -36,7 +37,8 @@ __global__ void ntt_pass_table_kernel(uint4* out, const uint4* tw_hi, const uint
 
 template <int LOGR>
 static int launch_pass(const NttPassArgs& a, dim3 grid, uint32_t threads, size_t smem, cudaStream_t s) {
-    static bool attr_set = false;  // per process; one device per process
+    struct AttrSet { bool v = false; };  // the attribute belongs to the (function, device) pair
+    bool& attr_set = per_device<AttrSet>().v;
     if (!attr_set) {
         ZKB_CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel<LOGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
@@ -57,10 +59,8 @@ int ntt_launch_pass(uint32_t logr, const NttPassArgs& a, dim3 grid, uint32_t thr
 }
 
 // ---- plan cache: twiddle tables for (log_n, omega) ---------------------------------------------------------------
-static std::map<std::pair<uint32_t, std::array<uint64_t, 4>>, NttPlan*>& plan_cache() {  // key.first = log_n | small_first << 8
-    static std::map<std::pair<uint32_t, std::array<uint64_t, 4>>, NttPlan*> m;
-    return m;
-}
+using PlanCache = std::map<std::pair<uint32_t, std::array<uint64_t, 4>>, NttPlan*>;  // key.first = log_n | small_first << 8
+static PlanCache& plan_cache() { return per_device<PlanCache>(); }  // twiddle tables live in one device's HBM
 
 static int build_table(DevBuf& buf, const Fr& w, uint64_t count, uint32_t shift, cudaStream_t s) {
     ZKB_TRY(buf.reserve(count * 32));

@@ -67,6 +67,7 @@ struct NttPassArgs {
     uint32_t dist_log_slice;
     const uint4* peer_src[NTT_MAX_RANKS];
     uint4* peer_dst[NTT_MAX_RANKS];
+    const uint32_t* dist_abort;  // status word of the device-side barriers: non-zero = a peer never arrived, skip the pass
 };
 
 // shared memory is split in two planes (low / high 16 bytes) so a warp's 128-bit accesses are conflict-free

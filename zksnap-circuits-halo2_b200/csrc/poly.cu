@@ -100,23 +100,15 @@ struct PolyWs {
     DevBuf tmp;
     void* h_out = nullptr;  // pinned 32 B
 };
-static DevBuf& graph_ws() {
-    static DevBuf b;
-    return b;
-}
+struct GraphWsBuf : DevBuf {};
+static DevBuf& graph_ws() { return per_device<GraphWsBuf>(); }
 struct GraphRing {   // upload buffers of zkb_graph_evaluate_dev
     DevBuf buf[4];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned next = 0;
 };
-static GraphRing& graph_ring() {
-    static GraphRing r;
-    return r;
-}
-static PolyWs& poly_ws() {
-    static PolyWs w;
-    return w;
-}
+static GraphRing& graph_ring() { return per_device<GraphRing>(); }
+static PolyWs& poly_ws() { return per_device<PolyWs>(); }
 
 // sum_i a[i] x^i -> d_out (one Fr on the device)
 static int poly_eval_dev(const uint4* d_a, uint64_t n, Fr x, uint4* d_tmp, uint4** d_result, cudaStream_t s) {
@@ -213,10 +205,7 @@ struct PolyPool {
     size_t bytes = 0;
     size_t limit = ~(size_t)0;          // resolved on first use
 };
-static PolyPool& poly_pool() {
-    static PolyPool p;
-    return p;
-}
+static PolyPool& poly_pool() { return per_device<PolyPool>(); }
 void poly_pool_flush() {
     PolyPool& pool = poly_pool();
     for (auto& kv : pool.free) cudaFree(kv.second);

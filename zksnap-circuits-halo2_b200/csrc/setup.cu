@@ -47,10 +47,7 @@ struct SetupWs {
     DevBuf xyzz, scalars, points;
     uint32_t* d_status = nullptr;
 };
-static SetupWs& setup_ws() {
-    static SetupWs w;
-    return w;
-}
+static SetupWs& setup_ws() { return per_device<SetupWs>(); }
 __global__ void __launch_bounds__(128) g1_on_curve_kernel(const OnCurveArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = i >= a.n || g1_affine_is_valid(affine_load(a.pts + 4 * i));

@@ -17,13 +17,23 @@ def device_count() -> int:
     return lib().zkb_device_count()
 
 
-def init(device: int | None = None) -> None:
-    """Bind this process to one GPU (one process per GPU).  Raises ZkbError if no CUDA device is usable."""
+def init(device=None) -> None:
+    """Bind this process to one GPU (an int), to several GPUs of the box (a list — commits are then sharded by SRS point
+    range, batches by column, one large NTT over NVLink peer memory, all behind the same calls), or to what ZKB_DEVICES /
+    the current CUDA device select (None).  Raises ZkbError if no CUDA device is usable."""
     if device is None:
         check(lib().zkb_init(None, 0))
     else:
-        arr = (ctypes.c_int * 1)(device)
-        check(lib().zkb_init(arr, 1))
+        devs = [int(device)] if isinstance(device, (int, np.integer)) else [int(d) for d in device]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        check(lib().zkb_init(arr, len(devs)))
+
+
+def bound_devices() -> list:
+    """CUDA ordinals bound by init(), home device first."""
+    arr = (ctypes.c_int * 8)()
+    n = lib().zkb_bound_devices(arr, 8)
+    return [int(arr[i]) for i in range(n)]
 
 
 def shutdown() -> None:
@@ -211,7 +221,7 @@ class Polynomial:
 
     def scale_add(self, k: np.ndarray, other: "Polynomial | None" = None) -> "Polynomial":
         """self <- self * k + other (Horner fold of query polynomials in the multiopen provers)"""
-        check(lib().zkb_poly_scale_add(self._h, _p(np.ascontiguousarray(k, dtype=np.uint64).reshape(4)), other._h if other else 0))
+        check(lib().zkb_poly_scale_add(self._h, _p(np.ascontiguousarray(k, dtype=np.uint64).reshape(4)), other._h if other is not None else 0))
         return self
 
     def add_const(self, c: np.ndarray) -> "Polynomial":
