@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — headline measurement of the zkb200 hot path (see DESIGN.md "Measurement").
+"""bench.py — measurement of the zkb200 hot path (DESIGN.md "Measurement").
 
-Step   : one 2^24-point BN254 G1 MSM (ParamsKZG::commit shape: uniform Fr scalars against an SRS resident in
-         HBM) per GPU.  At N GPUs the MSM is sharded by SRS point range, one 2^24-point shard per rank (weak
-         scaling; at N=4 this is the 2^26-point MSM of BASELINE.json's sweep), the 96-byte partial results are
-         folded on the host.
-value  : points/s, whole job, scalars already in HBM, timed with CUDA events on the launch stream.
-e2e    : the same through the host-buffer C ABI call (zkb_msm_g1_srs): pinned host scalars -> H2D -> kernels ->
-         window sums D2H -> host fold, wall clock (the host fold is part of the call).
-ntt    : secondary object: batched 2^22 Fr NTT (16 columns) elements/s and its HBM roofline.
-quotient: secondary object: evaluate_h's custom-gate pass (halo2-base gate on 4 advice columns, 2^24 extended rows resident in HBM)
-         rows/s and its HBM roofline.  At N > 1 `sharded_quotient` is the same pass sharded by rows (halo exchange over NCCL) and
-         `sharded_ntt` one 2^26 NTT sharded over the ranks.
-`--impl reference` times the CPU restatement of halo2's best_multiexp (oracle/, all host threads) on a bounded
-sample of the same workload; the reference itself is Rust with un-vendored dependencies and cannot be built
-in this image (DESIGN.md "Oracle").
+Headline step (the driver's contract line): one 2^24-point BN254 G1 MSM (ParamsKZG::commit shape: uniform Fr scalars against
+an SRS resident in HBM) per GPU.  At N GPUs the MSM is sharded by SRS point range, one 2^24-point shard per rank (weak
+scaling), the 96-byte partial results are folded on the host.
+  value        points/s, whole job, scalars already in HBM, CUDA events on the launch stream
+  e2e          the same through the host-buffer C ABI call (zkb_msm_g1_srs): page-locked host scalars -> H2D -> kernels ->
+               sums D2H -> host fold, wall clock; `e2e_pageable`: the same from pageable memory (what a Rust Vec<Fr> is)
+  roofline     integer-pipe fraction of the dominant kernel (bucket accumulation), IMAD peak measured in the same run
+Objects beside it (all parity-checked, all in the same JSON line):
+  ntt, quotient                 batched 2^22 x 16 best_fft and evaluate_h's gate pass, per GPU
+  wrapper_replay / voter_replay / st_replay
+                                 BASELINE configs #1-#3 "proof-gen sec": the prover's op sequence on the hot path (commits, iNTTs,
+                                 coset NTTs, the quotient transform) replayed in prover order, as STRONG scaling over the N GPUs:
+                                 `kernel` (operands resident in HBM), `dropin` (host buffers through the C ABI, PCIe included)
+  msm_split                     one 2^26-point MSM split N ways (strong scaling, BASELINE config #4's largest size)
+  sharded_ntt, sharded_quotient N > 1: one 2^26 NTT sharded over the ranks / the quotient pass sharded by rows
+  single_process                N > 1: rank 0 ALONE drives all N devices through the unchanged C ABI (zkb_init with N devices) —
+                                 the deployment of the reference's one-process prover — and must reproduce the torchrun results
+`--impl reference` times the CPU restatement of halo2's best_multiexp (oracle/, all host threads, built -O3 -march=native on
+this host) on the same 2^24-point workload; the reference itself is Rust with un-vendored dependencies and cannot be built in
+this image (DESIGN.md "Oracle").
 """
 from __future__ import annotations
 
@@ -27,6 +33,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -40,9 +47,13 @@ NTT_COLS = int(os.environ.get("ZKB_BENCH_NTT_COLS", "16"))
 QUOT_LOG_N = int(os.environ.get("ZKB_BENCH_QUOT_LOG_N", "24"))   # extended domain of the wrapper circuit (k = 22, extended_k = 24)
 QUOT_COLS = int(os.environ.get("ZKB_BENCH_QUOT_COLS", "4"))
 SHARDED_LOG_N = int(os.environ.get("ZKB_BENCH_SHARDED_LOG_N", "26"))
-CPU_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_CPU_LOG_N", "24"))   # cpu_baseline leg: the full workload once, ~10 s on 16 threads
-REF_SAMPLE_LOG_N = int(os.environ.get("ZKB_BENCH_REF_LOG_N", "22"))   # --impl reference: bounded sample per step
+SPLIT_LOG_N = int(os.environ.get("ZKB_BENCH_SPLIT_LOG_N", "26"))   # one MSM of this size split over the N GPUs
+WRAPPER_K = int(os.environ.get("ZKB_BENCH_WRAPPER_K", "22"))
+REF_MAX_STEPS = int(os.environ.get("ZKB_BENCH_REF_STEPS", "3"))     # --impl reference: one 2^24 step is ~8 s of 16 host threads
 METRIC = "BN254 G1 MSM throughput (2^%d points per GPU, SRS resident)" % LOG_N_MSM
+WORKLOAD = "msm_g1_2^%d_uniform_per_gpu" % LOG_N_MSM
+u64p = ctypes.POINTER(ctypes.c_uint64)
+FR_ONE = np.array([0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f], dtype=np.uint64)  # R mod r
 
 
 def random_field(n, seed):
@@ -117,52 +128,886 @@ class ClockSampler:
                 "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
-def cpu_baseline_msm(log_n: int, repeats: int = 1):
-    """Oracle restatement of best_multiexp on all host threads; returns (pts/s, cores, seconds)."""
+def measured_traffic(key):
+    """DRAM bytes per launch of a kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture), read
+    from the tracked profiles/traffic.json, which names the ncu summary each number comes from.  None when no capture of the
+    configuration is on file — never a typed-in constant."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f).get(key)
+        return (float(e["bytes_per_launch"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def cpu_baseline_msm(log_n: int):
+    """Oracle restatement of best_multiexp on all host threads; returns (pts/s, cores, seconds, native build?)."""
     from oracle import coracle
 
     coracle.build()
+    native = coracle.use_native()   # -O3 -march=native, compiled on this host (BASELINE.md §4)
     n = 1 << log_n
     s = random_field(n, 0x5EED0000 + log_n)
     # bases: cheap synthetic curve points for the CPU arm — multiples of G by small random scalars (CPU fixed-base)
     b = coracle.g1_fixed_base_mul(random_field(min(n, 4096), 7))
     bases = np.ascontiguousarray(np.tile(b, (n // b.shape[0] + 1, 1))[:n])
     cores = coracle.num_threads()
-    best = None
-    for _ in range(repeats):
-        t = time.perf_counter()
-        coracle.best_multiexp(s, bases, 0)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    return n / best, cores, best
+    t = time.perf_counter()
+    coracle.best_multiexp(s, bases, 0)
+    dt = time.perf_counter() - t
+    return n / dt, cores, dt, native
 
 
 def run_reference(args):
+    """The reference arm: same metric, same config (2^24 uniform points per step) on the host cores.  One step is ~8 s, so at
+    most REF_MAX_STEPS timed steps (and one warm-up) are run whatever --steps asks; the line says how many."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ts = []
-    cores = 0
-    for i in range(args.warmup + args.steps):
-        v, cores, dt = cpu_baseline_msm(REF_SAMPLE_LOG_N)
-        if i >= args.warmup:
+    steps = max(1, min(args.steps, REF_MAX_STEPS))
+    warm = 1 if args.warmup else 0
+    ts, cores, native = [], 0, False
+    for i in range(warm + steps):
+        _, cores, dt, native = cpu_baseline_msm(LOG_N_MSM)
+        if i >= warm:
             ts.append(dt)
-    n = 1 << REF_SAMPLE_LOG_N
+    n = 1 << LOG_N_MSM
     value = n * len(ts) / sum(ts)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts),
+        "steps": steps, "warmup": warm, "steps_requested": args.steps, "ms_per_step": 1e3 * sum(ts) / len(ts),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (254-bit Montgomery)",
         "data": "synthetic",
-        "config": {"workload": "msm_g1_2^%d_uniform" % LOG_N_MSM, "sample": "2^%d points per step" % REF_SAMPLE_LOG_N},
+        "config": {"workload": WORKLOAD, "sample": "the full 2^%d-point step, %d timed steps" % (LOG_N_MSM, steps)},
         "cpu_baseline": {"value": value, "unit": "pts/s", "cores": cores, "kind": "port",
-                         "sample": "best_multiexp restatement (C, pthreads; not rayon) on 2^%d uniform points per step"
-                                   % REF_SAMPLE_LOG_N},
+                         "sample": "best_multiexp restatement (C, pthreads; not rayon; %s) on 2^%d uniform points per step, %d steps"
+                                   % ("-O3 -march=native built on this host" if native else "portable -O3 build", LOG_N_MSM, steps)},
         "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+# ---- small helpers shared by the legs ------------------------------------------------------------------------------------------
+class Env:
+    """torch / torch.distributed / libzkb200 plumbing of one rank."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.host_group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.host_group = dist.new_group(backend="gloo")   # host-side barrier / small exchanges that must not touch the GPUs
+        self.zkb = importlib.import_module("zksnap-circuits-halo2_b200")
+        self.zdist = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
+        self.zkb.init(self.local_rank)
+        self.lib = self.zkb.lib()
+        self.stream = torch.cuda.current_stream()
+        self.sptr = ctypes.c_void_p(self.stream.cuda_stream)
+        self.launches = 0
+        self.parity = {}
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.zkb_last_error().decode())
+
+    def timed_events(self, fn, steps):
+        """device time of `steps` calls of fn on the torch stream, max over ranks, per step (ms); counts launches"""
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        l0 = self.zkb.launch_count()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        self.launches += self.zkb.launch_count() - l0
+        return self.max_over_ranks(e0.elapsed_time(e1))[0] / steps
+
+    def timed_wall(self, fn, steps):
+        self.barrier()
+        l0 = self.zkb.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.barrier()
+        dt = time.perf_counter() - t0
+        self.launches += self.zkb.launch_count() - l0
+        return self.max_over_ranks(dt)[0] / steps * 1e3
+
+    def dptr(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def device_field(self, n, seed):
+        """n Fr elements on the device (int64 limbs, top limb < 2^60 so every value is < r): same seed -> same values on any GPU"""
+        g = self.torch.Generator(device=self.dev)
+        g.manual_seed(seed)
+        return self.torch.randint(0, 1 << 60, (n, 4), dtype=self.torch.int64, device=self.dev, generator=g)
+
+    def fold(self, out):
+        """host fold of the per-rank partial sums (96 B each) — the only inter-GPU exchange of a sharded MSM"""
+        if self.world == 1:
+            return out.copy()
+        return self.zkb.g1_sum(self.zdist.all_gather_g1(out, device=self.dev))
+
+
+def known_dlog_point(scal_np, dlog_np):
+    """[sum s_i b_i] G by the oracle (the checker; outside every timed region)"""
+    from oracle import coracle
+
+    coracle.build()
+    return coracle.g1_mul(coracle.g1_generator(), coracle.fr_inner_product(scal_np, dlog_np))
+
+
+def to_np(t):
+    return t.cpu().numpy().view(np.uint64).reshape(-1, 4)
+
+
+# ---- headline: 2^24-point commit per GPU ---------------------------------------------------------------------------------------
+def headline_msm(env: Env, clocks: ClockSampler):
+    zkb, lib, torch = env.zkb, env.lib, env.torch
+    args = env.args
+    n = 1 << LOG_N_MSM
+    seed = 0x5EED0000 + LOG_N_MSM + 1000 * env.rank
+    scal_np = random_field(n, seed)
+    h_scal = torch.from_numpy(scal_np.view(np.int64)).pin_memory()
+    d_scal = h_scal.to(env.dev, non_blocking=False)
+    dlog = random_field(n, seed + 7)
+    bases = zkb.g1_fixed_base_mul(dlog)           # [b_i]G on the GPU, known discrete logs
+    params = zkb.ParamsKZG(LOG_N_MSM, bases)
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(u64p)
+    c_bits, n_win, chunk = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    lib.zkb_msm_get_params(n, ctypes.byref(c_bits), ctypes.byref(n_win), ctypes.byref(chunk))
+    # the commit runs through the SRS window table (steady state of a long-running prover: built once per SRS, forced here), whose
+    # window width comes from its own cost model: report that one
+    t_bits, t_bytes = ctypes.c_uint32(), ctypes.c_uint64()
+    t0 = time.perf_counter()
+    lib.zkb_srs_precompute(params.handle_g, ctypes.byref(t_bits), ctypes.byref(t_bytes))
+    table_build_s = time.perf_counter() - t0
+    if t_bits.value:
+        c_bits.value = t_bits.value
+        n_win.value = (255 + t_bits.value - 1) // t_bits.value
+
+    def step_dev():
+        env.check(lib.zkb_msm_g1_srs_dev(params.handle_g, 0, env.dptr(d_scal), n, outp, env.sptr))
+
+    def step_e2e():
+        env.check(lib.zkb_msm_g1_srs(params.handle_g, ctypes.cast(h_scal.data_ptr(), u64p), n, outp))
+
+    def step_pageable():
+        env.check(lib.zkb_msm_g1_srs(params.handle_g, scal_np.ctypes.data_as(u64p), n, outp))
+
+    for _ in range(args.warmup):
+        step_dev()
+    want = known_dlog_point(scal_np, dlog)
+    parity = bool((out[:8] == want).all())
+    # ---- timed: device-resident
+    zkb.prof.enable(True)
+    zkb.prof.reset()
+    t_win0 = time.time()
+    ms_per_step = env.timed_events(lambda: (step_dev(), env.fold(out)), args.steps)
+    clocks.window(t_win0, time.time())
+    acc_ms, acc_calls = zkb.prof.get("msm_accumulate")
+    sort_ms, _ = zkb.prof.get("msm_sort")
+    dig_ms, _ = zkb.prof.get("msm_digits")
+    red_ms, _ = zkb.prof.get("msm_reduce")
+    zkb.prof.enable(False)
+    ent = ctypes.c_uint64(0)
+    lib.zkb_msm_last_entries(ctypes.byref(ent))
+    value = env.world * n / (ms_per_step * 1e-3)
+    # ---- timed: end to end through the host-buffer ABI, page-locked scalars (the contract's e2e) and pageable ones
+    for _ in range(2):
+        step_e2e()
+    t_win0 = time.time()
+    e2e_ms = env.timed_wall(lambda: (step_e2e(), env.fold(out)), args.steps)
+    clocks.window(t_win0, time.time())
+    parity = parity and bool((out[:8] == want).all())
+    step_pageable()
+    pg_ms = env.timed_wall(lambda: (step_pageable(), env.fold(out)), max(2, args.steps // 2))
+    parity = parity and bool((out[:8] == want).all())
+    # ---- the same commit WITHOUT the window table (what the first ~100 commits against a fresh SRS cost)
+    lib.zkb_srs_set_precompute(0)
+    plain = zkb.ParamsKZG(LOG_N_MSM, bases)
+
+    def step_plain():
+        env.check(lib.zkb_msm_g1_srs_dev(plain.handle_g, 0, env.dptr(d_scal), n, outp, env.sptr))
+
+    step_plain()
+    parity = parity and bool((out[:8] == want).all())
+    no_table_ms = env.timed_events(step_plain, 3)
+    plain.close()
+    lib.zkb_srs_set_precompute(2)
+    del bases
+    # ---- integer-pipe peak (measured here) and the roofline of the dominant kernel
+    peak = ctypes.c_double(0)
+    lib.zkb_measure_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    lib.zkb_measure_imad_peak(ctypes.byref(peak))
+    alg_mac = n * n_win.value * 10 * 128          # SURVEY.md §8d: n*W mixed adds x 10 Fq mul x 128 32-bit MACs
+    acc_launch_ms = acc_ms / max(acc_calls, 1)
+    achieved = alg_mac / (acc_launch_ms * 1e-3) / 1e9 if acc_launch_ms else 0.0
+    traffic, traffic_src = measured_traffic("msm_accumulate_2^%d" % LOG_N_MSM)
+    roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel<level0> (+partial levels, bucket memset)",
+                "achieved": achieved, "peak": peak.value / 1e9, "unit": "GMAC/s (32x32+64 wide MACs)",
+                "frac": achieved / (peak.value / 1e9) if peak.value else None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "measured in this run: unrolled independent mad.wide.u32 chains (zkb_measure_imad_peak)",
+                "hbm_view": ({"achieved": traffic / (acc_launch_ms * 1e-3) / 1e9, "unit": "GB/s",
+                              "note": "measured DRAM traffic of the same launch / its duration: the kernel is not HBM bound"}
+                             if (traffic and acc_launch_ms) else None),
+                "ms_per_launch": acc_launch_ms, "window_bits": c_bits.value, "windows": n_win.value,
+                "bucket_additions": int(ent.value),
+                "share_of_step": acc_launch_ms / ms_per_step if ms_per_step else None,
+                "other_ms": {"digits": dig_ms / max(acc_calls, 1), "sort": sort_ms / max(acc_calls, 1), "reduce": red_ms / max(acc_calls, 1)}}
+    params.close()
+    del d_scal, h_scal
+    torch.cuda.empty_cache()
+    return {"value": value, "ms_per_step": ms_per_step, "parity": parity, "roofline": roofline,
+            "e2e": {"value": env.world * n / (e2e_ms * 1e-3), "unit": "pts/s", "h2d_bytes_per_step": n * 32 * env.world,
+                    "d2h_bytes_per_step": 128 * env.world, "ms_per_step": e2e_ms,
+                    "timer": "wall clock around the C-ABI call (includes host fold), page-locked scalars"},
+            "e2e_pageable": {"value": env.world * n / (pg_ms * 1e-3), "unit": "pts/s", "ms_per_step": pg_ms,
+                             "note": "the same call from pageable memory (a Rust Vec<Fr>): staged through pinned buffers by host threads"},
+            "no_table_ms_per_step": no_table_ms,
+            "config": {"workload": WORKLOAD, "sharding": "srs_point_range_per_rank, host fold",
+                       "l2": "inputs_exceed_l2 (512 MiB scalars + 1 GiB bases per step)", "window_bits": c_bits.value,
+                       "windows": n_win.value, "srs_window_table_bytes": int(t_bytes.value), "srs_window_table_build_s": table_build_s,
+                       "chunk": chunk.value}}
+
+
+# ---- secondary: batched NTT ----------------------------------------------------------------------------------------------------
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ntt_object(env: Env, imad_peak):
+    zkb, lib, torch = env.zkb, env.lib, env.torch
+    args = env.args
+    peak, src = hbm_peak()
+    N, cols = 1 << NTT_LOG_N, NTT_COLS
+    a_np = random_field(N * cols, 0xF0F0 + NTT_LOG_N + env.rank)
+    h_a = torch.from_numpy(a_np.view(np.int64)).pin_memory()
+    d_a = h_a.to(env.dev)
+    d_s = torch.empty_like(d_a)
+    w = zkb.omega(NTT_LOG_N)
+    wp = w.ctypes.data_as(u64p)
+
+    def ntt_step():
+        env.check(lib.zkb_ntt_fr_dev(env.dptr(d_a), env.dptr(d_s), cols, wp, NTT_LOG_N, env.sptr))
+
+    # parity of the measured configuration: column 0 against the definition on a 2-sparse probe, and forward/inverse round trip
+    probe = torch.zeros_like(d_a)
+    j1, j2 = 12345 % N, N - 7
+    pr = np.zeros((N, 4), dtype=np.uint64)
+    pr[j1], pr[j2] = a_np[1], a_np[2]
+    probe.view(-1, 4)[:N] = torch.from_numpy(pr.view(np.int64)).to(env.dev)
+    env.check(lib.zkb_ntt_fr_dev(env.dptr(probe), env.dptr(d_s), cols, wp, NTT_LOG_N, env.sptr))
+    torch.cuda.synchronize()
+    ok = two_sparse_ok(to_np(probe.view(-1, 4)[:N]), a_np[1], a_np[2], j1, j2, NTT_LOG_N, [0, 1, 2, N // 2 + 3, N - 1, N // 3])
+    del probe, pr
+    for _ in range(args.warmup):
+        ntt_step()
+    nms = env.timed_events(ntt_step, args.steps)
+    alg_bytes = 64.0 * N * cols
+    gbs = alg_bytes / (nms * 1e-3) / 1e9
+    ptrs = (u64p * cols)(*[ctypes.cast(h_a.data_ptr() + i * N * 32, u64p) for i in range(cols)])
+    lib.zkb_ntt_fr_batch(ptrs, cols, wp, NTT_LOG_N)
+    e2e_ms = env.timed_wall(lambda: lib.zkb_ntt_fr_batch(ptrs, cols, wp, NTT_LOG_N), max(1, args.steps // 2))
+    traffic, tsrc = measured_traffic("ntt_2^%dx%d" % (NTT_LOG_N, NTT_COLS))
+    # integer view: Montgomery products per element of this plan (DESIGN.md §3) = radix-8 butterfly rounds (1.375 products per
+    # element per full round of 3 bits, fewer for the shorter last round of a pass) + one inter-pass twiddle per later pass
+    prods = ntt_products_per_element(NTT_LOG_N)
+    mac = prods * 128 * N * cols / (nms * 1e-3)
+    obj = {"workload": "best_fft 2^%d x %d columns (batched, in HBM)" % (NTT_LOG_N, cols),
+           "value": env.world * N * cols / (nms * 1e-3), "unit": "elems/s", "ms_per_step": nms, "parity_checked": ok,
+           "e2e": {"value": env.world * N * cols / (e2e_ms * 1e-3), "unit": "elems/s", "h2d_bytes_per_step": N * cols * 32,
+                   "d2h_bytes_per_step": N * cols * 32},
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "traffic": traffic, "traffic_source": tsrc, "peak_source": src,
+                        "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound (imad view), see DESIGN.md"},
+           "roofline_imad": {"bound": "imad", "achieved": mac / 1e9, "peak": imad_peak / 1e9, "unit": "GMAC/s",
+                             "frac": mac / imad_peak if imad_peak else None,
+                             "note": "%.2f Montgomery products (128 MACs each) per element: butterflies + inter-pass twiddles" % prods}}
+    del d_a, d_s, h_a
+    torch.cuda.empty_cache()
+    return obj
+
+
+def ntt_products_per_element(log_n):
+    """Montgomery products per element of the multi-pass plan ntt_plan.hpp picks for 2^log_n: per pass of radix 2^lr, DIF rounds of
+    3,3,..,rem bits; a radix-8 round costs 5 internal + 7 output twiddle products per 8 elements (the last round of a pass has no
+    output twiddles), radix-4: 1 + 3 per 4, radix-2: 0 + 1 per 2; plus one inter-pass twiddle per element for every pass after the
+    first.  2^22 (passes 8, 7, 7): 11.25."""
+    if log_n <= 10:
+        lrs = [log_n]
+    else:
+        npass = (log_n + 8) // 9
+        base, rem = divmod(log_n, npass)
+        lrs = [base + (1 if p < rem else 0) for p in range(npass)]
+    total = 0.0
+    for p, lr in enumerate(lrs):
+        left = lr
+        while left > 0:
+            t = 3 if left >= 3 else left
+            left -= t
+            internal = {3: 5 / 8, 2: 1 / 4, 1: 0.0}[t]
+            outtw = {3: 7 / 8, 2: 3 / 4, 1: 1 / 2}[t] if left > 0 else 0.0
+            total += internal + outtw
+        if p > 0:
+            total += 1.0
+    return total
+
+
+def two_sparse_ok(out_rows, v1, v2, j1, j2, log_n, idx, base=0):
+    """out_rows[i - base] must equal v1 w^(i j1) + v2 w^(i j2) for i in idx: the NTT of a 2-sparse input by its definition —
+    exact for any size, sensitive to any permutation or twiddle error (Python integers)."""
+    from oracle import pyref as R
+    from util import limbs_to_int
+
+    w = R.omega_for(log_n)
+    a1, a2 = R.from_mont(limbs_to_int(v1), R.FR), R.from_mont(limbs_to_int(v2), R.FR)
+    for i in idx:
+        want = (a1 * pow(w, i * j1, R.FR) + a2 * pow(w, i * j2, R.FR)) % R.FR
+        if R.from_mont(limbs_to_int(out_rows[i - base]), R.FR) != want:
+            return False
+    return True
+
+
+# ---- secondary: quotient evaluation on resident cosets (GraphEvaluator row loop, SURVEY.md §8f row 1) -----------------------------
+def quotient_object(env: Env):
+    zkb, torch = env.zkb, env.torch
+    args = env.args
+    peak, _ = hbm_peak()
+    ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
+    rows, qc, rs = 1 << QUOT_LOG_N, QUOT_COLS, 4
+    gr = ev.GraphEvaluator()
+    parts = []
+    for i in range(qc):   # halo2-base: q_i * (a + b * c - d), a..d = advice column i at rotations 0..3
+        a_, b_, c_, d_ = (("advice", i, r) for r in range(4))
+        parts.append(gr.add_expression(("prod", ("fixed", i, 0), ("sum", ("sum", a_, ("prod", b_, c_)), ("neg", d_)))))
+    gr.add_horner(ev.ValueSource(ev.PREVIOUS), parts, ev.ValueSource(ev.Y))
+    adv_np, sel_np = random_field(rows, 0x9A7E + env.rank), random_field(rows, 0x5E1 + env.rank)
+    y_np = random_field(1, 0x77)[0]
+    adv = [zkb.Polynomial(adv_np) for _ in range(qc)]   # same values, distinct HBM buffers: the traffic is real
+    sel = [zkb.Polynomial(sel_np) for _ in range(qc)]
+    vals = zkb.Polynomial(np.zeros((rows, 4), dtype=np.uint64))
+    gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
+    # parity of the measured configuration on sampled rows, Python integers (previous value 0):
+    # value = gate * (y^(qc-1) + ... + 1), gate = q (a + b c - d)
+    FRM = ev.FR
+    Rinv = pow(1 << 256, FRM - 2, FRM)
+    li = lambda v: sum(int(v[j]) << (64 * j) for j in range(4)) * Rinv % FRM  # noqa: E731
+    got = vals.to_host()
+    yv = li(y_np)
+    ysum = sum(pow(yv, j, FRM) for j in range(qc)) % FRM
+    q_ok = True
+    for r in [0, 1, rows - 1, rows - 5, rows // 3, rows // 2 + 7]:
+        av = [li(adv_np[(r + j * rs) % rows]) for j in range(4)]
+        q_ok &= li(got[r]) == li(sel_np[r]) * (av[0] + av[1] * av[2] - av[3]) % FRM * ysum % FRM
+    del got
+    for _ in range(args.warmup):
+        gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
+    env.barrier()
+    l0 = zkb.launch_count()
+    zkb.prof.enable(True)
+    zkb.prof.reset()
+    for _ in range(args.steps):
+        gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
+    env.barrier()
+    qms, qk = zkb.prof.get("graph_evaluate")   # CUDA events around the kernel on the library stream
+    qms /= max(qk, 1)
+    zkb.prof.enable(False)
+    env.launches += zkb.launch_count() - l0
+    info = gr.last_info()
+    qgbs = info["bytes_per_row"] * rows / (qms * 1e-3) / 1e9
+    traffic, tsrc = measured_traffic("graph_evaluate_2^%dx%d" % (QUOT_LOG_N, QUOT_COLS))
+    obj = {"workload": "evaluate_h custom gates: halo2-base gate q(a+bc-d) on %d advice columns, 2^%d extended rows, rot_scale %d, resident in HBM" % (qc, QUOT_LOG_N, rs),
+           "value": env.world * rows / (qms * 1e-3), "unit": "rows/s", "ms_per_step": qms, "parity_checked": bool(q_ok),
+           "lowered": info, "modmul_per_row": 3 * qc,
+           "roofline": {"bound": "hbm", "achieved": qgbs, "peak": peak, "unit": "GB/s", "frac": qgbs / peak,
+                        "traffic": traffic, "traffic_source": tsrc,
+                        "note": "32 B x (polynomials read + previous value + result) per row; integer-issue bound, see DESIGN.md"}}
+    for p_ in adv + sel + [vals]:
+        p_.free()
+    return obj, gr, y_np
+
+
+# ---- N > 1: one 2^26 NTT sharded over the ranks (exchange fused into the NTT passes over NVLink peer memory) --------------------
+def sharded_ntt_object(env: Env):
+    zkb, lib, torch, zdist = env.zkb, env.lib, env.torch, env.zdist
+    args = env.args
+    peak, _ = hbm_peak()
+    k = SHARDED_LOG_N
+    rank, world = env.rank, env.world
+    sh = zdist.ShardedNtt(k, device=env.dev)
+    off, ln = zdist.ntt_slice(k, rank, world)
+    w = zkb.omega(k)
+    wp = w.ctypes.data_as(u64p)
+    N = 1 << k
+    # (1) the measured size, by the definition: a 2-sparse input (one non-zero in the first rank's slice, one in the last rank's)
+    #     must give out[i] = v1 w^(i j1) + v2 w^(i j2) at sampled positions of EVERY rank's output slice
+    v = random_field(3, 0xD157)
+    j1, j2 = 0x2345677 % ln, N - 11
+    d_in = torch.zeros(ln * 4, dtype=torch.int64, device=env.dev)
+    if off <= j1 < off + ln:
+        d_in.view(-1, 4)[j1 - off] = torch.from_numpy(v[1].view(np.int64)).to(env.dev)
+    if off <= j2 < off + ln:
+        d_in.view(-1, 4)[j2 - off] = torch.from_numpy(v[2].view(np.int64)).to(env.dev)
+    d_out = torch.empty_like(d_in)
+    rc = lib.zkb_dist_ntt_fr_dev(env.dptr(d_in), env.dptr(d_out), wp, k, env.sptr)
+    if rc != 0 or lib.zkb_dist_status(env.sptr) != 0:
+        raise RuntimeError(lib.zkb_last_error().decode())
+    rng = np.random.default_rng(77 + rank)
+    idx = [off, off + 1, off + ln - 1, off + ln // 2 + 3] + [off + int(x) for x in rng.integers(0, ln, 12)]
+    got = d_out.view(-1, 4)
+    rows = {i: got[i - off].cpu().numpy().view(np.uint64) for i in idx}
+    sparse_ok = all(two_sparse_ok([rows[i]], v[1], v[2], j1, j2, k, [i], base=i) for i in idx)
+    # (2) a random vector at 2^22: this rank's output slice against the single-GPU zkb_ntt_fr_dev of the whole vector, all elements
+    k2 = min(22, k)
+    N2 = 1 << k2
+    full = env.device_field(N2, 0xD1570)        # same vector on every rank
+    off2, ln2 = zdist.ntt_slice(k2, rank, world)
+    w2 = zkb.omega(k2)
+    w2p = w2.ctypes.data_as(u64p)
+    d_in2 = full[off2:off2 + ln2].contiguous()
+    d_out2 = torch.empty_like(d_in2)
+    rc = lib.zkb_dist_ntt_fr_dev(env.dptr(d_in2), env.dptr(d_out2), w2p, k2, env.sptr)
+    if rc != 0 or lib.zkb_dist_status(env.sptr) != 0:
+        raise RuntimeError(lib.zkb_last_error().decode())
+    scr = torch.empty_like(full)
+    env.check(lib.zkb_ntt_fr_dev(env.dptr(full), env.dptr(scr), 1, w2p, k2, env.sptr))
+    torch.cuda.synchronize()
+    slice_ok = bool(torch.equal(d_out2, full[off2:off2 + ln2]))
+    del full, scr, d_in2, d_out2
+    # timing at the measured size
+    d_in = env.device_field(ln, 0xD157 + rank).view(-1)
+    lib.zkb_dist_ntt_fr_dev(env.dptr(d_in), None, wp, k, env.sptr)  # loads the symmetric input slice
+    for _ in range(args.warmup):
+        lib.zkb_dist_ntt_fr_dev(None, None, wp, k, env.sptr)
+    sms = env.timed_events(lambda: lib.zkb_dist_ntt_fr_dev(None, None, wp, k, env.sptr), args.steps)
+    if lib.zkb_dist_status(env.sptr) != 0:
+        raise RuntimeError(lib.zkb_last_error().decode())
+    ok = env.max_over_ranks(0.0 if (sparse_ok and slice_ok) else 1.0)[0] == 0.0
+    obj = {"workload": "one best_fft of 2^%d sharded over %d GPUs (contiguous slices in, contiguous slices out)" % (k, world),
+           "value": N / (sms * 1e-3), "unit": "elems/s", "ms_per_step": sms, "parity_checked": ok,
+           "parity": "2-sparse input against the definition at 16 positions of every rank's output slice (2^%d); random vector at 2^%d: "
+                     "every rank's whole output slice equals the single-GPU transform" % (k, k2),
+           "exchange": "fused into NTT pass 0 (peer loads+stores) and the final pass (peer stores) over NVLink; device-side barriers",
+           "nvlink_bytes_per_gpu_per_step": int(3 * (world - 1) / world * ln * 32),
+           "roofline": {"bound": "hbm", "achieved": 64.0 * N / (sms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                        "frac": 64.0 * N / (sms * 1e-3) / 1e9 / (peak * world)}}
+    sh.close()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return obj
+
+
+def sharded_quotient_object(env: Env, gr, y_np):
+    torch, zdist = env.torch, env.zdist
+    args = env.args
+    try:
+        srows = (1 << QUOT_LOG_N) // env.world
+        sq = zdist.ShardedQuotient(gr, 4)
+        base = env.device_field(srows, 0x51AB)   # the same rows on every rank: the domain is periodic with period srows, so the
+        bufs = []                                # sharded result must equal a wrapping evaluation of one period
+        for _ in range(2 * QUOT_COLS):
+            buf, view = sq.alloc_column(srows, env.dev)
+            view.copy_(base)
+            bufs.append(buf)
+        sel_b, adv_b = bufs[:QUOT_COLS], bufs[QUOT_COLS:]
+        vals_s = torch.zeros_like(base)
+        sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
+        ref_s = torch.zeros_like(base)
+        plain = [base.clone() for _ in range(2)]
+        gr.evaluate_dev(ref_s.data_ptr(), srows, [plain[0].data_ptr()] * QUOT_COLS, [plain[1].data_ptr()] * QUOT_COLS, y=y_np, rot_scale=4,
+                        stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        sq_ok = bool(torch.equal(vals_s, ref_s))
+        for _ in range(args.warmup):
+            sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
+        qsms = env.timed_events(lambda: sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np), args.steps)
+        sq_ok = env.max_over_ranks(0.0 if sq_ok else 1.0)[0] == 0.0
+        obj = {"workload": "the quotient workload above, 2^%d rows sharded by rows over %d GPUs" % (QUOT_LOG_N, env.world),
+               "value": (1 << QUOT_LOG_N) / (qsms * 1e-3), "unit": "rows/s", "ms_per_step": qsms, "parity_checked": sq_ok,
+               "exchange": "ring halo exchange, %d + %d rows per column over NCCL point-to-point, then zkb_graph_evaluate_dev on the row window" % (sq.halo_lo, sq.halo_hi),
+               "halo_bytes_per_rank": (sq.halo_lo + sq.halo_hi) * 32 * 2 * QUOT_COLS}
+        del bufs, vals_s, ref_s, plain, base
+        torch.cuda.empty_cache()
+        return obj
+    except Exception as exc:  # a secondary object must not take the headline line down
+        return {"error": repr(exc)[:300], "parity_checked": False}
+
+
+# ---- one MSM of 2^26 points split over the N GPUs (strong scaling) ------------------------------------------------------------------
+SPLIT_SEED = 0x26A0
+
+
+def split_shard(env: Env, shard, parts, dev=None):
+    """shard `shard` of `parts` of the 2^SPLIT_LOG_N-point workload: (scalars, discrete logs) on the device, seeded per shard so
+    that any process / device regenerates the same values"""
+    n = (1 << SPLIT_LOG_N) // parts
+    torch = env.torch
+    d = dev if dev is not None else env.dev
+    g = torch.Generator(device=d)
+    g.manual_seed(SPLIT_SEED + 2 * shard + 64 * parts)
+    s = torch.randint(0, 1 << 60, (n, 4), dtype=torch.int64, device=d, generator=g)
+    g.manual_seed(SPLIT_SEED + 2 * shard + 1 + 64 * parts)
+    b = torch.randint(0, 1 << 60, (n, 4), dtype=torch.int64, device=d, generator=g)
+    return s, b
+
+
+def msm_split_object(env: Env):
+    """rank r commits shard r (2^26 / N points) against its SRS range; all_gather + host fold.  Returns the object and the folded
+    point (compared bit for bit with the single-process run of the same workload)."""
+    zkb, lib, torch = env.zkb, env.lib, env.torch
+    args = env.args
+    n = (1 << SPLIT_LOG_N) // env.world
+    d_s, d_b = split_shard(env, env.rank, env.world)
+    s_np, b_np = to_np(d_s), to_np(d_b)
+    bases = zkb.g1_fixed_base_mul(b_np)
+    h = ctypes.c_uint64(0)
+    env.check(lib.zkb_srs_register(bases.ctypes.data_as(u64p), n, ctypes.byref(h)))
+    del bases
+    lib.zkb_srs_precompute(h, None, None)
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(u64p)
+
+    def step():
+        env.check(lib.zkb_msm_g1_srs_dev(h, 0, env.dptr(d_s), n, outp, env.sptr))
+        return env.fold(out)
+
+    total = step()
+    # parity: [sum over all shards of <s, b>] G; every rank contributes its inner product through the host group
+    from oracle import coracle
+
+    coracle.build()
+    ip = coracle.fr_inner_product(s_np, b_np)
+    if env.world > 1:
+        t = torch.from_numpy(ip.view(np.int64).copy())
+        parts = [torch.empty_like(t) for _ in range(env.world)]
+        env.dist.all_gather(parts, t, group=env.host_group)
+        ips = np.stack([p.numpy().view(np.uint64) for p in parts])
+        ip = ips[0]
+        for x in ips[1:]:
+            ip = coracle.vec_op("fr", "add", ip.reshape(1, 4), x.reshape(1, 4))[0]
+    want = coracle.g1_mul(coracle.g1_generator(), ip)
+    ok = bool((total[:8] == want).all())
+    step()
+    ms = env.timed_events(step, max(2, min(args.steps, 5)))
+    lib.zkb_srs_release(h)
+    del d_s, d_b
+    torch.cuda.empty_cache()
+    obj = {"workload": "one MSM of 2^%d uniform points split over %d GPU(s) by SRS point range, scalars resident in HBM, host fold per commit"
+                       % (SPLIT_LOG_N, env.world),
+           "scaling": "strong", "value": (1 << SPLIT_LOG_N) / (ms * 1e-3), "unit": "pts/s", "ms_per_step": ms, "parity_checked": ok}
+    return obj, total
+
+
+# ---- prover op-sequence replays (BASELINE configs #1-#3: "proof-gen sec") ------------------------------------------------------------
+def wrapper_replay_object(env: Env):
+    """Wrapper circuit, k = 22 (create_proof at /root/reference/aggregator/src/wrapper.rs:129-137 as driven by gen_recursion_snark,
+    wrapper.rs:869-902): 22 commitments of 2^22 scalars, 13 lagrange_to_coeff, 16 coeff_to_extended (2^22 -> 2^24),
+    one 2^24 inverse transform for h(X) — in prover order, every commitment folded on the host BEFORE the next op (the transcript
+    needs it).  Multi-process sharding: every MSM by SRS point range, independent columns round-robin, the 2^24 transform through
+    the sharded NTT.  STRONG scaling: the work is fixed, N GPUs share it."""
+    zkb, lib, torch, zd = env.zkb, env.lib, env.torch, env.zdist
+    rank, world = env.rank, env.world
+    k, ek = WRAPPER_K, WRAPPER_K + 2
+    n, N = 1 << k, 1 << ek
+    n_msm, n_intt, n_c2e = 22, 13, 16
+    off, ln = zd.point_range(n, rank, world)
+    dlog = random_field(n, 0xB45E)                      # same on every rank
+    bases = zkb.g1_fixed_base_mul(dlog[off:off + ln])   # this rank's SRS range
+    h = ctypes.c_uint64(0)
+    env.check(lib.zkb_srs_register(bases.ctypes.data_as(u64p), ln, ctypes.byref(h)))
+    lib.zkb_srs_precompute(h, None, None)
+    cols = random_field(4 * n, 0x22).reshape(4, n, 4)   # four distinct columns reused round-robin
+    d_slices = [torch.from_numpy(np.ascontiguousarray(cols[c, off:off + ln]).view(np.int64)).to(env.dev) for c in range(4)]
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(u64p)
+    mine_intt = zd.columns_for_rank(n_intt, rank, world)
+    mine_c2e = zd.columns_for_rank(n_c2e, rank, world)
+    d_col = torch.from_numpy(np.ascontiguousarray(cols[0]).view(np.int64)).reshape(-1).to(env.dev)
+    d_work = torch.empty(n * 4, dtype=torch.int64, device=env.dev)
+    d_ext = torch.empty(N * 4, dtype=torch.int64, device=env.dev)
+    d_scr = torch.empty(N * 4, dtype=torch.int64, device=env.dev)
+    sharded = world > 1 and (world & (world - 1)) == 0 and world <= 8
+    sh = zd.ShardedNtt(ek, device=env.dev) if sharded else None
+    w_inv = zkb.EvaluationDomain(4, k).get_extended_omega()   # any 2^24-th root times the transform the same
+    wp = w_inv.ctypes.data_as(u64p)
+    if sh is not None:
+        d_in = env.device_field(N // world, 7 + rank).view(-1)
+        env.check(lib.zkb_dist_ntt_fr_dev(env.dptr(d_in), None, wp, ek, env.sptr))
+        del d_in
+
+    def replay():
+        first = None
+        for i in range(n_msm):
+            env.check(lib.zkb_msm_g1_srs_dev(h, 0, env.dptr(d_slices[i % 4]), ln, outp, env.sptr))
+            c = env.fold(out)
+            if first is None:
+                first = c
+        for _ in mine_intt:
+            d_work.copy_(d_col)
+            env.check(lib.zkb_lagrange_to_coeff_dev(env.dptr(d_work), env.dptr(d_scr), 1, k, env.sptr))
+        for _ in mine_c2e:
+            env.check(lib.zkb_coeff_to_extended_dev(env.dptr(d_col), env.dptr(d_ext), env.dptr(d_scr), 1, k, ek, env.sptr))
+        if sh is not None:
+            env.check(lib.zkb_dist_ntt_fr_dev(None, None, wp, ek, env.sptr))
+            env.check(lib.zkb_dist_status(env.sptr))
+        else:
+            env.check(lib.zkb_extended_to_coeff_dev(env.dptr(d_ext), env.dptr(d_scr), 1, k, ek, env.sptr))
+        return first
+
+    first = replay()
+    ok = bool((first[:8] == known_dlog_point(np.ascontiguousarray(cols[0]), dlog)).all())
+    # one coset of the replay against Horner at sampled points of the extended domain (rank 0's last coeff_to_extended output)
+    if mine_c2e:
+        from oracle import coracle
+        from oracle import pyref as R
+        from util import ints_to_limbs
+
+        env.check(lib.zkb_coeff_to_extended_dev(env.dptr(d_col), env.dptr(d_ext), env.dptr(d_scr), 1, k, ek, env.sptr))
+        torch.cuda.synchronize()
+        wext = R.omega_for(ek)
+        for i in (0, 5, N // 2 + 1, N - 1):
+            x = R.FR_ZETA * pow(wext, i, R.FR) % R.FR
+            wantv = coracle.fr_eval_polynomial(np.ascontiguousarray(cols[0]), ints_to_limbs([R.to_mont(x, R.FR)])[0])
+            ok = ok and bool((d_ext.view(-1, 4)[i].cpu().numpy().view(np.uint64) == wantv).all())
+    ok = env.max_over_ranks(0.0 if ok else 1.0)[0] == 0.0
+    best = min(env.timed_events(replay, 1) for _ in range(3))
+    lib.zkb_srs_release(h)
+    if sh is not None:
+        sh.close()
+    del d_slices, d_col, d_work, d_ext, d_scr
+    torch.cuda.empty_cache()
+    return {"workload": "wrapper circuit k = %d prover op sequence: %d MSM 2^%d + %d iNTT 2^%d + %d coset NTT 2^%d->2^%d + 1 iNTT 2^%d, prover order, "
+                        "host fold after every commitment" % (k, n_msm, k, n_intt, k, n_c2e, k, ek, ek),
+            "mode": "kernel (operands resident in HBM)", "scaling": "strong", "n_gpus": world,
+            "proof_gen_hot_path_ms": best, "value": 1e3 / best, "unit": "proofs/s (hot path only)", "parity_checked": ok,
+            "parity": "first commitment == [<s, b>]G (oracle); one coset == Horner at 4 points of the extended domain",
+            "sharding": "MSM by SRS point range + all_gather/fold per commitment; columns round-robin; the 2^%d transform through the sharded NTT" % ek}
+
+
+def dropin_replays(env: Env, pinned: bool):
+    """The same op sequences through the host-buffer C ABI (what the patched halo2 calls): PCIe and staging included.  With
+    several devices bound in this process the library shards every call itself.  Returns {wrapper, voter, st} objects."""
+    zkb, lib, torch = env.zkb, env.lib, env.torch
+
+    def host(a):
+        if not pinned:
+            return a, a.ctypes.data
+        t = torch.from_numpy(a.view(np.int64)).pin_memory()
+        return t, t.data_ptr()
+
+    res = {}
+    mem = "page-locked" if pinned else "pageable"
+    # ---- wrapper k = 22
+    k, ek = WRAPPER_K, WRAPPER_K + 2
+    n, N = 1 << k, 1 << ek
+    n_msm, n_intt, n_c2e = 22, 13, 16
+    dlog = random_field(n, 0xB45E)
+    bases = zkb.g1_fixed_base_mul(dlog)
+    params = zkb.ParamsKZG(k, bases)
+    lib.zkb_srs_precompute(params.handle_g, None, None)
+    cols_np = random_field(4 * n, 0x22)
+    hold, base = host(cols_np)
+    work = [host(np.empty((n, 4), dtype=np.uint64)) for _ in range(4)]      # the prover's own column Vecs (mutated in place)
+    exts = [host(np.empty((N, 4), dtype=np.uint64)) for _ in range(4)]
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(u64p)
+    in4 = (u64p * 4)(*[ctypes.cast(base + c * n * 32, u64p) for c in range(4)])
+    work4 = (u64p * 4)(*[ctypes.cast(w[1], u64p) for w in work])
+    ext4 = (u64p * 4)(*[ctypes.cast(e[1], u64p) for e in exts])
+
+    def refill():
+        for c in range(4):
+            ctypes.memmove(work[c][1], base + c * n * 32, n * 32)
+
+    def wrapper():
+        first = None
+        for i in range(n_msm):
+            env.check(lib.zkb_msm_g1_srs(params.handle_g, ctypes.cast(base + (i % 4) * n * 32, u64p), n, outp))
+            if first is None:
+                first = out.copy()
+        for i in range(0, n_intt, 4):
+            env.check(lib.zkb_lagrange_to_coeff_batch(work4, min(4, n_intt - i), k))
+        for i in range(0, n_c2e, 4):
+            env.check(lib.zkb_coeff_to_extended_batch(in4, ext4, 4, k, ek))
+        env.check(lib.zkb_extended_to_coeff(ctypes.cast(exts[0][1], u64p), k, ek))
+        return first
+
+    refill()
+    first = wrapper()
+    ok = bool((first[:8] == known_dlog_point(cols_np[:n], dlog)).all())
+    best = 1e30
+    for _ in range(2):
+        refill()
+        t0 = time.perf_counter()
+        wrapper()
+        best = min(best, time.perf_counter() - t0)
+    res["wrapper"] = {"workload": "wrapper k = %d op sequence through the host-buffer C ABI (%s operands)" % (k, mem),
+                      "proof_gen_hot_path_ms": best * 1e3, "parity_checked": ok,
+                      "h2d_bytes": n_msm * n * 32 + n_intt * n * 32 + n_c2e * n * 32 + N * 32,
+                      "d2h_bytes": n_intt * n * 32 + n_c2e * N * 32 + N * 32}
+    params.close()
+    del hold, work, exts, bases
+    # ---- voter (k = 13, 256 advice columns) and state_transition (k = 15, 8 columns): batched column calls
+    for name, kk, ncols in (("voter", 13, 256), ("st", 15, 8)):
+        nn, NN = 1 << kk, 1 << (kk + 2)
+        dl = random_field(nn, 0x700 + kk)
+        g = zkb.g1_fixed_base_mul(dl)
+        p = zkb.ParamsKZG(kk, g, g)
+        lib.zkb_srs_precompute(p.handle_g, None, None)
+        lib.zkb_srs_precompute(p.handle_g_lagrange, None, None)
+        c_np = random_field(nn * ncols, 77 + kk)
+        hc, cb = host(c_np)
+        he, eb = host(np.empty((NN * ncols, 4), dtype=np.uint64))
+        ptrs = (u64p * ncols)(*[ctypes.cast(cb + i * nn * 32, u64p) for i in range(ncols)])
+        eptrs = (u64p * ncols)(*[ctypes.cast(eb + i * NN * 32, u64p) for i in range(ncols)])
+        outs = np.zeros((ncols, 12), dtype=np.uint64)
+        saved = c_np.copy()
+
+        def shape():
+            env.check(lib.zkb_msm_g1_srs_batch(p.handle_g_lagrange, ptrs, ncols, nn, outs.ctypes.data_as(u64p)))   # advice commits
+            env.check(lib.zkb_lagrange_to_coeff_batch(ptrs, ncols, kk))
+            env.check(lib.zkb_coeff_to_extended_batch(ptrs, eptrs, ncols, kk, kk + 2))
+            env.check(lib.zkb_extended_to_coeff(ctypes.cast(eb, u64p), kk, kk + 2))                                  # h(X)
+            for i in range(8):                                                                                        # h pieces + openings
+                env.check(lib.zkb_msm_g1_srs(p.handle_g, ctypes.cast(cb + (i % ncols) * nn * 32, u64p), nn, outp))
+
+        def reset():
+            ctypes.memmove(cb, saved.ctypes.data, saved.nbytes)
+
+        reset()
+        shape()
+        from oracle import coracle
+
+        coracle.build()
+        okc = bool((outs[0] == coracle.best_multiexp(saved[:nn], g)).all()) and bool((outs[ncols - 1] == coracle.best_multiexp(saved[(ncols - 1) * nn:], g)).all())
+        bestc = 1e30
+        for _ in range(3):
+            reset()
+            t0 = time.perf_counter()
+            shape()
+            bestc = min(bestc, time.perf_counter() - t0)
+        res[name] = {"workload": "%s circuit shape: k = %d, %d columns: commit_lagrange batch + lagrange_to_coeff batch + coeff_to_extended batch + "
+                                 "extended_to_coeff + 8 commits, host-buffer C ABI (%s operands)" % (name, kk, ncols, mem),
+                     "proof_gen_hot_path_ms": bestc * 1e3, "parity_checked": okc}
+        p.close()
+        del hc, he
+    return res
+
+
+# ---- N > 1: rank 0 alone drives all N devices through the unchanged C ABI --------------------------------------------------------------
+def single_process_object(env: Env, mp_split, mp_split_point):
+    """zkb_init(all N devices) in ONE process — the deployment of the reference's prover (create_proof is one process,
+    /root/reference/aggregator/src/wrapper.rs:129-137).  Must reproduce the torchrun results: the 2^26 MSM split N ways bit for
+    bit and within a few percent of the multi-process time; drop-in replays are reported beside the N = 1 ones."""
+    zkb, lib, torch = env.zkb, env.lib, env.torch
+    world = env.world
+    obj = {"devices": world}
+    zkb.shutdown()
+    zkb.init(list(range(world)))
+    try:
+        # ---- the 2^26 MSM of msm_split, sharded by the library: same per-shard seeds, so the same points and scalars
+        n = 1 << SPLIT_LOG_N
+        per = n // world
+        h_s = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+        b_np = np.empty((n, 4), dtype=np.uint64)
+        for r in range(world):
+            s, b = split_shard(env, r, world, dev=torch.device("cuda", 0))
+            h_s[r * per:(r + 1) * per].copy_(s)
+            b_np[r * per:(r + 1) * per] = to_np(b)
+            del s, b
+        torch.cuda.synchronize()
+        bases = zkb.g1_fixed_base_mul(b_np)
+        h = ctypes.c_uint64(0)
+        env.check(lib.zkb_srs_register(bases.ctypes.data_as(u64p), n, ctypes.byref(h)))   # replicated to every device
+        del bases, b_np
+        lib.zkb_srs_precompute(h, None, None)
+        out = np.zeros(12, dtype=np.uint64)
+        outp = out.ctypes.data_as(u64p)
+        sp = ctypes.cast(h_s.data_ptr(), u64p)
+        env.check(lib.zkb_msm_g1_srs(h, sp, n, outp))
+        identical = bool((out == mp_split_point).all())
+        # device-resident, one host thread per device (what a torchrun rank does, without processes or NCCL): shard r on device r
+        d_sh = [h_s[r * per:(r + 1) * per].to(torch.device("cuda", r)) for r in range(world)]
+        outs = [np.zeros(12, dtype=np.uint64) for _ in range(world)]
+        streams = [torch.cuda.Stream(device=r) for r in range(world)]
+        pool = ThreadPoolExecutor(world)
+
+        def one(r):
+            rc = lib.zkb_msm_g1_srs_dev(h, r * per, ctypes.c_void_p(d_sh[r].data_ptr()), per, outs[r].ctypes.data_as(u64p),
+                                        ctypes.c_void_p(streams[r].cuda_stream))
+            if rc != 0:
+                raise RuntimeError(lib.zkb_last_error().decode())
+
+        def resident():
+            list(pool.map(one, range(world)))
+            return zkb.g1_sum(np.stack(outs))
+
+        tot = resident()
+        identical = identical and bool((tot == mp_split_point).all())
+        resident()
+        for r in range(world):
+            torch.cuda.synchronize(r)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            resident()
+        res_ms = (time.perf_counter() - t0) / reps * 1e3
+        env.check(lib.zkb_msm_g1_srs(h, sp, n, outp))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            env.check(lib.zkb_msm_g1_srs(h, sp, n, outp))
+        e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+        pool.shutdown()
+        obj["msm_split"] = {"workload": "the msm_split workload (one 2^%d MSM over %d devices) driven by ONE process" % (SPLIT_LOG_N, world),
+                            "resident_ms_per_step": res_ms, "multiprocess_ms_per_step": mp_split["ms_per_step"],
+                            "resident_vs_multiprocess": res_ms / mp_split["ms_per_step"],
+                            "timer": "wall clock (the call returns the folded result), one host thread per device",
+                            "e2e_ms_per_step": e2e_ms, "e2e_value": n / (e2e_ms * 1e-3), "unit": "pts/s",
+                            "e2e_note": "zkb_msm_g1_srs from page-locked host scalars: every device uploads its own share over its own PCIe link",
+                            "bit_identical_to_multiprocess": identical}
+        lib.zkb_srs_release(h)
+        del d_sh, h_s
+        torch.cuda.empty_cache()
+        # ---- drop-in replays with all devices behind the same calls
+        rep = dropin_replays(env, pinned=False)
+        obj["wrapper_replay_dropin_pageable"] = rep["wrapper"]
+        obj["voter_replay_dropin_pageable"] = rep["voter"]
+        obj["st_replay_dropin_pageable"] = rep["st"]
+        obj["parity_checked"] = identical and all(v["parity_checked"] for v in rep.values())
+        obj["launches"] = int(zkb.launch_count())
+    finally:
+        zkb.shutdown()
+    return obj
 
 
 def main():
@@ -171,8 +1016,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zkb200")
-    ap.add_argument("--skip-ntt", action="store_true")
+    ap.add_argument("--skip-ntt", action="store_true", help="headline MSM only (skips every secondary object)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-replay", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -183,386 +1029,117 @@ def main():
 
     def note(msg):
         if os.environ.get("ZKB_BENCH_VERBOSE"):
-            print("[bench] " + msg, file=sys.stderr, flush=True)
+            print("[bench %.1f] %s" % (time.time() - t_start, msg), file=sys.stderr, flush=True)
 
-    import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    zkb = importlib.import_module("zksnap-circuits-halo2_b200")
-    zkb.init(local_rank)
-    lib = zkb.lib()
-    stream = torch.cuda.current_stream()
-    sptr = ctypes.c_void_p(stream.cuda_stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- synthetic inputs: this rank's point-range shard -------------------------------------------------------------
-    n = 1 << LOG_N_MSM
-    seed = 0x5EED0000 + LOG_N_MSM + 1000 * rank
-    scal_np = random_field(n, seed)
-    h_scal = torch.from_numpy(scal_np.view(np.int64)).pin_memory()
-    d_scal = h_scal.to(dev, non_blocking=False)
-    dlog = random_field(n, seed + 7)
-    bases = zkb.g1_fixed_base_mul(dlog)           # [b_i]G on the GPU, known discrete logs
-    params = zkb.ParamsKZG(LOG_N_MSM, bases)
-    del bases
-    out = np.zeros(12, dtype=np.uint64)
-    outp = out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
-    c_bits, n_win, chunk = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
-    lib.zkb_msm_get_params(n, ctypes.byref(c_bits), ctypes.byref(n_win), ctypes.byref(chunk))
-    # the commit runs through the SRS window table, whose window width is chosen by its own cost model: report that one
-    t_bits, t_bytes = ctypes.c_uint32(), ctypes.c_uint64()
-    lib.zkb_srs_precompute(params.handle_g, ctypes.byref(t_bits), ctypes.byref(t_bytes))
-    if t_bits.value:
-        c_bits.value = t_bits.value
-        n_win.value = (255 + t_bits.value - 1) // t_bits.value
-
-    def step_dev():
-        rc = lib.zkb_msm_g1_srs_dev(params.handle_g, 0, ctypes.c_void_p(d_scal.data_ptr()), n, outp, sptr)
-        if rc != 0:
-            raise RuntimeError(lib.zkb_last_error().decode())
-
-    def step_e2e():
-        rc = lib.zkb_msm_g1_srs(params.handle_g, ctypes.cast(h_scal.data_ptr(), ctypes.POINTER(ctypes.c_uint64)), n, outp)
-        if rc != 0:
-            raise RuntimeError(lib.zkb_last_error().decode())
-
-    zdist = importlib.import_module("zksnap-circuits-halo2_b200.distributed")
-
-    def fold(result):
-        """host fold of the per-rank partial sums (96 B each) — the only inter-GPU exchange of a sharded MSM"""
-        if world == 1:
-            return result
-        return zkb.g1_sum(zdist.all_gather_g1(result, device=dev))
-
-    note("inputs ready")
-    clocks = ClockSampler(local_rank)
+    t_start = time.time()
+    env = Env(args)
+    rank, world = env.rank, env.world
+    clocks = ClockSampler(env.local_rank)
     clocks.start()
-    # ---- warm-up + correctness of the measured configuration (rank-local known-dlog check on the first step) ------------
-    for _ in range(args.warmup):
-        step_dev()
-    # checker leg (the oracle, like the cpu_baseline leg below; outside every timed region): the bases are [b_i]G, so the
-    # measured configuration must return [sum s_i b_i]G
-    from oracle import coracle
-
-    ip = coracle.fr_inner_product(scal_np, dlog)
-    want = coracle.g1_mul(coracle.g1_generator(), ip)
-    parity = bool((out[:8] == want).all())
-
-    note("warm-up + parity done")
-    # ---- timed: device-resident ------------------------------------------------------------------------------------------
-    zkb.prof.enable(True)
-    zkb.prof.reset()
-    launches0 = zkb.launch_count()
-    barrier()
-    t_win0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_dev()
-        total = fold(out)
-    e1.record(stream)
-    barrier()
-    clocks.window(t_win0, time.time())
-    ms = e0.elapsed_time(e1)
-    launches = zkb.launch_count() - launches0
-    acc_ms, acc_calls = zkb.prof.get("msm_accumulate")
-    sort_ms, _ = zkb.prof.get("msm_sort")
-    dig_ms, _ = zkb.prof.get("msm_digits")
-    red_ms, _ = zkb.prof.get("msm_reduce")
-    zkb.prof.enable(False)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
-
-    note("device-resident timing done")
-    # ---- timed: end to end through the host-buffer ABI ---------------------------------------------------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t_win0 = time.time()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-        total = fold(out)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clocks.window(t_win0, time.time())
+    note("init done")
+    head = headline_msm(env, clocks)
     clock_info = clocks.stop()
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * n * args.steps / e2e_s
-
-    note("e2e timing done")
-    # ---- integer-pipe peak (measured here) and the roofline of the dominant kernel -----------------------------------------
+    note("headline done")
+    parity = {"msm_2^%d_known_dlog" % LOG_N_MSM: head["parity"]}
     peak = ctypes.c_double(0)
-    lib.zkb_measure_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
-    lib.zkb_measure_imad_peak(ctypes.byref(peak))
-    alg_mac = n * n_win.value * 10 * 128          # SURVEY.md §8d: n*W mixed adds x 10 Fq mul x 128 32-bit MACs
-    acc_launch_ms = acc_ms / max(acc_calls, 1)
-    achieved = alg_mac / (acc_launch_ms * 1e-3) / 1e9 if acc_launch_ms else 0.0
-    roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel<level0> (+partial levels, bucket memset)",
-                "achieved": achieved, "peak": peak.value / 1e9, "unit": "GMAC/s (32x32+64 wide MACs)",
-                "frac": achieved / (peak.value / 1e9) if peak.value else None,
-                "traffic": 28.87e9 if LOG_N_MSM == 24 else None,
-                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the level-0 launch at 2^24 (profiles/r1c_msm_accumulate_ncu.txt)",
-                "peak_source": "measured in this run: unrolled independent mad.wide.u32 chains (zkb_measure_imad_peak)",
-                "hbm_view": ({"achieved": 28.87e9 / (acc_launch_ms * 1e-3) / 1e9, "unit": "GB/s",
-                              "note": "measured DRAM traffic of the same launch / its duration: the kernel is not HBM bound"}
-                             if (LOG_N_MSM == 24 and acc_launch_ms) else None),
-                "ms_per_launch": acc_launch_ms, "window_bits": c_bits.value, "windows": n_win.value,
-                "share_of_step": acc_launch_ms / ms_per_step if ms_per_step else None,
-                "other_ms": {"digits": dig_ms / max(acc_calls, 1), "sort": sort_ms / max(acc_calls, 1), "reduce": red_ms / max(acc_calls, 1)}}
+    env.lib.zkb_measure_imad_peak(ctypes.byref(peak))
 
-    # ---- secondary: batched NTT ----------------------------------------------------------------------------------------------
-    ntt_obj = None
-    if not args.skip_ntt:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm_peak, src = 6650.0, "fallback"
-        if os.path.exists(peaks_path):
-            hbm_peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-        N = 1 << NTT_LOG_N
-        cols = NTT_COLS
-        a_np = random_field(N * cols, 0xF0F0 + NTT_LOG_N + rank)
-        h_a = torch.from_numpy(a_np.view(np.int64)).pin_memory()
-        d_a = h_a.to(dev)
-        d_s = torch.empty_like(d_a)
-        w = zkb.omega(NTT_LOG_N)
-        wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
-
-        def ntt_step():
-            rc = lib.zkb_ntt_fr_dev(ctypes.c_void_p(d_a.data_ptr()), ctypes.c_void_p(d_s.data_ptr()), cols, wp, NTT_LOG_N, sptr)
-            if rc != 0:
-                raise RuntimeError(lib.zkb_last_error().decode())
-
-        note("ntt inputs ready")
-        for _ in range(args.warmup):
-            ntt_step()
-        barrier()
-        launches1 = zkb.launch_count()
-        e0.record(stream)
-        for _ in range(args.steps):
-            ntt_step()
-        e1.record(stream)
-        barrier()
-        nms = e0.elapsed_time(e1) / args.steps
-        launches += zkb.launch_count() - launches1
-        alg_bytes = 64.0 * N * cols
-        gbs = alg_bytes / (nms * 1e-3) / 1e9
-        note("ntt device timing done")
-        # e2e: host columns through zkb_ntt_fr_batch (H2D + kernels + D2H)
-        cols_np = [a_np[i * N:(i + 1) * N] for i in range(cols)]
-        ptrs = (ctypes.POINTER(ctypes.c_uint64) * cols)(*[ctypes.cast(h_a.data_ptr() + i * N * 32, ctypes.POINTER(ctypes.c_uint64)) for i in range(cols)])
-        lib.zkb_ntt_fr_batch(ptrs, cols, wp, NTT_LOG_N)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(max(1, args.steps // 2)):
-            lib.zkb_ntt_fr_batch(ptrs, cols, wp, NTT_LOG_N)
-        barrier()
-        ntt_e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
-        ntt_obj = {"workload": "best_fft 2^%d x %d columns (batched, in HBM)" % (NTT_LOG_N, cols),
-                   "value": world * N * cols / (nms * 1e-3), "unit": "elems/s", "ms_per_step": nms,
-                   "e2e": {"value": world * N * cols / ntt_e2e_s, "unit": "elems/s", "h2d_bytes_per_step": N * cols * 32,
-                           "d2h_bytes_per_step": N * cols * 32},
-                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                "traffic": 12.9e9 if (NTT_LOG_N, NTT_COLS) == (22, 16) else None, "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
-                                "note": "64 B algorithmic bytes per element; the kernel is integer-issue bound, see DESIGN.md"}}
-        del cols_np
-
-    # ---- secondary: quotient evaluation on resident cosets (GraphEvaluator row loop, SURVEY.md §8f row 1) ------------------------
-    quot_obj = None
-    if not args.skip_ntt:
-        ev = importlib.import_module("zksnap-circuits-halo2_b200.evaluation")
-        rows, qc, rs = 1 << QUOT_LOG_N, QUOT_COLS, 4
-        gr = ev.GraphEvaluator()
-        parts = []
-        for i in range(qc):   # halo2-base: q_i * (a + b * c - d), a..d = advice column i at rotations 0..3
-            a_, b_, c_, d_ = (("advice", i, r) for r in range(4))
-            parts.append(gr.add_expression(("prod", ("fixed", i, 0), ("sum", ("sum", a_, ("prod", b_, c_)), ("neg", d_)))))
-        gr.add_horner(ev.ValueSource(ev.PREVIOUS), parts, ev.ValueSource(ev.Y))
-        adv_np, sel_np = random_field(rows, 0x9A7E + rank), random_field(rows, 0x5E1 + rank)
-        y_np = random_field(1, 0x77)[0]
-        adv = [zkb.Polynomial(adv_np) for _ in range(qc)]   # same values, distinct HBM buffers: the traffic is real
-        sel = [zkb.Polynomial(sel_np) for _ in range(qc)]
-        vals = zkb.Polynomial(np.zeros((rows, 4), dtype=np.uint64))
-        note("quotient inputs ready")
-        gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
-        # parity of the measured configuration on sampled rows, Python integers (previous value 0):
-        # value = gate * (y^(qc-1) + ... + 1), gate = q (a + b c - d)
-        FRM = ev.FR
-        Rinv = pow(1 << 256, FRM - 2, FRM)
-        li = lambda v: sum(int(v[j]) << (64 * j) for j in range(4)) * Rinv % FRM  # noqa: E731
-        got = vals.to_host()
-        yv = li(y_np)
-        ysum = sum(pow(yv, j, FRM) for j in range(qc)) % FRM
-        q_ok = True
-        for r in [0, 1, rows - 1, rows - 5, rows // 3, rows // 2 + 7]:
-            av = [li(adv_np[(r + j * rs) % rows]) for j in range(4)]
-            q_ok &= li(got[r]) == li(sel_np[r]) * (av[0] + av[1] * av[2] - av[3]) % FRM * ysum % FRM
-        del got
-        for _ in range(args.warmup):
-            gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
-        barrier()
-        launches3 = zkb.launch_count()
-        zkb.prof.enable(True)
-        zkb.prof.reset()
-        for _ in range(args.steps):
-            gr.evaluate(vals, fixed=sel, advice=adv, y=y_np, rot_scale=rs)
-        barrier()
-        qms, qk = zkb.prof.get("graph_evaluate")   # CUDA events around the kernel on the library stream
-        qms /= max(qk, 1)
-        zkb.prof.enable(False)
-        launches += zkb.launch_count() - launches3
-        info = gr.last_info()
-        qgbs = info["bytes_per_row"] * rows / (qms * 1e-3) / 1e9
-        quot_obj = {"workload": "evaluate_h custom gates: halo2-base gate q(a+bc-d) on %d advice columns, 2^%d extended rows, rot_scale %d, resident in HBM" % (qc, QUOT_LOG_N, rs),
-                    "value": world * rows / (qms * 1e-3), "unit": "rows/s", "ms_per_step": qms, "parity_checked": bool(q_ok),
-                    "lowered": info, "modmul_per_row": 3 * qc,
-                    "roofline": {"bound": "hbm", "achieved": qgbs, "peak": hbm_peak, "unit": "GB/s", "frac": qgbs / hbm_peak,
-                                 "traffic": 5.362e9 if (QUOT_LOG_N, QUOT_COLS) == (24, 4) else None,   # ncu, profiles/r1d_graph_ncu.txt
-                                 "note": "32 B x (polynomials read + previous value + result) per row; integer-issue bound, see DESIGN.md"}}
-        parity = parity and bool(q_ok)
-        for p_ in adv + sel + [vals]:
-            p_.free()
-        del adv_np, sel_np
-        note("quotient done")
-
-    # ---- N > 1: one 2^26 NTT sharded over the ranks (exchange fused into the NTT passes over NVLink peer memory) ----------------
-    sharded_obj = None
-    if world > 1 and not args.skip_ntt and (world & (world - 1)) == 0 and world <= 8:
-        k = SHARDED_LOG_N
-        sh = zdist.ShardedNtt(k, device=dev)
-        off, ln = zdist.ntt_slice(k, rank, world)
-        w = zkb.omega(k)
-        wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
-        # parity of the measured configuration, size-independent: NTT(delta_0) = (1, 1, ..., 1)
-        d_in = torch.zeros(ln * 4, dtype=torch.int64, device=dev)
-        one = torch.from_numpy(np.array([0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f],
-                                        dtype=np.uint64).view(np.int64)).to(dev)
-        if rank == 0:
-            d_in[:4] = one
-        d_out = torch.empty_like(d_in)
-        rc = lib.zkb_dist_ntt_fr_dev(ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr()), wp, k, sptr)
-        if rc != 0 or lib.zkb_dist_status(sptr) != 0:
-            raise RuntimeError(lib.zkb_last_error().decode())
-        sh_ok = bool((d_out.view(-1, 4) == one).all().item())
-        g = torch.Generator(device=dev)
-        g.manual_seed(0xD157 + rank)
-        d_in = torch.randint(0, 1 << 60, (ln * 4,), dtype=torch.int64, device=dev, generator=g)
-        lib.zkb_dist_ntt_fr_dev(ctypes.c_void_p(d_in.data_ptr()), None, wp, k, sptr)  # loads the symmetric input slice
-        for _ in range(args.warmup):
-            lib.zkb_dist_ntt_fr_dev(None, None, wp, k, sptr)
-        barrier()
-        launches2 = zkb.launch_count()
-        e0.record(stream)
-        for _ in range(args.steps):
-            lib.zkb_dist_ntt_fr_dev(None, None, wp, k, sptr)
-        e1.record(stream)
-        if lib.zkb_dist_status(sptr) != 0:
-            raise RuntimeError(lib.zkb_last_error().decode())
-        barrier()
-        sms = e0.elapsed_time(e1) / args.steps
-        launches += zkb.launch_count() - launches2
-        t = torch.tensor([sms, 0.0 if sh_ok else 1.0], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sms, sh_ok = float(t[0].item()), t[1].item() == 0.0
-        N = 1 << k
-        sharded_obj = {"workload": "one best_fft of 2^%d sharded over %d GPUs (contiguous slices in, contiguous slices out)" % (k, world),
-                       "value": N / (sms * 1e-3), "unit": "elems/s", "ms_per_step": sms, "parity_checked": sh_ok,
-                       "exchange": "fused into NTT pass 0 (peer loads+stores) and the final pass (peer stores) over NVLink; device-side barriers",
-                       "nvlink_bytes_per_gpu_per_step": int(3 * (world - 1) / world * ln * 32),
-                       "roofline": {"bound": "hbm", "achieved": 64.0 * N / (sms * 1e-3) / 1e9, "peak": hbm_peak * world, "unit": "GB/s",
-                                    "frac": 64.0 * N / (sms * 1e-3) / 1e9 / (hbm_peak * world)}}
-        parity = parity and sh_ok
-        sh.close()
-        del d_in, d_out
-    # ---- N > 1: the same quotient evaluation sharded by rows (ring halo exchange over NCCL, then the row window on every rank) ------
-    sq_obj = None
-    if world > 1 and not args.skip_ntt and (world & (world - 1)) == 0:
+    def guarded(name, fn):
+        """a secondary object must not take the headline line down; its failure is reported and fails parity"""
         try:
-            srows = (1 << QUOT_LOG_N) // world
-            sq = zdist.ShardedQuotient(gr, 4)
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(0x51AB)   # the same rows on every rank: the domain is periodic with period srows, so the sharded result
-            base = torch.randint(0, 1 << 60, (srows, 4), dtype=torch.int64, device=dev, generator=gen)  # must equal a wrapping evaluation of one period
-            bufs = []
-            for _ in range(2 * QUOT_COLS):
-                buf, view = sq.alloc_column(srows, dev)
-                view.copy_(base)
-                bufs.append(buf)
-            sel_b, adv_b = bufs[:QUOT_COLS], bufs[QUOT_COLS:]
-            vals_s = torch.zeros_like(base)
-            sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
-            ref_s = torch.zeros_like(base)
-            plain = [base.clone() for _ in range(2)]
-            gr.evaluate_dev(ref_s.data_ptr(), srows, [plain[0].data_ptr()] * QUOT_COLS, [plain[1].data_ptr()] * QUOT_COLS, y=y_np, rot_scale=4,
-                            stream=torch.cuda.current_stream().cuda_stream)
-            torch.cuda.synchronize()
-            sq_ok = bool(torch.equal(vals_s, ref_s))
-            for _ in range(args.warmup):
-                sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
-            barrier()
-            launches4 = zkb.launch_count()
-            e0.record(stream)
-            for _ in range(args.steps):
-                sq.run_padded(vals_s, sel_b, adv_b, [], y=y_np)
-            e1.record(stream)
-            barrier()
-            qsms = e0.elapsed_time(e1) / args.steps
-            launches += zkb.launch_count() - launches4
-            t = torch.tensor([qsms, 0.0 if sq_ok else 1.0], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            qsms, sq_ok = float(t[0].item()), t[1].item() == 0.0
-            sq_obj = {"workload": "the quotient workload above, 2^%d rows sharded by rows over %d GPUs" % (QUOT_LOG_N, world),
-                      "value": (1 << QUOT_LOG_N) / (qsms * 1e-3), "unit": "rows/s", "ms_per_step": qsms, "parity_checked": sq_ok,
-                      "exchange": "ring halo exchange, %d + %d rows per column over NCCL point-to-point, then zkb_graph_evaluate_dev on the row window" % (sq.halo_lo, sq.halo_hi),
-                      "halo_bytes_per_rank": (sq.halo_lo + sq.halo_hi) * 32 * 2 * QUOT_COLS}
-            parity = parity and sq_ok
-            del bufs, vals_s, ref_s, plain, base
-        except Exception as exc:  # a secondary object must not take the headline line down
-            sq_obj = {"error": repr(exc)[:300]}
-    note("ntt done")
-    # ---- CPU baseline on this box (rank 0, N=1 only) ---------------------------------------------------------------------------
+            o = fn()
+            note(name + " done")
+            return o
+        except Exception as exc:
+            note(name + " FAILED: " + repr(exc))
+            return {"error": repr(exc)[:400], "parity_checked": False}
+
+    ntt_obj = quot_obj = sharded_obj = sq_obj = wrap_obj = split_obj = sp_obj = None
+    dropin = {}
+    gr = y_np = None
+    split_point = None
+    if not args.skip_ntt:
+        ntt_obj = guarded("ntt", lambda: ntt_object(env, peak.value))
+
+        def _q():
+            nonlocal gr, y_np
+            o, gr, y_np = quotient_object(env)
+            return o
+
+        quot_obj = guarded("quotient", _q)
+        if world > 1 and (world & (world - 1)) == 0 and world <= 8:
+            sharded_obj = guarded("sharded_ntt", lambda: sharded_ntt_object(env))
+            if gr is not None:
+                sq_obj = sharded_quotient_object(env, gr, y_np)
+    if not args.skip_ntt and not args.skip_replay:
+        wrap_obj = guarded("wrapper_replay", lambda: wrapper_replay_object(env))
+
+        def _s():
+            nonlocal split_point
+            o, split_point = msm_split_object(env)
+            return o
+
+        split_obj = guarded("msm_split", _s)
+        if world == 1:   # drop-in (host-buffer) replays of the three circuits on one GPU; at N > 1 the single process runs them
+            dropin = guarded("dropin_replays", lambda: {"pageable": dropin_replays(env, False), "page_locked": dropin_replays(env, True)})
+    # ---- N > 1: every rank releases its GPU, then rank 0 alone drives all N devices
+    if world > 1 and not args.skip_ntt and not args.skip_replay and split_point is not None:
+        env.torch.cuda.synchronize()
+        env.zkb.shutdown()
+        env.torch.cuda.empty_cache()
+        env.dist.barrier(group=env.host_group)      # host-side: an NCCL barrier would keep the other GPUs spinning
+        if rank == 0:
+            sp_obj = guarded("single_process", lambda: single_process_object(env, split_obj, split_point))
+        env.dist.barrier(group=env.host_group)
+        env.zkb.init(env.local_rank)
+    for name, o in (("ntt", ntt_obj), ("quotient", quot_obj), ("sharded_ntt", sharded_obj), ("sharded_quotient", sq_obj),
+                    ("wrapper_replay", wrap_obj), ("msm_split", split_obj), ("single_process", sp_obj)):
+        if o is not None:
+            parity[name] = bool(o.get("parity_checked", False))
+    if dropin:
+        if "error" in dropin:
+            parity["dropin_replays"] = False
+        else:
+            for memk, d in dropin.items():
+                for nm, o in d.items():
+                    parity["dropin_%s_%s" % (nm, memk)] = bool(o.get("parity_checked", False))
+    # ---- CPU baseline on this box (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        v, cores, dt = cpu_baseline_msm(CPU_SAMPLE_LOG_N)
+        v, cores, dt, native = cpu_baseline_msm(LOG_N_MSM)
         cpu = {"value": v, "unit": "pts/s", "cores": cores, "kind": "port",
-               "sample": "best_multiexp restatement (C, pthreads; not rayon) on 2^%d uniform points, %.1f s" % (CPU_SAMPLE_LOG_N, dt)}
-
+               "sample": "best_multiexp restatement (C, pthreads; not rayon; %s) on the full 2^%d uniform points once, %.1f s"
+                         % ("-O3 -march=native built on this host" if native else "portable -O3 build", LOG_N_MSM, dt)}
+        note("cpu baseline done")
+    all_ok = all(parity.values())
     if rank == 0:
+        replay = None
+        if wrap_obj is not None:
+            replay = {"kernel": wrap_obj}
+            if dropin and "error" not in dropin:
+                replay["dropin_pageable"] = dropin["pageable"]["wrapper"]
+                replay["dropin_page_locked"] = dropin["page_locked"]["wrapper"]
         line = {
-            "metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": head["value"], "unit": "pts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
-            "config": {"workload": "msm_g1_2^%d_uniform_per_gpu" % LOG_N_MSM, "sharding": "srs_point_range_per_rank, host fold",
-                       "l2": "inputs_exceed_l2 (512 MiB scalars + 1 GiB bases per step)", "window_bits": c_bits.value,
-                       "windows": n_win.value, "srs_window_table_bytes": int(t_bytes.value), "chunk": chunk.value},
-            "e2e": {"value": e2e_value, "unit": "pts/s", "h2d_bytes_per_step": n * 32 * world,
-                    "d2h_bytes_per_step": n_win.value * 128 * world, "timer": "wall clock around the C-ABI call (includes host fold)"},
-            "gpu_launches": int(launches), "parity_checked": parity, "roofline": roofline, "cpu_baseline": cpu,
-            "clocks": clock_info, "ntt": ntt_obj, "quotient": quot_obj, "sharded_ntt": sharded_obj, "sharded_quotient": sq_obj,
+            "config": head["config"], "e2e": head["e2e"], "e2e_pageable": head["e2e_pageable"],
+            "no_table_ms_per_step": head["no_table_ms_per_step"],
+            "gpu_launches": int(env.launches), "parity_checked": all_ok, "parity": parity, "roofline": head["roofline"],
+            "cpu_baseline": cpu, "clocks": clock_info, "ntt": ntt_obj, "quotient": quot_obj,
+            "sharded_ntt": sharded_obj, "sharded_quotient": sq_obj,
+            "wrapper_replay": replay, "msm_split": split_obj,
+            "voter_replay": ({"dropin_pageable": dropin["pageable"]["voter"], "dropin_page_locked": dropin["page_locked"]["voter"]}
+                             if dropin and "error" not in dropin else None),
+            "st_replay": ({"dropin_pageable": dropin["pageable"]["st"], "dropin_page_locked": dropin["page_locked"]["st"]}
+                          if dropin and "error" not in dropin else None),
+            "single_process": sp_obj,
+            "bench_wall_s": time.time() - t_start,
         }
         print(json.dumps(line))
-    params.close()
     if world > 1:
-        dist.destroy_process_group()
-    return 0 if parity else 1
+        env.dist.destroy_process_group()
+    return 0 if all_ok else 1
 
 
 if __name__ == "__main__":

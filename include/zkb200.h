@@ -362,6 +362,9 @@ int zkb_msm_set_slices(int slices);
 /* MSM window bits / level-0 chunk length override (0 = automatic). */
 int zkb_msm_set_params(uint32_t window_bits, uint32_t chunk);
 int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, uint32_t* chunk);
+/* Bucket additions the last MSM on the home device performed = its non-zero signed digits (zero digits are skipped, which is
+ * most of a witness column): the work figure to use for roofline fractions of non-uniform scalar distributions. */
+int zkb_msm_last_entries(uint64_t* entries);
 
 /* Per-kernel CUDA-event timers.  Names: "msm_digits", "msm_sort", "msm_accumulate", "msm_reduce",
  * "ntt_pass", "graph_evaluate", "dist_ntt_pass0", "dist_ntt_middle", "dist_ntt_final", "dist_barrier".  zkb_prof_get returns the summed milliseconds and launch count since the last reset. */

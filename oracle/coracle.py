@@ -25,6 +25,25 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def use_native() -> bool:
+    """bench.py's CPU-baseline legs only: recompile the oracle ON THIS HOST with -O3 -march=native into
+    oracle/_native/ and bind that build from now on.  The portable build that travels with the repository stays what the tests
+    use (a -march=native binary built in one container may not run on another host).  Returns False (and keeps the portable
+    build) if the compiler is missing or fails."""
+    global _lib, _LIB_PATH
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "libzkb_oracle_native.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-pthread", "-fPIC", "-fvisibility=hidden", "-std=c11", "-shared", "-o", out,
+                               os.path.join(_HERE, "zkb_oracle.c"), "-lm", "-lpthread"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return False
+    _LIB_PATH = out
+    _lib = None
+    return True
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -142,10 +142,14 @@ def main():
             lib.zkb_msm_get_params(n, ctypes.byref(cb), ctypes.byref(nw), ctypes.byref(ch))
             c = cb.value
         W = (255 + c - 1) // c
-        alg = n * W * 10 * 128
+        ent = ctypes.c_uint64(0)
+        lib.zkb_msm_last_entries(ctypes.byref(ent))
+        # work actually asked of the kernel: one mixed addition per NON-ZERO digit (a witness-like column has few); for
+        # uniform scalars this equals the n * W of SURVEY.md §8d up to 2^-c
+        alg = ent.value * 10 * 128
         acc = parts["msm_accumulate"]
         emit({"op": "msm", "log_n": k, "dist": dist, "ms": ms, "pts_per_s": n / (ms * 1e-3), "parity": ok, "window_bits": c,
-              "windows": W, "table_GiB": tb.value / 2**30, "kernels_ms": parts,
+              "windows": W, "bucket_additions": ent.value, "table_GiB": tb.value / 2**30, "kernels_ms": parts,
               "accumulate_frac_of_imad_peak": alg / (acc * 1e-3) / peak.value if acc else None})
         del d_s
 

@@ -119,6 +119,7 @@ def load() -> ctypes.CDLL:
         "zkb_field_vec_op": [ci, ci, u64p, u64p, u64p, sz],
         "zkb_msm_set_params": [u32, u32],
         "zkb_msm_get_params": [sz, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)],
+        "zkb_msm_last_entries": [ctypes.POINTER(u64)],
         "zkb_prof_enable": [ci],
         "zkb_prof_reset": [],
         "zkb_measure_imad_peak": [ctypes.POINTER(ctypes.c_double)],

@@ -1644,6 +1644,11 @@ int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, u
     if (chunk) *chunk = g.chunk0;
     return ZKB_OK;
 }
+int zkb_msm_last_entries(uint64_t* entries) {
+    ZKB_TRY(check_ptr(entries, "entries"));
+    *entries = msm_workspace().last_entries;
+    return ZKB_OK;
+}
 int zkb_prof_enable(int on) {
     ctx().prof_on = on != 0;
     return ZKB_OK;

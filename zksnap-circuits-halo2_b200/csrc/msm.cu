@@ -300,6 +300,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_CUDA_TRY(cudaMemcpyAsync(h_cnt, w.counter[set].p, 8, cudaMemcpyDeviceToHost, sp));
         ZKB_CUDA_TRY(cudaStreamSynchronize(sp));   // overlap: waits for this slice's digits only, not for the accumulation on `s`
         valid = *h_cnt;
+        w.last_entries = (phase & MSM_FIRST) ? valid : w.last_entries + valid;
     }
     // ---- 2. sort
     const uint32_t* sk;

@@ -19,6 +19,7 @@ struct MsmWorkspace {
     uint32_t slice_ix = 0;
     int overlap = 1;         // ZKB_MSM_OVERLAP=0 (environment, read once): run the slices on one stream
     bool env_read = false;
+    uint64_t last_entries = 0;  // non-zero digits (bucket additions) of the last MSM / slice on this device
 };
 
 MsmWorkspace& msm_workspace();

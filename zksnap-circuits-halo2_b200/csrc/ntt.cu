@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(128, ZKB_NTT_MIN_CTAS) ntt_pass_kernel(const N
     extern __shared__ uint4 ntt_smem[];
     CtaBarrier bar;
     if (a.dist_abort && *reinterpret_cast<const volatile uint32_t*>(a.dist_abort)) return;  // sharded NTT: a barrier timed out
-    ntt_cta_program<LOGR>(a, ntt_smem, threadIdx.x, blockDim.x, (uint64_t)blockIdx.x, blockIdx.y, bar);
+    const uint32_t ncols = a.ncols ? a.ncols : 1;
+    ntt_cta_program<LOGR>(a, ntt_smem, threadIdx.x, blockDim.x, (uint64_t)(blockIdx.x / ncols), blockIdx.x % ncols, bar);
 }
 
 // out[t] = omega^(t << shift)
@@ -159,7 +160,10 @@ int ntt_run(const NttPlan& plan, const NttIo& io, cudaStream_t s) {
                 a.in_scale[m][i] = io.in_scale ? io.in_scale[m].l[i] : 0;
                 a.out_scale[m][i] = io.out_scale ? io.out_scale[m].l[i] : 0;
             }
-        dim3 grid((unsigned)ntt_cta_count(g, p), (unsigned)io.cols);
+        a.ncols = (uint32_t)io.cols;
+        const uint64_t blocks = ntt_cta_count(g, p) * io.cols;
+        if (blocks >= (1ull << 31)) { set_error("NTT batch too large for one launch: %llu CTAs", (unsigned long long)blocks); return ZKB_ERR_ARG; }
+        dim3 grid((unsigned)blocks, 1);
         ZKB_TRY(ntt_launch_pass(g.lr[p], a, grid, ntt_cta_threads(g, p), ntt_cta_smem_bytes(g, p), s));
     }
     return ZKB_OK;

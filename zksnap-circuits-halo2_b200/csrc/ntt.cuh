@@ -44,6 +44,8 @@ struct NttPassArgs {
     uint32_t npass;           // P
     uint32_t pass;            // p (0-based)
     uint32_t lr[NTT_MAX_PASSES];  // log2 R_q
+    uint32_t ncols;           // columns of the batch: block b of the 1-D grid is (cta b / ncols, column b % ncols), so the
+                              // columns of one tile run back to back and share its twiddle-table lines in L2
     uint32_t log_t;           // log2 T (tile width)
     uint32_t is_final;        // last pass: transposed (digit-reversed) store
     // twiddles (device pointers)
@@ -144,16 +146,39 @@ ZKB_HD uint32_t ntt_dif_pos(uint32_t k) {
     return pos;
 }
 
+// Strided layout with fewer than 8 columns per row (R >= 256: T = 1024 / R): a row covers only T/8 of the 32 banks, so the 8/T
+// rows one quarter-warp touches in a 128-bit access must fall into different bank groups.  Which row bits vary inside a
+// quarter-warp depends on the phase: the low bits in the load and the first DIF rounds, bits [L+t ..] in the rounds whose
+// sub-block is shorter than the group of adjacent threads, the top digit in the digit-reversed store.  XOR-ing those bits
+// into the low 3 - log_t row bits makes every phase conflict-free (a bijection on the rows: only low bits change, from
+// higher bits).  Rounds are 3,3,2 (R = 2^8), 3,3,3 (2^9), 3,3,3,1 (2^10).
+template <int LOGR>
+ZKB_HD uint32_t ntt_row_swizzle(uint32_t r) {
+    if (LOGR == 8) return r ^ (((r >> 2) ^ (r >> 5)) & 1u);                                  // T = 4: one bit
+    if (LOGR == 9) return r ^ (((r >> 3) ^ (r >> 6)) & 3u);                                  // T = 2: two bits (r3,r4 / r6,r7)
+    if (LOGR == 10) return r ^ (((r >> 3) & 1u) | (((r >> 4) & 3u) << 1)) ^ ((r >> 7) & 7u);  // T = 1: three bits
+    return r;
+}
+
+// Column pitch of the transposed (final-pass) layout: R + 1 for T >= 8 (8 adjacent threads = 8 adjacent columns land 1 slot
+// apart mod 8); for T < 8 the T columns of a row are spread 8/T bank groups apart and the swizzled row supplies the rest.
+template <int LOGR>
+ZKB_HD uint32_t ntt_final_pitch(uint32_t log_t) {
+    constexpr uint32_t R = 1u << LOGR;
+    return (LOGR >= 8 && log_t + LOGR == 10) ? R + ((8u >> log_t) & 7u) : R + 1;
+}
+
 // shared-memory index of (row r, column c)
 template <int LOGR>
 ZKB_HD uint32_t ntt_sm_index(const NttPassArgs& a, uint32_t r, uint32_t c) {
-    constexpr uint32_t R = 1u << LOGR;
-    return a.is_final ? c * (R + 1) + r : (r << a.log_t) + c;
+    if (LOGR >= 8 && a.log_t + LOGR == 10) r = ntt_row_swizzle<LOGR>(r);
+    if (a.is_final) return c * ntt_final_pitch<LOGR>(a.log_t) + r;
+    return (r << a.log_t) + c;
 }
 template <int LOGR>
 ZKB_HD uint32_t ntt_sm_plane(const NttPassArgs& a) {  // uint4 elements per plane
     constexpr uint32_t R = 1u << LOGR;
-    return a.is_final ? ((R + 1) << a.log_t) : (R << a.log_t);
+    return a.is_final ? (ntt_final_pitch<LOGR>(a.log_t) << a.log_t) : (R << a.log_t);
 }
 
 // entry t = K * R + r of pass p's twiddle table: omega_N^((r*K) << shift), from the two-level power tables

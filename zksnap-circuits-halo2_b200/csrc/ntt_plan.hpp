@@ -83,7 +83,7 @@ inline uint64_t ntt_cta_count(const NttGeometry& g, uint32_t p) {
 inline size_t ntt_cta_smem_bytes(const NttGeometry& g, uint32_t p) {
     uint32_t R = 1u << g.lr[p];
     bool fin = (p + 1 == g.npass);
-    size_t plane = fin ? ((size_t)(R + 1) << g.log_t[p]) : ((size_t)R << g.log_t[p]);
+    size_t plane = fin ? ((size_t)(R + 4) << g.log_t[p]) : ((size_t)R << g.log_t[p]);  // R + 4 >= every ntt_final_pitch
     return plane * 2 * 16;
 }
 
