@@ -206,7 +206,19 @@ int zkb_lagrange_to_coeff_dev(void* d_data, void* d_scratch, size_t ncols, uint3
  *                                z of the permutation and lookup arguments (numerators * inverted denominators, scanned) */
 int zkb_poly_upload(const uint64_t* values, size_t n, uint64_t* handle);
 int zkb_poly_alloc(size_t n, uint64_t* handle); /* zero-filled */
+/* Proving-key residency: n raw Fr (32-byte Montgomery limbs — the element encoding of
+ * SerdeFormat::RawBytesUnchecked, the format the reference keeps its proving keys in, /root/reference/aggregator/src/wrapper.rs:
+ * 970-988, 1006-1034, 1072-1106) are read from `path` at byte `offset` through two pinned staging buffers straight into a
+ * polynomial handle.  The fixed / selector / sigma polynomials and cosets, l_0, l_last and l_active of a ProvingKey are loaded
+ * once this way and reused by every proof of the IVC loop (wrapper.rs:884-900); the container layout (which polynomial sits
+ * where) stays with the caller, who passes offsets — see zksnap-circuits-halo2_b200/plonk.py: ProvingKey.read. */
+int zkb_poly_load_file(const char* path, uint64_t offset, size_t n, uint64_t* handle);
+/* Host->device bytes the library has copied since load (or since the last call with reset != 0), all devices: lets a caller
+ * assert that a second proof against a resident proving key uploads witness data only. */
+int zkb_transfer_stats(uint64_t* h2d_bytes, int reset);
 int zkb_poly_len(uint64_t handle, size_t* n);
+/* poly[offset .. offset + n) = values (host -> device): e.g. the random blinding rows at the end of a product column */
+int zkb_poly_write(uint64_t handle, size_t offset, const uint64_t* values, size_t n);
 int zkb_poly_download(uint64_t handle, uint64_t* out, size_t n);
 int zkb_poly_free(uint64_t handle);
 /* new handle with a copy of poly[offset .. offset + n) — the pieces of h(X) after extended_to_coeff (n coefficients each), which the

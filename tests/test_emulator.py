@@ -97,6 +97,23 @@ def test_msm_matches_best_multiexp(oracle, n, c, chunk):
     assert (emu.msm(s, b, c, chunk) == oracle.best_multiexp(s, b)).all()
 
 
+@pytest.mark.parametrize("n,c,chunk", [(700, 6, 3), (3000, 9, 16), (257, 4, 1)])
+def test_msm_level0_throughput_form(oracle, n, c, chunk):
+    """Level 0 without the in-CTA tree (what large MSMs run): thread summaries go straight to the partial list and the next
+    levels combine them — same result as the tree form and as the oracle."""
+    s = random_field(n, 31 + n)
+    b = oracle.g1_fixed_base_mul(random_field(n, 32 + n))
+    s[: n // 3] = s[0]
+    want = oracle.best_multiexp(s, b)
+    emu.lib().zkb_emu_msm_set_direct0(1)
+    try:
+        assert (emu.msm(s, b, c=c, chunk=chunk) == want).all()
+        assert (emu.msm(s, b, c=c, chunk=chunk, table=True) == want).all()
+    finally:
+        emu.lib().zkb_emu_msm_set_direct0(0)
+    assert (emu.msm(s, b, c=c, chunk=chunk) == want).all()
+
+
 def test_msm_edge_cases(oracle):
     n = 300
     b = _bases(oracle, n, 5)

@@ -83,7 +83,10 @@ def load() -> ctypes.CDLL:
         "zkb_lagrange_to_coeff_dev": [vp, vp, sz, u32, vp],
         "zkb_poly_upload": [u64p, sz, ctypes.POINTER(u64)],
         "zkb_poly_alloc": [sz, ctypes.POINTER(u64)],
+        "zkb_poly_load_file": [ctypes.c_char_p, u64, sz, ctypes.POINTER(u64)],
+        "zkb_transfer_stats": [ctypes.POINTER(u64), ci],
         "zkb_poly_len": [u64, ctypes.POINTER(sz)],
+        "zkb_poly_write": [u64, sz, u64p, sz],
         "zkb_poly_download": [u64, u64p, sz],
         "zkb_poly_free": [u64],
         "zkb_poly_commit": [u64, u64, u64p],

@@ -741,6 +741,7 @@ static int domain_op_host_one(DomainOp op, const uint64_t* const* in, uint64_t* 
                 src = (char*)s.h_in.p + i * col_in;
             }
             e = cudaMemcpyAsync(d_in + i * col_in, src, col_in, cudaMemcpyHostToDevice, pl.s_h2d);
+            count_h2d(col_in);
         }
         if (e == cudaSuccess) e = cudaEventRecord(s.ev_h2d, pl.s_h2d);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, s.ev_h2d, 0);
@@ -840,6 +841,7 @@ static int upload_scalars(const uint64_t* scalars, size_t n) {
     ZKB_TRY(check_ptr(scalars, "scalars"));
     ZKB_TRY(h.scalars.reserve(n * 32));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    count_h2d(n * 32);
     return ZKB_OK;
 }
 
@@ -904,6 +906,7 @@ static int msm_srs_host(Srs* srs, size_t offset, const uint64_t* scalars, size_t
             src = st.p;
         }
         cudaError_t e = cudaMemcpyAsync((char*)h.scalars.p + lo * 32, src, cnt * 32, cudaMemcpyHostToDevice, pl.s_h2d);
+        count_h2d(cnt * 32);
         if (e == cudaSuccess && !pinned) e = cudaEventRecord(h.stage_ev[sidx & 1], pl.s_h2d);
         if (e == cudaSuccess) e = cudaEventRecord(ev.ev_h2d, pl.s_h2d);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, ev.ev_h2d, 0);
@@ -1113,6 +1116,7 @@ int zkb_msm_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_
         HostIo& h = hostio();
         ZKB_TRY(h.bases.reserve(len * 64));
         ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, bases + 8 * off, len * 64, cudaMemcpyHostToDevice, ctx().stream));
+        count_h2d(len * 64);
         ZKB_TRY(upload_scalars(scalars + 4 * off, len));
         return msm_run(h.scalars.as<uint4>(), h.bases.as<uint4>(), len, ctx().stream, out);
     };
@@ -1138,6 +1142,7 @@ int zkb_srs_register(const uint64_t* bases, size_t n, uint64_t* handle) {
     if (rc != ZKB_OK) { delete s; return rc; }
     if (n) {
         cudaError_t e = cudaMemcpy(s->bases.p, bases, n * 64, cudaMemcpyHostToDevice);
+        count_h2d(n * 64);
         if (e != cudaSuccess) { set_error("SRS upload failed: %s", cudaGetErrorString(e)); s->bases.release(); delete s; return ZKB_ERR_CUDA; }
     }
     return srs_publish(s, handle);
@@ -1191,6 +1196,7 @@ int zkb_srs_load_file(const char* path, uint64_t offset, size_t n, int check_poi
         if (i >= 2 && cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { set_error("SRS upload failed"); return cleanup(ZKB_ERR_CUDA); }
         if (fread(pin[i & 1], 1, len, f) != len) { set_error("short read from %s", path); return cleanup(ZKB_ERR_ARG); }
         cudaError_t e = cudaMemcpyAsync((char*)s->bases.p + done, pin[i & 1], len, cudaMemcpyHostToDevice, st);
+        count_h2d(len);
         if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
         if (e != cudaSuccess) { set_error("SRS upload failed: %s", cudaGetErrorString(e)); return cleanup(ZKB_ERR_CUDA); }
         done += len;
@@ -1294,6 +1300,7 @@ static int msm_batch_one(Srs* s, const uint64_t* const* scalars, size_t ncols, s
         for (size_t i = 0; i < nc; ++i)
             ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h.scalars.p) + i * n * 32, scalars[c0 + i], n * 32,
                                          cudaMemcpyHostToDevice, c.stream));
+        count_h2d(nc * n * 32);
         ZKB_TRY(msm_srs_dev(s, 0, h.scalars.as<uint4>(), n, c.stream, out_jac + 12 * c0, (uint32_t)nc));
     }
     return ZKB_OK;
@@ -1389,6 +1396,7 @@ static int fixed_base_host(const uint64_t* scalars, size_t n, uint64_t* out_affi
     ZKB_TRY(h.scalars.reserve(n * 32));
     ZKB_TRY(h.bases.reserve(n * 64));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    count_h2d(n * 32);
     if (windowed) ZKB_TRY(g1_fixed_base_window_dev(h.scalars.as<uint4>(), n, h.bases.as<uint4>(), c.stream));
     else ZKB_TRY(g1_fixed_base_mul_dev(h.scalars.as<uint4>(), n, h.bases.as<uint4>(), c.stream));
     ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
@@ -1413,6 +1421,7 @@ int zkb_g1_batch_normalize(const uint64_t* points_jac, size_t n, uint64_t* out_a
     ZKB_TRY(h.x.reserve(n * 96));
     ZKB_TRY(h.bases.reserve(n * 64));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.x.p, points_jac, n * 96, cudaMemcpyHostToDevice, c.stream));
+    count_h2d(n * 96);
     ZKB_TRY(g1_batch_to_affine_dev(h.x.as<uint4>(), n, h.bases.as<uint4>(), true, c.stream));
     ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.bases.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
     ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
@@ -1477,6 +1486,7 @@ int zkb_g1_ntt(const uint64_t* points_affine, uint64_t* out_affine, const uint64
     ZKB_TRY(h.bases.reserve(n * 64));
     ZKB_TRY(h.x.reserve(n * 64));
     ZKB_CUDA_TRY(cudaMemcpyAsync(h.bases.p, points_affine, n * 64, cudaMemcpyHostToDevice, c.stream));
+    count_h2d(n * 64);
     ZKB_TRY(g1_fft_dev(h.bases.as<uint4>(), h.x.as<uint4>(), log_n, fr_from_limbs64(omega), nullptr, c.stream));
     ZKB_CUDA_TRY(cudaMemcpyAsync(out_affine, h.x.p, n * 64, cudaMemcpyDeviceToHost, c.stream));
     ZKB_CUDA_TRY(cudaStreamSynchronize(c.stream));
@@ -1642,6 +1652,16 @@ int zkb_msm_get_params(size_t n, uint32_t* window_bits, uint32_t* num_windows, u
     if (window_bits) *window_bits = g.c;
     if (num_windows) *num_windows = g.nwin;
     if (chunk) *chunk = g.chunk0;
+    return ZKB_OK;
+}
+int zkb_transfer_stats(uint64_t* h2d_bytes, int reset) {
+    Ctx* all = per_device_array<Ctx>();
+    uint64_t total = 0;
+    for (int i = 0; i < ZKB_MAX_DEVICES; ++i) {
+        total += all[i].h2d_bytes.load();
+        if (reset) all[i].h2d_bytes.store(0);
+    }
+    if (h2d_bytes) *h2d_bytes = total;
     return ZKB_OK;
 }
 int zkb_msm_last_entries(uint64_t* entries) {

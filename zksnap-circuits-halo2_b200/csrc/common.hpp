@@ -67,6 +67,7 @@ struct Ctx {
     std::map<std::string, ProfTimer> timers;
     std::vector<cudaEvent_t> event_pool;
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> h2d_bytes{0};   // host->device bytes copied by the library on this device (zkb_transfer_stats)
     // tuning
     uint32_t msm_c_override = 0;
     uint32_t msm_chunk_override = 0;
@@ -109,5 +110,6 @@ struct ProfScope {
 };
 
 inline void count_launch(uint64_t n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
+inline void count_h2d(uint64_t bytes) { ctx().h2d_bytes.fetch_add(bytes, std::memory_order_relaxed); }
 
 }  // namespace zkb

@@ -256,6 +256,7 @@ int dist_inprocess_ntt_host(const uint64_t* in, uint64_t* out, const uint64_t om
         DistCtx& d = dctx();
         cudaStream_t s = ctx().stream;
         ZKB_CUDA_TRY(cudaMemcpyAsync(d.local[0], reinterpret_cast<const char*>(in) + (size_t)slot * slice, slice, cudaMemcpyHostToDevice, s));
+        count_h2d(slice);
         ZKB_TRY(dist_ntt_dev(nullptr, nullptr, omega, log_n, s, out_scale));
         ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)slot * slice, d.local[2], slice, cudaMemcpyDeviceToHost, s));
         return dist_check_status(s);
@@ -364,6 +365,7 @@ int zkb_dist_ntt_fr(const uint64_t* in_slice, uint64_t* out_slice, const uint64_
     cudaStream_t s = ctx().stream;
     const size_t slice = ((size_t)1 << (log_n - d.log_g)) * 32;
     ZKB_CUDA_TRY(cudaMemcpyAsync(d.local[0], in_slice, slice, cudaMemcpyHostToDevice, s));
+    count_h2d(slice);
     ZKB_TRY(dist_ntt_dev(nullptr, nullptr, omega, log_n, s));
     ZKB_CUDA_TRY(cudaMemcpyAsync(out_slice, d.local[2], slice, cudaMemcpyDeviceToHost, s));
     return dist_check_status(s);

@@ -49,9 +49,40 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const MsmDigitArgs a) {
     }
 }
 
+// the tree phase is kept out of line: its full additions must not raise the register count of the level-0 chunk loop
+__device__ __noinline__ void msm_acc_tree(const MsmAccArgs& a, uint32_t* skey, uint4* sval) {
+    for (uint32_t d = 1; d < MSM_ACC_CTA; d <<= 1) {
+        __syncthreads();
+        msm_acc_phase_combine(a, threadIdx.x, d, MSM_ACC_CTA, skey, sval);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) msm_acc_phase_emit(a, blockIdx.x, skey, sval);
+}
+
 template <bool LEVEL0>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const MsmAccArgs a) {
-    msm_accumulate_thread<LEVEL0>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(MSM_ACC_CTA, 4) msm_accumulate_kernel(const MsmAccArgs a) {
+    __shared__ uint32_t skey[2 * MSM_ACC_CTA];
+    __shared__ uint4 sval[2 * MSM_ACC_CTA * 8];
+    msm_acc_phase_chunk<LEVEL0>(a, (uint64_t)blockIdx.x * MSM_ACC_CTA + threadIdx.x, threadIdx.x, skey, sval);
+    msm_acc_tree(a, skey, sval);
+}
+
+template <bool LEVEL0>
+__global__ void __launch_bounds__(MSM_ACC_CTA) msm_accumulate_direct_kernel(const MsmAccArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * MSM_ACC_CTA + threadIdx.x;
+    if (t * a.chunk < a.count) msm_acc_thread_direct<LEVEL0>(a, t);
+    else { a.pkeys_out[2 * t] = MSM_INVALID_KEY; a.pkeys_out[2 * t + 1] = MSM_INVALID_KEY; }
+}
+
+__global__ void __launch_bounds__(MSM_ACC_CTA) msm_sum_tree_kernel(const MsmSumTreeArgs a) {
+    __shared__ uint4 sval[MSM_ACC_CTA * 8];
+    msm_sum_tree_phase_load(a, blockIdx.x, threadIdx.x, sval);
+    for (uint32_t d = MSM_ACC_CTA / 2; d >= 1; d >>= 1) {
+        __syncthreads();
+        msm_sum_tree_phase_step(threadIdx.x, d, sval);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) msm_sum_tree_phase_store(a, blockIdx.x, sval);
 }
 
 __global__ void __launch_bounds__(128) msm_merge_kernel(const MsmMergeArgs a) {
@@ -60,10 +91,6 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(const MsmMergeArgs a) {
 
 __global__ void __launch_bounds__(128) msm_reduce_segment_kernel(const MsmReduceArgs a) {
     msm_reduce_segment_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
-}
-
-__global__ void __launch_bounds__(128) msm_sum_groups_kernel(const MsmSumArgs a) {
-    msm_sum_groups_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void __launch_bounds__(128) msm_finalize_kernel(const MsmFinalArgs a) {
@@ -319,45 +346,46 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_CUDA_TRY(cudaEventRecord(w.ev_sorted[set], sp));
         ZKB_CUDA_TRY(cudaStreamWaitEvent(s, w.ev_sorted[set], 0));
     }
-    uint32_t chunk0 = g.chunk0;
-    if (!c.msm_chunk_override)
-        while (chunk0 > 16 && valid / chunk0 < 147456) chunk0 >>= 1;  // few entries: shorter chains, more threads
-    {
-        const uint64_t t0 = (valid + chunk0 - 1) / chunk0 + 1;  // level-0 threads: two partial entries each
-        for (int i = 0; i < 2; ++i) {
-            ZKB_TRY(w.pk[i].reserve(2 * t0 * 4));
-            ZKB_TRY(w.pv[i].reserve(2 * t0 * 128));
-        }
+    // level-0 chunk: all threads do the same amount of work, so the grid is cut to a whole number of waves (4 CTAs of 128
+    // threads per SM) — a last wave that is 25 % full costs as much as a full one (2^19 points: 3.2 waves of chunk 32 -> 1 wave
+    // of chunk 104)
+    const uint64_t wave_threads = (uint64_t)c.sm_count * 4 * MSM_ACC_CTA;
+    uint64_t waves = (valid + wave_threads * 128 - 1) / (wave_threads * 128);
+    if (waves < 1) waves = 1;
+    uint32_t chunk0 = c.msm_chunk_override ? c.msm_chunk_override : (uint32_t)((valid + waves * wave_threads - 1) / (waves * wave_threads));
+    if (!c.msm_chunk_override) chunk0 = chunk0 < 16 ? 16 : (chunk0 > 128 ? 128 : chunk0);
+    static const int tree_max_waves = getenv("ZKB_MSM_TREE_WAVES") ? atoi(getenv("ZKB_MSM_TREE_WAVES")) : 1;
+    const MsmAccPlan plan = msm_acc_plan(valid, chunk0, waves > (uint64_t)tree_max_waves);
+    for (int i = 0; i < 2; ++i) {
+        ZKB_TRY(w.pk[i].reserve(plan.partials0 * 4 + 64));
+        ZKB_TRY(w.pv[i].reserve(plan.partials0 * 128 + 128));
     }
-    // ---- 3. accumulate (levels)
+    // ---- 3. accumulate (levels): every CTA leaves two partial entries, so the list shrinks by chunk x 64 per level
     {
         ProfScope prof("msm_accumulate", s);
         ZKB_CUDA_TRY(cudaMemsetAsync(bucket_acc, 0, bucket_bytes, s));
         uint64_t count = valid;
-        int level = 0, pp = 0;
-        while (count > 0) {
+        int pp = 0;
+        for (uint32_t level = 0; level < plan.levels; ++level) {
             MsmAccArgs a{};
-            const bool last = level > 0 && count <= g.last_max;
             a.keys = level == 0 ? sk : w.pk[pp ^ 1].as<uint32_t>();
             a.vals = sv;
             a.bases = table ? table->rows : d_bases;
             a.pin = w.pv[pp ^ 1].as<uint4>();
             a.count = count;
-            a.chunk = last ? (uint32_t)count : (level == 0 ? chunk0 : msm_chunk_up(count, g.chunk_up));
+            a.chunk = plan.chunk[level];
             a.invalid_key = g.invalid_key;
-            a.last_level = last ? 1 : 0;
+            a.last_level = level + 1 == plan.levels ? 1 : 0;
             a.buckets = bucket_acc;
             a.pkeys_out = w.pk[pp].as<uint32_t>();
             a.pvals_out = w.pv[pp].as<uint4>();
-            const uint64_t nthreads = (count + a.chunk - 1) / a.chunk;
-            if (level == 0) msm_accumulate_kernel<true><<<blocks_for(nthreads, 128), 128, 0, s>>>(a);
-            else msm_accumulate_kernel<false><<<blocks_for(nthreads, 128), 128, 0, s>>>(a);
+            if (level == 0 && plan.direct0) msm_accumulate_direct_kernel<true><<<(unsigned)plan.ctas[0], MSM_ACC_CTA, 0, s>>>(a);
+            else if (level == 0) msm_accumulate_kernel<true><<<(unsigned)plan.ctas[level], MSM_ACC_CTA, 0, s>>>(a);
+            else msm_accumulate_kernel<false><<<(unsigned)plan.ctas[level], MSM_ACC_CTA, 0, s>>>(a);
             count_launch();
             ZKB_CUDA_TRY(cudaGetLastError());
-            if (last) break;
-            count = 2 * nthreads;
+            count = (level == 0 && plan.direct0) ? plan.partials0 : 2 * plan.ctas[level];
             pp ^= 1;
-            ++level;
         }
     }
     if (!(phase & MSM_FIRST)) {  // fold this slice's buckets into the main array
@@ -384,11 +412,11 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.total_sets * J, 128), 128, 0, s>>>(r);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
-        while (J > 1) {
-            uint32_t grp = J >= g.sum_group ? g.sum_group : (uint32_t)J;
-            uint64_t Jn = J / grp;
-            MsmSumArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), (uint64_t)g.total_sets * Jn, grp};
-            msm_sum_groups_kernel<<<blocks_for(sa.out_count, 128), 128, 0, s>>>(sa);
+        while (J > 1) {   // CTA-cooperative sums: one or two launches
+            const uint32_t grp = J <= (uint64_t)MSM_ACC_CTA * 8 ? (uint32_t)((J + MSM_ACC_CTA - 1) / MSM_ACC_CTA) : 8u;
+            const uint64_t Jn = (J + (uint64_t)MSM_ACC_CTA * grp - 1) / ((uint64_t)MSM_ACC_CTA * grp);
+            MsmSumTreeArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), J, Jn, grp};
+            msm_sum_tree_kernel<<<(unsigned)((uint64_t)g.total_sets * Jn), MSM_ACC_CTA, 0, s>>>(sa);
             count_launch();
             ZKB_CUDA_TRY(cudaGetLastError());
             cur ^= 1;

@@ -11,10 +11,12 @@
 //                 balanced for ANY digit distribution (witness-like columns put most points in a few buckets).
 //                 A thread sums each run of equal keys with mixed additions (XYZZ accumulator).  Runs strictly
 //                 inside a chunk are complete buckets and are written to the bucket array; the first and last
-//                 run of a chunk may continue in the neighbours and go to a (key, partial) list, which is
-//                 reduced by the same routine one level up (full XYZZ adds) until one thread remains.
+//                 run of a chunk may continue in the neighbours: the threads of a CTA combine theirs by a tree in
+//                 shared memory (warp-/CTA-cooperative XYZZ additions), the CTA's own first and last run go to a
+//                 (key, partial) list reduced by the same routine one level up until one CTA remains.
 //   4. reduce   : per window sum_b (b+1)*B[b] by segments: running sums inside a segment of m buckets, plus
-//                 (segment offset)*(segment sum) by a short double-and-add; segment results are tree-summed.
+//                 (segment offset)*(segment sum) by a short double-and-add; segment results are summed by
+//                 CTA-cooperative trees.
 //   5. the W window sums (128 B each) go to the host, which does the c-bit Horner combination and the final
 //                 normalisation (north_star: "tiny bucket sums combined on the host").
 #pragma once
@@ -102,68 +104,137 @@ struct MsmAccArgs {
     uint64_t count;         // entries at this level
     uint32_t chunk;         // S
     uint32_t invalid_key;
-    uint32_t last_level;    // single thread: head/tail are complete and go to the bucket array
+    uint32_t last_level;    // single CTA: its head/tail are complete and go to the bucket array
     uint4* buckets;         // XYZZ [nbuckets], zero-initialised
-    uint32_t* pkeys_out;    // [2 * nthreads]
-    uint4* pvals_out;       // XYZZ [2 * nthreads]
+    uint32_t* pkeys_out;    // [2 * CTAs]
+    uint4* pvals_out;       // XYZZ [2 * CTAs]
 };
 
 ZKB_HD void msm_store_xyzz(uint4* base, uint64_t idx, const XYZZ& p) { p.store(base + 8 * idx); }
 ZKB_HD XYZZ msm_load_xyzz(const uint4* base, uint64_t idx) { return XYZZ::load(base + 8 * idx); }
 
-template <bool LEVEL0>
-ZKB_HD void msm_accumulate_thread(const MsmAccArgs& a, uint64_t t) {
-    const uint64_t lo = t * a.chunk;
-    if (lo >= a.count) return;
-    const uint64_t hi = lo + a.chunk < a.count ? lo + a.chunk : a.count;
-    XYZZ acc = XYZZ::identity();
-    uint32_t cur = MSM_INVALID_KEY;
-    uint32_t runs_done = 0;       // completed runs before the current one
-    uint32_t head_key = MSM_INVALID_KEY, tail_key = MSM_INVALID_KEY;
-    XYZZ tail = XYZZ::identity();
-    // level 0 keeps the accumulator lazy (coordinates < 2p, see xyzz_add_mixed_lazy); it becomes canonical when it leaves
-    auto out = [](const XYZZ& p) { return LEVEL0 ? xyzz_canon(p) : p; };
+// One CTA of MSM_ACC_CTA threads.  Phase 1: every thread sums its chunk; runs strictly inside the chunk are complete buckets
+// (stored), the first and the last run (which may continue in the neighbouring chunks) are left as the thread's SUMMARY in shared
+// memory: skey / sval [2 tid] = head run, [2 tid + 1] = tail run (INVALID key = absent; a chunk with one run has a head only).
+// Phase 2: the summaries of the CTA are combined by a binary tree (log2 MSM_ACC_CTA steps, at most one full addition per
+// combination): a run that turns out to lie strictly inside the combined range is complete and is stored, so the CTA ends
+// with ONE head and ONE tail.  Phase 3: thread 0 writes them to the partial list of the next level (2 entries per CTA — the
+// list shrinks by chunk x 64 per level, so two or three launches finish any MSM), or to the buckets when this CTA is the last.
+// Every bucket is written exactly once over all levels.
+constexpr uint32_t MSM_ACC_CTA = 128;
 
-    for (uint64_t i = lo; i < hi; ++i) {
-        uint32_t k = a.keys[i];
-        if (k >= a.invalid_key) {
-            if (LEVEL0) break;   // sorted: only invalid entries follow
-            continue;            // partial lists carry holes
-        }
-        if (k != cur) {
-            if (cur != MSM_INVALID_KEY) {
-                if (runs_done == 0) {                      // first run of the chunk: may continue to the left
-                    if (a.last_level) msm_store_xyzz(a.buckets, cur, out(acc));
-                    else { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, out(acc)); }
-                } else {
-                    msm_store_xyzz(a.buckets, cur, out(acc));   // strictly interior run == complete bucket
+template <bool LEVEL0>
+ZKB_HD void msm_acc_phase_chunk(const MsmAccArgs& a, uint64_t t, uint32_t tid, uint32_t* skey, uint4* sval) {
+    const uint64_t lo = t * a.chunk;
+    uint32_t head_key = MSM_INVALID_KEY, tail_key = MSM_INVALID_KEY;
+    if (lo < a.count) {
+        const uint64_t hi = lo + a.chunk < a.count ? lo + a.chunk : a.count;
+        XYZZ acc = XYZZ::identity();
+        uint32_t cur = MSM_INVALID_KEY;
+        uint32_t runs_done = 0;       // completed runs before the current one
+        // level 0 keeps the accumulator lazy (coordinates < 2p, see xyzz_add_mixed_lazy); it becomes canonical when it leaves
+        auto out = [](const XYZZ& p) { return LEVEL0 ? xyzz_canon(p) : p; };
+        for (uint64_t i = lo; i < hi; ++i) {
+            uint32_t k = a.keys[i];
+            if (k >= a.invalid_key) {
+                if (LEVEL0) break;   // sorted: only invalid entries follow
+                continue;            // partial lists carry holes
+            }
+            if (k != cur) {
+                if (cur != MSM_INVALID_KEY) {
+                    if (runs_done == 0) { head_key = cur; msm_store_xyzz(sval, 2 * tid, out(acc)); }  // may continue to the left
+                    else msm_store_xyzz(a.buckets, cur, out(acc));   // strictly interior run == complete bucket
+                    ++runs_done;
                 }
-                ++runs_done;
+                acc = XYZZ::identity();
+                cur = k;
             }
-            acc = XYZZ::identity();
-            cur = k;
+            if (LEVEL0) {
+                uint32_t v = a.vals[i];
+                Affine p = affine_load(a.bases + 4 * (uint64_t)(v & 0x7fffffffu));
+                if (!p.is_identity()) {
+                    if (v >> 31) p.y = fp_neg(p.y);
+                    xyzz_add_mixed_lazy(acc, p.x, p.y);
+                }
+            } else {
+                xyzz_add(acc, msm_load_xyzz(a.pin, i));
+            }
         }
-        if (LEVEL0) {
-            uint32_t v = a.vals[i];
-            Affine p = affine_load(a.bases + 4 * (uint64_t)(v & 0x7fffffffu));
-            if (!p.is_identity()) {
-                if (v >> 31) p.y = fp_neg(p.y);
-                xyzz_add_mixed_lazy(acc, p.x, p.y);
-            }
+        if (cur != MSM_INVALID_KEY) {
+            if (runs_done == 0) { head_key = cur; msm_store_xyzz(sval, 2 * tid, out(acc)); }
+            else { tail_key = cur; msm_store_xyzz(sval, 2 * tid + 1, out(acc)); }
+        }
+    }
+    skey[2 * tid] = head_key;
+    skey[2 * tid + 1] = tail_key;
+}
+
+// Throughput regime (many waves of CTAs): no tree — every thread writes its summary straight to the partial list (two entries
+// per thread, slots 2t and 2t+1), and the next level, which is small, does the combining.  `skey` / `sval` of the chunk phase
+// then point into the global lists.
+template <bool LEVEL0>
+ZKB_HD void msm_acc_thread_direct(const MsmAccArgs& a, uint64_t t) {
+    msm_acc_phase_chunk<LEVEL0>(a, t, 0, a.pkeys_out + 2 * t, a.pvals_out + 16 * t);
+}
+
+// tree step d: summary[l] (threads l .. l+d-1) absorbs summary[l+d] (threads l+d .. l+2d-1), l = 2 d j.  The combinations of a
+// step are done by the FIRST nthreads / 2d threads (pair j by thread j), so the full additions fill whole warps instead of
+// being spread one lane per warp.
+ZKB_HD void msm_acc_phase_combine(const MsmAccArgs& a, uint32_t tid, uint32_t d, uint32_t nthreads, uint32_t* skey, uint4* sval) {
+    const uint32_t left = 2 * d * tid;
+    if (left + d >= nthreads) return;
+    const uint32_t ia = 2 * left, ib = 2 * (left + d);
+    const uint32_t ah = skey[ia], at = skey[ia + 1], bh = skey[ib], bt = skey[ib + 1];
+    if (bh == MSM_INVALID_KEY) return;  // right half empty
+    auto copy = [&](uint32_t dst, uint32_t src) {
+        for (int q = 0; q < 8; ++q) sval[8 * dst + q] = sval[8 * src + q];
+    };
+    if (ah == MSM_INVALID_KEY) {        // left half empty
+        skey[ia] = bh; skey[ia + 1] = bt;
+        copy(ia, ib);
+        if (bt != MSM_INVALID_KEY) copy(ia + 1, ib + 1);
+        return;
+    }
+    const bool a_multi = at != MSM_INVALID_KEY, b_multi = bt != MSM_INVALID_KEY;
+    const uint32_t a_last = a_multi ? at : ah;
+    if (a_last == bh) {                 // the run continues across the boundary
+        XYZZ m = msm_load_xyzz(sval, a_multi ? ia + 1 : ia);
+        xyzz_add(m, msm_load_xyzz(sval, ib));
+        if (a_multi && b_multi) {       // now strictly inside the combined range: complete
+            msm_store_xyzz(a.buckets, a_last, m);
+            skey[ia + 1] = bt;
+            copy(ia + 1, ib + 1);
+        } else if (a_multi) {
+            msm_store_xyzz(sval, ia + 1, m);
         } else {
-            xyzz_add(acc, msm_load_xyzz(a.pin, i));
+            msm_store_xyzz(sval, ia, m);
+            if (b_multi) { skey[ia + 1] = bt; copy(ia + 1, ib + 1); }
+        }
+    } else {
+        if (a_multi) msm_store_xyzz(a.buckets, at, msm_load_xyzz(sval, ia + 1));
+        if (b_multi) {
+            msm_store_xyzz(a.buckets, bh, msm_load_xyzz(sval, ib));
+            skey[ia + 1] = bt;
+            copy(ia + 1, ib + 1);
+        } else {
+            skey[ia + 1] = bh;
+            copy(ia + 1, ib);
         }
     }
-    if (cur != MSM_INVALID_KEY) {
-        if (a.last_level) msm_store_xyzz(a.buckets, cur, out(acc));
-        else if (runs_done == 0) { head_key = cur; msm_store_xyzz(a.pvals_out, 2 * t, out(acc)); }
-        else { tail_key = cur; tail = out(acc); }
+}
+
+// thread 0, after the tree
+ZKB_HD void msm_acc_phase_emit(const MsmAccArgs& a, uint64_t cta, const uint32_t* skey, const uint4* sval) {
+    const uint32_t hk = skey[0], tk = skey[1];
+    if (a.last_level) {
+        if (hk != MSM_INVALID_KEY) msm_store_xyzz(a.buckets, hk, msm_load_xyzz(sval, 0));
+        if (tk != MSM_INVALID_KEY) msm_store_xyzz(a.buckets, tk, msm_load_xyzz(sval, 1));
+        return;
     }
-    if (!a.last_level) {
-        a.pkeys_out[2 * t] = head_key;
-        a.pkeys_out[2 * t + 1] = tail_key;
-        if (tail_key != MSM_INVALID_KEY) msm_store_xyzz(a.pvals_out, 2 * t + 1, tail);
-    }
+    a.pkeys_out[2 * cta] = hk;
+    a.pkeys_out[2 * cta + 1] = tk;
+    if (hk != MSM_INVALID_KEY) msm_store_xyzz(a.pvals_out, 2 * cta, msm_load_xyzz(sval, 0));
+    if (tk != MSM_INVALID_KEY) msm_store_xyzz(a.pvals_out, 2 * cta + 1, msm_load_xyzz(sval, 1));
 }
 
 // ---- slice merge: main[b] += part[b] -----------------------------------------------------------------------------------
@@ -224,18 +295,30 @@ ZKB_HD void msm_reduce_segment_thread(const MsmReduceArgs& a, uint64_t t) {
     msm_store_xyzz(a.seg_out, t, acc);
 }
 
-// out[t] = sum_{i<g} in[t*g + i]   (tree level of the segment sum)
-struct MsmSumArgs {
-    const uint4* in;
-    uint4* out;
-    uint64_t out_count;
+// CTA-cooperative sum: CTA (set, tile) adds up to MSM_ACC_CTA * group consecutive elements of its set — `group` serial
+// additions per thread, then a log2(MSM_ACC_CTA)-step tree in shared memory — so a whole set of segment sums is folded in one
+// or two launches whose dependent chains are ~15 additions long (the serial fan-in-8 chain it replaces took five launches).
+struct MsmSumTreeArgs {
+    const uint4* in;     // XYZZ [sets * in_per_set]
+    uint4* out;          // XYZZ [sets * out_per_set]
+    uint64_t in_per_set, out_per_set;
     uint32_t group;
 };
-ZKB_HD void msm_sum_groups_thread(const MsmSumArgs& a, uint64_t t) {
-    if (t >= a.out_count) return;
-    XYZZ acc = msm_load_xyzz(a.in, t * a.group);
-    for (uint32_t i = 1; i < a.group; ++i) xyzz_add(acc, msm_load_xyzz(a.in, t * a.group + i));
-    msm_store_xyzz(a.out, t, acc);
+ZKB_HD void msm_sum_tree_phase_load(const MsmSumTreeArgs& a, uint64_t cta, uint32_t tid, uint4* sval) {
+    const uint64_t set = cta / a.out_per_set, tile = cta % a.out_per_set;
+    const uint64_t first = (tile * MSM_ACC_CTA + tid) * a.group;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t i = 0; i < a.group && first + i < a.in_per_set; ++i) xyzz_add(acc, msm_load_xyzz(a.in, set * a.in_per_set + first + i));
+    msm_store_xyzz(sval, tid, acc);
+}
+ZKB_HD void msm_sum_tree_phase_step(uint32_t tid, uint32_t d, uint4* sval) {
+    if (tid >= d) return;
+    XYZZ x = msm_load_xyzz(sval, tid);
+    xyzz_add(x, msm_load_xyzz(sval, tid + d));
+    msm_store_xyzz(sval, tid, x);
+}
+ZKB_HD void msm_sum_tree_phase_store(const MsmSumTreeArgs& a, uint64_t cta, const uint4* sval) {
+    msm_store_xyzz(a.out, cta, msm_load_xyzz(sval, 0));
 }
 
 // ---- window combination + normalisation (host side of step 5; also usable on the device) ----------------------------

@@ -15,10 +15,7 @@ struct MsmGeometry {
     uint32_t invalid_key;  // == nbuckets
     uint32_t key_bits;     // radix-sort bits covering [0, invalid_key]
     uint32_t chunk0;       // entries per thread, level 0
-    uint32_t chunk_up;     // entries per thread, levels >= 1
-    uint32_t last_max;     // a level with <= last_max entries is finished by one thread
     uint32_t log_m;        // bucket-reduction segment length 2^log_m
-    uint32_t sum_group;    // tree fan-in of the segment sum
 };
 
 // cost model: W * (n mixed adds + ~2.8 * 2^(c-1) full-add equivalents for the reduction)
@@ -42,13 +39,42 @@ inline uint32_t msm_pick_window_table(uint64_t n) {
         double cost = (double)w * (double)n + 2.8 * (double)(1ull << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
     }
+    if (const char* e = getenv("ZKB_MSM_TABLE_C_DELTA")) {  // experiment hook: shift the table window width
+        int v = (int)best_c + atoi(e);
+        best_c = (uint32_t)(v < 4 ? 4 : (v > 22 ? 22 : v));
+    }
     return best_c;
 }
 
-// entries per thread at partial levels >= 1: long chunks while the level is large enough to be throughput bound (fewer
-// levels, less total work), short ones when only a few thousand partials remain and the dependent chain of full additions
-// (~4 us each) is what the MSM waits for — this tail was ~0.5 ms of a 1.3 ms 2^16-point MSM
-inline uint32_t msm_chunk_up(uint64_t count, uint32_t chunk_up_large) { return count >= (1u << 20) ? chunk_up_large : 8; }
+// Launch plan of the accumulation levels (msm.cuh): level 0 cuts `entries` sorted entries into chunks of chunk0 per thread, 128
+// threads per CTA; every CTA leaves two partial entries for the next level; a level that fits one CTA is the last.
+// direct0: level 0 runs without the in-CTA tree (throughput regime: its threads write two partial entries each and the
+// next, much smaller, level combines them — the tree would keep three of a CTA's four warps idle for ~2 % of a long chunk loop).
+struct MsmAccPlan {
+    uint32_t levels;
+    uint32_t chunk[8];
+    uint64_t ctas[8];
+    bool direct0;
+    uint64_t partials0;   // partial entries level 0 leaves
+};
+inline MsmAccPlan msm_acc_plan(uint64_t entries, uint32_t chunk0, bool direct0 = false) {
+    MsmAccPlan p{};
+    uint64_t count = entries;
+    uint32_t chunk = chunk0 ? chunk0 : 1;
+    while (count > 0 && p.levels < 8) {
+        if (p.levels > 0) chunk = count <= 128ull * 16 ? (uint32_t)((count + 127) / 128) : 16u;
+        const uint64_t threads = (count + chunk - 1) / chunk;
+        const uint64_t ctas = (threads + 127) / 128;
+        p.chunk[p.levels] = chunk;
+        p.ctas[p.levels] = ctas;
+        const bool direct = p.levels == 0 && direct0 && ctas > 1;
+        if (p.levels == 0) { p.direct0 = direct; p.partials0 = direct ? 2 * ctas * 128 : 2 * ctas; }
+        ++p.levels;
+        if (ctas == 1) break;
+        count = direct ? 2 * ctas * 128 : 2 * ctas;
+    }
+    return p;
+}
 
 // n = points per column.  For a batch of ncols columns the bucket array holds ncols * bucket_sets sets.
 inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t chunk_override = 0, bool table = false,
@@ -71,18 +97,14 @@ inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t ch
     const uint64_t total = (uint64_t)g.nwin * (n ? n : 1) * g.ncols;
     while (ch > 16 && total / ch < 147456) ch >>= 1;
     g.chunk0 = chunk_override ? chunk_override : ch;
-    g.chunk_up = 32;
-    g.last_max = 16;
     // bucket reduction: ~2^15 segment threads keep the SMs busy while the per-thread chain (2m adds + the (c-1)-bit offset
     // multiplication) stays short; measured on B200 (profiles/r1_tuning.txt): 2^19 buckets -> m = 16, 2^21 -> m = 64.
     uint32_t lb = g.c - 1;
     uint32_t total_log = lb;  // log2 of all buckets of all sets (rounded down)
     while ((1ull << (total_log + 1)) <= ((uint64_t)g.total_sets << lb)) ++total_log;
-    g.log_m = total_log > 18 ? (total_log - 15 > 7 ? 7 : total_log - 15) : (lb > 6 ? 3 : 0);
+    g.log_m = total_log > 18 ? (total_log - 15 > 7 ? 7 : total_log - 15) : (lb > 6 ? (total_log > 16 ? 3 : 2) : 0);
     if (g.log_m > lb) g.log_m = lb;
-    g.sum_group = 8;
     if (const char* e = getenv("ZKB_MSM_LOG_M")) { uint32_t v = (uint32_t)atoi(e); if (v <= lb) g.log_m = v; }
-    if (const char* e = getenv("ZKB_MSM_SUM_GROUP")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2) g.sum_group = v; }
     return g;
 }
 

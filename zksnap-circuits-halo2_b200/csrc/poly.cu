@@ -5,6 +5,7 @@
 //   commit_lagrange -> lagrange_to_coeff -> coeff_to_extended -> eval_polynomial -> kate_division -> commit
 // into device-only steps: one upload per polynomial, 96-byte commitments and 32-byte evaluations coming back
 // (coset-resident pipeline, eval / division helpers, proving-key residency).
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -294,10 +295,66 @@ int zkb_poly_upload(const uint64_t* values, size_t n, uint64_t* handle) {
     ZKB_TRY(new_poly(n, &p, handle));
     if (n) {
         cudaError_t e = cudaMemcpyAsync(p->buf.p, values, n * 32, cudaMemcpyHostToDevice, ctx().stream);
+        count_h2d(n * 32);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);  // the caller may reuse `values` on return
         if (e != cudaSuccess) { set_error("polynomial upload failed: %s", cudaGetErrorString(e)); return ZKB_ERR_CUDA; }
     }
     return ZKB_OK;
+}
+
+// n raw Fr (32 B Montgomery limbs each: the element encoding of SerdeFormat::RawBytesUnchecked, which is how the reference
+// stores its proving keys, /root/reference/aggregator/src/wrapper.rs:970-988) from `path` at byte `offset` straight into a
+// polynomial handle: read(2) into one pinned buffer while the other is in flight to the device.
+int zkb_poly_load_file(const char* path, uint64_t offset, size_t n, uint64_t* handle) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!handle || !path) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s", path); return ZKB_ERR_ARG; }
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    if (fseeko(f, 0, SEEK_END) != 0) { set_error("cannot seek in %s", path); return ZKB_ERR_ARG; }
+    const uint64_t fsize = (uint64_t)ftello(f);
+    if (offset > fsize || (uint64_t)n * 32 > fsize - offset) {
+        set_error("%s holds %llu bytes, %zu field elements at offset %llu need %llu", path, (unsigned long long)fsize, n,
+                  (unsigned long long)offset, (unsigned long long)(offset + (uint64_t)n * 32));
+        return ZKB_ERR_ARG;
+    }
+    if (fseeko(f, (off_t)offset, SEEK_SET) != 0) { set_error("cannot seek in %s", path); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(new_poly(n, &p, handle));
+    const size_t chunk = (size_t)16 << 20;
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = ctx().stream;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; ++i) {
+            if (pin[i]) cudaFreeHost(pin[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+        if (code != ZKB_OK) { pool_release(p->buf); delete p; poly_map().erase(*handle); *handle = 0; }
+        return code;
+    };
+    const size_t total = n * 32;
+    const size_t pin_bytes = total < chunk ? (total ? total : 32) : chunk;
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMallocHost(&pin[i], pin_bytes) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pinned staging allocation failed");
+            return cleanup(ZKB_ERR_OOM);
+        }
+    }
+    for (size_t done = 0, i = 0; done < total; ++i) {
+        const size_t len = total - done < chunk ? total - done : chunk;
+        if (i >= 2 && cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { set_error("polynomial upload failed"); return cleanup(ZKB_ERR_CUDA); }
+        if (fread(pin[i & 1], 1, len, f) != len) { set_error("short read from %s", path); return cleanup(ZKB_ERR_ARG); }
+        cudaError_t e = cudaMemcpyAsync(p->buf.as<char>() + done, pin[i & 1], len, cudaMemcpyHostToDevice, st);
+        count_h2d(len);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
+        if (e != cudaSuccess) { set_error("polynomial upload failed: %s", cudaGetErrorString(e)); return cleanup(ZKB_ERR_CUDA); }
+        done += len;
+    }
+    return cleanup(ZKB_OK);
 }
 
 int zkb_poly_alloc(size_t n, uint64_t* handle) {
@@ -307,6 +364,22 @@ int zkb_poly_alloc(size_t n, uint64_t* handle) {
     Poly* p;
     ZKB_TRY(new_poly(n, &p, handle));
     ZKB_CUDA_TRY(cudaMemsetAsync(p->buf.p, 0, n ? n * 32 : 32, ctx().stream));
+    return ZKB_OK;
+}
+
+// poly[offset .. offset + n) = values: the prover overwrites the last blinding_factors + 1 rows of a product column (computed on
+// the device) with its random blinding values before committing
+int zkb_poly_write(uint64_t handle, size_t offset, const uint64_t* values, size_t n) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    Poly* p;
+    ZKB_TRY(find_poly(handle, &p));
+    if (offset > p->n || n > p->n - offset) { set_error("write [%zu, %zu) into a polynomial of %zu elements", offset, offset + n, (size_t)p->n); return ZKB_ERR_ARG; }
+    if (n == 0) return ZKB_OK;
+    if (!values) { set_error("values is NULL"); return ZKB_ERR_ARG; }
+    ZKB_CUDA_TRY(cudaMemcpyAsync(p->buf.as<char>() + offset * 32, values, n * 32, cudaMemcpyHostToDevice, ctx().stream));
+    count_h2d(n * 32);
+    ZKB_CUDA_TRY(cudaStreamSynchronize(ctx().stream));
     return ZKB_OK;
 }
 
@@ -544,6 +617,7 @@ static int graph_launch(const GraphPlan& plan, const std::vector<const uint4*>& 
     if (!queries.empty()) memcpy(host.data() + o_q, queries.data(), queries.size() * sizeof(GraphQuery));
     ZKB_TRY(ws.reserve(total));
     ZKB_CUDA_TRY(cudaMemcpyAsync(ws.p, host.data(), total, cudaMemcpyHostToDevice, s));  // pageable source: staged before return
+    count_h2d(total);
     char* d = reinterpret_cast<char*>(ws.p);
     GraphArgs a{};
     a.prog = reinterpret_cast<const uint4*>(d + o_prog);
@@ -641,7 +715,9 @@ int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, ui
     char* d = reinterpret_cast<char*>(w.tmp.p);
     cudaStream_t s = ctx().stream;
     ZKB_CUDA_TRY(cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, s));
+    count_h2d(n * 32);
     ZKB_CUDA_TRY(cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, s));
+    count_h2d(n * 32);
     field_vec_op_kernel<<<nblk(n, 128), 128, 0, s>>>(field, op, reinterpret_cast<const uint4*>(d), reinterpret_cast<const uint4*>(d + n * 32),
                                                      reinterpret_cast<uint4*>(d + 2 * n * 32), n);
     count_launch();

@@ -172,6 +172,19 @@ class Polynomial:
         check(lib().zkb_poly_download(self._h, _p(out), out.shape[0]))
         return out
 
+    def write(self, offset: int, values: np.ndarray) -> "Polynomial":
+        """self[offset : offset + len(values)] = values (e.g. the random blinding rows of a product column)"""
+        v = _fr(values, "values")
+        check(lib().zkb_poly_write(self._h, offset, _p(v), v.shape[0]))
+        return self
+
+    @classmethod
+    def load_file(cls, path: str, offset: int, n: int) -> "Polynomial":
+        """n raw Fr (RawBytesUnchecked element encoding) from a file straight into HBM (proving-key residency)"""
+        h = ctypes.c_uint64(0)
+        check(lib().zkb_poly_load_file(path.encode(), offset, n, ctypes.byref(h)))
+        return cls(_handle=h.value)
+
     def slice(self, offset: int, n: int) -> "Polynomial":
         """A new resident polynomial holding self[offset : offset + n] (the pieces of h(X) after extended_to_coeff)."""
         h = ctypes.c_uint64(0)
