@@ -179,6 +179,13 @@ class Polynomial:
         return self
 
     @classmethod
+    def zeros(cls, n: int) -> "Polynomial":
+        """n zero elements allocated and cleared on the device (nothing crosses PCIe)"""
+        h = ctypes.c_uint64(0)
+        check(lib().zkb_poly_alloc(n, ctypes.byref(h)))
+        return cls(_handle=h.value)
+
+    @classmethod
     def load_file(cls, path: str, offset: int, n: int) -> "Polynomial":
         """n raw Fr (RawBytesUnchecked element encoding) from a file straight into HBM (proving-key residency)"""
         h = ctypes.c_uint64(0)

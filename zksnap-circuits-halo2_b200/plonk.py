@@ -73,7 +73,8 @@ class Circuit(NamedTuple):
         return 2                        # cs.degree() - 2
 
     def queries(self):
-        """(kind, column, rotation) of every column query of the gates, first-seen order (the prover's evaluation order)"""
+        """(kind, column, rotation) of every column query of the gates and the permutation, first-seen order (the prover's
+        evaluation order)"""
         seen = []
 
         def walk(e):
@@ -87,6 +88,9 @@ class Circuit(NamedTuple):
 
         for g in self.gates:
             walk(g)
+        for kind, col in self.permutation_columns:   # enable_equality queries the column at the current rotation
+            if (kind, col, 0) not in seen:
+                seen.append((kind, col, 0))
         return seen
 
 
@@ -254,8 +258,7 @@ def permutation_commit(params: ParamsKZG, pk: ProvingKey, advice_lagrange: list,
         gd.add_expression(den)
         adv = [advice_lagrange[cols[j][1]] for j in chunk]
         ch = np.stack([mont(beta), mont(gamma)])
-        zn = Polynomial(np.zeros((n, 4), dtype=np.uint64))
-        zd = Polynomial(np.zeros((n, 4), dtype=np.uint64))
+        zn, zd = Polynomial.zeros(n), Polynomial.zeros(n)
         gn.evaluate(zn, fixed=[pk.id_lagrange[j] for j in chunk], advice=adv, challenges=ch, rot_scale=1)
         gd.evaluate(zd, fixed=[pk.sigma_lagrange[j] for j in chunk], advice=adv, challenges=ch, rot_scale=1)
         zd.batch_invert()
@@ -315,7 +318,7 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, advice_lagrange_host: list, 
     advice_cosets = [p.coeff_to_extended(d) for p in advice_polys]
     z_cosets = [p.coeff_to_extended(d) for p in z_polys]
     q = ev.QuotientEvaluator(c.gates, dict(columns=c.permutation_columns, chunk_len=c.chunk_len, last_rotation=-(c.blinding_factors + 1)))
-    h = Polynomial(np.zeros((N, 4), dtype=np.uint64))
+    h = Polynomial.zeros(N)
     q.evaluate_h(h, pk.fixed_cosets, advice_cosets, [], None, mont(y), mont(beta), mont(gamma), None, 1 << (d.extended_k - c.k),
                  pk.l0, pk.l_last, pk.l_active, pk.x_coset, pk.sigma_cosets, z_cosets)
     if "after_h" in hooks:
