@@ -236,6 +236,16 @@ int zkb_poly_mul(uint64_t poly, uint64_t other);
 int zkb_poly_scale_add(uint64_t poly, const uint64_t k[4], uint64_t other);
 int zkb_poly_add_const(uint64_t poly, const uint64_t c[4]);
 int zkb_poly_prefix_product(uint64_t poly);
+/* plonk::lookup::prover::permute_expression_pair (halo2-axiom plonk/lookup/prover.rs; reached from create_proof,
+ * /root/reference/aggregator/src/wrapper.rs:129-137) on resident columns.  `input` / `table`: the theta-compressed input and table
+ * expressions (Lagrange basis, same length); rows [0, usable_rows) take part.  New handles receive
+ *   permuted_input  A' = the input values sorted ascending by canonical value (Fr's Ord),
+ *   permuted_table  S' with S'[i] = A'[i] wherever A'[i] != A'[i-1], and the table elements left over (ascending) on the repeated
+ *                   rows, assigned from the last repeated row backwards (upstream's `repeated_input_rows.pop()`),
+ * rows >= usable_rows are zero (the caller writes its random blinding rows with zkb_poly_write).  Fails with ZKB_ERR_ARG when an
+ * input value does not occur in the table (upstream: Error::ConstraintSystemFailure). */
+int zkb_lookup_permute_expression_pair(uint64_t input, uint64_t table, size_t usable_rows, uint64_t* permuted_input,
+                                       uint64_t* permuted_table);
 /* host-buffer forms of the three helpers (upload + op + download) */
 int zkb_fr_eval_polynomial(const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
 int zkb_fr_kate_division(const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* out /* n - 1 */);

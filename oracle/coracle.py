@@ -217,6 +217,18 @@ def fr_batch_invert(a: np.ndarray) -> np.ndarray:
     return a
 
 
+def permute_expression_pair(input_: np.ndarray, table: np.ndarray, usable_rows: int):
+    """-> (permuted_input, permuted_table), usable_rows elements each; raises ValueError when an input value is not in the table"""
+    a = np.ascontiguousarray(input_, dtype=np.uint64).reshape(-1, 4)
+    t = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1, 4)
+    oa, ot = _new(usable_rows, 4), _new(usable_rows, 4)
+    lib().zko_permute_expression_pair.restype = ctypes.c_int
+    rc = lib().zko_permute_expression_pair(_p(a), _p(t), ctypes.c_size_t(usable_rows), _p(oa), _p(ot))
+    if rc != 0:
+        raise ValueError("ConstraintSystemFailure" if rc == -1 else "malformed lookup")
+    return oa, ot
+
+
 def g1_fft_naive(points_aff: np.ndarray, omega: np.ndarray) -> np.ndarray:
     """best_fft with G = G1 by the DFT definition (O(n^2) scalar multiplications)."""
     p = np.ascontiguousarray(points_aff, dtype=np.uint64).reshape(-1, 8)

@@ -32,6 +32,7 @@
  *   arithmetic::eval_polynomial (Horner)                                               -> zko_fr_eval_polynomial
  *   arithmetic::kate_division(a, b): q_{n-2} = a_{n-1}, q_{i-1} = a_i + b q_i            -> zko_fr_kate_division
  *   ff::BatchInvert (zeros are skipped and stay zero)                                   -> zko_fr_batch_invert
+ *   plonk::lookup::prover::permute_expression_pair                                      -> zko_permute_expression_pair
  *   best_fft with G = G1 (FftGroup for curve points), by the DFT definition             -> zko_g1_fft_naive
  *   plonk::evaluation::GraphEvaluator::evaluate in evaluate_h's row loop (intermediates
  *       numbered as upstream numbers them, rotated rows by rem_euclid)                  -> zko_graph_evaluate
@@ -637,6 +638,59 @@ EXPORT void zko_fr_batch_invert(u64 *a, size_t n) {
     }
 }
 
+
+/* plonk::lookup::prover::permute_expression_pair (halo2-axiom plonk/lookup/prover.rs, un-vendored; restated from the published
+ * halo2 algorithm):
+ *   permuted_input = input[..usable_rows] sorted (Fr's Ord = canonical integer value)
+ *   leftover_table_map: BTreeMap value -> count over table[..usable_rows]
+ *   for every row: first occurrence of its value in permuted_input -> permuted_table[row] = value, one copy leaves the map
+ *                  (absent: Err(ConstraintSystemFailure), returns -1 here); otherwise the row is pushed on repeated_input_rows
+ *   for (value, count) in the map, ascending: count times permuted_table[repeated_input_rows.pop()] = value
+ * Outputs hold usable_rows elements each (the caller appends the blinding rows). */
+typedef struct { fe canon; fe mont; } pe_item;
+static int pe_cmp(const void *x, const void *y) {
+    const pe_item *a = (const pe_item *)x, *b = (const pe_item *)y;
+    for (int i = 3; i >= 0; --i) {
+        if (a->canon.l[i] != b->canon.l[i]) return a->canon.l[i] < b->canon.l[i] ? -1 : 1;
+    }
+    return 0;
+}
+EXPORT int zko_permute_expression_pair(const u64 *input, const u64 *table, size_t usable_rows, u64 *out_input, u64 *out_table) {
+    const size_t u = usable_rows;
+    if (u == 0) return 0;
+    pe_item *a = (pe_item *)malloc(sizeof(pe_item) * u), *t = (pe_item *)malloc(sizeof(pe_item) * u);
+    size_t *repeated = (size_t *)malloc(sizeof(size_t) * u);
+    unsigned char *taken = (unsigned char *)calloc(u, 1);
+    for (size_t i = 0; i < u; ++i) {
+        a[i].mont = *CFE(input + 4 * i); f_from_mont(&FR, &a[i].canon, &a[i].mont);
+        t[i].mont = *CFE(table + 4 * i); f_from_mont(&FR, &t[i].canon, &t[i].mont);
+    }
+    qsort(a, u, sizeof(pe_item), pe_cmp);
+    qsort(t, u, sizeof(pe_item), pe_cmp);   /* the BTreeMap's iteration order; equal keys are adjacent = its counts */
+    size_t nrep = 0;
+    int rc = 0;
+    for (size_t row = 0; row < u && rc == 0; ++row) {
+        *FE(out_input + 4 * row) = a[row].mont;
+        if (row == 0 || pe_cmp(&a[row], &a[row - 1]) != 0) {
+            *FE(out_table + 4 * row) = a[row].mont;
+            /* remove one instance from the map: the first not yet taken element equal to the value */
+            size_t lo = 0, hi = u;
+            while (lo < hi) { size_t mid = (lo + hi) / 2; if (pe_cmp(&t[mid], &a[row]) < 0) lo = mid + 1; else hi = mid; }
+            if (lo >= u || pe_cmp(&t[lo], &a[row]) != 0) rc = -1;
+            else taken[lo] = 1;   /* distinct input values hit distinct table values, so one copy each */
+        } else {
+            repeated[nrep++] = row;
+        }
+    }
+    for (size_t i = 0; i < u && rc == 0; ++i) {
+        if (taken[i]) continue;
+        if (nrep == 0) { rc = -2; break; }
+        *FE(out_table + 4 * repeated[--nrep]) = t[i].mont;
+    }
+    if (rc == 0 && nrep != 0) rc = -2;
+    free(a); free(t); free(repeated); free(taken);
+    return rc;
+}
 
 /* plonk::evaluation::GraphEvaluator::evaluate for every row idx of the extended domain, as evaluate_h calls it:
  *   values[idx] = graph.evaluate(data, fixed, advice, instance, challenges, beta, gamma, theta, y, &values[idx], idx, rot_scale, isize)

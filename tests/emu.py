@@ -189,3 +189,14 @@ def graph_evaluate(graph, fixed, advice, instance, challenges, beta, gamma, thet
                                       ctypes.c_uint32(cta_threads), info, ctypes.c_uint64(lo), ctypes.c_uint64(hi))
     del kg, ki
     return rc, out, list(info)
+
+
+def permute_expression_pair(input_, table, usable_rows):
+    a = np.ascontiguousarray(input_, dtype=np.uint64).reshape(-1, 4)
+    t = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1, 4)
+    oa, ot = np.zeros((usable_rows, 4), dtype=np.uint64), np.zeros((usable_rows, 4), dtype=np.uint64)
+    lib().zkb_emu_permute_expression_pair.restype = ctypes.c_int
+    rc = lib().zkb_emu_permute_expression_pair(_p(a), _p(t), ctypes.c_uint64(usable_rows), _p(oa), _p(ot))
+    if rc != 0:
+        raise ValueError("ConstraintSystemFailure")
+    return oa, ot

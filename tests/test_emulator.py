@@ -684,3 +684,23 @@ def test_graph_row_windows_random_programs(oracle, seed):
         rc, o, _ = emu.graph_evaluate(g, [fixed[0][idx]], [a[idx] for a in advice], [], None, sc[0], sc[1], sc[2], sc[3], rs,
                                       prev[r * rows:(r + 1) * rows], halo=(lo, hi))
         assert rc == 0 and (o == want[r * rows:(r + 1) * rows]).all()
+
+
+@pytest.mark.parametrize("u,distinct,big", [(1, 1, False), (9, 4, False), (300, 300, True), (1500, 33, True), (4000, 256, False)])
+def test_permute_expression_pair_device_phases_vs_oracle(oracle, u, distinct, big):
+    """lookup.cuh's per-thread phases (canonical copies, four limb-wise stable sorts, first-occurrence flags, table matching by
+    binary search, rank scans, leftover assignment) against the oracle's restatement of upstream's algorithm."""
+    from test_oracle import lookup_case
+    inp, tab = lookup_case(7 * u + distinct, u, distinct, big)
+    a = ints_to_limbs([R.to_mont(x, R.FR) for x in inp])
+    t = ints_to_limbs([R.to_mont(x, R.FR) for x in tab])
+    want = oracle.permute_expression_pair(a, t, u)
+    got = emu.permute_expression_pair(a, t, u)
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_permute_expression_pair_missing_value_emulated(oracle):
+    a = ints_to_limbs([R.to_mont(x, R.FR) for x in (1, 2, 9)])
+    t = ints_to_limbs([R.to_mont(x, R.FR) for x in (1, 2, 3)])
+    with pytest.raises(ValueError):
+        emu.permute_expression_pair(a, t, 3)

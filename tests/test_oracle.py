@@ -427,3 +427,54 @@ def test_published_halo2curves_montgomery_constants(oracle):
     one = np.array([[1, 0, 0, 0]], dtype=np.uint64)
     assert [int(x) for x in oracle.fr_to_mont(one)[0]] == fr["R"]
     assert [int(x) for x in oracle.vec_op("fq", "mul", np.array([fq["R2"]], dtype=np.uint64), one)[0]] == fq["R"]   # mont(R2, 1) = R
+
+
+# ---- lookup argument: permute_expression_pair ----------------------------------------------------------------------------------
+def py_permute_expression_pair(inp, tab, u):
+    """upstream's algorithm with Python containers (sorted list, Counter as the BTreeMap), on canonical integers"""
+    from collections import Counter
+    a = sorted(inp[:u])
+    left = Counter(tab[:u])
+    out_t, rep = [0] * u, []
+    for row, v in enumerate(a):
+        if row == 0 or v != a[row - 1]:
+            out_t[row] = v
+            if left.get(v, 0) == 0:
+                raise ValueError("ConstraintSystemFailure")
+            left[v] -= 1
+        else:
+            rep.append(row)
+    for v in sorted(left):
+        for _ in range(left[v]):
+            out_t[rep.pop()] = v
+    assert not rep
+    return a, out_t
+
+
+def lookup_case(seed, u, distinct, big=False):
+    import random
+    rnd = random.Random(seed)
+    pool = [rnd.randrange(R.FR) if big else rnd.randrange(1 << 20) for _ in range(distinct)]
+    tab = pool + [rnd.choice(pool) for _ in range(u - distinct)]
+    rnd.shuffle(tab)
+    inp = [rnd.choice(pool[: max(1, distinct // 2)]) for _ in range(u)]
+    return inp, tab
+
+
+@pytest.mark.parametrize("u,distinct,big", [(1, 1, False), (7, 3, False), (64, 64, True), (500, 17, True), (2000, 256, False)])
+def test_permute_expression_pair_vs_python(oracle, u, distinct, big):
+    inp, tab = lookup_case(u + distinct, u, distinct, big)
+    want_a, want_t = py_permute_expression_pair(inp, tab, u)
+    m = lambda xs: ints_to_limbs([R.to_mont(x, R.FR) for x in xs])  # noqa: E731
+    got_a, got_t = oracle.permute_expression_pair(m(inp + [5, 6]), m(tab + [7, 8]), u)   # rows past usable_rows are ignored
+    un = lambda a: [R.from_mont(x, R.FR) for x in limbs_to_ints(a)]  # noqa: E731
+    assert un(got_a) == want_a and un(got_t) == want_t
+    # the lookup argument's conditions: A'[i] == S'[i] or A'[i] == A'[i-1]; S' is a permutation of the table
+    assert all(want_a[i] == want_t[i] or want_a[i] == want_a[i - 1] for i in range(u)) and want_a[0] == want_t[0]
+    assert sorted(want_t) == sorted(tab[:u])
+
+
+def test_permute_expression_pair_missing_value(oracle):
+    m = lambda xs: ints_to_limbs([R.to_mont(x, R.FR) for x in xs])  # noqa: E731
+    with pytest.raises(ValueError):
+        oracle.permute_expression_pair(m([1, 2, 9]), m([1, 2, 3]), 3)

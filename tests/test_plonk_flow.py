@@ -31,7 +31,9 @@ S_TRAPDOOR = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % FR
 def _circuit():
     a = [("advice", 0, r) for r in range(4)]
     gate = ("prod", ("fixed", 0, 0), ("sum", ("sum", a[0], ("prod", a[1], a[2])), ("neg", a[3])))   # halo2-base: q (a + b c - d)
-    return plonk.Circuit(k=K, num_advice=2, num_fixed=1, gates=[gate], permutation_columns=[("advice", 0), ("advice", 1)])
+    # lookup: advice column 2 (range-checked cells) must lie in the table held by fixed column 1
+    return plonk.Circuit(k=K, num_advice=3, num_fixed=2, gates=[gate], permutation_columns=[("advice", 0), ("advice", 1)],
+                         lookups=(([("advice", 2, 0)], [("fixed", 1, 0)]),))
 
 
 def _witness(c, seed):
@@ -51,7 +53,9 @@ def _witness(c, seed):
     for r1, r0 in zip(rows1, rows0):
         w1[r1] = w0[r0]
         mapping[1][r1], mapping[0][r0] = (0, r0), (1, r1)     # a 2-cycle between cell (1, r1) and cell (0, r0)
-    return [w0, w1], q, mapping
+    w2 = [rnd.randrange(256) if rnd.random() < 0.7 else 7 for _ in range(n)]     # many repeated values: exercises the leftover rows
+    table = [i % 256 for i in range(n)]
+    return [w0, w1, w2], [q, table], mapping
 
 
 @pytest.fixture(scope="module")
@@ -59,8 +63,8 @@ def setup():
     zkb.init()
     c = _circuit()
     params = zkb.ParamsKZG.setup(K, plonk.mont(S_TRAPDOOR))
-    advice, q, mapping = _witness(c, 99)
-    pk = plonk.ProvingKey.keygen(params, c, [plonk.mont_vec(q)], mapping)
+    advice, fixed, mapping = _witness(c, 99)
+    pk = plonk.ProvingKey.keygen(params, c, [plonk.mont_vec(f) for f in fixed], mapping)
     yield c, params, pk, [plonk.mont_vec(w) for w in advice]
     pk.free()
     params.close()
@@ -81,9 +85,15 @@ def verify(c, pk, proof):
         tr.write_point(cm)
     for cm in proof["advice_commitments"]:
         tr.write_point(cm)
+    theta = tr.squeeze_challenge()
+    for lk in proof["lookup_commitments"]:
+        tr.write_point(lk[0])
+        tr.write_point(lk[1])
     beta, gamma = tr.squeeze_challenge(), tr.squeeze_challenge()
     for cm in proof["z_commitments"]:
         tr.write_point(cm)
+    for lk in proof["lookup_commitments"]:
+        tr.write_point(lk[2])
     y = tr.squeeze_challenge()
     for cm in proof["h_commitments"]:
         tr.write_point(cm)
@@ -92,7 +102,7 @@ def verify(c, pk, proof):
     for label in evals:                     # dict order == the prover's query order
         tr.write_scalar(evals[label])
     v = tr.squeeze_challenge()
-    if (beta, gamma, y, x, v) != tuple(proof["challenges"][k_] for k_ in ("beta", "gamma", "y", "x", "v")):
+    if (theta, beta, gamma, y, x, v) != tuple(proof["challenges"][k_] for k_ in ("theta", "beta", "gamma", "y", "x", "v")):
         return False, "challenges"
     # ---- vanishing identity at x
     xn = pow(x, n, FR)
@@ -133,6 +143,14 @@ def verify(c, pk, proof):
         terms.append((left - right) * l_active % FR)
     for t in terms:
         value = (value * y + t) % FR
+    for li, (inputs, table) in enumerate(c.lookups):
+        compress = lambda exprs: __import__("functools").reduce(lambda acc, e: (acc * theta + expr(e)) % FR, exprs, 0)  # noqa: E731
+        A, S = compress(inputs), compress(table)
+        lz, lzw = evals[("lookup_z", li, 0)], evals[("lookup_z", li, 1)]
+        ap, apm, sp = evals[("lookup_a", li, 0)], evals[("lookup_a", li, -1)], evals[("lookup_s", li, 0)]
+        for t in (l0 * (1 - lz), l_last * (lz * lz - lz), l_active * (lzw * (ap + beta) * (sp + gamma) - lz * (A + beta) * (S + gamma)),
+                  l0 * (ap - sp), l_active * (ap - sp) * (ap - apm)):
+            value = (value * y + t) % FR
     hx = sum(pow(xn, i, FR) * evals[("h", i, 0)] for i in range(len(proof["h_commitments"]))) % FR
     if value != hx * (xn - 1) % FR:
         return False, "vanishing identity"
@@ -241,4 +259,30 @@ def test_proving_key_file_round_trip_straight_into_hbm(setup):
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, "pk.bin")
             pk.write(path)
-            plonk.ProvingKey.read(path, c._replace(num_advice=3))
+            plonk.ProvingKey.read(path, c._replace(num_advice=4))
+
+
+def test_lookup_input_outside_the_table_is_a_constraint_failure(setup):
+    """upstream: permute_expression_pair returns Error::ConstraintSystemFailure; here the C ABI's ZKB_ERR_ARG surfaces as ZkbError"""
+    c, params, pk, advice = setup
+    bad = [a.copy() for a in advice]
+    bad[2][5] = plonk.mont(300)
+    with pytest.raises(zkb.ZkbError):
+        plonk.create_proof(params, pk, bad, np.random.default_rng(8))
+
+
+@pytest.mark.parametrize("u,distinct,big", [(1000, 1000, True), (5000, 33, True), (1 << 16, 256, False), ((1 << 18) - 6, 4096, False)])
+def test_permute_expression_pair_device_vs_oracle(oracle, u, distinct, big):
+    from test_oracle import lookup_case
+    from util import ints_to_limbs
+    inp, tab = lookup_case(3 * u + distinct, u, distinct, big)
+    n = 1 << (u - 1).bit_length()
+    pad = [0] * (n - u)
+    a = ints_to_limbs([R.to_mont(x, R.FR) for x in inp + pad])
+    t = ints_to_limbs([R.to_mont(x, R.FR) for x in tab + pad])
+    want = oracle.permute_expression_pair(a, t, u)
+    A, T = zkb.Polynomial(a), zkb.Polynomial(t)
+    ap, sp = plonk._permute_expression_pair(A, T, u)
+    got_a, got_s = ap.to_host(), sp.to_host()
+    assert (got_a[:u] == want[0]).all() and (got_s[:u] == want[1]).all()
+    assert not got_a[u:].any() and not got_s[u:].any()

@@ -102,6 +102,7 @@ def load() -> ctypes.CDLL:
         "zkb_poly_scale_add": [u64, u64p, u64],
         "zkb_poly_add_const": [u64, u64p],
         "zkb_poly_prefix_product": [u64],
+        "zkb_lookup_permute_expression_pair": [u64, u64, sz, ctypes.POINTER(u64), ctypes.POINTER(u64)],
         "zkb_fr_eval_polynomial": [u64p, sz, u64p, u64p],
         "zkb_fr_kate_division": [u64p, sz, u64p, u64p],
         "zkb_fr_batch_invert": [u64p, sz],

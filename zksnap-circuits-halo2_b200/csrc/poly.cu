@@ -11,7 +11,11 @@
 
 #include "msm_host.hpp"
 #include "ntt_host.hpp"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "graph.cuh"
+#include "lookup.cuh"
 #include "poly.cuh"
 
 namespace zkb {
@@ -79,6 +83,23 @@ __global__ void __launch_bounds__(128) graph_evaluate_kernel(const GraphArgs g, 
         prog = sp;
     }
     graph_eval_thread(g, prog, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, slots, blockDim.x, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(128) lookup_canon_kernel(const LookupArgs a) { lookup_canon_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) lookup_gather_limb_kernel(const uint4* canon, const uint32_t* idx, uint64_t u, uint32_t limb, unsigned long long* keys) {
+    lookup_gather_limb_thread(canon, idx, u, limb, keys, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) lookup_iota_kernel(uint32_t* idx, uint64_t u) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < u) idx[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(128) lookup_first_kernel(const LookupArgs a) { lookup_first_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) lookup_match_kernel(const LookupArgs a) { lookup_match_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) lookup_rep_rows_kernel(const LookupArgs a) { lookup_rep_rows_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) lookup_leftover_kernel(const LookupArgs a) { lookup_leftover_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) lookup_not_kernel(const uint32_t* in, uint32_t* out, uint64_t u) {   // out = 1 - in
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < u) out[i] = 1u - in[i];
 }
 
 static inline unsigned nblk(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -589,6 +610,28 @@ int zkb_poly_prefix_product(uint64_t poly) {
     return prefix_product_dev(p->buf.as<uint4>(), p->n, p->buf.as<uint4>(), w.tmp.as<uint4>(), ctx().stream);
 }
 
+// ---- lookup argument: permute_expression_pair on resident columns (lookup.cuh) -------------------------------------------------------
+// sorted order of `canon` (u canonical 256-bit values) into idx: four stable radix sorts on the 64-bit limbs, least significant first
+static int lookup_sort_dev(const uint4* canon, uint64_t u, uint32_t* idx, uint32_t* idx_alt, unsigned long long* keys, unsigned long long* keys_alt,
+                           DevBuf& tmp, cudaStream_t s) {
+    lookup_iota_kernel<<<nblk(u, 128), 128, 0, s>>>(idx, u);
+    count_launch();
+    uint32_t* cur = idx;
+    uint32_t* alt = idx_alt;
+    for (uint32_t limb = 0; limb < 4; ++limb) {
+        lookup_gather_limb_kernel<<<nblk(u, 128), 128, 0, s>>>(canon, cur, u, limb, keys);
+        count_launch();
+        size_t bytes = 0;
+        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys_alt, cur, alt, (int)u, 0, 64, s));
+        ZKB_TRY(tmp.reserve(bytes));
+        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys, keys_alt, cur, alt, (int)u, 0, 64, s));
+        uint32_t* t = cur; cur = alt; alt = t;
+    }
+    if (cur != idx) ZKB_CUDA_TRY(cudaMemcpyAsync(idx, cur, u * 4, cudaMemcpyDeviceToDevice, s));   // four swaps: already back in idx
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
 // ---- quotient evaluation: GraphEvaluator::evaluate for every row (graph.cuh, graph_plan.hpp) --------------------------------------
 struct GraphInfo { uint32_t instructions = 0, slots = 0, polys = 0, bytes_per_row = 0; };
 static GraphInfo g_graph_info;
@@ -752,6 +795,98 @@ int zkb_fr_batch_invert(uint64_t* values, size_t n) {
     if (rc == ZKB_OK) rc = zkb_poly_download(h, values, n);
     zkb_poly_free(h);
     return rc;
+}
+
+
+// plonk::lookup::prover::permute_expression_pair on resident columns: input / table hold the compressed expressions (>= usable_rows
+// elements); two new polynomials of the same length receive A' and S' in rows [0, usable_rows), zeros above (the caller writes
+// its blinding rows).  ZKB_ERR_ARG when an input value does not occur in the table (upstream: Error::ConstraintSystemFailure).
+int zkb_lookup_permute_expression_pair(uint64_t input, uint64_t table, size_t usable_rows, uint64_t* permuted_input, uint64_t* permuted_table) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!permuted_input || !permuted_table) { set_error("NULL output handle"); return ZKB_ERR_ARG; }
+    Poly *pi, *pt;
+    ZKB_TRY(find_poly(input, &pi));
+    ZKB_TRY(find_poly(table, &pt));
+    const uint64_t u = usable_rows;
+    if (pi->n != pt->n || u > pi->n || u >= (1ull << 31)) { set_error("lookup columns hold %zu / %zu elements, usable rows %zu", (size_t)pi->n, (size_t)pt->n, usable_rows); return ZKB_ERR_ARG; }
+    Poly *oi, *ot;
+    ZKB_TRY(new_poly(pi->n, &oi, permuted_input));
+    int rc = new_poly(pi->n, &ot, permuted_table);
+    if (rc != ZKB_OK) { zkb_poly_free(*permuted_input); *permuted_input = 0; return rc; }
+    cudaStream_t s = ctx().stream;
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(s);
+        zkb_poly_free(*permuted_input); zkb_poly_free(*permuted_table);
+        *permuted_input = *permuted_table = 0;
+        return code;
+    };
+    if (cudaMemsetAsync(oi->buf.p, 0, pi->n ? pi->n * 32 : 32, s) != cudaSuccess || cudaMemsetAsync(ot->buf.p, 0, pi->n ? pi->n * 32 : 32, s) != cudaSuccess) return fail(ZKB_ERR_CUDA);
+    if (u == 0) return ZKB_OK;
+    // workspace: canonical copies (2 x 32 u), sort keys (2 x 8 u), five index / flag arrays ... in one buffer
+    struct LookupWs { DevBuf buf, cub; uint32_t* h_flag = nullptr; };
+    LookupWs& ws = per_device<LookupWs>();
+    const size_t need = u * (64 + 16 + 4 * 10) + 256;
+    rc = ws.buf.reserve(need);
+    if (rc != ZKB_OK) return fail(rc);
+    if (!ws.h_flag && cudaMallocHost(&ws.h_flag, 16) != cudaSuccess) { cudaGetLastError(); set_error("pinned allocation failed"); return fail(ZKB_ERR_OOM); }
+    char* b = ws.buf.as<char>();
+    uint4* canon_in = reinterpret_cast<uint4*>(b); b += u * 32;
+    uint4* canon_tab = reinterpret_cast<uint4*>(b); b += u * 32;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(b); b += u * 8;
+    unsigned long long* keys_alt = reinterpret_cast<unsigned long long*>(b); b += u * 8;
+    uint32_t* arr[10];
+    for (auto& x : arr) { x = reinterpret_cast<uint32_t*>(b); b += u * 4; }
+    uint32_t* d_flags = reinterpret_cast<uint32_t*>(b);   // [0] missing
+    uint32_t *idx_in = arr[0], *idx_tab = arr[1], *alt = arr[2], *first = arr[3], *consumed = arr[4], *rep_rank = arr[5], *left_rank = arr[6],
+             *rep_rows = arr[7], *inv = arr[8];
+    LookupArgs a{};
+    a.input = pi->buf.as<uint4>(); a.table = pt->buf.as<uint4>(); a.u = u;
+    a.canon_in = canon_in; a.canon_tab = canon_tab; a.idx_in = idx_in; a.idx_tab = idx_tab; a.first = first; a.consumed = consumed;
+    a.rep_rank = rep_rank; a.left_rank = left_rank; a.out_in = oi->buf.as<uint4>(); a.out_tab = ot->buf.as<uint4>(); a.rep_rows = rep_rows;
+    a.missing = d_flags;
+    ProfScope prof("lookup_permute", s);
+    cudaMemsetAsync(d_flags, 0, 16, s);
+    cudaMemsetAsync(consumed, 0, u * 4, s);
+    const unsigned nb = nblk(u, 128);
+    lookup_canon_kernel<<<nb, 128, 0, s>>>(a);
+    count_launch();
+    rc = lookup_sort_dev(canon_in, u, idx_in, alt, keys, keys_alt, ws.cub, s);
+    if (rc == ZKB_OK) rc = lookup_sort_dev(canon_tab, u, idx_tab, alt, keys, keys_alt, ws.cub, s);
+    if (rc != ZKB_OK) return fail(rc);
+    lookup_first_kernel<<<nb, 128, 0, s>>>(a);
+    lookup_match_kernel<<<nb, 128, 0, s>>>(a);
+    count_launch(2);
+    // ranks of the repeated rows and of the leftover table elements (exclusive scans of the complemented flags)
+    auto scan_not = [&](const uint32_t* flags, uint32_t* out) -> int {
+        lookup_not_kernel<<<nb, 128, 0, s>>>(flags, inv, u);
+        count_launch();
+        size_t bytes = 0;
+        ZKB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, inv, out, (int)u, s));
+        ZKB_TRY(ws.cub.reserve(bytes));
+        ZKB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws.cub.p, bytes, inv, out, (int)u, s));
+        return ZKB_OK;
+    };
+    rc = scan_not(first, rep_rank);
+    if (rc != ZKB_OK) return fail(rc);
+    // number of repeated rows = rank of the last row + its own flag
+    uint32_t tail[2] = {0, 0};
+    if (cudaMemcpyAsync(&ws.h_flag[0], rep_rank + (u - 1), 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(&ws.h_flag[1], first + (u - 1), 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaGetLastError(); set_error("lookup: device read-back failed"); return fail(ZKB_ERR_CUDA);
+    }
+    tail[0] = ws.h_flag[0]; tail[1] = ws.h_flag[1];
+    a.repeated = tail[0] + (1u - tail[1]);
+    rc = scan_not(consumed, left_rank);
+    if (rc != ZKB_OK) return fail(rc);
+    lookup_rep_rows_kernel<<<nb, 128, 0, s>>>(a);
+    lookup_leftover_kernel<<<nb, 128, 0, s>>>(a);
+    count_launch(2);
+    if (cudaMemcpyAsync(&ws.h_flag[2], d_flags, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        set_error("lookup: kernels failed"); return fail(ZKB_ERR_CUDA);
+    }
+    if (ws.h_flag[2]) { set_error("lookup: an input value does not occur in the table (ConstraintSystemFailure)"); return fail(ZKB_ERR_ARG); }
+    return ZKB_OK;
 }
 
 }  // extern "C"

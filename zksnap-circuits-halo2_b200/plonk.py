@@ -59,6 +59,7 @@ class Circuit(NamedTuple):
     gates: list
     permutation_columns: list          # [("advice", i), ...]
     blinding_factors: int = 5
+    lookups: tuple = ()                # ((input expressions, table expressions), ...)
 
     @property
     def n(self) -> int:
@@ -88,6 +89,9 @@ class Circuit(NamedTuple):
 
         for g in self.gates:
             walk(g)
+        for inputs, table in self.lookups:
+            for e in list(inputs) + list(table):
+                walk(e)
         for kind, col in self.permutation_columns:   # enable_equality queries the column at the current rotation
             if (kind, col, 0) not in seen:
                 seen.append((kind, col, 0))
@@ -125,7 +129,7 @@ class ProvingKey:
     def __init__(self, circuit: Circuit):
         self.circuit = circuit
         self.domain = EvaluationDomain(4, circuit.k)
-        self.fixed_polys, self.fixed_cosets = [], []
+        self.fixed_polys, self.fixed_cosets, self.fixed_lagrange = [], [], []
         self.sigma_polys, self.sigma_cosets, self.sigma_lagrange = [], [], []
         self.id_lagrange = []
         self.l0 = self.l_last = self.l_active = self.x_coset = None
@@ -143,9 +147,10 @@ class ProvingKey:
         for i in range(1, n):
             wp[i] = wp[i - 1] * omega % FR
         for col in fixed_lagrange:
-            p = Polynomial(col)
-            pk.fixed_commitments.append(p.commit(params, lagrange=True))
-            p.lagrange_to_coeff(d)
+            lag = Polynomial(col)
+            pk.fixed_commitments.append(lag.commit(params, lagrange=True))
+            pk.fixed_lagrange.append(lag)
+            p = lag.slice(0, n).lagrange_to_coeff(d)
             pk.fixed_polys.append(p)
             pk.fixed_cosets.append(p.coeff_to_extended(d))
         for j, mapping in enumerate(sigma_mapping):
@@ -184,7 +189,7 @@ class ProvingKey:
     # the reader takes offsets, so adopting upstream's order is a change of the index table only.
     def write(self, path: str) -> None:
         c = self.circuit
-        groups = [("fixed_polys", self.fixed_polys), ("fixed_cosets", self.fixed_cosets), ("sigma_lagrange", self.sigma_lagrange),
+        groups = [("fixed_lagrange", self.fixed_lagrange), ("fixed_polys", self.fixed_polys), ("fixed_cosets", self.fixed_cosets), ("sigma_lagrange", self.sigma_lagrange),
                   ("sigma_polys", self.sigma_polys), ("sigma_cosets", self.sigma_cosets)]
         with open(path, "wb") as f:
             f.write(_MAGIC + struct.pack("<IIIII", c.k, c.num_advice, c.num_fixed, len(c.permutation_columns), c.blinding_factors))
@@ -217,7 +222,7 @@ class ProvingKey:
                 off += length * 32
             return out
 
-        pk.fixed_polys, pk.fixed_cosets = take(nf, n), take(nf, N)
+        pk.fixed_lagrange, pk.fixed_polys, pk.fixed_cosets = take(nf, n), take(nf, n), take(nf, N)
         pk.sigma_lagrange, pk.sigma_polys, pk.sigma_cosets = take(np_, n), take(np_, n), take(np_, N)
         with open(path, "rb") as f:
             f.seek(off)
@@ -227,7 +232,7 @@ class ProvingKey:
         return pk
 
     def free(self) -> None:
-        for p in (self.fixed_polys + self.fixed_cosets + self.sigma_polys + self.sigma_cosets + self.sigma_lagrange + self.id_lagrange
+        for p in (self.fixed_lagrange + self.fixed_polys + self.fixed_cosets + self.sigma_polys + self.sigma_cosets + self.sigma_lagrange + self.id_lagrange
                   + [self.l0, self.l_last, self.l_active, self.x_coset]):
             if p is not None:
                 p.free()
@@ -274,6 +279,54 @@ def permutation_commit(params: ParamsKZG, pk: ProvingKey, advice_lagrange: list,
     return out
 
 
+# ---- plonk::lookup::prover: commit_permuted and commit_product ------------------------------------------------------------------------
+def _permute_expression_pair(input_: Polynomial, table: Polynomial, usable_rows: int):
+    import ctypes
+
+    from .halo2 import check, lib
+    ha, ht = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    check(lib().zkb_lookup_permute_expression_pair(input_._h, table._h, usable_rows, ctypes.byref(ha), ctypes.byref(ht)))
+    return Polynomial(_handle=ha.value), Polynomial(_handle=ht.value)
+
+
+def lookup_commit_permuted(params: ParamsKZG, pk: ProvingKey, lookup, advice_lagrange: list, theta: int, blind_rows):
+    """Argument::commit_permuted: compress the input / table expressions with theta over the 2^k domain (one row-interpreter pass
+    each, rot_scale 1), permute_expression_pair on the device, blinding rows, commitments.
+    Returns dict(A, S: compressed columns; Ap, Sp: permuted columns; commitments)."""
+    c = pk.circuit
+    n, u = c.n, c.usable_rows
+    inputs, table = lookup
+    cols = {}
+    for name, exprs in (("A", inputs), ("S", table)):
+        g = ev.GraphEvaluator()
+        g.add_horner(ev.ValueSource(ev.CONSTANT, 0), [g.add_expression(e) for e in exprs], ev.ValueSource(ev.THETA))
+        out = Polynomial.zeros(n)
+        g.evaluate(out, fixed=pk.fixed_lagrange, advice=advice_lagrange, theta=mont(theta), rot_scale=1)
+        cols[name] = out
+    ap, sp = _permute_expression_pair(cols["A"], cols["S"], u)
+    ap.write(u, blind_rows())
+    sp.write(u, blind_rows())
+    cols.update(Ap=ap, Sp=sp, commitments=[ap.commit(params, lagrange=True), sp.commit(params, lagrange=True)])
+    return cols
+
+
+def lookup_commit_product(params: ParamsKZG, pk: ProvingKey, cols: dict, beta: int, gamma: int, blind_rows):
+    """Argument::commit_product: z[0] = 1, z[i+1] = z[i] (A_i + beta)(S_i + gamma) / ((A'_i + beta)(S'_i + gamma)) on the usable rows."""
+    c = pk.circuit
+    n, u = c.n, c.usable_rows
+    g = ev.GraphEvaluator()
+    g.add_expression(("prod", ("sum", ("advice", 0, 0), ("challenge", 0)), ("sum", ("advice", 1, 0), ("challenge", 1))))
+    ch = np.stack([mont(beta), mont(gamma)])
+    num, den = Polynomial.zeros(n), Polynomial.zeros(n)
+    g.evaluate(num, advice=[cols["A"], cols["S"]], challenges=ch, rot_scale=1)
+    g.evaluate(den, advice=[cols["Ap"], cols["Sp"]], challenges=ch, rot_scale=1)
+    den.batch_invert()
+    num.mul(den).prefix_product()
+    den.free()
+    num.write(u + 1, blind_rows())
+    return num, num.commit(params, lagrange=True)
+
+
 # ---- create_proof -----------------------------------------------------------------------------------------------------------------
 def create_proof(params: ParamsKZG, pk: ProvingKey, advice_lagrange_host: list, rng: np.random.Generator, hooks: dict | None = None) -> dict:
     """advice_lagrange_host: one (n, 4) Montgomery array per advice column with the witness in the usable rows (the blinding rows
@@ -303,7 +356,12 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, advice_lagrange_host: list, 
     advice_commitments = [p.commit(params, lagrange=True) for p in advice]
     for cm in advice_commitments:
         tr.write_point(cm)
-    # 2. permutation products
+    # 2. lookups: permuted columns (theta), then (beta, gamma) the permutation and lookup products
+    theta = tr.squeeze_challenge()
+    lookups = [lookup_commit_permuted(params, pk, lk, advice, theta, lambda: rand_fr(n - u)) for lk in c.lookups]
+    for lk in lookups:
+        for cm in lk["commitments"]:
+            tr.write_point(cm)
     beta, gamma = tr.squeeze_challenge(), tr.squeeze_challenge()
     zs = permutation_commit(params, pk, advice, beta, gamma, lambda s: rand_fr(c.blinding_factors))
     if "after_z" in hooks:
@@ -311,16 +369,23 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, advice_lagrange_host: list, 
     z_commitments = [z.commit(params, lagrange=True) for z, _ in zs] if "after_z" in hooks else [cm for _, cm in zs]
     for cm in z_commitments:
         tr.write_point(cm)
+    for lk in lookups:
+        lk["z"], lk["z_commitment"] = lookup_commit_product(params, pk, lk, beta, gamma, lambda: rand_fr(c.blinding_factors))
+        tr.write_point(lk["z_commitment"])
     y = tr.squeeze_challenge()
     # 3. h(X): coefficient forms, extended cosets, evaluate_h, / (X^n - 1), back to coefficients, pieces
     advice_polys = [p.slice(0, n).lagrange_to_coeff(d) for p in advice]
     z_polys = [z.slice(0, n).lagrange_to_coeff(d) for z, _ in zs]
     advice_cosets = [p.coeff_to_extended(d) for p in advice_polys]
     z_cosets = [p.coeff_to_extended(d) for p in z_polys]
-    q = ev.QuotientEvaluator(c.gates, dict(columns=c.permutation_columns, chunk_len=c.chunk_len, last_rotation=-(c.blinding_factors + 1)))
+    for lk in lookups:   # coefficient forms and extended cosets of z, A', S'
+        lk["polys"] = [lk[name].slice(0, n).lagrange_to_coeff(d) for name in ("z", "Ap", "Sp")]
+        lk["cosets"] = [p.coeff_to_extended(d) for p in lk["polys"]]
+    q = ev.QuotientEvaluator(c.gates, dict(columns=c.permutation_columns, chunk_len=c.chunk_len, last_rotation=-(c.blinding_factors + 1)),
+                             list(c.lookups))
     h = Polynomial.zeros(N)
-    q.evaluate_h(h, pk.fixed_cosets, advice_cosets, [], None, mont(y), mont(beta), mont(gamma), None, 1 << (d.extended_k - c.k),
-                 pk.l0, pk.l_last, pk.l_active, pk.x_coset, pk.sigma_cosets, z_cosets)
+    q.evaluate_h(h, pk.fixed_cosets, advice_cosets, [], None, mont(y), mont(beta), mont(gamma), mont(theta), 1 << (d.extended_k - c.k),
+                 pk.l0, pk.l_last, pk.l_active, pk.x_coset, pk.sigma_cosets, z_cosets, [tuple(lk["cosets"]) for lk in lookups])
     if "after_h" in hooks:
         hooks["after_h"]([h])
     d.divide_by_vanishing_poly(h)
@@ -351,6 +416,13 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, advice_lagrange_host: list, 
         query(("z", s, 1), p, z_commitments[s], 1)
         if s + 1 < len(z_polys):
             query(("z", s, -(c.blinding_factors + 1)), p, z_commitments[s], -(c.blinding_factors + 1))
+    for li, lk in enumerate(lookups):
+        zp, app, spp = lk["polys"]
+        query(("lookup_z", li, 0), zp, lk["z_commitment"], 0)
+        query(("lookup_z", li, 1), zp, lk["z_commitment"], 1)
+        query(("lookup_a", li, 0), app, lk["commitments"][0], 0)
+        query(("lookup_a", li, -1), app, lk["commitments"][0], -1)
+        query(("lookup_s", li, 0), spp, lk["commitments"][1], 0)
     for i, p in enumerate(pieces):
         query(("h", i, 0), p, h_commitments[i], 0)
     # 5. GWC multiopen: per distinct point, fold polynomials and evaluations with powers of v, divide by (X - point), commit
@@ -378,8 +450,12 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, advice_lagrange_host: list, 
         "advice_commitments": advice_commitments, "z_commitments": z_commitments, "h_commitments": h_commitments,
         "evals": {qq[0]: qq[4] for qq in queries}, "eval_points": {qq[0]: qq[3] for qq in queries},
         "commitment_of": {qq[0]: qq[2] for qq in queries}, "openings": openings,
-        "challenges": {"beta": beta, "gamma": gamma, "y": y, "x": x, "v": v},
+        "lookup_commitments": [lk["commitments"] + [lk["z_commitment"]] for lk in lookups],
+        "challenges": {"theta": theta, "beta": beta, "gamma": gamma, "y": y, "x": x, "v": v},
     }
+    for lk in lookups:
+        for p in [lk["A"], lk["S"], lk["Ap"], lk["Sp"], lk["z"]] + lk["polys"] + lk["cosets"]:
+            p.free()
     for p in advice + advice_polys + z_polys + advice_cosets + z_cosets + pieces + [h] + [z for z, _ in zs]:
         p.free()
     return proof
