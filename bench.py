@@ -924,6 +924,73 @@ def dropin_replays(env: Env, pinned: bool):
     return res
 
 
+# ---- BASELINE configs #4 / #5: the MSM and NTT sweeps through the host-buffer C ABI ---------------------------------------------------
+def sweep_object(env: Env):
+    """Standalone G1 MSM 2^16..2^24 (2^26: msm_split) and Fr NTT 2^18..2^26 x {1, 16} columns (capped at 2 GiB per call), each as ONE
+    host-buffer call from page-locked memory (PCIe included).  With several devices bound in this process (single_process leg)
+    the library shards every call itself, so the same rows at N = 1, 2, 4, 8 are the strong-scaling curve of the drop-in."""
+    zkb, lib, torch = env.zkb, env.lib, env.torch
+    rows = []
+    kmax = min(LOG_N_MSM, 24)
+    dl = random_field(1 << kmax, 0x5EE9)
+    bases = zkb.g1_fixed_base_mul(dl)
+    sc = random_field(1 << kmax, 0x5EEA)
+    h_s = torch.from_numpy(sc.view(np.int64)).pin_memory()
+    out = np.zeros(12, dtype=np.uint64)
+    outp = out.ctypes.data_as(u64p)
+    for k in range(16, kmax + 1, 2):
+        n = 1 << k
+        h = ctypes.c_uint64(0)
+        env.check(lib.zkb_srs_register(bases.ctypes.data_as(u64p), n, ctypes.byref(h)))
+        lib.zkb_srs_precompute(h, None, None)
+        sp = ctypes.cast(h_s.data_ptr(), u64p)
+        env.check(lib.zkb_msm_g1_srs(h, sp, n, outp))
+        ok = bool((out[:8] == known_dlog_point(sc[:n], dl[:n])).all())
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            env.check(lib.zkb_msm_g1_srs(h, sp, n, outp))
+            best = min(best, time.perf_counter() - t0)
+        rows.append({"op": "msm", "log_n": k, "e2e_ms": best * 1e3, "pts_per_s": n / best, "parity": ok})
+        lib.zkb_srs_release(h)
+    del bases, h_s
+    cap = 1 << 26    # elements per call (2 GiB)
+    buf = torch.empty((cap, 4), dtype=torch.int64).pin_memory()
+    rnd = env.device_field(1 << 24, 0x5EEB).cpu()
+    for k in (18, 20, 22, 24, 26):
+        N = 1 << k
+        w = zkb.omega(k)
+        wp = w.ctypes.data_as(u64p)
+        for cols in (1, 16):
+            if N * cols > cap:
+                cols = cap // N
+                if cols <= 1 and any(r["op"] == "ntt" and r["log_n"] == k and r["cols"] == 1 for r in rows):
+                    continue
+            ptrs = (u64p * cols)(*[ctypes.cast(buf.data_ptr() + i * N * 32, u64p) for i in range(cols)])
+            # parity: a 2-sparse column 0 against the definition
+            buf[:N * cols].zero_()
+            j1, j2 = 12345 % N, N - 7
+            v = random_field(3, 0x5EEC + k)
+            buf[j1] = torch.from_numpy(v[1].view(np.int64))
+            buf[j2] = torch.from_numpy(v[2].view(np.int64))
+            env.check(lib.zkb_ntt_fr_batch(ptrs, cols, wp, k))
+            got = buf[:N].numpy().view(np.uint64).reshape(-1, 4)
+            ok = two_sparse_ok(got, v[1], v[2], j1, j2, k, [0, 1, N // 2 + 3, N - 1, N // 3])
+            for off in range(0, N * cols, 1 << 24):
+                m = min(1 << 24, N * cols - off)
+                buf[off:off + m] = rnd[:m]
+            best = 1e30
+            for _ in range(3):
+                t0 = time.perf_counter()
+                env.check(lib.zkb_ntt_fr_batch(ptrs, cols, wp, k))
+                best = min(best, time.perf_counter() - t0)
+            rows.append({"op": "ntt", "log_n": k, "cols": cols, "e2e_ms": best * 1e3, "elems_per_s": N * cols / best, "parity": ok})
+    del buf
+    return {"workload": "BASELINE configs #4 / #5 through the host-buffer C ABI, page-locked operands, devices bound in this process: %d"
+                        % max(1, len(zkb.bound_devices())),
+            "rows": rows, "parity_checked": all(r["parity"] for r in rows)}
+
+
 # ---- N > 1: rank 0 alone drives all N devices through the unchanged C ABI --------------------------------------------------------------
 def single_process_object(env: Env, mp_split, mp_split_point):
     """zkb_init(all N devices) in ONE process — the deployment of the reference's prover (create_proof is one process,
@@ -1003,7 +1070,8 @@ def single_process_object(env: Env, mp_split, mp_split_point):
         obj["wrapper_replay_dropin_pageable"] = rep["wrapper"]
         obj["voter_replay_dropin_pageable"] = rep["voter"]
         obj["st_replay_dropin_pageable"] = rep["st"]
-        obj["parity_checked"] = identical and all(v["parity_checked"] for v in rep.values())
+        obj["sweep"] = sweep_object(env)
+        obj["parity_checked"] = identical and all(v["parity_checked"] for v in rep.values()) and obj["sweep"]["parity_checked"]
         obj["launches"] = int(zkb.launch_count())
     finally:
         zkb.shutdown()
@@ -1054,7 +1122,7 @@ def main():
             note(name + " FAILED: " + repr(exc))
             return {"error": repr(exc)[:400], "parity_checked": False}
 
-    ntt_obj = quot_obj = sharded_obj = sq_obj = wrap_obj = split_obj = sp_obj = None
+    ntt_obj = quot_obj = sharded_obj = sq_obj = wrap_obj = split_obj = sp_obj = sweep_obj = None
     dropin = {}
     gr = y_np = None
     split_point = None
@@ -1082,6 +1150,7 @@ def main():
         split_obj = guarded("msm_split", _s)
         if world == 1:   # drop-in (host-buffer) replays of the three circuits on one GPU; at N > 1 the single process runs them
             dropin = guarded("dropin_replays", lambda: {"pageable": dropin_replays(env, False), "page_locked": dropin_replays(env, True)})
+            sweep_obj = guarded("sweep", lambda: sweep_object(env))
     # ---- N > 1: every rank releases its GPU, then rank 0 alone drives all N devices
     if world > 1 and not args.skip_ntt and not args.skip_replay and split_point is not None:
         env.torch.cuda.synchronize()
@@ -1093,7 +1162,7 @@ def main():
         env.dist.barrier(group=env.host_group)
         env.zkb.init(env.local_rank)
     for name, o in (("ntt", ntt_obj), ("quotient", quot_obj), ("sharded_ntt", sharded_obj), ("sharded_quotient", sq_obj),
-                    ("wrapper_replay", wrap_obj), ("msm_split", split_obj), ("single_process", sp_obj)):
+                    ("wrapper_replay", wrap_obj), ("msm_split", split_obj), ("single_process", sp_obj), ("sweep", sweep_obj)):
         if o is not None:
             parity[name] = bool(o.get("parity_checked", False))
     if dropin:
@@ -1133,7 +1202,7 @@ def main():
                              if dropin and "error" not in dropin else None),
             "st_replay": ({"dropin_pageable": dropin["pageable"]["st"], "dropin_page_locked": dropin["page_locked"]["st"]}
                           if dropin and "error" not in dropin else None),
-            "single_process": sp_obj,
+            "single_process": sp_obj, "sweep": sweep_obj,
             "bench_wall_s": time.time() - t_start,
         }
         print(json.dumps(line))

@@ -233,6 +233,10 @@ int zkb_poly_eval(uint64_t poly, const uint64_t x[4], uint64_t out[4]);
 int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_handle);
 int zkb_poly_batch_invert(uint64_t poly);
 int zkb_poly_mul(uint64_t poly, uint64_t other);
+/* poly[i] *= table[i mod period] (period a power of two <= 16, table: period x 4 Montgomery limbs): EvaluationDomain::
+ * divide_by_vanishing_poly — on the extended coset 1 / (X^n - 1) takes only 2^(extended_k - k) distinct values, so no
+ * extended-size array of them is ever built or uploaded */
+int zkb_poly_mul_periodic(uint64_t poly, const uint64_t* table, uint32_t period);
 int zkb_poly_scale_add(uint64_t poly, const uint64_t k[4], uint64_t other);
 int zkb_poly_add_const(uint64_t poly, const uint64_t c[4]);
 int zkb_poly_prefix_product(uint64_t poly);

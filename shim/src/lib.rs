@@ -40,6 +40,32 @@ extern "C" {
     pub fn zkb_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn zkb_graph_evaluate(graph: *const zkb_graph, inputs: *const zkb_graph_inputs, values: u64) -> c_int;
     pub fn zkb_msm_g1_srs_dev(handle: u64, offset: size_t, d_scalars: *const c_void, n: size_t, out_jac: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn zkb_fr_zeta(out: *mut u64) -> c_int;
+    pub fn zkb_bound_devices(devices: *mut c_int, capacity: c_int) -> c_int;
+    pub fn zkb_poly_upload(values: *const u64, n: size_t, handle: *mut u64) -> c_int;
+    pub fn zkb_poly_load_file(path: *const c_char, offset: u64, n: size_t, handle: *mut u64) -> c_int;
+    pub fn zkb_poly_write(handle: u64, offset: size_t, values: *const u64, n: size_t) -> c_int;
+    pub fn zkb_poly_free(handle: u64) -> c_int;
+    pub fn zkb_lookup_permute_expression_pair(input: u64, table: u64, usable_rows: size_t, permuted_input: *mut u64, permuted_table: *mut u64) -> c_int;
+}
+
+/// Call once before the first proof (e.g. from the patched `ParamsKZG::setup` / `read`).  `devices`: CUDA ordinals to drive from
+/// this ONE process — the reference's prover is one process (`create_proof`, /root/reference/aggregator/src/wrapper.rs:129-137,
+/// chained by `gen_recursion_snark`, wrapper.rs:869-902), so the 8 GPUs of a box are reached by listing them here (or by setting
+/// ZKB_DEVICES=all and passing an empty slice): commits are then sharded by SRS point range, batches by column and a large
+/// transform over NVLink peer memory behind the same wrappers below.
+/// Also pins the one constant the two sides must agree on and that first-principles tests cannot see: the cube root of unity used
+/// as the coset generator.  halo2curves releases have shipped either primitive root as `Fr::ZETA`; a mismatch would evaluate
+/// `coeff_to_extended` on a different coset than the host-side pieces of the prover (valid-looking but unverifiable proofs).
+pub fn init(devices: &[i32]) {
+    use halo2curves::ff::WithSmallOrderMulGroup;
+    let rc = unsafe { zkb_init(if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() }, devices.len() as c_int) };
+    check(rc, "init");
+    let mut zeta = [0u64; 4];
+    check(unsafe { zkb_fr_zeta(zeta.as_mut_ptr()) }, "fr_zeta");
+    let crate_zeta: Fr = <Fr as WithSmallOrderMulGroup<3>>::ZETA;
+    let crate_limbs: [u64; 4] = unsafe { std::mem::transmute(crate_zeta) };
+    assert_eq!(zeta, crate_limbs, "zkb200 and halo2curves disagree on Fr::ZETA (coset generator of the extended domain)");
 }
 
 /// `plonk::evaluation::ValueSource` / `Calculation` / `GraphEvaluator` as the C ABI reads them (include/zkb200.h).

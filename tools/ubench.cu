@@ -1,5 +1,5 @@
 // ubench.cu — instruction-throughput and field-multiplication microbenchmarks for sm_100a (standalone binary).
-//   build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I zksnap-circuits-halo2_b200/csrc tools/ubench.cu -o tools/ubench
+//   build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I zksnap-circuits-halo2_b200/csrc -I tools tools/ubench.cu -o tools/ubench
 #include <cstdio>
 #include <cuda_runtime.h>
 

@@ -98,6 +98,7 @@ def load() -> ctypes.CDLL:
         "zkb_poly_kate_division": [u64, u64p, ctypes.POINTER(u64)],
         "zkb_poly_batch_invert": [u64],
         "zkb_poly_mul": [u64, u64],
+        "zkb_poly_mul_periodic": [u64, u64p, u32],
         "zkb_poly_slice": [u64, sz, sz, u64p],
         "zkb_poly_scale_add": [u64, u64p, u64],
         "zkb_poly_add_const": [u64, u64p],

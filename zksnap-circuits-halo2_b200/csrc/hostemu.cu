@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "curve.cuh"
-#include "field29.cuh"
+#include "../../tools/field29.cuh"  // rejected 9 x 29-bit prototype, kept with the microbenchmarks (not on any product path)
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "ntt_plan.hpp"

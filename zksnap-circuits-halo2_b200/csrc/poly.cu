@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(128) field_vec_op_kernel(int field, int op, co
 __global__ void __launch_bounds__(128) poly_mul_kernel(const PolyMulArgs a) {
     poly_mul_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
+__global__ void __launch_bounds__(128) poly_mul_periodic_kernel(const PolyMulPeriodicArgs a) {
+    poly_mul_periodic_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
 __global__ void __launch_bounds__(128) poly_scale_add_kernel(const PolyScaleAddArgs a) {
     poly_scale_add_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -558,6 +561,23 @@ int zkb_poly_mul(uint64_t poly, uint64_t other) {
     if (p->n == 0) return ZKB_OK;
     PolyMulArgs a{p->buf.as<uint4>(), q->buf.as<uint4>(), p->n};
     poly_mul_kernel<<<nblk(p->n, 128), 128, 0, ctx().stream>>>(a);
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
+}
+
+// poly[i] *= table[i mod period]
+int zkb_poly_mul_periodic(uint64_t poly, const uint64_t* table, uint32_t period) {
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (!table || period == 0 || period > POLY_PERIOD_MAX || (period & (period - 1))) { set_error("period must be a power of two <= %u", POLY_PERIOD_MAX); return ZKB_ERR_ARG; }
+    Poly* p;
+    ZKB_TRY(find_poly(poly, &p));
+    if (p->n == 0) return ZKB_OK;
+    PolyMulPeriodicArgs a{};
+    a.a = p->buf.as<uint4>(); a.n = p->n; a.period = period;
+    for (uint32_t i = 0; i < period; ++i) words_of(fr_of(table + 4 * i), a.t[i]);
+    poly_mul_periodic_kernel<<<nblk(p->n, 128), 128, 0, ctx().stream>>>(a);
     count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
     return ZKB_OK;

@@ -91,6 +91,20 @@ ZKB_HD void poly_mul_thread(const PolyMulArgs& p, uint64_t i) {
     fr_store2(p.a, i, fp_mul(fr_load2(p.a, i), fr_load2(p.b, i)));
 }
 
+// a[i] <- a[i] * t[i mod period], period a power of two <= 16: EvaluationDomain::divide_by_vanishing_poly — 1 / (X^n - 1) takes
+// only 2^(extended_k - k) distinct values on the extended coset, so the table travels in the kernel arguments
+constexpr uint32_t POLY_PERIOD_MAX = 16;
+struct PolyMulPeriodicArgs {
+    uint4* a;
+    uint64_t n;
+    uint32_t period;
+    uint32_t t[POLY_PERIOD_MAX][8];
+};
+ZKB_HD void poly_mul_periodic_thread(const PolyMulPeriodicArgs& p, uint64_t i) {
+    if (i >= p.n) return;
+    fr_store2(p.a, i, fp_mul(fr_load2(p.a, i), fr_from_words(p.t[i & (p.period - 1)])));
+}
+
 // acc[i] <- acc[i] * k + other[i]   (Horner over polynomials: the multiopen provers fold their queries with powers of v)
 struct PolyScaleAddArgs {
     uint4* acc;

@@ -311,6 +311,10 @@ class EvaluationDomain:
         """1 / (X^n - 1) on the extended coset zeta <w_ext> (upstream's `t_evaluations`, inverted as divide_by_vanishing_poly uses
         them): X^n takes only 2^(extended_k - k) distinct values there, so the (extended_len, 4) array is that many Montgomery
         values tiled.  Host integers; no GPU needed."""
+        return np.tile(self._t_inverse_period(), (self.extended_len() >> (self.extended_k - self.k), 1))
+
+    def _t_inverse_period(self) -> np.ndarray:
+        """the 2^(extended_k - k) distinct values of 1 / (X^n - 1) on the extended coset, Montgomery limbs"""
         r = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
         R = (1 << 256) % r
         Rinv = pow(R, -1, r)
@@ -318,15 +322,16 @@ class EvaluationDomain:
         w = sum(int(x) << (64 * i) for i, x in enumerate(self.get_extended_omega())) * Rinv % r
         period = 1 << (self.extended_k - self.k)
         vals = [pow((pow(zeta, self.n, r) * pow(w, i * self.n, r) - 1) % r, -1, r) * R % r for i in range(period)]
-        one_period = np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64)
-        return np.tile(one_period, (self.extended_len() // period, 1))
+        return np.array([[(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in vals], dtype=np.uint64)
 
     def divide_by_vanishing_poly(self, h: "Polynomial") -> "Polynomial":
         """EvaluationDomain::divide_by_vanishing_poly on a resident polynomial of extended evaluations: h[i] *= 1 / (X^n - 1) at the
-        i-th coset point.  The coset of inverses is uploaded once per domain and kept in HBM."""
+        i-th coset point.  Only the 2^(extended_k - k) distinct inverses travel (in the kernel arguments); no extended-size array
+        of them is built, uploaded or read."""
         if getattr(self, "_t_inv", None) is None:
-            self._t_inv = Polynomial(self.t_evaluations_inverse())
-        return h.mul(self._t_inv)
+            self._t_inv = np.ascontiguousarray(self._t_inverse_period())
+        check(lib().zkb_poly_mul_periodic(h._h, _p(self._t_inv), self._t_inv.shape[0]))
+        return h
 
     def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
         v = _fr(a)
