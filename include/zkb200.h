@@ -64,6 +64,11 @@ extern "C" {
  * on one device: the first of the list (home device), or for *_dev the device that owns the pointer.
  * The one-process-per-GPU deployment (torchrun, one rank per device, zkb_dist_* over CUDA IPC) remains available. */
 int zkb_init(const int* devices, int ndev);
+/* Binds the CALLING THREAD to one of the devices given to zkb_init: from then on every call this thread makes acts on that device
+ * alone (its SRS replica, its streams and workspaces; polynomial handles it creates live there and must be used from threads bound
+ * to the same device) and never fans out.  Threads that never call this act on the home device and get the sharded behaviour of
+ * zkb_init.  This is how one process keeps resident work on every GPU: one host thread per device. */
+int zkb_thread_bind_device(int device);
 /* Thresholds of the multi-device paths, as log2 sizes (0 = default): smallest per-device share of points for which a commit
  * is sharded (default 16), smallest transform whose batch is split by column (16), smallest single transform sharded over
  * the devices (22; needs >= 2 NTT passes, i.e. >= 2^11).  Environment: ZKB_MULTI_MIN_SHARE_LOG, ZKB_MULTI_NTT_MIN_LOG,
@@ -357,6 +362,11 @@ int zkb_graph_last_info(uint32_t* instructions, uint32_t* slots, uint32_t* polys
 int zkb_dist_create(int rank, int world, uint32_t max_log_n, uint8_t* handle_out);
 int zkb_dist_connect(const uint8_t* all_handles);
 int zkb_dist_destroy(void);
+/* One process, several devices (zkb_init with a device list): allocates and connects the symmetric slices of every bound device
+ * (largest power of two <= their number) through peer access — no handles to exchange.  The host-buffer entry points do this
+ * themselves for transforms of >= 2^22 elements; call it to use zkb_dist_ntt_fr_dev / zkb_dist_buffers / zkb_dist_status from one
+ * host thread per device (zkb_thread_bind_device), rank = position of the device in zkb_init's list. */
+int zkb_dist_create_inprocess(uint32_t max_log_n);
 /* host slices (N/world x 4 u64 each); synchronous */
 int zkb_dist_ntt_fr(const uint64_t* in_slice, uint64_t* out_slice, const uint64_t omega[4], uint32_t log_n);
 /* device slices; NULL d_in_slice / d_out_slice = use the symmetric slices directly (zkb_dist_buffers).  Asynchronous on

@@ -175,3 +175,78 @@ def test_dev_calls_follow_the_pointer(multi):
             assert rc == 0, lib.zkb_last_error()
             st.synchronize()
             assert (d_a.cpu().numpy().view(np.uint64).reshape(-1, 4) == want).all()
+
+
+def test_thread_bound_to_a_device_keeps_resident_work_there(oracle, multi):
+    """zkb_thread_bind_device: a host thread bound to device 1 creates polynomial handles there and runs the resident chain
+    (commit against that device's SRS replica, lagrange_to_coeff, eval) with the same results as the home device; it never fans out."""
+    import threading
+    k = 12
+    n = 1 << k
+    bases = zkb.g1_fixed_base_mul(random_field(n, 21))
+    params = zkb.ParamsKZG(k, bases)
+    a = random_field(n, 22)
+    x = random_field(1, 23)[0]
+    d = zkb.EvaluationDomain(4, k)
+    res = {}
+
+    def chain(tag, device):
+        try:
+            if device is not None:
+                assert zkb.lib().zkb_thread_bind_device(device) == 0
+            p = zkb.Polynomial(a)
+            c = p.commit(params, lagrange=False)
+            p.lagrange_to_coeff(d)
+            res[tag] = (c, p.eval(x), p.to_host())
+            p.free()
+        except Exception as exc:  # surfaced by the assertions below
+            res[tag] = exc
+
+    chain("home", None)
+    t = threading.Thread(target=chain, args=("dev1", multi[1]))
+    t.start()
+    t.join()
+    assert not isinstance(res["dev1"], Exception), res["dev1"]
+    assert (res["home"][0] == oracle.best_multiexp(a, bases)).all()
+    for u, v in zip(res["home"], res["dev1"]):
+        assert (u == v).all()
+    params.close()
+
+
+def test_inprocess_sharded_ntt_on_device_slices(multi):
+    """zkb_dist_create_inprocess + one host thread per device calling zkb_dist_ntt_fr_dev on resident slices == the single-device
+    transform of the whole vector."""
+    torch = pytest.importorskip("torch")
+    from concurrent.futures import ThreadPoolExecutor
+    lib = zkb.lib()
+    world = 1
+    while world * 2 <= len(multi):
+        world *= 2
+    k = 16
+    n = 1 << k
+    a = random_field(n, 31)
+    w = zkb.omega(k)
+    wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+    want = a.copy()
+    zkb.lib().zkb_multi_device_set(10, 10, 28)      # keep the reference transform on one device
+    zkb.best_fft(want, w, k)
+    zkb.lib().zkb_multi_device_set(10, 10, 12)
+    assert lib.zkb_dist_create_inprocess(k) == 0, lib.zkb_last_error()
+    ln = n // world
+    outs = [None] * world
+
+    def rank(r):
+        assert lib.zkb_thread_bind_device(multi[r]) == 0
+        dev = torch.device("cuda", multi[r])
+        d_in = torch.from_numpy(a[r * ln:(r + 1) * ln].view(np.int64).copy()).to(dev)
+        d_out = torch.empty_like(d_in)
+        st = torch.cuda.Stream(device=dev)
+        sp = ctypes.c_void_p(st.cuda_stream)
+        assert lib.zkb_dist_ntt_fr_dev(ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr()), wp, k, sp) == 0, lib.zkb_last_error()
+        assert lib.zkb_dist_status(sp) == 0, lib.zkb_last_error()
+        outs[r] = d_out.cpu().numpy().view(np.uint64).reshape(-1, 4)
+
+    with ThreadPoolExecutor(world) as pool:
+        list(pool.map(rank, range(world)))
+    lib.zkb_dist_destroy()
+    assert (np.concatenate(outs) == want).all()

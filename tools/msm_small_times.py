@@ -12,6 +12,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log-n", type=int, nargs="+", default=[13, 14, 15, 16, 17, 18, 19, 20, 22])
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--chunk", type=int, default=0, help="level-0 chunk override (0 = wave-fitted)")
+    ap.add_argument("--table-only", action="store_true")
     a = ap.parse_args()
     import torch
     from oracle import coracle
@@ -19,6 +21,7 @@ def main():
     zkb = importlib.import_module("zksnap-circuits-halo2_b200")
     zkb.init(0)
     lib = zkb.lib()
+    lib.zkb_msm_set_params(0, a.chunk)
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream(); sp = ctypes.c_void_p(st.cuda_stream)
     kmax = max(a.log_n)
@@ -31,7 +34,7 @@ def main():
         s = random_field(n, 100 + k)
         d_s = torch.from_numpy(s.view(np.int64)).to(dev)
         want = coracle.g1_mul(coracle.g1_generator(), coracle.fr_inner_product(s, dl[:n]))
-        for table in (1, 0):
+        for table in ((1,) if a.table_only else (1, 0)):
             lib.zkb_srs_set_precompute(table)
             h = ctypes.c_uint64(0)
             assert lib.zkb_srs_register(bases.ctypes.data_as(u64p), n, ctypes.byref(h)) == 0

@@ -76,6 +76,8 @@ def load() -> ctypes.CDLL:
         "zkb_fr_zeta": [u64p],
         "zkb_bound_devices": [ctypes.POINTER(ci), ci],
         "zkb_multi_device_set": [ci, ci, ci],
+        "zkb_thread_bind_device": [ci],
+        "zkb_dist_create_inprocess": [u32],
         "zkb_msm_g1_srs_dev": [u64, sz, vp, sz, u64p, vp],
         "zkb_ntt_fr_dev": [vp, vp, sz, u64p, u32, vp],
         "zkb_coeff_to_extended_dev": [vp, vp, vp, sz, u32, u32, vp],

@@ -1567,6 +1567,17 @@ int zkb_fr_zeta(uint64_t out[4]) {
     fr_to_limbs64(fr_zeta(), out);
     return ZKB_OK;
 }
+int zkb_thread_bind_device(int device) {
+    if (g_nslots == 0) ZKB_TRY(require_init());
+    for (int i = 0; i < g_nslots; ++i)
+        if (g_slot_device[i] == device) {
+            tl_slot = i;
+            ZKB_CUDA_TRY(cudaSetDevice(device));
+            return ZKB_OK;
+        }
+    set_error("device %d is not bound (zkb_init)", device);
+    return ZKB_ERR_ARG;
+}
 int zkb_multi_device_set(int msm_min_share_log, int batch_ntt_min_log, int dist_ntt_min_log) {
     const int v[3] = {msm_min_share_log, batch_ntt_min_log, dist_ntt_min_log};
     for (int i = 0; i < 3; ++i) {

@@ -333,6 +333,18 @@ int zkb_dist_connect(const uint8_t* all_handles) {
     return ZKB_OK;
 }
 
+// one process, several devices: the symmetric slices of every bound device, connected through peer access (no handles to exchange)
+int zkb_dist_create_inprocess(uint32_t max_log_n) {
+    if (cur_slot() != 0) { set_error("zkb_dist_create_inprocess must be called from a thread bound to the home device"); return ZKB_ERR_ARG; }
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    int world = 1;
+    while (world * 2 <= device_slots() && world * 2 <= NTT_MAX_RANKS) world *= 2;
+    if (world < 2) { set_error("needs >= 2 bound devices"); return ZKB_ERR_ARG; }
+    if (max_log_n < 11 || max_log_n > 28) { set_error("max_log_n %u out of range [11, 28]", max_log_n); return ZKB_ERR_ARG; }
+    return dist_inprocess_setup(max_log_n, world);
+}
+
 int zkb_dist_destroy(void) {
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     dist_release();
@@ -349,6 +361,7 @@ int zkb_dist_buffers(void** d_in_slice, void** d_out_slice, size_t* slice_bytes)
 }
 
 int zkb_dist_ntt_fr_dev(const void* d_in_slice, void* d_out_slice, const uint64_t omega[4], uint32_t log_n, void* stream) {
+    SlotScope scope(slot_of_device_ptr(d_in_slice ? d_in_slice : d_out_slice));
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
     if (!omega) { set_error("omega is NULL"); return ZKB_ERR_ARG; }

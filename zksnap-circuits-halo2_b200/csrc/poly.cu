@@ -214,12 +214,14 @@ static size_t poly_tmp_bytes(uint64_t n) {  // generous: 4 Fr per chunk on every
 struct Poly {
     DevBuf buf;
     uint64_t n = 0;
+    int slot = 0;   // device slot whose HBM holds it (the slot of the thread that created it)
 };
 static std::map<uint64_t, Poly*>& poly_map() {
     static std::map<uint64_t, Poly*> m;
     return m;
 }
 static uint64_t g_next_poly = 1;
+static std::mutex g_poly_mu;   // the registry is global (handles are unique across devices); entry points lock only their own device
 
 // Buffer pool.  The prover allocates and frees polynomials of two or three sizes (2^k, 2^extended_k) all the time, and
 // cudaMalloc / cudaFree of half a gigabyte cost a device synchronisation each.  Freed buffers are kept (up to a quarter of the
@@ -271,17 +273,28 @@ static void pool_release(DevBuf& b) {
     b.release();
 }
 
+static void poly_erase(uint64_t h) {
+    std::lock_guard<std::mutex> lk(g_poly_mu);
+    poly_map().erase(h);
+}
 static int find_poly(uint64_t h, Poly** out) {
+    std::lock_guard<std::mutex> lk(g_poly_mu);
     auto it = poly_map().find(h);
     if (it == poly_map().end()) { set_error("unknown polynomial handle %llu", (unsigned long long)h); return ZKB_ERR_HANDLE; }
+    if (it->second->slot != cur_slot()) {
+        set_error("polynomial handle %llu lives on device slot %d; this thread acts on slot %d (zkb_thread_bind_device)", (unsigned long long)h, it->second->slot, cur_slot());
+        return ZKB_ERR_HANDLE;
+    }
     *out = it->second;
     return ZKB_OK;
 }
 static int new_poly(uint64_t n, Poly** out, uint64_t* handle) {
     Poly* p = new Poly();
     p->n = n;
+    p->slot = cur_slot();
     int rc = pool_alloc(p->buf, n ? n * 32 : 32);
     if (rc != ZKB_OK) { delete p; return rc; }
+    std::lock_guard<std::mutex> lk(g_poly_mu);
     *handle = g_next_poly++;
     poly_map()[*handle] = p;
     *out = p;
@@ -356,7 +369,7 @@ int zkb_poly_load_file(const char* path, uint64_t offset, size_t n, uint64_t* ha
             if (pin[i]) cudaFreeHost(pin[i]);
             if (ev[i]) cudaEventDestroy(ev[i]);
         }
-        if (code != ZKB_OK) { pool_release(p->buf); delete p; poly_map().erase(*handle); *handle = 0; }
+        if (code != ZKB_OK) { pool_release(p->buf); delete p; poly_erase(*handle); *handle = 0; }
         return code;
     };
     const size_t total = n * 32;
@@ -436,7 +449,7 @@ int zkb_poly_free(uint64_t handle) {
     if (poly_pool_limit() == 0) cudaStreamSynchronize(ctx().stream);
     pool_release(p->buf);  // stream-ordered reuse; a buffer that does not fit in the pool is cudaFree'd (which synchronises)
     delete p;
-    poly_map().erase(handle);
+    poly_erase(handle);
     return ZKB_OK;
 }
 
@@ -454,7 +467,7 @@ int zkb_poly_slice(uint64_t poly, size_t offset, size_t n, uint64_t* out_handle)
         cudaError_t e = cudaMemcpyAsync(q->buf.p, p->buf.as<char>() + offset * 32, n * 32, cudaMemcpyDeviceToDevice, ctx().stream);
         if (e != cudaSuccess) {
             set_error("slice copy failed: %s", cudaGetErrorString(e));
-            pool_release(q->buf); delete q; poly_map().erase(*out_handle); *out_handle = 0;
+            pool_release(q->buf); delete q; poly_erase(*out_handle); *out_handle = 0;
             return ZKB_ERR_CUDA;
         }
     }
@@ -499,7 +512,7 @@ int zkb_poly_coeff_to_extended(uint64_t poly, uint32_t k, uint32_t extended_k, u
     Poly* e;
     ZKB_TRY(new_poly(N, &e, out_handle));
     int rc = domain_dev_by_op(3, p->buf.as<uint4>(), e->buf.as<uint4>(), w.tmp.as<uint4>(), 1, k, extended_k, ctx().stream);
-    if (rc != ZKB_OK) { pool_release(e->buf); delete e; poly_map().erase(*out_handle); *out_handle = 0; }
+    if (rc != ZKB_OK) { pool_release(e->buf); delete e; poly_erase(*out_handle); *out_handle = 0; }
     return rc;
 }
 
@@ -533,7 +546,7 @@ int zkb_poly_kate_division(uint64_t poly, const uint64_t b[4], uint64_t* out_han
     Poly* q;
     ZKB_TRY(new_poly(p->n, &q, out_handle));  // Q_0 .. Q_{n-1}; the quotient is the first n-1 of them (Q_{n-1} = 0)
     int rc = kate_q_dev(p->buf.as<uint4>(), p->n, fr_of(b), q->buf.as<uint4>(), w.tmp.as<uint4>(), ctx().stream);
-    if (rc != ZKB_OK) { pool_release(q->buf); delete q; poly_map().erase(*out_handle); *out_handle = 0; return rc; }
+    if (rc != ZKB_OK) { pool_release(q->buf); delete q; poly_erase(*out_handle); *out_handle = 0; return rc; }
     q->n = p->n - 1;  // upstream returns a.len() - 1 coefficients
     return ZKB_OK;
 }
