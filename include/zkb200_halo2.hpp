@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <utility>
+
 #include "zkb200.h"
 
 namespace halo2 {
@@ -28,6 +30,20 @@ using G1 = std::array<uint64_t, 12>;       // bn256::G1 (x, y, z) Jacobian
 
 inline void check(int rc, const char* what) {
     if (rc != ZKB_OK) throw std::runtime_error(std::string(what) + ": " + zkb_last_error());
+}
+
+// Process set-up: bind the library to `devices` (CUDA ordinals; empty = ZKB_DEVICES or the current device).  With several devices
+// the ONE prover process (create_proof, /root/reference/aggregator/src/wrapper.rs:129-137) reaches all of them behind the same
+// functions below: commits are sharded by SRS point range, batches by column, one large transform over NVLink peer memory.
+inline void init(const std::vector<int>& devices = {}) {
+    check(zkb_init(devices.empty() ? nullptr : devices.data(), (int)devices.size()), "init");
+}
+// the calling thread acts on `device` alone from now on (one host thread per device keeps resident work everywhere)
+inline void bind_thread_to_device(int device) { check(zkb_thread_bind_device(device), "bind_thread_to_device"); }
+inline std::vector<int> bound_devices() {
+    int d[8];
+    const int n = zkb_bound_devices(d, 8);
+    return std::vector<int>(d, d + (n > 8 ? 8 : n));
 }
 
 // arithmetic::best_multiexp(coeffs, bases) -> G1
@@ -230,6 +246,28 @@ class Polynomial {
         return out;
     }
     void mul(const Polynomial& other) { check(zkb_poly_mul(h_, other.h_), "mul"); }
+    // ProvingKey::read(.., RawBytesUnchecked), polynomial by polynomial: n raw Montgomery Fr from the file straight into HBM
+    // (/root/reference/aggregator/src/wrapper.rs:970-988)
+    static Polynomial load_file(const std::string& path, uint64_t offset, size_t n) {
+        Polynomial p;
+        check(zkb_poly_load_file(path.c_str(), offset, n, &p.h_), "Polynomial::load_file");
+        return p;
+    }
+    // self[offset ..] = values: the random blinding rows at the end of a product column computed on the device
+    void write(size_t offset, const std::vector<Fr>& values) {
+        check(zkb_poly_write(h_, offset, values.empty() ? nullptr : values[0].data(), values.size()), "write");
+    }
+    // EvaluationDomain::divide_by_vanishing_poly from the 2^(extended_k - k) distinct values of 1 / (X^n - 1) on the coset
+    void mul_periodic(const std::vector<Fr>& table) {
+        check(zkb_poly_mul_periodic(h_, table.empty() ? nullptr : table[0].data(), (uint32_t)table.size()), "mul_periodic");
+    }
+    // plonk::lookup::prover::permute_expression_pair(input = *this, table) on the usable rows -> (A', S'); throws where upstream
+    // returns Error::ConstraintSystemFailure (an input value that does not occur in the table)
+    std::pair<Polynomial, Polynomial> permute_expression_pair(const Polynomial& table, size_t usable_rows) const {
+        Polynomial a, t;
+        check(zkb_lookup_permute_expression_pair(h_, table.h_, usable_rows, &a.h_, &t.h_), "permute_expression_pair");
+        return {std::move(a), std::move(t)};
+    }
     Polynomial slice(size_t offset, size_t n) const { Polynomial p; check(zkb_poly_slice(h_, offset, n, &p.h_), "slice"); return p; }
 
    private:

@@ -109,6 +109,53 @@ int main(int argc, char** argv) {
         } catch (const std::runtime_error&) {
         }
     }
+    // round-2 interface: lookup permute_expression_pair, blinding-row write, periodic multiply, polynomial file -> HBM, device list
+    {
+        if (halo2::bound_devices().empty()) return fail("bound_devices after use");
+        // input (1, 2, 2, 1, 3, 1, .., ..) against table (3, 1, 2, 2, 1, 1, .., ..), 6 usable rows:
+        //   A' = 1 1 1 2 2 3;  first occurrences at rows 0, 3, 5 -> S' = 1 . . 2 . 3; leftovers 1 1 2 go to rows 4, 2, 1 (popped from the end)
+        auto fr = [&](int v) { halo2::Fr x; std::memcpy(x.data(), in[v - 1], 32); return x; };
+        std::vector<halo2::Fr> inp{fr(1), fr(2), fr(2), fr(1), fr(3), fr(1), fr(8), fr(8)}, tab{fr(3), fr(1), fr(2), fr(2), fr(1), fr(1), fr(7), fr(7)};
+        halo2::Polynomial pi(inp), pt(tab);
+        auto pr = pi.permute_expression_pair(pt, 6);
+        auto a = pr.first.to_vec(), t = pr.second.to_vec();
+        const int want_a[6] = {1, 1, 1, 2, 2, 3}, want_t[6] = {1, 2, 1, 2, 1, 3};
+        for (int i = 0; i < 6; ++i)
+            if (a[i] != fr(want_a[i]) || t[i] != fr(want_t[i])) return fail("permute_expression_pair");
+        if (a[6] != halo2::Fr{0, 0, 0, 0} || t[7] != halo2::Fr{0, 0, 0, 0}) return fail("rows past usable_rows must stay zero");
+        try {
+            std::vector<halo2::Fr> bad = inp;
+            bad[0] = fr(5);
+            halo2::Polynomial pb(bad);
+            pb.permute_expression_pair(pt, 6);
+            return fail("an input value outside the table must throw (ConstraintSystemFailure)");
+        } catch (const std::runtime_error&) {
+        }
+        pr.first.write(6, {fr(4), fr(5)});
+        auto a2 = pr.first.to_vec();
+        if (a2[6] != fr(4) || a2[7] != fr(5) || a2[5] != fr(3)) return fail("Polynomial::write");
+        // periodic multiply by (1, 2): element i times (i even ? 1 : 2) == col + (col masked to odd rows)
+        halo2::Polynomial pm(inp);
+        pm.mul_periodic({fr(1), fr(2)});
+        auto m = pm.to_vec();
+        for (int i = 0; i < 8; ++i)
+            if (m[i] != (i & 1 ? halo2::fr::add(inp[i], inp[i]) : inp[i])) return fail("mul_periodic");
+        // raw limbs from a file straight into a handle
+        const char* path = "/tmp/zkb200_cpp_poly.bin";
+        if (FILE* f = std::fopen(path, "wb")) {
+            std::fwrite("HEAD", 1, 4, f);
+            std::fwrite(inp[0].data(), 32, inp.size(), f);
+            std::fclose(f);
+        } else return fail("cannot write the temporary polynomial file");
+        halo2::Polynomial pf = halo2::Polynomial::load_file(path, 4, 8);
+        if (pf.to_vec() != inp) return fail("Polynomial::load_file");
+        std::remove(path);
+        try {
+            halo2::Polynomial::load_file(path, 0, 8);
+            return fail("a missing file must throw");
+        } catch (const std::runtime_error&) {
+        }
+    }
     std::printf("gpu ok\n");
     return 0;
 }
