@@ -413,7 +413,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
         while (J > 1) {   // CTA-cooperative sums: one or two launches
-            const uint32_t grp = J <= (uint64_t)MSM_ACC_CTA * 8 ? (uint32_t)((J + MSM_ACC_CTA - 1) / MSM_ACC_CTA) : 8u;
+            const uint32_t grp = msm_sum_tree_group(J);
             const uint64_t Jn = (J + (uint64_t)MSM_ACC_CTA * grp - 1) / ((uint64_t)MSM_ACC_CTA * grp);
             MsmSumTreeArgs sa{w.seg[cur].as<uint4>(), w.seg[cur ^ 1].as<uint4>(), J, Jn, grp};
             msm_sum_tree_kernel<<<(unsigned)((uint64_t)g.total_sets * Jn), MSM_ACC_CTA, 0, s>>>(sa);

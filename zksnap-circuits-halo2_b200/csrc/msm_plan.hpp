@@ -46,6 +46,15 @@ inline uint32_t msm_pick_window_table(uint64_t n) {
     return best_c;
 }
 
+// Fan-in of one CTA-tree sum level over J elements per set (msm_sum_tree_kernel: `group` serial additions per thread, then a
+// 7-step tree): the dependent chain is group + 7 per level, so spread the elements over as many CTAs as a single-CTA second
+// level can absorb (128 x 128 elements -> group 1 twice: 16 additions deep; before: 8 + 7, then 1..8 + 7).
+inline uint32_t msm_sum_tree_group(uint64_t J) {
+    if (J <= 128) return 1;
+    const uint64_t g = (J + 128ull * 128 - 1) / (128ull * 128);
+    return (uint32_t)(g < 1 ? 1 : (g > 64 ? 64 : g));
+}
+
 // Launch plan of the accumulation levels (msm.cuh): level 0 cuts `entries` sorted entries into chunks of chunk0 per thread, 128
 // threads per CTA; every CTA leaves two partial entries for the next level; a level that fits one CTA is the last.
 // direct0: level 0 runs without the in-CTA tree (throughput regime: its threads write two partial entries each and the
