@@ -50,10 +50,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const MsmDigitArgs a) {
 }
 
 // the tree phase is kept out of line: its full additions must not raise the register count of the level-0 chunk loop
-__device__ __noinline__ void msm_acc_tree(const MsmAccArgs& a, uint32_t* skey, uint4* sval) {
+__device__ __noinline__ void msm_acc_tree(const MsmAccArgs& a, uint32_t* skey, uint4* sval, uint4* scr) {
     for (uint32_t d = 1; d < MSM_ACC_CTA; d <<= 1) {
-        __syncthreads();
-        msm_acc_phase_combine(a, threadIdx.x, d, MSM_ACC_CTA, skey, sval);
+        const uint32_t pairs = MSM_ACC_CTA / (2 * d);
+        for (uint32_t base = 0; base < pairs; base += COOP_GROUPS) {
+            __syncthreads();   // the previous round's results (other warps) are in place
+            for (uint32_t phase = 0; phase < COOP_PHASES; ++phase) {
+                msm_acc_phase_combine(a, threadIdx.x, d, base, phase, MSM_ACC_CTA, skey, sval, scr);
+                __syncwarp();  // the four lanes of an addition sit in one warp
+            }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) msm_acc_phase_emit(a, blockIdx.x, skey, sval);
@@ -63,8 +69,9 @@ template <bool LEVEL0>
 __global__ void __launch_bounds__(MSM_ACC_CTA, 4) msm_accumulate_kernel(const MsmAccArgs a) {
     __shared__ uint32_t skey[2 * MSM_ACC_CTA];
     __shared__ uint4 sval[2 * MSM_ACC_CTA * 8];
+    __shared__ uint4 scr[COOP_GROUPS * COOP_SCRATCH_FQ * 2];
     msm_acc_phase_chunk<LEVEL0>(a, (uint64_t)blockIdx.x * MSM_ACC_CTA + threadIdx.x, threadIdx.x, skey, sval);
-    msm_acc_tree(a, skey, sval);
+    msm_acc_tree(a, skey, sval, scr);
 }
 
 template <bool LEVEL0>
@@ -76,11 +83,16 @@ __global__ void __launch_bounds__(MSM_ACC_CTA) msm_accumulate_direct_kernel(cons
 
 __global__ void __launch_bounds__(MSM_ACC_CTA) msm_sum_tree_kernel(const MsmSumTreeArgs a) {
     __shared__ uint4 sval[MSM_ACC_CTA * 8];
+    __shared__ uint4 scr[COOP_GROUPS * COOP_SCRATCH_FQ * 2];
     msm_sum_tree_phase_load(a, blockIdx.x, threadIdx.x, sval);
-    for (uint32_t d = MSM_ACC_CTA / 2; d >= 1; d >>= 1) {
-        __syncthreads();
-        msm_sum_tree_phase_step(threadIdx.x, d, sval);
-    }
+    for (uint32_t d = MSM_ACC_CTA / 2; d >= 1; d >>= 1)
+        for (uint32_t base = 0; base < d; base += COOP_GROUPS) {
+            __syncthreads();
+            for (uint32_t phase = 0; phase < COOP_PHASES; ++phase) {
+                msm_sum_tree_phase_step(threadIdx.x, d, base, phase, sval, scr);
+                __syncwarp();
+            }
+        }
     __syncthreads();
     if (threadIdx.x == 0) msm_sum_tree_phase_store(a, blockIdx.x, sval);
 }

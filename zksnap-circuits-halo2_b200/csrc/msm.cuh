@@ -113,6 +113,111 @@ struct MsmAccArgs {
 ZKB_HD void msm_store_xyzz(uint4* base, uint64_t idx, const XYZZ& p) { p.store(base + 8 * idx); }
 ZKB_HD XYZZ msm_load_xyzz(const uint4* base, uint64_t idx) { return XYZZ::load(base + 8 * idx); }
 
+// ---- lane-cooperative XYZZ addition (the serial tails of a commit) ---------------------------------------------------------------
+// One full addition is 14 field products of which at most 4 are independent at any time; on one thread that is 14 dependent
+// product-times (~4 us), and the finishing levels of a commit are chains of such additions with most lanes idle.  Here FOUR
+// ADJACENT LANES share one addition: four product phases (u1 u2 s1 s2 | pp rr zz12 zzz12 | ppp q zz3 | t v zzz3) exchanged through a
+// small shared-memory scratch, so the chain is 4 product-times long.  Same formulas as xyzz_add (add-2008-s), same canonical
+// values, exceptional cases handled exactly: an identity operand returns the other one, equal points are doubled (serially, by
+// lane 0: it does not occur for bucket sums of an honest commit but must be right), opposite points give the identity.
+// Every phase is a per-thread function of (role = lane & 3, operands, scratch); the kernel puts a barrier between phases and
+// the CPU emulator runs them in the same order.
+constexpr uint32_t COOP_SCRATCH_FQ = 14;   // Fq slots per addition in flight
+enum : uint32_t { COOP_U1, COOP_U2, COOP_S1, COOP_S2, COOP_PP, COOP_RR, COOP_ZZ12, COOP_ZZZ12, COOP_PPP, COOP_Q, COOP_ZZ3, COOP_T, COOP_V, COOP_ZZZ3 };
+enum : uint32_t { COOP_ADD = 0, COOP_TAKE_A = 1, COOP_TAKE_B = 2 };
+
+struct CoopOperands {
+    const uint4* a;   // XYZZ (8 uint4)
+    const uint4* b;
+    uint4* scr;       // COOP_SCRATCH_FQ x 2 uint4
+    uint4* out;       // XYZZ, may alias a
+};
+ZKB_HD Fq coop_get(const uint4* scr, uint32_t slot) { return Fq::load(scr + 2 * slot); }
+ZKB_HD void coop_put(uint4* scr, uint32_t slot, const Fq& v) { v.store(scr + 2 * slot); }
+ZKB_HD Fq coop_coord(const uint4* p, uint32_t k) { return Fq::load(p + 2 * k); }   // 0 x, 1 y, 2 zz, 3 zzz
+// which of the three outcomes the operands' identity flags select (every lane evaluates it: two 32-byte loads)
+ZKB_HD uint32_t coop_case(const CoopOperands& o) {
+    if (coop_coord(o.b, 2).is_zero()) return COOP_TAKE_A;
+    if (coop_coord(o.a, 2).is_zero()) return COOP_TAKE_B;
+    return COOP_ADD;
+}
+// The four product phases.  Every lane runs the SAME instruction stream — operands are selected by role with predicated moves,
+// then one fp_mul — so the four products of a phase issue as one warp instruction stream (a switch over the role would
+// serialise them: lanes of one warp cannot run different code at the same time).
+ZKB_HD Fq coop_sel(bool c, const Fq& x, const Fq& y) {
+    Fq r;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; ++i) r.l[i] = c ? x.l[i] : y.l[i];
+    return r;
+}
+ZKB_HD void coop_add_p1(const CoopOperands& o, uint32_t role) {   // u1 = X1 ZZ2, u2 = X2 ZZ1, s1 = Y1 ZZZ2, s2 = Y2 ZZZ1
+    if (coop_case(o) != COOP_ADD) return;
+    const uint4* first = (role & 1) ? o.b : o.a;
+    const uint4* second = (role & 1) ? o.a : o.b;
+    const uint32_t hi = role >> 1;   // 0: x, zz   1: y, zzz
+    coop_put(o.scr, COOP_U1 + role, fp_mul(coop_coord(first, hi), coop_coord(second, 2 + hi)));
+}
+ZKB_HD void coop_add_p2(const CoopOperands& o, uint32_t role) {   // pp = (u2 - u1)^2, rr = (s2 - s1)^2, zz12, zzz12
+    if (coop_case(o) != COOP_ADD) return;
+    const bool diff = role < 2;
+    const uint32_t pr = 2 * (role & 1);
+    const Fq d = fp_sub(coop_get(o.scr, COOP_U1 + pr + 1), coop_get(o.scr, COOP_U1 + pr));   // p (role 0) / r (role 1)
+    const Fq x = coop_sel(diff, d, coop_coord(o.a, role));       // roles 2, 3: ZZ1 / ZZZ1
+    const Fq y = coop_sel(diff, d, coop_coord(o.b, role));       //             ZZ2 / ZZZ2
+    coop_put(o.scr, COOP_PP + role, fp_mul(x, y));
+}
+ZKB_HD bool coop_p_is_zero(const CoopOperands& o) { return coop_get(o.scr, COOP_U2) == coop_get(o.scr, COOP_U1); }
+ZKB_HD void coop_add_p3(const CoopOperands& o, uint32_t role) {   // ppp = p pp, q = u1 pp, zz3 = zz12 pp   (role 3: nothing to do)
+    if (coop_case(o) != COOP_ADD || coop_p_is_zero(o)) return;
+    const Fq pp = coop_get(o.scr, COOP_PP);
+    const Fq p = fp_sub(coop_get(o.scr, COOP_U2), coop_get(o.scr, COOP_U1));
+    const Fq x = coop_sel(role == 0, p, coop_get(o.scr, role == 1 ? COOP_U1 : COOP_ZZ12));
+    const Fq z = fp_mul(x, pp);
+    if (role < 3) coop_put(o.scr, COOP_PPP + role, z);
+}
+ZKB_HD void coop_add_p4(const CoopOperands& o, uint32_t role) {   // t = r (q - x3), v = s1 ppp, zzz3 = zzz12 ppp
+    if (coop_case(o) != COOP_ADD || coop_p_is_zero(o)) return;
+    const Fq ppp = coop_get(o.scr, COOP_PPP);
+    const Fq q = coop_get(o.scr, COOP_Q);
+    const Fq x3 = fp_sub(fp_sub(coop_get(o.scr, COOP_RR), ppp), fp_dbl(q));
+    const Fq r = fp_sub(coop_get(o.scr, COOP_S2), coop_get(o.scr, COOP_S1));
+    const Fq x = coop_sel(role == 0, r, coop_get(o.scr, role == 1 ? COOP_S1 : COOP_ZZZ12));
+    const Fq y = coop_sel(role == 0, fp_sub(q, x3), ppp);
+    const Fq z = fp_mul(x, y);
+    if (role < 3) coop_put(o.scr, COOP_T + role, z);
+    if (role == 3) coop_put(o.scr, COOP_PP, x3);   // pp is dead (read above, before any lane of this group stores): its slot carries x3
+}
+// lane 0 assembles the result (and handles the outcomes that need no products, or the serial doubling)
+ZKB_HD void coop_add_p5(const CoopOperands& o, uint32_t role) {
+    if (role != 0) return;
+    const uint32_t c = coop_case(o);
+    if (c == COOP_TAKE_A) { if (o.out != o.a) msm_store_xyzz(o.out, 0, msm_load_xyzz(o.a, 0)); return; }
+    if (c == COOP_TAKE_B) { msm_store_xyzz(o.out, 0, msm_load_xyzz(o.b, 0)); return; }
+    if (coop_p_is_zero(o)) {
+        if (coop_get(o.scr, COOP_S2) == coop_get(o.scr, COOP_S1)) msm_store_xyzz(o.out, 0, xyzz_double(msm_load_xyzz(o.a, 0)));
+        else msm_store_xyzz(o.out, 0, XYZZ::identity());
+        return;
+    }
+    XYZZ r;
+    r.x = coop_get(o.scr, COOP_PP);
+    r.y = fp_sub(coop_get(o.scr, COOP_T), coop_get(o.scr, COOP_V));
+    r.zz = coop_get(o.scr, COOP_ZZ3);
+    r.zzz = coop_get(o.scr, COOP_ZZZ3);
+    msm_store_xyzz(o.out, 0, r);
+}
+ZKB_HD void coop_add_phase(uint32_t phase, const CoopOperands& o, uint32_t role) {
+    switch (phase) {
+        case 0: coop_add_p1(o, role); break;
+        case 1: coop_add_p2(o, role); break;
+        case 2: coop_add_p3(o, role); break;
+        case 3: coop_add_p4(o, role); break;
+        default: coop_add_p5(o, role); break;
+    }
+}
+constexpr uint32_t COOP_PHASES = 5;
+
 // One CTA of MSM_ACC_CTA threads.  Phase 1: every thread sums its chunk; runs strictly inside the chunk are complete buckets
 // (stored), the first and the last run (which may continue in the neighbouring chunks) are left as the thread's SUMMARY in shared
 // memory: skey / sval [2 tid] = head run, [2 tid + 1] = tail run (INVALID key = absent; a chunk with one run has a head only).
@@ -122,6 +227,7 @@ ZKB_HD XYZZ msm_load_xyzz(const uint4* base, uint64_t idx) { return XYZZ::load(b
 // list shrinks by chunk x 64 per level, so two or three launches finish any MSM), or to the buckets when this CTA is the last.
 // Every bucket is written exactly once over all levels.
 constexpr uint32_t MSM_ACC_CTA = 128;
+constexpr uint32_t COOP_GROUPS = MSM_ACC_CTA / 4;   // lane-cooperative additions in flight per CTA
 
 template <bool LEVEL0>
 ZKB_HD void msm_acc_phase_chunk(const MsmAccArgs& a, uint64_t t, uint32_t tid, uint32_t* skey, uint4* sval) {
@@ -177,40 +283,41 @@ ZKB_HD void msm_acc_thread_direct(const MsmAccArgs& a, uint64_t t) {
     msm_acc_phase_chunk<LEVEL0>(a, t, 0, a.pkeys_out + 2 * t, a.pvals_out + 16 * t);
 }
 
-// tree step d: summary[l] (threads l .. l+d-1) absorbs summary[l+d] (threads l+d .. l+2d-1), l = 2 d j.  The combinations of a
-// step are done by the FIRST nthreads / 2d threads (pair j by thread j), so the full additions fill whole warps instead of
-// being spread one lane per warp.
-ZKB_HD void msm_acc_phase_combine(const MsmAccArgs& a, uint32_t tid, uint32_t d, uint32_t nthreads, uint32_t* skey, uint4* sval) {
-    const uint32_t left = 2 * d * tid;
+// tree step d, round `base`: summary[l] (threads l .. l+d-1) absorbs summary[l+d] (threads l+d .. l+2d-1), l = 2 d pair,
+// pair = base + tid / 4.  The (at most one) full addition of a combination is shared by FOUR lanes (lane-cooperative addition
+// below: 4 product-times instead of 14) and the pairs of a step are taken by the first threads, so the additions fill whole warps;
+// `phase` runs 0 .. COOP_PHASES-1 with a barrier in between, the bookkeeping (keys, copies, stores of runs that became complete)
+// is done by lane 0 in the last phase.
+ZKB_HD void msm_acc_phase_combine(const MsmAccArgs& a, uint32_t tid, uint32_t d, uint32_t base, uint32_t phase, uint32_t nthreads,
+                                  uint32_t* skey, uint4* sval, uint4* scr) {
+    const uint32_t pair = base + (tid >> 2), role = tid & 3;
+    const uint32_t left = 2 * d * pair;
     if (left + d >= nthreads) return;
     const uint32_t ia = 2 * left, ib = 2 * (left + d);
     const uint32_t ah = skey[ia], at = skey[ia + 1], bh = skey[ib], bt = skey[ib + 1];
     if (bh == MSM_INVALID_KEY) return;  // right half empty
+    const bool book = phase + 1 == COOP_PHASES && role == 0;
     auto copy = [&](uint32_t dst, uint32_t src) {
         for (int q = 0; q < 8; ++q) sval[8 * dst + q] = sval[8 * src + q];
     };
     if (ah == MSM_INVALID_KEY) {        // left half empty
-        skey[ia] = bh; skey[ia + 1] = bt;
-        copy(ia, ib);
-        if (bt != MSM_INVALID_KEY) copy(ia + 1, ib + 1);
+        if (book) {
+            skey[ia] = bh; skey[ia + 1] = bt;
+            copy(ia, ib);
+            if (bt != MSM_INVALID_KEY) copy(ia + 1, ib + 1);
+        }
         return;
     }
     const bool a_multi = at != MSM_INVALID_KEY, b_multi = bt != MSM_INVALID_KEY;
     const uint32_t a_last = a_multi ? at : ah;
-    if (a_last == bh) {                 // the run continues across the boundary
-        XYZZ m = msm_load_xyzz(sval, a_multi ? ia + 1 : ia);
-        xyzz_add(m, msm_load_xyzz(sval, ib));
-        if (a_multi && b_multi) {       // now strictly inside the combined range: complete
-            msm_store_xyzz(a.buckets, a_last, m);
-            skey[ia + 1] = bt;
-            copy(ia + 1, ib + 1);
-        } else if (a_multi) {
-            msm_store_xyzz(sval, ia + 1, m);
-        } else {
-            msm_store_xyzz(sval, ia, m);
-            if (b_multi) { skey[ia + 1] = bt; copy(ia + 1, ib + 1); }
-        }
-    } else {
+    if (a_last == bh) {                 // the run continues across the boundary: one full addition
+        const uint32_t sa = a_multi ? ia + 1 : ia;
+        // both halves multi-run: the merged run is now strictly inside the combined range, i.e. a complete bucket
+        uint4* out = (a_multi && b_multi) ? a.buckets + 8 * (uint64_t)a_last : sval + 8 * sa;
+        CoopOperands o{sval + 8 * sa, sval + 8 * ib, scr + 2 * COOP_SCRATCH_FQ * (tid >> 2), out};
+        coop_add_phase(phase, o, role);
+        if (book && b_multi) { skey[ia + 1] = bt; copy(ia + 1, ib + 1); }
+    } else if (book) {
         if (a_multi) msm_store_xyzz(a.buckets, at, msm_load_xyzz(sval, ia + 1));
         if (b_multi) {
             msm_store_xyzz(a.buckets, bh, msm_load_xyzz(sval, ib));
@@ -311,11 +418,12 @@ ZKB_HD void msm_sum_tree_phase_load(const MsmSumTreeArgs& a, uint64_t cta, uint3
     for (uint32_t i = 0; i < a.group && first + i < a.in_per_set; ++i) xyzz_add(acc, msm_load_xyzz(a.in, set * a.in_per_set + first + i));
     msm_store_xyzz(sval, tid, acc);
 }
-ZKB_HD void msm_sum_tree_phase_step(uint32_t tid, uint32_t d, uint4* sval) {
-    if (tid >= d) return;
-    XYZZ x = msm_load_xyzz(sval, tid);
-    xyzz_add(x, msm_load_xyzz(sval, tid + d));
-    msm_store_xyzz(sval, tid, x);
+// tree step d, round `base`: pair t = base + tid / 4 (t < d) is sval[t] += sval[t + d], shared by four lanes; `phase` of COOP_PHASES
+ZKB_HD void msm_sum_tree_phase_step(uint32_t tid, uint32_t d, uint32_t base, uint32_t phase, uint4* sval, uint4* scr) {
+    const uint32_t t = base + (tid >> 2);
+    if (t >= d) return;
+    CoopOperands o{sval + 8 * t, sval + 8 * (t + d), scr + 2 * COOP_SCRATCH_FQ * (tid >> 2), sval + 8 * t};
+    coop_add_phase(phase, o, tid & 3);
 }
 ZKB_HD void msm_sum_tree_phase_store(const MsmSumTreeArgs& a, uint64_t cta, const uint4* sval) {
     msm_store_xyzz(a.out, cta, msm_load_xyzz(sval, 0));
