@@ -114,6 +114,24 @@ def test_msm_level0_throughput_form(oracle, n, c, chunk):
     assert (emu.msm(s, b, c=c, chunk=chunk) == want).all()
 
 
+@pytest.mark.parametrize("n,c", [(700, 6), (3000, 9), (64, 4), (300, 12)])
+def test_msm_segment_sum_both_forms(oracle, n, c):
+    """The bucket reduction's segment sum as one thread per segment (throughput form) and as four lanes per segment in lock-step
+    phases (lane-cooperative additions and doublings, latency form): both against the oracle, repeated bases included (doubling)."""
+    s = random_field(n, 41 + n)
+    b = oracle.g1_fixed_base_mul(random_field(n, 42 + n))
+    b[1] = b[0]
+    s[1] = s[0]
+    want = oracle.best_multiexp(s, b)
+    for coop in (0, 1):
+        emu.lib().zkb_emu_msm_set_reduce_coop(coop)
+        try:
+            assert (emu.msm(s, b, c=c) == want).all()
+            assert (emu.msm(s, b, c=c, table=True) == want).all()
+        finally:
+            emu.lib().zkb_emu_msm_set_reduce_coop(1)
+
+
 def test_msm_edge_cases(oracle):
     n = 300
     b = _bases(oracle, n, 5)

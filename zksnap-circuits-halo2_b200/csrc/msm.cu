@@ -105,6 +105,23 @@ __global__ void __launch_bounds__(128) msm_reduce_segment_kernel(const MsmReduce
     msm_reduce_segment_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+// four lanes per segment, lock-step phases (msm.cuh): the latency-regime form of the segment sum
+__global__ void __launch_bounds__(MSM_ACC_CTA) msm_reduce_segment_coop_kernel(const MsmReduceArgs a) {
+    __shared__ uint4 state[COOP_GROUPS * 3 * 8];
+    __shared__ uint4 scr[COOP_GROUPS * COOP_SCRATCH_FQ * 2];
+    const uint32_t g = threadIdx.x >> 2, role = threadIdx.x & 3;
+    const uint64_t t = (uint64_t)blockIdx.x * COOP_GROUPS + g;
+    uint4* st = state + 24 * g;
+    uint4* sc = scr + 2 * COOP_SCRATCH_FQ * g;
+    msm_reduce_coop_init(role, st);
+    __syncwarp();
+    const uint32_t steps = msm_reduce_coop_steps(a);
+    for (uint32_t s = 0; s < steps; ++s) {
+        msm_reduce_coop_step(a, t, role, s, st, sc);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(128) msm_finalize_kernel(const MsmFinalArgs a) {
     msm_finalize_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
@@ -421,7 +438,12 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         r.buckets = bucket_main; r.c = g.c; r.nwin = g.total_sets; r.log_m = g.log_m;
         r.seg_out = w.seg[0].as<uint4>();
         uint64_t J = J0;
-        msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.total_sets * J, 128), 128, 0, s>>>(r);
+        // few segments (latency regime): four lanes share a segment; many: one thread per segment (throughput)
+        static const uint64_t coop_max = getenv("ZKB_MSM_REDUCE_COOP_MAX") ? strtoull(getenv("ZKB_MSM_REDUCE_COOP_MAX"), nullptr, 10) : (1ull << 14);   // 4 lanes x 2^14 = one wave of threads
+        if ((uint64_t)g.total_sets * J <= coop_max)
+            msm_reduce_segment_coop_kernel<<<blocks_for((uint64_t)g.total_sets * J, COOP_GROUPS), MSM_ACC_CTA, 0, s>>>(r);
+        else
+            msm_reduce_segment_kernel<<<blocks_for((uint64_t)g.total_sets * J, 128), 128, 0, s>>>(r);
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
         while (J > 1) {   // CTA-cooperative sums: one or two launches

@@ -402,6 +402,87 @@ ZKB_HD void msm_reduce_segment_thread(const MsmReduceArgs& a, uint64_t t) {
     msm_store_xyzz(a.seg_out, t, acc);
 }
 
+// ---- the same segment sum shared by four lanes per segment (latency regime) ----------------------------------------------------
+// Lane-cooperative doubling [dbl-2008-s-1, a = 0]: three product phases (v xx | w s mm zz3 | t wy zzz3) + assembly.
+enum : uint32_t { COOPD_V = 0, COOPD_XX, COOPD_W, COOPD_S, COOPD_MM, COOPD_ZZ3, COOPD_T, COOPD_WY, COOPD_ZZZ3, COOPD_X3 };
+constexpr uint32_t COOP_DBL_PHASES = 4;
+ZKB_HD void coop_dbl_phase(uint32_t phase, const uint4* p, uint4* scr, uint4* out, uint32_t role) {
+    if (coop_coord(p, 2).is_zero()) {   // identity: stays the identity
+        if (phase + 1 == COOP_DBL_PHASES && role == 0 && out != p) msm_store_xyzz(out, 0, XYZZ::identity());
+        return;
+    }
+    if (phase == 0) {            // v = (2Y)^2, xx = X^2
+        const Fq y = coop_coord(p, 1);
+        const Fq x = coop_sel(role == 0, fp_dbl(y), coop_coord(p, 0));
+        const Fq z = fp_mul(x, x);
+        if (role < 2) coop_put(scr, COOPD_V + role, z);
+    } else if (phase == 1) {     // w = u v, s = X v, mm = (3 xx)^2, zz3 = v ZZ
+        const Fq v = coop_get(scr, COOPD_V), xx = coop_get(scr, COOPD_XX);
+        const Fq m = fp_add(fp_dbl(xx), xx);
+        const Fq u = fp_dbl(coop_coord(p, 1));
+        const Fq x = coop_sel(role == 0, u, coop_sel(role == 1, coop_coord(p, 0), coop_sel(role == 2, m, coop_coord(p, 2))));
+        const Fq y = coop_sel(role == 2, m, v);
+        coop_put(scr, COOPD_W + role, fp_mul(x, y));
+    } else if (phase == 2) {     // t = m (s - x3), wy = w Y, zzz3 = w ZZZ
+        const Fq xx = coop_get(scr, COOPD_XX), sv = coop_get(scr, COOPD_S), w = coop_get(scr, COOPD_W);
+        const Fq m = fp_add(fp_dbl(xx), xx);
+        const Fq x3 = fp_sub(coop_get(scr, COOPD_MM), fp_dbl(sv));
+        const Fq x = coop_sel(role == 0, m, w);
+        const Fq y = coop_sel(role == 0, fp_sub(sv, x3), coop_coord(p, role == 1 ? 1 : 3));
+        const Fq z = fp_mul(x, y);
+        if (role < 3) coop_put(scr, COOPD_T + role, z);
+        if (role == 3) coop_put(scr, COOPD_X3, x3);
+    } else if (role == 0) {
+        XYZZ r;
+        r.x = coop_get(scr, COOPD_X3);
+        r.y = fp_sub(coop_get(scr, COOPD_T), coop_get(scr, COOPD_WY));
+        r.zz = coop_get(scr, COOPD_ZZ3);
+        r.zzz = coop_get(scr, COOPD_ZZZ3);
+        msm_store_xyzz(out, 0, r);
+    }
+}
+
+// Number of lock-step steps of one segment: 2m additions, then (segment offset) * (segment sum) by double-and-add over the log_j
+// bits of j (every bit pays its conditional addition's phases: the lanes of a warp hold different j), log_m more doublings, and the
+// final addition.
+ZKB_HD uint32_t msm_reduce_coop_steps(const MsmReduceArgs& a) {
+    const uint32_t log_j = a.c - 1 - a.log_m, m = 1u << a.log_m;
+    return 2 * m * COOP_PHASES + log_j * (COOP_DBL_PHASES + COOP_PHASES) + a.log_m * COOP_DBL_PHASES + COOP_PHASES;
+}
+// state: run, acc, off (3 XYZZ) of the group; scr: COOP_SCRATCH_FQ Fq; segment t = w*J + j as in msm_reduce_segment_thread
+ZKB_HD void msm_reduce_coop_init(uint32_t role, uint4* state) {
+    if (role < 3) msm_store_xyzz(state, role, XYZZ::identity());
+}
+ZKB_HD void msm_reduce_coop_step(const MsmReduceArgs& a, uint64_t t, uint32_t role, uint32_t step, uint4* state, uint4* scr) {
+    const uint32_t log_j = a.c - 1 - a.log_m;
+    if (t >= ((uint64_t)a.nwin << log_j)) return;
+    const uint32_t w = (uint32_t)(t >> log_j), j = (uint32_t)(t & ((1u << log_j) - 1));
+    const uint32_t m = 1u << a.log_m;
+    const uint64_t first = ((uint64_t)w << (a.c - 1)) + ((uint64_t)j << a.log_m);
+    uint4* run = state;
+    uint4* acc = state + 8;
+    uint4* off = state + 16;
+    uint32_t s = step;
+    if (s < 2 * m * COOP_PHASES) {                      // run += B[i]; acc += run   for i = m-1 .. 0
+        const uint32_t k = s / COOP_PHASES, i = m - 1 - k / 2;
+        CoopOperands o = (k & 1) ? CoopOperands{acc, run, scr, acc} : CoopOperands{run, a.buckets + 8 * (first + i), scr, run};
+        coop_add_phase(s % COOP_PHASES, o, role);
+        return;
+    }
+    s -= 2 * m * COOP_PHASES;
+    const uint32_t per_bit = COOP_DBL_PHASES + COOP_PHASES;
+    if (s < log_j * per_bit) {                          // off = 2 off (+ run when the bit of j is set), from the top bit
+        const uint32_t b = log_j - 1 - s / per_bit, q = s % per_bit;
+        if (q < COOP_DBL_PHASES) coop_dbl_phase(q, off, scr, off, role);
+        else if ((j >> b) & 1) coop_add_phase(q - COOP_DBL_PHASES, CoopOperands{off, run, scr, off}, role);
+        return;
+    }
+    s -= log_j * per_bit;
+    if (s < a.log_m * COOP_DBL_PHASES) { coop_dbl_phase(s % COOP_DBL_PHASES, off, scr, off, role); return; }   // * m
+    s -= a.log_m * COOP_DBL_PHASES;
+    coop_add_phase(s, CoopOperands{acc, off, scr, a.seg_out + 8 * t}, role);
+}
+
 // CTA-cooperative sum: CTA (set, tile) adds up to MSM_ACC_CTA * group consecutive elements of its set — `group` serial
 // additions per thread, then a log2(MSM_ACC_CTA)-step tree in shared memory — so a whole set of segment sums is folded in one
 // or two launches whose dependent chains are ~15 additions long (the serial fan-in-8 chain it replaces took five launches).
