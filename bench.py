@@ -361,6 +361,34 @@ def headline_msm(env: Env, clocks: ClockSampler):
     plain.close()
     lib.zkb_srs_set_precompute(2)
     del bases
+    # ---- the same commit for a WITNESS-LIKE column (BASELINE sweep distribution W: 50 % zero, 25 % < 2^16, 20 % < 2^88, 5 % uniform —
+    # the shape of halo2-base advice columns): zero digits are never emitted, so the cost follows the non-zero digits
+    rng = np.random.default_rng(0x517 + env.rank)
+    w_np = scal_np.copy()
+    u = rng.random(n)
+    w_np[u < 0.5] = 0
+    for lo_, hi_, nbytes in ((0.5, 0.75, 2), (0.75, 0.95, 11)):
+        m_ = (u >= lo_) & (u < hi_)
+        pool = np.zeros((4096, 4), dtype=np.uint64)
+        raw = rng.integers(0, 256, size=(4096, nbytes), dtype=np.uint64)
+        vals_ = [sum(int(b) << (8 * j) for j, b in enumerate(row)) for row in raw]
+        R_ = (1 << 256) % 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+        for i_, v_ in enumerate(vals_):
+            mv = v_ * R_ % 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+            pool[i_] = [(mv >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
+        w_np[m_] = pool[rng.integers(0, 4096, int(m_.sum()))]
+    d_w = torch.from_numpy(w_np.view(np.int64)).to(env.dev)
+
+    def step_w():
+        env.check(lib.zkb_msm_g1_srs_dev(params.handle_g, 0, env.dptr(d_w), n, outp, env.sptr))
+
+    step_w()
+    w_ok = bool((out[:8] == known_dlog_point(w_np, dlog)).all())
+    w_ms = env.timed_events(step_w, max(3, args.steps // 2))
+    w_ent = ctypes.c_uint64(0)
+    lib.zkb_msm_last_entries(ctypes.byref(w_ent))
+    parity = parity and w_ok
+    del d_w, w_np
     # ---- integer-pipe peak (measured here) and the roofline of the dominant kernel
     peak = ctypes.c_double(0)
     lib.zkb_measure_imad_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
@@ -391,6 +419,9 @@ def headline_msm(env: Env, clocks: ClockSampler):
             "e2e_pageable": {"value": env.world * n / (pg_ms * 1e-3), "unit": "pts/s", "ms_per_step": pg_ms,
                              "note": "the same call from pageable memory (a Rust Vec<Fr>): staged through pinned buffers by host threads"},
             "no_table_ms_per_step": no_table_ms,
+            "witness_like": {"workload": "the same 2^%d-point commit for a witness-like column (50 %% zero, 25 %% < 2^16, 20 %% < 2^88, 5 %% uniform)" % LOG_N_MSM,
+                             "ms_per_step": w_ms, "value": env.world * n / (w_ms * 1e-3), "unit": "pts/s", "bucket_additions": int(w_ent.value),
+                             "parity_checked": w_ok},
             "config": {"workload": WORKLOAD, "sharding": "srs_point_range_per_rank, host fold",
                        "l2": "inputs_exceed_l2 (512 MiB scalars + 1 GiB bases per step)", "window_bits": c_bits.value,
                        "windows": n_win.value, "srs_window_table_bytes": int(t_bytes.value), "srs_window_table_build_s": table_build_s,
@@ -1285,7 +1316,7 @@ def main():
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
             "config": head["config"], "e2e": head["e2e"], "e2e_pageable": head["e2e_pageable"],
-            "no_table_ms_per_step": head["no_table_ms_per_step"],
+            "no_table_ms_per_step": head["no_table_ms_per_step"], "witness_like": head["witness_like"],
             "gpu_launches": int(env.launches), "parity_checked": all_ok, "parity": parity, "roofline": head["roofline"],
             "cpu_baseline": cpu, "clocks": clock_info, "ntt": ntt_obj, "quotient": quot_obj,
             "sharded_ntt": sharded_obj, "sharded_quotient": sq_obj,

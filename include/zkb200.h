@@ -374,6 +374,11 @@ int zkb_dist_ntt_fr(const uint64_t* in_slice, uint64_t* out_slice, const uint64_
 int zkb_dist_ntt_fr_dev(const void* d_in_slice, void* d_out_slice, const uint64_t omega[4], uint32_t log_n, void* stream);
 int zkb_dist_buffers(void** d_in_slice, void** d_out_slice, size_t* slice_bytes);
 int zkb_dist_status(void* stream);
+/* Bound of the device-side barrier waits (default 120 s, or ZKB_DIST_TIMEOUT_MS; 0 restores the default).  When a peer never
+ * arrives the waiting rank's remaining NTT passes return at once (no half-exchanged data is read or written), zkb_dist_status /
+ * zkb_dist_ntt_fr report ZKB_ERR_CUDA once and clear the flag.  The ranks' barrier epochs are then out of step: every rank must
+ * zkb_dist_destroy and create / connect again before the next collective (the in-process form does that by itself). */
+int zkb_dist_set_timeout_ms(uint64_t ms);
 
 /* ---- host memory and the transfer scheduler --------------------------------------------------------------------
  * The host-buffer batch entry points (zkb_*_batch, and the single-column forms through them) run a three-stream

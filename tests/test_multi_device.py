@@ -250,3 +250,56 @@ def test_inprocess_sharded_ntt_on_device_slices(multi):
         list(pool.map(rank, range(world)))
     lib.zkb_dist_destroy()
     assert (np.concatenate(outs) == want).all()
+
+
+def test_sharded_ntt_peer_never_arrives_is_an_error_not_a_hang(multi):
+    """One rank calls the collective, the other never does: the device-side barrier gives up after the configured bound, the
+    remaining passes return without touching half-exchanged data, zkb_dist_status reports the failure ONCE, and after the contexts
+    are rebuilt the same transform succeeds."""
+    torch = pytest.importorskip("torch")
+    import threading
+    lib = zkb.lib()
+    k = 14
+    n = 1 << k
+    a = random_field(n, 61)
+    w = zkb.omega(k)
+    wp = w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+    world = 1
+    while world * 2 <= len(multi):
+        world *= 2
+    ln = n // world
+    lib.zkb_dist_set_timeout_ms(300)
+    try:
+        assert lib.zkb_dist_create_inprocess(k) == 0, lib.zkb_last_error()
+        res = {}
+
+        def lonely():
+            assert lib.zkb_thread_bind_device(multi[0]) == 0
+            dev = torch.device("cuda", multi[0])
+            d_in = torch.from_numpy(a[:ln].view(np.int64).copy()).to(dev)
+            d_out = torch.zeros_like(d_in)
+            st = torch.cuda.Stream(device=dev)
+            sp = ctypes.c_void_p(st.cuda_stream)
+            assert lib.zkb_dist_ntt_fr_dev(ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr()), wp, k, sp) == 0
+            res["first"] = lib.zkb_dist_status(sp)
+            res["msg"] = lib.zkb_last_error().decode()
+            res["second"] = lib.zkb_dist_status(sp)       # reported once, then cleared
+
+        t = threading.Thread(target=lonely)
+        t.start()
+        t.join(timeout=30)
+        assert not t.is_alive(), "the lonely rank hung"
+        assert res["first"] != 0 and "never arrived" in res["msg"]
+        assert res["second"] == 0
+        lib.zkb_dist_destroy()
+        lib.zkb_dist_set_timeout_ms(0)
+        # rebuilt contexts: the host-buffer entry point (in-process sharding) works again
+        want = a.copy()
+        lib.zkb_multi_device_set(10, 10, 28)
+        zkb.best_fft(want, w, k)
+        lib.zkb_multi_device_set(10, 10, 12)
+        got = a.copy()
+        zkb.best_fft(got, w, k)
+        assert (got == want).all()
+    finally:
+        lib.zkb_dist_set_timeout_ms(0)

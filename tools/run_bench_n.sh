@@ -19,7 +19,7 @@ drop=("workload","note","sharding","exchange","peak_source","traffic_source","sa
 def short(o):
     if isinstance(o,dict): return {k:short(v) for k,v in o.items() if k not in drop}
     return o
-for k in ("value","ms_per_step","e2e","e2e_pageable","no_table_ms_per_step","parity","ntt","sharded_ntt","sharded_quotient","wrapper_replay","msm_split","voter_replay","st_replay","single_process","sweep","bench_wall_s"):
+for k in ("value","ms_per_step","e2e","e2e_pageable","no_table_ms_per_step","witness_like","parity","ntt","sharded_ntt","sharded_quotient","wrapper_replay","msm_split","voter_replay","st_replay","single_process","sweep","bench_wall_s"):
     print(k, json.dumps(short(l.get(k)) if k!="parity" else l.get(k)))
 print("roofline", json.dumps({k:v for k,v in l["roofline"].items() if k in ("frac","ms_per_launch","other_ms","share_of_step")}))
 PY

@@ -119,6 +119,7 @@ def load() -> ctypes.CDLL:
         "zkb_dist_ntt_fr_dev": [vp, vp, u64p, u32, vp],
         "zkb_dist_buffers": [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(sz)],
         "zkb_dist_status": [vp],
+        "zkb_dist_set_timeout_ms": [u64],
         "zkb_host_register": [vp, sz],
         "zkb_host_unregister": [vp],
         "zkb_pipeline_set": [ci, sz],

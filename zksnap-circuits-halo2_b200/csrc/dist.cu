@@ -68,6 +68,13 @@ __global__ void dist_barrier_kernel(const DistBarrierArgs a) {
     __threadfence_system();
 }
 
+static unsigned long long g_dist_timeout_ms = 0;   // 0: ZKB_DIST_TIMEOUT_MS or 120 s
+static unsigned long long dist_timeout_ms() {
+    if (g_dist_timeout_ms) return g_dist_timeout_ms;
+    static const unsigned long long env = getenv("ZKB_DIST_TIMEOUT_MS") ? strtoull(getenv("ZKB_DIST_TIMEOUT_MS"), nullptr, 10) : 120000ull;
+    return env ? env : 120000ull;
+}
+
 static int dist_barrier(cudaStream_t s) {
     DistCtx& d = dctx();
     DistBarrierArgs a{};
@@ -78,8 +85,7 @@ static int dist_barrier(cudaStream_t s) {
     a.epoch = ++d.epoch;
     // Ranks are independent processes (or threads): a first-call plan build or a large pageable staging copy on one of them can
     // delay its arrival by seconds.  Default 120 s, ZKB_DIST_TIMEOUT_MS overrides.
-    static const unsigned long long timeout_ms = getenv("ZKB_DIST_TIMEOUT_MS") ? strtoull(getenv("ZKB_DIST_TIMEOUT_MS"), nullptr, 10) : 120000ull;
-    a.timeout_ns = timeout_ms * 1000ull * 1000ull;
+    a.timeout_ns = dist_timeout_ms() * 1000ull * 1000ull;
     ProfScope prof("dist_barrier", s);
     dist_barrier_kernel<<<1, 32, 0, s>>>(a);
     count_launch();
@@ -250,7 +256,7 @@ int dist_inprocess_ntt_host(const uint64_t* in, uint64_t* out, const uint64_t om
     if (world < 2 || !ntt_dist_supported(ntt_geometry(log_n, true), log_g)) { set_error("a 2^%u NTT cannot be sharded over %d devices", log_n, world); return ZKB_ERR_ARG; }
     ZKB_TRY(dist_inprocess_setup(log_n, world));
     const size_t slice = ((size_t)1 << (log_n - log_g)) * 32;
-    return run_on_devices(world, [&](int slot) -> int {
+    const int rc = run_on_devices(world, [&](int slot) -> int {
         std::lock_guard<std::recursive_mutex> lk(ctx().mu);
         ZKB_TRY(require_init());
         DistCtx& d = dctx();
@@ -261,6 +267,8 @@ int dist_inprocess_ntt_host(const uint64_t* in, uint64_t* out, const uint64_t om
         ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)slot * slice, d.local[2], slice, cudaMemcpyDeviceToHost, s));
         return dist_check_status(s);
     });
+    if (rc != ZKB_OK) inproc_reset();   // the ranks' barrier epochs may be out of step: rebuild the contexts next time
+    return rc;
 }
 
 }  // namespace zkb
@@ -343,6 +351,11 @@ int zkb_dist_create_inprocess(uint32_t max_log_n) {
     if (world < 2) { set_error("needs >= 2 bound devices"); return ZKB_ERR_ARG; }
     if (max_log_n < 11 || max_log_n > 28) { set_error("max_log_n %u out of range [11, 28]", max_log_n); return ZKB_ERR_ARG; }
     return dist_inprocess_setup(max_log_n, world);
+}
+
+int zkb_dist_set_timeout_ms(uint64_t ms) {
+    g_dist_timeout_ms = ms;
+    return ZKB_OK;
 }
 
 int zkb_dist_destroy(void) {
