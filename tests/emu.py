@@ -200,3 +200,12 @@ def permute_expression_pair(input_, table, usable_rows):
     if rc != 0:
         raise ValueError("ConstraintSystemFailure")
     return oa, ot
+
+
+def bucket_sort(keys, vals, key_bits, tile=0):
+    """csrc/bucket_sort.cuh run phase by phase on the CPU: returns (sorted keys, permuted values), or None when the key is too wide."""
+    k = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+    v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    rc = lib().zkb_emu_bucket_sort(k.ctypes.data_as(u32p), v.ctypes.data_as(u32p), ctypes.c_uint64(k.size), ctypes.c_uint32(key_bits), ctypes.c_uint32(tile))
+    return (k, v) if rc == 0 else None

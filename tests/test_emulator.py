@@ -722,3 +722,43 @@ def test_permute_expression_pair_missing_value_emulated(oracle):
     t = ints_to_limbs([R.to_mont(x, R.FR) for x in (1, 2, 3)])
     with pytest.raises(ValueError):
         emu.permute_expression_pair(a, t, 3)
+
+
+# ---- csrc/bucket_sort.cuh: the MSM's own most-significant-digit-first partition -------------------------------------------------------
+def _check_bucket_sort(keys, key_bits, tile=0):
+    keys = np.asarray(keys, dtype=np.uint32)
+    vals = np.arange(keys.size, dtype=np.uint32) * np.uint32(2654435761) + np.uint32(12345)   # distinct payloads
+    got = emu.bucket_sort(keys, vals, key_bits, tile)
+    assert got is not None
+    gk, gv = got
+    assert (gk == np.sort(keys)).all(), "keys not sorted"
+    # every payload still sits next to its own key, nothing lost or duplicated (order inside a bucket is free)
+    back = dict(zip(vals.tolist(), keys.tolist()))
+    assert len(set(gv.tolist())) == keys.size
+    assert all(back[v] == k for k, v in zip(gk.tolist(), gv.tolist()))
+
+
+@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (5, 3, 0), (1000, 7, 0), (5000, 11, 0), (5000, 12, 0), (40000, 16, 512),
+                                            (40000, 21, 1024), (70000, 22, 8192), (9000, 10, 8192), (20000, 15, 1536)])
+def test_bucket_sort_uniform_keys(n, key_bits, tile):
+    rng = np.random.default_rng(n + key_bits)
+    _check_bucket_sort(rng.integers(0, 1 << key_bits, size=n, dtype=np.uint32), key_bits, tile)
+
+
+def test_bucket_sort_skewed_and_degenerate_keys():
+    rng = np.random.default_rng(7)
+    n = 30000
+    # witness-like: most entries in a few buckets
+    keys = np.where(rng.random(n) < 0.8, rng.integers(0, 8, size=n), rng.integers(0, 1 << 18, size=n)).astype(np.uint32)
+    _check_bucket_sort(keys, 18, 1024)
+    _check_bucket_sort(np.full(n, 0x2ABCD, dtype=np.uint32), 18, 2048)            # the all-equal column: one bucket
+    _check_bucket_sort(np.full(n, (1 << 18) - 1, dtype=np.uint32), 18, 512)       # last bucket of the last segment
+    _check_bucket_sort(np.zeros(3, dtype=np.uint32), 22, 0)
+    _check_bucket_sort(np.arange(n, dtype=np.uint32)[::-1] % (1 << 14), 14, 512)  # descending, every bucket hit
+    # segment sizes that are exact multiples of the tile, and segments of one entry
+    keys = np.concatenate([np.full(1024, 5 << 9, dtype=np.uint32), np.full(2048, 6 << 9, dtype=np.uint32), np.array([7 << 9, 9 << 9 | 3], dtype=np.uint32)])
+    _check_bucket_sort(keys, 18, 1024)
+
+
+def test_bucket_sort_key_too_wide_is_refused():
+    assert emu.bucket_sort(np.arange(10, dtype=np.uint32), np.arange(10, dtype=np.uint32), 23) is None

@@ -4,9 +4,12 @@ Bar: bit-exact (integer/field arithmetic).  Small sizes compare every output lim
 BASELINE.json's full sizes use size-independent properties (inverse round trip, known-discrete-log MSM,
 shard-split invariance).  Nothing here reads /root/reference.
 """
+import ctypes
 import importlib
 import json
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -17,6 +20,7 @@ from util import FQ_LIMBS, int_to_limbs, ints_to_limbs, limbs_to_int, random_fie
 pytestmark = pytest.mark.gpu
 
 zkb = importlib.import_module("zksnap-circuits-halo2_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hotpath_kats.json")))
 
 
@@ -1294,3 +1298,72 @@ def test_quotient_evaluator_evaluate_h_on_resident_cosets(oracle):
     q.evaluate_h(values, [P(c) for c in fixed], [P(c) for c in advice], [P(c) for c in instance], None, y, beta, gamma, theta, rs,
                  P(l0), P(l_last), P(l_active), P(xc), [P(c) for c in sigmas], [P(c) for c in zs], [(P(lz), P(la), P(ls))])
     assert (values.to_host() == state["v"]).all()
+
+
+# ---- the MSM's own bucket sort (csrc/bucket_sort.cuh) on the device ----------------------------------------------------------------
+def _gpu_bucket_sort(keys, key_bits, tile=0):
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    k = keys.copy()
+    v = np.arange(keys.size, dtype=np.uint32)          # value = original position
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    rc = zkb.lib().zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), v.ctypes.data_as(u32p), keys.size, key_bits, tile)
+    assert rc == 0, zkb.lib().zkb_last_error()
+    assert (k == np.sort(keys)).all(), "keys not sorted"
+    assert (keys[v] == k).all(), "a value left its key"
+    assert (np.sort(v) == np.arange(keys.size, dtype=np.uint32)).all(), "values lost or duplicated"
+
+
+@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (7, 3, 0), (5000, 11, 0), (5000, 12, 512), (100_000, 16, 1024), (1 << 20, 21, 0),
+                                            (1 << 20, 22, 8192), (3_000_001, 17, 4096), (1 << 22, 13, 0)])
+def test_bucket_sort_uniform_keys(n, key_bits, tile):
+    rng = np.random.default_rng(n + key_bits)
+    _gpu_bucket_sort(rng.integers(0, 1 << key_bits, size=n, dtype=np.uint32), key_bits, tile)
+
+
+def test_bucket_sort_skewed_and_degenerate_keys():
+    rng = np.random.default_rng(11)
+    n = 1 << 21
+    # witness-like: most entries in a handful of buckets, the rest spread out
+    keys = np.where(rng.random(n) < 0.8, rng.integers(0, 8, size=n), rng.integers(0, 1 << 21, size=n)).astype(np.uint32)
+    _gpu_bucket_sort(keys, 21)
+    _gpu_bucket_sort(np.full(n, 0x12345, dtype=np.uint32), 21)                 # the all-equal column: ONE bucket gets everything
+    _gpu_bucket_sort(np.full(n, (1 << 21) - 1, dtype=np.uint32), 21, 512)      # the last bucket of the last segment
+    _gpu_bucket_sort((np.arange(n, dtype=np.uint32)[::-1] % (1 << 18)).astype(np.uint32), 18)
+    # segments whose sizes are exact multiples of the tile, and one-entry segments
+    keys = np.concatenate([np.full(8192, 5 << 10, dtype=np.uint32), np.full(16384, 6 << 10, dtype=np.uint32), np.array([7 << 10, (9 << 10) | 3], dtype=np.uint32)])
+    _gpu_bucket_sort(keys, 21, 8192)
+
+
+def test_bucket_sort_full_size_and_refusals():
+    # the headline's entry count: 2^24 points x 12 windows of c = 22 -> 2^21 buckets
+    rng = np.random.default_rng(5)
+    n = 12 << 24
+    keys = rng.integers(0, 1 << 21, size=n, dtype=np.uint32)
+    _gpu_bucket_sort(keys, 21)
+    lib = zkb.lib()
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    k = np.zeros(4, dtype=np.uint32)
+    assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 23, 0) != 0      # too wide for two levels
+    assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 10, 100) != 0    # tile not a multiple of the CTA
+    assert lib.zkb_bucket_sort_pairs(None, k.ctypes.data_as(u32p), 4, 10, 0) != 0
+
+
+def test_msm_same_result_with_either_sort():
+    """ZKB_MSM_SORT=cub (a fresh process: the variable is read once) keeps the toolkit's radix sort as the fallback path for keys wider
+    than 22 bits; both must give the oracle's commitment, also for a batch whose folded key needs the fallback."""
+    code = (
+        "import os, sys, importlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "from util import random_field\n"
+        "from oracle import coracle\n"
+        "zkb = importlib.import_module('zksnap-circuits-halo2_b200')\n"
+        "zkb.init(0); coracle.build()\n"
+        "n = 1 << 12\n"
+        "b = zkb.g1_fixed_base_mul(random_field(n, 2)); s = random_field(n, 3)\n"
+        "p = zkb.ParamsKZG(12, b)\n"
+        "assert (p.commit(s) == coracle.best_multiexp(s, b)).all()\n"
+        "print('OK')\n" % (ROOT, ROOT))
+    for mode in ("cub", "own"):
+        env = dict(os.environ, ZKB_MSM_SORT=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "OK" in r.stdout, (mode, r.stdout[-500:], r.stderr[-2000:])

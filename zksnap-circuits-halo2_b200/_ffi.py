@@ -125,6 +125,7 @@ def load() -> ctypes.CDLL:
         "zkb_pipeline_set": [ci, sz],
         "zkb_msm_set_slices": [ci],
         "zkb_field_vec_op": [ci, ci, u64p, u64p, u64p, sz],
+        "zkb_bucket_sort_pairs": [ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), sz, u32, u32],
         "zkb_msm_set_params": [u32, u32],
         "zkb_msm_get_params": [sz, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)],
         "zkb_msm_last_entries": [ctypes.POINTER(u64)],

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "bucket_sort.cuh"
 #include "msm_host.hpp"
 
 namespace zkb {
@@ -132,6 +133,131 @@ __global__ void __launch_bounds__(128) srs_table_kernel(const SrsTableArgs a) {
 
 __global__ void __launch_bounds__(128) g1_fixed_base_mul_kernel(const FixedBaseArgs a) {
     g1_fixed_base_mul_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// ---- bucket sort (bucket_sort.cuh): phases separated by CTA barriers -------------------------------------------------------------
+__global__ void bsort_init_kernel(const unsigned long long* count, uint32_t tile, uint32_t* seg_off, uint32_t* tile_start) {
+    bsort_init_thread(count, tile, seg_off, tile_start);
+}
+
+__global__ void __launch_bounds__(128) bsort_tiles_kernel(const BsortArgs a) {
+    bsort_tiles_thread(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(BSORT_THREADS) bsort_count_kernel(const BsortArgs a) {
+    extern __shared__ uint32_t bsort_smem[];
+    uint32_t* hist = bsort_smem;
+    uint32_t* info = hist + (1u << a.bits);
+    bsort_phase_begin(a, blockIdx.x, threadIdx.x, hist, info);
+    __syncthreads();
+    if (!info[2]) return;
+    bsort_count_phase_hist(a, threadIdx.x, hist, info);
+    __syncthreads();
+    bsort_count_phase_flush(a, threadIdx.x, hist, info);
+}
+
+// exclusive prefix of v over the threads of the CTA (warp shuffles + one word per warp); two barriers
+__device__ __forceinline__ uint32_t bsort_cta_scan(uint32_t v, uint32_t* wsum) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < BSORT_THREADS / 32 ? wsum[lane] : 0;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += u;
+        }
+        if (lane < BSORT_THREADS / 32) wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    return wsum[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(BSORT_THREADS) bsort_scan_kernel(const BsortArgs a) {
+    __shared__ uint32_t part[2 * BSORT_THREADS];
+    __shared__ uint32_t wsum[2][32];
+    bsort_scan_phase_sum(a, blockIdx.x, threadIdx.x, part);
+    const uint32_t base = bsort_cta_scan(part[threadIdx.x], wsum[0]);
+    const uint32_t tbase = bsort_cta_scan(part[BSORT_THREADS + threadIdx.x], wsum[1]);
+    bsort_scan_phase_write(a, blockIdx.x, threadIdx.x, base, tbase);
+}
+
+__global__ void __launch_bounds__(BSORT_THREADS, 1024 / BSORT_THREADS) bsort_scatter_kernel(const BsortArgs a) {
+    extern __shared__ uint32_t bsort_smem[];
+    const uint32_t bins = 1u << a.bits;
+    uint32_t* hist = bsort_smem;
+    uint32_t* delta = hist + bins;
+    uint32_t* part = delta + bins;
+    uint32_t* wsum = part + BSORT_THREADS;
+    uint32_t* info = wsum + BSORT_GROUPS;
+    uint32_t* skeys = info + 4;
+    uint32_t* svals = skeys + a.tile;
+    uint32_t rk[BSORT_ITEMS], rv[BSORT_ITEMS], rr[BSORT_ITEMS / 2], g[BSORT_KMAX];
+    bsort_phase_begin(a, blockIdx.x, threadIdx.x, hist, info);
+    __syncthreads();
+    if (!info[2]) return;
+    bsort_scatter_phase_rank(a, threadIdx.x, hist, info, rk, rv, rr);
+    __syncthreads();
+    bsort_scatter_phase_sum(a, threadIdx.x, hist, part);
+    const uint32_t base = bsort_cta_scan(part[threadIdx.x], wsum);
+    bsort_scatter_phase_reserve(a, threadIdx.x, hist, base, info, g);
+    __syncthreads();
+    bsort_scatter_phase_stage(a, threadIdx.x, hist, info, rk, rv, rr, skeys, svals);
+    bsort_scatter_phase_delta(a, threadIdx.x, hist, delta, g);
+    __syncthreads();
+    bsort_scatter_phase_write(a, threadIdx.x, delta, info, skeys, svals);
+}
+
+struct BsortAttr { bool set = false; };
+// Sorts the first *d_count (== valid, already known to the host) entries of (keys[0], vals[0]) by their low key_bits bits; *cur = the
+// buffer pair that holds the result.
+static int bsort_run(DevBuf* keys, DevBuf* vals, DevBuf& tmp, const unsigned long long* d_count, uint64_t valid, const BsortPlan& p,
+                     cudaStream_t s, int* cur) {
+    bool& attr = per_device<BsortAttr>().set;
+    if (!attr) {
+        BsortPlan big{};
+        big.bits[0] = BSORT_MAX_BITS; big.tile = BSORT_MAX_TILE;
+        ZKB_CUDA_TRY(cudaFuncSetAttribute(bsort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsort_scatter_smem(big, 0)));
+        attr = true;
+    }
+    uint32_t* t = tmp.as<uint32_t>();
+    ZKB_CUDA_TRY(cudaMemsetAsync(t + p.zero_from, 0, p.zero_words * 4, s));
+    bsort_init_kernel<<<1, 1, 0, s>>>(d_count, p.tile, t + p.off_seg1, t + p.off_tile1);
+    count_launch();
+    int in = 0;
+    uint32_t shift = p.levels == 2 ? p.bits[1] : 0;
+    for (uint32_t level = 0; level < p.levels; ++level) {
+        BsortArgs a{};
+        a.keys_in = keys[in].as<uint32_t>(); a.vals_in = vals[in].as<uint32_t>();
+        a.keys_out = keys[in ^ 1].as<uint32_t>(); a.vals_out = vals[in ^ 1].as<uint32_t>();
+        a.seg_off = t + (level == 0 ? p.off_seg1 : p.off_seg2);
+        a.tile_start = t + (level == 0 ? p.off_tile1 : p.off_tile2);
+        a.nseg = level == 0 ? 1u : 1u << p.bits[0];
+        a.shift = shift; a.bits = p.bits[level]; a.tile = p.tile;
+        a.cnt = t + (level == 0 ? p.off_cnt1 : p.off_cnt2);
+        if (level == 0 && p.levels == 2) { a.next_seg_off = t + p.off_seg2; a.next_tile_start = t + p.off_tile2; a.next_tile = p.tile; }
+        const unsigned tiles = (unsigned)bsort_max_tiles(p, level, valid);
+        a.tile_info = reinterpret_cast<uint4*>(t + p.off_info);
+        a.max_tiles = tiles;
+        bsort_tiles_kernel<<<(tiles + 127) / 128, 128, 0, s>>>(a);
+        bsort_count_kernel<<<tiles, BSORT_THREADS, bsort_count_smem(p, level), s>>>(a);
+        bsort_scan_kernel<<<a.nseg, BSORT_THREADS, 0, s>>>(a);
+        bsort_scatter_kernel<<<tiles, BSORT_THREADS, bsort_scatter_smem(p, level), s>>>(a);
+        count_launch(4);
+        ZKB_CUDA_TRY(cudaGetLastError());
+        in ^= 1;
+        shift = 0;
+    }
+    *cur = in;
+    return ZKB_OK;
 }
 
 // Integer-pipe peak probe: 8 independent chains per thread of a_j = a_j * y + x (IMAD, multiplicand is the running
@@ -304,6 +430,13 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
         ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, sp));
     }
+    // the library's own bucket sort (bucket_sort.cuh) unless the key is too wide for two levels or ZKB_MSM_SORT=cub asks for the toolkit's
+    static const bool own_sort = !(getenv("ZKB_MSM_SORT") && !strcmp(getenv("ZKB_MSM_SORT"), "cub"));
+    uint32_t sort_kb = 1;  // keys are < nbuckets (zero digits are never emitted, so there is no "invalid" key to sort)
+    while ((1ull << sort_kb) < g.nbuckets) ++sort_kb;
+    const BsortPlan bp0 = bsort_plan(total, sort_kb);
+    const bool use_own = own_sort && bp0.levels > 0;
+    if (use_own && bp0.words * 4 > sort_bytes) sort_bytes = bp0.words * 4;
     ZKB_TRY(w.sort_tmp[set].reserve(sort_bytes));
     ZKB_TRY(w.counter[set].reserve(8));
     if (overlap) {
@@ -363,13 +496,22 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
     const uint32_t* sv;
     {
         ProfScope prof("msm_sort", sp);
-        cub::DoubleBuffer<uint32_t> dk(keys[0].as<uint32_t>(), keys[1].as<uint32_t>());
-        cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
-        uint32_t kb = 1;  // keys are < nbuckets now (no "invalid" key)
-        while ((1ull << kb) < g.nbuckets) ++kb;
-        if (valid) ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp[set].p, sort_bytes, dk, dv, (int)valid, 0, (int)kb, sp));
-        sk = dk.Current();
-        sv = dv.Current();
+        if (use_own) {
+            static const uint32_t tile_override = getenv("ZKB_MSM_SORT_TILE") ? (uint32_t)atoi(getenv("ZKB_MSM_SORT_TILE")) : 0;
+            int cur = 0;
+            static const uint32_t b1_override = getenv("ZKB_MSM_SORT_B1") ? (uint32_t)atoi(getenv("ZKB_MSM_SORT_B1")) : 0;   // experiment hook
+            const BsortPlan bp = bsort_plan(valid, sort_kb, tile_override, b1_override);
+            ZKB_TRY(w.sort_tmp[set].reserve(bp.words * 4));   // a shorter tile can mean more tile descriptors than the first estimate
+            if (valid) ZKB_TRY(bsort_run(keys, vals, w.sort_tmp[set], reinterpret_cast<const unsigned long long*>(w.counter[set].p), valid, bp, sp, &cur));
+            sk = keys[cur].as<uint32_t>();
+            sv = vals[cur].as<uint32_t>();
+        } else {
+            cub::DoubleBuffer<uint32_t> dk(keys[0].as<uint32_t>(), keys[1].as<uint32_t>());
+            cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
+            if (valid) ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp[set].p, sort_bytes, dk, dv, (int)valid, 0, (int)sort_kb, sp));
+            sk = dk.Current();
+            sv = dv.Current();
+        }
     }
     if (overlap) {
         ZKB_CUDA_TRY(cudaEventRecord(w.ev_sorted[set], sp));
@@ -503,3 +645,37 @@ int g1_sum_host(const uint64_t* pts, size_t count, uint64_t out[12]) {
 }
 
 }  // namespace zkb
+
+// Self-test entry of the bucket sort: n (key, value) pairs from host memory, sorted by the low key_bits bits of the key on the
+// device and copied back (the order inside one key is unspecified).  Counts as test infrastructure like zkb_field_vec_op.
+int zkb_bucket_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, uint32_t key_bits, uint32_t tile) {
+    using namespace zkb;
+    std::lock_guard<std::recursive_mutex> lock(ctx().mu);
+    ZKB_TRY(require_init());
+    if (n == 0) return ZKB_OK;
+    if (!keys || !vals) { set_error("NULL argument"); return ZKB_ERR_ARG; }
+    if (n >= (1ull << 31)) { set_error("too many pairs"); return ZKB_ERR_ARG; }
+    if (tile && (tile > BSORT_MAX_TILE || tile % BSORT_THREADS)) { set_error("tile must be a multiple of %u and at most %u", BSORT_THREADS, BSORT_MAX_TILE); return ZKB_ERR_ARG; }
+    const BsortPlan p = bsort_plan(n, key_bits, tile);
+    if (!p.levels) { set_error("keys of %u bits are too wide for the two-level bucket sort (at most %u)", key_bits, 2 * BSORT_MAX_BITS); return ZKB_ERR_ARG; }
+    DevBuf k[2], v[2], tmp, cnt;
+    auto done = [&](int rc) { for (auto& b : k) b.release(); for (auto& b : v) b.release(); tmp.release(); cnt.release(); return rc; };
+    for (int i = 0; i < 2; ++i) {
+        int rc = k[i].reserve(n * 4);
+        if (rc == ZKB_OK) rc = v[i].reserve(n * 4);
+        if (rc != ZKB_OK) return done(rc);
+    }
+    int rc = tmp.reserve(p.words * 4);
+    if (rc == ZKB_OK) rc = cnt.reserve(8);
+    if (rc != ZKB_OK) return done(rc);
+    cudaStream_t s = ctx().stream;
+    const unsigned long long n64 = n;
+    int cur = 0;
+    if (cudaMemcpyAsync(k[0].p, keys, n * 4, cudaMemcpyHostToDevice, s) != cudaSuccess || cudaMemcpyAsync(v[0].p, vals, n * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(cnt.p, &n64, 8, cudaMemcpyHostToDevice, s) != cudaSuccess) { set_error("upload failed"); return done(ZKB_ERR_CUDA); }
+    rc = bsort_run(k, v, tmp, reinterpret_cast<const unsigned long long*>(cnt.p), n, p, s, &cur);
+    if (rc != ZKB_OK) return done(rc);
+    if (cudaMemcpyAsync(keys, k[cur].p, n * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaMemcpyAsync(vals, v[cur].p, n * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { set_error("bucket sort failed: %s", cudaGetErrorString(cudaGetLastError())); return done(ZKB_ERR_CUDA); }
+    return done(ZKB_OK);
+}
