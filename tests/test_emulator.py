@@ -738,8 +738,8 @@ def _check_bucket_sort(keys, key_bits, tile=0):
     assert all(back[v] == k for k, v in zip(gk.tolist(), gv.tolist()))
 
 
-@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (5, 3, 0), (1000, 7, 0), (5000, 11, 0), (5000, 12, 0), (40000, 16, 512),
-                                            (40000, 21, 1024), (70000, 22, 8192), (9000, 10, 8192), (20000, 15, 1536)])
+@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (5, 3, 0), (1000, 7, 0), (5000, 12, 0), (5000, 13, 0), (40000, 16, 512),
+                                            (40000, 21, 1024), (70000, 24, 8192), (60000, 23, 0), (9000, 10, 8192), (20000, 15, 1536)])
 def test_bucket_sort_uniform_keys(n, key_bits, tile):
     rng = np.random.default_rng(n + key_bits)
     _check_bucket_sort(rng.integers(0, 1 << key_bits, size=n, dtype=np.uint32), key_bits, tile)
@@ -761,4 +761,4 @@ def test_bucket_sort_skewed_and_degenerate_keys():
 
 
 def test_bucket_sort_key_too_wide_is_refused():
-    assert emu.bucket_sort(np.arange(10, dtype=np.uint32), np.arange(10, dtype=np.uint32), 23) is None
+    assert emu.bucket_sort(np.arange(10, dtype=np.uint32), np.arange(10, dtype=np.uint32), 25) is None

@@ -1314,7 +1314,7 @@ def _gpu_bucket_sort(keys, key_bits, tile=0):
 
 
 @pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (7, 3, 0), (5000, 11, 0), (5000, 12, 512), (100_000, 16, 1024), (1 << 20, 21, 0),
-                                            (1 << 20, 22, 8192), (3_000_001, 17, 4096), (1 << 22, 13, 0)])
+                                            (1 << 20, 22, 8192), (1 << 21, 23, 0), (1 << 20, 24, 2048), (3_000_001, 17, 4096), (1 << 22, 13, 0)])
 def test_bucket_sort_uniform_keys(n, key_bits, tile):
     rng = np.random.default_rng(n + key_bits)
     _gpu_bucket_sort(rng.integers(0, 1 << key_bits, size=n, dtype=np.uint32), key_bits, tile)
@@ -1343,7 +1343,7 @@ def test_bucket_sort_full_size_and_refusals():
     lib = zkb.lib()
     u32p = ctypes.POINTER(ctypes.c_uint32)
     k = np.zeros(4, dtype=np.uint32)
-    assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 23, 0) != 0      # too wide for two levels
+    assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 25, 0) != 0      # too wide for two levels
     assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 10, 100) != 0    # tile not a multiple of the CTA
     assert lib.zkb_bucket_sort_pairs(None, k.ctypes.data_as(u32p), 4, 10, 0) != 0
 

@@ -13,7 +13,7 @@
 //            each (tile -> segment by binary search in the scanned tile counts); a segment's sub-bins are laid out in order
 //            inside the segment, so after level 2 the array is sorted by the whole key.
 //
-// Keys of up to 11 bits take one level, up to 22 bits two (every MSM of this library: c <= 22 and few columns; wider keys —
+// Keys of up to 12 bits take one level, up to 24 bits two (every MSM of this library: c <= 22 and few columns; wider keys —
 // hundreds of columns folded into the key — fall back to the toolkit's radix sort in msm.cu).  Any digit distribution is
 // handled by construction: tiles are equal-sized pieces of the INPUT, a heavy bucket is just a long run that many tiles
 // append to (witness columns put most entries into a few buckets; the all-equal column puts everything into W of them).
@@ -34,7 +34,7 @@ constexpr uint32_t BSORT_THREADS = ZKB_BSORT_THREADS;
 constexpr uint32_t BSORT_ITEMS = 16;                               // entries a scatter thread holds in registers
 constexpr uint32_t BSORT_MAX_TILE = BSORT_THREADS * BSORT_ITEMS;   // entries per tile (8192)
 static_assert(BSORT_MAX_TILE <= 65536, "ranks inside a tile are kept in 16 bits");
-constexpr uint32_t BSORT_MAX_BITS = 11;                            // digit width per level (4 bins per thread)
+constexpr uint32_t BSORT_MAX_BITS = 12;                            // digit width per level (<= 11: 4 bins per thread, 12: 8)
 constexpr uint32_t BSORT_GROUP = 16;                               // per-thread partial sums scanned serially by one thread
 constexpr uint32_t BSORT_GROUPS = BSORT_THREADS / BSORT_GROUP;     // 32
 
@@ -205,34 +205,38 @@ ZKB_HD void bsort_scatter_phase_sum(const BsortArgs& a, uint32_t tid, const uint
 // Local offsets replace the counts, and one global atomicAdd per non-empty digit reserves the tile's run in the digit's segment.
 // The reservations are only ISSUED here (g stays in the thread's registers): staging does not need them, so their round trip
 // to L2 hides behind it, and bsort_scatter_phase_delta turns them into the per-digit displacement afterwards.
+// KMAX: bins per thread the instantiation covers (4 for digits of <= 11 bits — every table-mode commit — 8 for 12-bit digits)
 constexpr uint32_t BSORT_KMAX = ((1u << BSORT_MAX_BITS) + BSORT_THREADS - 1) / BSORT_THREADS;
+constexpr uint32_t BSORT_KMAX_NARROW = (BSORT_KMAX + 1) / 2;
+template <uint32_t KMAX>
 ZKB_HD void bsort_scatter_phase_reserve(const BsortArgs& a, uint32_t tid, uint32_t* hist, uint32_t base, const uint32_t* info, uint32_t* g) {
     const uint32_t bins = 1u << a.bits, K = bsort_bins_per_thread(a.bits);
     uint32_t* cnt = a.cnt + ((size_t)info[0] << a.bits);
-    uint32_t c[BSORT_KMAX];
+    uint32_t c[KMAX];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t j = 0; j < BSORT_KMAX; ++j) { const uint32_t b = tid * K + j; c[j] = (j < K && b < bins) ? hist[b] : 0; }
+    for (uint32_t j = 0; j < KMAX; ++j) { const uint32_t b = tid * K + j; c[j] = (j < K && b < bins) ? hist[b] : 0; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t j = 0; j < BSORT_KMAX; ++j) g[j] = c[j] ? bsort_atomic_add(cnt + tid * K + j, c[j]) : 0;
+    for (uint32_t j = 0; j < KMAX; ++j) g[j] = c[j] ? bsort_atomic_add(cnt + tid * K + j, c[j]) : 0;
     uint32_t run = base;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t j = 0; j < BSORT_KMAX; ++j) {
+    for (uint32_t j = 0; j < KMAX; ++j) {
         const uint32_t b = tid * K + j;
         if (j < K && b < bins) { hist[b] = run; run += c[j]; }
     }
 }
+template <uint32_t KMAX>
 ZKB_HD void bsort_scatter_phase_delta(const BsortArgs& a, uint32_t tid, const uint32_t* hist, uint32_t* delta, const uint32_t* g) {
     const uint32_t bins = 1u << a.bits, K = bsort_bins_per_thread(a.bits);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t j = 0; j < BSORT_KMAX; ++j) {
+    for (uint32_t j = 0; j < KMAX; ++j) {
         const uint32_t b = tid * K + j;
         if (j < K && b < bins) delta[b] = g[j] - hist[b];   // empty digits: never looked up
     }
@@ -279,7 +283,7 @@ inline BsortPlan bsort_plan(uint64_t entries, uint32_t key_bits, uint32_t tile_o
     if (key_bits > 2 * BSORT_MAX_BITS) return p;
     if (key_bits <= BSORT_MAX_BITS) { p.levels = 1; p.bits[0] = key_bits; }
     else {
-        p.levels = 2; p.bits[1] = key_bits / 2; p.bits[0] = key_bits - p.bits[1];
+        p.levels = 2; p.bits[0] = key_bits / 2; p.bits[1] = key_bits - p.bits[0];   // measured: the narrower digit first (2^24: 3.83 vs 4.01 ms)
         if (b1_override && b1_override <= BSORT_MAX_BITS && b1_override < key_bits && key_bits - b1_override <= BSORT_MAX_BITS) { p.bits[0] = b1_override; p.bits[1] = key_bits - b1_override; }
     }
     // tile: the full 8192 entries when that still gives every SM several tiles, shorter for small sorts (latency regime)

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(BSORT_THREADS) bsort_scan_kernel(const BsortAr
     bsort_scan_phase_write(a, blockIdx.x, threadIdx.x, base, tbase);
 }
 
+template <uint32_t KMAX>
 __global__ void __launch_bounds__(BSORT_THREADS, 1024 / BSORT_THREADS) bsort_scatter_kernel(const BsortArgs a) {
     extern __shared__ uint32_t bsort_smem[];
     const uint32_t bins = 1u << a.bits;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(BSORT_THREADS, 1024 / BSORT_THREADS) bsort_sca
     uint32_t* info = wsum + BSORT_GROUPS;
     uint32_t* skeys = info + 4;
     uint32_t* svals = skeys + a.tile;
-    uint32_t rk[BSORT_ITEMS], rv[BSORT_ITEMS], rr[BSORT_ITEMS / 2], g[BSORT_KMAX];
+    uint32_t rk[BSORT_ITEMS], rv[BSORT_ITEMS], rr[BSORT_ITEMS / 2], g[KMAX];
     bsort_phase_begin(a, blockIdx.x, threadIdx.x, hist, info);
     __syncthreads();
     if (!info[2]) return;
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(BSORT_THREADS, 1024 / BSORT_THREADS) bsort_sca
     __syncthreads();
     bsort_scatter_phase_sum(a, threadIdx.x, hist, part);
     const uint32_t base = bsort_cta_scan(part[threadIdx.x], wsum);
-    bsort_scatter_phase_reserve(a, threadIdx.x, hist, base, info, g);
+    bsort_scatter_phase_reserve<KMAX>(a, threadIdx.x, hist, base, info, g);
     __syncthreads();
     bsort_scatter_phase_stage(a, threadIdx.x, hist, info, rk, rv, rr, skeys, svals);
-    bsort_scatter_phase_delta(a, threadIdx.x, hist, delta, g);
+    bsort_scatter_phase_delta<KMAX>(a, threadIdx.x, hist, delta, g);
     __syncthreads();
     bsort_scatter_phase_write(a, threadIdx.x, delta, info, skeys, svals);
 }
@@ -225,7 +226,8 @@ static int bsort_run(DevBuf* keys, DevBuf* vals, DevBuf& tmp, const unsigned lon
     if (!attr) {
         BsortPlan big{};
         big.bits[0] = BSORT_MAX_BITS; big.tile = BSORT_MAX_TILE;
-        ZKB_CUDA_TRY(cudaFuncSetAttribute(bsort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsort_scatter_smem(big, 0)));
+        ZKB_CUDA_TRY(cudaFuncSetAttribute(bsort_scatter_kernel<BSORT_KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsort_scatter_smem(big, 0)));
+        ZKB_CUDA_TRY(cudaFuncSetAttribute(bsort_scatter_kernel<BSORT_KMAX_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsort_scatter_smem(big, 0)));
         attr = true;
     }
     uint32_t* t = tmp.as<uint32_t>();
@@ -250,7 +252,8 @@ static int bsort_run(DevBuf* keys, DevBuf* vals, DevBuf& tmp, const unsigned lon
         bsort_tiles_kernel<<<(tiles + 127) / 128, 128, 0, s>>>(a);
         bsort_count_kernel<<<tiles, BSORT_THREADS, bsort_count_smem(p, level), s>>>(a);
         bsort_scan_kernel<<<a.nseg, BSORT_THREADS, 0, s>>>(a);
-        bsort_scatter_kernel<<<tiles, BSORT_THREADS, bsort_scatter_smem(p, level), s>>>(a);
+        if (bsort_bins_per_thread(a.bits) <= BSORT_KMAX_NARROW) bsort_scatter_kernel<BSORT_KMAX_NARROW><<<tiles, BSORT_THREADS, bsort_scatter_smem(p, level), s>>>(a);
+        else bsort_scatter_kernel<BSORT_KMAX><<<tiles, BSORT_THREADS, bsort_scatter_smem(p, level), s>>>(a);
         count_launch(4);
         ZKB_CUDA_TRY(cudaGetLastError());
         in ^= 1;
