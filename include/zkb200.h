@@ -422,7 +422,7 @@ int zkb_measure_imad_peak(double* wide_macs_per_s);
 int zkb_field_vec_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* Device self-test of the MSM's bucket sort (csrc/bucket_sort.cuh): n (key, value) pairs in host memory are sorted on the GPU by the
  * low key_bits (<= 24) bits of the key and copied back; the order of the values inside one key is unspecified.  tile: entries per
- * CTA tile (0 = automatic; otherwise a multiple of 512 up to 8192) — lets the tests exercise every tile / segment geometry. */
+ * CTA tile (0 = automatic; otherwise a multiple of 1024 up to 8192) — lets the tests exercise every tile / segment geometry. */
 int zkb_bucket_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, uint32_t key_bits, uint32_t tile);
 /* Kernels launched by this library since load (the bench's gpu_launches claim). */
 uint64_t zkb_launch_count(void);

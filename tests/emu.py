@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "zksnap-circuits-halo2_b200")
-LIB = os.path.join(PKG, "libzkb200_hostemu.so")
+LIB = os.environ.get("ZKB200_EMU_LIB") or os.path.join(PKG, "libzkb200_hostemu.so")  # override: the ASan / UBSan build (tools/asan_emulator.sh)
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 _lib = None
 
@@ -15,6 +15,8 @@ _lib = None
 def build(force=False):
     srcs = [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))]
     newest = max(os.path.getmtime(s) for s in srcs)
+    if os.environ.get("ZKB200_EMU_LIB"):
+        return LIB
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
         subprocess.check_call(["make", "-C", PKG, "-B", "libzkb200_hostemu.so"], stdout=subprocess.DEVNULL)
     return LIB

@@ -738,8 +738,8 @@ def _check_bucket_sort(keys, key_bits, tile=0):
     assert all(back[v] == k for k, v in zip(gk.tolist(), gv.tolist()))
 
 
-@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (5, 3, 0), (1000, 7, 0), (5000, 12, 0), (5000, 13, 0), (40000, 16, 512),
-                                            (40000, 21, 1024), (70000, 24, 8192), (60000, 23, 0), (9000, 10, 8192), (20000, 15, 1536)])
+@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (5, 3, 0), (1000, 7, 0), (5000, 12, 0), (5000, 13, 0), (40000, 16, 1024),
+                                            (40000, 21, 1024), (70000, 24, 8192), (60000, 23, 0), (9000, 10, 8192), (20000, 15, 3072)])
 def test_bucket_sort_uniform_keys(n, key_bits, tile):
     rng = np.random.default_rng(n + key_bits)
     _check_bucket_sort(rng.integers(0, 1 << key_bits, size=n, dtype=np.uint32), key_bits, tile)
@@ -752,9 +752,9 @@ def test_bucket_sort_skewed_and_degenerate_keys():
     keys = np.where(rng.random(n) < 0.8, rng.integers(0, 8, size=n), rng.integers(0, 1 << 18, size=n)).astype(np.uint32)
     _check_bucket_sort(keys, 18, 1024)
     _check_bucket_sort(np.full(n, 0x2ABCD, dtype=np.uint32), 18, 2048)            # the all-equal column: one bucket
-    _check_bucket_sort(np.full(n, (1 << 18) - 1, dtype=np.uint32), 18, 512)       # last bucket of the last segment
+    _check_bucket_sort(np.full(n, (1 << 18) - 1, dtype=np.uint32), 18, 1024)       # last bucket of the last segment
     _check_bucket_sort(np.zeros(3, dtype=np.uint32), 22, 0)
-    _check_bucket_sort(np.arange(n, dtype=np.uint32)[::-1] % (1 << 14), 14, 512)  # descending, every bucket hit
+    _check_bucket_sort(np.arange(n, dtype=np.uint32)[::-1] % (1 << 14), 14, 2048)  # descending, every bucket hit
     # segment sizes that are exact multiples of the tile, and segments of one entry
     keys = np.concatenate([np.full(1024, 5 << 9, dtype=np.uint32), np.full(2048, 6 << 9, dtype=np.uint32), np.array([7 << 9, 9 << 9 | 3], dtype=np.uint32)])
     _check_bucket_sort(keys, 18, 1024)

@@ -1313,7 +1313,7 @@ def _gpu_bucket_sort(keys, key_bits, tile=0):
     assert (np.sort(v) == np.arange(keys.size, dtype=np.uint32)).all(), "values lost or duplicated"
 
 
-@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (7, 3, 0), (5000, 11, 0), (5000, 12, 512), (100_000, 16, 1024), (1 << 20, 21, 0),
+@pytest.mark.parametrize("n,key_bits,tile", [(1, 1, 0), (7, 3, 0), (5000, 11, 0), (5000, 12, 1024), (100_000, 16, 1024), (1 << 20, 21, 0),
                                             (1 << 20, 22, 8192), (1 << 21, 23, 0), (1 << 20, 24, 2048), (3_000_001, 17, 4096), (1 << 22, 13, 0)])
 def test_bucket_sort_uniform_keys(n, key_bits, tile):
     rng = np.random.default_rng(n + key_bits)
@@ -1327,7 +1327,7 @@ def test_bucket_sort_skewed_and_degenerate_keys():
     keys = np.where(rng.random(n) < 0.8, rng.integers(0, 8, size=n), rng.integers(0, 1 << 21, size=n)).astype(np.uint32)
     _gpu_bucket_sort(keys, 21)
     _gpu_bucket_sort(np.full(n, 0x12345, dtype=np.uint32), 21)                 # the all-equal column: ONE bucket gets everything
-    _gpu_bucket_sort(np.full(n, (1 << 21) - 1, dtype=np.uint32), 21, 512)      # the last bucket of the last segment
+    _gpu_bucket_sort(np.full(n, (1 << 21) - 1, dtype=np.uint32), 21, 1024)      # the last bucket of the last segment
     _gpu_bucket_sort((np.arange(n, dtype=np.uint32)[::-1] % (1 << 18)).astype(np.uint32), 18)
     # segments whose sizes are exact multiples of the tile, and one-entry segments
     keys = np.concatenate([np.full(8192, 5 << 10, dtype=np.uint32), np.full(16384, 6 << 10, dtype=np.uint32), np.array([7 << 10, (9 << 10) | 3], dtype=np.uint32)])

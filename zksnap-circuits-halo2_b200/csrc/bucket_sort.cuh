@@ -27,16 +27,21 @@
 
 namespace zkb {
 
+// CTA geometry (overridable for A/B builds).  Measured at 2^24 (profiles/r2_sort_ab.txt): 1024 threads x 8 entries — 32 registers, two
+// CTAs = 64 warps per SM — 3.35 ms; 512 x 16 (64 registers, 32 warps per SM) 3.77 ms: the scatter waits on global loads, warps hide it.
 #ifndef ZKB_BSORT_THREADS
-#define ZKB_BSORT_THREADS 512
+#define ZKB_BSORT_THREADS 1024
+#endif
+#ifndef ZKB_BSORT_ITEMS
+#define ZKB_BSORT_ITEMS 8
 #endif
 constexpr uint32_t BSORT_THREADS = ZKB_BSORT_THREADS;
-constexpr uint32_t BSORT_ITEMS = 16;                               // entries a scatter thread holds in registers
+constexpr uint32_t BSORT_ITEMS = ZKB_BSORT_ITEMS;                  // entries a scatter thread holds in registers
 constexpr uint32_t BSORT_MAX_TILE = BSORT_THREADS * BSORT_ITEMS;   // entries per tile (8192)
 static_assert(BSORT_MAX_TILE <= 65536, "ranks inside a tile are kept in 16 bits");
-constexpr uint32_t BSORT_MAX_BITS = 12;                            // digit width per level (<= 11: 4 bins per thread, 12: 8)
+constexpr uint32_t BSORT_MAX_BITS = 12;                            // digit width per level (<= 11: 2 bins per thread, 12: 4)
 constexpr uint32_t BSORT_GROUP = 16;                               // per-thread partial sums scanned serially by one thread
-constexpr uint32_t BSORT_GROUPS = BSORT_THREADS / BSORT_GROUP;     // 32
+constexpr uint32_t BSORT_GROUPS = BSORT_THREADS / BSORT_GROUP;     // 64
 
 struct BsortArgs {
     const uint32_t* keys_in;
@@ -107,9 +112,28 @@ ZKB_HD void bsort_phase_begin(const BsortArgs& a, uint32_t t, uint32_t tid, uint
 }
 
 // ---- count ----------------------------------------------------------------------------------------------------------------------
+// All loads of a batch are issued before the first atomic: an atomic orders the memory operations around it, so a loop of
+// load -> atomic pays the global-memory latency once per ENTRY (measured: long-scoreboard stalls dominated both kernels).
+// Out-of-range slots re-read the tile's last entry (always valid: len >= 1) so the loads need no branch.
+constexpr uint32_t BSORT_COUNT_BATCH = 8;
 ZKB_HD void bsort_count_phase_hist(const BsortArgs& a, uint32_t tid, uint32_t* hist, const uint32_t* info) {
     const uint32_t lo = info[1], len = info[2];
-    for (uint32_t i = tid; i < len; i += BSORT_THREADS) bsort_atomic_add(hist + bsort_digit(a, a.keys_in[lo + i]), 1);
+    if (!len) return;
+    for (uint32_t first = 0; first < len; first += BSORT_COUNT_BATCH * BSORT_THREADS) {
+        uint32_t k[BSORT_COUNT_BATCH];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t it = 0; it < BSORT_COUNT_BATCH; ++it) {
+            const uint32_t i = first + it * BSORT_THREADS + tid;
+            k[it] = a.keys_in[lo + (i < len ? i : len - 1)];
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t it = 0; it < BSORT_COUNT_BATCH; ++it)
+            if (first + it * BSORT_THREADS + tid < len) bsort_atomic_add(hist + bsort_digit(a, k[it]), 1);
+    }
 }
 ZKB_HD void bsort_count_phase_flush(const BsortArgs& a, uint32_t tid, const uint32_t* hist, const uint32_t* info) {
     if (!info[2]) return;
@@ -179,21 +203,28 @@ ZKB_HD void bsort_scan_phase_write(const BsortArgs& a, uint32_t seg, uint32_t ti
 
 // ---- scatter --------------------------------------------------------------------------------------------------------------------
 // smem: hist[2^bits], delta[2^bits], part[BSORT_THREADS], gsum[BSORT_GROUPS], info[4], skeys[tile], svals[tile]
-// registers: rk / rv [BSORT_ITEMS] = the thread's entries, rr [BSORT_ITEMS / 2] their ranks inside their (tile, digit) run (16 bits each); g [BSORT_KMAX]
-ZKB_HD void bsort_scatter_phase_rank(const BsortArgs& a, uint32_t tid, uint32_t* hist, const uint32_t* info, uint32_t* rk, uint32_t* rv,
-                                     uint32_t* rr) {
-    const uint32_t lo = info[1], len = info[2];
+// registers: rk / rv [BSORT_ITEMS] = the thread's entries; g [KMAX] = the reservations in flight
+ZKB_HD void bsort_scatter_phase_rank(const BsortArgs& a, uint32_t tid, uint32_t* hist, const uint32_t* info, uint32_t* rk, uint32_t* rv) {
+    const uint32_t lo = info[1], len = info[2];   // len >= 1 (the kernel returns on an empty tile)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t it = 0; it < BSORT_ITEMS; ++it) {   // every key load first (see bsort_count_phase_hist), branch-free
+        const uint32_t i = it * BSORT_THREADS + tid;
+        rk[it] = a.keys_in[lo + (i < len ? i : len - 1)];
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t it = 0; it < BSORT_ITEMS; ++it)     // counts only: the position inside the run is handed out by the staging
+        if (it * BSORT_THREADS + tid < len) bsort_atomic_add(hist + bsort_digit(a, rk[it]), 1);
+    // the values are not needed before the staging: their loads are issued last and fly during the scan and the reservation
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (uint32_t it = 0; it < BSORT_ITEMS; ++it) {
         const uint32_t i = it * BSORT_THREADS + tid;
-        if (i < len) {
-            rk[it] = a.keys_in[lo + i];
-            rv[it] = a.vals_in[lo + i];
-            const uint32_t r = bsort_atomic_add(hist + bsort_digit(a, rk[it]), 1);   // < tile <= 2^16: two ranks per register
-            rr[it >> 1] = (it & 1) ? (rr[it >> 1] | (r << 16)) : r;
-        }
+        rv[it] = a.vals_in[lo + (i < len ? i : len - 1)];
     }
 }
 ZKB_HD void bsort_scatter_phase_sum(const BsortArgs& a, uint32_t tid, const uint32_t* hist, uint32_t* part) {
@@ -204,12 +235,13 @@ ZKB_HD void bsort_scatter_phase_sum(const BsortArgs& a, uint32_t tid, const uint
 }
 // Local offsets replace the counts, and one global atomicAdd per non-empty digit reserves the tile's run in the digit's segment.
 // The reservations are only ISSUED here (g stays in the thread's registers): staging does not need them, so their round trip
-// to L2 hides behind it, and bsort_scatter_phase_delta turns them into the per-digit displacement afterwards.
-// KMAX: bins per thread the instantiation covers (4 for digits of <= 11 bits — every table-mode commit — 8 for 12-bit digits)
+// to L2 hides behind it; delta[] starts as minus the local offset and bsort_scatter_phase_delta adds the reserved start afterwards.
+// KMAX: bins per thread the instantiation covers (2 for digits of <= 11 bits — every table-mode commit — 4 for 12-bit digits)
 constexpr uint32_t BSORT_KMAX = ((1u << BSORT_MAX_BITS) + BSORT_THREADS - 1) / BSORT_THREADS;
 constexpr uint32_t BSORT_KMAX_NARROW = (BSORT_KMAX + 1) / 2;
 template <uint32_t KMAX>
-ZKB_HD void bsort_scatter_phase_reserve(const BsortArgs& a, uint32_t tid, uint32_t* hist, uint32_t base, const uint32_t* info, uint32_t* g) {
+ZKB_HD void bsort_scatter_phase_reserve(const BsortArgs& a, uint32_t tid, uint32_t* hist, uint32_t* delta, uint32_t base, const uint32_t* info,
+                                        uint32_t* g) {
     const uint32_t bins = 1u << a.bits, K = bsort_bins_per_thread(a.bits);
     uint32_t* cnt = a.cnt + ((size_t)info[0] << a.bits);
     uint32_t c[KMAX];
@@ -227,22 +259,24 @@ ZKB_HD void bsort_scatter_phase_reserve(const BsortArgs& a, uint32_t tid, uint32
 #endif
     for (uint32_t j = 0; j < KMAX; ++j) {
         const uint32_t b = tid * K + j;
-        if (j < K && b < bins) { hist[b] = run; run += c[j]; }
+        if (j < K && b < bins) { hist[b] = run; delta[b] = 0u - run; run += c[j]; }
     }
 }
 template <uint32_t KMAX>
-ZKB_HD void bsort_scatter_phase_delta(const BsortArgs& a, uint32_t tid, const uint32_t* hist, uint32_t* delta, const uint32_t* g) {
+ZKB_HD void bsort_scatter_phase_delta(const BsortArgs& a, uint32_t tid, uint32_t* delta, const uint32_t* g) {
     const uint32_t bins = 1u << a.bits, K = bsort_bins_per_thread(a.bits);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (uint32_t j = 0; j < KMAX; ++j) {
         const uint32_t b = tid * K + j;
-        if (j < K && b < bins) delta[b] = g[j] - hist[b];   // empty digits: never looked up
+        if (j < K && b < bins) delta[b] += g[j];   // reserved start - local offset (empty digits: never looked up)
     }
 }
-ZKB_HD void bsort_scatter_phase_stage(const BsortArgs& a, uint32_t tid, const uint32_t* hist, const uint32_t* info, const uint32_t* rk,
-                                      const uint32_t* rv, const uint32_t* rr, uint32_t* skeys, uint32_t* svals) {
+// hist holds the local offset of every digit's run: a second shared-memory atomic hands out the positions inside the run (no
+// ranks kept in registers; the order inside a run is free)
+ZKB_HD void bsort_scatter_phase_stage(const BsortArgs& a, uint32_t tid, uint32_t* hist, const uint32_t* info, const uint32_t* rk,
+                                      const uint32_t* rv, uint32_t* skeys, uint32_t* svals) {
     const uint32_t len = info[2];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -250,12 +284,13 @@ ZKB_HD void bsort_scatter_phase_stage(const BsortArgs& a, uint32_t tid, const ui
     for (uint32_t it = 0; it < BSORT_ITEMS; ++it) {
         const uint32_t i = it * BSORT_THREADS + tid;
         if (i < len) {
-            const uint32_t pos = hist[bsort_digit(a, rk[it])] + ((rr[it >> 1] >> (16 * (it & 1))) & 0xffffu);
+            const uint32_t pos = bsort_atomic_add(hist + bsort_digit(a, rk[it]), 1);
             skeys[pos] = rk[it];
             svals[pos] = rv[it];
         }
     }
 }
+// (measured and dropped: (key, value) staged as one 8-byte word, atomics batched ahead of their stores — 2^24: 3.13 vs 3.04 ms)
 ZKB_HD void bsort_scatter_phase_write(const BsortArgs& a, uint32_t tid, const uint32_t* delta, const uint32_t* info, const uint32_t* skeys,
                                       const uint32_t* svals) {
     const uint32_t len = info[2];

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(BSORT_THREADS) bsort_scan_kernel(const BsortAr
 }
 
 template <uint32_t KMAX>
-__global__ void __launch_bounds__(BSORT_THREADS, 1024 / BSORT_THREADS) bsort_scatter_kernel(const BsortArgs a) {
+__global__ void __launch_bounds__(BSORT_THREADS, (BSORT_ITEMS <= 8 ? 2048 : 1024) / BSORT_THREADS) bsort_scatter_kernel(const BsortArgs a) {
     extern __shared__ uint32_t bsort_smem[];
     const uint32_t bins = 1u << a.bits;
     uint32_t* hist = bsort_smem;
@@ -201,18 +201,18 @@ __global__ void __launch_bounds__(BSORT_THREADS, 1024 / BSORT_THREADS) bsort_sca
     uint32_t* info = wsum + BSORT_GROUPS;
     uint32_t* skeys = info + 4;
     uint32_t* svals = skeys + a.tile;
-    uint32_t rk[BSORT_ITEMS], rv[BSORT_ITEMS], rr[BSORT_ITEMS / 2], g[KMAX];
+    uint32_t rk[BSORT_ITEMS], rv[BSORT_ITEMS], g[KMAX];
     bsort_phase_begin(a, blockIdx.x, threadIdx.x, hist, info);
     __syncthreads();
     if (!info[2]) return;
-    bsort_scatter_phase_rank(a, threadIdx.x, hist, info, rk, rv, rr);
+    bsort_scatter_phase_rank(a, threadIdx.x, hist, info, rk, rv);
     __syncthreads();
     bsort_scatter_phase_sum(a, threadIdx.x, hist, part);
     const uint32_t base = bsort_cta_scan(part[threadIdx.x], wsum);
-    bsort_scatter_phase_reserve<KMAX>(a, threadIdx.x, hist, base, info, g);
+    bsort_scatter_phase_reserve<KMAX>(a, threadIdx.x, hist, delta, base, info, g);
     __syncthreads();
-    bsort_scatter_phase_stage(a, threadIdx.x, hist, info, rk, rv, rr, skeys, svals);
-    bsort_scatter_phase_delta<KMAX>(a, threadIdx.x, hist, delta, g);
+    bsort_scatter_phase_stage(a, threadIdx.x, hist, info, rk, rv, skeys, svals);
+    bsort_scatter_phase_delta<KMAX>(a, threadIdx.x, delta, g);
     __syncthreads();
     bsort_scatter_phase_write(a, threadIdx.x, delta, info, skeys, svals);
 }
