@@ -190,6 +190,34 @@ def run_reference(args):
 
 
 # ---- small helpers shared by the legs ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: keep the rank's host threads (and therefore its page-locked buffers, first touched by them) on the NUMA node
+    its GPU hangs off, as a production launcher does with numactl — eight ranks uploading 512 MiB each otherwise cross the socket link.
+    Returns a description for the JSON line, or None when the topology cannot be read (nothing is changed then).  ZKB_BENCH_NUMA=0 disables."""
+    if os.environ.get("ZKB_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        mine = cpus & allowed
+        if len(mine) < 2 or mine == allowed:
+            return {"node": node, "cpus": len(allowed), "bound": False}
+        os.sched_setaffinity(0, mine)
+        return {"node": node, "cpus": len(mine), "bound": True, "all": sorted(allowed)}
+    except Exception:
+        return None
+
+
 class Env:
     """torch / torch.distributed / libzkb200 plumbing of one rank."""
 
@@ -203,6 +231,7 @@ class Env:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else None   # before any host thread / pinned buffer of this rank exists
         self.host_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
@@ -425,7 +454,8 @@ def headline_msm(env: Env, clocks: ClockSampler):
             "config": {"workload": WORKLOAD, "sharding": "srs_point_range_per_rank, host fold",
                        "l2": "inputs_exceed_l2 (512 MiB scalars + 1 GiB bases per step)", "window_bits": c_bits.value,
                        "windows": n_win.value, "srs_window_table_bytes": int(t_bytes.value), "srs_window_table_build_s": table_build_s,
-                       "chunk": chunk.value}}
+                       "chunk": chunk.value,
+                       "host_numa": ({k: v for k, v in env.numa.items() if k != "all"} if env.numa else None)}}
 
 
 # ---- secondary: batched NTT ----------------------------------------------------------------------------------------------------
@@ -1115,6 +1145,8 @@ def single_process_object(env: Env, mp_split, mp_split_point, mp_wrapper=None):
     world = env.world
     obj = {"devices": world}
     zkb.shutdown()
+    if env.numa and env.numa.get("bound"):   # one process drives every device now: back to all the host's cores
+        os.sched_setaffinity(0, set(env.numa["all"]))
     zkb.init(list(range(world)))
     try:
         # ---- the 2^26 MSM of msm_split, sharded by the library: same per-shard seeds, so the same points and scalars
