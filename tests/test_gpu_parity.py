@@ -271,6 +271,27 @@ def test_commit_batch_one_pass(oracle, k, ncols, precompute):
     zkb.lib().zkb_srs_set_precompute(1)
 
 
+def test_commit_batch_wider_than_one_key_group(oracle):
+    """Short columns against a long SRS: with the window table every column owns 2^(c-1) buckets for the SRS's c, so a batch soon
+    exceeds the 24 key bits of one sort pass (the library's own bucket sort) and is cut into groups — every column still gets its own
+    commitment."""
+    K, k = 20, 10
+    n = 1 << k
+    _, g = _bases_known_dlog(1 << K, 77)
+    params = zkb.ParamsKZG(K, g)
+    wb, tb = ctypes.c_uint32(0), ctypes.c_uint64(0)
+    zkb.lib().zkb_srs_precompute(params.handle_g, ctypes.byref(wb), ctypes.byref(tb))
+    assert wb.value >= 18
+    ncols = ((1 << 24) >> (wb.value - 1)) + 5              # one full group and a short second one
+    base_cols = [random_field(n, 1200 + i) for i in range(5)]
+    cols = [base_cols[i % 5] for i in range(ncols)]
+    got = params.commit_batch(cols)
+    want = [oracle.best_multiexp(p, g[:n]) for p in base_cols]
+    for i in range(ncols):
+        assert (got[i] == want[i % 5]).all(), i
+    params.close()
+
+
 # ---- BASELINE.json full sizes: size-independent properties -------------------------------------------------------------------
 @pytest.mark.parametrize("k", [22, 24])
 def test_ntt_full_size_roundtrip_and_linearity(oracle, k):

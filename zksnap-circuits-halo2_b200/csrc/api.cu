@@ -1272,7 +1272,7 @@ static int msm_batch_one(Srs* s, const uint64_t* const* scalars, size_t ncols, s
     std::lock_guard<std::recursive_mutex> lock(ctx().mu);
     ZKB_TRY(require_init());
     // all columns of a group are digit-decomposed, sorted and accumulated in ONE pass (column folded into the bucket
-    // key); groups bound the sort size to 2^28 (key, index) pairs, the bucket keys to 31 bits and the bucket arrays to a
+    // key); groups bound the sort size to 2^28 (key, index) pairs, the bucket keys to 24 bits and the bucket arrays to a
     // quarter of the free HBM (in table mode every column owns 2^(c-1) buckets whatever its length)
     const size_t per_col = n * 16;  // generous bound on windows per scalar
     size_t group = ((size_t)1 << 28) / per_col;
@@ -1285,7 +1285,9 @@ static int msm_batch_one(Srs* s, const uint64_t* const* scalars, size_t ncols, s
         const MsmGeometry g1 = table ? msm_geometry(n, s->table_c, c.msm_chunk_override, true, 1)
                                      : msm_geometry(n, c.msm_c_override, c.msm_chunk_override, false, 1);
         const size_t per_col_buckets = (size_t)g1.bucket_sets << (g1.c - 1);
-        size_t by_keys = (((size_t)1 << 31) - 1) / per_col_buckets;
+        // bucket keys of a group stay within the 24 bits the library's own bucket sort covers (bucket_sort.cuh), so no commit
+        // ever leaves it for the toolkit's radix sort; a single column never needs more (W x 2^(c-1) <= 13 x 2^19)
+        size_t by_keys = ((size_t)1 << 24) / per_col_buckets;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
         size_t by_mem = (free_b / 4) / (per_col_buckets * 128);
