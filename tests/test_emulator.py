@@ -704,7 +704,7 @@ def test_graph_row_windows_random_programs(oracle, seed):
         assert rc == 0 and (o == want[r * rows:(r + 1) * rows]).all()
 
 
-@pytest.mark.parametrize("u,distinct,big", [(1, 1, False), (9, 4, False), (300, 300, True), (1500, 33, True), (4000, 256, False)])
+@pytest.mark.parametrize("u,distinct,big", [(1, 1, False), (9, 4, False), (300, 300, True), (1500, 33, True), (4000, 256, False), (9000, 700, True), (40000, 5000, False)])
 def test_permute_expression_pair_device_phases_vs_oracle(oracle, u, distinct, big):
     """lookup.cuh's per-thread phases (canonical copies, four limb-wise stable sorts, first-occurrence flags, table matching by
     binary search, rank scans, leftover assignment) against the oracle's restatement of upstream's algorithm."""

@@ -1367,24 +1367,3 @@ def test_bucket_sort_full_size_and_refusals():
     assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 25, 0) != 0      # too wide for two levels
     assert lib.zkb_bucket_sort_pairs(k.ctypes.data_as(u32p), k.ctypes.data_as(u32p), 4, 10, 100) != 0    # tile not a multiple of the CTA
     assert lib.zkb_bucket_sort_pairs(None, k.ctypes.data_as(u32p), 4, 10, 0) != 0
-
-
-def test_msm_same_result_with_either_sort():
-    """ZKB_MSM_SORT=cub (a fresh process: the variable is read once) keeps the toolkit's radix sort as the fallback path for keys wider
-    than 22 bits; both must give the oracle's commitment, also for a batch whose folded key needs the fallback."""
-    code = (
-        "import os, sys, importlib, numpy as np\n"
-        "sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
-        "from util import random_field\n"
-        "from oracle import coracle\n"
-        "zkb = importlib.import_module('zksnap-circuits-halo2_b200')\n"
-        "zkb.init(0); coracle.build()\n"
-        "n = 1 << 12\n"
-        "b = zkb.g1_fixed_base_mul(random_field(n, 2)); s = random_field(n, 3)\n"
-        "p = zkb.ParamsKZG(12, b)\n"
-        "assert (p.commit(s) == coracle.best_multiexp(s, b)).all()\n"
-        "print('OK')\n" % (ROOT, ROOT))
-    for mode in ("cub", "own"):
-        env = dict(os.environ, ZKB_MSM_SORT=mode)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0 and "OK" in r.stdout, (mode, r.stdout[-500:], r.stderr[-2000:])

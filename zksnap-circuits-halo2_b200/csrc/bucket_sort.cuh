@@ -13,8 +13,8 @@
 //            each (tile -> segment by binary search in the scanned tile counts); a segment's sub-bins are laid out in order
 //            inside the segment, so after level 2 the array is sorted by the whole key.
 //
-// Keys of up to 12 bits take one level, up to 24 bits two (every MSM of this library: c <= 22 and few columns; wider keys —
-// hundreds of columns folded into the key — fall back to the toolkit's radix sort in msm.cu).  Any digit distribution is
+// Keys of up to 12 bits take one level, up to 24 bits two: every commit of this library (with the window table 2^(c-1) <= 2^21 buckets
+// per column; without it c is capped so that W x 2^(c-1) <= 2^24; batches are cut into groups that fit).  Any digit distribution is
 // handled by construction: tiles are equal-sized pieces of the INPUT, a heavy bucket is just a long run that many tiles
 // append to (witness columns put most entries into a few buckets; the all-equal column puts everything into W of them).
 // Two passes over the pairs instead of the three of an 8-bit least-significant-digit sort, no ranking by warp-wide matching, and

@@ -1,6 +1,4 @@
 // msm.cu — kernels and host driver of the G1 MSM (see msm.cuh for the algorithm).
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cstdlib>
 #include <cstring>
 
@@ -427,20 +425,13 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_TRY(keys[i].reserve(total * 4));
         ZKB_TRY(vals[i].reserve(total * 4));
     }
-    size_t sort_bytes = 0;
-    {
-        cub::DoubleBuffer<uint32_t> dk(keys[0].as<uint32_t>(), keys[1].as<uint32_t>());
-        cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
-        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, (int)total, 0, (int)g.key_bits, sp));
-    }
-    // the library's own bucket sort (bucket_sort.cuh) unless the key is too wide for two levels or ZKB_MSM_SORT=cub asks for the toolkit's
-    static const bool own_sort = !(getenv("ZKB_MSM_SORT") && !strcmp(getenv("ZKB_MSM_SORT"), "cub"));
+    // the library's own bucket sort (bucket_sort.cuh): keys of up to 24 bits — every single-column commit (W x 2^(c-1) <= 13 x 2^19) and
+    // every group of a batch (the caller bounds its groups accordingly)
     uint32_t sort_kb = 1;  // keys are < nbuckets (zero digits are never emitted, so there is no "invalid" key to sort)
     while ((1ull << sort_kb) < g.nbuckets) ++sort_kb;
     const BsortPlan bp0 = bsort_plan(total, sort_kb);
-    const bool use_own = own_sort && bp0.levels > 0;
-    if (use_own && bp0.words * 4 > sort_bytes) sort_bytes = bp0.words * 4;
-    ZKB_TRY(w.sort_tmp[set].reserve(sort_bytes));
+    if (!bp0.levels) { set_error("MSM batch too wide for one sort pass: %u bucket-key bits (at most %u)", sort_kb, 2 * BSORT_MAX_BITS); return ZKB_ERR_ARG; }
+    ZKB_TRY(w.sort_tmp[set].reserve(bp0.words * 4));
     ZKB_TRY(w.counter[set].reserve(8));
     if (overlap) {
         ZKB_CUDA_TRY(cudaStreamWaitEvent(sp, input_ready, 0));
@@ -499,21 +490,15 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
     const uint32_t* sv;
     {
         ProfScope prof("msm_sort", sp);
-        if (use_own) {
+        {
             static const uint32_t tile_override = getenv("ZKB_MSM_SORT_TILE") ? (uint32_t)atoi(getenv("ZKB_MSM_SORT_TILE")) : 0;
-            int cur = 0;
-            static const uint32_t b1_override = getenv("ZKB_MSM_SORT_B1") ? (uint32_t)atoi(getenv("ZKB_MSM_SORT_B1")) : 0;   // experiment hook
+            static const uint32_t b1_override = getenv("ZKB_MSM_SORT_B1") ? (uint32_t)atoi(getenv("ZKB_MSM_SORT_B1")) : 0;   // experiment hooks
             const BsortPlan bp = bsort_plan(valid, sort_kb, tile_override, b1_override);
             ZKB_TRY(w.sort_tmp[set].reserve(bp.words * 4));   // a shorter tile can mean more tile descriptors than the first estimate
+            int cur = 0;
             if (valid) ZKB_TRY(bsort_run(keys, vals, w.sort_tmp[set], reinterpret_cast<const unsigned long long*>(w.counter[set].p), valid, bp, sp, &cur));
             sk = keys[cur].as<uint32_t>();
             sv = vals[cur].as<uint32_t>();
-        } else {
-            cub::DoubleBuffer<uint32_t> dk(keys[0].as<uint32_t>(), keys[1].as<uint32_t>());
-            cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
-            if (valid) ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.sort_tmp[set].p, sort_bytes, dk, dv, (int)valid, 0, (int)sort_kb, sp));
-            sk = dk.Current();
-            sv = dv.Current();
         }
     }
     if (overlap) {

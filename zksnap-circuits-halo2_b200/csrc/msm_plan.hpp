@@ -94,6 +94,9 @@ inline MsmGeometry msm_geometry(uint64_t n, uint32_t c_override = 0, uint32_t ch
     if (g.c < 2) g.c = 2;
     if (g.c > 22) g.c = 22;
     g.nwin = (255 + g.c - 1) / g.c;
+    // without the window table every window has its own bucket set: keep W x 2^(c-1) within the 24 key bits of one sort pass
+    // (bucket_sort.cuh) — only c = 22 (12 x 2^21) exceeds them, at sizes where c = 21 costs < 4 % more additions
+    while (!table && g.c > 2 && ((uint64_t)g.nwin << (g.c - 1)) > (1ull << 24)) { --g.c; g.nwin = (255 + g.c - 1) / g.c; }
     g.bucket_sets = table ? 1 : g.nwin;
     g.total_sets = g.bucket_sets * g.ncols;
     g.nbuckets = g.total_sets << (g.c - 1);

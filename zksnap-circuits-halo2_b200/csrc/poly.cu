@@ -11,8 +11,6 @@
 
 #include "msm_host.hpp"
 #include "ntt_host.hpp"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include "graph.cuh"
 #include "lookup.cuh"
@@ -89,12 +87,103 @@ __global__ void __launch_bounds__(128) graph_evaluate_kernel(const GraphArgs g, 
 }
 
 __global__ void __launch_bounds__(128) lookup_canon_kernel(const LookupArgs a) { lookup_canon_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(128) lookup_gather_limb_kernel(const uint4* canon, const uint32_t* idx, uint64_t u, uint32_t limb, unsigned long long* keys) {
-    lookup_gather_limb_thread(canon, idx, u, limb, keys, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(128) lookup_sort_init_kernel(const LookupSortArgs a) { lookup_sort_init_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) lookup_sort_global_kernel(const LookupSortArgs a, uint64_t k, uint64_t j) {
+    lookup_sort_global_thread(a, k, j, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-__global__ void __launch_bounds__(128) lookup_iota_kernel(uint32_t* idx, uint64_t u) {
+__global__ void __launch_bounds__(128) lookup_sort_global2_kernel(const LookupSortArgs a, uint64_t k, uint32_t log_j) {
+    lookup_sort_global2_thread(a, k, log_j, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+// steps (k, j) for k = k_first .. k_last, j from (k == k_first && j_first ? j_first : k / 2) down to 1, on one block in shared memory
+__global__ void __launch_bounds__(LOOKUP_SORT_THREADS) lookup_sort_block_kernel(const LookupSortArgs a, uint64_t k_first, uint64_t k_last, uint32_t j_first) {
+    extern __shared__ uint4 lookup_sort_smem[];
+    uint4* slo = lookup_sort_smem;
+    uint4* shi = slo + LOOKUP_SORT_BLOCK;
+    uint32_t* srow = reinterpret_cast<uint32_t*>(shi + LOOKUP_SORT_BLOCK);
+    lookup_sort_block_load(a, blockIdx.x, threadIdx.x, slo, shi, srow);
+    for (uint64_t k = k_first; k <= k_last; k <<= 1)
+        for (uint32_t j = (k == k_first && j_first) ? j_first : (uint32_t)(k / 2); j >= 1; j >>= 1) {
+            __syncthreads();
+            lookup_sort_block_step(blockIdx.x, threadIdx.x, k, j, slo, shi, srow);
+        }
+    __syncthreads();
+    lookup_sort_block_store(a, blockIdx.x, threadIdx.x, slo, shi, srow);
+}
+__global__ void __launch_bounds__(128) lookup_take_rows_kernel(const uint32_t* row, uint32_t* idx, uint64_t u) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < u) idx[i] = (uint32_t)i;
+    if (i < u) idx[i] = row[i];
+}
+// ---- exclusive scan of 32-bit counts (the ranks of the lookup argument): tiles of 4096, tile sums scanned by one CTA (u <= 2^32 / ...) ---
+constexpr uint32_t SCAN_THREADS = 1024, SCAN_ITEMS = 4, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+__device__ __forceinline__ uint32_t scan_cta_exclusive(uint32_t v, uint32_t* wsum, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += x;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = wsum[lane];   // SCAN_THREADS / 32 == 32 warps
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += x;
+        }
+        wsum[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return wsum[warp] + incl - v;
+}
+// phase 0: out = exclusive scan inside every tile, sums[tile] = tile total; phase 1 (one CTA): sums -> exclusive scan of sums, tile by
+// tile; phase 2: out += sums[tile]
+__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t* sums, uint64_t n, int phase) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t total;
+    if (phase == 0) {
+        const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+        uint32_t run = scan_cta_exclusive(s, wsum, &total);
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = run; run += v[i]; }
+        if (threadIdx.x == 0) sums[blockIdx.x] = total;
+    } else if (phase == 1) {
+        uint32_t carry = 0;   // n = number of tiles here
+        for (uint64_t first = 0; first < n; first += SCAN_THREADS) {
+            const uint64_t i = first + threadIdx.x;
+            const uint32_t v = i < n ? sums[i] : 0;
+            const uint32_t ex = scan_cta_exclusive(v, wsum, &total);
+            if (i < n) sums[i] = carry + ex;
+            carry += total;
+            __syncthreads();
+        }
+    } else {
+        const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        const uint32_t add = sums[blockIdx.x];
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < n) out[base + i] += add;
+    }
+}
+static int scan_u32_exclusive_dev(const uint32_t* in, uint32_t* out, uint64_t n, DevBuf& tmp, cudaStream_t s) {
+    const uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    ZKB_TRY(tmp.reserve(tiles * 4 + 16));
+    uint32_t* sums = tmp.as<uint32_t>();
+    scan_u32_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, out, sums, n, 0);
+    if (tiles > 1) {
+        scan_u32_kernel<<<1, SCAN_THREADS, 0, s>>>(nullptr, nullptr, sums, tiles, 1);
+        scan_u32_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(nullptr, out, sums, n, 2);
+        count_launch(2);
+    }
+    count_launch();
+    ZKB_CUDA_TRY(cudaGetLastError());
+    return ZKB_OK;
 }
 __global__ void __launch_bounds__(128) lookup_first_kernel(const LookupArgs a) { lookup_first_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(128) lookup_match_kernel(const LookupArgs a) { lookup_match_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
@@ -644,23 +733,36 @@ int zkb_poly_prefix_product(uint64_t poly) {
 }
 
 // ---- lookup argument: permute_expression_pair on resident columns (lookup.cuh) -------------------------------------------------------
-// sorted order of `canon` (u canonical 256-bit values) into idx: four stable radix sorts on the 64-bit limbs, least significant first
-static int lookup_sort_dev(const uint4* canon, uint64_t u, uint32_t* idx, uint32_t* idx_alt, unsigned long long* keys, unsigned long long* keys_alt,
-                           DevBuf& tmp, cudaStream_t s) {
-    lookup_iota_kernel<<<nblk(u, 128), 128, 0, s>>>(idx, u);
+// sorted order of `canon` (u canonical 256-bit values) into idx: the bitonic network of lookup.cuh over (value, row) records
+static int lookup_sort_dev(const uint4* canon, uint64_t u, uint32_t* idx, DevBuf& ws, cudaStream_t s) {
+    LookupSortArgs a{};
+    a.log_p = lookup_sort_log_p(u);
+    const uint64_t P = (uint64_t)1 << a.log_p;
+    ZKB_TRY(ws.reserve(P * 36));
+    a.klo = ws.as<uint4>();
+    a.khi = a.klo + P;
+    a.row = reinterpret_cast<uint32_t*>(a.khi + P);
+    a.canon = canon;
+    a.u = u;
+    lookup_sort_init_kernel<<<nblk(P, 128), 128, 0, s>>>(a);
     count_launch();
-    uint32_t* cur = idx;
-    uint32_t* alt = idx_alt;
-    for (uint32_t limb = 0; limb < 4; ++limb) {
-        lookup_gather_limb_kernel<<<nblk(u, 128), 128, 0, s>>>(canon, cur, u, limb, keys);
-        count_launch();
-        size_t bytes = 0;
-        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys_alt, cur, alt, (int)u, 0, 64, s));
-        ZKB_TRY(tmp.reserve(bytes));
-        ZKB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys, keys_alt, cur, alt, (int)u, 0, 64, s));
-        uint32_t* t = cur; cur = alt; alt = t;
+    constexpr size_t block_smem = (size_t)LOOKUP_SORT_BLOCK * 36;
+    struct LookupSortAttr { bool set = false; };
+    bool& attr = per_device<LookupSortAttr>().set;
+    if (!attr) {
+        ZKB_CUDA_TRY(cudaFuncSetAttribute(lookup_sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem));
+        attr = true;
     }
-    if (cur != idx) ZKB_CUDA_TRY(cudaMemcpyAsync(idx, cur, u * 4, cudaMemcpyDeviceToDevice, s));   // four swaps: already back in idx
+    lookup_sort_schedule(
+        a.log_p,
+        [&](uint64_t k, uint64_t j) { lookup_sort_global_kernel<<<nblk(P / 2, 128), 128, 0, s>>>(a, k, j); count_launch(); },
+        [&](uint64_t k, uint32_t log_j) { lookup_sort_global2_kernel<<<nblk(P / 4, 128), 128, 0, s>>>(a, k, log_j); count_launch(); },
+        [&](uint64_t k_first, uint64_t k_last, uint32_t j_first) {
+            lookup_sort_block_kernel<<<(unsigned)(P / LOOKUP_SORT_BLOCK), LOOKUP_SORT_THREADS, block_smem, s>>>(a, k_first, k_last, j_first);
+            count_launch();
+        });
+    lookup_take_rows_kernel<<<nblk(u, 128), 128, 0, s>>>(a.row, idx, u);   // the padding sorted to the end
+    count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
     return ZKB_OK;
 }
@@ -856,22 +958,20 @@ int zkb_lookup_permute_expression_pair(uint64_t input, uint64_t table, size_t us
     };
     if (cudaMemsetAsync(oi->buf.p, 0, pi->n ? pi->n * 32 : 32, s) != cudaSuccess || cudaMemsetAsync(ot->buf.p, 0, pi->n ? pi->n * 32 : 32, s) != cudaSuccess) return fail(ZKB_ERR_CUDA);
     if (u == 0) return ZKB_OK;
-    // workspace: canonical copies (2 x 32 u), sort keys (2 x 8 u), five index / flag arrays ... in one buffer
-    struct LookupWs { DevBuf buf, cub; uint32_t* h_flag = nullptr; };
+    // workspace: canonical copies (2 x 32 u) and the index / flag arrays in one buffer; the sort's records and the scan's tile sums in `sort`
+    struct LookupWs { DevBuf buf, sort; uint32_t* h_flag = nullptr; };
     LookupWs& ws = per_device<LookupWs>();
-    const size_t need = u * (64 + 16 + 4 * 10) + 256;
+    const size_t need = u * (64 + 4 * 10) + 256;
     rc = ws.buf.reserve(need);
     if (rc != ZKB_OK) return fail(rc);
     if (!ws.h_flag && cudaMallocHost(&ws.h_flag, 16) != cudaSuccess) { cudaGetLastError(); set_error("pinned allocation failed"); return fail(ZKB_ERR_OOM); }
     char* b = ws.buf.as<char>();
     uint4* canon_in = reinterpret_cast<uint4*>(b); b += u * 32;
     uint4* canon_tab = reinterpret_cast<uint4*>(b); b += u * 32;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(b); b += u * 8;
-    unsigned long long* keys_alt = reinterpret_cast<unsigned long long*>(b); b += u * 8;
     uint32_t* arr[10];
     for (auto& x : arr) { x = reinterpret_cast<uint32_t*>(b); b += u * 4; }
     uint32_t* d_flags = reinterpret_cast<uint32_t*>(b);   // [0] missing
-    uint32_t *idx_in = arr[0], *idx_tab = arr[1], *alt = arr[2], *first = arr[3], *consumed = arr[4], *rep_rank = arr[5], *left_rank = arr[6],
+    uint32_t *idx_in = arr[0], *idx_tab = arr[1], *first = arr[3], *consumed = arr[4], *rep_rank = arr[5], *left_rank = arr[6],
              *rep_rows = arr[7], *inv = arr[8];
     LookupArgs a{};
     a.input = pi->buf.as<uint4>(); a.table = pt->buf.as<uint4>(); a.u = u;
@@ -884,8 +984,8 @@ int zkb_lookup_permute_expression_pair(uint64_t input, uint64_t table, size_t us
     const unsigned nb = nblk(u, 128);
     lookup_canon_kernel<<<nb, 128, 0, s>>>(a);
     count_launch();
-    rc = lookup_sort_dev(canon_in, u, idx_in, alt, keys, keys_alt, ws.cub, s);
-    if (rc == ZKB_OK) rc = lookup_sort_dev(canon_tab, u, idx_tab, alt, keys, keys_alt, ws.cub, s);
+    rc = lookup_sort_dev(canon_in, u, idx_in, ws.sort, s);
+    if (rc == ZKB_OK) rc = lookup_sort_dev(canon_tab, u, idx_tab, ws.sort, s);
     if (rc != ZKB_OK) return fail(rc);
     lookup_first_kernel<<<nb, 128, 0, s>>>(a);
     lookup_match_kernel<<<nb, 128, 0, s>>>(a);
@@ -894,10 +994,7 @@ int zkb_lookup_permute_expression_pair(uint64_t input, uint64_t table, size_t us
     auto scan_not = [&](const uint32_t* flags, uint32_t* out) -> int {
         lookup_not_kernel<<<nb, 128, 0, s>>>(flags, inv, u);
         count_launch();
-        size_t bytes = 0;
-        ZKB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, inv, out, (int)u, s));
-        ZKB_TRY(ws.cub.reserve(bytes));
-        ZKB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws.cub.p, bytes, inv, out, (int)u, s));
+        ZKB_TRY(scan_u32_exclusive_dev(inv, out, u, ws.sort, s));
         return ZKB_OK;
     };
     rc = scan_not(first, rep_rank);
