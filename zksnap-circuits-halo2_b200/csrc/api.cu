@@ -456,8 +456,11 @@ static int domain_op_dev(DomainOp op, const uint4* d_in, uint4* d_a, uint4* d_b,
 // and group i-1 is copied device->host on `s_d2h` (PCIe is full duplex).  Pageable caller memory (a Rust Vec) is
 // staged through per-slot pinned buffers by a small pool of host threads; pinned / registered caller memory is
 // DMA'd directly.
+struct HostCopy { void* dst; const void* src; size_t bytes; };
 struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
     std::vector<std::thread> workers;
+    const HostCopy* list = nullptr;   // copy_many: the threads split the CONCATENATED byte range of the list
+    size_t list_count = 0;
     std::mutex mu;
     std::condition_variable cv_go, cv_done;
     uint64_t gen = 0;
@@ -485,7 +488,16 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
         size_t lo = (size_t)i * per, hi = lo + per;
         if (lo >= bytes) return;
         if (hi > bytes) hi = bytes;
-        memcpy(dst + lo, src + lo, hi - lo);
+        if (!list) { memcpy(dst + lo, src + lo, hi - lo); return; }
+        size_t off = 0;   // start of the current list entry in the concatenation
+        for (size_t e = 0; e < list_count && off < hi; ++e) {
+            const size_t b = list[e].bytes;
+            if (off + b > lo) {
+                const size_t from = lo > off ? lo - off : 0, to = hi - off < b ? hi - off : b;
+                memcpy((char*)list[e].dst + from, (const char*)list[e].src + from, to - from);
+            }
+            off += b;
+        }
     }
     void loop(unsigned i, uint64_t seen) {
         for (;;) {
@@ -502,12 +514,36 @@ struct HostPool {  // parallel memcpy for the pageable <-> pinned staging copies
             }
         }
     }
+    // many copies as ONE parallel job: a batch of short columns (hundreds of 256 KiB .. 1 MiB arrays for the voter circuit) would
+    // otherwise be copied one column at a time by one thread each (measured: a pageable 256-column coeff_to_extended batch 34 ms
+    // against 7 ms from page-locked memory)
+    void copy_many(const HostCopy* l, size_t count) {
+        size_t total = 0;
+        for (size_t e = 0; e < count; ++e) total += l[e].bytes;
+        if (total >= (4u << 20)) start();
+        if (total < (4u << 20) || nparts <= 1) {
+            for (size_t e = 0; e < count; ++e) memcpy(l[e].dst, l[e].src, l[e].bytes);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            list = l; list_count = count; bytes = total;
+            pending = nparts - 1;
+            ++gen;
+        }
+        cv_go.notify_all();
+        part(0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        list = nullptr; list_count = 0;
+    }
     void copy(void* d, const void* s, size_t n) {
         if (n < (4u << 20)) { memcpy(d, s, n); return; }
         start();
         if (nparts <= 1) { memcpy(d, s, n); return; }
         {
             std::lock_guard<std::mutex> lk(mu);
+            list = nullptr; list_count = 0;
             dst = (char*)d; src = (const char*)s; bytes = n;
             pending = nparts - 1;
             ++gen;
@@ -539,7 +575,7 @@ static HostPool& out_pool() { return per_device<StageOutPool>(); }
 // staging buffer into the caller's arrays while the calling thread is already staging the next group in — without it the two
 // host copies serialise and a pageable batch runs at half the speed of a page-locked one (tools/ntt_e2e_ab.py).
 struct Drainer {
-    struct Copy { void* dst; const void* src; size_t bytes; };
+    using Copy = HostCopy;
     struct Job { cudaEvent_t ev; std::vector<Copy> copies; uint64_t id; };
     std::thread th;
     std::mutex mu;
@@ -568,7 +604,7 @@ struct Drainer {
                 q.pop_front();
             }
             bool ok = cudaEventSynchronize(j.ev) == cudaSuccess;
-            if (ok) for (auto& c : j.copies) out_pool().copy(c.dst, c.src, c.bytes);
+            if (ok) out_pool().copy_many(j.copies.data(), j.copies.size());
             {
                 std::lock_guard<std::mutex> lk(mu);
                 if (!ok) failed = true;
@@ -734,14 +770,23 @@ static int domain_op_host_one(DomainOp op, const uint64_t* const* in, uint64_t* 
         if (rc != ZKB_OK) return fail(rc);
         char* d_in = op == OP_C2E ? (char*)s.in.p : (char*)s.x.p;
         cudaError_t e = cudaSuccess;
-        for (size_t i = 0; i < nc && e == cudaSuccess; ++i) {
-            const void* src = in[c0 + i];
-            if (!pinned_in[c0 + i]) {
-                host_pool().copy((char*)s.h_in.p + i * col_in, src, col_in);
-                src = (char*)s.h_in.p + i * col_in;
+        bool all_pg_in = true, all_pg_out = true;
+        for (size_t i = 0; i < nc; ++i) { all_pg_in &= !pinned_in[c0 + i]; all_pg_out &= !pinned_out[c0 + i]; }
+        if (any_pg_in) {   // every pageable column of the group in one parallel copy
+            std::vector<HostCopy> stage;
+            for (size_t i = 0; i < nc; ++i)
+                if (!pinned_in[c0 + i]) stage.push_back({(char*)s.h_in.p + i * col_in, in[c0 + i], col_in});
+            host_pool().copy_many(stage.data(), stage.size());
+        }
+        if (all_pg_in) {   // the staged group is contiguous on both sides: one DMA
+            e = cudaMemcpyAsync(d_in, s.h_in.p, nc * col_in, cudaMemcpyHostToDevice, pl.s_h2d);
+            count_h2d(nc * col_in);
+        } else {
+            for (size_t i = 0; i < nc && e == cudaSuccess; ++i) {
+                const void* src = pinned_in[c0 + i] ? (const void*)in[c0 + i] : (const void*)((char*)s.h_in.p + i * col_in);
+                e = cudaMemcpyAsync(d_in + i * col_in, src, col_in, cudaMemcpyHostToDevice, pl.s_h2d);
+                count_h2d(col_in);
             }
-            e = cudaMemcpyAsync(d_in + i * col_in, src, col_in, cudaMemcpyHostToDevice, pl.s_h2d);
-            count_h2d(col_in);
         }
         if (e == cudaSuccess) e = cudaEventRecord(s.ev_h2d, pl.s_h2d);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(c.stream, s.ev_h2d, 0);
@@ -750,9 +795,13 @@ static int domain_op_host_one(DomainOp op, const uint64_t* const* in, uint64_t* 
         if (rc != ZKB_OK) return fail(rc);
         e = cudaEventRecord(s.ev_comp, c.stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(pl.s_d2h, s.ev_comp, 0);
-        for (size_t i = 0; i < nc && e == cudaSuccess; ++i) {
-            void* dst = pinned_out[c0 + i] ? (void*)out[c0 + i] : (void*)((char*)s.h_out.p + i * col_out);
-            e = cudaMemcpyAsync(dst, (char*)s.x.p + i * col_out, col_out, cudaMemcpyDeviceToHost, pl.s_d2h);
+        if (all_pg_out) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(s.h_out.p, s.x.p, nc * col_out, cudaMemcpyDeviceToHost, pl.s_d2h);
+        } else {
+            for (size_t i = 0; i < nc && e == cudaSuccess; ++i) {
+                void* dst = pinned_out[c0 + i] ? (void*)out[c0 + i] : (void*)((char*)s.h_out.p + i * col_out);
+                e = cudaMemcpyAsync(dst, (char*)s.x.p + i * col_out, col_out, cudaMemcpyDeviceToHost, pl.s_d2h);
+            }
         }
         if (e == cudaSuccess) e = cudaEventRecord(s.ev_d2h, pl.s_d2h);
         if (e != cudaSuccess) { set_error("device->host staging failed: %s", cudaGetErrorString(e)); return fail(ZKB_ERR_CUDA); }
@@ -1299,9 +1348,19 @@ static int msm_batch_one(Srs* s, const uint64_t* const* scalars, size_t ncols, s
     for (size_t c0 = 0; c0 < ncols; c0 += group) {
         size_t nc = ncols - c0 < group ? ncols - c0 : group;
         ZKB_TRY(h.scalars.reserve(nc * n * 32));
-        for (size_t i = 0; i < nc; ++i)
-            ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h.scalars.p) + i * n * 32, scalars[c0 + i], n * 32,
-                                         cudaMemcpyHostToDevice, c.stream));
+        bool all_pageable = nc * n * 32 >= ((size_t)4 << 20);
+        for (size_t i = 0; i < nc && all_pageable; ++i) all_pageable = !host_ptr_is_pinned(scalars[c0 + i]);
+        if (all_pageable) {   // many short pageable columns (the voter circuit): one parallel staging copy, one DMA
+            ZKB_TRY(h.stage[0].reserve(nc * n * 32));
+            std::vector<HostCopy> stage(nc);
+            for (size_t i = 0; i < nc; ++i) stage[i] = {(char*)h.stage[0].p + i * n * 32, scalars[c0 + i], n * 32};
+            host_pool().copy_many(stage.data(), stage.size());
+            ZKB_CUDA_TRY(cudaMemcpyAsync(h.scalars.p, h.stage[0].p, nc * n * 32, cudaMemcpyHostToDevice, c.stream));   // msm_run synchronises: the buffer is free again afterwards
+        } else {
+            for (size_t i = 0; i < nc; ++i)
+                ZKB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h.scalars.p) + i * n * 32, scalars[c0 + i], n * 32,
+                                             cudaMemcpyHostToDevice, c.stream));
+        }
         count_h2d(nc * n * 32);
         ZKB_TRY(msm_srs_dev(s, 0, h.scalars.as<uint4>(), n, c.stream, out_jac + 12 * c0, (uint32_t)nc));
     }
