@@ -41,15 +41,19 @@ ZKB_HD void lookup_canon_thread(const LookupArgs& a, uint64_t i) {
     fr_store2(a.canon_tab, i, fp_from_mont(fr_load2(a.table, i)));
 }
 
-// ---- the sort: a bitonic network over (canonical value, row) records -----------------------------------------------------------------
+// ---- the sort: (canonical value, row) records, block-wise bitonic network + merge-path merges --------------------------------------------
 // The records are compared as the pair (256-bit value, original row), a TOTAL order, so the result is exactly what a stable sort by
 // value gives and does not depend on the schedule.  P = 2^log_p >= u records (the padding carries the all-ones key, above every
-// canonical value, and row 0xffffffff), structure-of-arrays so that every access is a full 16-byte or 4-byte vector.  Steps (k, j)
-// with j >= LOOKUP_SORT_BLOCK exchange partners that are far apart: they run on global memory, TWO consecutive j per launch (a thread
-// owns the four records that differ in bits j and j / 2, so the array is read and written once for two steps); all the steps with
-// j < LOOKUP_SORT_BLOCK of one k (and the whole network up to k = LOOKUP_SORT_BLOCK) run inside one CTA on a block staged in shared
-// memory.  Written by hand instead of calling a library sort: no library kernel is left anywhere in this package.
-constexpr uint32_t LOOKUP_SORT_BLOCK = 4096;                 // records per CTA block (144 KB of shared memory: one CTA per SM)
+// canonical value, and row 0xffffffff), structure-of-arrays so that every access is a full 16-byte or 4-byte vector.
+//   1. every block of LOOKUP_SORT_BLOCK records is sorted ascending inside one CTA: the bitonic network on shared memory;
+//   2. log2(P / block) merge passes, runs of length L pairwise into runs of 2 L (ping-pong buffers): a partition kernel finds, for
+//      every output tile of LOOKUP_MERGE_TILE records, how many of the records before it come from the left run (merge path: one
+//      binary search per tile boundary, all boundaries in parallel); a CTA then stages its tile's two input pieces in shared memory,
+//      every thread finds its own split the same way and merges LOOKUP_MERGE_VT records serially.  The array is read and written
+//      once per pass (a bitonic network over global memory needs ~3 passes per doubling at 2^22 records: measured 9.1 ms for the
+//      whole permute_expression_pair against the merges' figure in DESIGN.md).
+// Written by hand instead of calling a library sort: no library kernel is left anywhere in this package.
+constexpr uint32_t LOOKUP_SORT_BLOCK = 4096;                 // records per bitonic block (144 KB of shared memory: one CTA per SM)
 constexpr uint32_t LOOKUP_SORT_LOG_BLOCK = 12;
 constexpr uint32_t LOOKUP_SORT_THREADS = 1024;               // two pairs per thread and step
 struct LookupSortArgs {
@@ -81,40 +85,6 @@ ZKB_HD void lookup_sort_pair(uint64_t t, uint64_t j, uint64_t* i, uint64_t* p) {
     *i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
     *p = *i | j;
 }
-ZKB_HD void lookup_sort_global_thread(const LookupSortArgs& a, uint64_t k, uint64_t j, uint64_t t) {
-    if (t >= ((uint64_t)1 << a.log_p) / 2) return;
-    uint64_t i, p;
-    lookup_sort_pair(t, j, &i, &p);
-    const uint4 alo = a.klo[i], ahi = a.khi[i], blo = a.klo[p], bhi = a.khi[p];
-    const uint32_t ar = a.row[i], br = a.row[p];
-    const bool up = (i & k) == 0;
-    if (lookup_rec_less(blo, bhi, br, alo, ahi, ar) == up) {   // out of order for this direction: exchange
-        a.klo[i] = blo; a.khi[i] = bhi; a.row[i] = br;
-        a.klo[p] = alo; a.khi[p] = ahi; a.row[p] = ar;
-    }
-}
-// steps (k, j) and (k, j / 2) in one pass: thread t owns the records at q, q | j/2, q | j, q | j | j/2 (q: bits j and j/2 clear)
-ZKB_HD void lookup_sort_global2_thread(const LookupSortArgs& a, uint64_t k, uint32_t log_j, uint64_t t) {
-    if (t >= ((uint64_t)1 << a.log_p) / 4) return;
-    const uint64_t j = (uint64_t)1 << log_j, h = j >> 1;
-    const uint64_t low = t & (h - 1), rest = t >> (log_j - 1);   // two zero bits inserted at log2(h) and log2(j)
-    const uint64_t q = (rest << (log_j + 1)) | low;
-    const uint64_t pos[4] = {q, q | h, q | j, q | j | h};
-    uint4 lo[4], hi[4];
-    uint32_t row[4];
-    for (int e = 0; e < 4; ++e) { lo[e] = a.klo[pos[e]]; hi[e] = a.khi[pos[e]]; row[e] = a.row[pos[e]]; }
-    const bool up = (q & k) == 0;   // k > j: the same direction for the four records
-    auto cx = [&](int x, int y) {
-        if (lookup_rec_less(lo[y], hi[y], row[y], lo[x], hi[x], row[x]) == up) {
-            const uint4 tl = lo[x], th = hi[x]; const uint32_t tr = row[x];
-            lo[x] = lo[y]; hi[x] = hi[y]; row[x] = row[y];
-            lo[y] = tl; hi[y] = th; row[y] = tr;
-        }
-    };
-    cx(0, 2); cx(1, 3);   // step j
-    cx(0, 1); cx(2, 3);   // step j / 2
-    for (int e = 0; e < 4; ++e) { a.klo[pos[e]] = lo[e]; a.khi[pos[e]] = hi[e]; a.row[pos[e]] = row[e]; }
-}
 // block kernel phases: shared arrays slo / shi / srow of LOOKUP_SORT_BLOCK records; block b covers [b, b + 1) * LOOKUP_SORT_BLOCK
 ZKB_HD void lookup_sort_block_load(const LookupSortArgs& a, uint64_t block, uint32_t tid, uint4* slo, uint4* shi, uint32_t* srow) {
     for (uint32_t r = tid; r < LOOKUP_SORT_BLOCK; r += LOOKUP_SORT_THREADS) {
@@ -122,11 +92,11 @@ ZKB_HD void lookup_sort_block_load(const LookupSortArgs& a, uint64_t block, uint
         slo[r] = a.klo[g]; shi[r] = a.khi[g]; srow[r] = a.row[g];
     }
 }
-ZKB_HD void lookup_sort_block_step(uint64_t block, uint32_t tid, uint64_t k, uint32_t j, uint4* slo, uint4* shi, uint32_t* srow) {
+ZKB_HD void lookup_sort_block_step(uint32_t tid, uint32_t k, uint32_t j, uint4* slo, uint4* shi, uint32_t* srow) {
     for (uint32_t t = tid; t < LOOKUP_SORT_BLOCK / 2; t += LOOKUP_SORT_THREADS) {
         uint64_t i, p;
         lookup_sort_pair(t, j, &i, &p);
-        const bool up = ((block * LOOKUP_SORT_BLOCK + i) & k) == 0;
+        const bool up = (i & k) == 0;   // local index: at k = block size every block ends ascending
         const uint4 alo = slo[i], ahi = shi[i], blo = slo[p], bhi = shi[p];
         const uint32_t ar = srow[i], br = srow[p];
         if (lookup_rec_less(blo, bhi, br, alo, ahi, ar) == up) {
@@ -141,22 +111,73 @@ ZKB_HD void lookup_sort_block_store(const LookupSortArgs& a, uint64_t block, uin
         a.klo[g] = slo[r]; a.khi[g] = shi[r]; a.row[g] = srow[r];
     }
 }
-// the schedule, shared by the driver and the emulator: calls global(k, j) / block(k_first, k_last, j_first) in network order
-template <class G, class G2, class B>
-inline void lookup_sort_schedule(uint32_t log_p, G&& global, G2&& global2, B&& block) {
-    const uint64_t P = (uint64_t)1 << log_p;
-    block(2, P < LOOKUP_SORT_BLOCK ? P : (uint64_t)LOOKUP_SORT_BLOCK, 0);     // the whole network up to k = block size (j_first 0: from k / 2)
-    for (uint64_t k = 2 * (uint64_t)LOOKUP_SORT_BLOCK; k <= P; k <<= 1) {
-        uint64_t j = k / 2;
-        for (; j >= 2 * (uint64_t)LOOKUP_SORT_BLOCK; j >>= 2) {   // steps j and j / 2, both still >= the block size
-            uint32_t log_j = 0;
-            while (((uint64_t)1 << log_j) < j) ++log_j;
-            global2(k, log_j);
-        }
-        if (j >= LOOKUP_SORT_BLOCK) global(k, j);
-        block(k, k, LOOKUP_SORT_BLOCK / 2);
+// ---- merge passes ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t LOOKUP_MERGE_TILE = 1024;     // output records per CTA (36 KB of shared memory)
+constexpr uint32_t LOOKUP_MERGE_THREADS = 256;
+constexpr uint32_t LOOKUP_MERGE_VT = LOOKUP_MERGE_TILE / LOOKUP_MERGE_THREADS;
+struct LookupMergeArgs {
+    const uint4* ilo; const uint4* ihi; const uint32_t* irow;   // input: sorted runs of `run` records
+    uint4* olo; uint4* ohi; uint32_t* orow;                     // output: sorted runs of 2 * run
+    uint64_t run;
+    uint32_t log_p;
+    uint32_t* part;   // [P / LOOKUP_MERGE_TILE] records taken from the LEFT run before every tile boundary
+};
+ZKB_HD bool lookup_merge_in_less(const LookupMergeArgs& a, uint64_t x, uint64_t y) {
+    return lookup_rec_less(a.ilo[x], a.ihi[x], a.irow[x], a.ilo[y], a.ihi[y], a.irow[y]);
+}
+// merge path: of the first d records of merge(A, B), how many come from A (|A| = na, |B| = nb; A wins ties — there are none)
+template <class Less>
+ZKB_HD uint64_t lookup_merge_path(uint64_t d, uint64_t na, uint64_t nb, Less&& b_less_a) {
+    uint64_t lo = d > nb ? d - nb : 0, hi = d < na ? d : na;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (!b_less_a(d - 1 - mid, mid)) lo = mid + 1;   // A[mid] <= B[d - 1 - mid]: A[mid] is among the first d
+        else hi = mid;
+    }
+    return lo;
+}
+ZKB_HD void lookup_merge_partition_thread(const LookupMergeArgs& a, uint64_t c) {
+    const uint64_t P = (uint64_t)1 << a.log_p;
+    if (c >= P / LOOKUP_MERGE_TILE) return;
+    const uint64_t g = c * LOOKUP_MERGE_TILE, base = g & ~(2 * a.run - 1), d = g - base;
+    a.part[c] = (uint32_t)lookup_merge_path(d, a.run, a.run, [&](uint64_t y, uint64_t x) { return lookup_merge_in_less(a, base + a.run + y, base + x); });
+}
+// the two input pieces of tile c: A[a0, a0 + na) and B[b0, b0 + nb) of the pair of runs starting at `base`
+ZKB_HD void lookup_merge_tile_geometry(const LookupMergeArgs& a, uint64_t c, uint64_t* base, uint64_t* a0, uint64_t* b0, uint32_t* na, uint32_t* nb) {
+    const uint64_t g = c * LOOKUP_MERGE_TILE;
+    *base = g & ~(2 * a.run - 1);
+    const uint64_t d = g - *base;
+    *a0 = a.part[c];
+    const uint64_t a1 = (d + LOOKUP_MERGE_TILE == 2 * a.run) ? a.run : a.part[c + 1];
+    *b0 = d - *a0;
+    *na = (uint32_t)(a1 - *a0);
+    *nb = LOOKUP_MERGE_TILE - *na;
+}
+ZKB_HD void lookup_merge_tile_load(const LookupMergeArgs& a, uint64_t c, uint32_t tid, uint4* slo, uint4* shi, uint32_t* srow) {
+    uint64_t base, a0, b0;
+    uint32_t na, nb;
+    lookup_merge_tile_geometry(a, c, &base, &a0, &b0, &na, &nb);
+    for (uint32_t r = tid; r < LOOKUP_MERGE_TILE; r += LOOKUP_MERGE_THREADS) {
+        const uint64_t src = r < na ? base + a0 + r : base + a.run + b0 + (r - na);
+        slo[r] = a.ilo[src]; shi[r] = a.ihi[src]; srow[r] = a.irow[src];
     }
 }
+ZKB_HD void lookup_merge_tile_merge(const LookupMergeArgs& a, uint64_t c, uint32_t tid, const uint4* slo, const uint4* shi, const uint32_t* srow) {
+    uint64_t base, a0, b0;
+    uint32_t na, nb;
+    lookup_merge_tile_geometry(a, c, &base, &a0, &b0, &na, &nb);
+    auto less = [&](uint32_t x, uint32_t y) { return lookup_rec_less(slo[x], shi[x], srow[x], slo[y], shi[y], srow[y]); };
+    const uint32_t d = tid * LOOKUP_MERGE_VT;
+    uint32_t ta = (uint32_t)lookup_merge_path(d, na, nb, [&](uint64_t y, uint64_t x) { return less(na + (uint32_t)y, (uint32_t)x); });
+    uint32_t tb = d - ta;
+    const uint64_t out = c * LOOKUP_MERGE_TILE + d;
+    for (uint32_t e = 0; e < LOOKUP_MERGE_VT; ++e) {
+        const bool take_a = tb >= nb || (ta < na && !less(na + tb, ta));
+        const uint32_t src = take_a ? ta++ : na + tb++;
+        a.olo[out + e] = slo[src]; a.ohi[out + e] = shi[src]; a.orow[out + e] = srow[src];
+    }
+}
+
 inline uint32_t lookup_sort_log_p(uint64_t u) {
     uint32_t lp = LOOKUP_SORT_LOG_BLOCK;   // at least one block
     while (((uint64_t)1 << lp) < u) ++lp;

@@ -88,26 +88,31 @@ __global__ void __launch_bounds__(128) graph_evaluate_kernel(const GraphArgs g, 
 
 __global__ void __launch_bounds__(128) lookup_canon_kernel(const LookupArgs a) { lookup_canon_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(128) lookup_sort_init_kernel(const LookupSortArgs a) { lookup_sort_init_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(128) lookup_sort_global_kernel(const LookupSortArgs a, uint64_t k, uint64_t j) {
-    lookup_sort_global_thread(a, k, j, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
-}
-__global__ void __launch_bounds__(128) lookup_sort_global2_kernel(const LookupSortArgs a, uint64_t k, uint32_t log_j) {
-    lookup_sort_global2_thread(a, k, log_j, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
-}
-// steps (k, j) for k = k_first .. k_last, j from (k == k_first && j_first ? j_first : k / 2) down to 1, on one block in shared memory
-__global__ void __launch_bounds__(LOOKUP_SORT_THREADS) lookup_sort_block_kernel(const LookupSortArgs a, uint64_t k_first, uint64_t k_last, uint32_t j_first) {
+// the bitonic network up to k = block size on one block in shared memory: every block ends sorted ascending
+__global__ void __launch_bounds__(LOOKUP_SORT_THREADS) lookup_sort_block_kernel(const LookupSortArgs a) {
     extern __shared__ uint4 lookup_sort_smem[];
     uint4* slo = lookup_sort_smem;
     uint4* shi = slo + LOOKUP_SORT_BLOCK;
     uint32_t* srow = reinterpret_cast<uint32_t*>(shi + LOOKUP_SORT_BLOCK);
     lookup_sort_block_load(a, blockIdx.x, threadIdx.x, slo, shi, srow);
-    for (uint64_t k = k_first; k <= k_last; k <<= 1)
-        for (uint32_t j = (k == k_first && j_first) ? j_first : (uint32_t)(k / 2); j >= 1; j >>= 1) {
+    for (uint32_t k = 2; k <= LOOKUP_SORT_BLOCK; k <<= 1)
+        for (uint32_t j = k / 2; j >= 1; j >>= 1) {
             __syncthreads();
-            lookup_sort_block_step(blockIdx.x, threadIdx.x, k, j, slo, shi, srow);
+            lookup_sort_block_step(threadIdx.x, k, j, slo, shi, srow);
         }
     __syncthreads();
     lookup_sort_block_store(a, blockIdx.x, threadIdx.x, slo, shi, srow);
+}
+__global__ void __launch_bounds__(128) lookup_merge_partition_kernel(const LookupMergeArgs a) {
+    lookup_merge_partition_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(LOOKUP_MERGE_THREADS) lookup_merge_tile_kernel(const LookupMergeArgs a) {
+    __shared__ uint4 slo[LOOKUP_MERGE_TILE];
+    __shared__ uint4 shi[LOOKUP_MERGE_TILE];
+    __shared__ uint32_t srow[LOOKUP_MERGE_TILE];
+    lookup_merge_tile_load(a, blockIdx.x, threadIdx.x, slo, shi, srow);
+    __syncthreads();
+    lookup_merge_tile_merge(a, blockIdx.x, threadIdx.x, slo, shi, srow);
 }
 __global__ void __launch_bounds__(128) lookup_take_rows_kernel(const uint32_t* row, uint32_t* idx, uint64_t u) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -733,19 +738,23 @@ int zkb_poly_prefix_product(uint64_t poly) {
 }
 
 // ---- lookup argument: permute_expression_pair on resident columns (lookup.cuh) -------------------------------------------------------
-// sorted order of `canon` (u canonical 256-bit values) into idx: the bitonic network of lookup.cuh over (value, row) records
+// sorted order of `canon` (u canonical 256-bit values) into idx: block-wise bitonic sort + merge-path merges (lookup.cuh)
 static int lookup_sort_dev(const uint4* canon, uint64_t u, uint32_t* idx, DevBuf& ws, cudaStream_t s) {
     LookupSortArgs a{};
     a.log_p = lookup_sort_log_p(u);
     const uint64_t P = (uint64_t)1 << a.log_p;
-    ZKB_TRY(ws.reserve(P * 36));
-    a.klo = ws.as<uint4>();
-    a.khi = a.klo + P;
-    a.row = reinterpret_cast<uint32_t*>(a.khi + P);
+    const uint64_t tiles = P / LOOKUP_MERGE_TILE;
+    ZKB_TRY(ws.reserve(2 * P * 36 + tiles * 4 + 64));
+    // two record buffers (klo | khi | row each) and the merge partition
+    char* b = ws.as<char>();
+    uint4* lo[2]; uint4* hi[2]; uint32_t* row[2];
+    for (int i = 0; i < 2; ++i) { lo[i] = reinterpret_cast<uint4*>(b); b += P * 16; hi[i] = reinterpret_cast<uint4*>(b); b += P * 16; }
+    for (int i = 0; i < 2; ++i) { row[i] = reinterpret_cast<uint32_t*>(b); b += P * 4; }
+    uint32_t* part = reinterpret_cast<uint32_t*>(b);
+    a.klo = lo[0]; a.khi = hi[0]; a.row = row[0];
     a.canon = canon;
     a.u = u;
     lookup_sort_init_kernel<<<nblk(P, 128), 128, 0, s>>>(a);
-    count_launch();
     constexpr size_t block_smem = (size_t)LOOKUP_SORT_BLOCK * 36;
     struct LookupSortAttr { bool set = false; };
     bool& attr = per_device<LookupSortAttr>().set;
@@ -753,15 +762,19 @@ static int lookup_sort_dev(const uint4* canon, uint64_t u, uint32_t* idx, DevBuf
         ZKB_CUDA_TRY(cudaFuncSetAttribute(lookup_sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem));
         attr = true;
     }
-    lookup_sort_schedule(
-        a.log_p,
-        [&](uint64_t k, uint64_t j) { lookup_sort_global_kernel<<<nblk(P / 2, 128), 128, 0, s>>>(a, k, j); count_launch(); },
-        [&](uint64_t k, uint32_t log_j) { lookup_sort_global2_kernel<<<nblk(P / 4, 128), 128, 0, s>>>(a, k, log_j); count_launch(); },
-        [&](uint64_t k_first, uint64_t k_last, uint32_t j_first) {
-            lookup_sort_block_kernel<<<(unsigned)(P / LOOKUP_SORT_BLOCK), LOOKUP_SORT_THREADS, block_smem, s>>>(a, k_first, k_last, j_first);
-            count_launch();
-        });
-    lookup_take_rows_kernel<<<nblk(u, 128), 128, 0, s>>>(a.row, idx, u);   // the padding sorted to the end
+    lookup_sort_block_kernel<<<(unsigned)(P / LOOKUP_SORT_BLOCK), LOOKUP_SORT_THREADS, block_smem, s>>>(a);
+    count_launch(2);
+    int cur = 0;
+    for (uint64_t run = LOOKUP_SORT_BLOCK; run < P; run <<= 1, cur ^= 1) {
+        LookupMergeArgs m{};
+        m.ilo = lo[cur]; m.ihi = hi[cur]; m.irow = row[cur];
+        m.olo = lo[cur ^ 1]; m.ohi = hi[cur ^ 1]; m.orow = row[cur ^ 1];
+        m.run = run; m.log_p = a.log_p; m.part = part;
+        lookup_merge_partition_kernel<<<nblk(tiles, 128), 128, 0, s>>>(m);
+        lookup_merge_tile_kernel<<<(unsigned)tiles, LOOKUP_MERGE_THREADS, 0, s>>>(m);
+        count_launch(2);
+    }
+    lookup_take_rows_kernel<<<nblk(u, 128), 128, 0, s>>>(row[cur], idx, u);   // the padding sorted to the end
     count_launch();
     ZKB_CUDA_TRY(cudaGetLastError());
     return ZKB_OK;
