@@ -53,9 +53,12 @@ ZKB_HD void lookup_canon_thread(const LookupArgs& a, uint64_t i) {
 //      once per pass (a bitonic network over global memory needs ~3 passes per doubling at 2^22 records: measured 9.1 ms for the
 //      whole permute_expression_pair against the merges' figure in DESIGN.md).
 // Written by hand instead of calling a library sort: no library kernel is left anywhere in this package.
-constexpr uint32_t LOOKUP_SORT_BLOCK = 4096;                 // records per bitonic block (144 KB of shared memory: one CTA per SM)
-constexpr uint32_t LOOKUP_SORT_LOG_BLOCK = 12;
-constexpr uint32_t LOOKUP_SORT_THREADS = 1024;               // two pairs per thread and step
+#ifndef ZKB_LOOKUP_SORT_LOG_BLOCK
+#define ZKB_LOOKUP_SORT_LOG_BLOCK 10
+#endif
+constexpr uint32_t LOOKUP_SORT_LOG_BLOCK = ZKB_LOOKUP_SORT_LOG_BLOCK;
+constexpr uint32_t LOOKUP_SORT_BLOCK = 1u << LOOKUP_SORT_LOG_BLOCK;   // records per bitonic block (36 bytes of shared memory each)
+constexpr uint32_t LOOKUP_SORT_THREADS = LOOKUP_SORT_BLOCK / 2 < 1024 ? LOOKUP_SORT_BLOCK / 2 : 1024;   // pairs per step / threads
 struct LookupSortArgs {
     uint4* klo;        // [P] low 128 bits of the value
     uint4* khi;        // [P] high 128 bits
