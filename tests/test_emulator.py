@@ -3,6 +3,8 @@
 This is how limb arithmetic, NTT index maths and MSM chunk/partial logic are checked where no GPU exists; the
 `-m gpu` tests repeat the comparisons on the real kernels through the C ABI.
 """
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -762,3 +764,12 @@ def test_bucket_sort_skewed_and_degenerate_keys():
 
 def test_bucket_sort_key_too_wide_is_refused():
     assert emu.bucket_sort(np.arange(10, dtype=np.uint32), np.arange(10, dtype=np.uint32), 25) is None
+
+
+def test_host_fold_64bit_arithmetic_matches_the_portable_chains():
+    """csrc/host_fq64.hpp (the product's per-commit host fold: Horner combination, sum of partials, normalisation — 4 x 64-bit limbs)
+    against the portable twins of the device code on random operands and the edge cases (0, 1, p - 1, identity / equal / opposite points)."""
+    fn = emu.lib().zkb_emu_host64_check
+    fn.restype = ctypes.c_uint64
+    assert fn(ctypes.c_uint64(1), ctypes.c_uint64(300)) == 0
+    assert fn(ctypes.c_uint64(0xDEADBEEF), ctypes.c_uint64(50)) == 0

@@ -213,3 +213,76 @@ EMU_EXPORT int zkb_emu_ntt_dist_phase(int phase, uint32_t rank, uint32_t log_g, 
 
 // ---- MSM -----------------------------------------------------------------------------------------------------
 #include "hostemu_msm.inc"
+
+// ---- host_fq64.hpp (the product's host fold in 64-bit arithmetic) against the portable twins of the device code ---------------------
+#include "host_fq64.hpp"
+// returns the number of mismatches over `n` random cases plus the edge cases (identity operands, equal points, opposite points, zero)
+EMU_EXPORT uint64_t zkb_emu_host64_check(uint64_t seed, uint64_t n) {
+    uint64_t bad = 0, st = seed * 0x9e3779b97f4a7c15ull + 1;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    auto rnd_fq = [&]() {
+        Fq v;
+        for (int i = 0; i < 8; ++i) v.l[i] = (uint32_t)rnd();
+        v.l[7] &= 0x0fffffffu;   // < 2^252 < p: a canonical residue
+        return v;
+    };
+    auto same = [&](const host64::F& a, const Fq& b) { return host64::equal(a, host64::from_fq(b)); };
+    auto same_point = [&](const host64::P& a, const XYZZ& b) {   // compare the normalised output encodings
+        uint64_t oa[12], ob[12];
+        host64::to_out(a, oa);
+        xyzz_to_jacobian_u64(b, ob);
+        return memcmp(oa, ob, 96) == 0;
+    };
+    for (uint64_t i = 0; i < n; ++i) {
+        const Fq a = rnd_fq(), b = rnd_fq();
+        const host64::F fa = host64::from_fq(a), fb = host64::from_fq(b);
+        if (!same(host64::mul(fa, fb), fp_mul(a, b))) ++bad;
+        if (!same(host64::add(fa, fb), fp_add(a, b))) ++bad;
+        if (!same(host64::sub(fa, fb), fp_sub(a, b))) ++bad;
+        XYZZ p, q;
+        p.x = rnd_fq(); p.y = rnd_fq(); p.zz = rnd_fq(); p.zzz = rnd_fq();
+        q.x = rnd_fq(); q.y = rnd_fq(); q.zz = rnd_fq(); q.zzz = rnd_fq();
+        XYZZ s = p;
+        xyzz_add(s, q);
+        if (!same_point(host64::added(host64::from_xyzz(p), host64::from_xyzz(q)), s)) ++bad;
+        if (!same_point(host64::doubled(host64::from_xyzz(p)), xyzz_double(p))) ++bad;
+        if (i < 8) {   // the expensive ones: inversion, Horner combination
+            if (!same(host64::inv(fa), fq_inv(a))) ++bad;
+            XYZZ sums[5] = {p, q, s, XYZZ::identity(), xyzz_double(q)};
+            if (!same_point(host64::combine_windows(sums, 5, 7), msm_combine_windows(sums, 5, 7))) ++bad;
+        }
+    }
+    // edge cases
+    const Fq zero = Fq::zero(), one = Fq::one();
+    Fq pm1;   // p - 1
+    for (int i = 0; i < 8; ++i) pm1.l[i] = FqParams::M(i);
+    pm1.l[0] -= 1;
+    const Fq edge[4] = {zero, one, pm1, fp_neg(one)};
+    for (const Fq& a : edge)
+        for (const Fq& b : edge) {
+            const host64::F fa = host64::from_fq(a), fb = host64::from_fq(b);
+            if (!same(host64::mul(fa, fb), fp_mul(a, b))) ++bad;
+            if (!same(host64::add(fa, fb), fp_add(a, b))) ++bad;
+            if (!same(host64::sub(fa, fb), fp_sub(a, b))) ++bad;
+        }
+    if (!host64::is_zero(host64::inv(host64::from_fq(zero)))) ++bad;
+    XYZZ g;   // the generator (1, 2) and friends
+    g.x = one; g.y = fp_dbl(one); g.zz = one; g.zzz = one;
+    XYZZ neg = g;
+    neg.y = fp_neg(g.y);
+    const XYZZ id = XYZZ::identity();
+    const XYZZ cases[4] = {g, neg, id, xyzz_double(g)};
+    for (const XYZZ& x : cases)
+        for (const XYZZ& y : cases) {
+            XYZZ s = x;
+            xyzz_add(s, y);
+            if (!same_point(host64::added(host64::from_xyzz(x), host64::from_xyzz(y)), s)) ++bad;
+        }
+    // Jacobian input of g1_sum: (x, y, z) with z = 1 and z = 0
+    uint64_t jac[12];
+    xyzz_to_jacobian_u64(g, jac);
+    if (!same_point(host64::from_jacobian(jac), g)) ++bad;
+    memset(jac + 8, 0, 32);
+    if (!host64::is_identity(host64::from_jacobian(jac))) ++bad;
+    return bad;
+}
