@@ -223,16 +223,28 @@ static Fr fr_inv_host(const Fr& a) {  // a^(r-2)
     }
     return acc;
 }
-static Fr fr_omega_host(uint32_t k) {
-    Fr w = fr_root_of_unity();
-    for (uint32_t i = k; i < 28; ++i) w = fp_sqr(w);
-    return w;
+// omega(k), omega(k)^-1 and (2^k)^-1 for k = 0 .. 28, built ONCE (two host inversions): lagrange_to_coeff / extended_to_coeff used to
+// run two 256-step Fermat inversions on the portable 32-bit chains per CALL — ~0.1–0.25 ms of host time in front of transforms
+// that take 20 us at the voter's k = 13
+struct DomainConsts {
+    Fr omega[29], omega_inv[29], pow2_inv[29];
+    DomainConsts() {
+        omega[28] = fr_root_of_unity();
+        for (int k = 27; k >= 0; --k) omega[k] = fp_sqr(omega[k + 1]);
+        omega_inv[28] = fr_inv_host(omega[28]);
+        for (int k = 27; k >= 0; --k) omega_inv[k] = fp_sqr(omega_inv[k + 1]);
+        const Fr inv2 = fr_inv_host(fp_dbl(Fr::one()));
+        pow2_inv[0] = Fr::one();
+        for (int k = 1; k <= 28; ++k) pow2_inv[k] = fp_mul(pow2_inv[k - 1], inv2);
+    }
+};
+static const DomainConsts& domain_consts() {
+    static const DomainConsts c;   // thread-safe one-time initialisation
+    return c;
 }
-static Fr fr_pow2_inv_host(uint32_t k) {  // (2^k)^-1
-    Fr two = fp_dbl(Fr::one()), v = Fr::one();
-    for (uint32_t i = 0; i < k; ++i) v = fp_mul(v, two);
-    return fr_inv_host(v);
-}
+static Fr fr_omega_host(uint32_t k) { return domain_consts().omega[k <= 28 ? k : 28]; }
+static Fr fr_omega_inv_host(uint32_t k) { return domain_consts().omega_inv[k <= 28 ? k : 28]; }
+static Fr fr_pow2_inv_host(uint32_t k) { return domain_consts().pow2_inv[k <= 28 ? k : 28]; }  // (2^k)^-1
 
 // ---- SRS registry ---------------------------------------------------------------------------------------------------------
 struct Srs {
@@ -409,7 +421,7 @@ static int domain_op_dev(DomainOp op, const uint4* d_in, uint4* d_a, uint4* d_b,
         case OP_FFT: memcpy(om, omega_user, 32); break;
         case OP_C2L: fr_to_limbs64(fr_omega_host(k), om); break;
         case OP_L2C: {
-            fr_to_limbs64(fr_inv_host(fr_omega_host(k)), om);
+            fr_to_limbs64(fr_omega_inv_host(k), om);
             scale[0] = scale[1] = scale[2] = fr_pow2_inv_host(k);
             out_scale = scale;
             break;
@@ -421,7 +433,7 @@ static int domain_op_dev(DomainOp op, const uint4* d_in, uint4* d_a, uint4* d_b,
             break;
         }
         case OP_E2C: {
-            fr_to_limbs64(fr_inv_host(fr_omega_host(ek)), om);
+            fr_to_limbs64(fr_omega_inv_host(ek), om);
             Fr ninv = fr_pow2_inv_host(ek), z = fr_zeta(), z2 = fp_sqr(z);
             scale[0] = ninv; scale[1] = fp_mul(ninv, z2); scale[2] = fp_mul(ninv, z);
             out_scale = scale;
@@ -849,12 +861,12 @@ static int domain_op_host(DomainOp op, const uint64_t* const* in, uint64_t* cons
             case OP_FFT: ZKB_TRY(check_ptr(omega_user, "omega")); memcpy(om, omega_user, 32); break;
             case OP_C2L: fr_to_limbs64(fr_omega_host(k), om); break;
             case OP_L2C:
-                fr_to_limbs64(fr_inv_host(fr_omega_host(k)), om);
+                fr_to_limbs64(fr_omega_inv_host(k), om);
                 scale[0] = scale[1] = scale[2] = fr_pow2_inv_host(k);
                 out_scale = scale;
                 break;
             default: {  // OP_E2C
-                fr_to_limbs64(fr_inv_host(fr_omega_host(ek)), om);
+                fr_to_limbs64(fr_omega_inv_host(ek), om);
                 Fr ninv = fr_pow2_inv_host(ek), z = fr_zeta(), z2 = fp_sqr(z);
                 scale[0] = ninv; scale[1] = fp_mul(ninv, z2); scale[2] = fp_mul(ninv, z);
                 out_scale = scale;
@@ -1567,7 +1579,7 @@ int zkb_srs_g_to_lagrange(uint64_t handle_g, uint32_t k, uint64_t* handle_g_lagr
     Srs* gl = new Srs();
     gl->n = n;
     int rc = gl->bases.reserve(n * 64);
-    const Fr omega_inv = fr_inv_host(fr_omega_host(k)), n_inv = fr_pow2_inv_host(k);
+    const Fr omega_inv = fr_omega_inv_host(k), n_inv = fr_pow2_inv_host(k);
     if (rc == ZKB_OK) rc = g1_fft_dev(g->bases.as<uint4>(), gl->bases.as<uint4>(), k, omega_inv, &n_inv, ctx().stream);
     if (rc == ZKB_OK && cudaStreamSynchronize(ctx().stream) != cudaSuccess) { set_error("g_to_lagrange failed"); rc = ZKB_ERR_CUDA; }
     if (rc != ZKB_OK) { cudaGetLastError(); gl->bases.release(); delete gl; return rc; }
