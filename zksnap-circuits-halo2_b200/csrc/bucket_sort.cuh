@@ -7,18 +7,18 @@
 //   level 1  digit = the top b1 bits of the key.  The entry array is cut into tiles; a CTA counts its tile's digits in a
 //            shared-memory histogram (`count`), one CTA turns the global histogram into segment offsets (`scan`), and each
 //            CTA then reserves, per digit, ONE run in that digit's segment with a single global atomicAdd and moves its
-//            entries there (`scatter`): ranks inside a (tile, digit) run come from shared-memory atomics, the tile is
+//            entries there (`scatter`): positions inside a (tile, digit) run come from shared-memory atomics, the tile is
 //            reordered in shared memory first so that consecutive lanes write consecutive addresses.
-//   level 2  the same three kernels on the remaining b2 = key_bits - b1 bits, with the tiles confined to one level-1 segment
-//            each (tile -> segment by binary search in the scanned tile counts); a segment's sub-bins are laid out in order
-//            inside the segment, so after level 2 the array is sorted by the whole key.
+//   level 2  the same kernels on the remaining b2 = key_bits - b1 bits, with the tiles confined to one level-1 segment each
+//            (`tiles`: tile -> segment by binary search in the scanned tile counts, one thread per tile); a segment's sub-bins
+//            are laid out in order inside the segment, so after level 2 the array is sorted by the whole key.
 //
 // Keys of up to 12 bits take one level, up to 24 bits two: every commit of this library (with the window table 2^(c-1) <= 2^21 buckets
 // per column; without it c is capped so that W x 2^(c-1) <= 2^24; batches are cut into groups that fit).  Any digit distribution is
 // handled by construction: tiles are equal-sized pieces of the INPUT, a heavy bucket is just a long run that many tiles
 // append to (witness columns put most entries into a few buckets; the all-equal column puts everything into W of them).
 // Two passes over the pairs instead of the three of an 8-bit least-significant-digit sort, no ranking by warp-wide matching, and
-// the entry count is read on the device (`BsortArgs::count`), never by the launches' geometry.
+// the entry count is read on the device (`bsort_init_thread`): the launches' geometry only needs an upper bound.
 //
 // Every kernel is a sequence of per-thread phase functions with a barrier in between, so the CPU emulator (hostemu.cu) runs
 // exactly this code.
@@ -38,7 +38,6 @@ namespace zkb {
 constexpr uint32_t BSORT_THREADS = ZKB_BSORT_THREADS;
 constexpr uint32_t BSORT_ITEMS = ZKB_BSORT_ITEMS;                  // entries a scatter thread holds in registers
 constexpr uint32_t BSORT_MAX_TILE = BSORT_THREADS * BSORT_ITEMS;   // entries per tile (8192)
-static_assert(BSORT_MAX_TILE <= 65536, "ranks inside a tile are kept in 16 bits");
 constexpr uint32_t BSORT_MAX_BITS = 12;                            // digit width per level (<= 11: 2 bins per thread, 12: 4)
 constexpr uint32_t BSORT_GROUP = 16;                               // per-thread partial sums scanned serially by one thread
 constexpr uint32_t BSORT_GROUPS = BSORT_THREADS / BSORT_GROUP;     // 64
