@@ -66,7 +66,9 @@ __device__ __noinline__ void msm_acc_tree(const MsmAccArgs& a, uint32_t* skey, u
 }
 
 template <bool LEVEL0>
-__global__ void __launch_bounds__(MSM_ACC_CTA, 4) msm_accumulate_kernel(const MsmAccArgs a) {
+__global__ void __launch_bounds__(MSM_ACC_CTA, 4) msm_accumulate_kernel(const MsmAccArgs a0) {
+    MsmAccArgs a = a0;
+    if (LEVEL0 && a0.count_dev) a.count = *a0.count_dev;   // small commits: the digits kernel's count never visits the host
     __shared__ uint32_t skey[2 * MSM_ACC_CTA];
     __shared__ uint4 sval[2 * MSM_ACC_CTA * 8];
     __shared__ uint4 scr[COOP_GROUPS * COOP_SCRATCH_FQ * 2];
@@ -75,7 +77,9 @@ __global__ void __launch_bounds__(MSM_ACC_CTA, 4) msm_accumulate_kernel(const Ms
 }
 
 template <bool LEVEL0>
-__global__ void __launch_bounds__(MSM_ACC_CTA) msm_accumulate_direct_kernel(const MsmAccArgs a) {
+__global__ void __launch_bounds__(MSM_ACC_CTA) msm_accumulate_direct_kernel(const MsmAccArgs a0) {
+    MsmAccArgs a = a0;
+    if (LEVEL0 && a0.count_dev) a.count = *a0.count_dev;
     const uint64_t t = (uint64_t)blockIdx.x * MSM_ACC_CTA + threadIdx.x;
     if (t * a.chunk < a.count) msm_acc_thread_direct<LEVEL0>(a, t);
     else { a.pkeys_out[2 * t] = MSM_INVALID_KEY; a.pkeys_out[2 * t + 1] = MSM_INVALID_KEY; }
@@ -464,11 +468,15 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         count_launch();
         ZKB_CUDA_TRY(cudaGetLastError());
     }
-    // the number of non-zero digits decides the size of everything downstream (a witness column has few)
-    uint64_t valid = 0;
-    {
-        unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(w.h_cnt) + set;
-        ZKB_CUDA_TRY(cudaMemcpyAsync(h_cnt, w.counter[set].p, 8, cudaMemcpyDeviceToHost, sp));
+    // The number of non-zero digits decides the size of everything downstream (a witness column has few).  Large commits read it
+    // back: the sort's and the accumulation's launch plans are fitted to it (whole waves of equal chunks; a witness-like 2^24 column
+    // has 29 M entries of 201 M possible).  Small commits (latency regime, <= 2^21 possible entries) never wait for it: every launch is
+    // sized for the upper bound W n, the kernels read the count on the device, and it comes back with the result.
+    const bool count_on_device = phase == MSM_WHOLE && total <= (1ull << 21);
+    unsigned long long* const h_cnt = reinterpret_cast<unsigned long long*>(w.h_cnt) + set;
+    ZKB_CUDA_TRY(cudaMemcpyAsync(h_cnt, w.counter[set].p, 8, cudaMemcpyDeviceToHost, sp));
+    uint64_t valid = total;
+    if (!count_on_device) {
         ZKB_CUDA_TRY(cudaStreamSynchronize(sp));   // overlap: waits for this slice's digits only, not for the accumulation on `s`
         valid = *h_cnt;
         w.last_entries = (phase & MSM_FIRST) ? valid : w.last_entries + valid;
@@ -522,6 +530,7 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
             a.bases = table ? table->rows : d_bases;
             a.pin = w.pv[pp ^ 1].as<uint4>();
             a.count = count;
+            a.count_dev = (level == 0 && count_on_device) ? reinterpret_cast<const unsigned long long*>(w.counter[set].p) : nullptr;
             a.chunk = plan.chunk[level];
             a.invalid_key = g.invalid_key;
             a.last_level = level + 1 == plan.levels ? 1 : 0;
@@ -588,11 +597,13 @@ int msm_run(const uint4* d_scalars, const uint4* d_bases, uint64_t n, cudaStream
         ZKB_CUDA_TRY(cudaGetLastError());
         ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, f.out, (size_t)ncols * 96, cudaMemcpyDeviceToHost, s));
         ZKB_CUDA_TRY(cudaStreamSynchronize(s));
+        if (count_on_device) w.last_entries = *h_cnt;
         memcpy(out_jac, w.h_sums, (size_t)ncols * 96);
         return ZKB_OK;
     }
     ZKB_CUDA_TRY(cudaMemcpyAsync(w.h_sums, sums, (size_t)g.total_sets * 128, cudaMemcpyDeviceToHost, s));
     ZKB_CUDA_TRY(cudaStreamSynchronize(s));
+    if (count_on_device) w.last_entries = *h_cnt;
     for (uint32_t col = 0; col < ncols; ++col) {
         XYZZ hs[MSM_MAX_WINDOWS];  // c >= 2 gives at most 128 window sums per column
         for (uint32_t i = 0; i < g.bucket_sets; ++i)

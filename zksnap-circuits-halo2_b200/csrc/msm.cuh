@@ -101,7 +101,8 @@ struct MsmAccArgs {
     const uint32_t* vals;   // level 0: point index | sign<<31
     const uint4* bases;     // level 0: affine points (64 B each)
     const uint4* pin;       // level >= 1: partial XYZZ values (128 B each)
-    uint64_t count;         // entries at this level
+    uint64_t count;         // entries at this level (level 0 with count_dev: an upper bound, the launches' geometry)
+    const unsigned long long* count_dev;   // level 0, latency regime: the entry count is read on the device (no host round trip)
     uint32_t chunk;         // S
     uint32_t invalid_key;
     uint32_t last_level;    // single CTA: its head/tail are complete and go to the bucket array
