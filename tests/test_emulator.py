@@ -773,3 +773,25 @@ def test_host_fold_64bit_arithmetic_matches_the_portable_chains():
     fn.restype = ctypes.c_uint64
     assert fn(ctypes.c_uint64(1), ctypes.c_uint64(300)) == 0
     assert fn(ctypes.c_uint64(0xDEADBEEF), ctypes.c_uint64(50)) == 0
+
+
+def test_bucket_sort_random_geometries():
+    """Random sizes, key widths, tile sizes and key distributions (hypothesis): sorted keys, every payload still next to its key."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(1, 30000), key_bits=st.integers(1, 24), tile_k=st.integers(0, 8), skew=st.integers(0, 3), seed=st.integers(0, 2**31))
+    def run(n, key_bits, tile_k, skew, seed):
+        rng = np.random.default_rng(seed)
+        hi = 1 << key_bits
+        if skew == 0:
+            keys = rng.integers(0, hi, size=n)
+        elif skew == 1:     # a few heavy buckets
+            keys = np.where(rng.random(n) < 0.9, rng.integers(0, min(hi, 4), size=n), rng.integers(0, hi, size=n))
+        elif skew == 2:     # one bucket
+            keys = np.full(n, int(rng.integers(0, hi)))
+        else:               # only the top of the range
+            keys = hi - 1 - rng.integers(0, min(hi, 7), size=n)
+        _check_bucket_sort(keys.astype(np.uint32), key_bits, 1024 * tile_k)
+
+    run()
