@@ -708,8 +708,9 @@ def test_graph_row_windows_random_programs(oracle, seed):
 
 @pytest.mark.parametrize("u,distinct,big", [(1, 1, False), (9, 4, False), (300, 300, True), (1500, 33, True), (4000, 256, False), (9000, 700, True), (40000, 5000, False)])
 def test_permute_expression_pair_device_phases_vs_oracle(oracle, u, distinct, big):
-    """lookup.cuh's per-thread phases (canonical copies, four limb-wise stable sorts, first-occurrence flags, table matching by
-    binary search, rank scans, leftover assignment) against the oracle's restatement of upstream's algorithm."""
+    """lookup.cuh's per-thread phases (canonical copies, the block-wise bitonic + merge-path sort of (value, row) records,
+    first-occurrence flags, table matching by binary search, rank scans, leftover assignment) against the oracle's restatement of
+    upstream's algorithm.  Sizes above 1024 rows exercise the merge passes (9000 rows: four of them)."""
     from test_oracle import lookup_case
     inp, tab = lookup_case(7 * u + distinct, u, distinct, big)
     a = ints_to_limbs([R.to_mont(x, R.FR) for x in inp])
@@ -717,6 +718,26 @@ def test_permute_expression_pair_device_phases_vs_oracle(oracle, u, distinct, bi
     want = oracle.permute_expression_pair(a, t, u)
     got = emu.permute_expression_pair(a, t, u)
     assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_permute_expression_pair_random_shapes(oracle):
+    """Random row counts (around the 1024-record block and tile boundaries too), numbers of distinct values and value widths."""
+    from hypothesis import given, settings, strategies as st
+    from test_oracle import lookup_case
+
+    @settings(max_examples=25, deadline=None)
+    @given(u=st.one_of(st.integers(1, 5000), st.sampled_from([1023, 1024, 1025, 2047, 2048, 2049, 4096, 4097])), frac=st.floats(0.001, 1.0),
+           big=st.booleans(), seed=st.integers(0, 10**6))
+    def run(u, frac, big, seed):
+        distinct = max(1, min(u, int(u * frac)))
+        inp, tab = lookup_case(seed, u, distinct, big)
+        a = ints_to_limbs([R.to_mont(x, R.FR) for x in inp])
+        t = ints_to_limbs([R.to_mont(x, R.FR) for x in tab])
+        want = oracle.permute_expression_pair(a, t, u)
+        got = emu.permute_expression_pair(a, t, u)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+    run()
 
 
 def test_permute_expression_pair_missing_value_emulated(oracle):
